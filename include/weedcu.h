@@ -1,0 +1,253 @@
+/*
+ * weedcu.h — C-ABI of the B200 (sm_100a) compute layer for Weed's GPU device.
+ *
+ * This is the drop-in boundary: the entry points a `WEED_ENABLE_CUDA` build of Weed
+ * binds where the reference's OpenCL build calls `GpuDevice::RequestKernel(OCLAPI, ...)`
+ * (reference: include/devices/gpu_device.hpp:30-287, include/common/oclapi.hpp:18-121).
+ * Plain pointers and sizes only; no C++ or torch types cross this line. Every function
+ * returns 0 on success, a positive cudaError_t / ncclResult_t (+1000) value on a driver
+ * failure, or a negative WEEDCU_E* code on bad arguments. Nothing here throws and nothing
+ * here falls back to the host: if the device path cannot run, the call fails.
+ *
+ * Data model (reference: include/tensors/base_tensor.hpp:25-142):
+ *   a tensor is a VIEW (offset, shape[], stride[]) over a flat device buffer of `real`
+ *   (= float, WEED_FPPOW=5, include/common/weed_types.hpp:91-95). Layout is column-major:
+ *   flat element index i resolves as  offset + sum_d ((i / prod(shape[<d])) % shape[d]) * stride[d]
+ *   (BaseTensor::get_storage_index, base_tensor.hpp:123-142). stride 0 = broadcast.
+ *   Shapes/strides are `tcapint` = uint32 (WEED_TCAPPOW=5, weed_types.hpp:54-57); byte
+ *   offsets are formed in 64-bit on the device.
+ *
+ * All launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL selects
+ * the library's own compute stream, weedcu_default_stream()).
+ */
+#ifndef WEEDCU_H
+#define WEEDCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WEEDCU_MAX_RANK 8
+
+#define WEEDCU_OK 0
+#define WEEDCU_EINVAL (-1)   /* bad argument (rank, null pointer, shape mismatch) */
+#define WEEDCU_ENOSUP (-2)   /* valid request this build cannot serve (e.g. TMA alignment) */
+#define WEEDCU_ENCCL  (-3)   /* NCCL library not loaded */
+
+typedef struct weedcu_view {
+  uint64_t offset;                   /* BaseTensor::offset */
+  int32_t rank;                      /* shape.size() */
+  uint32_t shape[WEEDCU_MAX_RANK];   /* BaseTensor::shape  */
+  uint32_t stride[WEEDCU_MAX_RANK];  /* BaseTensor::stride */
+} weedcu_view;
+
+/* ------------------------------------------------------------------ runtime / memory
+ * Replaces OCLEngine device discovery (include/common/oclengine.hpp:249-395) and
+ * GpuDevice::MakeBuffer / LockSync / clFinish (src/devices/gpu_device.cpp:34-76,388-447). */
+int weedcu_device_count(int *count);
+int weedcu_set_device(int device);
+int weedcu_get_device(int *device);
+int weedcu_device_info(int device, char *name, int name_len, uint64_t *total_mem, int *sm_count,
+                       int *cc_major, int *cc_minor);
+const char *weedcu_error_string(int code);
+void *weedcu_default_stream(void);          /* per-device compute stream, created on demand */
+int weedcu_set_default_stream(void *stream);/* adopt an external stream (e.g. torch's) */
+int weedcu_stream_create(void **stream);
+int weedcu_stream_destroy(void *stream);
+int weedcu_stream_sync(void *stream);       /* GpuDevice::clFinish */
+int weedcu_stream_wait_event(void *stream, void *event);
+int weedcu_event_create(void **event);
+int weedcu_event_destroy(void *event);
+int weedcu_event_record(void *event, void *stream);
+int weedcu_event_sync(void *event);
+int weedcu_event_elapsed_ms(void *start, void *stop, float *ms);
+/* Stream-ordered pool allocation (cudaMallocAsync with an unbounded release threshold):
+ * freeing while kernels are in flight is safe, like QueueItem holding BufferPtrs
+ * (include/devices/queue_item.hpp:27-47). */
+int weedcu_malloc(void **ptr, size_t bytes, void *stream);
+int weedcu_free(void *ptr, void *stream);
+int weedcu_mem_info(uint64_t *free_bytes, uint64_t *total_bytes);
+int weedcu_host_alloc(void **ptr, size_t bytes); /* pinned staging memory */
+int weedcu_host_free(void *ptr);
+int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int weedcu_launch_count(uint64_t *count);   /* kernels launched by this library so far */
+
+/* ------------------------------------------------------------------ F1 fills
+ * GpuDevice::ClearRealBuffer / FillOnesReal / FillValueReal (src/devices/gpu_device.cpp:314-386);
+ * kernels clear_buffer_real / fill_ones_real / fill_value_real (src/common/qengine.cl:99-134). */
+int weedcu_fill_real(float *p, uint64_t n, float value, void *stream);
+int weedcu_fill_int(int32_t *p, uint64_t n, int32_t value, void *stream);
+
+/* ------------------------------------------------------------------ E1-E3 elementwise
+ * Weed::add / mul (src/ops/commuting.cpp:53-58,87-92,187-192), sub (src/ops/sub.cpp:48-53),
+ * div (src/ops/div.cpp:48-53): out[i] = a[i] (op) b[i] over the flat col-major index of the
+ * common broadcast shape; every operand resolves i through its own view. The reference's
+ * OpenCL launch only forwards stride[0] (SURVEY §2.3 defect 1); this entry is N-D correct
+ * like the CPU path. All three views must have equal rank and shape. */
+enum { WEEDCU_ADD = 0, WEEDCU_MUL = 1, WEEDCU_SUB = 2, WEEDCU_DIV = 3 };
+int weedcu_binary_real(int op, const float *a, const weedcu_view *av, const float *b,
+                       const weedcu_view *bv, float *out, const weedcu_view *ov, void *stream);
+/* Weed::add_in_place / sub_in_place (src/ops/in_place.cpp:49-54,79-84): a[i] (+/-)= b[i],
+ * i over a's broadcast size. */
+int weedcu_inplace_real(int op, float *a, const weedcu_view *av, const float *b,
+                        const weedcu_view *bv, void *stream);
+/* Weed::copy_broadcast (src/ops/copy_broadcast.cpp:44-49): dst[i] = src[i]. */
+int weedcu_copy_real(float *dst, const weedcu_view *dv, const float *src, const weedcu_view *sv,
+                     void *stream);
+
+/* ------------------------------------------------------------------ U1-U3 unary + grads
+ * relu/sigmoid/tanh (src/ops/real_unary.cpp:77-83,132-138,188-194), abs (src/ops/abs.cpp:88-94),
+ * pow/exp/log (src/ops/pow.cpp:52-77; `param` = p, log(b), 1/log(b) respectively),
+ * gelu = fused Tensor::gelu (src/tensors/tensor.cpp:841-851, tanh approximation). */
+enum {
+  WEEDCU_RELU = 0, WEEDCU_SIGMOID = 1, WEEDCU_TANH = 2, WEEDCU_ABS = 3, WEEDCU_POW = 4,
+  WEEDCU_EXP = 5, WEEDCU_LOG = 6, WEEDCU_GELU = 7, WEEDCU_SIN = 8, WEEDCU_COS = 9
+};
+int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av, float *out,
+                      const weedcu_view *ov, void *stream);
+/* din[i] += f'(.) * dout[i]. `in` is the forward INPUT for relu/abs/gelu/sin/cos and the forward
+ * OUTPUT for sigmoid/tanh (src/ops/real_unary.cpp:47-76; src/tensors/tensor.cpp:867-935). */
+int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in,
+                           const weedcu_view *inv, const float *dout, const weedcu_view *doutv,
+                           void *stream);
+
+/* ------------------------------------------------------------------ R1-R2 reductions
+ * Weed::reduce (src/ops/reduce.cpp:17-38,60-66): out[o] = sum_j a[base(o) + j*stride[axis]];
+ * `a` must be contiguous (Tensor::sum makes it so, src/tensors/tensor.cpp:626), out is a dense
+ * buffer of prod(shape)/shape[axis] elements.
+ * index_order 0: o enumerates the non-axis coordinates column-major, i.e. the layout the
+ *   output tensor built by Tensor::sum (tensor.cpp:629-645) is read with (intended semantics).
+ * index_order 1: reproduces the reference CPU loop bit-for-bit: o is decomposed LAST dimension
+ *   fastest (REDUCE_HEAD, reduce.cpp:17-31), which permutes the output whenever two or more
+ *   non-axis dims exceed 1 (see DESIGN.md "Reference defects"). */
+int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *out,
+                       int index_order, void *stream);
+/* Weed::reduce_grad (src/ops/reduce.cpp:84-113): din[i] += dout[o(i)], dout broadcast along axis.
+ * index_order as above (REDUCE_GRAD_HEAD, reduce.cpp:84-99). */
+int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout,
+                            const weedcu_view *doutv, int axis, int index_order, void *stream);
+/* Weed::sum / mean (src/ops/sum.cpp:74-98): *out = scale * sum_i a[i]. Device-side (the
+ * reference copies the buffer to the host, sum.cpp:52-67). Deterministic two-pass tree. */
+int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *stream);
+
+/* ------------------------------------------------------------------ S1-S2 softmax family
+ * Weed::softmax / softmax_grad (src/ops/softmax.cpp:85-138), logsoftmax / logsoftmax_grad
+ * (src/ops/logsoftmax.cpp:87-149). Rows run along `axis`; all views share one shape.
+ * grad: din += out*(dout - sum(dout*out))   |   din += dout - exp(out)*sum(dout). */
+int weedcu_softmax_real(int log_mode, const float *a, const weedcu_view *av, int axis, float *out,
+                        const weedcu_view *ov, void *stream);
+int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, const float *out,
+                             const weedcu_view *ov, const float *dout, const weedcu_view *doutv,
+                             int axis, void *stream);
+/* Fused causal attention probabilities: out = softmax(scores*scale + triu_mask(mask_val), last
+ * axis) for scores[batch, Tq, Tk] with batch fastest (strides 1, batch, batch*Tq) — the
+ * div + triu_fill + add + softmax chain of MultiHeadAttention::forward
+ * (src/modules/multihead_attention.cpp:319-334) in one pass. key_offset = Tk - Tq for KV cache. */
+int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq,
+                             uint32_t Tk, float inv_scale_divisor, float mask_val, int causal,
+                             void *stream);
+/* Fused cross-entropy over logits[rows, V] (row stride rs, vocab stride vs):
+ * cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34) = -mean_rows lsm[row, target].
+ * fwd writes per-row log-sum-exp (lse[rows]) and the scalar loss; bwd does
+ * dlogits += (softmax - onehot) * (dloss / rows). Targets are int32, gathered exactly. */
+int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
+                             uint32_t rs, uint32_t vs, const int32_t *targets, float *lse,
+                             float *loss, void *stream);
+int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
+                             uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse,
+                             const float *dloss, float *dlogits, uint64_t d_offset, void *stream);
+
+/* ------------------------------------------------------------------ L1 LayerNorm (fused)
+ * LayerNorm::forward (src/modules/layernorm.cpp:29-42): x[rows, F] with row stride 1 and
+ * feature stride `rows` (last axis is slowest in col-major). y = (x-mean)/sqrt(var+eps)*gamma+beta,
+ * biased variance. Saves mean[rows], rstd[rows] for the backward. */
+int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma,
+                         const float *beta, float eps, float *y, float *mean, float *rstd,
+                         void *stream);
+/* dx += ..., dgamma[F] += sum_rows dy*xhat, dbeta[F] += sum_rows dy. */
+int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
+                         const float *gamma, const float *mean, const float *rstd, float *dx,
+                         float *dgamma, float *dbeta, void *stream);
+
+/* ------------------------------------------------------------------ M1-M2 embedding, mask
+ * Weed::embedding_gather / embedding_scatter_add (src/ops/embedding.cpp:56-110):
+ * out[i + d*o_s1] = W[w_off + tok_i*w_s0 + d*w_s1]; dW[...] += dout[...] (atomic on duplicates).
+ * Indices are int32 `symint`, used exactly. */
+int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n,
+                            const float *W, uint64_t w_off, uint32_t w_s0, uint32_t w_s1,
+                            uint32_t D, float *out, uint64_t o_off, uint32_t o_s0, uint32_t o_s1,
+                            void *stream);
+int weedcu_embedding_scatter_add(float *dW, uint64_t w_off, uint32_t w_s0, uint32_t w_s1,
+                                 const int32_t *idx, uint64_t idx_off, uint32_t idx_stride,
+                                 uint32_t n, uint32_t D, const float *dout, uint64_t o_off,
+                                 uint32_t o_s0, uint32_t o_s1, void *stream);
+/* Weed::triu_fill (src/ops/triu_fill.cpp:41-59): a[i,j] = val where i + diagonal <= j. */
+int weedcu_triu_fill_real(float *a, const weedcu_view *av, float val, uint32_t diagonal,
+                          void *stream);
+/* argmax over the last axis of logits[rows,V] (greedy decode; the reference only has axis max,
+ * src/ops/reduce.cpp:40-49). Ties resolve to the lowest index. */
+int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs,
+                       uint32_t vs, int32_t *out, void *stream);
+
+/* ------------------------------------------------------------------ O1-O3 optimisers
+ * sgd_step (include/autograd/sgd.hpp:23-37): p -= lr * (gscale*g).
+ * adam_step (include/autograd/adam.hpp:70-106):
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr*m / (bc1*(sqrt(v/bc2)+eps)).
+ * gscale folds the 1/world_size of data-parallel gradient averaging into the read of g. */
+int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale, void *stream);
+int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr,
+                     float beta1, float beta2, float eps, float bc1, float bc2, float gscale,
+                     void *stream);
+
+/* ------------------------------------------------------------------ G1-G4 matmul
+ * Weed::matmul (src/ops/matmul.cpp:242-279; dims :95-122): C[M,N] (+)= A[M,K] * B[K,N], every
+ * operand an arbitrary (offset, s0, s1) view. `batch` > 1 runs independent products with
+ * per-operand batch strides (the host loop of Tensor::matmul, src/tensors/tensor.cpp:1259-1269).
+ * accumulate != 0 adds into C (fuses the tmp + add_in_place of make_matmul_node,
+ * tensor.cpp:1361-1400).
+ * precision: WEEDCU_GEMM_FP32  — FFMA, fp32 in / fp32 accumulate (FpMath parity path)
+ *            WEEDCU_GEMM_BF16  — operands rounded to bf16, tcgen05.mma kind::f16 with fp32
+ *                                accumulators in TMEM, operands staged by TMA
+ *            WEEDCU_GEMM_TF32X3 — 3xTF32 split on tcgen05 kind::tf32 (fp32-accurate to ~1e-6) */
+enum { WEEDCU_GEMM_FP32 = 0, WEEDCU_GEMM_BF16 = 1, WEEDCU_GEMM_TF32X3 = 2 };
+typedef struct weedcu_mat {
+  uint64_t offset;      /* element offset of [0,0] of batch 0 */
+  uint32_t s0, s1;      /* element strides of the row / column index */
+  uint64_t batch_stride;
+} weedcu_mat;
+int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm,
+                       float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
+                       uint32_t batch, int accumulate, int precision, void *stream);
+/* bf16 tensor-core GEMM on operands already held in bf16 (raw uint16 bit patterns).
+ * a_major / b_major: 0 = K contiguous, 1 = M (resp. N) contiguous; lda/ldb are the strides
+ * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc. */
+int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
+                     uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                     int accumulate, void *stream);
+/* strided fp32 -> packed bf16 (round-to-nearest-even); dst is a dense [rows, cols] matrix whose
+ * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
+int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
+                     uint32_t cols, uint16_t *dst, int dst_major, void *stream);
+int weedcu_gemm_workspace_bytes(uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
+                                int precision, uint64_t *bytes);
+
+/* ------------------------------------------------------------------ data-parallel collectives
+ * No reference counterpart (Weed has no gradient exchange). NCCL over NVLink,
+ * one process per GPU. The unique id is produced by rank 0 and shipped by the caller
+ * (bench.py uses torch.distributed for that plumbing). */
+int weedcu_nccl_load(const char *libnccl_path);
+int weedcu_nccl_unique_id(void *id128);      /* writes 128 bytes */
+int weedcu_nccl_init(const void *id128, int rank, int world, void **comm);
+int weedcu_nccl_destroy(void *comm);
+int weedcu_nccl_allreduce_sum(void *comm, float *buf, uint64_t n, void *stream);
+int weedcu_nccl_broadcast(void *comm, float *buf, uint64_t n, int root, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEEDCU_H */
