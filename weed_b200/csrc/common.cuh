@@ -1,0 +1,122 @@
+// common.cuh — shared device/host helpers for the weedcu kernels (sm_100a only).
+#pragma once
+#include "weedcu.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WCU_CHECK(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return (int)_e;                                                         \
+  } while (0)
+
+namespace weedcu {
+
+constexpr int kMaxRank = WEEDCU_MAX_RANK;
+constexpr int kNumSMs = 148; // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+cudaStream_t resolve_stream(void *s);
+void count_launch(int n = 1);
+int after_launch(); // cudaGetLastError -> return code, bumps the launch counter
+
+// ---------------------------------------------------------------------------------------------
+// Collapsed multi-operand index space. All operands share `shape`; each has its own strides.
+// Offsets are folded into the base pointers on the host.
+template <int NOPS> struct IndexSpace {
+  int rank;
+  uint32_t n; // total elements (tcapint is uint32 in the reference build)
+  uint32_t shape[kMaxRank];
+  uint32_t stride[NOPS][kMaxRank];
+};
+
+// Merge adjacent dims that are jointly contiguous for every operand and drop extent-1 dims.
+template <int NOPS>
+static inline bool build_index_space(const weedcu_view *const *views, IndexSpace<NOPS> &sp) {
+  const int rank = views[0]->rank;
+  if (rank <= 0 || rank > kMaxRank) return false;
+  for (int o = 1; o < NOPS; ++o) {
+    if (views[o]->rank != rank) return false;
+    for (int d = 0; d < rank; ++d)
+      if (views[o]->shape[d] != views[0]->shape[d]) return false;
+  }
+  uint64_t n = 1;
+  int r = 0;
+  for (int d = 0; d < rank; ++d) {
+    const uint32_t ext = views[0]->shape[d];
+    if (ext == 0) return false;
+    n *= ext;
+    if (ext == 1) continue;
+    bool merge = (r > 0);
+    if (merge) {
+      for (int o = 0; o < NOPS; ++o) {
+        const uint32_t st = views[o]->stride[d];
+        if ((uint64_t)sp.stride[o][r - 1] * sp.shape[r - 1] != st) { merge = false; break; }
+      }
+    }
+    if (merge) {
+      sp.shape[r - 1] *= ext;
+    } else {
+      sp.shape[r] = ext;
+      for (int o = 0; o < NOPS; ++o) sp.stride[o][r] = views[o]->stride[d];
+      ++r;
+    }
+  }
+  if (n > 0xffffffffull) return false;
+  if (r == 0) { // all extents 1
+    sp.shape[0] = 1;
+    for (int o = 0; o < NOPS; ++o) sp.stride[o][0] = 0;
+    r = 1;
+  }
+  for (int d = r; d < kMaxRank; ++d) {
+    sp.shape[d] = 1;
+    for (int o = 0; o < NOPS; ++o) sp.stride[o][d] = 0;
+  }
+  sp.rank = r;
+  sp.n = (uint32_t)n;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory. Result valid in every thread.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.0f;
+  t = warp_sum(t);
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+static inline unsigned grid_for(uint64_t work_items, unsigned block, unsigned max_waves = 16) {
+  uint64_t g = (work_items + block - 1) / block;
+  const uint64_t cap = (uint64_t)kNumSMs * max_waves;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (unsigned)g;
+}
+
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
+
+} // namespace weedcu

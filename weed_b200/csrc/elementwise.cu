@@ -1,0 +1,384 @@
+// elementwise.cu — fills, N-D broadcast binary/in-place/copy, unary + unary-grad, SGD/Adam.
+// HBM-bound: 128-bit vectorised, coalesced along the column-major fastest dim, grid sized in
+// multiples of the SM count. No shared memory (no reuse to stage).
+//
+// Reference semantics: every operand resolves the flat column-major index i through its own
+// (shape, stride) view — BaseTensor::get_storage_index (include/tensors/base_tensor.hpp:123-142)
+// as used by the CPU lambdas in src/ops/commuting.cpp:27-35, in_place.cpp:27-35,
+// copy_broadcast.cpp:27-30, real_unary.cpp:47-83, abs.cpp:70-94, pow.cpp:52-77.
+#include "common.cuh"
+
+namespace weedcu {
+
+template <int NIN> struct EwPtrs {
+  const float *in[NIN];
+  float *out;
+};
+
+// One thread = one element. Handles any rank <= 8 / any strides.
+template <int NIN, class F>
+__global__ void __launch_bounds__(256) ew_scalar_kernel(IndexSpace<NIN + 1> sp, EwPtrs<NIN> p, F f) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sp.n; i += stride) {
+    uint64_t off[NIN + 1];
+#pragma unroll
+    for (int o = 0; o <= NIN; ++o) off[o] = 0;
+    uint32_t rem = i;
+    for (int d = 0; d < sp.rank; ++d) {
+      const uint32_t ext = sp.shape[d];
+      const uint32_t c = rem % ext;
+      rem /= ext;
+#pragma unroll
+      for (int o = 0; o <= NIN; ++o) off[o] += (uint64_t)c * sp.stride[o][d];
+    }
+    float x[NIN];
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) x[o] = p.in[o][off[o]];
+    p.out[off[NIN]] = f(x);
+  }
+}
+
+// One thread = four consecutive elements of dim 0. Requires shape[0] % 4 == 0, every operand's
+// dim-0 stride in {0,1}, 16-byte aligned bases and (for stride-1 operands) higher strides % 4 == 0.
+template <int NIN, class F>
+__global__ void __launch_bounds__(256) ew_vec4_kernel(IndexSpace<NIN + 1> sp, EwPtrs<NIN> p, F f) {
+  const uint32_t nq = sp.n >> 2, s0q = sp.shape[0] >> 2;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    uint64_t off[NIN + 1];
+    uint32_t rem = q / s0q;
+    const uint32_t c0 = (q - rem * s0q) << 2;
+#pragma unroll
+    for (int o = 0; o <= NIN; ++o) off[o] = (uint64_t)c0 * sp.stride[o][0];
+    for (int d = 1; d < sp.rank; ++d) {
+      const uint32_t ext = sp.shape[d];
+      const uint32_t c = rem % ext;
+      rem /= ext;
+#pragma unroll
+      for (int o = 0; o <= NIN; ++o) off[o] += (uint64_t)c * sp.stride[o][d];
+    }
+    float4 v[NIN];
+#pragma unroll
+    for (int o = 0; o < NIN; ++o) {
+      if (sp.stride[o][0]) {
+        v[o] = *reinterpret_cast<const float4 *>(p.in[o] + off[o]);
+      } else {
+        const float s = p.in[o][off[o]];
+        v[o] = make_float4(s, s, s, s);
+      }
+    }
+    float4 r;
+    {
+      float x[NIN];
+#pragma unroll
+      for (int o = 0; o < NIN; ++o) x[o] = v[o].x;
+      r.x = f(x);
+#pragma unroll
+      for (int o = 0; o < NIN; ++o) x[o] = v[o].y;
+      r.y = f(x);
+#pragma unroll
+      for (int o = 0; o < NIN; ++o) x[o] = v[o].z;
+      r.z = f(x);
+#pragma unroll
+      for (int o = 0; o < NIN; ++o) x[o] = v[o].w;
+      r.w = f(x);
+    }
+    *reinterpret_cast<float4 *>(p.out + off[NIN]) = r;
+  }
+}
+
+template <int NIN, class F>
+static int launch_ew(const weedcu_view *const *views, const float *const *ins, float *out, F f,
+                     cudaStream_t st) {
+  IndexSpace<NIN + 1> sp;
+  if (!build_index_space<NIN + 1>(views, sp)) return WEEDCU_EINVAL;
+  EwPtrs<NIN> p;
+  for (int o = 0; o < NIN; ++o) {
+    if (!ins[o]) return WEEDCU_EINVAL;
+    p.in[o] = ins[o] + views[o]->offset;
+  }
+  if (!out) return WEEDCU_EINVAL;
+  p.out = out + views[NIN]->offset;
+  if (sp.stride[NIN][0] == 0 && sp.n > 1) return WEEDCU_EINVAL; // broadcast output is a race
+
+  bool vec = (sp.shape[0] % 4u) == 0;
+  for (int o = 0; o <= NIN && vec; ++o) {
+    const float *base = (o < NIN) ? p.in[o] : p.out;
+    const uint32_t s0 = sp.stride[o][0];
+    if (s0 > 1) vec = false;
+    if (s0 == 1) {
+      if (!aligned16(base)) vec = false;
+      for (int d = 1; d < sp.rank; ++d)
+        if (sp.stride[o][d] % 4u) vec = false;
+    }
+  }
+  if (sp.stride[NIN][0] != 1) vec = false;
+  if (vec) {
+    const unsigned grid = grid_for(sp.n >> 2, 256, 16);
+    ew_vec4_kernel<NIN, F><<<grid, 256, 0, st>>>(sp, p, f);
+  } else {
+    const unsigned grid = grid_for(sp.n, 256, 32);
+    ew_scalar_kernel<NIN, F><<<grid, 256, 0, st>>>(sp, p, f);
+  }
+  return after_launch();
+}
+
+// ------------------------------------------------------------------------------- functors
+struct AddF { __device__ float operator()(const float *x) const { return x[0] + x[1]; } };
+struct MulF { __device__ float operator()(const float *x) const { return x[0] * x[1]; } };
+struct SubF { __device__ float operator()(const float *x) const { return x[0] - x[1]; } };
+struct DivF { __device__ float operator()(const float *x) const { return x[0] / x[1]; } };
+struct CopyF { __device__ float operator()(const float *x) const { return x[0]; } };
+
+__device__ __forceinline__ float gelu_fwd(float x) {
+  // Tensor::gelu, reference src/tensors/tensor.cpp:841-851 (tanh approximation)
+  const float k1 = 0.044715f, k2 = 0.7978845608028654f;
+  const float x3 = (x * x) * x;
+  const float t = tanhf(k2 * (x + k1 * x3));
+  return (0.5f * x) * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_dfdx(float x) {
+  const float k1 = 0.044715f, k2 = 0.7978845608028654f;
+  const float t = tanhf(k2 * (x + k1 * ((x * x) * x)));
+  const float dinner = k2 * (1.0f + 3.0f * k1 * (x * x));
+  return 0.5f * (1.0f + t) + (0.5f * x) * ((1.0f - t * t) * dinner);
+}
+
+template <int OP> struct UnaryF {
+  float param;
+  __device__ float operator()(const float *x) const {
+    const float v = x[0];
+    if (OP == WEEDCU_RELU) return fmaxf(v, 0.0f);
+    if (OP == WEEDCU_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (OP == WEEDCU_TANH) return tanhf(v);
+    if (OP == WEEDCU_ABS) return (v < 0.0f) ? -v : v;
+    if (OP == WEEDCU_POW) return powf(v, param);
+    if (OP == WEEDCU_EXP) return expf(v * param);
+    if (OP == WEEDCU_LOG) return logf(v) * param;
+    if (OP == WEEDCU_GELU) return gelu_fwd(v);
+    if (OP == WEEDCU_SIN) return sinf(v);
+    if (OP == WEEDCU_COS) return cosf(v);
+    return v;
+  }
+};
+
+// x[0] = din (old), x[1] = in (forward input or output), x[2] = dout
+template <int OP> struct UnaryGradF {
+  __device__ float operator()(const float *x) const {
+    const float d = x[0], v = x[1], g = x[2];
+    if (OP == WEEDCU_RELU) return (v > 0.0f) ? d + g : d;
+    if (OP == WEEDCU_SIGMOID) return d + v * (1.0f - v) * g;
+    if (OP == WEEDCU_TANH) return d + g * (1.0f - v * v);
+    if (OP == WEEDCU_ABS) return (v != 0.0f) ? d + ((v > 0.0f) ? g : -g) : d;
+    if (OP == WEEDCU_GELU) return d + g * gelu_dfdx(v);
+    if (OP == WEEDCU_SIN) return d + cosf(v) * g;
+    if (OP == WEEDCU_COS) return d + (-sinf(v)) * g;
+    return d;
+  }
+};
+
+// ------------------------------------------------------------------------------- fills
+template <typename T> struct alignas(16) Quad { T x, y, z, w; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(T *p, uint64_t n, T v) {
+  // body in 128-bit stores; head/tail elements handled by the first warp of block 0
+  const uintptr_t addr = (uintptr_t)p;
+  uint64_t head = ((16 - (addr & 15)) & 15) / sizeof(T);
+  if (head > n) head = n;
+  const uint64_t nq = (n - head) >> 2;
+  Quad<T> *q = reinterpret_cast<Quad<T> *>(p + head);
+  const Quad<T> val = {v, v, v, v};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) q[i] = val;
+  if (blockIdx.x == 0 && threadIdx.x < 8) {
+    if (threadIdx.x < head) p[threadIdx.x] = v;
+    const uint64_t tail0 = head + (nq << 2);
+    if (threadIdx.x >= 4 && tail0 + (threadIdx.x - 4) < n) p[tail0 + (threadIdx.x - 4)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------- optimisers
+// sgd_step (reference include/autograd/sgd.hpp:23-37): p -= lr * g.  12 B/param.
+__global__ void __launch_bounds__(256)
+sgd_kernel(float *__restrict__ p, const float *__restrict__ g, uint64_t n, float lr, float gscale,
+           bool vec) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const uint64_t nq = n >> 2;
+    for (uint64_t i = tid; i < nq; i += stride) {
+      float4 pv = reinterpret_cast<float4 *>(p)[i];
+      const float4 gv = reinterpret_cast<const float4 *>(g)[i];
+      pv.x -= lr * (gscale * gv.x);
+      pv.y -= lr * (gscale * gv.y);
+      pv.z -= lr * (gscale * gv.z);
+      pv.w -= lr * (gscale * gv.w);
+      reinterpret_cast<float4 *>(p)[i] = pv;
+    }
+    for (uint64_t i = (nq << 2) + tid; i < n; i += stride) p[i] -= lr * (gscale * g[i]);
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) p[i] -= lr * (gscale * g[i]);
+  }
+}
+
+// adam_step (reference include/autograd/adam.hpp:70-106), one fused pass, 28 B/param:
+// m = b1*m + (1-b1)*g ; v = b2*v + ((1-b2)*g)*g ; p -= (lr*m) / (bc1*(sqrt(v/bc2)+eps)).
+struct AdamArgs {
+  float lr, beta1, beta2, eps, bc1, bc2, gscale, omb1, omb2;
+};
+__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamArgs &a) {
+  g = a.gscale * g;
+  m = a.beta1 * m + a.omb1 * g;
+  v = a.beta2 * v + (a.omb2 * g) * g;
+  p -= (a.lr * m) / (a.bc1 * (sqrtf(v / a.bc2) + a.eps));
+}
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+            float *__restrict__ v, uint64_t n, AdamArgs a, bool vec) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const uint64_t nq = n >> 2;
+    for (uint64_t i = tid; i < nq; i += stride) {
+      float4 pv = reinterpret_cast<float4 *>(p)[i];
+      const float4 gv = reinterpret_cast<const float4 *>(g)[i];
+      float4 mv = reinterpret_cast<float4 *>(m)[i];
+      float4 vv = reinterpret_cast<float4 *>(v)[i];
+      adam_one(pv.x, gv.x, mv.x, vv.x, a);
+      adam_one(pv.y, gv.y, mv.y, vv.y, a);
+      adam_one(pv.z, gv.z, mv.z, vv.z, a);
+      adam_one(pv.w, gv.w, mv.w, vv.w, a);
+      reinterpret_cast<float4 *>(p)[i] = pv;
+      reinterpret_cast<float4 *>(m)[i] = mv;
+      reinterpret_cast<float4 *>(v)[i] = vv;
+    }
+    for (uint64_t i = (nq << 2) + tid; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
+  }
+}
+
+} // namespace weedcu
+
+using namespace weedcu;
+
+extern "C" {
+
+int weedcu_fill_real(float *p, uint64_t n, float value, void *stream) {
+  if (!p) return WEEDCU_EINVAL;
+  if (!n) return 0;
+  fill_kernel<float><<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, n, value);
+  return after_launch();
+}
+int weedcu_fill_int(int32_t *p, uint64_t n, int32_t value, void *stream) {
+  if (!p) return WEEDCU_EINVAL;
+  if (!n) return 0;
+  fill_kernel<int32_t><<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, n, value);
+  return after_launch();
+}
+
+int weedcu_binary_real(int op, const float *a, const weedcu_view *av, const float *b,
+                       const weedcu_view *bv, float *out, const weedcu_view *ov, void *stream) {
+  if (!av || !bv || !ov) return WEEDCU_EINVAL;
+  const weedcu_view *views[3] = {av, bv, ov};
+  const float *ins[2] = {a, b};
+  cudaStream_t st = resolve_stream(stream);
+  switch (op) {
+  case WEEDCU_ADD: return launch_ew<2>(views, ins, out, AddF(), st);
+  case WEEDCU_MUL: return launch_ew<2>(views, ins, out, MulF(), st);
+  case WEEDCU_SUB: return launch_ew<2>(views, ins, out, SubF(), st);
+  case WEEDCU_DIV: return launch_ew<2>(views, ins, out, DivF(), st);
+  }
+  return WEEDCU_EINVAL;
+}
+
+int weedcu_inplace_real(int op, float *a, const weedcu_view *av, const float *b,
+                        const weedcu_view *bv, void *stream) {
+  if (!av || !bv) return WEEDCU_EINVAL;
+  const weedcu_view *views[3] = {av, bv, av};
+  const float *ins[2] = {a, b};
+  cudaStream_t st = resolve_stream(stream);
+  if (op == WEEDCU_ADD) return launch_ew<2>(views, ins, a, AddF(), st);
+  if (op == WEEDCU_SUB) return launch_ew<2>(views, ins, a, SubF(), st);
+  return WEEDCU_EINVAL;
+}
+
+int weedcu_copy_real(float *dst, const weedcu_view *dv, const float *src, const weedcu_view *sv,
+                     void *stream) {
+  if (!dv || !sv) return WEEDCU_EINVAL;
+  const weedcu_view *views[2] = {sv, dv};
+  const float *ins[1] = {src};
+  return launch_ew<1>(views, ins, dst, CopyF(), resolve_stream(stream));
+}
+
+#define WCU_UNARY_CASE(OP)                                                                         \
+  case OP: {                                                                                       \
+    UnaryF<OP> f;                                                                                  \
+    f.param = param;                                                                               \
+    return launch_ew<1>(views, ins, out, f, st);                                                   \
+  }
+int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av, float *out,
+                      const weedcu_view *ov, void *stream) {
+  if (!av || !ov) return WEEDCU_EINVAL;
+  const weedcu_view *views[2] = {av, ov};
+  const float *ins[1] = {a};
+  cudaStream_t st = resolve_stream(stream);
+  switch (op) {
+    WCU_UNARY_CASE(WEEDCU_RELU)
+    WCU_UNARY_CASE(WEEDCU_SIGMOID)
+    WCU_UNARY_CASE(WEEDCU_TANH)
+    WCU_UNARY_CASE(WEEDCU_ABS)
+    WCU_UNARY_CASE(WEEDCU_POW)
+    WCU_UNARY_CASE(WEEDCU_EXP)
+    WCU_UNARY_CASE(WEEDCU_LOG)
+    WCU_UNARY_CASE(WEEDCU_GELU)
+    WCU_UNARY_CASE(WEEDCU_SIN)
+    WCU_UNARY_CASE(WEEDCU_COS)
+  }
+  return WEEDCU_EINVAL;
+}
+
+#define WCU_GRAD_CASE(OP)                                                                          \
+  case OP: return launch_ew<3>(views, ins, din, UnaryGradF<OP>(), st);
+int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in,
+                           const weedcu_view *inv, const float *dout, const weedcu_view *doutv,
+                           void *stream) {
+  if (!dinv || !inv || !doutv) return WEEDCU_EINVAL;
+  const weedcu_view *views[4] = {dinv, inv, doutv, dinv};
+  const float *ins[3] = {din, in, dout};
+  cudaStream_t st = resolve_stream(stream);
+  switch (op) {
+    WCU_GRAD_CASE(WEEDCU_RELU)
+    WCU_GRAD_CASE(WEEDCU_SIGMOID)
+    WCU_GRAD_CASE(WEEDCU_TANH)
+    WCU_GRAD_CASE(WEEDCU_ABS)
+    WCU_GRAD_CASE(WEEDCU_GELU)
+    WCU_GRAD_CASE(WEEDCU_SIN)
+    WCU_GRAD_CASE(WEEDCU_COS)
+  }
+  return WEEDCU_EINVAL;
+}
+
+int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale, void *stream) {
+  if (!p || !g) return WEEDCU_EINVAL;
+  if (!n) return 0;
+  const bool vec = aligned16(p) && aligned16(g);
+  sgd_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, n, lr, gscale,
+                                                                               vec);
+  return after_launch();
+}
+
+int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr,
+                     float beta1, float beta2, float eps, float bc1, float bc2, float gscale,
+                     void *stream) {
+  if (!p || !g || !m || !v) return WEEDCU_EINVAL;
+  if (!n) return 0;
+  AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
+  const bool vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  adam_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, m, v, n, a,
+                                                                                vec);
+  return after_launch();
+}
+
+} // extern "C"

@@ -1,0 +1,499 @@
+// gemm_tc.cu — Blackwell tensor-core matmul: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the
+// accumulator in TMEM, operands staged by TMA into 128B-swizzled shared memory, mbarrier pipelines,
+// warp-specialised persistent CTAs (one per SM).
+//
+// Serves rows G1-G3 of SURVEY §8(a): Weed::matmul forward (A MN-major, B K-major), dA = dC*B^T
+// (A MN-major, B MN-major) and dB = A^T*dC (A K-major, B K-major) — reference
+// src/ops/matmul.cpp:242-279 and src/tensors/tensor.cpp:1361-1400. All three operand-majorness
+// cases run on the same kernel; majorness is a template parameter that selects the TMA box shape
+// and the UMMA shared-memory descriptor (no transposes are materialised). C is written directly in
+// Weed's column-major layout: TMEM lane == row m, so each warp-wide store of one column is a
+// coalesced 128-byte line; `accumulate` folds the reference's tmp + add_in_place into the epilogue.
+//
+// Pipelines:  TMA warp --full[s]--> MMA warp --empty[s]--> TMA warp      (STAGES smem slots)
+//             MMA warp --tmem_full[a]--> epilogue warps --tmem_empty[a]--> MMA warp (2 TMEM accs)
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace weedcu {
+namespace tc {
+
+constexpr uint32_t BLOCK_M = 128;
+constexpr uint32_t BLOCK_K = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr uint32_t UMMA_K = 16;    // fixed for 16-bit operands
+constexpr uint32_t NUM_THREADS = 256;
+constexpr uint32_t EPI_WARP0 = 4;  // warps 4..7 = epilogue (warpgroup-aligned: TMEM lane quarter = warp % 4)
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap(); // ~2 s: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; single-thread issue
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+
+struct Params {
+  float *c;
+  uint64_t ldc, c_bs;
+  uint32_t M, N, K, batch;
+  uint32_t tiles_m, tiles_n;
+  int accumulate;
+};
+
+template <uint32_t BLOCK_N, uint32_t STAGES> struct SmemLayout {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t BAR_OFF = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+};
+
+// A_MN / B_MN: operand is MN-major (1) or K-major (0).
+template <uint32_t BLOCK_N, uint32_t STAGES, int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  constexpr uint32_t NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 32)    ? 32
+                                 : (NUM_ACC * BLOCK_N <= 64)  ? 64
+                                 : (NUM_ACC * BLOCK_N <= 128) ? 128
+                                 : (NUM_ACC * BLOCK_N <= 256) ? 256
+                                                              : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-B aligned: round up to the 1024 B the swizzle needs
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * L::A_BYTES;
+  const uint32_t bars = base + L::BAR_OFF;
+  auto full_bar = [&](uint32_t s) { return bars + 8 * s; };
+  auto empty_bar = [&](uint32_t s) { return bars + 8 * (STAGES + s); };
+  auto tfull_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + a); };
+  auto tempty_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + 2 + a); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + (2 * STAGES + 4) * 8);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t tiles_per_batch = p.tiles_m * p.tiles_n;
+  const uint32_t num_tiles = tiles_per_batch * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32((const void *)tmem_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+        const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
+          const int k0 = (int)(kb * BLOCK_K);
+          const uint32_t a_dst = sA + stage * L::A_BYTES, b_dst = sB + stage * L::B_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (uint32_t i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_3d(a_dst + i * (64 * BLOCK_K * 2), &tmA, full_bar(stage), (int)(m0 + 64 * i), k0, (int)z);
+          } else {
+            tma_load_3d(a_dst, &tmA, full_bar(stage), k0, (int)m0, (int)z);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (uint32_t i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_3d(b_dst + i * (64 * BLOCK_K * 2), &tmB, full_bar(stage), (int)(n0 + 64 * i), k0, (int)z);
+          } else {
+            tma_load_3d(b_dst, &tmB, full_bar(stage), k0, (int)n0, (int)z);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1); // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase); // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t a_s = sA + stage * L::A_BYTES, b_s = sB + stage * L::B_BYTES;
+#pragma unroll
+          for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 16 k-elements = 32 B inside the 128-B swizzle row; SBO = 8 rows * 128 B.
+            // MN-major: 16 k-rows of 128 B = 2048 B; LBO = next 64-wide MN block (BLOCK_K rows).
+            const uint64_t adesc = A_MN ? make_smem_desc(a_s + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc(a_s + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_s + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc(b_s + k * (UMMA_K * 2), 16, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage)); // frees the smem slot once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================================ epilogue: TMEM -> registers -> global C ==========
+    const uint32_t q = warp & 3; // TMEM lanes [32q, 32q+32)
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+      const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
+      const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t m = m0 + q * 32 + lane;
+      float *crow = p.c + (uint64_t)z * p.c_bs + m;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+        tmem_ld_wait();
+        if (m < p.M) {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) {
+            const uint32_t n = n0 + c0 + j;
+            if (n < p.N) {
+              float *dst = crow + (uint64_t)n * p.ldc;
+              const float v = __uint_as_float(r[j]);
+              *dst = p.accumulate ? (*dst + v) : v;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// bf16 matrix [mn, k] per batch. major 0: k contiguous (ld = stride of mn index);
+// major 1: mn contiguous (ld = stride of k index). box_mn rows of the MN index per TMA box.
+static int make_operand_map(CUtensorMap *map, const uint16_t *ptr, int major, uint64_t mn, uint64_t k,
+                            uint64_t ld, uint64_t batch, uint64_t batch_stride, uint32_t box_mn) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return WEEDCU_ENOSUP;
+  if ((((uintptr_t)ptr) & 15u) || (ld % 8) || (batch > 1 && (batch_stride % 8))) return WEEDCU_ENOSUP;
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  if (major == 0) {
+    dims[0] = k; dims[1] = mn;
+    box[0] = BLOCK_K; box[1] = box_mn;
+  } else {
+    dims[0] = mn; dims[1] = k;
+    box[0] = 64; box[1] = BLOCK_K;
+  }
+  dims[2] = batch;
+  box[2] = 1;
+  strides[0] = ld * 2;
+  strides[1] = (batch > 1 ? batch_stride : (uint64_t)ld * dims[1]) * 2; // ld % 8 == 0 => 16-B multiple
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : WEEDCU_ENOSUP;
+}
+
+template <uint32_t BLOCK_N, uint32_t STAGES>
+static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, int a_major,
+                      int b_major, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
+  const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const unsigned grid = num_tiles < (uint32_t)kNumSMs ? num_tiles : (unsigned)kNumSMs;
+#define WCU_TC_LAUNCH(AM, BM_)                                                                     \
+  {                                                                                                \
+    auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);                                               \
+  }
+  if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
+  else if (a_major) WCU_TC_LAUNCH(1, 0)
+  else if (b_major) WCU_TC_LAUNCH(0, 1)
+  else WCU_TC_LAUNCH(0, 0)
+#undef WCU_TC_LAUNCH
+  return after_launch();
+}
+
+int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
+                     int b_major, uint64_t ldb, uint64_t b_bs, float *c, uint64_t ldc, uint64_t c_bs,
+                     uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st) {
+  if (!a || !b || !c || !M || !N || !K || !batch) return WEEDCU_EINVAL;
+  const bool wide = (N > 128);
+  const uint32_t block_n = wide ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, b, b_major, N, K, ldb, batch, b_bs, block_n);
+  if (rc) return rc;
+  Params p;
+  p.c = c;
+  p.ldc = ldc;
+  p.c_bs = c_bs;
+  p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_n = (N + block_n - 1) / block_n;
+  p.accumulate = accumulate;
+  if (wide) return launch_cfg<256, 4>(tmA, tmB, p, a_major, b_major, st);
+  return launch_cfg<128, 6>(tmA, tmB, p, a_major, b_major, st);
+}
+
+} // namespace tc
+
+// ------------------------------------------------------------------------------------ packing
+// fp32 strided [rows, cols] (+batch) -> dense bf16 with leading dimension ld.
+// dst_major 1: dst[r + c*ld] (rows contiguous); 0: dst[c + r*ld] (cols contiguous).
+// 32x32 tiles through shared memory so both the fp32 read and the bf16 write walk their own
+// contiguous index with adjacent lanes.
+__global__ void __launch_bounds__(256)
+pack_bf16_kernel(const float *__restrict__ src, uint64_t s_bs, uint32_t s0, uint32_t s1, uint32_t rows,
+                 uint32_t cols, __nv_bfloat16 *__restrict__ dst, uint64_t d_bs, uint64_t ld, int dst_major,
+                 int src_rowfast) {
+  __shared__ float tile[32][33]; // tile[r][c]
+  const uint32_t r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float *s = src + (uint64_t)blockIdx.z * s_bs;
+  __nv_bfloat16 *d = dst + (uint64_t)blockIdx.z * d_bs;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t r, c;
+    if (src_rowfast) { r = tx; c = ty + 8 * i; } else { c = tx; r = ty + 8 * i; }
+    const uint32_t gr = r0 + r, gc = c0 + c;
+    tile[r][c] = (gr < rows && gc < cols) ? s[(uint64_t)gr * s0 + (uint64_t)gc * s1] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t r, c;
+    if (dst_major) { r = tx; c = ty + 8 * i; } else { c = tx; r = ty + 8 * i; }
+    const uint32_t gr = r0 + r, gc = c0 + c;
+    if (gr < rows && gc < cols) {
+      const uint64_t off = dst_major ? ((uint64_t)gr + (uint64_t)gc * ld) : ((uint64_t)gc + (uint64_t)gr * ld);
+      d[off] = __float2bfloat16_rn(tile[r][c]);
+    }
+  }
+}
+
+int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols,
+                     uint16_t *dst, uint64_t d_bs, uint64_t ld, int dst_major, uint32_t batch,
+                     cudaStream_t st) {
+  const dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch);
+  if (grid.y > 65535 || grid.z > 65535) return WEEDCU_EINVAL;
+  const int src_rowfast = (s0 <= s1) ? 1 : 0;
+  pack_bf16_kernel<<<grid, 256, 0, st>>>(src, s_bs, s0, s1, rows, cols, (__nv_bfloat16 *)dst, d_bs, ld,
+                                         dst_major, src_rowfast);
+  return after_launch();
+}
+
+int launch_gemm_f32(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c,
+                    const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, uint32_t batch, int accumulate,
+                    cudaStream_t st);
+
+static inline uint64_t round8(uint64_t x) { return (x + 7) & ~7ull; }
+
+} // namespace weedcu
+
+using namespace weedcu;
+
+extern "C" {
+
+int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
+                     uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                     int accumulate, void *stream) {
+  return tc::launch_gemm_bf16(a, a_major, lda, 0, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
+                              resolve_stream(stream));
+}
+
+int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
+                     uint32_t cols, uint16_t *dst, int dst_major, void *stream) {
+  if (!src || !dst || !rows || !cols) return WEEDCU_EINVAL;
+  const uint64_t ld = round8(dst_major ? rows : cols);
+  return launch_pack_bf16(src + offset, 0, s0, s1, rows, cols, dst, 0, ld, dst_major, 1, resolve_stream(stream));
+}
+
+int weedcu_gemm_workspace_bytes(uint32_t M, uint32_t K, uint32_t N, uint32_t batch, int precision,
+                                uint64_t *bytes) {
+  if (!bytes) return WEEDCU_EINVAL;
+  if (precision == WEEDCU_GEMM_FP32) { *bytes = 0; return 0; }
+  *bytes = 2ull * batch * (round8(M) * round8(K) + round8(K) * round8(N)) + 512;
+  return 0;
+}
+
+int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm,
+                       float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
+                       uint32_t batch, int accumulate, int precision, void *stream) {
+  if (!a || !am || !b || !bm || !c || !cm || !M || !K || !N || !batch) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  // The tensor-core path writes C column-major (M contiguous). Other C layouts, and problems too
+  // small to fill one 128-wide tile, take the FFMA kernel (a precision upgrade, never a host path).
+  const bool tc_ok = (precision == WEEDCU_GEMM_BF16) && (cm->s0 == 1) && (M >= 64) && (N >= 16) && (K >= 32);
+  if (!tc_ok) return launch_gemm_f32(a, am, b, bm, c, cm, M, K, N, batch, accumulate, st);
+
+  // Pack to bf16 in whichever majorness the fp32 source is already contiguous in.
+  const int a_major = (am->s0 <= am->s1) ? 1 : 0; // 1: M contiguous
+  const int b_major = (bm->s1 < bm->s0) ? 1 : 0;  // 1: N contiguous; B[k,n]: s0 = k stride
+  const uint64_t lda = a_major ? round8(M) : round8(K);
+  const uint64_t ldb = b_major ? round8(N) : round8(K);
+  const uint64_t a_elems = a_major ? lda * K : lda * M, b_elems = b_major ? ldb * K : ldb * N;
+  const uint64_t a_bs = round8(a_elems), b_bs = round8(b_elems);
+  uint16_t *ws = nullptr;
+  WCU_CHECK(cudaMallocAsync((void **)&ws, 2ull * batch * (a_bs + b_bs), st));
+  uint16_t *wa = ws, *wb = ws + (uint64_t)batch * a_bs;
+  int rc = launch_pack_bf16(a + am->offset, am->batch_stride, am->s0, am->s1, M, K, wa, a_bs, lda, a_major,
+                            batch, st);
+  // B as an [N, K] operand: rows = n (stride s1), cols = k (stride s0)
+  if (rc == 0)
+    rc = launch_pack_bf16(b + bm->offset, bm->batch_stride, bm->s1, bm->s0, N, K, wb, b_bs, ldb, b_major,
+                          batch, st);
+  if (rc == 0)
+    rc = tc::launch_gemm_bf16(wa, a_major, lda, a_bs, wb, b_major, ldb, b_bs, c + cm->offset, cm->s1,
+                              cm->batch_stride, M, N, K, batch, accumulate, st);
+  cudaFreeAsync(ws, st);
+  if (rc == WEEDCU_ENOSUP) return launch_gemm_f32(a, am, b, bm, c, cm, M, K, N, batch, accumulate, st);
+  return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,304 @@
+// layernorm.cu — fused LayerNorm forward/backward, embedding gather / scatter-add, triu fill.
+//
+// LayerNorm reference: LayerNorm::forward (src/modules/layernorm.cpp:29-42) composes ~12 tensor ops
+// (mean, sub, mul, mean, +eps, ^0.5, div, *gamma, +beta) and ~30 backward closures. Here: one
+// forward kernel (8 B/elem) and one backward kernel (16 B/elem + parameter partials).
+// x is [rows, F] with row stride 1 and feature stride `rows`: the normalised axis is the slowest,
+// so RT adjacent rows are tiled against all F features, staged once in shared memory, and the
+// reference's two-pass statistics (mean, then mean of centred squares) run from the staged copy.
+#include "common.cuh"
+
+namespace weedcu {
+
+constexpr size_t kLnMaxTileBytes = 160 * 1024;
+
+template <int RT, int NT, bool STAGED>
+__global__ void __launch_bounds__(NT)
+layernorm_fwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float eps, float *__restrict__ y, float *__restrict__ mean,
+                     float *__restrict__ rstd) {
+  constexpr int BY = NT / RT;
+  extern __shared__ float tile[]; // [F][RT]
+  __shared__ float red[BY][RT + 1];
+  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
+  const uint32_t r = blockIdx.x * RT + tx;
+  const bool live = r < rows;
+  const float *p = x + r;
+
+  float s = 0.0f;
+  if (live)
+    for (uint32_t f = ty; f < F; f += BY) {
+      const float v = p[(uint64_t)f * rows];
+      if (STAGED) tile[f * RT + tx] = v;
+      s += v;
+    }
+  red[ty][tx] = s;
+  __syncthreads();
+  s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < BY; ++k) s += red[k][tx];
+  const float mu = s / (float)F;
+  __syncthreads();
+
+  float q = 0.0f;
+  if (live)
+    for (uint32_t f = ty; f < F; f += BY) {
+      const float xc = (STAGED ? tile[f * RT + tx] : p[(uint64_t)f * rows]) - mu;
+      q += xc * xc;
+    }
+  red[ty][tx] = q;
+  __syncthreads();
+  q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < BY; ++k) q += red[k][tx];
+  const float den = sqrtf(q / (float)F + eps); // (var + eps) ^ 0.5, layernorm.cpp:35
+  if (live) {
+    if (ty == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = 1.0f / den;
+    }
+    float *py = y + r;
+    for (uint32_t f = ty; f < F; f += BY) {
+      const float xc = (STAGED ? tile[f * RT + tx] : p[(uint64_t)f * rows]) - mu;
+      py[(uint64_t)f * rows] = (xc / den) * gamma[f] + beta[f];
+    }
+  }
+}
+
+// dx += rstd*(g - mean_f(g) - xhat*mean_f(g*xhat)), g = dy*gamma, xhat = (x-mean)*rstd.
+// Per-block column partials of dy*xhat and dy go to part_g/part_b[blockIdx][F].
+template <int RT, int NT, bool STAGED>
+__global__ void __launch_bounds__(NT)
+layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
+                     const float *__restrict__ gamma, const float *__restrict__ mean,
+                     const float *__restrict__ rstd, float *dx, float *__restrict__ part_g,
+                     float *__restrict__ part_b) {
+  constexpr int BY = NT / RT;
+  extern __shared__ float tile[]; // STAGED: xhat [F][RT] then dy [F][RT]
+  __shared__ float red_a[BY][RT + 1];
+  __shared__ float red_b[BY][RT + 1];
+  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
+  const uint32_t r = blockIdx.x * RT + tx;
+  const bool live = r < rows;
+  const float mu = live ? mean[r] : 0.0f, rs = live ? rstd[r] : 0.0f;
+  float *t_xh = tile, *t_dy = tile + (size_t)F * RT;
+
+  float sg = 0.0f, sgx = 0.0f;
+  for (uint32_t f0 = 0; f0 < F; f0 += BY) { // uniform trip count: the shuffles below need it
+    const uint32_t f = f0 + ty;
+    const bool fv = f < F;
+    float xh = 0.0f, d = 0.0f;
+    if (live && fv) {
+      xh = (x[r + (uint64_t)f * rows] - mu) * rs;
+      d = dy[r + (uint64_t)f * rows];
+    }
+    if (STAGED && fv) {
+      t_xh[f * RT + tx] = xh;
+      t_dy[f * RT + tx] = d;
+    }
+    const float g = fv ? d * gamma[f] : 0.0f;
+    sg += g;
+    sgx += g * xh;
+    // column partials over the RT rows of this tile (lanes tx of one ty share f)
+    float cg = d * xh, cb = d;
+#pragma unroll
+    for (int o = RT / 2; o > 0; o >>= 1) {
+      cg += __shfl_xor_sync(0xffffffffu, cg, o, RT);
+      cb += __shfl_xor_sync(0xffffffffu, cb, o, RT);
+    }
+    if (tx == 0 && fv) {
+      part_g[(uint64_t)blockIdx.x * F + f] = cg;
+      part_b[(uint64_t)blockIdx.x * F + f] = cb;
+    }
+  }
+  red_a[ty][tx] = sg;
+  red_b[ty][tx] = sgx;
+  __syncthreads();
+  sg = sgx = 0.0f;
+#pragma unroll
+  for (int k = 0; k < BY; ++k) {
+    sg += red_a[k][tx];
+    sgx += red_b[k][tx];
+  }
+  const float mg = sg / (float)F, mgx = sgx / (float)F;
+  if (live)
+    for (uint32_t f = ty; f < F; f += BY) {
+      float xh, d;
+      if (STAGED) {
+        xh = t_xh[f * RT + tx];
+        d = t_dy[f * RT + tx];
+      } else {
+        xh = (x[r + (uint64_t)f * rows] - mu) * rs;
+        d = dy[r + (uint64_t)f * rows];
+      }
+      const float g = d * gamma[f];
+      dx[r + (uint64_t)f * rows] += rs * ((g - mg) - xh * mgx);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_param_reduce_kernel(const float *__restrict__ part_g, const float *__restrict__ part_b,
+                              uint32_t nblocks, uint32_t F, float *dgamma, float *dbeta) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+  uint32_t b = 0;
+  for (; b + 1 < nblocks; b += 2) {
+    a0 += part_g[(uint64_t)b * F + f];
+    a1 += part_g[(uint64_t)(b + 1) * F + f];
+    b0 += part_b[(uint64_t)b * F + f];
+    b1 += part_b[(uint64_t)(b + 1) * F + f];
+  }
+  if (b < nblocks) {
+    a0 += part_g[(uint64_t)b * F + f];
+    b0 += part_b[(uint64_t)b * F + f];
+  }
+  if (dgamma) dgamma[f] += a0 + a1;
+  if (dbeta) dbeta[f] += b0 + b1;
+}
+
+// --------------------------------------------------------------------------- embedding / mask
+// Reference cpu_forward / cpu_backward, src/ops/embedding.cpp:56-110. Thread per (token, feature)
+// with the token index fastest: output rows are contiguous, weight reads are gathers.
+__global__ void __launch_bounds__(256)
+embedding_gather_kernel(const int32_t *__restrict__ idx, uint32_t idx_stride, uint32_t n,
+                        const float *__restrict__ W, uint32_t w_s0, uint32_t w_s1, uint32_t D,
+                        float *__restrict__ out, uint32_t o_s0, uint32_t o_s1) {
+  const uint64_t total = (uint64_t)n * D, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t i = (uint32_t)(t % n), d = (uint32_t)(t / n);
+    const uint64_t tok = (uint32_t)idx[(uint64_t)i * idx_stride];
+    out[(uint64_t)i * o_s0 + (uint64_t)d * o_s1] = W[tok * w_s0 + (uint64_t)d * w_s1];
+  }
+}
+__global__ void __launch_bounds__(256)
+embedding_scatter_kernel(float *dW, uint32_t w_s0, uint32_t w_s1, const int32_t *__restrict__ idx,
+                         uint32_t idx_stride, uint32_t n, uint32_t D, const float *__restrict__ dout,
+                         uint32_t o_s0, uint32_t o_s1) {
+  const uint64_t total = (uint64_t)n * D, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t i = (uint32_t)(t % n), d = (uint32_t)(t / n);
+    const uint64_t tok = (uint32_t)idx[(uint64_t)i * idx_stride];
+    atomicAdd(&dW[tok * w_s0 + (uint64_t)d * w_s1], dout[(uint64_t)i * o_s0 + (uint64_t)d * o_s1]);
+  }
+}
+// cpu_triu_fill, src/ops/triu_fill.cpp:41-59
+__global__ void __launch_bounds__(256)
+triu_fill_kernel(float *a, uint32_t t0, uint32_t t1, uint32_t s0, uint32_t s1, float val,
+                 uint32_t diagonal) {
+  const uint64_t total = (uint64_t)t0 * t1, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t i = (uint32_t)(t % t0), j = (uint32_t)(t / t0);
+    if ((uint64_t)i + diagonal <= j) a[(uint64_t)i * s0 + (uint64_t)j * s1] = val;
+  }
+}
+
+template <int RT, int NT>
+static int ln_fwd_launch(const float *x, uint32_t rows, uint32_t F, const float *gamma,
+                         const float *beta, float eps, float *y, float *mean, float *rstd,
+                         cudaStream_t st) {
+  const unsigned grid = (rows + RT - 1) / RT;
+  const size_t bytes = (size_t)F * RT * sizeof(float);
+  if (bytes <= kLnMaxTileBytes) {
+    auto k = layernorm_fwd_kernel<RT, NT, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLnMaxTileBytes);
+    k<<<grid, NT, bytes, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
+  } else {
+    layernorm_fwd_kernel<RT, NT, false><<<grid, NT, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
+  }
+  return after_launch();
+}
+template <int RT, int NT>
+static int ln_bwd_launch(const float *x, const float *dy, uint32_t rows, uint32_t F,
+                         const float *gamma, const float *mean, const float *rstd, float *dx,
+                         float *pg, float *pb, cudaStream_t st) {
+  const unsigned grid = (rows + RT - 1) / RT;
+  const size_t bytes = 2 * (size_t)F * RT * sizeof(float);
+  if (bytes <= kLnMaxTileBytes) {
+    auto k = layernorm_bwd_kernel<RT, NT, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLnMaxTileBytes);
+    k<<<grid, NT, bytes, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb);
+  } else {
+    layernorm_bwd_kernel<RT, NT, false><<<grid, NT, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb);
+  }
+  return after_launch();
+}
+static int pick_rt(uint32_t rows) {
+  if (rows / 32 >= 2 * kNumSMs) return 32;
+  if (rows / 16 >= 2 * kNumSMs) return 16;
+  return 8;
+}
+
+} // namespace weedcu
+
+using namespace weedcu;
+
+extern "C" {
+
+int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma,
+                         const float *beta, float eps, float *y, float *mean, float *rstd,
+                         void *stream) {
+  if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  switch (pick_rt(rows)) {
+  case 32: return ln_fwd_launch<32, 512>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
+  case 16: return ln_fwd_launch<16, 256>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
+  default: return ln_fwd_launch<8, 256>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
+  }
+}
+
+int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
+                         const float *gamma, const float *mean, const float *rstd, float *dx,
+                         float *dgamma, float *dbeta, void *stream) {
+  if (!x || !dy || !gamma || !mean || !rstd || !dx || !rows || !F) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  const int rt = pick_rt(rows);
+  const uint32_t nblocks = (rows + rt - 1) / rt;
+  float *part = nullptr;
+  WCU_CHECK(cudaMallocAsync((void **)&part, sizeof(float) * 2 * (size_t)nblocks * F, st));
+  float *pg = part, *pb = part + (size_t)nblocks * F;
+  int rc;
+  switch (rt) {
+  case 32: rc = ln_bwd_launch<32, 512>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
+  case 16: rc = ln_bwd_launch<16, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
+  default: rc = ln_bwd_launch<8, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
+  }
+  if (rc == 0 && (dgamma || dbeta)) {
+    layernorm_param_reduce_kernel<<<(F + 255) / 256, 256, 0, st>>>(pg, pb, nblocks, F, dgamma, dbeta);
+    rc = after_launch();
+  }
+  cudaFreeAsync(part, st);
+  return rc;
+}
+
+int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n,
+                            const float *W, uint64_t w_off, uint32_t w_s0, uint32_t w_s1,
+                            uint32_t D, float *out, uint64_t o_off, uint32_t o_s0, uint32_t o_s1,
+                            void *stream) {
+  if (!idx || !W || !out || !n || !D) return WEEDCU_EINVAL;
+  embedding_gather_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
+      idx + idx_off, idx_stride, n, W + w_off, w_s0, w_s1, D, out + o_off, o_s0, o_s1);
+  return after_launch();
+}
+
+int weedcu_embedding_scatter_add(float *dW, uint64_t w_off, uint32_t w_s0, uint32_t w_s1,
+                                 const int32_t *idx, uint64_t idx_off, uint32_t idx_stride,
+                                 uint32_t n, uint32_t D, const float *dout, uint64_t o_off,
+                                 uint32_t o_s0, uint32_t o_s1, void *stream) {
+  if (!dW || !idx || !dout || !n || !D) return WEEDCU_EINVAL;
+  embedding_scatter_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
+      dW + w_off, w_s0, w_s1, idx + idx_off, idx_stride, n, D, dout + o_off, o_s0, o_s1);
+  return after_launch();
+}
+
+int weedcu_triu_fill_real(float *a, const weedcu_view *av, float val, uint32_t diagonal,
+                          void *stream) {
+  if (!a || !av || av->rank != 2) return WEEDCU_EINVAL;
+  const uint64_t total = (uint64_t)av->shape[0] * av->shape[1];
+  if (!total) return WEEDCU_EINVAL;
+  triu_fill_kernel<<<grid_for(total, 256, 16), 256, 0, resolve_stream(stream)>>>(
+      a + av->offset, av->shape[0], av->shape[1], av->stride[0], av->stride[1], val, diagonal);
+  return after_launch();
+}
+
+} // extern "C"

@@ -1,0 +1,350 @@
+// reduce.cu — axis sum + its gradient, full sum/mean, row argmax.  HBM-bound (4 B / input elem).
+//
+// Reference: Weed::reduce / reduce_grad (src/ops/reduce.cpp:17-38,60-66,84-113) and Weed::sum /
+// mean (src/ops/sum.cpp:74-98). The reference's OpenCL reduce kernels never receive the rank
+// (SURVEY §2.3 defect 2) and full sum copies the buffer to the host (sum.cpp:52-67); here both are
+// real device reductions: shared-memory staging across column slices + warp-shuffle trees.
+#include "common.cuh"
+
+namespace weedcu {
+
+struct ReduceView {
+  int rank, axis;
+  uint32_t shape[kMaxRank];
+  uint32_t stride[kMaxRank];
+};
+
+// Generic / reference-order kernel: one thread per output, serial over the axis. Used for
+// index_order = 1 (reproduces REDUCE_HEAD's last-dim-fastest decomposition, reduce.cpp:17-31) and
+// for layouts the tiled kernels do not cover.
+__global__ void __launch_bounds__(256)
+reduce_generic_kernel(const float *__restrict__ a, ReduceView v, uint32_t n_out, float *__restrict__ out,
+                      int index_order) {
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  uint64_t base = 0;
+  uint32_t tmp = o;
+  if (index_order) {
+    for (int d = v.rank - 1; d >= 0; --d) {
+      if (d == v.axis) continue;
+      base += (uint64_t)(tmp % v.shape[d]) * v.stride[d];
+      tmp /= v.shape[d];
+    }
+  } else {
+    for (int d = 0; d < v.rank; ++d) {
+      if (d == v.axis) continue;
+      base += (uint64_t)(tmp % v.shape[d]) * v.stride[d];
+      tmp /= v.shape[d];
+    }
+  }
+  float s = 0.0f;
+  const uint64_t as = v.stride[v.axis];
+  for (uint32_t j = 0; j < v.shape[v.axis]; ++j) s += a[base + j * as];
+  out[o] = s;
+}
+
+// Canonical contiguous form a[inner, L, outer] (strides 1, inner, inner*L), output [inner, outer].
+// Case "strided axis" (inner >= 32): a warp spans 32 adjacent outputs (coalesced 128-B rows), the
+// BY warps of a block split the axis, partial sums meet in shared memory.
+template <int BY>
+__global__ void __launch_bounds__(32 * BY)
+reduce_strided_kernel(const float *__restrict__ a, uint32_t inner, uint32_t L, float *__restrict__ out) {
+  __shared__ float part[BY][33];
+  const uint32_t ii = blockIdx.x * 32 + threadIdx.x;
+  const uint64_t slab = (uint64_t)blockIdx.y * inner * L;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  if (ii < inner) {
+    const float *p = a + slab + ii;
+    uint32_t j = threadIdx.y;
+    for (; j + 3 * BY < L; j += 4 * BY) { // four independent loads in flight per thread
+      s0 += p[(uint64_t)j * inner];
+      s1 += p[(uint64_t)(j + BY) * inner];
+      s2 += p[(uint64_t)(j + 2 * BY) * inner];
+      s3 += p[(uint64_t)(j + 3 * BY) * inner];
+    }
+    for (; j < L; j += BY) s0 += p[(uint64_t)j * inner];
+  }
+  part[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.y == 0 && ii < inner) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < BY; ++y) t += part[y][threadIdx.x];
+    out[(uint64_t)blockIdx.y * inner + ii] = t;
+  }
+}
+
+// Case "contiguous axis" (inner == 1): one block per output, 128-bit loads along the axis.
+__global__ void __launch_bounds__(256)
+reduce_contig_kernel(const float *__restrict__ a, uint32_t L, float *__restrict__ out) {
+  __shared__ float red[32];
+  const float *p = a + (uint64_t)blockIdx.x * L;
+  float s = 0.0f;
+  if ((((uintptr_t)p) & 15u) == 0) {
+    const uint32_t nq = L >> 2;
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+      const float4 v = q[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    for (uint32_t i = (nq << 2) + threadIdx.x; i < L; i += blockDim.x) s += p[i];
+  } else {
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) s += p[i];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// reduce_grad, reference order (REDUCE_GRAD_HEAD, reduce.cpp:84-101): i is decomposed over the
+// NON-axis dims only, last dim fastest.
+template <int NOPS>
+__global__ void __launch_bounds__(256)
+reduce_grad_reforder_kernel(float *din, IndexSpace<NOPS> sp_din, ReduceView dims,
+                            const float *__restrict__ dout, ReduceView dv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sp_din.n) return;
+  uint64_t o = 0;
+  uint32_t tmp = i;
+  for (int d = dims.rank - 1; d >= 0; --d) {
+    if (d == dims.axis) continue;
+    o += (uint64_t)(tmp % dims.shape[d]) * dv.stride[d];
+    tmp /= dims.shape[d];
+  }
+  uint64_t off = 0;
+  uint32_t rem = i;
+  for (int d = 0; d < sp_din.rank; ++d) {
+    off += (uint64_t)(rem % sp_din.shape[d]) * sp_din.stride[0][d];
+    rem /= sp_din.shape[d];
+  }
+  din[off] += dout[o];
+}
+
+// ------------------------------------------------------------------------ full sum (two pass)
+template <int NOPS>
+__global__ void __launch_bounds__(256)
+sum_pass1_kernel(const float *__restrict__ a, IndexSpace<NOPS> sp, bool linear_vec, float *__restrict__ partial) {
+  __shared__ float red[32];
+  float s0 = 0.0f, s1 = 0.0f;
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (linear_vec) {
+    const uint32_t nq = sp.n >> 2;
+    const float4 *q = reinterpret_cast<const float4 *>(a);
+    uint32_t i = tid;
+    for (; i + stride < nq; i += 2 * stride) {
+      const float4 v = q[i], w = q[i + stride];
+      s0 += (v.x + v.y) + (v.z + v.w);
+      s1 += (w.x + w.y) + (w.z + w.w);
+    }
+    if (i < nq) {
+      const float4 v = q[i];
+      s0 += (v.x + v.y) + (v.z + v.w);
+    }
+    for (uint32_t k = (nq << 2) + tid; k < sp.n; k += stride) s0 += a[k];
+  } else {
+    for (uint32_t i = tid; i < sp.n; i += stride) {
+      uint64_t off = 0;
+      uint32_t rem = i;
+      for (int d = 0; d < sp.rank; ++d) {
+        off += (uint64_t)(rem % sp.shape[d]) * sp.stride[0][d];
+        rem /= sp.shape[d];
+      }
+      s0 += a[off];
+    }
+  }
+  const float t = block_sum(s0 + s1, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(1024)
+sum_pass2_kernel(const float *__restrict__ partial, uint32_t n, float scale, float *__restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.0f;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s * scale;
+}
+
+// ------------------------------------------------------------------------ argmax over rows
+// logits[rows, V] with row stride rs (normally 1) and vocab stride vs: 32 rows x BY slices per
+// block, lowest index wins ties (matches a serial first-max scan).
+template <int BY>
+__global__ void __launch_bounds__(32 * BY)
+argmax_rows_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
+                   int32_t *__restrict__ out) {
+  __shared__ float mv[BY][33];
+  __shared__ uint32_t mi[BY][33];
+  const uint32_t r = blockIdx.x * 32 + threadIdx.x;
+  float best = -INFINITY;
+  uint32_t bi = 0xffffffffu;
+  if (r < rows) {
+    const float *p = x + (uint64_t)r * rs;
+    for (uint32_t v = threadIdx.y; v < V; v += BY) {
+      const float y = p[(uint64_t)v * vs];
+      if (y > best || bi == 0xffffffffu) {
+        best = y;
+        bi = v;
+      }
+    }
+  }
+  mv[threadIdx.y][threadIdx.x] = best;
+  mi[threadIdx.y][threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.y == 0 && r < rows) {
+    for (int y = 1; y < BY; ++y) {
+      const float c = mv[y][threadIdx.x];
+      const uint32_t ci = mi[y][threadIdx.x];
+      if (ci != 0xffffffffu && (c > best || (c == best && ci < bi))) {
+        best = c;
+        bi = ci;
+      }
+    }
+    out[r] = (int32_t)bi;
+  }
+}
+
+static bool canonical_contiguous(const weedcu_view *v, int axis, uint64_t &inner, uint64_t &outer) {
+  uint64_t st = 1;
+  inner = 1;
+  outer = 1;
+  for (int d = 0; d < v->rank; ++d) {
+    const uint32_t ext = v->shape[d];
+    if (ext != 1 && v->stride[d] != st) return false;
+    if (d < axis) inner *= ext;
+    if (d > axis) outer *= ext;
+    st *= ext;
+  }
+  return true;
+}
+
+} // namespace weedcu
+
+using namespace weedcu;
+
+extern "C" {
+
+int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *out, int index_order,
+                       void *stream) {
+  if (!a || !av || !out || av->rank <= 0 || av->rank > kMaxRank || axis < 0 || axis >= av->rank)
+    return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  uint64_t total = 1;
+  for (int d = 0; d < av->rank; ++d) total *= av->shape[d];
+  const uint32_t L = av->shape[axis];
+  if (!L || !total) return WEEDCU_EINVAL;
+  const uint64_t n_out = total / L;
+  const float *base = a + av->offset;
+  uint64_t inner, outer;
+  // Row-major and column-major enumeration of the non-axis coordinates coincide when at most one
+  // non-axis dim has extent > 1; then the fast kernels serve index_order 1 as well.
+  int big = 0;
+  for (int d = 0; d < av->rank; ++d)
+    if (d != axis && av->shape[d] > 1) ++big;
+  const bool order_free = (index_order == 0) || (big <= 1);
+  if (order_free && canonical_contiguous(av, axis, inner, outer)) {
+    if (inner == 1) {
+      reduce_contig_kernel<<<(unsigned)outer, 256, 0, st>>>(base, L, out);
+      return after_launch();
+    }
+    if (inner >= 32 && outer <= 65535) {
+      dim3 grid((unsigned)((inner + 31) / 32), (unsigned)outer);
+      const uint64_t blocks = (uint64_t)grid.x * grid.y;
+      if (L >= 64 && blocks < 4 * kNumSMs) {
+        reduce_strided_kernel<16><<<grid, dim3(32, 16), 0, st>>>(base, (uint32_t)inner, L, out);
+      } else {
+        reduce_strided_kernel<4><<<grid, dim3(32, 4), 0, st>>>(base, (uint32_t)inner, L, out);
+      }
+      return after_launch();
+    }
+  }
+  ReduceView v;
+  v.rank = av->rank;
+  v.axis = axis;
+  for (int d = 0; d < kMaxRank; ++d) {
+    v.shape[d] = d < av->rank ? av->shape[d] : 1;
+    v.stride[d] = d < av->rank ? av->stride[d] : 0;
+  }
+  reduce_generic_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(base, v, (uint32_t)n_out, out,
+                                                                       index_order);
+  return after_launch();
+}
+
+int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout,
+                            const weedcu_view *doutv, int axis, int index_order, void *stream) {
+  if (!din || !dinv || !dout || !doutv || dinv->rank != doutv->rank || axis < 0 ||
+      axis >= dinv->rank)
+    return WEEDCU_EINVAL;
+  int big = 0;
+  for (int d = 0; d < dinv->rank; ++d)
+    if (d != axis && dinv->shape[d] > 1) ++big;
+  // The reference's decomposition skips the axis coordinate entirely, so it agrees with the
+  // intended broadcast only when the axis is the last dim with extent > 1 and <= 1 other dim is.
+  bool axis_last = true;
+  for (int d = axis + 1; d < dinv->rank; ++d)
+    if (dinv->shape[d] > 1) axis_last = false;
+  if (index_order == 0 || (big <= 1 && axis_last)) {
+    // intended semantics: din[i] += dout[i] with dout broadcast (stride 0) along `axis`
+    weedcu_view dv = *doutv;
+    dv.stride[axis] = 0;
+    return weedcu_inplace_real(WEEDCU_ADD, din, dinv, dout, &dv, stream);
+  }
+  const weedcu_view *views[1] = {dinv};
+  IndexSpace<1> sp;
+  // no collapsing: the reference formula needs the original dims
+  sp.rank = dinv->rank;
+  uint64_t n = 1;
+  for (int d = 0; d < kMaxRank; ++d) {
+    sp.shape[d] = d < dinv->rank ? dinv->shape[d] : 1;
+    sp.stride[0][d] = d < dinv->rank ? dinv->stride[d] : 0;
+    n *= sp.shape[d];
+  }
+  (void)views;
+  if (n > 0xffffffffull) return WEEDCU_EINVAL;
+  sp.n = (uint32_t)n;
+  ReduceView dims, dv;
+  dims.rank = dv.rank = dinv->rank;
+  dims.axis = dv.axis = axis;
+  for (int d = 0; d < kMaxRank; ++d) {
+    dims.shape[d] = sp.shape[d];
+    dims.stride[d] = sp.stride[0][d];
+    dv.shape[d] = sp.shape[d];
+    dv.stride[d] = d < doutv->rank ? doutv->stride[d] : 0;
+  }
+  reduce_grad_reforder_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, resolve_stream(stream)>>>(
+      din + dinv->offset, sp, dims, dout + doutv->offset, dv);
+  return after_launch();
+}
+
+int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *stream) {
+  if (!a || !av || !out) return WEEDCU_EINVAL;
+  const weedcu_view *views[1] = {av};
+  IndexSpace<1> sp;
+  if (!build_index_space<1>(views, sp)) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  const float *base = a + av->offset;
+  const bool linear = (sp.rank == 1 && sp.stride[0][0] == 1);
+  const bool vec = linear && aligned16(base);
+  if (sp.rank == 1 && sp.stride[0][0] == 0) { // broadcast scalar: n * value
+    sp.stride[0][0] = 0;
+  }
+  unsigned blocks = grid_for(vec ? (sp.n >> 2) : sp.n, 256, 4);
+  if (blocks > 1024) blocks = 1024;
+  float *partial = nullptr;
+  WCU_CHECK(cudaMallocAsync((void **)&partial, sizeof(float) * blocks, st));
+  sum_pass1_kernel<1><<<blocks, 256, 0, st>>>(base, sp, vec, partial);
+  int rc = after_launch();
+  if (rc == 0) {
+    sum_pass2_kernel<<<1, 1024, 0, st>>>(partial, blocks, scale, out);
+    rc = after_launch();
+  }
+  cudaFreeAsync(partial, st);
+  return rc;
+}
+
+int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs,
+                       uint32_t vs, int32_t *out, void *stream) {
+  if (!x || !out || !rows || !V) return WEEDCU_EINVAL;
+  argmax_rows_kernel<16><<<(rows + 31) / 32, dim3(32, 16), 0, resolve_stream(stream)>>>(
+      x + offset, rows, V, rs, vs, out);
+  return after_launch();
+}
+
+} // extern "C"

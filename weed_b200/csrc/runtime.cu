@@ -1,0 +1,204 @@
+// runtime.cu — device, stream, event, memory-pool and copy entry points of weedcu.h.
+// Replaces OCLEngine device discovery (reference include/common/oclengine.hpp:249-395) and the
+// buffer / queue half of GpuDevice (reference src/devices/gpu_device.cpp:34-76,250-312,388-447).
+// One in-order compute stream per device gives the same ordering as the reference's FIFO of
+// QueueItems (gpu_device.cpp:180-248) without its per-launch host wait (gpu_device.cpp:296-305).
+#include "common.cuh"
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace weedcu {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_mutex;
+static cudaStream_t g_default_stream[64] = {nullptr};
+static bool g_default_owned[64] = {false};
+static bool g_pool_configured[64] = {false};
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int after_launch() {
+  count_launch(1);
+  return (int)cudaGetLastError();
+}
+
+static int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < 64) ? d : 0;
+}
+
+static void configure_pool(int dev) {
+  if (g_pool_configured[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    // Keep freed blocks cached in the pool: allocation in the autograd hot loop must not
+    // touch the driver (180 GB of HBM3e; the host tracks its own budget).
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  g_pool_configured[dev] = true;
+}
+
+cudaStream_t resolve_stream(void *s) {
+  if (s) return (cudaStream_t)s;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!g_default_stream[dev]) {
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    g_default_stream[dev] = st;
+    g_default_owned[dev] = true;
+    configure_pool(dev);
+  }
+  return g_default_stream[dev];
+}
+
+} // namespace weedcu
+
+using namespace weedcu;
+
+extern "C" {
+
+int weedcu_device_count(int *count) {
+  if (!count) return WEEDCU_EINVAL;
+  WCU_CHECK(cudaGetDeviceCount(count));
+  return 0;
+}
+int weedcu_set_device(int device) {
+  WCU_CHECK(cudaSetDevice(device));
+  return 0;
+}
+int weedcu_get_device(int *device) {
+  if (!device) return WEEDCU_EINVAL;
+  WCU_CHECK(cudaGetDevice(device));
+  return 0;
+}
+int weedcu_device_info(int device, char *name, int name_len, uint64_t *total_mem, int *sm_count,
+                       int *cc_major, int *cc_minor) {
+  cudaDeviceProp p;
+  WCU_CHECK(cudaGetDeviceProperties(&p, device));
+  if (name && name_len > 0) {
+    strncpy(name, p.name, (size_t)name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (total_mem) *total_mem = (uint64_t)p.totalGlobalMem;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+const char *weedcu_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == WEEDCU_EINVAL) return "weedcu: invalid argument";
+  if (code == WEEDCU_ENOSUP) return "weedcu: unsupported configuration";
+  if (code == WEEDCU_ENCCL) return "weedcu: NCCL not loaded";
+  if (code >= 1000) return "weedcu: NCCL error";
+  return cudaGetErrorString((cudaError_t)code);
+}
+void *weedcu_default_stream(void) { return (void *)resolve_stream(nullptr); }
+int weedcu_set_default_stream(void *stream) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (g_default_stream[dev] && g_default_owned[dev]) cudaStreamDestroy(g_default_stream[dev]);
+  g_default_stream[dev] = (cudaStream_t)stream;
+  g_default_owned[dev] = false;
+  configure_pool(dev);
+  return 0;
+}
+int weedcu_stream_create(void **stream) {
+  if (!stream) return WEEDCU_EINVAL;
+  cudaStream_t st;
+  WCU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  configure_pool(current_device());
+  *stream = (void *)st;
+  return 0;
+}
+int weedcu_stream_destroy(void *stream) {
+  WCU_CHECK(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+int weedcu_stream_sync(void *stream) {
+  WCU_CHECK(cudaStreamSynchronize(resolve_stream(stream)));
+  return 0;
+}
+int weedcu_stream_wait_event(void *stream, void *event) {
+  WCU_CHECK(cudaStreamWaitEvent(resolve_stream(stream), (cudaEvent_t)event, 0));
+  return 0;
+}
+int weedcu_event_create(void **event) {
+  if (!event) return WEEDCU_EINVAL;
+  cudaEvent_t e;
+  WCU_CHECK(cudaEventCreate(&e));
+  *event = (void *)e;
+  return 0;
+}
+int weedcu_event_destroy(void *event) {
+  WCU_CHECK(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+int weedcu_event_record(void *event, void *stream) {
+  WCU_CHECK(cudaEventRecord((cudaEvent_t)event, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_event_sync(void *event) {
+  WCU_CHECK(cudaEventSynchronize((cudaEvent_t)event));
+  return 0;
+}
+int weedcu_event_elapsed_ms(void *start, void *stop, float *ms) {
+  if (!ms) return WEEDCU_EINVAL;
+  WCU_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+int weedcu_malloc(void **ptr, size_t bytes, void *stream) {
+  if (!ptr) return WEEDCU_EINVAL;
+  if (bytes == 0) bytes = 16;
+  WCU_CHECK(cudaMallocAsync(ptr, bytes, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_free(void *ptr, void *stream) {
+  if (!ptr) return 0;
+  WCU_CHECK(cudaFreeAsync(ptr, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_mem_info(uint64_t *free_bytes, uint64_t *total_bytes) {
+  size_t f = 0, t = 0;
+  WCU_CHECK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
+int weedcu_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return WEEDCU_EINVAL;
+  WCU_CHECK(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+int weedcu_host_free(void *ptr) {
+  if (!ptr) return 0;
+  WCU_CHECK(cudaFreeHost(ptr));
+  return 0;
+}
+int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+  if (!bytes) return 0;
+  WCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+  if (!bytes) return 0;
+  WCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+  if (!bytes) return 0;
+  WCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_launch_count(uint64_t *count) {
+  if (!count) return WEEDCU_EINVAL;
+  *count = g_launches.load();
+  return 0;
+}
+
+} // extern "C"
