@@ -1,0 +1,432 @@
+// weed_harness.cpp — ONE client source, compiled twice:
+//   (1) against the UNMODIFIED reference (vm6502q/weed CPU build, oracle/_ref/libweed_ref.a)
+//       -> oracle/_ref/libweed_ref_harness.so          (test infrastructure: the live oracle)
+//   (2) against this repo's host library (weed_b200/host, -DWEED_B200)
+//       -> weed_b200/libweed_b200_harness.so           (the product, driven by tests and bench.py)
+// It only uses Weed's public API (tensors/tensor.hpp, modules/*.hpp, autograd/*.hpp) — that the
+// same file builds against both trees is the source-level proof of the drop-in claim — and exposes
+// a small handle-based C-ABI in the style of the reference's own src/shared_api.cpp:79-449
+// (integer handles, int error codes, last-error string).
+#include "autograd/adam.hpp"
+#include "autograd/bci_with_logits_loss.hpp"
+#include "autograd/cross_entropy_loss.hpp"
+#include "autograd/mse_loss.hpp"
+#include "autograd/sgd.hpp"
+#include "autograd/zero_grad.hpp"
+#include "modules/embedding.hpp"
+#include "modules/gelu.hpp"
+#include "modules/layernorm.hpp"
+#include "modules/learned_positional_encoding.hpp"
+#include "modules/linear.hpp"
+#include "modules/multihead_attention.hpp"
+#include "modules/relu.hpp"
+#include "modules/sequential.hpp"
+#include "modules/sigmoid.hpp"
+#include "modules/tanh.hpp"
+#include "modules/transformer_encoder_layer.hpp"
+#include "tensors/real_tensor.hpp"
+#include "tensors/symbol_tensor.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <string>
+
+using namespace Weed;
+
+namespace {
+DeviceTag g_dtag = DeviceTag::CPU;
+std::string g_error;
+int64_t g_next = 1;
+std::map<int64_t, TensorPtr> g_tensors;
+std::map<int64_t, SymbolTensorPtr> g_symbols;
+std::map<int64_t, ModulePtr> g_modules;
+std::map<int64_t, std::shared_ptr<Adam>> g_adams;
+
+int64_t put(const TensorPtr &t) {
+  g_tensors[g_next] = t;
+  return g_next++;
+}
+TensorPtr T(int64_t h) {
+  auto it = g_tensors.find(h);
+  if (it == g_tensors.end()) throw std::invalid_argument("bad tensor handle");
+  return it->second;
+}
+ModulePtr M(int64_t h) {
+  auto it = g_modules.find(h);
+  if (it == g_modules.end()) throw std::invalid_argument("bad module handle");
+  return it->second;
+}
+std::vector<tcapint> shape_vec(int rank, const uint32_t *shape) { return std::vector<tcapint>(shape, shape + rank); }
+
+#define WH_TRY(...)                                                                                \
+  try {                                                                                            \
+    __VA_ARGS__;                                                                                   \
+  } catch (const std::exception &e) {                                                              \
+    g_error = e.what();                                                                            \
+    return -1;                                                                                     \
+  }
+} // namespace
+
+extern "C" {
+
+const char *wh_last_error() { return g_error.c_str(); }
+const char *wh_backend() {
+#ifdef WEED_B200
+  return "weed_b200";
+#else
+  return "reference";
+#endif
+}
+
+// device_tag: 2 = CPU, 3 = GPU (Weed::DeviceTag values)
+int wh_init(int device_tag) {
+  WH_TRY({
+    g_dtag = (device_tag == 3) ? DeviceTag::GPU : DeviceTag::CPU;
+#ifdef WEED_B200
+    if (g_dtag == DeviceTag::GPU) WEED_GPU_SINGLETON.InitOCL();
+#endif
+    return 0;
+  })
+}
+int wh_reset() {
+  g_tensors.clear();
+  g_symbols.clear();
+  g_modules.clear();
+  g_adams.clear();
+  return 0;
+}
+int wh_free(int64_t h) {
+  g_tensors.erase(h);
+  g_symbols.erase(h);
+  return 0;
+}
+// backend switches of this repo's host library; accepted and ignored by the reference build
+int wh_config(const char *name, double value) {
+#ifdef WEED_B200
+  WH_TRY({
+    const std::string n(name);
+    BackendConfig &c = backend_config();
+    if (n == "fused") c.fused = value != 0;
+    else if (n == "ref_index_quirks") c.ref_index_quirks = value != 0;
+    else if (n == "matmul_precision") c.matmul_precision = (int)value;
+    else if (n == "grad_scale") c.grad_scale = (real1)value;
+    else throw std::invalid_argument("unknown config key");
+    return 0;
+  })
+#else
+  (void)name;
+  (void)value;
+  return 0;
+#endif
+}
+int wh_sync() {
+#ifdef WEED_B200
+  WH_TRY({
+    if (g_dtag == DeviceTag::GPU) WEED_GPU_SINGLETON.GetWeedDevice(-1)->clFinish();
+    return 0;
+  })
+#else
+  return 0;
+#endif
+}
+// the cudaStream_t all device work of this library is issued on (0 for the reference build)
+void *wh_stream() {
+#ifdef WEED_B200
+  try {
+    return WEED_GPU_SINGLETON.GetWeedDevice(-1)->stream;
+  } catch (...) {
+    return nullptr;
+  }
+#else
+  return nullptr;
+#endif
+}
+
+// ------------------------------------------------------------------------------- tensors
+int64_t wh_tensor(const float *data, uint32_t n, int rank, const uint32_t *shape, int requires_grad) {
+  WH_TRY({
+    std::vector<real1> v(data, data + n);
+    return put(std::make_shared<Tensor>(v, shape_vec(rank, shape), requires_grad != 0, g_dtag));
+  })
+}
+int64_t wh_scalar(float value, int requires_grad) {
+  WH_TRY({ return put(std::make_shared<Tensor>((real1)value, requires_grad != 0, g_dtag)); })
+}
+int64_t wh_symbol(const int32_t *data, uint32_t n, int rank, const uint32_t *shape) {
+  WH_TRY({
+    std::vector<symint> v(data, data + n);
+    g_symbols[g_next] = std::make_shared<SymbolTensor>(v, shape_vec(rank, shape), false, g_dtag);
+    return g_next++;
+  })
+}
+// an explicit (offset, shape, stride) view on the storage of an existing tensor
+int64_t wh_view(int64_t h, uint32_t offset, int rank, const uint32_t *shape, const uint32_t *stride) {
+  WH_TRY({
+    TensorPtr v = std::make_shared<Tensor>(*T(h));
+    v->offset = offset;
+    v->shape = shape_vec(rank, shape);
+    v->stride = shape_vec(rank, stride);
+    v->grad = nullptr;
+    v->grad_node = nullptr;
+    return put(v);
+  })
+}
+int wh_info(int64_t h, int *rank, uint32_t *shape, uint32_t *stride, uint32_t *offset, uint32_t *storage_size, int *requires_grad) {
+  WH_TRY({
+    TensorPtr t = T(h);
+    *rank = (int)t->shape.size();
+    for (size_t i = 0; i < t->shape.size() && i < 8; ++i) {
+      shape[i] = t->shape[i];
+      stride[i] = t->stride[i];
+    }
+    *offset = t->offset;
+    *storage_size = t->storage->size;
+    *requires_grad = t->requires_grad ? 1 : 0;
+    return 0;
+  })
+}
+// logical values: element i of the flat column-major index space, through the view
+int wh_read(int64_t h, float *out, uint32_t capacity, uint32_t *count) {
+  WH_TRY({
+    TensorPtr t = T(h);
+    const tcapint n = t->get_broadcast_size();
+    *count = n;
+    if (n > capacity) throw std::invalid_argument("wh_read: buffer too small");
+#ifdef WEED_B200
+    const std::vector<real1> v = to_host_logical(*t);
+    std::memcpy(out, v.data(), sizeof(float) * n);
+#else
+    TensorPtr c = t->cast(DeviceTag::CPU);
+    RealTensor rt(*c);
+    for (tcapint i = 0; i < n; ++i) out[i] = rt[i];
+#endif
+    return 0;
+  })
+}
+// raw storage contents in storage order
+int wh_read_storage(int64_t h, float *out, uint32_t capacity, uint32_t *count) {
+  WH_TRY({
+    TensorPtr t = T(h);
+    StoragePtr s = t->storage->cpu();
+    const tcapint n = s->size;
+    *count = n;
+    if (n > capacity) throw std::invalid_argument("wh_read_storage: buffer too small");
+    RealStorage *rs = static_cast<RealStorage *>(s.get());
+    for (tcapint i = 0; i < n; ++i) out[i] = (*rs)[i];
+    return 0;
+  })
+}
+int64_t wh_grad(int64_t h) {
+  WH_TRY({
+    TensorPtr t = T(h);
+    if (!t->grad) return (int64_t)0;
+    return put(t->grad);
+  })
+}
+int wh_backward(int64_t h) {
+  WH_TRY({
+    Tensor::backward(T(h));
+    return 0;
+  })
+}
+
+// Tensor:: front-ends by name. ins: tensor handles; f: float params; i: int params.
+int64_t wh_op(const char *name, const int64_t *ins, int n_in, const float *f, int n_f, const int32_t *iv, int n_i) {
+  WH_TRY({
+    const std::string op(name);
+    auto in = [&](int k) {
+      if (k >= n_in) throw std::invalid_argument("wh_op: missing tensor argument");
+      return T(ins[k]);
+    };
+    auto fp = [&](int k) {
+      if (k >= n_f) throw std::invalid_argument("wh_op: missing float argument");
+      return (real1)f[k];
+    };
+    auto ip = [&](int k) {
+      if (k >= n_i) throw std::invalid_argument("wh_op: missing int argument");
+      return (symint)iv[k];
+    };
+    TensorPtr r;
+    if (op == "add") r = Tensor::add(in(0), in(1));
+    else if (op == "sub") r = Tensor::sub(in(0), in(1));
+    else if (op == "mul") r = Tensor::mul(in(0), in(1));
+    else if (op == "div") r = Tensor::div(in(0), in(1));
+    else if (op == "matmul") r = Tensor::matmul(in(0), in(1));
+    else if (op == "add_scalar") r = in(0) + fp(0);
+    else if (op == "mul_scalar") r = in(0) * fp(0);
+    else if (op == "div_scalar") r = in(0) / fp(0);
+    else if (op == "rsub_scalar") r = fp(0) - in(0);
+    else if (op == "relu") r = Tensor::relu(in(0));
+    else if (op == "sigmoid") r = Tensor::sigmoid(in(0));
+    else if (op == "tanh") r = Tensor::tanh(in(0));
+    else if (op == "gelu") r = Tensor::gelu(in(0));
+    else if (op == "abs") r = Tensor::abs(in(0));
+    else if (op == "pow") r = Tensor::pow(in(0), fp(0));
+    else if (op == "exp") r = (n_f > 0) ? Tensor::exp(in(0), fp(0)) : Tensor::exp(in(0));
+    else if (op == "log") r = (n_f > 0) ? Tensor::log(in(0), fp(0)) : Tensor::log(in(0));
+    else if (op == "sum") r = Tensor::sum(in(0));
+    else if (op == "mean") r = Tensor::mean(in(0));
+    else if (op == "sum_axis") r = Tensor::sum(in(0), ip(0));
+    else if (op == "mean_axis") r = Tensor::mean(in(0), ip(0));
+    else if (op == "softmax") r = Tensor::softmax(in(0), ip(0));
+    else if (op == "logsoftmax") r = Tensor::logsoftmax(in(0), ip(0));
+    else if (op == "transpose") r = (n_i >= 2) ? Tensor::transpose(in(0), ip(0), ip(1)) : Tensor::transpose(in(0));
+    else if (op == "contiguous") r = Tensor::contiguous(in(0));
+    else if (op == "slice") r = Tensor::slice(in(0), (int64_t)ip(0), (tcapint)ip(1), (tcapint)ip(2));
+    else if (op == "row_slice") r = Tensor::slice(in(0), (int64_t)ip(0));
+    else if (op == "reshape") {
+      std::vector<symint> s(iv, iv + n_i);
+      r = Tensor::reshape(in(0), s);
+    } else if (op == "mse_loss") r = mse_loss(in(0), in(1));
+    else if (op == "bci_with_logits_loss") r = bci_with_logits_loss(in(0), in(1));
+    else throw std::invalid_argument("wh_op: unknown op '" + op + "'");
+    return put(r);
+  })
+}
+int64_t wh_cross_entropy(int64_t logits, int64_t targets) {
+  WH_TRY({
+    auto it = g_symbols.find(targets);
+    if (it == g_symbols.end()) throw std::invalid_argument("bad symbol handle");
+    return put(cross_entropy_loss(T(logits), it->second));
+  })
+}
+
+// ------------------------------------------------------------------------------- modules
+int64_t wh_module(const char *kind, const int64_t *args, int n) {
+  WH_TRY({
+    const std::string k(kind);
+    auto a = [&](int i) {
+      if (i >= n) throw std::invalid_argument("wh_module: missing argument");
+      return args[i];
+    };
+    ModulePtr m;
+    if (k == "linear") m = std::make_shared<Linear>((tcapint)a(0), (tcapint)a(1), a(2) != 0, true, DType::REAL, g_dtag);
+    else if (k == "layernorm") m = std::make_shared<LayerNorm>((tcapint)a(0), g_dtag);
+    else if (k == "embedding") m = std::make_shared<Embedding>((tcapint)a(0), (tcapint)a(1), DType::REAL, g_dtag);
+    else if (k == "posenc") m = std::make_shared<LearnedPositionalEncoding>((tcapint)a(0), (tcapint)a(1), g_dtag);
+    else if (k == "mha") {
+      // use_kv_cache = false, kv_quant_bits = 0: the deterministic configuration (SURVEY §7 hard part 6)
+      m = std::make_shared<MultiHeadAttention>((tcapint)a(0), (tcapint)a(1), 0U, 0U, g_dtag, nullptr, ZERO_R1, -1, false, 0);
+    } else if (k == "encoder") {
+      TransformerEncoderLayerPtr e = std::make_shared<TransformerEncoderLayer>((tcapint)a(0), (tcapint)a(1), (tcapint)a(2), g_dtag);
+      e->self_attn->use_kv_cache = false; // public fields; constructor defaults are kv-cache + 4-bit quant
+      e->self_attn->kv_quant_bits = 0;
+      m = e;
+    } else if (k == "gelu") m = std::make_shared<GeLU>();
+    else if (k == "relu") m = std::make_shared<ReLU>();
+    else if (k == "tanh") m = std::make_shared<Tanh>();
+    else if (k == "sigmoid") m = std::make_shared<Sigmoid>();
+    else if (k == "sequential") {
+      std::vector<ModulePtr> layers;
+      for (int i = 0; i < n; ++i) layers.push_back(M(args[i]));
+      m = std::make_shared<Sequential>(layers);
+    } else throw std::invalid_argument("wh_module: unknown kind '" + k + "'");
+    g_modules[g_next] = m;
+    return g_next++;
+  })
+}
+int wh_module_set(int64_t mh, const char *field, int64_t value) {
+  WH_TRY({
+    const std::string f(field);
+    ModulePtr m = M(mh);
+    MultiHeadAttention *att = dynamic_cast<MultiHeadAttention *>(m.get());
+    if (TransformerEncoderLayer *e = dynamic_cast<TransformerEncoderLayer *>(m.get())) att = e->self_attn.get();
+    if (f == "train") value ? m->train() : m->eval();
+    else if (f == "reset_cache") m->reset_cache();
+    else if (f == "max_kv_seq_len") m->set_max_kv_seq_len((tcapint)value);
+    else if (att && f == "use_kv_cache") att->use_kv_cache = value != 0;
+    else if (att && f == "kv_quant_bits") att->kv_quant_bits = (int)value;
+    else throw std::invalid_argument("wh_module_set: unknown field");
+    return 0;
+  })
+}
+int wh_param_count(int64_t mh) {
+  WH_TRY({ return (int)M(mh)->parameters().size(); })
+}
+// storage element count of parameter i (what wh_param_set expects)
+int64_t wh_param_size(int64_t mh, int i) {
+  WH_TRY({ return (int64_t)M(mh)->parameters().at((size_t)i)->storage->size; })
+}
+int64_t wh_param(int64_t mh, int i) {
+  WH_TRY({ return put(M(mh)->parameters().at((size_t)i)); })
+}
+// inject weights: replace the parameter's storage contents (storage order), keeping its view
+int wh_param_set(int64_t mh, int i, const float *data, uint32_t n) {
+  WH_TRY({
+    ParameterPtr p = M(mh)->parameters().at((size_t)i);
+    if (p->storage->size != n) throw std::invalid_argument("wh_param_set: element count mismatch");
+    std::vector<real1> v(data, data + n);
+    Tensor tmp(v, std::vector<tcapint>{n}, false, g_dtag);
+    p->storage = tmp.storage;
+    return 0;
+  })
+}
+int64_t wh_forward(int64_t mh, int64_t x) {
+  WH_TRY({ return put(M(mh)->forward(T(x))); })
+}
+int64_t wh_forward_symbol(int64_t mh, int64_t s) {
+  WH_TRY({
+    auto it = g_symbols.find(s);
+    if (it == g_symbols.end()) throw std::invalid_argument("bad symbol handle");
+    return put(M(mh)->forward(it->second));
+  })
+}
+// mutating helpers used by the example workloads (binary_addition_transformer.cpp:128-131)
+int wh_squeeze(int64_t h, int axis) {
+  WH_TRY({
+    T(h)->squeeze(axis);
+    return 0;
+  })
+}
+
+// ------------------------------------------------------------------------------- optimisers
+int64_t wh_adam(float lr, float b1, float b2, float eps, int64_t module) {
+  WH_TRY({
+    std::shared_ptr<Adam> o = std::make_shared<Adam>((real1)lr, (real1)b1, (real1)b2, (real1)eps);
+    o->register_parameters(M(module)->parameters());
+    g_adams[g_next] = o;
+    return g_next++;
+  })
+}
+int wh_adam_step(int64_t opt, int64_t module) {
+  WH_TRY({
+    adam_step(*g_adams.at(opt), M(module)->parameters());
+    return 0;
+  })
+}
+int wh_sgd_step(int64_t module, float lr) {
+  WH_TRY({
+    sgd_step(M(module)->parameters(), (real1)lr);
+    return 0;
+  })
+}
+int wh_zero_grad(int64_t module) {
+  WH_TRY({
+    zero_grad(M(module)->parameters());
+    return 0;
+  })
+}
+
+// One full training step on token input: forward, cross-entropy, backward, Adam, zero_grad —
+// the loop body of the reference's train_step (src/shared_api.cpp:356-424) with Adam instead of SGD.
+// Returns the loss tensor handle (read it with wh_read; reading syncs).
+int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t targets) {
+  WH_TRY({
+    ModulePtr m = M(model);
+    TensorPtr logits = m->forward(g_symbols.at(tokens));
+    TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
+    Tensor::backward(loss);
+    const std::vector<ParameterPtr> params = m->parameters();
+    adam_step(*g_adams.at(opt), params);
+    zero_grad(params);
+    m->reset_cache();
+    return put(loss);
+  })
+}
+
+double wh_wall_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // extern "C"

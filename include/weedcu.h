@@ -144,13 +144,17 @@ int weedcu_softmax_real(int log_mode, const float *a, const weedcu_view *av, int
 int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, const float *out,
                              const weedcu_view *ov, const float *dout, const weedcu_view *doutv,
                              int axis, void *stream);
-/* Fused causal attention probabilities: out = softmax(scores*scale + triu_mask(mask_val), last
- * axis) for scores[batch, Tq, Tk] with batch fastest (strides 1, batch, batch*Tq) — the
- * div + triu_fill + add + softmax chain of MultiHeadAttention::forward
- * (src/modules/multihead_attention.cpp:319-334) in one pass. key_offset = Tk - Tq for KV cache. */
+/* Fused causal attention probabilities: out = softmax(scores/divisor + triu_mask(mask_val), key
+ * axis) — the div + triu_fill + add + softmax chain of MultiHeadAttention::forward
+ * (src/modules/multihead_attention.cpp:319-334) in one pass (out may alias scores).
+ * batch_fastest 1: scores[batch, Tq, Tk] column-major (strides 1, batch, batch*Tq), the layout
+ *                  the reference's [B,H,Tq,Tk] scores tensor has;
+ * batch_fastest 0: one contiguous [Tq, Tk] column-major matrix per batch (strides 1, Tq, Tq*Tk),
+ *                  the layout the fused attention path keeps its per-head products in.
+ * Masked where q + 1 <= k (triu_fill diagonal 1, src/ops/triu_fill.cpp:48-56) when causal != 0. */
 int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq,
-                             uint32_t Tk, float inv_scale_divisor, float mask_val, int causal,
-                             void *stream);
+                             uint32_t Tk, float divisor, float mask_val, int causal,
+                             int batch_fastest, void *stream);
 /* Fused cross-entropy over logits[rows, V] (row stride rs, vocab stride vs):
  * cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34) = -mean_rows lsm[row, target].
  * fwd writes per-row log-sum-exp (lse[rows]) and the scalar loss; bwd does
@@ -169,10 +173,15 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
 int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma,
                          const float *beta, float eps, float *y, float *mean, float *rstd,
                          void *stream);
-/* dx += ..., dgamma[F] += sum_rows dy*xhat, dbeta[F] += sum_rows dy. */
+/* dx += ..., dgamma[F] += sum_rows dy*xhat, dbeta[F] += sum_rows dy.
+ * grad_mode 0 reproduces what the reference's autograd chain computes: its div node omits dout on
+ *   the denominator branch (src/tensors/tensor.cpp:1506-1521), so the variance path contributes
+ *   only  xc * (-rstd^3/F) * sum_f(xc)  (rounding-level):  dxc = g*rstd + that;  dx += dxc - mean_f(dxc).
+ * grad_mode 1 is the analytic LayerNorm gradient: dx += rstd*(g - mean_f(g) - xhat*mean_f(g*xhat)).
+ * (g = dy*gamma, xc = x-mean, xhat = xc*rstd) */
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
-                         float *dgamma, float *dbeta, void *stream);
+                         float *dgamma, float *dbeta, int grad_mode, void *stream);
 
 /* ------------------------------------------------------------------ M1-M2 embedding, mask
  * Weed::embedding_gather / embedding_scatter_add (src/ops/embedding.cpp:56-110):

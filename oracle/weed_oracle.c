@@ -291,12 +291,15 @@ int wo_softmax_grad_real(int log_mode, float *din, const wo_view *dinv, const fl
  * scores / sqrt(hd); + mask where triu_fill(mask_val, diagonal=1) (src/ops/triu_fill.cpp:41-59:
  * filled where i + 1 <= j); softmax over the last axis. scores[batch,Tq,Tk], batch fastest. */
 int wo_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq, uint32_t Tk,
-                         float divisor, float mask_val, int causal) {
+                         float divisor, float mask_val, int causal, int batch_fastest) {
   float *row = (float *)malloc(sizeof(float) * Tk);
   if (!row) return -1;
   for (uint32_t q = 0; q < Tq; ++q)
     for (uint32_t b = 0; b < batch; ++b) {
-      const uint64_t base = (uint64_t)b + (uint64_t)batch * q, st = (uint64_t)batch * Tq;
+      /* element (b, q, k): batch-fastest b + batch*(q + Tq*k); per-batch q + Tq*k + Tq*Tk*b */
+      const uint64_t base = batch_fastest ? ((uint64_t)b + (uint64_t)batch * q)
+                                          : ((uint64_t)q + (uint64_t)Tq * Tk * b);
+      const uint64_t st = batch_fastest ? (uint64_t)batch * Tq : (uint64_t)Tq;
       for (uint32_t k = 0; k < Tk; ++k) {
         float v = scores[base + k * st] / divisor;
         if (causal && Tq > 1) v = v + (((uint64_t)q + 1 <= k) ? mask_val : 0.0f);
@@ -383,28 +386,50 @@ int wo_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gam
   return 0;
 }
 
-/* Analytic backward of the same function (the reference reaches it through ~30 autograd
- * closures over layernorm.cpp:29-42; pinned against the compiled reference in
- * tests/test_oracle_cpu.py). xhat = (x-mean)*rstd, g = dy*gamma:
- *   dx += rstd * (g - mean_f(g) - xhat*mean_f(g*xhat)); dgamma += sum_r dy*xhat; dbeta += sum_r dy */
+/* Backward of LayerNorm::forward as the reference's autograd chain computes it (grad_mode 0), node
+ * by node over layernorm.cpp:29-42:
+ *   y = y0*gamma + beta        mul/add nodes (tensor.cpp:1159-1202,1105-1136): g = dy*gamma,
+ *                              dgamma += sum_rows dy*y0, dbeta += sum_rows dy
+ *   y0 = xc / d                div node (tensor.cpp:1479-1524): dxc += g/d ;  dd -= sum_f xc/d^2
+ *                              -- NOTE the denominator branch does not multiply by dout
+ *   d = (v+eps)^0.5            pow node (tensor.cpp:1540-1573): dv = 0.5*dd*d/(v+eps) = 0.5*dd/d
+ *   v = mean_f(xc*xc)          mean(axis) + mul nodes: dxc += 2*xc*dv/F
+ *   xc = x - mean_f(x)         sub + mean(axis) nodes: dx += dxc - mean_f(dxc)
+ * grad_mode 1: the analytic gradient rstd*(g - mean_f(g) - xhat*mean_f(g*xhat)).
+ * Accumulation in double: the reference's float chain is pinned against this within 1e-5 by
+ * tests/test_oracle_cpu.py (live comparison with the compiled reference). */
 int wo_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma,
-                     const float *mean, const float *rstd, float *dx, float *dgamma,
-                     float *dbeta) {
+                     const float *mean, const float *rstd, float *dx, float *dgamma, float *dbeta,
+                     int grad_mode) {
   for (uint32_t r = 0; r < rows; ++r) {
-    double sg = 0.0, sgx = 0.0;
+    const double rs = rstd[r], mu = mean[r];
+    double sg = 0.0, sgx = 0.0, sx = 0.0;
     for (uint32_t f = 0; f < F; ++f) {
       const uint64_t i = r + (uint64_t)f * rows;
-      const double xh = ((double)x[i] - mean[r]) * rstd[r];
+      const double xc = (double)x[i] - mu;
       const double g = (double)dy[i] * gamma[f];
       sg += g;
-      sgx += g * xh;
+      sgx += g * (xc * rs);
+      sx += xc;
     }
-    const double mg = sg / F, mgx = sgx / F;
-    for (uint32_t f = 0; f < F; ++f) {
-      const uint64_t i = r + (uint64_t)f * rows;
-      const double xh = ((double)x[i] - mean[r]) * rstd[r];
-      const double g = (double)dy[i] * gamma[f];
-      dx[i] += (float)(rstd[r] * (g - mg - xh * mgx));
+    if (grad_mode) {
+      const double mg = sg / F, mgx = sgx / F;
+      for (uint32_t f = 0; f < F; ++f) {
+        const uint64_t i = r + (uint64_t)f * rows;
+        const double xh = ((double)x[i] - mu) * rs;
+        const double g = (double)dy[i] * gamma[f];
+        dx[i] += (float)(rs * (g - mg - xh * mgx));
+      }
+    } else {
+      const double dd = -(rs * rs) * sx;      /* -sum_f xc/d^2 */
+      const double c = dd * rs / F;           /* 2 * (0.5*dd/d) / F */
+      const double mean_dxc = (rs * sg + c * sx) / F;
+      for (uint32_t f = 0; f < F; ++f) {
+        const uint64_t i = r + (uint64_t)f * rows;
+        const double xc = (double)x[i] - mu;
+        const double g = (double)dy[i] * gamma[f];
+        dx[i] += (float)(g * rs + c * xc - mean_dxc);
+      }
     }
   }
   for (uint32_t f = 0; f < F; ++f) {

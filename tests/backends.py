@@ -75,12 +75,23 @@ class GpuBackend:
         self.torch = torch
         self.lib = weedcu()  # raises if the extension is not built: no fallback
         self.check = check
-        self.stream = torch.cuda.current_stream().cuda_stream
+        # A real (non-legacy) stream: handle 0 would mean "library default stream" to weedcu, which
+        # is not ordered against torch's copies.
+        self.tstream = torch.cuda.Stream()
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
 
     def buf(self, arr):
         torch = self.torch
-        t = torch.from_numpy(np.ascontiguousarray(arr).copy()).cuda()
-        return Handle(t.data_ptr(), lambda: t.cpu().numpy().copy(), t)
+        with torch.cuda.stream(self.tstream):
+            t = torch.from_numpy(np.ascontiguousarray(arr).copy()).cuda()
+
+        def get():
+            with torch.cuda.stream(self.tstream):
+                out = t.cpu()
+            self.tstream.synchronize()
+            return out.numpy().copy()
+        return Handle(t.data_ptr(), get, t)
 
     def call(self, name, *args):
         fn = getattr(self.lib, "weedcu_" + name)

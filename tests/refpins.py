@@ -1,0 +1,329 @@
+"""Pins of the C oracle (oracle/weed_oracle.c) to the UNMODIFIED reference.
+
+Each pin is `fn(rng) -> (inputs: dict, run_ref(R, inputs) -> dict, run_oracle(O, inputs) -> dict)`.
+`run_ref` drives the compiled reference CPU build through harness/weed_harness.cpp
+(oracle/_ref/libweed_ref_harness.so); `run_oracle` calls the plain-C restatement.
+tests/golden/make_golden.py stores run_ref's outputs as fixtures so the comparison also runs where
+/root/reference (and oracle/_ref) do not exist.
+"""
+import ctypes as C
+
+import numpy as np
+
+from cases import F32, I32, U32, U64, cview, uni
+from weed_b200._lib import Mat, contiguous_stride, make_view
+
+PINS = []
+
+
+def pin(name, tol=1e-5):
+    def deco(fn):
+        PINS.append((name, fn, tol))
+        return fn
+    return deco
+
+
+def _mat(off, s0, s1):
+    m = Mat()
+    m.offset, m.s0, m.s1, m.batch_stride = off, s0, s1, 0
+    return m
+
+
+# ------------------------------------------------------------------------------- elementwise
+for _nm, _op in (("add", 0), ("mul", 1), ("sub", 2), ("div", 3)):
+    @pin(f"binary_{_nm}_bias_broadcast")
+    def _p(rng, nm=_nm, op=_op):
+        M, N = 7, 5
+        inp = {"a": uni(rng, M * N), "b": uni(rng, N, 0.5, 1.5)}
+
+        def ref(R, i):
+            a, b = R.tensor(i["a"], [M, N]), R.tensor(i["b"], [N])
+            return {"out": R.read(R.op(nm, [a, b]))}
+
+        def orc(O, i):
+            ha, hb, ho = O.buf(i["a"]), O.buf(i["b"]), O.buf(np.zeros(M * N, F32))
+            O.call("binary_real", I32(op), ha, cview([M, N]), hb, make_view([M, N], [0, 1]), ho, cview([M, N]))
+            return {"out": ho.get()}
+        return inp, ref, orc
+
+for _nm, _op, _p0, _lo, _hi, _fl in (("relu", 0, 0, -1, 1, ()), ("sigmoid", 1, 0, -5, 5, ()), ("tanh", 2, 0, -3, 3, ()),
+                                      ("abs", 3, 0, -1, 1, ()), ("pow", 4, 0.5, 0.1, 4, (0.5,)), ("exp", 5, 1.0, -4, 4, ()),
+                                      ("log", 6, 1.0, 0.1, 9, ()), ("gelu", 7, 0, -4, 4, ())):
+    @pin(f"unary_{_nm}_fwd_bwd", tol=2e-5)
+    def _p(rng, nm=_nm, op=_op, p0=_p0, lo=_lo, hi=_hi, fl=_fl):
+        n = 37
+        inp = {"x": uni(rng, n, lo, hi), "w": uni(rng, n)}
+
+        def ref(R, i):
+            x, w = R.tensor(i["x"], [n], True), R.tensor(i["w"], [n])
+            y = R.op(nm, [x], floats=fl)
+            R.backward(R.op("sum", [R.op("mul", [y, w])]))
+            return {"y": R.read(y), "dx": R.read(R.grad(x))}
+
+        def orc(O, i):
+            hx, hy = O.buf(i["x"]), O.buf(np.zeros(n, F32))
+            O.call("unary_real", I32(op), F32(p0), hx, cview([n]), hy, cview([n]))
+            y = hy.get()
+            if op in (4, 5, 6):  # pow/exp/log: the reference's backward is composed of mul/div nodes
+                x, w = i["x"].astype(np.float64), i["w"].astype(np.float64)
+                dx = {4: w * 0.5 * y / x, 5: w * y, 6: w / x}[op]
+                return {"y": y, "dx": dx.astype(F32)}
+            hd, hw = O.buf(np.zeros(n, F32)), O.buf(i["w"])
+            src = hy if op in (1, 2) else hx  # sigmoid/tanh grads read the forward output
+            O.call("unary_grad_real", I32(op), hd, cview([n]), src, cview([n]), hw, cview([n]))
+            return {"y": y, "dx": hd.get()}
+        return inp, ref, orc
+
+
+# ------------------------------------------------------------------------------- reductions
+@pin("sum_mean_full")
+def _p(rng):
+    n = 1000
+    inp = {"x": uni(rng, n, 0, 1)}
+
+    def ref(R, i):
+        x = R.tensor(i["x"], [n])
+        return {"sum": R.read(R.op("sum", [x])), "mean": R.read(R.op("mean", [x]))}
+
+    def orc(O, i):
+        hx, hs, hm = O.buf(i["x"]), O.buf(np.zeros(1, F32)), O.buf(np.zeros(1, F32))
+        O.call("sum_real", hx, cview([n]), F32(1.0), hs)
+        O.call("sum_real", hx, cview([n]), F32(1.0 / n), hm)
+        return {"sum": hs.get(), "mean": hm.get()}
+    return inp, ref, orc
+
+
+for _shape, _axis in (([6, 5], 0), ([6, 5], 1), ([1, 7, 4], 2), ([3, 4, 5], 2), ([3, 4, 5], 1), ([3, 4, 5], 0)):
+    @pin(f"sum_axis_{'x'.join(map(str, _shape))}_axis{_axis}_reference_order")
+    def _p(rng, shape=_shape, axis=_axis):
+        n = int(np.prod(shape))
+        inp = {"x": uni(rng, n)}
+
+        def ref(R, i):  # raw storage of the result, in storage order (what the CPU loop writes)
+            x = R.tensor(i["x"], shape)
+            return {"out": R.read_storage(R.op("sum_axis", [x], ints=[axis]))}
+
+        def orc(O, i):
+            hx, ho = O.buf(i["x"]), O.buf(np.zeros(n // shape[axis], F32))
+            O.call("reduce_real", hx, cview(shape), I32(axis), ho, I32(1))  # index_order 1 = verbatim
+            return {"out": ho.get()}
+        return inp, ref, orc
+
+
+@pin("sum_axis_backward_last_axis_B1")
+def _p(rng):  # reduce_grad where the reference is self-consistent (one non-axis dim > 1, axis last)
+    shape = [1, 6, 5]
+    n = 30
+    inp = {"x": uni(rng, n), "w": uni(rng, 6)}
+
+    def ref(R, i):
+        x, w = R.tensor(i["x"], shape, True), R.tensor(i["w"], [1, 6, 1])
+        s = R.op("sum_axis", [x], ints=[2])
+        R.backward(R.op("sum", [R.op("mul", [s, w])]))
+        return {"dx": R.read(R.grad(x))}
+
+    def orc(O, i):
+        hd, hw = O.buf(np.zeros(n, F32)), O.buf(i["w"])
+        for order in (0, 1):  # both orders agree here
+            O.call("reduce_grad_real", hd, cview(shape), hw, make_view(shape, [0, 1, 0]), I32(2), I32(order))
+        return {"dx": hd.get() / 2}
+    return inp, ref, orc
+
+
+# ------------------------------------------------------------------------------- softmax family
+for _lm, _nm in ((0, "softmax"), (1, "logsoftmax")):
+    for _shape, _axis in (([9], 0), ([6, 11], 1), ([6, 11], 0), ([2, 3, 7], 2)):
+        @pin(f"{_nm}_{'x'.join(map(str, _shape))}_axis{_axis}_fwd_bwd", tol=2e-5)
+        def _p(rng, lm=_lm, nm=_nm, shape=_shape, axis=_axis):
+            n = int(np.prod(shape))
+            inp = {"x": uni(rng, n, -4, 4), "w": uni(rng, n)}
+
+            def ref(R, i):
+                x, w = R.tensor(i["x"], shape, True), R.tensor(i["w"], shape)
+                y = R.op(nm, [x], ints=[axis])
+                R.backward(R.op("sum", [R.op("mul", [y, w])]))
+                return {"y": R.read(y), "dx": R.read(R.grad(x))}
+
+            def orc(O, i):
+                hx, hy = O.buf(i["x"]), O.buf(np.zeros(n, F32))
+                O.call("softmax_real", I32(lm), hx, cview(shape), I32(axis), hy, cview(shape))
+                hd, hw = O.buf(np.zeros(n, F32)), O.buf(i["w"])
+                O.call("softmax_grad_real", I32(lm), hd, cview(shape), hy, cview(shape), hw, cview(shape), I32(axis))
+                return {"y": hy.get(), "dx": hd.get()}
+            return inp, ref, orc
+
+
+# ------------------------------------------------------------------------------- matmul
+@pin("matmul_fwd_bwd_13x7x9", tol=2e-5)
+def _p(rng):
+    M, K, N = 13, 7, 9
+    inp = {"a": uni(rng, M * K), "b": uni(rng, K * N), "w": uni(rng, M * N)}
+
+    def ref(R, i):
+        a, b, w = R.tensor(i["a"], [M, K], True), R.tensor(i["b"], [K, N], True), R.tensor(i["w"], [M, N])
+        c = R.op("matmul", [a, b])
+        R.backward(R.op("sum", [R.op("mul", [c, w])]))
+        return {"c": R.read(c), "da": R.read(R.grad(a)), "db": R.read(R.grad(b))}
+
+    def orc(O, i):
+        ha, hb, hw = O.buf(i["a"]), O.buf(i["b"]), O.buf(i["w"])
+        hc, hda, hdb = O.buf(np.zeros(M * N, F32)), O.buf(np.zeros(M * K, F32)), O.buf(np.zeros(K * N, F32))
+        O.call("matmul_real", ha, _mat(0, 1, M), hb, _mat(0, 1, K), hc, _mat(0, 1, M), U32(M), U32(K), U32(N), U32(1), I32(0))
+        # dA = dC * B^T (B^T view strides (K,1)); dB = A^T * dC (A^T view strides (M,1)); both accumulate
+        O.call("matmul_real", hw, _mat(0, 1, M), hb, _mat(0, K, 1), hda, _mat(0, 1, M), U32(M), U32(N), U32(K), U32(1), I32(1))
+        O.call("matmul_real", ha, _mat(0, M, 1), hw, _mat(0, 1, M), hdb, _mat(0, 1, K), U32(K), U32(M), U32(N), U32(1), I32(1))
+        return {"c": hc.get(), "da": hda.get(), "db": hdb.get()}
+    return inp, ref, orc
+
+
+# ------------------------------------------------------------------------------- LayerNorm (B = 1)
+@pin("layernorm_module_fwd_bwd_1x9x16", tol=3e-5)
+def _p(rng):
+    T, F = 9, 16
+    inp = {"x": uni(rng, T * F, -2, 2), "w": uni(rng, T * F), "gamma": uni(rng, F, 0.5, 1.5), "beta": uni(rng, F)}
+
+    def ref(R, i):
+        ln = R.module("layernorm", F)
+        R.param_set(ln, 0, i["gamma"])
+        R.param_set(ln, 1, i["beta"])
+        x, w = R.tensor(i["x"], [1, T, F], True), R.tensor(i["w"], [1, T, F])
+        y = R.forward(ln, x)
+        R.backward(R.op("sum", [R.op("mul", [y, w])]))
+        return {"y": R.read(y), "dx": R.read(R.grad(x)), "dgamma": R.read_storage(R.grad(R.param(ln, 0))),
+                "dbeta": R.read_storage(R.grad(R.param(ln, 1)))}
+
+    def orc(O, i):
+        hx, hg, hb = O.buf(i["x"]), O.buf(i["gamma"]), O.buf(i["beta"])
+        hy, hm, hr = O.buf(np.zeros(T * F, F32)), O.buf(np.zeros(T, F32)), O.buf(np.zeros(T, F32))
+        eps = F32(np.finfo(np.float32).eps / 4)
+        O.call("layernorm_fwd", hx, U32(T), U32(F), hg, hb, eps, hy, hm, hr)
+        hw, hdx, hdg, hdb = O.buf(i["w"]), O.buf(np.zeros(T * F, F32)), O.buf(np.zeros(F, F32)), O.buf(np.zeros(F, F32))
+        O.call("layernorm_bwd", hx, hw, U32(T), U32(F), hg, hm, hr, hdx, hdg, hdb, I32(0))
+        return {"y": hy.get(), "dx": hdx.get(), "dgamma": hdg.get(), "dbeta": hdb.get()}
+    return inp, ref, orc
+
+
+# ------------------------------------------------------------------------------- optimisers
+def _opt_pin(kind):
+    def _p(rng):
+        IN, OUT, B = 5, 4, 6
+        inp = {"w": uni(rng, IN * OUT), "b": uni(rng, OUT), "x": uni(rng, B * IN), "t": uni(rng, B * OUT)}
+
+        def ref(R, i):
+            lin = R.module("linear", IN, OUT, 1)
+            R.param_set(lin, 0, i["w"])
+            R.param_set(lin, 1, i["b"])
+            opt = R.adam(lin, 0.01) if kind == "adam" else None
+            x, t = R.tensor(i["x"], [B, IN]), R.tensor(i["t"], [B, OUT])
+            out = {}
+            for step in range(3):
+                loss = R.op("mse_loss", [R.forward(lin, x), t])
+                R.backward(loss)
+                out[f"gw{step}"] = R.read_storage(R.grad(R.param(lin, 0)))
+                out[f"gb{step}"] = R.read_storage(R.grad(R.param(lin, 1)))
+                R.adam_step(opt, lin) if kind == "adam" else R.sgd_step(lin, 0.05)
+                out[f"w{step}"] = R.read_storage(R.param(lin, 0))
+                out[f"b{step}"] = R.read_storage(R.param(lin, 1))
+                R.zero_grad(lin)
+            return out
+
+        def orc(O, i, ref_out):
+            # apply the oracle's optimiser to the reference's own gradients, step by step
+            out = {k: v for k, v in ref_out.items() if k.startswith("g")}
+            hw, hb = O.buf(i["w"]), O.buf(i["b"])
+            st = {n: (O.buf(np.zeros(sz, F32)), O.buf(np.zeros(sz, F32))) for n, sz in (("w", IN * OUT), ("b", OUT))}
+            b1, b2 = F32(0.9), F32(0.999)
+            for step in range(3):
+                for n, hp in (("w", hw), ("b", hb)):
+                    g = O.buf(ref_out[f"g{n}{step}"])
+                    sz = IN * OUT if n == "w" else OUT
+                    if kind == "adam":
+                        bc1 = F32(1.0) - F32(np.power(b1, F32(step + 1), dtype=F32))
+                        bc2 = F32(1.0) - F32(np.power(b2, F32(step + 1), dtype=F32))
+                        O.call("adam_step", hp, g, st[n][0], st[n][1], U64(sz), F32(0.01), b1, b2, F32(1e-8), bc1, bc2, F32(1.0))
+                    else:
+                        # Reference quirk (include/autograd/sgd.hpp:29-35): the bias Parameter was
+                        # mutated by match_shape to [B, OUT] with strides [0, 1] (tensor.cpp:306-332),
+                        # tmp is matched to that shape, and sub_in_place walks all B*OUT flat indices,
+                        # so each bias element is updated B times. Weights are updated once.
+                        times = float(B) if n == "b" else 1.0
+                        O.call("sgd_step", hp, g, U64(sz), F32(0.05), F32(times))
+                    out[f"{n}{step}"] = hp.get()
+            return out
+        return inp, ref, orc
+    return _p
+
+
+pin("adam_3_steps_on_linear")(_opt_pin("adam"))
+pin("sgd_3_steps_on_linear")(_opt_pin("sgd"))
+
+
+# ------------------------------------------------------------------------------- embedding + CE
+@pin("embedding_fwd_bwd_duplicates")
+def _p(rng):
+    # rank-1 indices: with a leading extent-1 dim the reference reads indices.stride[0] == 0 and
+    # out.stride[0] == 0 (src/ops/embedding.cpp:66-75) and gathers token 0 into slot 0 only.
+    V, D, n = 6, 5, 11
+    inp = {"W": uni(rng, V * D), "idx": rng.integers(0, V, size=n).astype(np.int32), "w": uni(rng, n * D)}
+
+    def ref(R, i):
+        emb = R.module("embedding", V, D)
+        R.param_set(emb, 0, i["W"])
+        s = R.symbol(i["idx"], [n])
+        y = R.forward_symbol(emb, s)
+        R.backward(R.op("sum", [R.op("mul", [y, R.tensor(i["w"], [n, D])])]))
+        return {"y": R.read(y), "dW": R.read_storage(R.grad(R.param(emb, 0)))}
+
+    def orc(O, i):
+        hW, hi, hy = O.buf(i["W"]), O.buf(i["idx"]), O.buf(np.zeros(n * D, F32))
+        O.call("embedding_gather", hi, U64(0), U32(1), U32(n), hW, U64(0), U32(1), U32(V), U32(D), hy, U64(0), U32(1), U32(n))
+        hd, hw = O.buf(np.zeros(V * D, F32)), O.buf(i["w"])
+        O.call("embedding_scatter_add", hd, U64(0), U32(1), U32(V), hi, U64(0), U32(1), U32(n), U32(D), hw, U64(0), U32(1), U32(n))
+        return {"y": hy.get(), "dW": hd.get()}
+    return inp, ref, orc
+
+
+@pin("cross_entropy_loss_value_1x7x13", tol=2e-5)
+def _p(rng):
+    # Loss VALUE only. The reference's gradient through cross_entropy_loss is identically zero:
+    # Tensor::reshape (tensor.hpp:336-345) returns a copy whose rank differs from its grad, so
+    # make_gradient() (tensor.cpp:83-113) gives the copy a fresh grad and the logsoftmax node never
+    # sees it (measured: dlogits == 0). The oracle's backward is the analytic one and is checked
+    # against numpy in test_oracle_cpu.py instead.
+    T, V = 7, 13
+    inp = {"logits": uni(rng, T * V, -3, 3), "tg": rng.integers(0, V, size=T).astype(np.int32)}
+
+    def ref(R, i):
+        lg = R.tensor(i["logits"], [1, T, V], True)
+        return {"loss": R.read(R.cross_entropy(lg, R.symbol(i["tg"], [T])))}
+
+    def orc(O, i):
+        hl, ht = O.buf(i["logits"]), O.buf(i["tg"])
+        hlse, hloss = O.buf(np.zeros(T, F32)), O.buf(np.zeros(1, F32))
+        O.call("cross_entropy_fwd", hl, U64(0), U32(T), U32(V), U32(1), U32(T), ht, hlse, hloss)
+        return {"loss": hloss.get()}
+    return inp, ref, orc
+
+
+@pin("attention_probabilities_chain", tol=2e-5)
+def _p(rng):  # scores / sqrt(hd) + triu mask -> softmax, composed from the reference's own ops
+    BH, Tq, hd = 3, 6, 4
+    inp = {"s": uni(rng, BH * Tq * Tq, -3, 3)}
+
+    def ref(R, i):
+        s = R.tensor(i["s"], [BH, Tq, Tq])
+        mask = np.zeros((Tq, Tq), np.float32)  # col-major [i + j*Tq]; filled where i + 1 <= j
+        for ii in range(Tq):
+            for jj in range(Tq):
+                if ii + 1 <= jj:
+                    mask[jj, ii] = -1.701411835e38
+        m = R.tensor(mask.ravel(), [Tq, Tq])
+        sc = R.op("div_scalar", [s], floats=[float(np.sqrt(np.float32(hd)))])
+        return {"p": R.read(R.op("softmax", [R.op("add", [sc, m])], ints=[-1]))}
+
+    def orc(O, i):
+        hs, ho = O.buf(i["s"]), O.buf(np.zeros(BH * Tq * Tq, F32))
+        O.call("attn_softmax_real", hs, ho, U32(BH), U32(Tq), U32(Tq), F32(np.sqrt(np.float32(hd))), F32(-1.701411835e38),
+               I32(1), I32(1))
+        return {"p": ho.get()}
+    return inp, ref, orc

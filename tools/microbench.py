@@ -146,7 +146,7 @@ def bench_ew(results, peaks):
     ms = timeit(lambda i: call("softmax_real", I32(0), P(X[i]), v4, I32(3), P(Y[i]), v4), 2, iters=10)
     rec("softmax_fwd_8x12x1024x1024", ms, 8 * n)
     ms = timeit(lambda i: call("attn_softmax_real", P(X[i]), P(Y[i]), U32(96), U32(1024), U32(1024), F(8.0),
-                               F(-1.7e38), I32(1)), 2, iters=10)
+                               F(-1.7e38), I32(1), I32(1)), 2, iters=10)
     rec("attn_softmax_fused_96x1024x1024", ms, 8 * n)
     DI = bufs(n, 2)
     ms = timeit(lambda i: call("softmax_grad_real", I32(0), P(DI[i]), v4, P(Y[i]), v4, P(X[i]), v4, I32(3)), 2, iters=10)
@@ -176,7 +176,7 @@ def bench_ew(results, peaks):
                                    P(mu), P(rs)), k)
         rec(f"layernorm_fwd_8192x{Fd}", ms, 8 * n)
         ms = timeit(lambda i: call("layernorm_bwd", P(X[i]), P(DY[i]), U32(rows), U32(Fd), P(g), P(mu), P(rs),
-                                   P(DX[i]), P(dg), P(db)), k)
+                                   P(DX[i]), P(dg), P(db), I32(0)), k)
         rec(f"layernorm_bwd_8192x{Fd}", ms, 16 * n)
         del X, Y, DY, DX
     # --- axis reductions
@@ -271,7 +271,10 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.json"))
     args = ap.parse_args()
     lib = weedcu()
-    STREAM = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()  # non-legacy stream: events, allocations and kernels all ordered on it
+    torch.cuda.set_stream(ts)
+    STREAM = ts.cuda_stream
+    assert STREAM != 0
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(NT)
 layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
                      const float *__restrict__ gamma, const float *__restrict__ mean,
                      const float *__restrict__ rstd, float *dx, float *__restrict__ part_g,
-                     float *__restrict__ part_b) {
+                     float *__restrict__ part_b, int grad_mode) {
   constexpr int BY = NT / RT;
   extern __shared__ float tile[]; // STAGED: xhat [F][RT] then dy [F][RT]
   __shared__ float red_a[BY][RT + 1];
@@ -98,7 +98,7 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, 
     }
     const float g = fv ? d * gamma[f] : 0.0f;
     sg += g;
-    sgx += g * xh;
+    sgx += grad_mode ? g * xh : xh; // mode 0 needs sum_f(xc) = sum_f(xhat)/rstd instead
     // column partials over the RT rows of this tile (lanes tx of one ty share f)
     float cg = d * xh, cb = d;
 #pragma unroll
@@ -120,7 +120,21 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, 
     sg += red_a[k][tx];
     sgx += red_b[k][tx];
   }
-  const float mg = sg / (float)F, mgx = sgx / (float)F;
+  // mode 1 (analytic):   dx += rs*(g - mean(g) - xh*mean(g*xh))
+  // mode 0 (reference chain, see weedcu.h): dxc = g*rs + c*xc with c = -rs^3*sum(xc)/F;
+  //                         dx += dxc - mean(dxc).  In xhat terms xc = xh/rs, sum(xc) = sgx/rs.
+  float k_g, k_x, k_0;
+  if (grad_mode) {
+    k_g = rs;
+    k_x = -rs * (sgx / (float)F);
+    k_0 = -rs * (sg / (float)F);
+  } else {
+    const float sx = (rs != 0.0f) ? sgx / rs : 0.0f;
+    const float c = -(rs * rs * rs) * sx / (float)F;
+    k_g = rs;
+    k_x = (rs != 0.0f) ? c / rs : 0.0f;
+    k_0 = -((rs * sg + c * sx) / (float)F);
+  }
   if (live)
     for (uint32_t f = ty; f < F; f += BY) {
       float xh, d;
@@ -132,7 +146,7 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, 
         d = dy[r + (uint64_t)f * rows];
       }
       const float g = d * gamma[f];
-      dx[r + (uint64_t)f * rows] += rs * ((g - mg) - xh * mgx);
+      dx[r + (uint64_t)f * rows] += (k_g * g + k_x * xh) + k_0;
     }
 }
 
@@ -211,15 +225,15 @@ static int ln_fwd_launch(const float *x, uint32_t rows, uint32_t F, const float 
 template <int RT, int NT>
 static int ln_bwd_launch(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
-                         float *pg, float *pb, cudaStream_t st) {
+                         float *pg, float *pb, int grad_mode, cudaStream_t st) {
   const unsigned grid = (rows + RT - 1) / RT;
   const size_t bytes = 2 * (size_t)F * RT * sizeof(float);
   if (bytes <= kLnMaxTileBytes) {
     auto k = layernorm_bwd_kernel<RT, NT, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLnMaxTileBytes);
-    k<<<grid, NT, bytes, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb);
+    k<<<grid, NT, bytes, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode);
   } else {
-    layernorm_bwd_kernel<RT, NT, false><<<grid, NT, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb);
+    layernorm_bwd_kernel<RT, NT, false><<<grid, NT, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode);
   }
   return after_launch();
 }
@@ -249,7 +263,7 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
 
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
-                         float *dgamma, float *dbeta, void *stream) {
+                         float *dgamma, float *dbeta, int grad_mode, void *stream) {
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !rows || !F) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
   const int rt = pick_rt(rows);
@@ -259,9 +273,9 @@ int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_
   float *pg = part, *pb = part + (size_t)nblocks * F;
   int rc;
   switch (rt) {
-  case 32: rc = ln_bwd_launch<32, 512>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
-  case 16: rc = ln_bwd_launch<16, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
-  default: rc = ln_bwd_launch<8, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, st); break;
+  case 32: rc = ln_bwd_launch<32, 512>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, st); break;
+  case 16: rc = ln_bwd_launch<16, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, st); break;
+  default: rc = ln_bwd_launch<8, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, st); break;
   }
   if (rc == 0 && (dgamma || dbeta)) {
     layernorm_param_reduce_kernel<<<(F + 255) / 256, 256, 0, st>>>(pg, pb, nblocks, F, dgamma, dbeta);

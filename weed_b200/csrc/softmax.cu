@@ -40,7 +40,7 @@ struct AttnLoad {
 // a[inner, L, outer] canonical contiguous; rows = inner (per outer slab).
 template <bool LOG, int BY, bool STAGED, class LD>
 __global__ void __launch_bounds__(kRT * BY)
-softmax_strided_fwd(const float *__restrict__ a, float *__restrict__ out, uint32_t inner, uint32_t L,
+softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
                     LD ld) {
   extern __shared__ float tile[]; // [L][kRT] when STAGED
   __shared__ float red_m[BY][kRT + 1];
@@ -449,12 +449,19 @@ int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, 
 }
 
 int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq,
-                             uint32_t Tk, float divisor, float mask_val, int causal, void *stream) {
+                             uint32_t Tk, float divisor, float mask_val, int causal, int batch_fastest,
+                             void *stream) {
   if (!scores || !out || !batch || !Tq || !Tk) return WEEDCU_EINVAL;
-  const uint64_t inner = (uint64_t)batch * Tq;
-  if (inner > 0xffffffffull) return WEEDCU_EINVAL;
-  AttnLoad ld = {batch, divisor, mask_val, (causal && Tq > 1) ? 1 : 0};
-  return launch_strided_fwd<false>(scores, out, (uint32_t)inner, Tk, 1, ld, resolve_stream(stream));
+  const int do_mask = (causal && Tq > 1) ? 1 : 0;
+  if (batch_fastest) {
+    const uint64_t inner = (uint64_t)batch * Tq;
+    if (inner > 0xffffffffull) return WEEDCU_EINVAL;
+    AttnLoad ld = {batch, divisor, mask_val, do_mask};
+    return launch_strided_fwd<false>(scores, out, (uint32_t)inner, Tk, 1, ld, resolve_stream(stream));
+  }
+  if (batch > 65535) return WEEDCU_EINVAL;
+  AttnLoad ld = {1u, divisor, mask_val, do_mask};
+  return launch_strided_fwd<false>(scores, out, Tq, Tk, batch, ld, resolve_stream(stream));
 }
 
 int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,

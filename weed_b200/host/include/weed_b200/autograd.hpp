@@ -1,0 +1,32 @@
+// autograd.hpp — optimisers and losses (reference include/autograd/*.hpp), same signatures.
+// With backend_config().fused (default) adam_step / sgd_step / cross_entropy_loss issue one fused
+// kernel per parameter / per loss; with it off they compose the same tensor ops the reference does.
+#pragma once
+#include "weed_b200/ops.hpp"
+
+namespace Weed {
+struct AdamState {
+  TensorPtr m; // first moment
+  TensorPtr v; // second moment
+};
+struct Adam {
+  real1 lr, beta1, beta2, eps;
+  uint64_t t;
+  std::unordered_map<ParameterPtr, AdamState> state;
+  Adam(real1 l, real1 b1 = ADAM_BETA1_DEFAULT, real1 b2 = ADAM_BETA2_DEFAULT, real1 e = ADAM_EPSILON_DEFAULT)
+      : lr(l), beta1(b1), beta2(b2), eps(e), t(0U) {}
+  void register_parameter(ParameterPtr p);
+  void register_parameters(const std::vector<ParameterPtr> &pv) {
+    for (const ParameterPtr &p : pv) register_parameter(p);
+  }
+};
+void adam_step(Adam &opt, const std::vector<ParameterPtr> &params);
+void sgd_step(const std::vector<ParameterPtr> &params, real1 lr);
+void zero_grad(const std::vector<ParameterPtr> &params);
+
+TensorPtr mse_loss(TensorPtr y_pred, TensorPtr y_true);
+TensorPtr bci_with_logits_loss(TensorPtr logits, TensorPtr y_true);
+// logits [B, T, V] (the reference assumes B == 1, cross_entropy_loss.hpp:22-27; any B works here:
+// rows = B*T), targets B*T token ids
+TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets);
+} // namespace Weed

@@ -1,0 +1,197 @@
+// modules.hpp — the transformer / MLP module set on the hot path (reference include/modules/*.hpp),
+// same class names, public fields, constructor argument order and forward() semantics.
+#pragma once
+#include "weed_b200/autograd.hpp"
+
+namespace Weed {
+enum ModuleType {
+  NONE_MODULE_TYPE = 0, SEQUENTIAL_T = 1, LINEAR_T = 2, RELU_T = 3, SIGMOID_T = 4, TANH_T = 5, DROPOUT_T = 6,
+  LAYERNORM_T = 7, EMBEDDING_T = 8, GRU_T = 9, LSTM_T = 10, MIGRATE_CPU_T = 11, MIGRATE_GPU_T = 12, SOFTMAX_T = 13,
+  LOGSOFTMAX_T = 14, QRACK_NEURON_T = 15, QRACK_NEURON_LAYER_T = 16, MULTIHEAD_ATTENTION_T = 17,
+  TRANSFORMER_ENCODER_LAYER_T = 18, GELU_T = 19, MEAN_T = 20, MIN_T = 21, MAX_T = 22, RESHAPE_T = 23, VARIANCE_T = 24,
+  STDDEV_T = 25, POSITIONAL_ENCODING_T = 26, MEAN_CENTER_T = 27, FLATTEN_T = 28, LEARNED_POSITIONAL_ENCODING_T = 29,
+  RMS_NORM_T = 30, ROPE_T = 31, SWIGLU_T = 32, QWEN_DECODER_LAYER_T = 33
+};
+
+struct Module;
+typedef std::shared_ptr<Module> ModulePtr;
+struct Module {
+  ModuleType mtype;
+  Module(ModuleType t) : mtype(t) {}
+  virtual ~Module() {}
+  virtual TensorPtr forward(const TensorPtr) = 0;
+  virtual TensorPtr forward(const SymbolTensorPtr) {
+    throw std::domain_error("Embedding::forward(x) takes a Tensor, not a SymbolTensor!");
+  }
+  virtual std::vector<ParameterPtr> parameters() { return std::vector<ParameterPtr>(); }
+  virtual void train() {
+    for (const auto &p : parameters()) p->train();
+  }
+  virtual void eval() {
+    for (const auto &p : parameters()) p->eval();
+  }
+  virtual void migrate_cpu() {}
+  virtual void migrate_gpu() {}
+  virtual void set_max_kv_seq_len(tcapint) {}
+  virtual void reset_cache() {}
+};
+
+#define WEED_UNARY_MODULE(Name, TypeTag, expr)                                                     \
+  struct Name : public Module {                                                                    \
+    Name() : Module(TypeTag) {}                                                                    \
+    TensorPtr forward(const TensorPtr x) override { return expr; }                                 \
+  };                                                                                               \
+  typedef std::shared_ptr<Name> Name##Ptr;
+WEED_UNARY_MODULE(ReLU, RELU_T, Tensor::relu(x))
+WEED_UNARY_MODULE(Sigmoid, SIGMOID_T, Tensor::sigmoid(x))
+WEED_UNARY_MODULE(Tanh, TANH_T, Tensor::tanh(x))
+WEED_UNARY_MODULE(GeLU, GELU_T, Tensor::gelu(x))
+#undef WEED_UNARY_MODULE
+
+struct Softmax : public Module {
+  symint axis;
+  Softmax(const symint &a = -1) : Module(SOFTMAX_T), axis(a) {}
+  TensorPtr forward(const TensorPtr x) override { return Tensor::softmax(x, axis); }
+};
+struct LogSoftmax : public Module {
+  symint axis;
+  LogSoftmax(const symint &a = -1) : Module(LOGSOFTMAX_T), axis(a) {}
+  TensorPtr forward(const TensorPtr x) override { return Tensor::logsoftmax(x, axis); }
+};
+
+// parameter migration helpers (reference include/modules/migrate_gpu.hpp / migrate_cpu.hpp)
+struct MigrateGpu : public Module {
+  MigrateGpu() : Module(MIGRATE_GPU_T) {}
+  TensorPtr forward(const TensorPtr x) override { return x->cast(DeviceTag::GPU); }
+  ParameterPtr pforward(const ParameterPtr p);
+};
+struct MigrateCpu : public Module {
+  MigrateCpu() : Module(MIGRATE_CPU_T) {}
+  TensorPtr forward(const TensorPtr x) override { return x->cast(DeviceTag::CPU); }
+  ParameterPtr pforward(const ParameterPtr p);
+};
+
+struct Linear : public Module {
+  tcapint in_features, out_features;
+  ParameterPtr weight; // (in_features, out_features), column-major
+  ParameterPtr bias;   // (out_features) or null
+  Linear() : Module(LINEAR_T) {}
+  Linear(tcapint in_f, tcapint out_f, bool use_bias = true, bool init_rand = true, DType dtype = DType::REAL,
+         DeviceTag device = DeviceTag::DEFAULT_DEVICE, int64_t device_id = -1);
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+  TensorPtr forward(const TensorPtr x) override;
+  std::vector<ParameterPtr> parameters() override;
+};
+typedef std::shared_ptr<Linear> LinearPtr;
+
+struct LayerNorm : Module {
+  tcapint features;
+  real1 eps;
+  ParameterPtr gamma, beta; // shape [1, 1, features]
+  LayerNorm() : Module(LAYERNORM_T) {}
+  LayerNorm(const tcapint &f, const DeviceTag &dtag = DeviceTag::DEFAULT_DEVICE, const real1 &e = FP_NORM_EPSILON,
+            const int64_t &did = -1);
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+  TensorPtr forward(const TensorPtr x) override;
+  std::vector<ParameterPtr> parameters() override { return {gamma, beta}; }
+};
+typedef std::shared_ptr<LayerNorm> LayerNormPtr;
+
+struct Embedding : public Module {
+  tcapint num_embeddings, embedding_dim;
+  ParameterPtr weight; // [vocab, dim] strides (1, vocab)
+  Embedding() : Module(EMBEDDING_T) {}
+  Embedding(const tcapint &vocab, const tcapint &dim, const DType &dtype = DType::REAL,
+            const DeviceTag &dtag = DeviceTag::DEFAULT_DEVICE, int64_t did = -1);
+  TensorPtr forward(const TensorPtr) override { throw std::domain_error("Embedding::forward(x) takes a SymbolTensor, not a Tensor!"); }
+  TensorPtr forward(const SymbolTensorPtr t) override;
+  std::vector<ParameterPtr> parameters() override { return {weight}; }
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+};
+typedef std::shared_ptr<Embedding> EmbeddingPtr;
+
+struct LearnedPositionalEncoding : public Module {
+  tcapint max_len, d_model;
+  ParameterPtr pos_encoding; // (1, max_len, d_model)
+  LearnedPositionalEncoding() : Module(LEARNED_POSITIONAL_ENCODING_T) {}
+  LearnedPositionalEncoding(const tcapint &max_len_, const tcapint &d_model_, const DeviceTag &dtag = DEFAULT_DEVICE);
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+  TensorPtr forward(const TensorPtr x) override;
+  std::vector<ParameterPtr> parameters() override { return {pos_encoding}; }
+};
+typedef std::shared_ptr<LearnedPositionalEncoding> LearnedPositionalEncodingPtr;
+
+struct RoPE; // outside SURVEY §8; the constructor argument is kept for signature compatibility
+typedef std::shared_ptr<RoPE> RoPEPtr;
+
+struct MultiHeadAttention : public Module {
+  symint d_model, num_heads, num_kv_heads, head_dim;
+  real1_f mask_val;
+  LinearPtr W_q, W_k, W_v, W_o;
+  RoPEPtr rope;
+  bool use_kv_cache;
+  TensorPtr k_cache, v_cache; // float KV cache (kv_quant_bits == 0), [B, H_kv, max_seq_len, hd]
+  tcapint cache_len = 0U;
+  tcapint max_seq_len = 0U;
+  int kv_quant_bits = 0;
+  std::vector<ParameterPtr> param_vector;
+
+  MultiHeadAttention()
+      : Module(MULTIHEAD_ATTENTION_T), d_model(0), num_heads(0), num_kv_heads(0), head_dim(0), mask_val(ZERO_R1),
+        use_kv_cache(false) {}
+  MultiHeadAttention(tcapint d_model_, tcapint num_heads_, tcapint num_kv_heads_ = 0, tcapint head_dim_ = 0U,
+                     DeviceTag dtag = DEFAULT_DEVICE, RoPEPtr r = nullptr, real1_f mask_val_ = ZERO_R1, const int64_t did = -1,
+                     const bool _use_kv_cache = true, int kv_quant_bits_ = 4);
+  std::vector<ParameterPtr> parameters() override { return param_vector; }
+  void train() override;
+  void eval() override;
+  void set_max_kv_seq_len(tcapint m) override { max_seq_len = m; }
+  void reset_cache() override;
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+  TensorPtr forward(const TensorPtr x) override;
+};
+typedef std::shared_ptr<MultiHeadAttention> MultiHeadAttentionPtr;
+
+struct TransformerEncoderLayer : public Module {
+  tcapint d_model, d_ff, num_heads;
+  MultiHeadAttentionPtr self_attn;
+  LinearPtr ff1, ff2;
+  LayerNormPtr norm1, norm2;
+  ModulePtr activation;
+  std::vector<ParameterPtr> param_vector;
+  TransformerEncoderLayer() : Module(TRANSFORMER_ENCODER_LAYER_T) {}
+  TransformerEncoderLayer(const tcapint &d_model_, const tcapint &num_heads_, const tcapint &d_ff_,
+                          const DeviceTag &dtag = DEFAULT_DEVICE, const ActivationFunctionType &afn = GELU_FN,
+                          const int64_t &did = -1);
+  std::vector<ParameterPtr> parameters() override { return param_vector; }
+  void train() override;
+  void eval() override;
+  void migrate_cpu() override;
+  void migrate_gpu() override;
+  void set_max_kv_seq_len(tcapint m) override { self_attn->set_max_kv_seq_len(m); }
+  void reset_cache() override { self_attn->reset_cache(); }
+  TensorPtr forward(const TensorPtr x) override;
+};
+typedef std::shared_ptr<TransformerEncoderLayer> TransformerEncoderLayerPtr;
+
+struct Sequential : public Module {
+  std::vector<ModulePtr> layers;
+  std::vector<ParameterPtr> param_vector;
+  Sequential(const std::vector<ModulePtr> &l);
+  void train() override { for (const ModulePtr &m : layers) m->train(); }
+  void eval() override { for (const ModulePtr &m : layers) m->eval(); }
+  void migrate_cpu() override { for (const ModulePtr &m : layers) m->migrate_cpu(); }
+  void migrate_gpu() override { for (const ModulePtr &m : layers) m->migrate_gpu(); }
+  void set_max_kv_seq_len(tcapint m) override { for (const ModulePtr &md : layers) md->set_max_kv_seq_len(m); }
+  void reset_cache() override { for (const ModulePtr &m : layers) m->reset_cache(); }
+  TensorPtr forward(const TensorPtr x) override;
+  TensorPtr forward(const SymbolTensorPtr x) override;
+  std::vector<ParameterPtr> parameters() override { return param_vector; }
+};
+typedef std::shared_ptr<Sequential> SequentialPtr;
+} // namespace Weed

@@ -1,0 +1,60 @@
+// ops.hpp — Weed's tensor-op entry points (reference include/ops/*.hpp), same names and argument
+// order. Each validates on the host with the reference's exception types, then, for GPU tensors,
+// issues ONE typed call into the extern "C" layer (include/weedcu.h). The reference packs a
+// 12-slot `tcapint` vector for RequestKernel (e.g. src/ops/commuting.cpp:37-50) — an OpenCL
+// artefact this backend does not keep. There is no CPU compute path here: ops on CPU-tagged
+// tensors throw std::domain_error (upstream Weed's own cpu_* functions serve that device).
+#pragma once
+#include "weed_b200/core.hpp"
+
+namespace Weed {
+void validate_all_same_device(const std::vector<const BaseTensor *> &t, const std::string cls);
+
+void add(const Tensor &a, const Tensor &b, Tensor &out);
+void mul(const Tensor &a, const Tensor &b, Tensor &out);
+void sub(const Tensor &a, const Tensor &b, Tensor &out);
+void div(const Tensor &a, const Tensor &b, Tensor &out);
+void add_in_place(Tensor &a, const Tensor &b);
+void sub_in_place(Tensor &a, const Tensor &b);
+void copy_broadcast(Tensor &a, const Tensor &b);
+
+void relu(const Tensor &a, Tensor &out);
+void relu_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void sigmoid(const Tensor &a, Tensor &out);
+void sigmoid_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void tanh(const Tensor &a, Tensor &out);
+void tanh_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void sin(const Tensor &a, Tensor &out);
+void sin_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void cos(const Tensor &a, Tensor &out);
+void cos_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void abs(const Tensor &a, Tensor &out);
+void abs_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+void pow(const Tensor &a, const real1 &p, Tensor &out);
+void exp(const Tensor &a, const real1 &b, Tensor &out);
+void log(const Tensor &a, const real1 &b, Tensor &out);
+// fused additions (no reference op of that name; behind Tensor::gelu, tensor.cpp:841-851)
+void gelu(const Tensor &a, Tensor &out);
+void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout);
+
+void sum(const Tensor &a, Tensor &out);
+void mean(const Tensor &a, Tensor &out);
+void reduce(const tcapint &index, const Tensor &a, Tensor &out);
+void reduce_grad(const tcapint &index, Tensor &din, const Tensor &a, const Tensor &dout);
+
+void softmax(const tcapint &index, const Tensor &a, Tensor &out);
+void softmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout);
+void logsoftmax(const tcapint &index, const Tensor &a, Tensor &out);
+void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout);
+
+void matmul(const Tensor &a, const Tensor &b, Tensor &out);
+// C (+)= A*B with the accumulate folded into the GEMM epilogue (make_matmul_node's tmp + add_in_place)
+void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out);
+// `batch` independent products over 3-D views [batch, M, K] x [batch, K, N] -> [batch, M, N]
+// (the host loop of Tensor::matmul, tensor.cpp:1259-1269, as one strided-batched launch)
+void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3);
+
+void embedding_gather(const SymbolTensor &indices, const Tensor &weight, Tensor &out);
+void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor &dout);
+void triu_fill(Tensor &a, const complex &val, const tcapint diagonal = 1);
+} // namespace Weed

@@ -1,0 +1,129 @@
+// autograd.cpp — optimisers and losses on the CUDA device.
+// Reference: include/autograd/adam.hpp:23-106, sgd.hpp:23-37, zero_grad.hpp:21-25, mse_loss.hpp,
+// bci_with_logits_loss.hpp:20-23, cross_entropy_loss.hpp:21-34.
+#include "weed_b200/autograd.hpp"
+
+#include <cmath>
+
+namespace Weed {
+namespace {
+// A tensor whose view is exactly its whole storage in storage order (so a flat kernel may walk it)
+bool covers_storage(const Tensor &t) {
+  if (t.offset) return false;
+  tcapint expect = 1U;
+  for (size_t i = 0U; i < t.shape.size(); ++i) {
+    if (t.shape[i] == 1U) continue;
+    if (t.stride[i] != expect) return false;
+    expect *= t.shape[i];
+  }
+  return expect == t.storage->size;
+}
+// Parameters are mutated by match_shape (a bias becomes [B,T,F] with strides [0,0,1], SURVEY §7
+// hard part 5(ii)), so flat kernels go by storage: n = storage->size, gradient reduced to the same
+// element count in the same order.
+bool flat_pair(const Tensor &p, const Tensor &g) {
+  return g.storage->size == p.storage->size && covers_storage(g) && p.storage->device == DeviceTag::GPU &&
+         g.storage->device == DeviceTag::GPU;
+}
+} // namespace
+
+void Adam::register_parameter(ParameterPtr p) {
+  AdamState s;
+  s.m = Tensor::zeros(p->shape, false, false, DType::REAL, p->storage->device, p->storage->get_device_id());
+  s.v = Tensor::zeros(p->shape, false, false, DType::REAL, p->storage->device, p->storage->get_device_id());
+  state[p] = s;
+}
+
+void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
+  opt.t += 1;
+  const real1 bias_correction1 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta1, (real1_s)opt.t));
+  const real1 bias_correction2 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta2, (real1_s)opt.t));
+  const BackendConfig &cfg = backend_config();
+  for (auto &p : params) {
+    const auto it = opt.state.find(p);
+    if (it == opt.state.end()) throw std::invalid_argument("Parameter passed to adam_step that was not registered with optimizer!");
+    AdamState &s = it->second;
+    TensorPtr g = p->grad;
+    if (!g) throw std::invalid_argument("adam_step: parameter has no gradient");
+    if (cfg.fused && flat_pair(*p, *g) && s.m->storage->size == p->storage->size && s.v->storage->size == p->storage->size) {
+      // one pass, 28 B/param: m, v, p updated in place (adam.hpp:84-104 allocates ~12 temporaries)
+      throw_on_error(weedcu_adam_step(p->device_ptr(), g->device_ptr(), s.m->device_ptr(), s.v->device_ptr(), p->storage->size, opt.lr,
+                                      opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, p->stream()),
+                     "adam_step");
+      continue;
+    }
+    if (cfg.grad_scale != ONE_R1) g = cfg.grad_scale * g;
+    s.m = opt.beta1 * s.m + (ONE_R1 - opt.beta1) * g;
+    s.v = opt.beta2 * s.v + (ONE_R1 - opt.beta2) * g * g;
+    TensorPtr tmp = opt.lr * s.m / (bias_correction1 * (((s.v / bias_correction2) ^ ((real1)0.5)) + opt.eps));
+    p->match_shape(tmp);
+    tmp->match_shape(p);
+    Weed::sub_in_place(*p, *tmp);
+  }
+}
+
+void sgd_step(const std::vector<ParameterPtr> &params, real1 lr) {
+  const BackendConfig &cfg = backend_config();
+  for (auto &p : params) {
+    TensorPtr pg = p->grad;
+    if (!pg) throw std::invalid_argument("sgd_step: parameter has no gradient");
+    if (cfg.fused && flat_pair(*p, *pg)) {
+      throw_on_error(weedcu_sgd_step(p->device_ptr(), pg->device_ptr(), p->storage->size, lr, cfg.grad_scale, p->stream()), "sgd_step");
+      continue;
+    }
+    TensorPtr tmp = (lr * cfg.grad_scale) * pg;
+    tmp->match_shape(p);
+    Weed::sub_in_place(*p, *tmp);
+  }
+}
+
+void zero_grad(const std::vector<ParameterPtr> &params) {
+  for (auto p : params)
+    if (p->grad) p->grad->storage->FillZeros();
+}
+
+TensorPtr mse_loss(TensorPtr y_pred, TensorPtr y_true) { return Tensor::mean((y_pred - y_true) * (y_pred - y_true)); }
+
+TensorPtr bci_with_logits_loss(TensorPtr logits, TensorPtr y_true) {
+  return Tensor::relu(logits) - logits * y_true + Tensor::log(ONE_R1 + Tensor::exp(-ONE_R1 * Tensor::abs(logits)));
+}
+
+TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
+  const size_t rank = logits->shape.size();
+  const tcapint V = logits->shape[rank - 1U];
+  const tcapint rows = logits->get_broadcast_size() / V;
+  if (backend_config().fused && logits->storage->device == DeviceTag::GPU && Tensor::is_contiguous(logits->shape, logits->stride) &&
+      targets->get_broadcast_size() == rows && targets->stride[0U] == 1U) {
+    // fused: one read of the logits forward (online log-sum-exp + exact int gather of the target
+    // column), one elementwise kernel backward; never materialises log-softmax or a one-hot
+    const bool rg = logits->requires_grad;
+    TensorPtr loss = Tensor::allocate_scalar_like(*logits, rg);
+    TensorPtr lse = Tensor::allocate_like(std::vector<tcapint>{rows}, *logits, DType::REAL, false, false);
+    SymbolTensorPtr tg = targets->storage->device == DeviceTag::GPU ? targets : targets->cast(DeviceTag::GPU);
+    const tcapint vs = logits->stride[rank - 1U];
+    throw_on_error(weedcu_cross_entropy_fwd(logits->device_ptr(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
+                                            lse->device_ptr(), loss->device_ptr(), logits->stream()),
+                   "cross_entropy_loss");
+    if (rg) {
+      loss->make_gradient();
+      loss->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{logits}, [logits, tg, lse, loss, rows, V, vs]() {
+        TensorPtr dl = std::make_shared<Tensor>(*(logits->grad));
+        throw_on_error(weedcu_cross_entropy_bwd(logits->device_ptr(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
+                                                lse->device_ptr(), loss->grad->device_ptr() + loss->grad->offset, dl->device_ptr(),
+                                                dl->offset, logits->stream()),
+                       "cross_entropy_loss backward");
+        logits->grad = dl;
+      });
+    }
+    return loss;
+  }
+  // reference composition (cross_entropy_loss.hpp:21-34): logits [1, T, V]
+  const symint T = (symint)rows, Vs = (symint)V;
+  TensorPtr lsm = Tensor::logsoftmax(logits, -1);
+  lsm = Tensor::reshape(lsm, {T, Vs});
+  TensorPtr oh = Tensor::one_hot(targets, V);
+  TensorPtr selected = lsm * oh;
+  TensorPtr gathered = Tensor::sum(selected, 1);
+  return Tensor::mean(gathered) * real1(-1.0f);
+}
+} // namespace Weed

@@ -1,0 +1,295 @@
+// ops.cpp — Weed:: op entry points on the CUDA device. Validation mirrors the reference (same
+// exception types at the same checks: src/ops/commuting.cpp:121-140, in_place.cpp:110-125,
+// copy_broadcast.cpp:66-80, reduce.cpp:234-278, sum.cpp:127-135, matmul.cpp:95-122,242-256,
+// util.cpp:18-34); the body of each op is one call into include/weedcu.h.
+#include "weed_b200/ops.hpp"
+
+#include <cmath>
+
+namespace Weed {
+
+void validate_all_same_device(const std::vector<const BaseTensor *> &t, const std::string cls) {
+  if (t.size() < 2U) return;
+  const DeviceTag dtag = t[0U]->storage->device;
+  for (const auto &x : t)
+    if (dtag != x->storage->device) throw std::domain_error(std::string("In ") + cls + std::string(", tensor storage devices do not match!"));
+}
+
+namespace {
+struct Dev {
+  real1 *ptr;
+  void *stream;
+};
+inline GpuRealStorage *gpu_storage(const BaseTensor &t, const char *op) {
+  if (!t.storage) throw std::invalid_argument(std::string(op) + ": tensor has no storage");
+  if (t.storage->dtype != DType::REAL) throw std::invalid_argument(std::string(op) + ": only real-valued tensors are supported on the CUDA device");
+  if (t.storage->device != DeviceTag::GPU)
+    throw std::domain_error(std::string(op) + ": this backend implements DeviceTag::GPU only; there is no CPU compute path "
+                                              "(move the tensor with cast(DeviceTag::GPU))");
+  return static_cast<GpuRealStorage *>(t.storage.get());
+}
+inline Dev dev_of(const BaseTensor &t, const char *op) {
+  GpuRealStorage *s = gpu_storage(t, op);
+  s->dev->Bind();
+  return Dev{s->device_ptr(), s->dev->stream};
+}
+inline void require_real(const Tensor &t, const char *msg) {
+  if (t.storage->dtype != DType::REAL) throw std::invalid_argument(msg);
+}
+
+void binary(int op, const Tensor &a, const Tensor &b, Tensor &out, const char *name) {
+  validate_all_same_device({&a, &b, &out}, name);
+  const tcapint aSize = a.get_broadcast_size(), bSize = b.get_broadcast_size(), oSize = out.get_broadcast_size();
+  if (aSize != bSize) throw std::invalid_argument(std::string("In ") + name + "(a, b, out), 'a' size does not match 'b' size!");
+  if (aSize != oSize) throw std::invalid_argument(std::string("In ") + name + "(a, b, out), out size does not match input size!");
+  const Dev da = dev_of(a, name), db = dev_of(b, name), dout = dev_of(out, name);
+  weedcu_view av = a.view(), bv = b.view(), ov = out.view();
+  // operands may carry different ranks for the same element count (e.g. a scalar [1] against
+  // [M,N]); present every operand with out's shape, broadcasting true scalars
+  auto conform = [&](const Tensor &t, weedcu_view &v) {
+    if (t.shape == out.shape) return;
+    if (t.is_scalar()) {
+      const uint64_t off = v.offset;
+      v = ov;
+      v.offset = off;
+      for (int d = 0; d < WEEDCU_MAX_RANK; ++d) v.stride[d] = 0;
+      return;
+    }
+    throw std::invalid_argument(std::string(name) + ": operand shapes differ (call match_shape first)");
+  };
+  conform(a, av);
+  conform(b, bv);
+  throw_on_error(weedcu_binary_real(op, da.ptr, &av, db.ptr, &bv, dout.ptr, &ov, dout.stream), name);
+}
+
+void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
+  validate_all_same_device({&a, &b}, name);
+  if (a.get_broadcast_size() != b.get_broadcast_size())
+    throw std::invalid_argument(std::string("In ") + name + "(a, b), 'a' size does not match 'b' size!");
+  const Dev da = dev_of(a, name), db = dev_of(b, name);
+  weedcu_view av = a.view(), bv = b.view();
+  if (b.shape != a.shape) {
+    if (!b.is_scalar()) throw std::invalid_argument(std::string(name) + ": operand shapes differ (call match_shape first)");
+    const uint64_t off = bv.offset;
+    bv = av;
+    bv.offset = off;
+    for (int d = 0; d < WEEDCU_MAX_RANK; ++d) bv.stride[d] = 0;
+  }
+  throw_on_error(weedcu_inplace_real(op, da.ptr, &av, db.ptr, &bv, da.stream), name);
+}
+
+void unary(int op, real1 param, const Tensor &a, Tensor &out, const char *name) {
+  validate_all_same_device({&a, &out}, name);
+  if (a.get_broadcast_size() != out.get_broadcast_size())
+    throw std::invalid_argument(std::string("In Weed::") + name + "(a, out), out size does not match input size!");
+  const Dev da = dev_of(a, name), dout = dev_of(out, name);
+  const weedcu_view av = a.view(), ov = out.view();
+  throw_on_error(weedcu_unary_real(op, param, da.ptr, &av, dout.ptr, &ov, dout.stream), name);
+}
+
+void unary_grad(int op, Tensor &din, const Tensor &in, const Tensor &dout, const char *name) {
+  validate_all_same_device({&din, &in, &dout}, name);
+  const tcapint n = din.get_broadcast_size();
+  if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size()))
+    throw std::invalid_argument(std::string("In Weed::") + name + "(din, in, dout), sizes do not match!");
+  const Dev dd = dev_of(din, name), di = dev_of(in, name), dg = dev_of(dout, name);
+  weedcu_view dv = din.view(), iv = in.view(), gv = dout.view();
+  auto conform = [&](const Tensor &t, weedcu_view &v) {
+    if (t.shape == din.shape) return;
+    if (!t.is_scalar()) throw std::invalid_argument(std::string(name) + ": operand shapes differ");
+    const uint64_t off = v.offset;
+    v = dv;
+    v.offset = off;
+    for (int d = 0; d < WEEDCU_MAX_RANK; ++d) v.stride[d] = 0;
+  };
+  conform(in, iv);
+  conform(dout, gv);
+  throw_on_error(weedcu_unary_grad_real(op, dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, dd.stream), name);
+}
+
+weedcu_mat mat_of(const Tensor &t, tcapint extra_offset = 0U, uint64_t batch_stride = 0U) {
+  weedcu_mat m;
+  m.offset = (uint64_t)t.offset + extra_offset;
+  m.s0 = t.stride[t.stride.size() - 2U];
+  m.s1 = t.stride[t.stride.size() - 1U];
+  m.batch_stride = batch_stride;
+  return m;
+}
+
+void matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate) {
+  validate_all_same_device({&a, &b, &out}, "MatMulKernel::matmul");
+  if ((a.shape.size() != 2U) || (b.shape.size() != 2U) || (out.shape.size() != 2U))
+    throw std::invalid_argument("MatMul is only for matrices with 2 indices!");
+  const tcapint K = a.shape[1U];
+  if (K != b.shape[0U]) throw std::invalid_argument("MatMul operand dimensions aren't compatible!");
+  const tcapint M = a.shape[0U], N = b.shape[1U];
+  if ((M != out.shape[0U]) || (N != out.shape[1U])) throw std::invalid_argument("MatMul output dimensions don't match inputs!");
+  const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dc = dev_of(out, "matmul");
+  const weedcu_mat am = mat_of(a), bm = mat_of(b), cm = mat_of(out);
+  throw_on_error(weedcu_matmul_real(da.ptr, &am, db.ptr, &bm, dc.ptr, &cm, M, K, N, 1U, accumulate,
+                                    backend_config().matmul_precision, dc.stream),
+                 "matmul");
+}
+} // namespace
+
+void add(const Tensor &a, const Tensor &b, Tensor &out) { binary(WEEDCU_ADD, a, b, out, "CommutingKernel::commuting"); }
+void mul(const Tensor &a, const Tensor &b, Tensor &out) { binary(WEEDCU_MUL, a, b, out, "CommutingKernel::commuting"); }
+void sub(const Tensor &a, const Tensor &b, Tensor &out) { binary(WEEDCU_SUB, a, b, out, "SubKernel::sub"); }
+void div(const Tensor &a, const Tensor &b, Tensor &out) { binary(WEEDCU_DIV, a, b, out, "DivKernel::div"); }
+void add_in_place(Tensor &a, const Tensor &b) { in_place(WEEDCU_ADD, a, b, "InPlaceKernel::in_place"); }
+void sub_in_place(Tensor &a, const Tensor &b) { in_place(WEEDCU_SUB, a, b, "InPlaceKernel::in_place"); }
+
+void copy_broadcast(Tensor &a, const Tensor &b) {
+  validate_all_same_device({&a, &b}, "CopyKernel::copy_broadcast");
+  if (a.get_size() != b.get_broadcast_size())
+    throw std::invalid_argument("In CopyKernel::copy_broadcast(a, b), 'a' size does not match 'b' size!");
+  const Dev da = dev_of(a, "copy_broadcast"), db = dev_of(b, "copy_broadcast");
+  const weedcu_view av = a.view(), bv = b.view();
+  throw_on_error(weedcu_copy_real(da.ptr, &av, db.ptr, &bv, da.stream), "copy_broadcast");
+}
+
+void relu(const Tensor &a, Tensor &out) { unary(WEEDCU_RELU, 0, a, out, "relu"); }
+void sigmoid(const Tensor &a, Tensor &out) { unary(WEEDCU_SIGMOID, 0, a, out, "sigmoid"); }
+void tanh(const Tensor &a, Tensor &out) { unary(WEEDCU_TANH, 0, a, out, "tanh"); }
+void sin(const Tensor &a, Tensor &out) { unary(WEEDCU_SIN, 0, a, out, "sin"); }
+void cos(const Tensor &a, Tensor &out) { unary(WEEDCU_COS, 0, a, out, "cos"); }
+void abs(const Tensor &a, Tensor &out) { unary(WEEDCU_ABS, 0, a, out, "abs"); }
+void gelu(const Tensor &a, Tensor &out) { unary(WEEDCU_GELU, 0, a, out, "gelu"); }
+void pow(const Tensor &a, const real1 &p, Tensor &out) { unary(WEEDCU_POW, p, a, out, "pow"); }
+void exp(const Tensor &a, const real1 &b, Tensor &out) { unary(WEEDCU_EXP, (real1)std::log((real1_s)b), a, out, "exp"); }
+void log(const Tensor &a, const real1 &b, Tensor &out) {
+  if (b <= ZERO_R1) throw std::invalid_argument("Log base must be positive!");
+  unary(WEEDCU_LOG, (real1)(ONE_R1 / std::log((real1_s)b)), a, out, "log");
+}
+void relu_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_RELU, din, in, dout, "relu_grad"); }
+void sigmoid_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_SIGMOID, din, in, dout, "sigmoid_grad"); }
+void tanh_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_TANH, din, in, dout, "tanh_grad"); }
+void sin_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_SIN, din, in, dout, "sin_grad"); }
+void cos_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_COS, din, in, dout, "cos_grad"); }
+void abs_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_ABS, din, in, dout, "abs_grad"); }
+void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_GELU, din, in, dout, "gelu_grad"); }
+
+static void full_reduce(const Tensor &a, Tensor &out, bool is_mean) {
+  validate_all_same_device({&a, &out}, "SumKernel::sum");
+  if (out.get_broadcast_size() != 1U)
+    throw std::invalid_argument("In Weed::sum(a, out) or Weed::mean(a, out), out parameter is not a scalar!");
+  const Dev da = dev_of(a, "sum"), dout = dev_of(out, "sum");
+  const weedcu_view av = a.view();
+  const real1 scale = is_mean ? (ONE_R1 / (real1)a.get_broadcast_size()) : ONE_R1;
+  throw_on_error(weedcu_sum_real(da.ptr, &av, scale, dout.ptr + out.offset, dout.stream), "sum");
+}
+void sum(const Tensor &a, Tensor &out) { full_reduce(a, out, false); }
+void mean(const Tensor &a, Tensor &out) { full_reduce(a, out, true); }
+
+void reduce(const tcapint &index, const Tensor &a, Tensor &out) {
+  validate_all_same_device({&a, &out}, "ReduceKernel::reduce");
+  if (a.storage->dtype != out.storage->dtype) throw std::invalid_argument("Output tensor dtype mismatch in reduce!");
+  if (index >= a.shape.size()) throw std::invalid_argument("reduce: axis out of range");
+  const Dev da = dev_of(a, "reduce"), dout = dev_of(out, "reduce");
+  const weedcu_view av = a.view();
+  // the output is written as a dense buffer starting at out.offset, which is how the tensor built
+  // by Tensor::sum(axis) (contiguous, axis extent 1) is read
+  throw_on_error(weedcu_reduce_real(da.ptr, &av, (int)index, dout.ptr + out.offset, backend_config().ref_index_quirks ? 1 : 0,
+                                    dout.stream),
+                 "reduce");
+}
+void reduce_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tensor &dout) {
+  validate_all_same_device({&din, &dout}, "ReduceKernel::reduce_grad");
+  const tcapint n = din.get_broadcast_size();
+  if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size()))
+    throw std::invalid_argument("In Weed::reduce_grad(din, in, dout), sizes do not match!");
+  const Dev dd = dev_of(din, "reduce_grad"), dg = dev_of(dout, "reduce_grad");
+  const weedcu_view dv = din.view(), gv = dout.view();
+  throw_on_error(weedcu_reduce_grad_real(dd.ptr, &dv, dg.ptr, &gv, (int)index, backend_config().ref_index_quirks ? 1 : 0, dd.stream),
+                 "reduce_grad");
+}
+
+static void softmax_fwd(int log_mode, const tcapint &index, const Tensor &a, Tensor &out, const char *name) {
+  validate_all_same_device({&a, &out}, name);
+  require_real(a, "Tensor dtype mismatch in softmax_forward!");
+  const Dev da = dev_of(a, name), dout = dev_of(out, name);
+  const weedcu_view av = a.view(), ov = out.view();
+  throw_on_error(weedcu_softmax_real(log_mode, da.ptr, &av, (int)index, dout.ptr, &ov, dout.stream), name);
+}
+static void softmax_bwd(int log_mode, const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout, const char *name) {
+  validate_all_same_device({&din, &out, &dout}, name);
+  const Dev dd = dev_of(din, name), dy = dev_of(out, name), dg = dev_of(dout, name);
+  const weedcu_view dv = din.view(), yv = out.view(), gv = dout.view();
+  throw_on_error(weedcu_softmax_grad_real(log_mode, dd.ptr, &dv, dy.ptr, &yv, dg.ptr, &gv, (int)index, dd.stream), name);
+}
+void softmax(const tcapint &index, const Tensor &a, Tensor &out) { softmax_fwd(0, index, a, out, "SoftmaxKernel::softmax_forward"); }
+void logsoftmax(const tcapint &index, const Tensor &a, Tensor &out) { softmax_fwd(1, index, a, out, "LogSoftmaxKernel::logsoftmax_forward"); }
+void softmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout) {
+  softmax_bwd(0, index, din, out, dout, "SoftmaxKernel::softmax_backward");
+}
+void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout) {
+  softmax_bwd(1, index, din, out, dout, "LogSoftmaxKernel::logsoftmax_backward");
+}
+
+void matmul(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 0); }
+void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 1); }
+
+void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {
+  validate_all_same_device({&a3, &b3, &out3}, "MatMulKernel::matmul_batched");
+  if ((a3.shape.size() != 3U) || (b3.shape.size() != 3U) || (out3.shape.size() != 3U))
+    throw std::invalid_argument("matmul_batched is for [batch, M, K] x [batch, K, N] views");
+  const tcapint batch = a3.shape[0U], M = a3.shape[1U], K = a3.shape[2U], N = b3.shape[2U];
+  if ((b3.shape[0U] != batch) || (out3.shape[0U] != batch)) throw std::invalid_argument("batched matmul batch mismatch");
+  if (b3.shape[1U] != K) throw std::invalid_argument("batched matmul inner dim mismatch");
+  if ((out3.shape[1U] != M) || (out3.shape[2U] != N)) throw std::invalid_argument("MatMul output dimensions don't match inputs!");
+  const Dev da = dev_of(a3, "matmul_batched"), db = dev_of(b3, "matmul_batched"), dc = dev_of(out3, "matmul_batched");
+  const weedcu_mat am = mat_of(a3, 0U, a3.stride[0U]), bm = mat_of(b3, 0U, b3.stride[0U]), cm = mat_of(out3, 0U, out3.stride[0U]);
+  throw_on_error(weedcu_matmul_real(da.ptr, &am, db.ptr, &bm, dc.ptr, &cm, M, K, N, batch, 0,
+                                    backend_config().matmul_precision, dc.stream),
+                 "matmul_batched");
+}
+
+// Token stride / output row stride. The reference reads stride[0] (src/ops/embedding.cpp:66-75),
+// which is 0 when the leading extent is 1 (e.g. indices [1, T]) and then gathers token 0 only;
+// for dense tensors the flat token index has stride 1, which is what is meant.
+static tcapint flat_stride(const BaseTensor &t) {
+  tcapint expect = 1U;
+  bool dense = true;
+  for (size_t i = 0U; i < t.shape.size(); ++i) {
+    if (t.shape[i] == 1U) continue;
+    if (t.stride[i] != expect) dense = false;
+    expect *= t.shape[i];
+  }
+  return dense ? 1U : t.stride[0U];
+}
+static tcapint row_stride_of_rows(const BaseTensor &t) { // all dims but the last form the token index
+  BaseTensor lead;
+  lead.shape.assign(t.shape.begin(), t.shape.end() - 1);
+  lead.stride.assign(t.stride.begin(), t.stride.end() - 1);
+  if (lead.shape.empty()) return t.stride[0U];
+  return flat_stride(lead);
+}
+static const symint *sym_ptr(const SymbolTensor &s, const char *op) {
+  if (s.storage->device != DeviceTag::GPU) throw std::domain_error(std::string(op) + ": indices must be GPU-resident");
+  return s.device_ptr();
+}
+void embedding_gather(const SymbolTensor &indices, const Tensor &weight, Tensor &out) {
+  validate_all_same_device({&indices, &weight, &out}, "embedding_gather");
+  const Dev dw = dev_of(weight, "embedding_gather"), dout = dev_of(out, "embedding_gather");
+  const tcapint D = weight.shape[1U], n = indices.get_broadcast_size();
+  throw_on_error(weedcu_embedding_gather(sym_ptr(indices, "embedding_gather"), indices.offset, flat_stride(indices), n, dw.ptr,
+                                         weight.offset, weight.stride[0U], weight.stride[1U], D, dout.ptr, out.offset,
+                                         row_stride_of_rows(out), out.stride.back(), dout.stream),
+                 "embedding_gather");
+}
+void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor &dout) {
+  validate_all_same_device({&dW, &indices, &dout}, "embedding_scatter_add");
+  const Dev dw = dev_of(dW, "embedding_scatter_add"), dg = dev_of(dout, "embedding_scatter_add");
+  const tcapint D = dW.shape[1U], n = indices.get_broadcast_size();
+  throw_on_error(weedcu_embedding_scatter_add(dw.ptr, dW.offset, dW.stride[0U], dW.stride[1U], sym_ptr(indices, "embedding_scatter_add"),
+                                              indices.offset, flat_stride(indices), n, D, dg.ptr, dout.offset, row_stride_of_rows(dout),
+                                              dout.stride.back(), dw.stream),
+                 "embedding_scatter_add");
+}
+void triu_fill(Tensor &a, const complex &val, const tcapint diagonal) {
+  if (a.shape.size() != 2U) throw std::invalid_argument("triu_fill requires a 2D tensor!");
+  const Dev da = dev_of(a, "triu_fill");
+  const weedcu_view av = a.view();
+  throw_on_error(weedcu_triu_fill_real(da.ptr, &av, val.real(), diagonal, da.stream), "triu_fill");
+}
+} // namespace Weed
