@@ -160,6 +160,25 @@ int64_t wh_symbol(const int32_t *data, uint32_t n, int rank, const uint32_t *sha
     return g_next++;
   })
 }
+// Overwrite an existing SymbolTensor from a host buffer (bench.py passes pinned memory: this is
+// the per-step host->device input copy of the end-to-end measurement). Asynchronous on the device
+// stream for the CUDA build; a plain copy for the reference build.
+int wh_symbol_upload(int64_t h, const int32_t *src, uint32_t n) {
+  WH_TRY({
+    SymbolTensorPtr s = g_symbols.at(h);
+    if (s->storage->size != n) throw std::invalid_argument("wh_symbol_upload: element count mismatch");
+#ifdef WEED_B200
+    if (s->storage->device == DeviceTag::GPU) {
+      GpuIntStorage *gs = static_cast<GpuIntStorage *>(s->storage.get());
+      throw_on_error(weedcu_memcpy_h2d(gs->device_ptr(), src, sizeof(int32_t) * (size_t)n, gs->dev->stream), "wh_symbol_upload");
+      return 0;
+    }
+#endif
+    IntStorage *is = static_cast<IntStorage *>(s->storage.get());
+    for (uint32_t i = 0; i < n; ++i) is->write(i, src[i]);
+    return 0;
+  })
+}
 // an explicit (offset, shape, stride) view on the storage of an existing tensor
 int64_t wh_view(int64_t h, uint32_t offset, int rank, const uint32_t *shape, const uint32_t *stride) {
   WH_TRY({
@@ -408,9 +427,60 @@ int wh_zero_grad(int64_t module) {
   })
 }
 
-// One full training step on token input: forward, cross-entropy, backward, Adam, zero_grad —
-// the loop body of the reference's train_step (src/shared_api.cpp:356-424) with Adam instead of SGD.
-// Returns the loss tensor handle (read it with wh_read; reading syncs).
+// ------------------------------------------------------------------------------- data parallel
+// (this repo's host library only; the reference has no gradient exchange)
+#ifdef WEED_B200
+namespace {
+void *g_comm = nullptr;
+int g_world = 1;
+} // namespace
+#endif
+int wh_dp_load(const char *libnccl_path) {
+#ifdef WEED_B200
+  return weedcu_nccl_load(libnccl_path);
+#else
+  (void)libnccl_path;
+  return -1;
+#endif
+}
+int wh_dp_unique_id(void *id128) {
+#ifdef WEED_B200
+  return weedcu_nccl_unique_id(id128);
+#else
+  (void)id128;
+  return -1;
+#endif
+}
+int wh_dp_init(const void *id128, int rank, int world) {
+#ifdef WEED_B200
+  WH_TRY({
+    throw_on_error(weedcu_nccl_init(id128, rank, world, &g_comm), "wh_dp_init");
+    g_world = world;
+    backend_config().grad_scale = ONE_R1 / (real1)world;
+    return 0;
+  })
+#else
+  (void)id128;
+  (void)rank;
+  (void)world;
+  return -1;
+#endif
+}
+int wh_dp_broadcast_params(int64_t model) {
+#ifdef WEED_B200
+  WH_TRY({
+    if (g_comm) broadcast_parameters(M(model)->parameters(), g_comm, 0);
+    return 0;
+  })
+#else
+  (void)model;
+  return 0;
+#endif
+}
+
+// One full training step on token input: forward, cross-entropy, backward, (gradient all-reduce,)
+// Adam, zero_grad — the loop body of the reference's train_step (src/shared_api.cpp:356-424) with
+// Adam instead of SGD. Returns the loss tensor handle (read it with wh_read; reading syncs).
 int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t targets) {
   WH_TRY({
     ModulePtr m = M(model);
@@ -418,6 +488,9 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
     Tensor::backward(loss);
     const std::vector<ParameterPtr> params = m->parameters();
+#ifdef WEED_B200
+    if (g_comm && g_world > 1) allreduce_gradients(params, g_comm);
+#endif
     adam_step(*g_adams.at(opt), params);
     zero_grad(params);
     m->reset_cache();

@@ -245,6 +245,20 @@ int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1
 int weedcu_gemm_workspace_bytes(uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
                                 int precision, uint64_t *bytes);
 
+/* ------------------------------------------------------------------ per-kernel-class timing
+ * Measurement support for bench.py's `roofline` object: when enabled, every launch of the classes
+ * below is bracketed by CUDA events on its own stream; weedcu_prof_read() synchronises and returns
+ * the summed device time, launch count and algorithmic work (FLOP for the GEMM classes, bytes for
+ * the rest, SURVEY §8d figures). Off by default: the normal hot path records nothing. */
+enum {
+  WEEDCU_PROF_GEMM_TC = 1, WEEDCU_PROF_GEMM_F32 = 2, WEEDCU_PROF_PACK = 3, WEEDCU_PROF_ELEMENTWISE = 4,
+  WEEDCU_PROF_SOFTMAX = 5, WEEDCU_PROF_LAYERNORM = 6, WEEDCU_PROF_CROSS_ENTROPY = 7,
+  WEEDCU_PROF_OPTIMIZER = 8, WEEDCU_PROF_REDUCE = 9, WEEDCU_PROF_EMBEDDING = 10, WEEDCU_PROF_FILL = 11,
+  WEEDCU_PROF_NCCL = 12, WEEDCU_PROF_NUM_CLASSES = 13
+};
+int weedcu_prof_enable(int on);
+int weedcu_prof_read(int cls, double *total_ms, uint64_t *launches, double *work);
+
 /* ------------------------------------------------------------------ data-parallel collectives
  * No reference counterpart (Weed has no gradient exchange). NCCL over NVLink,
  * one process per GPU. The unique id is produced by rank 0 and shipped by the caller

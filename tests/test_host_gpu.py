@@ -1,0 +1,280 @@
+"""GPU parity of the host library (Weed's Tensor / autograd / Module API on the CUDA device) against
+the UNMODIFIED reference CPU build, both driven by the SAME client source
+(harness/weed_harness.cpp) with the same seeded inputs and injected weights.
+
+Tolerances (BASELINE.json north_star): <= 1e-5 relative-to-max per op at fp32 (2e-5 where the chain
+is several ops deep), <= 1e-3 relative on loss after a fixed number of seeded training steps.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import refpins
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libweed_ref_harness.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
+
+
+def seed_of(name):
+    return sum(ord(ch) * (i + 1) for i, ch in enumerate(name)) % (2**31)
+
+
+@pytest.fixture(scope="module")
+def P():
+    from weed_b200.harness import Harness
+    h = Harness.product()  # raises if the CUDA build is missing: no fallback
+    assert h.backend() == "weed_b200"
+    return h
+
+
+@pytest.fixture(scope="module")
+def R():
+    from weed_b200.harness import Harness
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libweed_ref_harness.so not present on this box")
+    h = Harness.reference()
+    assert h.backend() == "reference"
+    return h
+
+
+def set_mode(P, fused, quirks=0, precision=0):
+    P.config("fused", fused)
+    P.config("ref_index_quirks", quirks)
+    P.config("matmul_precision", precision)
+    P.config("grad_scale", 1.0)
+
+
+# pins whose reference behaviour is an indexing defect: only the faithful mode reproduces it
+NEEDS_QUIRKS = {"sum_axis_3x4x5_axis2_reference_order", "sum_axis_3x4x5_axis1_reference_order",
+                "sum_axis_3x4x5_axis0_reference_order"}
+# the fused sgd_step applies each update once; the reference applies bias updates B times (refpins)
+UNFUSED_ONLY = {"sgd_3_steps_on_linear"}
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+@pytest.mark.parametrize("name,fn,tol", refpins.PINS, ids=[p[0] for p in refpins.PINS])
+def test_host_op_matches_reference_fixture(P, name, fn, tol, fused):
+    """Same harness calls on the GPU build vs the stored outputs of the compiled reference."""
+    if fused and name in UNFUSED_ONLY:
+        pytest.skip("documented deviation of the fused path (DESIGN.md, reference defects)")
+    set_mode(P, fused, quirks=1 if name in NEEDS_QUIRKS else 0)
+    z = np.load(GOLDEN)
+    inp, ref, _orc = fn(np.random.default_rng(seed_of(name)))
+    got = ref(P, inp)
+    P.reset()
+    for k, v in got.items():
+        want = z[f"{name}/out/{k}"]
+        err = cases.rel_err(v, want)
+        assert np.all(np.isfinite(v))
+        assert err <= max(tol, 2e-5), f"{name}:{k} host(GPU) vs reference rel-to-max {err:.3e}"
+
+
+def test_intended_axis_sum_differs_from_reference_only_by_permutation(P):
+    """Default mode implements the intended column-major output order."""
+    set_mode(P, 1, quirks=0)
+    x = P.tensor(np.arange(24, dtype=np.float32), [2, 3, 4])
+    s = P.op("sum_axis", [x], ints=[2])
+    got = P.read(s)
+    want = np.arange(24, dtype=np.float32).reshape(4, 3, 2).sum(axis=0).ravel()
+    assert np.array_equal(got, want)
+    P.reset()
+
+
+# ------------------------------------------------------------------------------------ models
+def build_mlp(H, sizes, act, seed):
+    layers = []
+    for i in range(len(sizes) - 1):
+        layers.append(H.module("linear", sizes[i], sizes[i + 1], 1))
+        if i < len(sizes) - 2:
+            layers.append(H.module(act))
+    m = H.module("sequential", *layers)
+    H.init_params(m, seed)
+    return m
+
+
+def train_mlp(H, x, y, sizes, steps, lr, seed=2000):
+    m = build_mlp(H, sizes, "tanh", seed)
+    opt = H.adam(m, lr)
+    # x is [rows, features]; Weed tensors are column-major: element (r, f) lives at r + rows*f
+    xt, yt = H.tensor(np.ascontiguousarray(x.T).ravel(), list(x.shape)), H.tensor(y, [len(y), 1])
+    losses = []
+    for _ in range(steps):
+        pred = H.forward(m, xt)
+        loss = H.op("bci_with_logits_loss", [pred, yt])
+        H.backward(loss)
+        H.adam_step(opt, m)
+        losses.append(float(np.sum(H.read(loss))))  # implicit-sum loss (SURVEY hard part 5(iii))
+        H.zero_grad(m)
+    params = [H.read_storage(H.param(m, i)) for i in range(H.param_count(m))]
+    H.reset()
+    return np.array(losses), params
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+def test_config_c1_xor_training_matches_reference(P, R, fused):
+    """examples/xor.cpp (config C1): Linear(2,4)-Tanh-Linear(4,1), bci_with_logits, Adam lr 0.01."""
+    set_mode(P, fused)
+    x = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], np.float32)
+    y = np.array([0, 1, 1, 0], np.float32)
+    a, pa = train_mlp(R, x, y, [2, 4, 1], 60, 0.01)
+    b, pb = train_mlp(P, x, y, [2, 4, 1], 60, 0.01)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-3, (a[-3:], b[-3:])
+    for u, v in zip(pa, pb):
+        assert cases.rel_err(v, u) <= 1e-3
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+def test_config_c2_tabular_mlp_training_matches_reference(P, R, fused):
+    """examples/heart_attack.cpp shape (config C2, reduced rows for the CPU reference):
+    Linear(13,26)-Tanh-Linear(26,1), bci_with_logits, Adam lr 1e-3, 20 fixed steps."""
+    set_mode(P, fused)
+    rng = np.random.default_rng(1002)
+    rows = 512
+    x = rng.uniform(-1, 1, size=(rows, 13)).astype(np.float32)
+    y = (rng.uniform(size=rows) > 0.5).astype(np.float32)
+    a, pa = train_mlp(R, x, y, [13, 26, 1], 20, 1e-3)
+    b, pb = train_mlp(P, x, y, [13, 26, 1], 20, 1e-3)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-3, (a[-3:], b[-3:])
+    for u, v in zip(pa, pb):
+        assert cases.rel_err(v, u) <= 1e-3
+
+
+def test_multihead_attention_forward_matches_reference(P, R):
+    """Fused attention core (batched GEMMs + fused scale/mask/softmax) vs the reference's composition,
+    B > 1 (no LayerNorm inside MHA, so the reference's indexing defects are not involved)."""
+    B, T, d, Hh = 3, 10, 16, 4
+    rng = np.random.default_rng(77)
+    x = rng.uniform(-1, 1, size=B * T * d).astype(np.float32)
+    outs = []
+    for H, fused in ((R, 1), (P, 1), (P, 0)):
+        if H is P:
+            set_mode(P, fused)
+        m = H.module("mha", d, Hh)
+        H.init_params(m, 31)
+        y = H.forward(m, H.tensor(x, [B, T, d], True))
+        outs.append(H.read(y))
+        H.reset()
+    assert cases.rel_err(outs[1], outs[0]) <= 2e-5
+    assert cases.rel_err(outs[2], outs[0]) <= 2e-5
+
+
+def encoder_run(H, x, w, seed, steps=1):
+    B, T, d = x.shape
+    enc = H.module("encoder", d, 2, 2 * d)
+    H.init_params(enc, seed)
+    xt = H.tensor(np.ascontiguousarray(x.transpose(2, 1, 0)).ravel(), [B, T, d], True)  # col-major
+    wt = H.tensor(np.ascontiguousarray(w.transpose(2, 1, 0)).ravel(), [B, T, d])
+    y = H.forward(enc, xt)
+    H.backward(H.op("sum", [H.op("mul", [y, wt])]))
+    # (the layer works on x_->cast(dtag), a copy, so the caller's tensor never receives a grad:
+    #  transformer_encoder_layer.cpp:71 — parameter gradients are what can be compared)
+    out = {"y": H.read(y)}
+    for i in range(H.param_count(enc)):
+        g = H.grad(H.param(enc, i))
+        out[f"g{i}"] = H.read_storage(g) if g else np.zeros(1, np.float32)
+    H.reset()
+    return out
+
+
+def test_encoder_layer_fused_matches_reference_B1(P, R):
+    """TransformerEncoderLayer forward + backward, B = 1 (where the reference's reduce indexing is
+    self-consistent): fused LayerNorm / GELU / attention / GEMM-accumulate vs the reference chain."""
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, size=(1, 12, 16)).astype(np.float32)
+    w = rng.uniform(-1, 1, size=(1, 12, 16)).astype(np.float32)
+    a = encoder_run(R, x, w, 9)
+    set_mode(P, 1)
+    b = encoder_run(P, x, w, 9)
+    for k in a:
+        assert cases.rel_err(b[k], a[k]) <= 5e-5, k
+
+
+def test_encoder_layer_faithful_mode_matches_reference_B4(P, R):
+    """B > 1: the reference's LayerNorm uses permuted row statistics (reduce.cpp:17-31). The un-fused
+    path with ref_index_quirks reproduces that op for op."""
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-1, 1, size=(4, 6, 8)).astype(np.float32)
+    w = rng.uniform(-1, 1, size=(4, 6, 8)).astype(np.float32)
+    a = encoder_run(R, x, w, 10)
+    set_mode(P, 0, quirks=1)
+    b = encoder_run(P, x, w, 10)
+    for k in a:
+        assert cases.rel_err(b[k], a[k]) <= 5e-5, k
+    set_mode(P, 1)
+
+
+def transformer_losses(H, B, T, V, d, steps, seed):
+    """config C4 shape family (examples/binary_addition_transformer.cpp): Embedding - LearnedPosEnc -
+    TransformerEncoderLayer - Linear(d,1); bci_with_logits on the last T//2 positions; Adam."""
+    rng = np.random.default_rng(seed)
+    tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+    tlen = T // 2
+    target = (rng.uniform(size=(B, tlen)) > 0.5).astype(np.float32)
+    model = H.module("sequential", H.module("embedding", V, d), H.module("posenc", T, d), H.module("encoder", d, 2, 2 * d),
+                     H.module("linear", d, 1, 1))
+    H.init_params(model, seed + 1)
+    opt = H.adam(model, 1e-3)
+    tok = H.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+    tgt = H.tensor(np.ascontiguousarray(target.T).ravel(), [B, tlen])
+    losses = []
+    for _ in range(steps):
+        logits = H.forward_symbol(model, tok)
+        H.squeeze(logits, 2)
+        pred = H.op("slice", [logits], ints=[1, T - tlen, tlen])
+        loss = H.op("bci_with_logits_loss", [pred, tgt])
+        H.backward(loss)
+        H.adam_step(opt, model)
+        losses.append(float(np.sum(H.read(loss))))
+        H.zero_grad(model)
+        H.module_set(model, "reset_cache", 1)
+    H.reset()
+    return np.array(losses)
+
+
+def test_config_c4_transformer_training_faithful_mode_matches_reference(P, R):
+    """10 fixed Adam steps on the C4 model at the reference example's own dimensions (B=16, T=6,
+    d=8, vocab 5), faithful mode: loss trajectory within 1e-3 relative of the reference CPU path."""
+    a = transformer_losses(R, 16, 6, 5, 8, 10, 40)
+    set_mode(P, 0, quirks=1)
+    b = transformer_losses(P, 16, 6, 5, 8, 10, 40)
+    set_mode(P, 1)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-3, (a, b)
+
+
+def test_config_c4_transformer_training_default_mode_runs_and_learns(P):
+    """Default (fused, intended indexing) mode on the same model: finite, and the loss goes down."""
+    set_mode(P, 1)
+    b = transformer_losses(P, 16, 6, 5, 8, 30, 40)
+    assert np.all(np.isfinite(b)) and b[-1] < b[0]
+
+
+def test_gpt_shape_train_step_bf16_vs_fp32(P):
+    """Token model with the fused cross-entropy: bf16 tensor-core GEMMs vs the fp32 path on the same
+    weights — loss after 3 steps within the stated bf16 bound (2e-2 relative)."""
+    B, T, V, d, L = 2, 64, 512, 64, 2
+
+    def run(precision):
+        set_mode(P, 1, precision=precision)
+        rng = np.random.default_rng(3000)
+        tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        targets = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        mods = [P.module("embedding", V, d), P.module("posenc", T, d)] + [P.module("encoder", d, 4, 4 * d) for _ in range(L)]
+        mods += [P.module("layernorm", d), P.module("linear", d, V, 1)]
+        model = P.module("sequential", *mods)
+        P.init_params(model, 2000)
+        opt = P.adam(model, 1e-3)
+        tok = P.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+        tgt = P.symbol(np.ascontiguousarray(targets.T).ravel(), [B, T])
+        out = [float(P.read(P.train_step_tokens(model, opt, tok, tgt))[0]) for _ in range(3)]
+        P.reset()
+        return np.array(out)
+
+    f32, bf16 = run(0), run(1)
+    set_mode(P, 1)
+    assert np.all(np.isfinite(f32)) and abs(f32[0] - np.log(V)) < 1.0
+    assert np.max(np.abs(f32 - bf16) / np.abs(f32)) <= 2e-2, (f32, bf16)

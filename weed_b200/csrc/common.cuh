@@ -19,6 +19,22 @@ cudaStream_t resolve_stream(void *s);
 void count_launch(int n = 1);
 int after_launch(); // cudaGetLastError -> return code, bumps the launch counter
 
+// Optional per-class event timing (weedcu_prof_*). A scope brackets the launches issued while it
+// is alive; when profiling is off it costs one predictable branch.
+bool prof_on();
+int prof_begin(int cls, cudaStream_t st, double work);
+void prof_end(int idx, cudaStream_t st);
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int cls, cudaStream_t s, double work) : idx(-1), st(s) {
+    if (prof_on()) idx = prof_begin(cls, s, work);
+  }
+  ~ProfScope() {
+    if (idx >= 0) prof_end(idx, st);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Collapsed multi-operand index space. All operands share `shape`; each has its own strides.
 // Offsets are folded into the base pointers on the host.

@@ -113,6 +113,14 @@ static int launch_ew(const weedcu_view *const *views, const float *const *ins, f
     }
   }
   if (sp.stride[NIN][0] != 1) vec = false;
+  double moved = 4.0 * sp.n; // algorithmic bytes: the write + every non-broadcast read
+  for (int o = 0; o < NIN; ++o) {
+    bool streams = false;
+    for (int d = 0; d < sp.rank; ++d)
+      if (sp.stride[o][d]) streams = true;
+    if (streams) moved += 4.0 * sp.n;
+  }
+  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, moved);
   if (vec) {
     const unsigned grid = grid_for(sp.n >> 2, 256, 16);
     ew_vec4_kernel<NIN, F><<<grid, 256, 0, st>>>(sp, p, f);
@@ -268,6 +276,7 @@ extern "C" {
 int weedcu_fill_real(float *p, uint64_t n, float value, void *stream) {
   if (!p) return WEEDCU_EINVAL;
   if (!n) return 0;
+  ProfScope prof(WEEDCU_PROF_FILL, resolve_stream(stream), 4.0 * n);
   fill_kernel<float><<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, n, value);
   return after_launch();
 }
@@ -364,6 +373,7 @@ int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale
   if (!p || !g) return WEEDCU_EINVAL;
   if (!n) return 0;
   const bool vec = aligned16(p) && aligned16(g);
+  ProfScope prof(WEEDCU_PROF_OPTIMIZER, resolve_stream(stream), 12.0 * n);
   sgd_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, n, lr, gscale,
                                                                                vec);
   return after_launch();
@@ -376,6 +386,7 @@ int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, f
   if (!n) return 0;
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
   const bool vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  ProfScope prof(WEEDCU_PROF_OPTIMIZER, resolve_stream(stream), 28.0 * n);
   adam_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, m, v, n, a,
                                                                                 vec);
   return after_launch();

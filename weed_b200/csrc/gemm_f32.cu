@@ -163,6 +163,7 @@ int launch_gemm_f32(const float *a, const weedcu_mat *am, const float *b, const 
   g.M = M; g.N = N; g.K = K;
   g.accumulate = accumulate;
   if (batch > 65535) return WEEDCU_EINVAL;
+  ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K * batch);
   if ((uint64_t)M * N * (uint64_t)K <= (1ull << 22) || N <= 4 || M <= 4) {
     if ((uint64_t)M * N <= (1ull << 24) && (N <= 4 || M <= 4 || (uint64_t)M * N * K <= (1ull << 18))) {
       const uint64_t total = (uint64_t)M * N;

@@ -377,6 +377,7 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (N + block_n - 1) / block_n;
   p.accumulate = accumulate;
+  ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch);
   if (wide) return launch_cfg<256, 4>(tmA, tmB, p, a_major, b_major, st);
   return launch_cfg<128, 6>(tmA, tmB, p, a_major, b_major, st);
 }
@@ -423,6 +424,7 @@ int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, 
   const dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch);
   if (grid.y > 65535 || grid.z > 65535) return WEEDCU_EINVAL;
   const int src_rowfast = (s0 <= s1) ? 1 : 0;
+  ProfScope prof(WEEDCU_PROF_PACK, st, 6.0 * (double)rows * cols * batch);
   pack_bf16_kernel<<<grid, 256, 0, st>>>(src, s_bs, s0, s1, rows, cols, (__nv_bfloat16 *)dst, d_bs, ld,
                                          dst_major, src_rowfast);
   return after_launch();

@@ -254,6 +254,7 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
                          void *stream) {
   if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
+  ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
   switch (pick_rt(rows)) {
   case 32: return ln_fwd_launch<32, 512>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
   case 16: return ln_fwd_launch<16, 256>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
@@ -271,6 +272,7 @@ int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_
   float *part = nullptr;
   WCU_CHECK(cudaMallocAsync((void **)&part, sizeof(float) * 2 * (size_t)nblocks * F, st));
   float *pg = part, *pb = part + (size_t)nblocks * F;
+  ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 16.0 * (double)rows * F);
   int rc;
   switch (rt) {
   case 32: rc = ln_bwd_launch<32, 512>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, st); break;
@@ -290,6 +292,7 @@ int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_s
                             uint32_t D, float *out, uint64_t o_off, uint32_t o_s0, uint32_t o_s1,
                             void *stream) {
   if (!idx || !W || !out || !n || !D) return WEEDCU_EINVAL;
+  ProfScope prof(WEEDCU_PROF_EMBEDDING, resolve_stream(stream), 8.0 * (double)n * D);
   embedding_gather_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
       idx + idx_off, idx_stride, n, W + w_off, w_s0, w_s1, D, out + o_off, o_s0, o_s1);
   return after_launch();
@@ -300,6 +303,7 @@ int weedcu_embedding_scatter_add(float *dW, uint64_t w_off, uint32_t w_s0, uint3
                                  uint32_t n, uint32_t D, const float *dout, uint64_t o_off,
                                  uint32_t o_s0, uint32_t o_s1, void *stream) {
   if (!dW || !idx || !dout || !n || !D) return WEEDCU_EINVAL;
+  ProfScope prof(WEEDCU_PROF_EMBEDDING, resolve_stream(stream), 12.0 * (double)n * D);
   embedding_scatter_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
       dW + w_off, w_s0, w_s1, idx + idx_off, idx_stride, n, D, dout + o_off, o_s0, o_s1);
   return after_launch();

@@ -232,6 +232,7 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
   if (!L || !total) return WEEDCU_EINVAL;
   const uint64_t n_out = total / L;
   const float *base = a + av->offset;
+  ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * total);
   uint64_t inner, outer;
   // Row-major and column-major enumeration of the non-axis coordinates coincide when at most one
   // non-axis dim has extent > 1; then the fast kernels serve index_order 1 as well.
@@ -329,6 +330,7 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
   if (blocks > 1024) blocks = 1024;
   float *partial = nullptr;
   WCU_CHECK(cudaMallocAsync((void **)&partial, sizeof(float) * blocks, st));
+  ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * sp.n);
   sum_pass1_kernel<1><<<blocks, 256, 0, st>>>(base, sp, vec, partial);
   int rc = after_launch();
   if (rc == 0) {

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace weedcu {
 
@@ -22,6 +23,27 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int after_launch() {
   count_launch(1);
   return (int)cudaGetLastError();
+}
+
+struct ProfRec {
+  int cls;
+  cudaEvent_t e0, e1;
+  double work;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+bool prof_on() { return g_prof_on; }
+int prof_begin(int cls, cudaStream_t st, double work) {
+  ProfRec r;
+  r.cls = cls;
+  r.work = work;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_end(int idx, cudaStream_t st) {
+  if (idx >= 0 && idx < (int)g_prof.size()) cudaEventRecord(g_prof[(size_t)idx].e1, st);
 }
 
 static int current_device() {
@@ -193,6 +215,33 @@ int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
 int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
   if (!bytes) return 0;
   WCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, resolve_stream(stream)));
+  return 0;
+}
+int weedcu_prof_enable(int on) {
+  if (on) {
+    for (auto &p : g_prof) {
+      cudaEventDestroy(p.e0);
+      cudaEventDestroy(p.e1);
+    }
+    g_prof.clear();
+  }
+  g_prof_on = on != 0;
+  return 0;
+}
+int weedcu_prof_read(int cls, double *total_ms, uint64_t *launches, double *work) {
+  if (!total_ms || !launches || !work) return WEEDCU_EINVAL;
+  *total_ms = 0.0;
+  *launches = 0;
+  *work = 0.0;
+  for (auto &p : g_prof) {
+    if (p.cls != cls) continue;
+    WCU_CHECK(cudaEventSynchronize(p.e1));
+    float ms = 0.0f;
+    WCU_CHECK(cudaEventElapsedTime(&ms, p.e0, p.e1));
+    *total_ms += ms;
+    *launches += 1;
+    *work += p.work;
+  }
   return 0;
 }
 int weedcu_launch_count(uint64_t *count) {

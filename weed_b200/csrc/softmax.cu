@@ -432,6 +432,9 @@ int weedcu_softmax_real(int log_mode, const float *a, const weedcu_view *av, int
       axis >= av->rank || !same_shape(av, ov))
     return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
+  double elems = 1.0;
+  for (int d = 0; d < av->rank; ++d) elems *= av->shape[d];
+  ProfScope prof(WEEDCU_PROF_SOFTMAX, st, 8.0 * elems);
   return log_mode ? softmax_fwd_impl<true>(a, av, axis, out, ov, st)
                   : softmax_fwd_impl<false>(a, av, axis, out, ov, st);
 }
@@ -444,6 +447,9 @@ int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, 
       !same_shape(dinv, doutv))
     return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
+  double elems = 1.0;
+  for (int d = 0; d < dinv->rank; ++d) elems *= dinv->shape[d];
+  ProfScope prof(WEEDCU_PROF_SOFTMAX, st, 16.0 * elems);
   return log_mode ? softmax_bwd_impl<true>(din, dinv, out, ov, dout, doutv, axis, st)
                   : softmax_bwd_impl<false>(din, dinv, out, ov, dout, doutv, axis, st);
 }
@@ -453,6 +459,7 @@ int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, ui
                              void *stream) {
   if (!scores || !out || !batch || !Tq || !Tk) return WEEDCU_EINVAL;
   const int do_mask = (causal && Tq > 1) ? 1 : 0;
+  ProfScope prof(WEEDCU_PROF_SOFTMAX, resolve_stream(stream), 8.0 * (double)batch * Tq * Tk);
   if (batch_fastest) {
     const uint64_t inner = (uint64_t)batch * Tq;
     if (inner > 0xffffffffull) return WEEDCU_EINVAL;
@@ -471,6 +478,7 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
   cudaStream_t st = resolve_stream(stream);
   float *nll = nullptr;
   WCU_CHECK(cudaMallocAsync((void **)&nll, sizeof(float) * rows, st));
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 4.0 * (double)rows * V);
   ce_fwd_kernel<32><<<(rows + kRT - 1) / kRT, dim3(kRT, 32), 0, st>>>(logits + offset, rows, V, rs, vs,
                                                                     targets, lse, nll);
   int rc = after_launch();
@@ -491,6 +499,7 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
                              const float *dloss, float *dlogits, uint64_t d_offset, void *stream) {
   if (!logits || !targets || !lse || !dloss || !dlogits || !rows || !V) return WEEDCU_EINVAL;
   const uint64_t n = (uint64_t)rows * V;
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, resolve_stream(stream), 12.0 * (double)n);
   ce_bwd_kernel<<<grid_for(n, 256, 32), 256, 0, resolve_stream(stream)>>>(
       logits + offset, rows, V, rs, vs, targets, lse, dloss, dlogits + d_offset);
   return after_launch();

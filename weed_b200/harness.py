@@ -72,6 +72,10 @@ class Harness:
         sh = (C.c_uint32 * len(shape))(*shape)
         return self._ck(self.lib.wh_symbol(a.ctypes.data_as(C.c_void_p), C.c_uint32(a.size), C.c_int(len(shape)), sh))
 
+    def symbol_upload(self, h, src_ptr, n):
+        """Refill symbol tensor `h` from host memory at address src_ptr (int32[n]); async H2D."""
+        self._ck(self.lib.wh_symbol_upload(C.c_int64(h), C.c_void_p(src_ptr), C.c_uint32(n)))
+
     def view(self, h, offset, shape, stride):
         sh = (C.c_uint32 * len(shape))(*shape)
         st = (C.c_uint32 * len(stride))(*stride)

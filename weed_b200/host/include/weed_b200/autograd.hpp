@@ -29,4 +29,11 @@ TensorPtr bci_with_logits_loss(TensorPtr logits, TensorPtr y_true);
 // logits [B, T, V] (the reference assumes B == 1, cross_entropy_loss.hpp:22-27; any B works here:
 // rows = B*T), targets B*T token ids
 TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets);
+
+// Data-parallel training (no reference counterpart: Weed has no gradient exchange).
+// One process per GPU; `comm` is an NCCL communicator from weedcu_nccl_init. Gradients are
+// sum-all-reduced in place on the compute stream; the 1/world average is folded into the fused
+// optimiser kernels through backend_config().grad_scale.
+void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm);
+void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root);
 } // namespace Weed

@@ -126,4 +126,16 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
   TensorPtr gathered = Tensor::sum(selected, 1);
   return Tensor::mean(gathered) * real1(-1.0f);
 }
+
+void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm) {
+  for (const ParameterPtr &p : params) {
+    if (!p->grad) continue;
+    Tensor &g = *(p->grad);
+    throw_on_error(weedcu_nccl_allreduce_sum(comm, g.device_ptr(), g.storage->size, g.stream()), "allreduce_gradients");
+  }
+}
+void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root) {
+  for (const ParameterPtr &p : params)
+    throw_on_error(weedcu_nccl_broadcast(comm, p->device_ptr(), p->storage->size, root, p->stream()), "broadcast_parameters");
+}
 } // namespace Weed

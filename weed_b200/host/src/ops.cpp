@@ -75,7 +75,24 @@ void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
     bv.offset = off;
     for (int d = 0; d < WEEDCU_MAX_RANK; ++d) bv.stride[d] = 0;
   }
-  throw_on_error(weedcu_inplace_real(op, da.ptr, &av, db.ptr, &bv, da.stream), name);
+  // Destination with broadcast (stride-0) dims: the reference's serial loop visits every flat index,
+  // so each stored element is updated once per broadcast index (this is how sgd_step ends up
+  // applying a bias update B times after match_shape mutated the Parameter, sgd.hpp:29-35).
+  // On the device that would be a write race; when b is broadcast along the same dims the effect is
+  // `times` identical updates, issued as `times` in-order launches over the collapsed views.
+  uint64_t times = 1;
+  for (int d = 0; d < av.rank; ++d) {
+    if (av.shape[d] > 1U && av.stride[d] == 0U) {
+      if (bv.stride[d] != 0U)
+        throw std::domain_error(std::string(name) + ": accumulating a non-broadcast source into a broadcast destination is not supported");
+      times *= av.shape[d];
+      av.shape[d] = 1U;
+      bv.shape[d] = 1U;
+    }
+  }
+  if (times > 4096) throw std::domain_error(std::string(name) + ": broadcast destination repeated too many times");
+  for (uint64_t t = 0; t < times; ++t)
+    throw_on_error(weedcu_inplace_real(op, da.ptr, &av, db.ptr, &bv, da.stream), name);
 }
 
 void unary(int op, real1 param, const Tensor &a, Tensor &out, const char *name) {
