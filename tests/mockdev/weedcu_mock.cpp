@@ -1,0 +1,138 @@
+// weedcu_mock.cpp — TEST INFRASTRUCTURE ONLY. Never shipped, never loaded by weed_b200/.
+//
+// A host-memory stand-in for libweedcu.so that implements every entry point of include/weedcu.h by
+// forwarding to the C oracle (oracle/weed_oracle.c). It exists so that the HOST logic of the product
+// (weed_b200/host: views, broadcasting, the autograd graph, module composition, optimiser plumbing)
+// can be exercised by `pytest -m "not gpu"` in a container without a GPU: tests/mockdev/Makefile
+// links a second copy of the host library + harness against this file. "Device memory" is malloc'd
+// host memory, streams and events are no-ops, every "launch" runs synchronously.
+// The GPU tests (-m gpu) and bench.py use the real CUDA library; nothing here is a fallback.
+#include "weedcu.h"
+extern "C" {
+#include "weed_oracle.h"
+}
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+static uint64_t g_launches = 0;
+#define VIEW(v) reinterpret_cast<const wo_view *>(v)
+#define MAT(m) reinterpret_cast<const wo_mat *>(m)
+#define RUN(expr) (++g_launches, ((expr) == 0 ? 0 : WEEDCU_EINVAL))
+
+extern "C" {
+int weedcu_device_count(int *count) { if (!count) return WEEDCU_EINVAL; *count = 1; return 0; }
+int weedcu_set_device(int) { return 0; }
+int weedcu_get_device(int *device) { if (!device) return WEEDCU_EINVAL; *device = 0; return 0; }
+int weedcu_device_info(int, char *name, int name_len, uint64_t *total_mem, int *sm_count, int *cc_major, int *cc_minor) {
+  if (name && name_len > 0) { strncpy(name, "mock (host memory, oracle-backed)", (size_t)name_len - 1); name[name_len - 1] = 0; }
+  if (total_mem) *total_mem = 1ull << 34;
+  if (sm_count) *sm_count = 1;
+  if (cc_major) *cc_major = 0;
+  if (cc_minor) *cc_minor = 0;
+  return 0;
+}
+const char *weedcu_error_string(int code) { return code == 0 ? "ok" : (code == WEEDCU_EINVAL ? "weedcu(mock): invalid argument" : "weedcu(mock): error"); }
+void *weedcu_default_stream(void) { return (void *)0x1; }
+int weedcu_set_default_stream(void *) { return 0; }
+int weedcu_stream_create(void **stream) { if (!stream) return WEEDCU_EINVAL; *stream = (void *)0x1; return 0; }
+int weedcu_stream_destroy(void *) { return 0; }
+int weedcu_stream_sync(void *) { return 0; }
+int weedcu_stream_wait_event(void *, void *) { return 0; }
+int weedcu_event_create(void **event) { if (!event) return WEEDCU_EINVAL; *event = new double(0); return 0; }
+int weedcu_event_destroy(void *event) { delete (double *)event; return 0; }
+int weedcu_event_record(void *event, void *) {
+  *(double *)event = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  return 0;
+}
+int weedcu_event_sync(void *) { return 0; }
+int weedcu_event_elapsed_ms(void *start, void *stop, float *ms) { if (!ms) return WEEDCU_EINVAL; *ms = (float)(*(double *)stop - *(double *)start); return 0; }
+int weedcu_malloc(void **ptr, size_t bytes, void *) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); return *ptr ? 0 : 2; }
+int weedcu_free(void *ptr, void *) { free(ptr); return 0; }
+int weedcu_mem_info(uint64_t *f, uint64_t *t) { if (f) *f = 1ull << 33; if (t) *t = 1ull << 34; return 0; }
+int weedcu_host_alloc(void **ptr, size_t bytes) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); return *ptr ? 0 : 2; }
+int weedcu_host_free(void *ptr) { free(ptr); return 0; }
+int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
+int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
+int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *) { memmove(dst, src, bytes); return 0; }
+int weedcu_launch_count(uint64_t *count) { if (!count) return WEEDCU_EINVAL; *count = g_launches; return 0; }
+int weedcu_prof_enable(int) { return 0; }
+int weedcu_prof_read(int, double *t, uint64_t *n, double *w) { if (t) *t = 0; if (n) *n = 0; if (w) *w = 0; return 0; }
+
+int weedcu_fill_real(float *p, uint64_t n, float value, void *) { return RUN(wo_fill_real(p, n, value)); }
+int weedcu_fill_int(int32_t *p, uint64_t n, int32_t value, void *) { for (uint64_t i = 0; i < n; ++i) p[i] = value; ++g_launches; return 0; }
+int weedcu_binary_real(int op, const float *a, const weedcu_view *av, const float *b, const weedcu_view *bv, float *out, const weedcu_view *ov, void *) {
+  return RUN(wo_binary_real(op, a, VIEW(av), b, VIEW(bv), out, VIEW(ov)));
+}
+int weedcu_inplace_real(int op, float *a, const weedcu_view *av, const float *b, const weedcu_view *bv, void *) {
+  return RUN(wo_inplace_real(op, a, VIEW(av), b, VIEW(bv)));
+}
+int weedcu_copy_real(float *dst, const weedcu_view *dv, const float *src, const weedcu_view *sv, void *) { return RUN(wo_copy_real(dst, VIEW(dv), src, VIEW(sv))); }
+int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av, float *out, const weedcu_view *ov, void *) {
+  return RUN(wo_unary_real(op, param, a, VIEW(av), out, VIEW(ov)));
+}
+int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, void *) {
+  return RUN(wo_unary_grad_real(op, din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv)));
+}
+int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *out, int index_order, void *) { return RUN(wo_reduce_real(a, VIEW(av), axis, out, index_order)); }
+int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout, const weedcu_view *doutv, int axis, int index_order, void *) {
+  return RUN(wo_reduce_grad_real(din, VIEW(dinv), dout, VIEW(doutv), axis, index_order));
+}
+int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *) { return RUN(wo_sum_real(a, VIEW(av), scale, out)); }
+int weedcu_softmax_real(int log_mode, const float *a, const weedcu_view *av, int axis, float *out, const weedcu_view *ov, void *) {
+  return RUN(wo_softmax_real(log_mode, a, VIEW(av), axis, out, VIEW(ov)));
+}
+int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, const float *out, const weedcu_view *ov, const float *dout, const weedcu_view *doutv, int axis, void *) {
+  return RUN(wo_softmax_grad_real(log_mode, din, VIEW(dinv), out, VIEW(ov), dout, VIEW(doutv), axis));
+}
+int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq, uint32_t Tk, float divisor, float mask_val, int causal, int batch_fastest, void *) {
+  return RUN(wo_attn_softmax_real(scores, out, batch, Tq, Tk, divisor, mask_val, causal, batch_fastest));
+}
+int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, float *lse, float *loss, void *) {
+  return RUN(wo_cross_entropy_fwd(logits, offset, rows, V, rs, vs, targets, lse, loss));
+}
+int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse, const float *dloss,
+                             float *dlogits, uint64_t d_offset, void *) {
+  return RUN(wo_cross_entropy_bwd(logits, offset, rows, V, rs, vs, targets, lse, dloss, dlogits, d_offset));
+}
+int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, void *) {
+  return RUN(wo_layernorm_fwd(x, rows, F, gamma, beta, eps, y, mean, rstd));
+}
+int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma, const float *mean, const float *rstd, float *dx, float *dgamma, float *dbeta,
+                         int grad_mode, void *) {
+  return RUN(wo_layernorm_bwd(x, dy, rows, F, gamma, mean, rstd, dx, dgamma, dbeta, grad_mode));
+}
+int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n, const float *W, uint64_t w_off, uint32_t w_s0, uint32_t w_s1, uint32_t D, float *out,
+                            uint64_t o_off, uint32_t o_s0, uint32_t o_s1, void *) {
+  return RUN(wo_embedding_gather(idx, idx_off, idx_stride, n, W, w_off, w_s0, w_s1, D, out, o_off, o_s0, o_s1));
+}
+int weedcu_embedding_scatter_add(float *dW, uint64_t w_off, uint32_t w_s0, uint32_t w_s1, const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n, uint32_t D,
+                                 const float *dout, uint64_t o_off, uint32_t o_s0, uint32_t o_s1, void *) {
+  return RUN(wo_embedding_scatter_add(dW, w_off, w_s0, w_s1, idx, idx_off, idx_stride, n, D, dout, o_off, o_s0, o_s1));
+}
+int weedcu_triu_fill_real(float *a, const weedcu_view *av, float val, uint32_t diagonal, void *) { return RUN(wo_triu_fill_real(a, VIEW(av), val, diagonal)); }
+int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, int32_t *out, void *) { return RUN(wo_argmax_rows(x, offset, rows, V, rs, vs, out)); }
+int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale, void *) { return RUN(wo_sgd_step(p, g, n, lr, gscale)); }
+int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float gscale, void *) {
+  return RUN(wo_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gscale));
+}
+int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
+                       int accumulate, int precision, void *) {
+  if (precision == WEEDCU_GEMM_BF16) return RUN(wo_matmul_bf16_model(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, batch, accumulate));
+  return RUN(wo_matmul_real(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, batch, accumulate));
+}
+int weedcu_gemm_bf16(const uint16_t *, int, uint64_t, const uint16_t *, int, uint64_t, float *, uint64_t, uint32_t, uint32_t, uint32_t, int, void *) { return WEEDCU_ENOSUP; }
+int weedcu_pack_bf16(const float *, uint64_t, uint32_t, uint32_t, uint32_t, uint32_t, uint16_t *, int, void *) { return WEEDCU_ENOSUP; }
+int weedcu_gemm_workspace_bytes(uint32_t, uint32_t, uint32_t, uint32_t, int, uint64_t *bytes) { if (bytes) *bytes = 0; return 0; }
+// collectives: single-process identity (world size 1); the gloo world_size-2 tests patch these from Python
+int weedcu_nccl_load(const char *) { return 0; }
+int weedcu_nccl_unique_id(void *id128) { if (id128) memset(id128, 0, 128); return 0; }
+int weedcu_nccl_init(const void *, int, int, void **comm) { if (comm) *comm = (void *)0x2; return 0; }
+int weedcu_nccl_destroy(void *) { return 0; }
+typedef int (*mock_allreduce_hook)(float *buf, uint64_t n);
+static mock_allreduce_hook g_allreduce_hook = nullptr, g_bcast_hook = nullptr;
+void weedcu_mock_set_collective_hooks(mock_allreduce_hook allreduce, mock_allreduce_hook bcast) { g_allreduce_hook = allreduce; g_bcast_hook = bcast; }
+int weedcu_nccl_allreduce_sum(void *, float *buf, uint64_t n, void *) { ++g_launches; return g_allreduce_hook ? g_allreduce_hook(buf, n) : 0; }
+int weedcu_nccl_broadcast(void *, float *buf, uint64_t n, int, void *) { ++g_launches; return g_bcast_hook ? g_bcast_hook(buf, n) : 0; }
+}

@@ -65,6 +65,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// smem -> global tile store through TMA (clips at the tensor edges); `.add` variant reduces into C
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -132,12 +150,17 @@ struct Params {
   uint32_t M, N, K, batch;
   uint32_t tiles_m, tiles_n;
   int accumulate;
+  int tma_store; // C goes out through TMA (needs 16-B aligned base / leading dimension); else direct stores
 };
+
+constexpr uint32_t EPI_COLS = 32;                             // columns per epilogue chunk
+constexpr uint32_t EPI_BUF_BYTES = EPI_COLS * BLOCK_M * 4;    // one [32 cols][128 rows] fp32 staging buffer
 
 template <uint32_t BLOCK_N, uint32_t STAGES> struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr uint32_t BAR_OFF = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t EPI_OFF = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t BAR_OFF = EPI_OFF + 2 * EPI_BUF_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
 };
 

@@ -37,6 +37,83 @@ inline void require_real(const Tensor &t, const char *msg) {
   if (t.storage->dtype != DType::REAL) throw std::invalid_argument(msg);
 }
 
+// The reference's CPU loops resolve ONE flat index through every operand's own (shape, stride)
+// (BaseTensor::get_storage_index), so operands only need equal element counts, not equal shapes:
+// autograd routinely pairs e.g. a [1,T] gradient with a [1,T,1] contribution after
+// squeeze()/unsqueeze(). The device kernels want one common shape, so bring the views to it:
+// drop extent-1 dims, broadcast true scalars, and re-express a dense operand in the other's shape.
+void strip_unit_dims(weedcu_view &v) {
+  int r = 0;
+  for (int d = 0; d < v.rank; ++d) {
+    if (v.shape[d] == 1U) continue;
+    v.shape[r] = v.shape[d];
+    v.stride[r] = v.stride[d];
+    ++r;
+  }
+  if (r == 0) {
+    v.shape[0] = 1U;
+    v.stride[0] = 0U;
+    r = 1;
+  }
+  for (int d = r; d < WEEDCU_MAX_RANK; ++d) {
+    v.shape[d] = 1U;
+    v.stride[d] = 0U;
+  }
+  v.rank = r;
+}
+bool same_dims(const weedcu_view &a, const weedcu_view &b) {
+  if (a.rank != b.rank) return false;
+  for (int d = 0; d < a.rank; ++d)
+    if (a.shape[d] != b.shape[d]) return false;
+  return true;
+}
+bool all_broadcast(const weedcu_view &v) {
+  for (int d = 0; d < v.rank; ++d)
+    if (v.shape[d] > 1U && v.stride[d]) return false;
+  return true;
+}
+bool dense_run(const weedcu_view &v) { // contiguous column-major run: flat index == storage offset
+  uint64_t expect = 1;
+  for (int d = 0; d < v.rank; ++d) {
+    if (v.shape[d] == 1U) continue;
+    if (v.stride[d] != expect) return false;
+    expect *= v.shape[d];
+  }
+  return true;
+}
+void conform_views(std::vector<weedcu_view *> views, const char *name) {
+  for (weedcu_view *v : views) strip_unit_dims(*v);
+  // reference shape: the first operand that is neither a pure broadcast nor a plain dense run
+  // (those two kinds can take any shape); else the first non-broadcast one; else the first
+  const weedcu_view *ref = nullptr;
+  for (weedcu_view *v : views)
+    if (!all_broadcast(*v) && !dense_run(*v)) { ref = v; break; }
+  if (!ref)
+    for (weedcu_view *v : views)
+      if (!all_broadcast(*v)) { ref = v; break; }
+  if (!ref) ref = views[0];
+  const weedcu_view r = *ref;
+  for (weedcu_view *v : views) {
+    if (same_dims(*v, r)) continue;
+    const uint64_t off = v->offset;
+    if (all_broadcast(*v)) {
+      *v = r;
+      v->offset = off;
+      for (int d = 0; d < WEEDCU_MAX_RANK; ++d) v->stride[d] = 0U;
+    } else if (dense_run(*v)) {
+      *v = r;
+      v->offset = off;
+      uint32_t acc = 1U;
+      for (int d = 0; d < v->rank; ++d) {
+        v->stride[d] = (v->shape[d] == 1U) ? 0U : acc;
+        acc *= v->shape[d];
+      }
+    } else {
+      throw std::invalid_argument(std::string(name) + ": operands with equal element counts but incompatible strided shapes");
+    }
+  }
+}
+
 void binary(int op, const Tensor &a, const Tensor &b, Tensor &out, const char *name) {
   validate_all_same_device({&a, &b, &out}, name);
   const tcapint aSize = a.get_broadcast_size(), bSize = b.get_broadcast_size(), oSize = out.get_broadcast_size();
@@ -44,21 +121,7 @@ void binary(int op, const Tensor &a, const Tensor &b, Tensor &out, const char *n
   if (aSize != oSize) throw std::invalid_argument(std::string("In ") + name + "(a, b, out), out size does not match input size!");
   const Dev da = dev_of(a, name), db = dev_of(b, name), dout = dev_of(out, name);
   weedcu_view av = a.view(), bv = b.view(), ov = out.view();
-  // operands may carry different ranks for the same element count (e.g. a scalar [1] against
-  // [M,N]); present every operand with out's shape, broadcasting true scalars
-  auto conform = [&](const Tensor &t, weedcu_view &v) {
-    if (t.shape == out.shape) return;
-    if (t.is_scalar()) {
-      const uint64_t off = v.offset;
-      v = ov;
-      v.offset = off;
-      for (int d = 0; d < WEEDCU_MAX_RANK; ++d) v.stride[d] = 0;
-      return;
-    }
-    throw std::invalid_argument(std::string(name) + ": operand shapes differ (call match_shape first)");
-  };
-  conform(a, av);
-  conform(b, bv);
+  conform_views({&ov, &av, &bv}, name);
   throw_on_error(weedcu_binary_real(op, da.ptr, &av, db.ptr, &bv, dout.ptr, &ov, dout.stream), name);
 }
 
@@ -68,29 +131,54 @@ void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
     throw std::invalid_argument(std::string("In ") + name + "(a, b), 'a' size does not match 'b' size!");
   const Dev da = dev_of(a, name), db = dev_of(b, name);
   weedcu_view av = a.view(), bv = b.view();
-  if (b.shape != a.shape) {
-    if (!b.is_scalar()) throw std::invalid_argument(std::string(name) + ": operand shapes differ (call match_shape first)");
-    const uint64_t off = bv.offset;
-    bv = av;
-    bv.offset = off;
-    for (int d = 0; d < WEEDCU_MAX_RANK; ++d) bv.stride[d] = 0;
-  }
   // Destination with broadcast (stride-0) dims: the reference's serial loop visits every flat index,
   // so each stored element is updated once per broadcast index (this is how sgd_step ends up
   // applying a bias update B times after match_shape mutated the Parameter, sgd.hpp:29-35).
   // On the device that would be a write race; when b is broadcast along the same dims the effect is
   // `times` identical updates, issued as `times` in-order launches over the collapsed views.
   uint64_t times = 1;
-  for (int d = 0; d < av.rank; ++d) {
-    if (av.shape[d] > 1U && av.stride[d] == 0U) {
-      if (bv.stride[d] != 0U)
-        throw std::domain_error(std::string(name) + ": accumulating a non-broadcast source into a broadcast destination is not supported");
-      times *= av.shape[d];
-      av.shape[d] = 1U;
-      bv.shape[d] = 1U;
+  if (same_dims(av, bv)) {
+    bool needs_reduce = false;
+    for (int d = 0; d < av.rank; ++d)
+      if (av.shape[d] > 1U && av.stride[d] == 0U && bv.stride[d] != 0U) needs_reduce = true;
+    if (needs_reduce) {
+      // a[j] (+/-)= sum over the broadcast indices of b: what the serial loop accumulates when a
+      // stale, un-reduced gradient meets a match_shape-mutated Parameter (e.g. adam_step on a bias
+      // whose add node never ran). Sum b over those dims (intended index order), then recurse.
+      struct QuirkOff {
+        bool prev;
+        QuirkOff() : prev(backend_config().ref_index_quirks) { backend_config().ref_index_quirks = false; }
+        ~QuirkOff() { backend_config().ref_index_quirks = prev; }
+      } guard;
+      TensorPtr bt = std::make_shared<Tensor>(b);
+      bt->requires_grad = false;
+      bt->grad = nullptr;
+      bt->grad_node = nullptr;
+      Tensor a2(a);
+      for (int d = (int)a.shape.size() - 1; d >= 0; --d) {
+        if (a.shape[(size_t)d] > 1U && a.stride[(size_t)d] == 0U && bt->stride[(size_t)d] != 0U) {
+          bt = Tensor::sum(bt, (symint)d);
+          a2.shape[(size_t)d] = 1U;
+        }
+      }
+      in_place(op, a2, *bt, name);
+      return;
+    }
+    for (int d = 0; d < av.rank; ++d) {
+      if (av.shape[d] > 1U && av.stride[d] == 0U) {
+        if (bv.stride[d] != 0U)
+          throw std::domain_error(std::string(name) + ": accumulating a non-broadcast source into a broadcast destination is not supported");
+        times *= av.shape[d];
+        av.shape[d] = 1U;
+        bv.shape[d] = 1U;
+      }
     }
   }
   if (times > 4096) throw std::domain_error(std::string(name) + ": broadcast destination repeated too many times");
+  conform_views({&av, &bv}, name);
+  for (int d = 0; d < av.rank; ++d)
+    if (av.shape[d] > 1U && av.stride[d] == 0U)
+      throw std::domain_error(std::string(name) + ": accumulating into a broadcast destination is not supported for these shapes");
   for (uint64_t t = 0; t < times; ++t)
     throw_on_error(weedcu_inplace_real(op, da.ptr, &av, db.ptr, &bv, da.stream), name);
 }
@@ -100,7 +188,8 @@ void unary(int op, real1 param, const Tensor &a, Tensor &out, const char *name) 
   if (a.get_broadcast_size() != out.get_broadcast_size())
     throw std::invalid_argument(std::string("In Weed::") + name + "(a, out), out size does not match input size!");
   const Dev da = dev_of(a, name), dout = dev_of(out, name);
-  const weedcu_view av = a.view(), ov = out.view();
+  weedcu_view av = a.view(), ov = out.view();
+  conform_views({&ov, &av}, name);
   throw_on_error(weedcu_unary_real(op, param, da.ptr, &av, dout.ptr, &ov, dout.stream), name);
 }
 
@@ -111,18 +200,10 @@ void unary_grad(int op, Tensor &din, const Tensor &in, const Tensor &dout, const
     throw std::invalid_argument(std::string("In Weed::") + name + "(din, in, dout), sizes do not match!");
   const Dev dd = dev_of(din, name), di = dev_of(in, name), dg = dev_of(dout, name);
   weedcu_view dv = din.view(), iv = in.view(), gv = dout.view();
-  auto conform = [&](const Tensor &t, weedcu_view &v) {
-    if (t.shape == din.shape) return;
-    if (!t.is_scalar()) throw std::invalid_argument(std::string(name) + ": operand shapes differ");
-    const uint64_t off = v.offset;
-    v = dv;
-    v.offset = off;
-    for (int d = 0; d < WEEDCU_MAX_RANK; ++d) v.stride[d] = 0;
-  };
-  conform(in, iv);
-  conform(dout, gv);
+  conform_views({&dv, &iv, &gv}, name);
   throw_on_error(weedcu_unary_grad_real(op, dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, dd.stream), name);
 }
+
 
 weedcu_mat mat_of(const Tensor &t, tcapint extra_offset = 0U, uint64_t batch_stride = 0U) {
   weedcu_mat m;

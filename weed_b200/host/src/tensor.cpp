@@ -31,6 +31,24 @@ std::vector<TensorPtr> grad_parents(const std::vector<TensorPtr> &parents) {
     if (p->requires_grad) out.push_back(p);
   return out;
 }
+// Gradient of `t` viewed at t's full shape. In the fused configuration broadcast tensors keep their
+// gradient at real extent (Tensor::make_gradient); ops that need it element-for-element with `t`
+// materialise it here and settle_grad() sums it back, exactly the reference's own sequence.
+TensorPtr full_grad(const TensorPtr &t) {
+  TensorPtr g = view_copy(t->grad);
+  if (g->get_broadcast_size() != t->get_broadcast_size()) {
+    g->match_shape(t);
+    g->materialize_broadcast();
+  }
+  return g;
+}
+void settle_grad(const TensorPtr &t, const TensorPtr &g) {
+  t->grad = g;
+  bool widened = false;
+  for (size_t i = 0U; i < t->stride.size() && i < g->shape.size(); ++i)
+    if (!t->stride[i] && g->shape.size() == t->shape.size() && g->shape[i] > 1U) widened = true;
+  if (widened) t->reduce_grad_broadcast();
+}
 symint wrap_axis(symint axis, size_t rank) {
   while (axis < 0) axis += (symint)rank;
   return axis;
@@ -145,8 +163,17 @@ TensorPtr Tensor::make_gradient(const std::vector<tcapint> &shp, const bool &s, 
 }
 void Tensor::make_gradient(const bool &) { // tensor.cpp:78-114 (device choice is not size-based here)
   if (!requires_grad) return;
-  if (grad && grad->shape == shape) return;
-  grad = Tensor::make_gradient(shape, false, storage->dtype, storage->device, storage->get_device_id());
+  std::vector<tcapint> gshape = shape;
+  if (backend_config().fused) {
+    // A tensor broadcast by match_shape (a bias that became [B,T,F] with strides [0,0,1]) would get
+    // a full [B,T,F] gradient in the reference, which every backward then fills, adds into and
+    // sums back down (tensor.cpp:1117-1134): 5 passes over B*T*F per bias. The fused path keeps
+    // the gradient at the tensor's real extent ([1,1,F]) and reduces contributions into it.
+    for (size_t i = 0U; i < gshape.size(); ++i)
+      if (!stride[i]) gshape[i] = 1U;
+  }
+  if (grad && grad->shape == gshape) return;
+  grad = Tensor::make_gradient(gshape, false, storage->dtype, storage->device, storage->get_device_id());
 }
 TensorPtr Tensor::allocate_scalar_like(const Tensor &orig, const bool &rg) {
   return allocate_like(std::vector<tcapint>{1U}, std::vector<tcapint>{0U}, orig, orig.storage->dtype, rg, false);
@@ -314,9 +341,9 @@ TensorPtr Tensor::softmax(const TensorPtr x, symint axis) {
 void Tensor::make_softmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, out, axis]() {
-    TensorPtr x_grad = view_copy(x->grad);
+    TensorPtr x_grad = full_grad(x);
     Weed::softmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
-    x->grad = x_grad;
+    settle_grad(x, x_grad);
   });
 }
 TensorPtr Tensor::logsoftmax(const TensorPtr x, symint axis) {
@@ -330,9 +357,9 @@ TensorPtr Tensor::logsoftmax(const TensorPtr x, symint axis) {
 void Tensor::make_logsoftmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, out, axis]() {
-    TensorPtr x_grad = view_copy(x->grad);
+    TensorPtr x_grad = full_grad(x);
     Weed::logsoftmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
-    x->grad = x_grad;
+    settle_grad(x, x_grad);
   });
 }
 
@@ -490,9 +517,9 @@ TensorPtr unary_op(TensorPtr a, UnaryFwd fwd, UnaryBwd bwd, bool uses_output) {
   if (rg) {
     out->make_gradient();
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out, bwd, uses_output]() {
-      TensorPtr a_grad = view_copy(a->grad);
+      TensorPtr a_grad = full_grad(a);
       bwd(*a_grad, uses_output ? *out : *a, *(out->grad));
-      a->grad = a_grad;
+      settle_grad(a, a_grad);
     });
   }
   return out;
@@ -508,9 +535,9 @@ TensorPtr Tensor::cos(TensorPtr a) { return unary_op(a, Weed::cos, Weed::cos_gra
   void Tensor::fn(TensorPtr a, TensorPtr out) {                                                    \
     out->make_gradient();                                                                          \
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out]() {               \
-      TensorPtr a_grad = view_copy(a->grad);                                                       \
+      TensorPtr a_grad = full_grad(a);                                                             \
       bwd(*a_grad, *src, *(out->grad));                                                            \
-      a->grad = a_grad;                                                                            \
+      settle_grad(a, a_grad);                                                                      \
     });                                                                                            \
   }
 WEED_NODE_ONLY(make_abs_node, Weed::abs_grad, a)
@@ -534,9 +561,74 @@ TensorPtr Tensor::gelu(const TensorPtr x) { // tensor.cpp:841-851
 namespace {
 // Accumulate `contribution` into parent's gradient with the reference's broadcast handling:
 // match_shape -> materialize_broadcast -> (+|-)= -> reduce_grad_broadcast (tensor.cpp:1117-1134).
+bool dense_like(const Tensor &t, const std::vector<tcapint> &shape) {
+  if (t.shape != shape) return false;
+  tcapint expect = 1U;
+  for (size_t i = 0U; i < shape.size(); ++i) {
+    if (shape[i] == 1U) continue;
+    if (t.stride[i] != expect) return false;
+    expect *= shape[i];
+  }
+  return true;
+}
+// Fused accumulation into a broadcast parent (see Tensor::make_gradient): sum the contribution over
+// the parent's broadcast dims (one reduction pass) and add the result into the real-extent gradient.
+bool accumulate_reduced(const TensorPtr &parent, const TensorPtr &like, const Tensor &contribution, bool subtract) {
+  TensorPtr pv = view_copy(parent);
+  // the parent's own (match_shape-mutated) view says which dims are broadcast; `like` may have lost
+  // or gained unit dims since (squeeze / unsqueeze mutate tensors in place)
+  if (pv->shape.size() < like->shape.size() && !pv->match_shape(like)) return false;
+  const size_t rank = pv->shape.size();
+  bool any = false;
+  size_t prefix = 0U;
+  while (prefix < rank && (pv->shape[prefix] == 1U || !pv->stride[prefix])) ++prefix;
+  bool prefix_only = true;
+  std::vector<tcapint> rshape = pv->shape;
+  for (size_t d = 0U; d < rank; ++d) {
+    if (pv->shape[d] > 1U && !pv->stride[d]) {
+      any = true;
+      rshape[d] = 1U;
+      if (d >= prefix) prefix_only = false;
+    }
+  }
+  if (!any || !dense_like(contribution, contribution.shape) || contribution.get_broadcast_size() != pv->get_broadcast_size()) return false;
+  tcapint rcount = 1U;
+  for (tcapint s : rshape) rcount *= s;
+  if (!parent->grad || parent->grad->get_broadcast_size() != rcount) return false;
+  struct QuirkOff { // internal reductions always use the intended index order
+    bool prev;
+    QuirkOff() : prev(backend_config().ref_index_quirks) { backend_config().ref_index_quirks = false; }
+    ~QuirkOff() { backend_config().ref_index_quirks = prev; }
+  } guard;
+  TensorPtr c = std::make_shared<Tensor>(contribution);
+  c->requires_grad = false;
+  c->grad = nullptr;
+  c->grad_node = nullptr;
+  if (prefix_only) { // leading dims are the broadcast ones (bias / gamma): one [P, rest] column sum
+    tcapint P = 1U, rest = 1U;
+    for (size_t d = 0U; d < rank; ++d) (d < prefix ? P : rest) *= pv->shape[d];
+    c->BaseTensor::reshape({(symint)P, (symint)rest});
+    c = Tensor::sum(c, 0);
+  } else {
+    c->BaseTensor::reshape(std::vector<symint>(pv->shape.begin(), pv->shape.end()));
+    for (symint d = (symint)rank - 1; d >= 0; --d)
+      if (pv->shape[(size_t)d] > 1U && !pv->stride[(size_t)d]) c = Tensor::sum(c, d);
+  }
+  TensorPtr g = view_copy(parent->grad);
+  if (subtract) Weed::sub_in_place(*g, *c);
+  else Weed::add_in_place(*g, *c);
+  parent->grad = g;
+  return true;
+}
 void accumulate(const TensorPtr &parent, const TensorPtr &like, const Tensor &contribution, bool subtract) {
+  if (backend_config().fused && accumulate_reduced(parent, like, contribution, subtract)) return;
   TensorPtr g = view_copy(parent->grad);
   g->match_shape(like);
+  if (g->get_broadcast_size() != contribution.get_broadcast_size()) {
+    // real-extent gradient of a broadcast parent whose rank no longer lines up with `like`
+    TensorPtr pv = view_copy(parent);
+    g->match_shape(pv);
+  }
   g->materialize_broadcast();
   if (subtract) Weed::sub_in_place(*g, contribution);
   else Weed::add_in_place(*g, contribution);
