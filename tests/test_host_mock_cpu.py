@@ -17,7 +17,7 @@ MOCK_DIR = os.path.join(ROOT, "tests", "mockdev")
 def P():
     from weed_b200.harness import GPU, Harness
     subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
-    h = Harness(os.path.join(MOCK_DIR, "libweed_b200_harness.so"), GPU)
+    h = Harness(os.path.join(MOCK_DIR, "libweed_b200_mock_harness.so"), GPU)
     assert h.backend() == "weed_b200"
     return h
 

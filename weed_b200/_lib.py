@@ -60,7 +60,7 @@ def weedcu():
         raise WeedcuError(
             f"{path} is missing: the CUDA extension is not built. There is no CPU fallback; "
             "run `python -c 'import __graft_entry__ as g; g.build()'` first.")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)  # RTLD_LOCAL: dependants find it through their own DT_NEEDED + $ORIGIN rpath
     lib.weedcu_error_string.restype = C.c_char_p
     lib.weedcu_default_stream.restype = C.c_void_p
     _lib = lib

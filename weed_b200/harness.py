@@ -39,7 +39,9 @@ class Harness:
     # ---------------------------------------------------------------- construction helpers
     @classmethod
     def product(cls):
-        """This repo's host library on the GPU. Loads libweedcu.so first (RTLD_GLOBAL)."""
+        """This repo's host library on the GPU (libweed_b200_harness.so -> libweed_b200.so ->
+        libweedcu.so, resolved through $ORIGIN rpaths). weedcu() is loaded first so that a missing
+        CUDA extension fails with the explicit no-fallback error."""
         from ._lib import weedcu
         weedcu()
         return cls(os.path.join(_HERE, "libweed_b200_harness.so"), GPU)
