@@ -272,24 +272,49 @@ def main_ours(args):
     losses = []
 
     def resident_step(s):
+        # the loss handle keeps the step's autograd graph (all activations) alive: drop the previous
+        # one as soon as the next step is issued; nothing is read back inside the timed loop
         st, sg = pairs[s % len(pairs)]
-        losses.append(P.train_step_tokens(model, opt, st, sg))
+        h = P.train_step_tokens(model, opt, st, sg)
+        for old in losses:
+            P.free(old)
+        losses.clear()
+        losses.append(h)
 
+    first_loss = None
     for s in range(args.warmup):
         resident_step(s)
-    first_loss = float(P.read(losses[0])[0]) if losses else None
+        if s == 0:
+            first_loss = float(P.read(losses[0])[0])
     for h in losses:
         P.free(h)
     losses.clear()
 
+    def host_stats():
+        a, b, c, d = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
+        lib.weedcu_host_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
+
     n0, n1 = C.c_uint64(), C.c_uint64()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     lib.weedcu_launch_count(C.byref(n0))
-    ms = timed(lambda s: resident_step(args.warmup + s), args.steps)
+    hs0 = host_stats()
+    host_t0 = time.perf_counter()
+    host_issue = [0.0]
+
+    def timed_step(s):
+        resident_step(args.warmup + s)
+        host_issue[0] = time.perf_counter() - host_t0
+
+    ms = timed(timed_step, args.steps)
+    hs1 = host_stats()
     lib.weedcu_launch_count(C.byref(n1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
+    host = {"issue_ms_per_step": host_issue[0] * 1000.0 / args.steps,
+            "pool_malloc_ms_per_step": (hs1[0] - hs0[0]) / args.steps, "pool_mallocs_per_step": (hs1[1] - hs0[1]) / args.steps,
+            "pool_free_ms_per_step": (hs1[2] - hs0[2]) / args.steps, "pool_frees_per_step": (hs1[3] - hs0[3]) / args.steps}
     last_loss = float(P.read(losses[-1])[0])
     for h in losses:
         P.free(h)
@@ -381,7 +406,7 @@ def main_ours(args):
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 2 * ntok * 4, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(n1.value - n0.value), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "kernel_breakdown": breakdown, "model_tflops": step_flops(cfg) * world / (ms_per_step / 1000.0) / 1e12}
+                "kernel_breakdown": breakdown, "host": host, "model_tflops": step_flops(cfg) * world / (ms_per_step / 1000.0) / 1e12}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -401,6 +426,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--vocab", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -76,6 +76,7 @@ int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_launch_count(uint64_t *count);   /* kernels launched by this library so far */
+int weedcu_host_stats(double *malloc_ms, uint64_t *mallocs, double *free_ms, uint64_t *frees);
 
 /* ------------------------------------------------------------------ F1 fills
  * GpuDevice::ClearRealBuffer / FillOnesReal / FillValueReal (src/devices/gpu_device.cpp:314-386);

@@ -167,7 +167,8 @@ template <uint32_t BLOCK_N, uint32_t STAGES> struct SmemLayout {
 // A_MN / B_MN: operand is MN-major (1) or K-major (0).
 template <uint32_t BLOCK_N, uint32_t STAGES, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, Params p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   constexpr uint32_t NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 32)    ? 32
@@ -277,7 +278,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue: TMEM -> registers -> global C ==========
     const uint32_t q = warp & 3; // TMEM lanes [32q, 32q+32)
-    uint32_t it = 0;
+    const uint32_t sEpi = base + L::EPI_OFF;
+    uint32_t it = 0, epi_chunk = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
       const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
@@ -285,28 +287,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t m = m0 + q * 32 + lane;
-      float *crow = p.c + (uint64_t)z * p.c_bs + m;
+      if (p.tma_store) {
+        // TMEM -> registers -> [32 cols][128 rows] fp32 staging tile -> one TMA store (or TMA
+        // reduce-add when accumulating) per 32-column chunk. Two staging buffers: the store of chunk
+        // i drains while chunk i+1 is read out of TMEM. TMA clips rows/columns beyond M/N.
+        const bool leader = (threadIdx.x == EPI_WARP0 * 32);
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
-        tmem_ld_wait();
-        if (m < p.M) {
+        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+          const uint32_t buf = sEpi + (epi_chunk & 1u) * EPI_BUF_BYTES;
+          if (leader) bulk_wait_read_1(); // the store issued two chunks ago has finished reading `buf`
+          epi_bar_sync();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+          tmem_ld_wait();
+          if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the MMA warp early
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          const uint32_t dst = buf + (q * 32 + lane) * 4;
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) {
-            const uint32_t n = n0 + c0 + j;
-            if (n < p.N) {
-              float *dst = crow + (uint64_t)n * p.ldc;
-              const float v = __uint_as_float(r[j]);
-              *dst = p.accumulate ? (*dst + v) : v;
+          for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+          fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
+          epi_bar_sync();
+          if (leader && n0 + c0 < p.N) {
+            if (p.accumulate) tma_reduce_add_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            else tma_store_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            bulk_commit();
+          } else if (leader) {
+            bulk_commit(); // keep the group count in step with the buffer rotation
+          }
+        }
+      } else {
+        float *crow = p.c + (uint64_t)z * p.c_bs + m;
+        const bool full_tile = (m0 + BLOCK_M <= p.M) && (n0 + BLOCK_N <= p.N);
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+          tmem_ld_wait();
+          float *dst = crow + (uint64_t)(n0 + c0) * p.ldc;
+          if (full_tile && !p.accumulate) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j, dst += p.ldc) *dst = __uint_as_float(r[j]);
+          } else if (m < p.M) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j, dst += p.ldc) {
+              if (n0 + c0 + j < p.N) {
+                const float v = __uint_as_float(r[j]);
+                *dst = p.accumulate ? (*dst + v) : v;
+              }
             }
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (p.tma_store && threadIdx.x == EPI_WARP0 * 32) bulk_wait_all(); // smem must outlive the last store
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -359,8 +398,22 @@ static int make_operand_map(CUtensorMap *map, const uint16_t *ptr, int major, ui
   return r == CUDA_SUCCESS ? 0 : WEEDCU_ENOSUP;
 }
 
+// fp32 C [M, N] (+batch) column-major with leading dimension ldc: TMA box = 128 rows x 32 columns,
+// no swizzle (the staging tile in shared memory is plain [col][row]). Needs a 16-B aligned base and
+// 16-B multiples for the column / batch strides; otherwise the kernel stores C directly.
+static bool make_c_map(CUtensorMap *map, float *c, uint64_t M, uint64_t N, uint64_t ldc, uint64_t batch, uint64_t c_bs) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  if ((((uintptr_t)c) & 15u) || (ldc % 4) || (batch > 1 && (c_bs % 4))) return false;
+  cuuint64_t dims[3] = {M, N, batch};
+  cuuint64_t strides[2] = {ldc * 4, (batch > 1 ? c_bs : ldc * N) * 4};
+  cuuint32_t box[3] = {BLOCK_M, EPI_COLS, 1}, estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <uint32_t BLOCK_N, uint32_t STAGES>
-static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const Params &p, int a_major,
+static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const Params &p, int a_major,
                       int b_major, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
@@ -371,7 +424,7 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const Para
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return (int)e;                                                           \
-    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);                                               \
+    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p);                                          \
   }
   if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
   else if (a_major) WCU_TC_LAUNCH(1, 0)
@@ -400,9 +453,12 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (N + block_n - 1) / block_n;
   p.accumulate = accumulate;
+  CUtensorMap tmC;
+  p.tma_store = make_c_map(&tmC, c, M, N, ldc, batch, c_bs) ? 1 : 0;
+  if (!p.tma_store) tmC = tmA; // unused by the kernel, but must be a valid descriptor
   ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch);
-  if (wide) return launch_cfg<256, 4>(tmA, tmB, p, a_major, b_major, st);
-  return launch_cfg<128, 6>(tmA, tmB, p, a_major, b_major, st);
+  if (wide) return launch_cfg<256, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
+  return launch_cfg<128, 6>(tmA, tmB, tmC, p, a_major, b_major, st);
 }
 
 } // namespace tc

@@ -5,6 +5,7 @@
 // QueueItems (gpu_device.cpp:180-248) without its per-launch host wait (gpu_device.cpp:296-305).
 #include "common.cuh"
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -174,15 +175,34 @@ int weedcu_event_elapsed_ms(void *start, void *stop, float *ms) {
   WCU_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
   return 0;
 }
+static double g_malloc_ms = 0.0, g_free_ms = 0.0;
+static uint64_t g_mallocs = 0, g_frees = 0;
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 int weedcu_malloc(void **ptr, size_t bytes, void *stream) {
   if (!ptr) return WEEDCU_EINVAL;
   if (bytes == 0) bytes = 16;
-  WCU_CHECK(cudaMallocAsync(ptr, bytes, resolve_stream(stream)));
-  return 0;
+  const double t0 = now_ms();
+  const cudaError_t e = cudaMallocAsync(ptr, bytes, resolve_stream(stream));
+  g_malloc_ms += now_ms() - t0;
+  ++g_mallocs;
+  return (int)e;
 }
 int weedcu_free(void *ptr, void *stream) {
   if (!ptr) return 0;
-  WCU_CHECK(cudaFreeAsync(ptr, resolve_stream(stream)));
+  const double t0 = now_ms();
+  const cudaError_t e = cudaFreeAsync(ptr, resolve_stream(stream));
+  g_free_ms += now_ms() - t0;
+  ++g_frees;
+  return (int)e;
+}
+// host-side time spent inside the pool allocator (diagnostics for launch-bound steps)
+int weedcu_host_stats(double *malloc_ms, uint64_t *mallocs, double *free_ms, uint64_t *frees) {
+  if (malloc_ms) *malloc_ms = g_malloc_ms;
+  if (mallocs) *mallocs = g_mallocs;
+  if (free_ms) *free_ms = g_free_ms;
+  if (frees) *frees = g_frees;
   return 0;
 }
 int weedcu_mem_info(uint64_t *free_bytes, uint64_t *total_bytes) {
