@@ -16,7 +16,7 @@ extern "C" {
 #include <cstdlib>
 #include <cstring>
 
-static uint64_t g_launches = 0;
+static uint64_t g_launches = 0, g_mallocs = 0, g_frees = 0;
 #define VIEW(v) reinterpret_cast<const wo_view *>(v)
 #define MAT(m) reinterpret_cast<const wo_mat *>(m)
 #define RUN(expr) (++g_launches, ((expr) == 0 ? 0 : WEEDCU_EINVAL))
@@ -48,8 +48,8 @@ int weedcu_event_record(void *event, void *) {
 }
 int weedcu_event_sync(void *) { return 0; }
 int weedcu_event_elapsed_ms(void *start, void *stop, float *ms) { if (!ms) return WEEDCU_EINVAL; *ms = (float)(*(double *)stop - *(double *)start); return 0; }
-int weedcu_malloc(void **ptr, size_t bytes, void *) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); return *ptr ? 0 : 2; }
-int weedcu_free(void *ptr, void *) { free(ptr); return 0; }
+int weedcu_malloc(void **ptr, size_t bytes, void *) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); ++g_mallocs; return *ptr ? 0 : 2; }
+int weedcu_free(void *ptr, void *) { if (ptr) ++g_frees; free(ptr); return 0; }
 int weedcu_mem_info(uint64_t *f, uint64_t *t) { if (f) *f = 1ull << 33; if (t) *t = 1ull << 34; return 0; }
 int weedcu_host_alloc(void **ptr, size_t bytes) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); return *ptr ? 0 : 2; }
 int weedcu_host_free(void *ptr) { free(ptr); return 0; }
@@ -57,7 +57,7 @@ int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy
 int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
 int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *) { memmove(dst, src, bytes); return 0; }
 int weedcu_launch_count(uint64_t *count) { if (!count) return WEEDCU_EINVAL; *count = g_launches; return 0; }
-int weedcu_host_stats(double *a, uint64_t *b, double *c, uint64_t *d) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; if (d) *d = 0; return 0; }
+int weedcu_host_stats(double *a, uint64_t *b, double *c, uint64_t *d) { if (a) *a = 0; if (b) *b = g_mallocs; if (c) *c = 0; if (d) *d = g_frees; return 0; }
 int weedcu_prof_enable(int) { return 0; }
 int weedcu_prof_read(int, double *t, uint64_t *n, double *w) { if (t) *t = 0; if (n) *n = 0; if (w) *w = 0; return 0; }
 

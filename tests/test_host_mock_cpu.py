@@ -34,3 +34,36 @@ test_encoder_faithful_B4 = G.test_encoder_layer_faithful_mode_matches_reference_
 test_c4_faithful = G.test_config_c4_transformer_training_faithful_mode_matches_reference
 test_c4_default = G.test_config_c4_transformer_training_default_mode_runs_and_learns
 test_gpt_shape_bf16_vs_fp32 = G.test_gpt_shape_train_step_bf16_vs_fp32
+
+
+def test_training_steps_do_not_leak_device_buffers(P):
+    """Every buffer allocated during a training step is released once the step's loss handle is
+    dropped. (The reference's closures capture their own output tensor strongly, tensor.cpp:418-430,
+    a shared_ptr cycle that keeps every graph alive; here the node captures it weakly.)"""
+    import ctypes as C
+
+    import numpy as np
+
+    import bench
+    mock = C.CDLL(os.path.join(MOCK_DIR, "libweedcu_mock.so"))
+
+    def outstanding():
+        m, f = C.c_uint64(), C.c_uint64()
+        mock.weedcu_host_stats(None, C.byref(m), None, C.byref(f))
+        return m.value - f.value
+
+    for fused in (1, 0):
+        G.set_mode(P, fused)
+        cfg = dict(V=40, d=16, H=2, dff=32, L=2, T=8, B=2)
+        model, _ = bench.build_model(P, cfg)
+        opt = P.adam(model, 1e-3)
+        tok, tgt = bench.make_tokens(cfg, 1)
+        st, sg = P.symbol(tok, [2, 8]), P.symbol(tgt, [2, 8])
+        for _ in range(3):
+            P.free(P.train_step_tokens(model, opt, st, sg))
+        base = outstanding()
+        for _ in range(5):
+            P.free(P.train_step_tokens(model, opt, st, sg))
+        assert outstanding() == base, f"fused={fused}: {outstanding() - base} device buffers leaked over 5 steps"
+        P.reset()
+    G.set_mode(P, 1)

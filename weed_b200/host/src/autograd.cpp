@@ -106,7 +106,9 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
                    "cross_entropy_loss");
     if (rg) {
       loss->make_gradient();
-      loss->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{logits}, [logits, tg, lse, loss, rows, V, vs]() {
+      loss->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{logits}, [logits, tg, lse, wloss = std::weak_ptr<Tensor>(loss), rows, V, vs]() {
+        TensorPtr loss = wloss.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+        if (!loss) return;
         TensorPtr dl = std::make_shared<Tensor>(*(logits->grad));
         throw_on_error(weedcu_cross_entropy_bwd(logits->device_ptr(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
                                                 lse->device_ptr(), loss->grad->device_ptr() + loss->grad->offset, dl->device_ptr(),

@@ -131,7 +131,9 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
       if (p->requires_grad) parents.push_back(p);
     const tcapint F = features;
     y->make_gradient();
-    y->grad_node = std::make_shared<Node>(parents, [x, g, b, y, mean, rstd, rows, F]() {
+    y->grad_node = std::make_shared<Node>(parents, [x, g, b, wy = std::weak_ptr<Tensor>(y), mean, rstd, rows, F]() {
+      TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+      if (!y) return;
       // one kernel: dx += ..., dgamma += sum_rows dy*xhat, dbeta += sum_rows dy (16 B/elem)
       TensorPtr dx, dg, db;
       if (x->requires_grad) {
@@ -187,7 +189,9 @@ TensorPtr Embedding::forward(const SymbolTensorPtr indices_) { // embedding.cpp:
   if (weight->requires_grad) {
     ParameterPtr w = weight;
     out->make_gradient();
-    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{w}, [indices, w, out]() {
+    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{w}, [indices, w, wout = std::weak_ptr<Tensor>(out)]() {
+      TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+      if (!out) return;
       TensorPtr dW = view_copy(w->grad);
       TensorPtr dout = view_copy(out->grad);
       dW->match_shape(w);

@@ -219,7 +219,9 @@ TensorPtr Tensor::contiguous(const TensorPtr a) { // tensor.hpp:319-331 (zeros +
   Weed::copy_broadcast(*out, *a);
   if (a->requires_grad) { // gradient flows straight through, like the reference's add node
     out->make_gradient();
-    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out]() {
+    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
+      TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+      if (!out) return;
       TensorPtr a_grad = view_copy(a->grad);
       TensorPtr out_grad = view_copy(out->grad);
       a_grad->match_shape(out_grad);
@@ -340,7 +342,9 @@ TensorPtr Tensor::softmax(const TensorPtr x, symint axis) {
 }
 void Tensor::make_softmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, out, axis]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, wout = std::weak_ptr<Tensor>(out), axis]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr x_grad = full_grad(x);
     Weed::softmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
     settle_grad(x, x_grad);
@@ -356,7 +360,9 @@ TensorPtr Tensor::logsoftmax(const TensorPtr x, symint axis) {
 }
 void Tensor::make_logsoftmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, out, axis]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, wout = std::weak_ptr<Tensor>(out), axis]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr x_grad = full_grad(x);
     Weed::logsoftmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
     settle_grad(x, x_grad);
@@ -375,7 +381,9 @@ TensorPtr Tensor::slice(TensorPtr a, const int64_t &row) { // tensor.cpp:463-479
 }
 void Tensor::make_row_slice_node(TensorPtr a, TensorPtr out, const tcapint &row) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out, row]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), row]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr keep = a_grad->grad; // slicing must not register new nodes
     const bool rg = a_grad->requires_grad;
@@ -400,7 +408,9 @@ TensorPtr Tensor::slice(TensorPtr a, int64_t axis, const tcapint &start, const t
 }
 void Tensor::make_slice_node(TensorPtr a, TensorPtr out, const int64_t &axis, const tcapint &start) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out, axis, start]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), axis, start]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     // reference: zero tmp of a's shape, add dout into the window, add tmp into a_grad
     // (tensor.cpp:528-553). Equivalent and one pass: add dout into the window of a_grad directly.
     TensorPtr a_grad = view_copy(a->grad);
@@ -427,7 +437,9 @@ TensorPtr Tensor::sum(TensorPtr a) {
 }
 void Tensor::make_sum_node(TensorPtr a, TensorPtr out) { // tensor.cpp:568-581: da += dout (broadcast)
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr out_grad = view_copy(out->grad);
     out_grad->match_shape(a_grad);
@@ -444,7 +456,9 @@ TensorPtr Tensor::mean(TensorPtr a) {
 }
 void Tensor::make_mean_node(TensorPtr a, TensorPtr out) { // tensor.cpp:596-612: da += dout / N
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr out_grad = view_copy(out->grad);
     out_grad->match_shape(a_grad);
@@ -479,7 +493,9 @@ TensorPtr Tensor::sum(TensorPtr a, symint axis) { // tensor.cpp:614-653
 }
 void Tensor::make_sum_node(TensorPtr a, TensorPtr out, const tcapint &axis) { // tensor.cpp:655-680
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out, axis]() {
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), axis]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr dx = view_copy(a->grad);
     TensorPtr dy = view_copy(out->grad);
     if (dy->shape.size() < a->shape.size()) dy->unsqueeze(axis); // re-insert the reduced axis
@@ -516,7 +532,9 @@ TensorPtr unary_op(TensorPtr a, UnaryFwd fwd, UnaryBwd bwd, bool uses_output) {
   fwd(*a, *out);
   if (rg) {
     out->make_gradient();
-    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out, bwd, uses_output]() {
+    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), bwd, uses_output]() {
+      TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+      if (!out) return;
       TensorPtr a_grad = full_grad(a);
       bwd(*a_grad, uses_output ? *out : *a, *(out->grad));
       settle_grad(a, a_grad);
@@ -534,7 +552,9 @@ TensorPtr Tensor::cos(TensorPtr a) { return unary_op(a, Weed::cos, Weed::cos_gra
 #define WEED_NODE_ONLY(fn, bwd, src)                                                               \
   void Tensor::fn(TensorPtr a, TensorPtr out) {                                                    \
     out->make_gradient();                                                                          \
-    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, out]() {               \
+    out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() { \
+      TensorPtr out = wout.lock(); /* the node is owned by this tensor: a strong capture would be a cycle */ \
+      if (!out) return; \
       TensorPtr a_grad = full_grad(a);                                                             \
       bwd(*a_grad, *src, *(out->grad));                                                            \
       settle_grad(a, a_grad);                                                                      \
@@ -650,7 +670,9 @@ TensorPtr Tensor::add(TensorPtr a, TensorPtr b) { // tensor.cpp:1084-1103
 }
 void Tensor::make_add_node(TensorPtr a, TensorPtr b, TensorPtr out) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, out]() {
+  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad) accumulate(a, out_grad, *out_grad, false);
     if (b->requires_grad) accumulate(b, out_grad, *out_grad, false);
@@ -666,7 +688,9 @@ TensorPtr Tensor::sub(TensorPtr a, TensorPtr b) { // tensor.cpp:1404-1423
 }
 void Tensor::make_sub_node(TensorPtr a, TensorPtr b, TensorPtr out) {
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, out]() {
+  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad) accumulate(a, out_grad, *out_grad, false);
     if (b->requires_grad) accumulate(b, out_grad, *out_grad, true);
@@ -682,7 +706,9 @@ TensorPtr Tensor::mul(TensorPtr a, TensorPtr b) { // tensor.cpp:1138-1157
 }
 void Tensor::make_mul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.cpp:1159-1202
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, out]() {
+  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
     auto side = [&](const TensorPtr &p, const TensorPtr &other) {
       TensorPtr tmp = Tensor::allocate_like(out_grad->shape, *out_grad, DType::REAL, false, false);
@@ -703,7 +729,9 @@ TensorPtr Tensor::div(TensorPtr a, TensorPtr b) { // tensor.cpp:1458-1477
 }
 void Tensor::make_div_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.cpp:1479-1524
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, out]() {
+  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad) { // da += dout / b
       TensorPtr tmp = Tensor::allocate_like(out_grad->shape, *out_grad, DType::REAL, false, false);
@@ -729,7 +757,9 @@ TensorPtr Tensor::pow(TensorPtr a, real1 p) {
 }
 void Tensor::make_pow_node(TensorPtr x, real1 p, TensorPtr y) { // tensor.cpp:1540-1573: dx += p * dy * y / x
   y->make_gradient();
-  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, p, y]() {
+  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, p, wy = std::weak_ptr<Tensor>(y)]() {
+    TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!y) return;
     TensorPtr dy = view_copy(y->grad);
     TensorPtr _x = view_copy(x), _y = view_copy(y);
     _y->match_shape(_x);
@@ -752,7 +782,9 @@ TensorPtr Tensor::exp(TensorPtr a, real1 b) {
 }
 void Tensor::make_exp_node(TensorPtr x, real1 log_b, TensorPtr y) { // tensor.cpp:1589-1616: dx += log_b * dy * y
   y->make_gradient();
-  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, log_b, y]() {
+  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, log_b, wy = std::weak_ptr<Tensor>(y)]() {
+    TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!y) return;
     TensorPtr dy = view_copy(y->grad);
     dy->match_shape(y);
     TensorPtr dy_v = SCALAR(log_b, dy) * dy;
@@ -770,7 +802,9 @@ TensorPtr Tensor::log(TensorPtr a, real1 b) {
 }
 void Tensor::make_log_node(TensorPtr x, real1 inv_log_b, TensorPtr y) { // tensor.cpp:1632-1659: dx += inv_log_b * dy / x
   y->make_gradient();
-  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, inv_log_b, y]() {
+  y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, inv_log_b, wy = std::weak_ptr<Tensor>(y)]() {
+    TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!y) return;
     TensorPtr dy = view_copy(y->grad);
     dy->match_shape(x);
     TensorPtr dy_v = SCALAR(inv_log_b, dy) * dy;
@@ -836,7 +870,9 @@ TensorPtr Tensor::matmul(TensorPtr a, TensorPtr b) { // tensor.cpp:1204-1326
 
 void Tensor::make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.cpp:1328-1402
   out->make_gradient();
-  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, out]() {
+  out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
     const bool needs_flatten = (a->shape.size() > 2U);
     const symint K = (symint)a->shape.back();
