@@ -69,6 +69,9 @@ int weedcu_event_elapsed_ms(void *start, void *stop, float *ms);
  * (include/devices/queue_item.hpp:27-47). */
 int weedcu_malloc(void **ptr, size_t bytes, void *stream);
 int weedcu_free(void *ptr, void *stream);
+/* weedcu_malloc/free keep freed blocks on per-stream free lists (a training step re-requests the
+ * same sizes every iteration); this returns every cached block to the driver. */
+int weedcu_pool_trim(void);
 int weedcu_mem_info(uint64_t *free_bytes, uint64_t *total_bytes);
 int weedcu_host_alloc(void **ptr, size_t bytes); /* pinned staging memory */
 int weedcu_host_free(void *ptr);
@@ -112,10 +115,12 @@ enum {
 int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av, float *out,
                       const weedcu_view *ov, void *stream);
 /* din[i] += f'(.) * dout[i]. `in` is the forward INPUT for relu/abs/gelu/sin/cos and the forward
- * OUTPUT for sigmoid/tanh (src/ops/real_unary.cpp:47-76; src/tensors/tensor.cpp:867-935). */
+ * OUTPUT for sigmoid/tanh (src/ops/real_unary.cpp:47-76; src/tensors/tensor.cpp:867-935).
+ * accumulate == 0 stores instead of adding (din is known to be all zeros and is not read): the
+ * host's lazily zero-filled gradients use it to skip the fill and the read (16 -> 12 B/elem). */
 int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in,
                            const weedcu_view *inv, const float *dout, const weedcu_view *doutv,
-                           void *stream);
+                           int accumulate, void *stream);
 
 /* ------------------------------------------------------------------ R1-R2 reductions
  * Weed::reduce (src/ops/reduce.cpp:17-38,60-66): out[o] = sum_j a[base(o) + j*stride[axis]];
@@ -156,6 +161,16 @@ int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, 
 int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq,
                              uint32_t Tk, float divisor, float mask_val, int causal,
                              int batch_fastest, void *stream);
+/* Fused attention core on bf16 tensor cores for q, k, v, out = [B, T, H*hd] column-major (b fastest;
+ * the layout Linear::forward leaves them in): per (b, h)  S = Q K^T / divisor (+ mask_val where
+ * q + 1 <= k when causal), P = softmax_k(S), O = P V — the chain of MultiHeadAttention::forward,
+ * src/modules/multihead_attention.cpp:289-345, without its transposing copies. Q, K, V and P are
+ * rounded to bf16, accumulation is fp32; like the reference's batched matmul (tensor.cpp:1253-1271)
+ * the result carries no autograd edge. Returns WEEDCU_ENOSUP for shapes outside T % 8 == 0,
+ * 64 <= T <= 1024, hd % 8 == 0 (callers then compose the generic ops). */
+int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
+                         uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
+                         int causal, void *stream);
 /* Fused cross-entropy over logits[rows, V] (row stride rs, vocab stride vs):
  * cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34) = -mean_rows lsm[row, target].
  * fwd writes per-row log-sum-exp (lse[rows]) and the scalar loss; bwd does
@@ -165,7 +180,8 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
                              float *loss, void *stream);
 int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
                              uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse,
-                             const float *dloss, float *dlogits, uint64_t d_offset, void *stream);
+                             const float *dloss, float *dlogits, uint64_t d_offset, int accumulate,
+                             void *stream); /* accumulate == 0: dlogits = ... (not read) */
 
 /* ------------------------------------------------------------------ L1 LayerNorm (fused)
  * LayerNorm::forward (src/modules/layernorm.cpp:29-42): x[rows, F] with row stride 1 and
@@ -179,10 +195,11 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
  *   the denominator branch (src/tensors/tensor.cpp:1506-1521), so the variance path contributes
  *   only  xc * (-rstd^3/F) * sum_f(xc)  (rounding-level):  dxc = g*rstd + that;  dx += dxc - mean_f(dxc).
  * grad_mode 1 is the analytic LayerNorm gradient: dx += rstd*(g - mean_f(g) - xhat*mean_f(g*xhat)).
- * (g = dy*gamma, xc = x-mean, xhat = xc*rstd) */
+ * (g = dy*gamma, xc = x-mean, xhat = xc*rstd)
+ * accumulate == 0: dx is stored, not added to (dgamma / dbeta always accumulate). */
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
-                         float *dgamma, float *dbeta, int grad_mode, void *stream);
+                         float *dgamma, float *dbeta, int grad_mode, int accumulate, void *stream);
 
 /* ------------------------------------------------------------------ M1-M2 embedding, mask
  * Weed::embedding_gather / embedding_scatter_add (src/ops/embedding.cpp:56-110):
@@ -213,6 +230,12 @@ int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale
 int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr,
                      float beta1, float beta2, float eps, float bc1, float bc2, float gscale,
                      void *stream);
+/* The same update for `count` parameters in ONE launch (adam_step walks a parameter list,
+ * adam.hpp:70-106; a 12-layer transformer has ~150 of them, most of them tiny). Host arrays of
+ * device pointers and sizes; they are copied before the call returns. */
+int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m,
+                           float *const *v, const uint64_t *n, float lr, float beta1, float beta2,
+                           float eps, float bc1, float bc2, float gscale, void *stream);
 
 /* ------------------------------------------------------------------ G1-G4 matmul
  * Weed::matmul (src/ops/matmul.cpp:242-279; dims :95-122): C[M,N] (+)= A[M,K] * B[K,N], every
@@ -235,10 +258,12 @@ int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, con
                        uint32_t batch, int accumulate, int precision, void *stream);
 /* bf16 tensor-core GEMM on operands already held in bf16 (raw uint16 bit patterns).
  * a_major / b_major: 0 = K contiguous, 1 = M (resp. N) contiguous; lda/ldb are the strides
- * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc. */
+ * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc.
+ * col_bias (optional, may be NULL): [N] fp32 added to every row in the epilogue — the bias add of
+ * Linear::forward (src/modules/linear.cpp) without a second pass over C. */
 int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
                      uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
-                     int accumulate, void *stream);
+                     int accumulate, const float *col_bias, void *stream);
 /* strided fp32 -> packed bf16 (round-to-nearest-even); dst is a dense [rows, cols] matrix whose
  * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,

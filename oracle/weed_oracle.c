@@ -127,13 +127,14 @@ int wo_unary_real(int op, float param, const float *a, const wo_view *av, float 
  * gelu: analytic derivative of the tanh-approximation (the reference back-propagates through the
  * nine composite ops of tensor.cpp:841-851, which is the same function). */
 int wo_unary_grad_real(int op, float *din, const wo_view *dinv, const float *in, const wo_view *inv,
-                       const float *dout, const wo_view *doutv) {
+                       const float *dout, const wo_view *doutv, int accumulate) {
   if (!same_shape(dinv, inv) || !same_shape(dinv, doutv)) return -1;
   const uint64_t n = wo_broadcast_size(dinv);
   for (uint64_t i = 0; i < n; ++i) {
     const float v = in[wo_storage_index(inv, i)];
     const float g = dout[wo_storage_index(doutv, i)];
     float *p = &din[wo_storage_index(dinv, i)];
+    if (!accumulate) *p = 0.0f; /* store variant: din is not read */
     switch (op) {
     case 0: if (v > 0.0f) *p += g; break;
     case 1: *p += v * (1.0f - v) * g; break;
@@ -347,14 +348,15 @@ int wo_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, ui
  * dlogits[r,v] += (exp(lsm[r,v]) - onehot[r,v]) * dloss / rows. */
 int wo_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
                          uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse,
-                         const float *dloss, float *dlogits, uint64_t d_offset) {
+                         const float *dloss, float *dlogits, uint64_t d_offset, int accumulate) {
   const float g = dloss[0] / (float)rows;
   for (uint32_t r = 0; r < rows; ++r) {
     const uint64_t base = offset + (uint64_t)r * rs, dbase = d_offset + (uint64_t)r * rs;
     for (uint32_t v = 0; v < V; ++v) {
       const float p = expf(logits[base + (uint64_t)v * vs] - lse[r]);
       const float oh = ((uint32_t)targets[r] == v) ? 1.0f : 0.0f;
-      dlogits[dbase + (uint64_t)v * vs] += (p - oh) * g;
+      float *o = &dlogits[dbase + (uint64_t)v * vs];
+      *o = (accumulate ? *o : 0.0f) + (p - oh) * g;
     }
   }
   return 0;
@@ -400,7 +402,9 @@ int wo_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gam
  * tests/test_oracle_cpu.py (live comparison with the compiled reference). */
 int wo_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma,
                      const float *mean, const float *rstd, float *dx, float *dgamma, float *dbeta,
-                     int grad_mode) {
+                     int grad_mode, int accumulate) {
+  if (!accumulate) /* store variant: dx is not read */
+    for (uint64_t i = 0; i < (uint64_t)rows * F; ++i) dx[i] = 0.0f;
   for (uint32_t r = 0; r < rows; ++r) {
     const double rs = rstd[r], mu = mean[r];
     double sg = 0.0, sgx = 0.0, sx = 0.0;
@@ -577,5 +581,51 @@ int wo_matmul_bf16_model(const float *a, const wo_mat *am, const float *b, const
         *o = accumulate ? (float)(*o + sum) : (float)sum;
       }
   }
+  return 0;
+}
+
+/* Model of the fused bf16 attention core (weedcu_attention_fwd): the same chain as
+ * MultiHeadAttention::forward, src/modules/multihead_attention.cpp:289-345 — per (b, h):
+ * S = Q K^T, S/divisor (+ triu mask), softmax over keys, O = P V — with the rounding points of the
+ * tensor-core path: Q, K, V and the probabilities P are rounded to bf16 (RNE), products are exact
+ * and sums are carried in double (the device accumulates in fp32; tolerance covers the difference).
+ * q, k, v, out: [B, T, H*hd] column-major (b fastest). */
+int wo_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
+                           uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
+                           int causal) {
+  float *S = (float *)malloc(sizeof(float) * (size_t)T * T);
+  float *P = (float *)malloc(sizeof(float) * (size_t)T * T);
+  if (!S || !P) {
+    free(S);
+    free(P);
+    return -1;
+  }
+  const uint64_t sT = B, sC = (uint64_t)B * T; /* strides of the token and the feature index */
+  for (uint32_t b = 0; b < B; ++b)
+    for (uint32_t h = 0; h < H; ++h) {
+      for (uint32_t i = 0; i < T; ++i)
+        for (uint32_t j = 0; j < T; ++j) {
+          double sum = 0.0;
+          for (uint32_t c = 0; c < hd; ++c)
+            sum += (double)bf16_round(q[b + i * sT + (uint64_t)(h * hd + c) * sC]) *
+                   (double)bf16_round(k[b + j * sT + (uint64_t)(h * hd + c) * sC]);
+          S[i + (size_t)T * j] = (float)sum;
+        }
+      if (wo_attn_softmax_real(S, P, 1, T, T, divisor, mask_val, causal, 0) != 0) {
+        free(S);
+        free(P);
+        return -1;
+      }
+      for (uint32_t i = 0; i < T; ++i)
+        for (uint32_t c = 0; c < hd; ++c) {
+          double sum = 0.0;
+          for (uint32_t j = 0; j < T; ++j)
+            sum += (double)bf16_round(P[i + (size_t)T * j]) *
+                   (double)bf16_round(v[b + j * sT + (uint64_t)(h * hd + c) * sC]);
+          out[b + i * sT + (uint64_t)(h * hd + c) * sC] = (float)sum;
+        }
+    }
+  free(S);
+  free(P);
   return 0;
 }

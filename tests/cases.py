@@ -178,6 +178,15 @@ for _op, _nm, _p, _lo, _hi in _UNARY:
 
 for _op, _nm, _lo, _hi in [(RELU, "relu", -1, 1), (SIGMOID, "sigmoid", 0.01, 0.99), (TANH, "tanh", -0.99, 0.99),
                            (ABS, "abs", -1, 1), (GELU, "gelu", -4, 4), (SIN, "sin", -3, 3), (COS, "cos", -3, 3)]:
+    @case(f"unary_grad_store_{_nm}")
+    def _c(be, rng, op=_op, lo=_lo, hi=_hi):  # accumulate = 0: din is overwritten, never read
+        s = [257, 5]
+        n = 257 * 5
+        din, x, dout = uni(rng, n), uni(rng, n, lo, hi), uni(rng, n)
+        hd, hx, hg = be.buf(din), be.buf(x), be.buf(dout)
+        be.call("unary_grad_real", I32(op), hd, cview(s), hx, cview(s), hg, cview(s), I32(0))
+        return {"din": hd.get()}
+
     @case(f"unary_grad_{_nm}")
     def _c(be, rng, op=_op, lo=_lo, hi=_hi):
         s = [130, 7]
@@ -186,7 +195,7 @@ for _op, _nm, _lo, _hi in [(RELU, "relu", -1, 1), (SIGMOID, "sigmoid", 0.01, 0.9
         if op in (RELU, ABS):
             x[::11] = 0.0
         hd, hx, hg = be.buf(din), be.buf(x), be.buf(dout)
-        be.call("unary_grad_real", I32(op), hd, cview(s), hx, cview(s), hg, cview(s))
+        be.call("unary_grad_real", I32(op), hd, cview(s), hx, cview(s), hg, cview(s), I32(1))
         return {"din": hd.get()}
 
 
@@ -195,7 +204,7 @@ def _c(be, rng):  # dout is the all-ones seed broadcast from one element (tensor
     s = [64, 5]
     din, x, dout = uni(rng, 320), uni(rng, 320), np.ones(1, F32)
     hd, hx, hg = be.buf(din), be.buf(x), be.buf(dout)
-    be.call("unary_grad_real", I32(TANH), hd, cview(s), hx, cview(s), hg, make_view(s, [0, 0]))
+    be.call("unary_grad_real", I32(TANH), hd, cview(s), hx, cview(s), hg, make_view(s, [0, 0]), I32(1))
     return {"din": hd.get()}
 
 
@@ -323,7 +332,7 @@ def _c(be, rng):  # Tq = 1: no mask is applied (multihead_attention.cpp:322)
     return {"out": ho.get()}
 
 
-def _ce(be, rng, rows, V):
+def _ce(be, rng, rows, V, acc=1):
     logits = uni(rng, rows * V, -5, 5)
     tg = rng.integers(0, V, size=rows).astype(np.int32)
     hl, ht = be.buf(logits), be.buf(tg)
@@ -331,7 +340,7 @@ def _ce(be, rng, rows, V):
     be.call("cross_entropy_fwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, hloss)
     dl = uni(rng, rows * V)
     hdl, hg = be.buf(dl), be.buf(np.ones(1, F32))
-    be.call("cross_entropy_bwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, hg, hdl, U64(0))
+    be.call("cross_entropy_bwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, hg, hdl, U64(0), I32(acc))
     return {"lse": hlse.get(), "loss": hloss.get(), "dlogits": hdl.get()}
 
 
@@ -345,8 +354,18 @@ def _c(be, rng):
     return _ce(be, rng, 7, 13)
 
 
+@case("cross_entropy_300x2000_store", tol=2e-5)
+def _c(be, rng):  # accumulate = 0: dlogits is overwritten (vocab split over several blocks)
+    return _ce(be, rng, 300, 2000, acc=0)
+
+
+@case("cross_entropy_33x50257", tol=2e-5)
+def _c(be, rng):  # GPT-2 vocabulary, ragged row tile
+    return _ce(be, rng, 33, 50257)
+
+
 # --------------------------------------------------------------------------------------- layernorm
-def _ln(be, rng, rows, F, grad_mode=0):
+def _ln(be, rng, rows, F, grad_mode=0, acc=1):
     x = uni(rng, rows * F, -2, 2)
     gamma, beta = uni(rng, F, 0.5, 1.5), uni(rng, F)
     hx, hg, hb = be.buf(x), be.buf(gamma), be.buf(beta)
@@ -356,7 +375,7 @@ def _ln(be, rng, rows, F, grad_mode=0):
     dy, dx = uni(rng, rows * F), uni(rng, rows * F)
     dg, db = uni(rng, F), uni(rng, F)
     hdy, hdx, hdg, hdb = be.buf(dy), be.buf(dx), be.buf(dg), be.buf(db)
-    be.call("layernorm_bwd", hx, hdy, U32(rows), U32(F), hg, hm, hr, hdx, hdg, hdb, I32(grad_mode))
+    be.call("layernorm_bwd", hx, hdy, U32(rows), U32(F), hg, hm, hr, hdx, hdg, hdb, I32(grad_mode), I32(acc))
     return {"y": hy.get(), "mean": hm.get(), "rstd": hr.get(), "dx": hdx.get(), "dgamma": hdg.get(),
             "dbeta": hdb.get()}
 
@@ -366,6 +385,16 @@ for _rows, _F in [(40, 24), (5, 8), (300, 64), (5000, 16), (9600, 12)]:
         @case(f"layernorm_{_rows}x{_F}_gradmode{_gm}", tol=3e-5)
         def _c(be, rng, rows=_rows, F=_F, gm=_gm):
             return _ln(be, rng, rows, F, gm)
+
+
+@case("layernorm_8192x768_store", tol=3e-5)
+def _c(be, rng):  # GPT-2 shape; accumulate = 0 (dx overwritten); persistent blocks loop over row tiles
+    return _ln(be, rng, 8192, 768, 0, acc=0)
+
+
+@case("layernorm_20000x40_multi_tile", tol=3e-5)
+def _c(be, rng):  # more row tiles than blocks: the per-block column sums span several tiles
+    return _ln(be, rng, 20000, 40, 1)
 
 
 # --------------------------------------------------------------------------------------- embedding etc.

@@ -13,13 +13,21 @@ extern "C" {
 }
 
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 static uint64_t g_launches = 0, g_mallocs = 0, g_frees = 0;
 #define VIEW(v) reinterpret_cast<const wo_view *>(v)
 #define MAT(m) reinterpret_cast<const wo_mat *>(m)
-#define RUN(expr) (++g_launches, ((expr) == 0 ? 0 : WEEDCU_EINVAL))
+static const bool g_trace = getenv("WEEDCU_MOCK_TRACE") != nullptr; // print one line per kernel call
+static inline void trace_call(const char *what) {
+  if (!g_trace) return;
+  const char *p = strchr(what, '(');
+  fprintf(stderr, "[mock] %.*s\n", p ? (int)(p - what) : (int)strlen(what), what);
+}
+#define RUN(expr) (++g_launches, trace_call(#expr), ((expr) == 0 ? 0 : WEEDCU_EINVAL))
 
 extern "C" {
 int weedcu_device_count(int *count) { if (!count) return WEEDCU_EINVAL; *count = 1; return 0; }
@@ -50,6 +58,7 @@ int weedcu_event_sync(void *) { return 0; }
 int weedcu_event_elapsed_ms(void *start, void *stop, float *ms) { if (!ms) return WEEDCU_EINVAL; *ms = (float)(*(double *)stop - *(double *)start); return 0; }
 int weedcu_malloc(void **ptr, size_t bytes, void *) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); ++g_mallocs; return *ptr ? 0 : 2; }
 int weedcu_free(void *ptr, void *) { if (ptr) ++g_frees; free(ptr); return 0; }
+int weedcu_pool_trim(void) { return 0; }
 int weedcu_mem_info(uint64_t *f, uint64_t *t) { if (f) *f = 1ull << 33; if (t) *t = 1ull << 34; return 0; }
 int weedcu_host_alloc(void **ptr, size_t bytes) { if (!ptr) return WEEDCU_EINVAL; *ptr = malloc(bytes ? bytes : 16); return *ptr ? 0 : 2; }
 int weedcu_host_free(void *ptr) { free(ptr); return 0; }
@@ -73,8 +82,8 @@ int weedcu_copy_real(float *dst, const weedcu_view *dv, const float *src, const 
 int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av, float *out, const weedcu_view *ov, void *) {
   return RUN(wo_unary_real(op, param, a, VIEW(av), out, VIEW(ov)));
 }
-int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, void *) {
-  return RUN(wo_unary_grad_real(op, din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv)));
+int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, int accumulate, void *) {
+  return RUN(wo_unary_grad_real(op, din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv), accumulate));
 }
 int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *out, int index_order, void *) { return RUN(wo_reduce_real(a, VIEW(av), axis, out, index_order)); }
 int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout, const weedcu_view *doutv, int axis, int index_order, void *) {
@@ -90,19 +99,23 @@ int weedcu_softmax_grad_real(int log_mode, float *din, const weedcu_view *dinv, 
 int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, uint32_t Tq, uint32_t Tk, float divisor, float mask_val, int causal, int batch_fastest, void *) {
   return RUN(wo_attn_softmax_real(scores, out, batch, Tq, Tk, divisor, mask_val, causal, batch_fastest));
 }
+int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal, void *) {
+  if ((T % 8u) || T < 64u || T > 1024u || hd < 16u || (hd % 8u)) return WEEDCU_ENOSUP; // same envelope as the device entry
+  return RUN(wo_attention_fwd(q, k, v, out, B, T, H, hd, divisor, mask_val, (causal && T > 1) ? 1 : 0));
+}
 int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, float *lse, float *loss, void *) {
   return RUN(wo_cross_entropy_fwd(logits, offset, rows, V, rs, vs, targets, lse, loss));
 }
 int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse, const float *dloss,
-                             float *dlogits, uint64_t d_offset, void *) {
-  return RUN(wo_cross_entropy_bwd(logits, offset, rows, V, rs, vs, targets, lse, dloss, dlogits, d_offset));
+                             float *dlogits, uint64_t d_offset, int accumulate, void *) {
+  return RUN(wo_cross_entropy_bwd(logits, offset, rows, V, rs, vs, targets, lse, dloss, dlogits, d_offset, accumulate));
 }
 int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, void *) {
   return RUN(wo_layernorm_fwd(x, rows, F, gamma, beta, eps, y, mean, rstd));
 }
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma, const float *mean, const float *rstd, float *dx, float *dgamma, float *dbeta,
-                         int grad_mode, void *) {
-  return RUN(wo_layernorm_bwd(x, dy, rows, F, gamma, mean, rstd, dx, dgamma, dbeta, grad_mode));
+                         int grad_mode, int accumulate, void *) {
+  return RUN(wo_layernorm_bwd(x, dy, rows, F, gamma, mean, rstd, dx, dgamma, dbeta, grad_mode, accumulate));
 }
 int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n, const float *W, uint64_t w_off, uint32_t w_s0, uint32_t w_s1, uint32_t D, float *out,
                             uint64_t o_off, uint32_t o_s0, uint32_t o_s1, void *) {
@@ -118,13 +131,49 @@ int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale
 int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float gscale, void *) {
   return RUN(wo_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gscale));
 }
+int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, float lr, float beta1, float beta2, float eps,
+                           float bc1, float bc2, float gscale, void *) {
+  ++g_launches;
+  for (uint32_t t = 0; t < count; ++t)
+    if (wo_adam_step(p[t], g[t], m[t], v[t], n[t], lr, beta1, beta2, eps, bc1, bc2, gscale) != 0) return WEEDCU_EINVAL;
+  return 0;
+}
 int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
                        int accumulate, int precision, void *) {
   if (precision == WEEDCU_GEMM_BF16) return RUN(wo_matmul_bf16_model(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, batch, accumulate));
   return RUN(wo_matmul_real(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, batch, accumulate));
 }
-int weedcu_gemm_bf16(const uint16_t *, int, uint64_t, const uint16_t *, int, uint64_t, float *, uint64_t, uint32_t, uint32_t, uint32_t, int, void *) { return WEEDCU_ENOSUP; }
-int weedcu_pack_bf16(const float *, uint64_t, uint32_t, uint32_t, uint32_t, uint32_t, uint16_t *, int, void *) { return WEEDCU_ENOSUP; }
+// bf16 operands: the same rounding model as wo_matmul_bf16_model, split the way the product does it
+// (pack once with wo_f32_to_bf16, multiply the widened values in fp32)
+static inline float bf16_widen(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, sizeof(f));
+  return f;
+}
+int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols, uint16_t *dst, int dst_major, void *) {
+  if (!src || !dst || !rows || !cols) return WEEDCU_EINVAL;
+  const uint64_t ld = ((uint64_t)(dst_major ? rows : cols) + 7U) & ~(uint64_t)7U;
+  for (uint32_t r = 0; r < rows; ++r)
+    for (uint32_t c = 0; c < cols; ++c)
+      dst[dst_major ? (r + c * ld) : (c + r * ld)] = wo_f32_to_bf16(src[offset + (uint64_t)r * s0 + (uint64_t)c * s1]);
+  return 0;
+}
+int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                     int accumulate, const float *col_bias, void *) {
+  if (!a || !b || !c || !M || !N || !K) return WEEDCU_EINVAL;
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      double sum = 0.0; // same accumulation as wo_matmul_bf16_model
+      for (uint32_t k = 0; k < K; ++k)
+        sum += (double)bf16_widen(a[a_major ? (m + k * lda) : (k + m * lda)]) * (double)bf16_widen(b[b_major ? (n + k * ldb) : (k + n * ldb)]);
+      float *o = &c[m + (uint64_t)n * ldc];
+      *o = accumulate ? (float)(*o + sum) : (float)sum;
+      if (col_bias) *o = *o + col_bias[n];
+    }
+  g_launches++;
+  return 0;
+}
 int weedcu_gemm_workspace_bytes(uint32_t, uint32_t, uint32_t, uint32_t, int, uint64_t *bytes) { if (bytes) *bytes = 0; return 0; }
 // collectives: single-process identity (world size 1); the gloo world_size-2 tests patch these from Python
 int weedcu_nccl_load(const char *) { return 0; }

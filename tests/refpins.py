@@ -70,7 +70,7 @@ for _nm, _op, _p0, _lo, _hi, _fl in (("relu", 0, 0, -1, 1, ()), ("sigmoid", 1, 0
                 return {"y": y, "dx": dx.astype(F32)}
             hd, hw = O.buf(np.zeros(n, F32)), O.buf(i["w"])
             src = hy if op in (1, 2) else hx  # sigmoid/tanh grads read the forward output
-            O.call("unary_grad_real", I32(op), hd, cview([n]), src, cview([n]), hw, cview([n]))
+            O.call("unary_grad_real", I32(op), hd, cview([n]), src, cview([n]), hw, cview([n]), I32(1))
             return {"y": y, "dx": hd.get()}
         return inp, ref, orc
 
@@ -198,7 +198,7 @@ def _p(rng):
         eps = F32(np.finfo(np.float32).eps / 4)
         O.call("layernorm_fwd", hx, U32(T), U32(F), hg, hb, eps, hy, hm, hr)
         hw, hdx, hdg, hdb = O.buf(i["w"]), O.buf(np.zeros(T * F, F32)), O.buf(np.zeros(F, F32)), O.buf(np.zeros(F, F32))
-        O.call("layernorm_bwd", hx, hw, U32(T), U32(F), hg, hm, hr, hdx, hdg, hdb, I32(0))
+        O.call("layernorm_bwd", hx, hw, U32(T), U32(F), hg, hm, hr, hdx, hdg, hdb, I32(0), I32(1))
         return {"y": hy.get(), "dx": hdx.get(), "dgamma": hdg.get(), "dbeta": hdb.get()}
     return inp, ref, orc
 

@@ -287,3 +287,52 @@ def test_gpt_shape_train_step_bf16_vs_fp32(P):
     set_mode(P, 1)
     assert np.all(np.isfinite(f32)) and abs(f32[0] - np.log(V)) < 1.0
     assert np.max(np.abs(f32 - bf16) / np.abs(f32)) <= 2e-2, (f32, bf16)
+
+
+def test_operand_cache_and_lazy_zero_change_nothing(P):
+    """The bf16 operand shadows (pack once per write instead of once per GEMM) and the deferred
+    zero-fill of gradients are pure scheduling: losses and every parameter after 3 Adam steps match
+    the run with both switched off — bit for bit on the serial mock device; on the GPU up to the
+    summation order of the embedding scatter's float atomics (duplicate tokens), i.e. ~1e-7.
+    A stale shadow or a skipped fill would show up here as an O(1e-3) difference."""
+    B, T, V, d, L = 2, 64, 512, 64, 2
+
+    def run(cache, lazy):
+        set_mode(P, 1, precision=1)
+        P.config("operand_cache", cache)
+        P.config("lazy_zero", lazy)
+        rng = np.random.default_rng(3100)
+        tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        targets = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        mods = [P.module("embedding", V, d), P.module("posenc", T, d)] + [P.module("encoder", d, 4, 4 * d) for _ in range(L)]
+        mods += [P.module("layernorm", d), P.module("linear", d, V, 1)]
+        model = P.module("sequential", *mods)
+        P.init_params(model, 2100)
+        opt = P.adam(model, 1e-3)
+        tok = P.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+        tgt = P.symbol(np.ascontiguousarray(targets.T).ravel(), [B, T])
+        losses = [float(P.read(P.train_step_tokens(model, opt, tok, tgt))[0]) for _ in range(3)]
+        params = [P.read_storage(P.param(model, i)).copy() for i in range(P.param_count(model))]
+        P.reset()
+        return np.array(losses), params
+
+    exact = "mock" in os.path.basename(P.path)
+    try:
+        l_ref, p_ref = run(0, 0)
+        for cache, lazy in ((1, 0), (0, 1), (1, 1)):
+            l, p = run(cache, lazy)
+            if exact:
+                assert np.array_equal(l, l_ref), (cache, lazy, l, l_ref)
+            else:
+                assert np.max(np.abs(l - l_ref) / np.abs(l_ref)) <= 1e-6, (cache, lazy, l, l_ref)
+            for i, (a, b) in enumerate(zip(p, p_ref)):
+                if exact:
+                    assert np.array_equal(a, b), f"cache={cache} lazy={lazy}: parameter {i} differs"
+                else:  # Adam normalises the step: a gradient that is pure rounding noise may move by ~lr
+                    assert np.mean(np.abs(a - b)) <= 1e-6 and np.max(np.abs(a - b)) <= 4e-3, \
+                        f"cache={cache} lazy={lazy}: parameter {i} differs by {np.max(np.abs(a - b))}"
+        assert np.all(np.isfinite(l_ref)) and l_ref[-1] < l_ref[0]
+    finally:
+        P.config("operand_cache", 1)
+        P.config("lazy_zero", 1)
+        set_mode(P, 1)

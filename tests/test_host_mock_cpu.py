@@ -34,6 +34,7 @@ test_encoder_faithful_B4 = G.test_encoder_layer_faithful_mode_matches_reference_
 test_c4_faithful = G.test_config_c4_transformer_training_faithful_mode_matches_reference
 test_c4_default = G.test_config_c4_transformer_training_default_mode_runs_and_learns
 test_gpt_shape_bf16_vs_fp32 = G.test_gpt_shape_train_step_bf16_vs_fp32
+test_operand_cache_and_lazy_zero = G.test_operand_cache_and_lazy_zero_change_nothing
 
 
 def test_training_steps_do_not_leak_device_buffers(P):

@@ -61,3 +61,82 @@ def test_launch_counter_counts(gpu):
     gpu.lib.weedcu_launch_count(C.byref(n1))
     assert n1.value == n0.value + 1
     assert np.all(h.get() == 2.0)
+
+
+ATTN_CASES = [  # B, T, H, hd, causal
+    (2, 64, 2, 16, 1), (3, 128, 4, 64, 1), (1, 72, 3, 32, 1), (2, 200, 2, 64, 0), (8, 256, 2, 64, 1),
+]
+
+
+@pytest.mark.parametrize("B,T,H,hd,causal", ATTN_CASES, ids=[f"attn_B{c[0]}_T{c[1]}_H{c[2]}_hd{c[3]}_causal{c[4]}" for c in ATTN_CASES])
+def test_attention_fwd_bf16(gpu, oracle, B, T, H, hd, causal):
+    """Fused attention core (heads relayout + bf16 pack, tcgen05 QK^T, softmax -> bf16 P, tcgen05 PV).
+    (1) vs the oracle model with the same bf16 rounding points: accumulation order and the odd
+    one-ulp flip of a rounded probability -> 2e-3 relative-to-max;
+    (2) vs the exact fp32 chain (reference arithmetic, multihead_attention.cpp:289-345): the bf16
+    bound, 2e-2 relative-to-max."""
+    import ctypes as C
+    rng = np.random.default_rng(9000 + B + T + H + hd)
+    n = B * T * H * hd
+    q, k, v = (rng.uniform(-1, 1, n).astype(np.float32) for _ in range(3))
+    div, mask = np.float32(np.sqrt(hd)), np.float32(-1.701411835e38)
+
+    def run(be):
+        hq, hk, hv, ho = be.buf(q), be.buf(k), be.buf(v), be.buf(np.zeros(n, np.float32))
+        be.call("attention_fwd", hq, hk, hv, ho, C.c_uint32(B), C.c_uint32(T), C.c_uint32(H), C.c_uint32(hd), div, mask, C.c_int(causal))
+        return ho.get()
+
+    got, model = run(gpu), run(oracle)
+    gpu.sync()
+    # exact fp32 chain in numpy: x[b, t, c] lives at b + B*t + B*T*c
+    def heads(x):
+        return x.reshape(H, hd, T, B).transpose(3, 0, 2, 1).astype(np.float64)  # [B, H, T, hd]
+    Q, K, V = heads(q), heads(k), heads(v)
+    S = Q @ K.transpose(0, 1, 3, 2) / float(div)
+    if causal:
+        S = S + np.triu(np.full((T, T), float(mask)), 1)
+    S = S - S.max(-1, keepdims=True)
+    Pm = np.exp(S)
+    Pm /= Pm.sum(-1, keepdims=True)
+    exact = (Pm @ V).transpose(1, 3, 2, 0).reshape(-1).astype(np.float32)  # back to [B, T, H*hd] col-major
+    assert np.all(np.isfinite(got))
+    assert cases.rel_err(got, model) <= 2e-3, f"vs bf16 model: {cases.rel_err(got, model):.3e}"
+    assert cases.rel_err(got, exact) <= 2e-2, f"vs fp32 chain: {cases.rel_err(got, exact):.3e}"
+
+
+def test_attention_fwd_unsupported_shapes_say_so(gpu):
+    """Outside the tensor-map envelope the entry returns WEEDCU_ENOSUP (callers compose the generic
+    ops) instead of computing something else."""
+    import ctypes as C
+    h = gpu.buf(np.zeros(4 * 60 * 16, np.float32))
+    fn = gpu.lib.weedcu_attention_fwd
+    fn.restype = C.c_int
+    rc = fn(C.c_void_p(h.ptr), C.c_void_p(h.ptr), C.c_void_p(h.ptr), C.c_void_p(h.ptr), C.c_uint32(4), C.c_uint32(60), C.c_uint32(1), C.c_uint32(16),
+            C.c_float(4.0), C.c_float(-1e38), C.c_int(1), C.c_void_p(gpu.stream))
+    assert rc == -2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 200, 96), (8192, 768, 256), (257, 130, 72)])
+def test_gemm_bf16_col_bias_epilogue(gpu, oracle, M, N, K):
+    """weedcu_pack_bf16 + weedcu_gemm_bf16 with the column bias added in the epilogue (TMA-store and
+    direct-store paths, ragged tiles) against the bf16-rounding model + a broadcast add."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K)
+    a = rng.uniform(-1, 1, M * K).astype(np.float32)   # [M, K] M contiguous
+    b = rng.uniform(-1, 1, K * N).astype(np.float32)   # [K, N] K contiguous
+    bias = rng.uniform(-2, 2, N).astype(np.float32)
+    r8 = lambda x: (x + 7) // 8 * 8
+    ha, hb, hbias = gpu.buf(a), gpu.buf(b), gpu.buf(bias)
+    pa, pb = gpu.buf(np.zeros(r8(M) * K + 8, np.uint16)), gpu.buf(np.zeros(r8(K) * N + 8, np.uint16))
+    hc = gpu.buf(np.zeros(M * N, np.float32))
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    gpu.call("pack_bf16", ha, U64(0), U32(1), U32(M), U32(M), U32(K), pa, I32(1))   # rows = m (stride 1), cols = k
+    gpu.call("pack_bf16", hb, U64(0), U32(K), U32(1), U32(N), U32(K), pb, I32(0))   # rows = n (stride K), cols = k
+    gpu.call("gemm_bf16", pa, I32(1), U64(r8(M)), pb, I32(0), U64(r8(K)), hc, U64(M), U32(M), U32(N), U32(K), I32(0), hbias)
+    got = hc.get().reshape(N, M).T
+    gpu.sync()
+    bf = lambda x: (lambda u: ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32))(x.view(np.uint32).astype(np.uint64))
+    A = bf(a).reshape(K, M).T.astype(np.float64)
+    B = bf(b).reshape(N, K).T.astype(np.float64)
+    want = (A @ B + bias[None, :].astype(np.float64)).astype(np.float32)
+    assert cases.rel_err(got, want) <= 1e-4

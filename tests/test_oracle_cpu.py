@@ -111,7 +111,7 @@ def test_reference_unit_test_vectors(O, v):
         hd = O.buf(np.zeros(src.size, F32))
         sh = [src.size]
         O.call("unary_grad_real", I32({"relu_grad": 0, "sigmoid_grad": 1, "tanh_grad": 2}[op]), hd, cview(sh), O.buf(src), cview(sh),
-               O.buf(np.ones(src.size, F32)), cview(sh))
+               O.buf(np.ones(src.size, F32)), cview(sh), I32(1))
         got = hd.get()
     else:
         raise AssertionError(f"unhandled vector op {op}")
@@ -192,7 +192,7 @@ def test_cross_entropy_backward_is_softmax_minus_onehot(O):
     hlse, hloss = O.buf(np.zeros(rows, F32)), O.buf(np.zeros(1, F32))
     O.call("cross_entropy_fwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, hloss)
     hd = O.buf(np.zeros(rows * V, F32))
-    O.call("cross_entropy_bwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, O.buf(np.ones(1, F32)), hd, U64(0))
+    O.call("cross_entropy_bwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, O.buf(np.ones(1, F32)), hd, U64(0), I32(1))
     x = logits.astype(np.float64).reshape(V, rows).T  # [rows, V]
     p = np.exp(x - x.max(1, keepdims=True))
     p /= p.sum(1, keepdims=True)

@@ -110,7 +110,7 @@ def bench_ew(results, peaks):
     ms = timeit(lambda i: call("unary_real", I32(0), F(0), P(A[i]), va, P(O[i]), va), k)
     rec("relu_fwd_8192x3072", ms, 8 * M * N)
     G = bufs(M * N, k)
-    ms = timeit(lambda i: call("unary_grad_real", I32(7), P(O[i]), va, P(A[i]), va, P(G[i]), va), k)
+    ms = timeit(lambda i: call("unary_grad_real", I32(7), P(O[i]), va, P(A[i]), va, P(G[i]), va, I32(1)), k)
     rec("gelu_grad_8192x3072", ms, 16 * M * N)
     # --- transposed copy: contiguous(transpose(x,1,2)) for [B,T,H,hd] -> [B,H,T,hd]
     Bq, T, H, hd = 8, 1024, 12, 64
@@ -176,8 +176,11 @@ def bench_ew(results, peaks):
                                    P(mu), P(rs)), k)
         rec(f"layernorm_fwd_8192x{Fd}", ms, 8 * n)
         ms = timeit(lambda i: call("layernorm_bwd", P(X[i]), P(DY[i]), U32(rows), U32(Fd), P(g), P(mu), P(rs),
-                                   P(DX[i]), P(dg), P(db), I32(0)), k)
+                                   P(DX[i]), P(dg), P(db), I32(0), I32(1)), k)
         rec(f"layernorm_bwd_8192x{Fd}", ms, 16 * n)
+        ms = timeit(lambda i: call("layernorm_bwd", P(X[i]), P(DY[i]), U32(rows), U32(Fd), P(g), P(mu), P(rs),
+                                   P(DX[i]), P(dg), P(db), I32(0), I32(0)), k)
+        rec(f"layernorm_bwd_store_8192x{Fd}", ms, 12 * n)
         del X, Y, DY, DX
     # --- axis reductions
     rows, Fd = 8192, 768
@@ -207,8 +210,11 @@ def bench_ew(results, peaks):
                                P(lse), P(loss)), 1, iters=5, warmup=2)
     rec("cross_entropy_fwd_8192x50257", ms, 4 * n)
     ms = timeit(lambda i: call("cross_entropy_bwd", P(L1), U64(0), U32(rows), U32(V), U32(1), U32(rows), P(tg),
-                               P(lse), P(one), P(DL), U64(0)), 1, iters=5, warmup=2)
+                               P(lse), P(one), P(DL), U64(0), I32(1)), 1, iters=5, warmup=2)
     rec("cross_entropy_bwd_8192x50257", ms, 12 * n)
+    ms = timeit(lambda i: call("cross_entropy_bwd", P(L1), U64(0), U32(rows), U32(V), U32(1), U32(rows), P(tg),
+                               P(lse), P(one), P(DL), U64(0), I32(0)), 1, iters=5, warmup=2)
+    rec("cross_entropy_bwd_store_8192x50257", ms, 8 * n)
     del L1, DL
     # --- embedding
     V, D, ntok = 50257, 768, 8192
@@ -252,7 +258,7 @@ def bench_gemm(results, peaks, which):
                 b = torch.randn(N * K, device="cuda").to(torch.bfloat16)
                 c = torch.zeros(M * N, device="cuda")
                 ms = timeit(lambda i: call("gemm_bf16", P(a), I32(am), U64(lda), P(b), I32(bm), U64(ldb), P(c), U64(M),
-                                           U32(M), U32(N), U32(K), I32(0)), 1, iters=10, warmup=3)
+                                           U32(M), U32(N), U32(K), I32(0), C.c_void_p(0)), 1, iters=10, warmup=3)
                 rec(f"gemm_bf16_tcgen05_M{M}_N{N}_K{K}_a{'MN' if am else 'K'}_b{'MN' if bm else 'K'}", ms,
                     2.0 * M * N * K)
                 del a, b, c

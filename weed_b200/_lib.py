@@ -78,14 +78,14 @@ SYMBOLS = """
 weedcu_device_count weedcu_set_device weedcu_get_device weedcu_device_info weedcu_error_string
 weedcu_default_stream weedcu_set_default_stream weedcu_stream_create weedcu_stream_destroy
 weedcu_stream_sync weedcu_stream_wait_event weedcu_event_create weedcu_event_destroy
-weedcu_event_record weedcu_event_sync weedcu_event_elapsed_ms weedcu_malloc weedcu_free
+weedcu_event_record weedcu_event_sync weedcu_event_elapsed_ms weedcu_malloc weedcu_free weedcu_pool_trim
 weedcu_mem_info weedcu_host_alloc weedcu_host_free weedcu_memcpy_h2d weedcu_memcpy_d2h
 weedcu_memcpy_d2d weedcu_launch_count weedcu_host_stats weedcu_fill_real weedcu_fill_int weedcu_binary_real
 weedcu_inplace_real weedcu_copy_real weedcu_unary_real weedcu_unary_grad_real weedcu_reduce_real
 weedcu_reduce_grad_real weedcu_sum_real weedcu_softmax_real weedcu_softmax_grad_real
-weedcu_attn_softmax_real weedcu_cross_entropy_fwd weedcu_cross_entropy_bwd weedcu_layernorm_fwd
+weedcu_attn_softmax_real weedcu_attention_fwd weedcu_cross_entropy_fwd weedcu_cross_entropy_bwd weedcu_layernorm_fwd
 weedcu_layernorm_bwd weedcu_embedding_gather weedcu_embedding_scatter_add weedcu_triu_fill_real
-weedcu_argmax_rows weedcu_sgd_step weedcu_adam_step weedcu_matmul_real weedcu_gemm_bf16
+weedcu_argmax_rows weedcu_sgd_step weedcu_adam_step weedcu_adam_step_multi weedcu_matmul_real weedcu_gemm_bf16
 weedcu_pack_bf16 weedcu_gemm_workspace_bytes weedcu_prof_enable weedcu_prof_read weedcu_nccl_load weedcu_nccl_unique_id
 weedcu_nccl_init weedcu_nccl_destroy weedcu_nccl_allreduce_sum weedcu_nccl_broadcast
 """.split()

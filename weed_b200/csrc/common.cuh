@@ -18,6 +18,11 @@ constexpr int kNumSMs = 148; // B200: 2 dies x 74 SMs; grids are sized in multip
 cudaStream_t resolve_stream(void *s);
 void count_launch(int n = 1);
 int after_launch(); // cudaGetLastError -> return code, bumps the launch counter
+// stream-ordered caching allocator (runtime.cu); kernels' workspaces come from it too
+cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t st);
+cudaError_t pool_free(void *ptr, cudaStream_t st);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel, not once per launch
+void ensure_dynamic_smem(const void *kernel, int bytes);
 
 // Optional per-class event timing (weedcu_prof_*). A scope brackets the launches issued while it
 // is alive; when profiling is off it costs one predictable branch.

@@ -8,6 +8,10 @@
 // copy_broadcast.cpp:27-30, real_unary.cpp:47-83, abs.cpp:70-94, pow.cpp:52-77.
 #include "common.cuh"
 
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 namespace weedcu {
 
 template <int NIN> struct EwPtrs {
@@ -185,6 +189,14 @@ template <int OP> struct UnaryGradF {
   }
 };
 
+// store variant (din known to be zero and never read): x[0] = in, x[1] = dout
+template <int OP> struct UnaryGradSetF {
+  __device__ float operator()(const float *x) const {
+    const float y[3] = {0.0f, x[0], x[1]};
+    return UnaryGradF<OP>()(y);
+  }
+};
+
 // ------------------------------------------------------------------------------- fills
 template <typename T> struct alignas(16) Quad { T x, y, z, w; };
 
@@ -207,6 +219,14 @@ __global__ void __launch_bounds__(256) fill_kernel(T *p, uint64_t n, T v) {
 }
 
 // ------------------------------------------------------------------------------- optimisers
+struct AdamChunk {
+  float *p;
+  const float *g;
+  float *m, *v;
+  uint32_t n;
+  int vec;
+};
+constexpr uint64_t kAdamChunk = 32768; // elements per block of the multi-tensor launch
 // sgd_step (reference include/autograd/sgd.hpp:23-37): p -= lr * g.  12 B/param.
 __global__ void __launch_bounds__(256)
 sgd_kernel(float *__restrict__ p, const float *__restrict__ g, uint64_t n, float lr, float gscale,
@@ -264,6 +284,30 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
     for (uint64_t i = (nq << 2) + tid; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
   } else {
     for (uint64_t i = tid; i < n; i += stride) adam_one(p[i], g[i], m[i], v[i], a);
+  }
+}
+
+// One block per chunk of one parameter: `count` parameters updated by a single launch.
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__restrict__ table, AdamArgs a) {
+  const AdamChunk c = table[blockIdx.x];
+  if (c.vec) {
+    const uint32_t nq = c.n >> 2;
+    for (uint32_t i = threadIdx.x; i < nq; i += 256) {
+      float4 pv = reinterpret_cast<float4 *>(c.p)[i];
+      const float4 gv = reinterpret_cast<const float4 *>(c.g)[i];
+      float4 mv = reinterpret_cast<float4 *>(c.m)[i];
+      float4 vv = reinterpret_cast<float4 *>(c.v)[i];
+      adam_one(pv.x, gv.x, mv.x, vv.x, a);
+      adam_one(pv.y, gv.y, mv.y, vv.y, a);
+      adam_one(pv.z, gv.z, mv.z, vv.z, a);
+      adam_one(pv.w, gv.w, mv.w, vv.w, a);
+      reinterpret_cast<float4 *>(c.p)[i] = pv;
+      reinterpret_cast<float4 *>(c.m)[i] = mv;
+      reinterpret_cast<float4 *>(c.v)[i] = vv;
+    }
+    for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g[i], c.m[i], c.v[i], a);
+  } else {
+    for (uint32_t i = threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g[i], c.m[i], c.v[i], a);
   }
 }
 
@@ -349,10 +393,12 @@ int weedcu_unary_real(int op, float param, const float *a, const weedcu_view *av
 }
 
 #define WCU_GRAD_CASE(OP)                                                                          \
-  case OP: return launch_ew<3>(views, ins, din, UnaryGradF<OP>(), st);
+  case OP:                                                                                         \
+    return accumulate ? launch_ew<3>(views, ins, din, UnaryGradF<OP>(), st)                        \
+                      : launch_ew<2>(views + 1, ins + 1, din, UnaryGradSetF<OP>(), st);
 int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const float *in,
                            const weedcu_view *inv, const float *dout, const weedcu_view *doutv,
-                           void *stream) {
+                           int accumulate, void *stream) {
   if (!dinv || !inv || !doutv) return WEEDCU_EINVAL;
   const weedcu_view *views[4] = {dinv, inv, doutv, dinv};
   const float *ins[3] = {din, in, dout};
@@ -367,6 +413,51 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
     WCU_GRAD_CASE(WEEDCU_COS)
   }
   return WEEDCU_EINVAL;
+}
+
+int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m,
+                           float *const *v, const uint64_t *n, float lr, float beta1, float beta2,
+                           float eps, float bc1, float bc2, float gscale, void *stream) {
+  if (!count) return 0;
+  if (!p || !g || !m || !v || !n) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  // chunk table, kept on the device between calls while the parameter list does not change
+  static std::vector<AdamChunk> host_table;
+  static AdamChunk *dev_table = nullptr;
+  static size_t dev_capacity = 0;
+  static std::mutex table_mutex;
+  std::lock_guard<std::mutex> lock(table_mutex);
+  std::vector<AdamChunk> table;
+  double total = 0.0;
+  for (uint32_t t = 0; t < count; ++t) {
+    if (!p[t] || !g[t] || !m[t] || !v[t]) return WEEDCU_EINVAL;
+    const int vec = (aligned16(p[t]) && aligned16(g[t]) && aligned16(m[t]) && aligned16(v[t])) ? 1 : 0;
+    for (uint64_t o = 0; o < n[t]; o += kAdamChunk) {
+      const uint64_t len = (n[t] - o < kAdamChunk) ? n[t] - o : kAdamChunk;
+      table.push_back(AdamChunk{p[t] + o, g[t] + o, m[t] + o, v[t] + o, (uint32_t)len, vec});
+    }
+    total += (double)n[t];
+  }
+  if (table.empty()) return 0;
+  const bool same = table.size() == host_table.size() &&
+                    memcmp(table.data(), host_table.data(), table.size() * sizeof(AdamChunk)) == 0;
+  if (!same) {
+    if (table.size() > dev_capacity) {
+      if (dev_table) pool_free(dev_table, st);
+      dev_table = nullptr;
+      dev_capacity = 0;
+      WCU_CHECK(pool_alloc((void **)&dev_table, table.size() * sizeof(AdamChunk), st));
+      dev_capacity = table.size();
+    }
+    host_table.swap(table); // the async copy reads host_table, which outlives it
+    WCU_CHECK(cudaMemcpyAsync(dev_table, host_table.data(), host_table.size() * sizeof(AdamChunk),
+                              cudaMemcpyHostToDevice, st));
+    WCU_CHECK(cudaStreamSynchronize(st)); // pageable source: make the staging copy complete
+  }
+  AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
+  ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total);
+  adam_multi_kernel<<<(unsigned)host_table.size(), 256, 0, st>>>(dev_table, a);
+  return after_launch();
 }
 
 int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale, void *stream) {

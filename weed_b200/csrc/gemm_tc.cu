@@ -150,6 +150,7 @@ struct Params {
   uint32_t M, N, K, batch;
   uint32_t tiles_m, tiles_n;
   int accumulate;
+  const float *col_bias; // optional [N]: C[m,n] = sum_k A B + col_bias[n]  (Linear::forward's bias add)
   int tma_store; // C goes out through TMA (needs 16-B aligned base / leading dimension); else direct stores
 };
 
@@ -299,7 +300,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           epi_bar_sync();
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+          float bias_lane = 0.0f; // lane j holds the bias of column c0 + j
+          if (p.col_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
           tmem_ld_wait();
+          if (p.col_bias) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
+          }
           if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the MMA warp early
             tcgen05_fence_before();
             __syncwarp();
@@ -325,7 +332,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+          float bias_lane = 0.0f;
+          if (p.col_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
           tmem_ld_wait();
+          if (p.col_bias) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
+          }
           float *dst = crow + (uint64_t)(n0 + c0) * p.ldc;
           if (full_tile && !p.accumulate) {
 #pragma unroll
@@ -422,8 +435,7 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return (int)e;                                                           \
+    ensure_dynamic_smem((const void *)k, (int)smem);                                               \
     k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p);                                          \
   }
   if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
@@ -436,7 +448,8 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
 
 int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
                      int b_major, uint64_t ldb, uint64_t b_bs, float *c, uint64_t ldc, uint64_t c_bs,
-                     uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st) {
+                     uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
+                     const float *col_bias) {
   if (!a || !b || !c || !M || !N || !K || !batch) return WEEDCU_EINVAL;
   const bool wide = (N > 128);
   const uint32_t block_n = wide ? 256 : 128;
@@ -453,6 +466,7 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (N + block_n - 1) / block_n;
   p.accumulate = accumulate;
+  p.col_bias = col_bias;
   CUtensorMap tmC;
   p.tma_store = make_c_map(&tmC, c, M, N, ldc, batch, c_bs) ? 1 : 0;
   if (!p.tma_store) tmC = tmA; // unused by the kernel, but must be a valid descriptor
@@ -497,6 +511,27 @@ pack_bf16_kernel(const float *__restrict__ src, uint64_t s_bs, uint32_t s0, uint
   }
 }
 
+// Same majorness on both sides (the usual case: operands are packed in the majorness they already
+// have): a pure streaming conversion, 8 elements per thread (2 x 128-bit loads, 1 x 128-bit store).
+__global__ void __launch_bounds__(256)
+pack_bf16_stream_kernel(const float *__restrict__ src, uint64_t s_bs, uint64_t ss, uint32_t n_fast8,
+                        uint32_t n_slow, __nv_bfloat16 *__restrict__ dst, uint64_t d_bs, uint64_t ld) {
+  const float *s = src + (uint64_t)blockIdx.z * s_bs;
+  __nv_bfloat16 *d = dst + (uint64_t)blockIdx.z * d_bs;
+  const uint64_t total = (uint64_t)n_fast8 * n_slow, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const uint32_t j = (uint32_t)(i / n_fast8), f = (uint32_t)(i - (uint64_t)j * n_fast8) << 3;
+    const float4 a = *reinterpret_cast<const float4 *>(s + (uint64_t)j * ss + f);
+    const float4 b = *reinterpret_cast<const float4 *>(s + (uint64_t)j * ss + f + 4);
+    __nv_bfloat162 o[4];
+    o[0] = __floats2bfloat162_rn(a.x, a.y);
+    o[1] = __floats2bfloat162_rn(a.z, a.w);
+    o[2] = __floats2bfloat162_rn(b.x, b.y);
+    o[3] = __floats2bfloat162_rn(b.z, b.w);
+    *reinterpret_cast<uint4 *>(d + (uint64_t)j * ld + f) = *reinterpret_cast<const uint4 *>(o);
+  }
+}
+
 int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols,
                      uint16_t *dst, uint64_t d_bs, uint64_t ld, int dst_major, uint32_t batch,
                      cudaStream_t st) {
@@ -504,6 +539,17 @@ int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, 
   if (grid.y > 65535 || grid.z > 65535) return WEEDCU_EINVAL;
   const int src_rowfast = (s0 <= s1) ? 1 : 0;
   ProfScope prof(WEEDCU_PROF_PACK, st, 6.0 * (double)rows * cols * batch);
+  {
+    const uint32_t n_fast = dst_major ? rows : cols, n_slow = dst_major ? cols : rows;
+    const uint64_t s_fast = dst_major ? s0 : s1, ss = dst_major ? s1 : s0;
+    if (s_fast == 1 && (n_fast % 8u) == 0 && (ss % 4u) == 0 && (s_bs % 4u) == 0 && (d_bs % 8u) == 0 &&
+        (((uintptr_t)src) & 15u) == 0 && (((uintptr_t)dst) & 15u) == 0) {
+      const uint64_t total = (uint64_t)(n_fast / 8u) * n_slow;
+      pack_bf16_stream_kernel<<<dim3(grid_for(total, 256, 16), 1, batch), 256, 0, st>>>(
+          src, s_bs, ss, n_fast / 8u, n_slow, (__nv_bfloat16 *)dst, d_bs, ld);
+      return after_launch();
+    }
+  }
   pack_bf16_kernel<<<grid, 256, 0, st>>>(src, s_bs, s0, s1, rows, cols, (__nv_bfloat16 *)dst, d_bs, ld,
                                          dst_major, src_rowfast);
   return after_launch();
@@ -523,9 +569,9 @@ extern "C" {
 
 int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
                      uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
-                     int accumulate, void *stream) {
+                     int accumulate, const float *col_bias, void *stream) {
   return tc::launch_gemm_bf16(a, a_major, lda, 0, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
-                              resolve_stream(stream));
+                              resolve_stream(stream), col_bias);
 }
 
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
@@ -561,7 +607,7 @@ int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, con
   const uint64_t a_elems = a_major ? lda * K : lda * M, b_elems = b_major ? ldb * K : ldb * N;
   const uint64_t a_bs = round8(a_elems), b_bs = round8(b_elems);
   uint16_t *ws = nullptr;
-  WCU_CHECK(cudaMallocAsync((void **)&ws, 2ull * batch * (a_bs + b_bs), st));
+  WCU_CHECK(pool_alloc((void **)&ws, 2ull * batch * (a_bs + b_bs), st));
   uint16_t *wa = ws, *wb = ws + (uint64_t)batch * a_bs;
   int rc = launch_pack_bf16(a + am->offset, am->batch_stride, am->s0, am->s1, M, K, wa, a_bs, lda, a_major,
                             batch, st);
@@ -571,8 +617,8 @@ int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, con
                           batch, st);
   if (rc == 0)
     rc = tc::launch_gemm_bf16(wa, a_major, lda, a_bs, wb, b_major, ldb, b_bs, c + cm->offset, cm->s1,
-                              cm->batch_stride, M, N, K, batch, accumulate, st);
-  cudaFreeAsync(ws, st);
+                              cm->batch_stride, M, N, K, batch, accumulate, st, nullptr);
+  pool_free(ws, st);
   if (rc == WEEDCU_ENOSUP) return launch_gemm_f32(a, am, b, bm, c, cm, M, K, N, batch, accumulate, st);
   return rc;
 }

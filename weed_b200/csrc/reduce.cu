@@ -329,7 +329,7 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
   unsigned blocks = grid_for(vec ? (sp.n >> 2) : sp.n, 256, 4);
   if (blocks > 1024) blocks = 1024;
   float *partial = nullptr;
-  WCU_CHECK(cudaMallocAsync((void **)&partial, sizeof(float) * blocks, st));
+  WCU_CHECK(pool_alloc((void **)&partial, sizeof(float) * blocks, st));
   ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * sp.n);
   sum_pass1_kernel<1><<<blocks, 256, 0, st>>>(base, sp, vec, partial);
   int rc = after_launch();
@@ -337,7 +337,7 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
     sum_pass2_kernel<<<1, 1024, 0, st>>>(partial, blocks, scale, out);
     rc = after_launch();
   }
-  cudaFreeAsync(partial, st);
+  pool_free(partial, st);
   return rc;
 }
 

@@ -20,6 +20,7 @@ constexpr size_t kMaxTileBytes = 200 * 1024;  // dynamic shared memory budget fo
 
 struct PlainLoad {
   __device__ float operator()(float x, uint32_t, uint32_t) const { return x; }
+  __device__ uint32_t cols(uint32_t, uint32_t L) const { return L; }
 };
 // scores / sqrt(hd) + triu mask (multihead_attention.cpp:319-328; triu_fill.cpp:48-56)
 struct AttnLoad {
@@ -34,31 +35,42 @@ struct AttnLoad {
     }
     return v;
   }
+  // columns some row of a tile ending at row_last can see: beyond them exp(v + mask - max) == 0.0f
+  __device__ uint32_t cols(uint32_t row_last, uint32_t L) const {
+    return (causal && mask_val <= -1e30f) ? min(L, row_last / batch + 1u) : L;
+  }
 };
 
 // ----------------------------------------------------------------------------- forward, strided
-// a[inner, L, outer] canonical contiguous; rows = inner (per outer slab).
-template <bool LOG, int BY, bool STAGED, class LD>
-__global__ void __launch_bounds__(kRT * BY)
+// a[inner, L, outer] canonical contiguous; rows = inner (per outer slab). Block = RT rows x BY column
+// lanes (a warp covers RT adjacent rows x 32/RT columns, so every access is whole 32-B sectors); the
+// host picks RT so that the staged tile stays ~32 KB and several CTAs are resident per SM — their
+// load / exp / store phases then overlap each other.
+// LD::cols() lets the attention variant skip columns that are masked for every row of the tile
+// (exp underflows to exactly 0 there): they are neither read nor exponentiated, only zero-filled.
+template <bool LOG, int RT, int BY, bool STAGED, class LD>
+__global__ void __launch_bounds__(RT * BY)
 softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
                     LD ld) {
-  extern __shared__ float tile[]; // [L][kRT] when STAGED
-  __shared__ float red_m[BY][kRT + 1];
-  __shared__ float red_s[BY][kRT + 1];
+  extern __shared__ float tile[]; // [L][RT] when STAGED
+  __shared__ float red_m[BY][RT + 1];
+  __shared__ float red_s[BY][RT + 1];
   const uint32_t tx = threadIdx.x, ty = threadIdx.y;
-  const uint32_t r = blockIdx.x * kRT + tx;
+  const uint32_t r0 = blockIdx.x * RT;
+  const uint32_t r = r0 + tx;
   const bool live = r < inner;
   const uint64_t slab = (uint64_t)blockIdx.y * inner * L;
   const float *p = a + slab + r;
   float *po = out + slab + r;
   const uint32_t grow = r; // row id inside the slab (attention: b + batch*q)
+  const uint32_t Lc = ld.cols(min(r0 + RT, inner) - 1u, L);
 
   float mx = -INFINITY, s = 0.0f;
   if (STAGED) {
     if (live)
-      for (uint32_t j = ty; j < L; j += BY) {
+      for (uint32_t j = ty; j < Lc; j += BY) {
         const float v = ld(p[(uint64_t)j * inner], grow, j);
-        tile[j * kRT + tx] = v;
+        tile[j * RT + tx] = v;
         mx = fmaxf(mx, v);
       }
     red_m[ty][tx] = mx;
@@ -66,9 +78,9 @@ softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
 #pragma unroll
     for (int y = 0; y < BY; ++y) mx = fmaxf(mx, red_m[y][tx]);
     if (live)
-      for (uint32_t j = ty; j < L; j += BY) {
-        const float e = expf(tile[j * kRT + tx] - mx);
-        if (!LOG) tile[j * kRT + tx] = e;
+      for (uint32_t j = ty; j < Lc; j += BY) {
+        const float e = expf(tile[j * RT + tx] - mx);
+        if (!LOG) tile[j * RT + tx] = e;
         s += e;
       }
     red_s[ty][tx] = s;
@@ -79,15 +91,15 @@ softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
     if (live) {
       if (LOG) {
         const float log_s = logf(s);
-        for (uint32_t j = ty; j < L; j += BY) po[(uint64_t)j * inner] = (tile[j * kRT + tx] - mx) - log_s;
+        for (uint32_t j = ty; j < Lc; j += BY) po[(uint64_t)j * inner] = (tile[j * RT + tx] - mx) - log_s;
       } else {
-        for (uint32_t j = ty; j < L; j += BY) po[(uint64_t)j * inner] = tile[j * kRT + tx] / s;
+        for (uint32_t j = ty; j < Lc; j += BY) po[(uint64_t)j * inner] = tile[j * RT + tx] / s;
       }
     }
   } else {
     // Row too long to stage: one online (max, sum) pass + one normalise pass (12 B/elem).
     if (live)
-      for (uint32_t j = ty; j < L; j += BY) {
+      for (uint32_t j = ty; j < Lc; j += BY) {
         const float v = ld(p[(uint64_t)j * inner], grow, j);
         if (v > mx) {
           s = s * expf(mx - v) + 1.0f;
@@ -110,12 +122,14 @@ softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
     }
     if (live) {
       const float log_s = logf(S);
-      for (uint32_t j = ty; j < L; j += BY) {
+      for (uint32_t j = ty; j < Lc; j += BY) {
         const float v = ld(p[(uint64_t)j * inner], grow, j);
         po[(uint64_t)j * inner] = LOG ? ((v - M) - log_s) : (expf(v - M) / S);
       }
     }
   }
+  if (live)
+    for (uint32_t j = Lc + ty; j < L; j += BY) po[(uint64_t)j * inner] = 0.0f;
 }
 
 // ----------------------------------------------------------------------------- forward, contiguous
@@ -242,27 +256,40 @@ softmax_contig_bwd(float *din, const float *__restrict__ out, const float *__res
 }
 
 // ----------------------------------------------------------------------------- cross entropy
-// logits[rows, V], row stride rs, vocab stride vs. One read of the logits (4 B/elem): online
-// (max, sum exp) per row, gather of the target logit, lse[r] and nll[r] = lse[r] - x[r,target].
-template <int BY>
-__global__ void __launch_bounds__(kRT * BY)
-ce_fwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
-              const int32_t *__restrict__ targets, float *__restrict__ lse, float *__restrict__ nll) {
-  __shared__ float red_m[BY][kRT + 1];
-  __shared__ float red_s[BY][kRT + 1];
+// logits[rows, V], row stride rs, vocab stride vs. One read of the logits (4 B/elem): the vocab
+// range is split over blockIdx.y so that the grid fills the GPU whatever `rows` is; each block keeps
+// an online (max, sum exp) per row over its slice, `ce_fwd_finish` merges the slices, gathers the
+// target logit and writes lse[r] and nll[r] = x[r,target] - lse[r] (loss = -mean).
+constexpr int kCeRT = 32, kCeBY = 8, kCeU = 4;
+__global__ void __launch_bounds__(kCeRT * kCeBY)
+ce_fwd_partial(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
+               uint32_t v_per_block, float *__restrict__ part_m, float *__restrict__ part_s) {
+  __shared__ float red_m[kCeBY][kCeRT + 1];
+  __shared__ float red_s[kCeBY][kCeRT + 1];
   const uint32_t tx = threadIdx.x, ty = threadIdx.y;
-  const uint32_t r = blockIdx.x * kRT + tx;
+  const uint32_t r = blockIdx.x * kCeRT + tx;
   const bool live = r < rows;
+  const uint32_t v0 = blockIdx.y * v_per_block, v1 = min(V, v0 + v_per_block);
   const float *p = x + (uint64_t)r * rs;
   float mx = -INFINITY, s = 0.0f;
   if (live)
-    for (uint32_t j = ty; j < V; j += BY) {
-      const float v = p[(uint64_t)j * vs];
-      if (v > mx) {
-        s = s * expf(mx - v) + 1.0f;
-        mx = v;
-      } else {
-        s += expf(v - mx);
+    for (uint32_t j0 = v0 + ty; j0 < v1; j0 += kCeBY * kCeU) {
+      float v[kCeU];
+#pragma unroll
+      for (int u = 0; u < kCeU; ++u) {
+        const uint32_t j = j0 + u * kCeBY;
+        v[u] = (j < v1) ? p[(uint64_t)j * vs] : -INFINITY;
+      }
+      float m4 = v[0];
+#pragma unroll
+      for (int u = 1; u < kCeU; ++u) m4 = fmaxf(m4, v[u]);
+      if (m4 > mx) { // rescale the running sum once per batch
+        s *= expf(mx - m4);
+        mx = m4;
+      }
+      if (mx > -INFINITY) {
+#pragma unroll
+        for (int u = 0; u < kCeU; ++u) s += expf(v[u] - mx);
       }
     }
   red_m[ty][tx] = mx;
@@ -271,35 +298,78 @@ ce_fwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
   if (ty == 0 && live) {
     float M = -INFINITY;
 #pragma unroll
-    for (int y = 0; y < BY; ++y) M = fmaxf(M, red_m[y][tx]);
+    for (int y = 0; y < kCeBY; ++y) M = fmaxf(M, red_m[y][tx]);
     float S = 0.0f;
 #pragma unroll
-    for (int y = 0; y < BY; ++y) {
+    for (int y = 0; y < kCeBY; ++y) {
       const float my = red_m[y][tx];
       if (my > -INFINITY) S += red_s[y][tx] * expf(my - M);
     }
-    const float log_s = logf(S);
-    const uint32_t t = (uint32_t)targets[r];
-    const float xt = (t < V) ? p[(uint64_t)t * vs] : NAN;
-    lse[r] = M + log_s;
-    nll[r] = (xt - M) - log_s; // = lsm[r, target]; loss = -mean
+    part_m[(uint64_t)blockIdx.y * rows + r] = M;
+    part_s[(uint64_t)blockIdx.y * rows + r] = S;
   }
 }
-// dlogits[r,v] += (exp(x - lse[r]) - onehot) * dloss/rows ; thread per element, r fastest.
 __global__ void __launch_bounds__(256)
-ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
-              const int32_t *__restrict__ targets, const float *__restrict__ lse,
-              const float *__restrict__ dloss, float *dlogits) {
-  const uint64_t n = (uint64_t)rows * V;
-  const float g = dloss[0] / (float)rows;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t r = (uint32_t)(i % rows), v = (uint32_t)(i / rows);
-    const uint64_t off = (uint64_t)r * rs + (uint64_t)v * vs;
-    const float pr = expf(x[off] - lse[r]);
-    const float oh = ((uint32_t)targets[r] == v) ? 1.0f : 0.0f;
-    dlogits[off] += (pr - oh) * g;
+ce_fwd_finish(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
+              const int32_t *__restrict__ targets, const float *__restrict__ part_m,
+              const float *__restrict__ part_s, uint32_t splits, float *__restrict__ lse,
+              float *__restrict__ nll) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float M = -INFINITY;
+  for (uint32_t k = 0; k < splits; ++k) M = fmaxf(M, part_m[(uint64_t)k * rows + r]);
+  float S = 0.0f;
+  for (uint32_t k = 0; k < splits; ++k) {
+    const float my = part_m[(uint64_t)k * rows + r];
+    if (my > -INFINITY) S += part_s[(uint64_t)k * rows + r] * expf(my - M);
   }
+  const float log_s = logf(S);
+  const uint32_t t = (uint32_t)targets[r];
+  const float xt = (t < V) ? x[(uint64_t)r * rs + (uint64_t)t * vs] : NAN;
+  lse[r] = M + log_s;
+  nll[r] = (xt - M) - log_s; // = lsm[r, target]
+}
+// dlogits[r,v] (+)= (exp(x - lse[r]) - onehot) * dloss/rows ; block = 32 rows x 8 vocab lanes.
+__global__ void __launch_bounds__(kCeRT * kCeBY)
+ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
+              uint32_t v_per_block, const int32_t *__restrict__ targets, const float *__restrict__ lse,
+              const float *__restrict__ dloss, float *dlogits, int accumulate) {
+  const uint32_t r = blockIdx.x * kCeRT + threadIdx.x;
+  if (r >= rows) return;
+  const uint32_t v0 = blockIdx.y * v_per_block, v1 = min(V, v0 + v_per_block);
+  const float g = dloss[0] / (float)rows, l = lse[r];
+  const uint32_t tgt = (uint32_t)targets[r];
+  const uint64_t base = (uint64_t)r * rs;
+  for (uint32_t j0 = v0 + threadIdx.y; j0 < v1; j0 += kCeBY * kCeU) {
+    float v[kCeU], d[kCeU];
+#pragma unroll
+    for (int u = 0; u < kCeU; ++u) {
+      const uint32_t j = j0 + u * kCeBY;
+      v[u] = (j < v1) ? x[base + (uint64_t)j * vs] : 0.0f;
+      d[u] = (accumulate && j < v1) ? dlogits[base + (uint64_t)j * vs] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kCeU; ++u) {
+      const uint32_t j = j0 + u * kCeBY;
+      if (j < v1) {
+        const float pr = expf(v[u] - l);
+        const float oh = (tgt == j) ? 1.0f : 0.0f;
+        dlogits[base + (uint64_t)j * vs] = d[u] + (pr - oh) * g;
+      }
+    }
+  }
+}
+// vocab slices so that (row tiles) x (slices) is ~8 blocks per SM
+static void ce_split(uint32_t rows, uint32_t V, uint32_t &splits, uint32_t &v_per_block) {
+  const uint32_t row_tiles = (rows + kCeRT - 1) / kCeRT;
+  uint32_t want = (8u * kNumSMs + row_tiles - 1) / row_tiles;
+  const uint32_t max_splits = (V + kCeBY * kCeU - 1) / (kCeBY * kCeU);
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 65535u) want = 65535u;
+  v_per_block = (V + want - 1) / want;
+  v_per_block = (v_per_block + kCeBY * kCeU - 1) / (kCeBY * kCeU) * (kCeBY * kCeU);
+  splits = (V + v_per_block - 1) / v_per_block;
 }
 
 // ----------------------------------------------------------------------------- host helpers
@@ -331,24 +401,29 @@ static bool same_shape(const weedcu_view *a, const weedcu_view *b) {
   return true;
 }
 
+template <bool LOG, int RT, int BY, bool STAGED, class LD>
+static void launch_strided_fwd_cfg(const float *a, float *out, uint32_t inner, uint32_t L, uint32_t outer,
+                                   LD ld, cudaStream_t st) {
+  const dim3 grid((inner + RT - 1) / RT, outer);
+  const size_t tile_bytes = STAGED ? (size_t)L * RT * sizeof(float) : 0;
+  auto k = softmax_strided_fwd<LOG, RT, BY, STAGED, LD>;
+  if (tile_bytes > 48 * 1024)
+    ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
+  k<<<grid, dim3(RT, BY), tile_bytes, st>>>(a, out, inner, L, ld);
+}
+
 template <bool LOG, class LD>
 static int launch_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L, uint32_t outer,
                               LD ld, cudaStream_t st) {
-  const dim3 grid((inner + kRT - 1) / kRT, outer);
-  const size_t tile_bytes = (size_t)L * kRT * sizeof(float);
-  if (tile_bytes <= kMaxTileBytes) {
-    if (L >= 512) {
-      auto k = softmax_strided_fwd<LOG, 32, true, LD>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes);
-      k<<<grid, dim3(kRT, 32), tile_bytes, st>>>(a, out, inner, L, ld);
-    } else {
-      auto k = softmax_strided_fwd<LOG, 8, true, LD>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes);
-      k<<<grid, dim3(kRT, 8), tile_bytes, st>>>(a, out, inner, L, ld);
-    }
-  } else {
-    softmax_strided_fwd<LOG, 32, false, LD><<<grid, dim3(kRT, 32), 0, st>>>(a, out, inner, L, ld);
-  }
+  // rows per tile: as wide as keeps the staged tile within ~32 KB (>= 6 CTAs per SM)
+  if ((size_t)L * 32 * sizeof(float) <= 32 * 1024)
+    launch_strided_fwd_cfg<LOG, 32, 8, true, LD>(a, out, inner, L, outer, ld, st);
+  else if ((size_t)L * 16 * sizeof(float) <= 32 * 1024)
+    launch_strided_fwd_cfg<LOG, 16, 16, true, LD>(a, out, inner, L, outer, ld, st);
+  else if ((size_t)L * 8 * sizeof(float) <= kMaxTileBytes)
+    launch_strided_fwd_cfg<LOG, 8, 32, true, LD>(a, out, inner, L, outer, ld, st);
+  else
+    launch_strided_fwd_cfg<LOG, 8, 64, false, LD>(a, out, inner, L, outer, ld, st);
   return after_launch();
 }
 
@@ -399,11 +474,11 @@ static int softmax_bwd_impl(float *din, const weedcu_view *iv, const float *out,
       if (tile_bytes <= kMaxTileBytes) {
         if (L >= 256) {
           auto k = softmax_strided_bwd<LOG, 32, true>;
-          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes);
+          ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
           k<<<grid, dim3(kRT, 32), tile_bytes, st>>>(pd, py, pg, (uint32_t)inner, L);
         } else {
           auto k = softmax_strided_bwd<LOG, 8, true>;
-          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes);
+          ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
           k<<<grid, dim3(kRT, 8), tile_bytes, st>>>(pd, py, pg, (uint32_t)inner, L);
         }
       } else {
@@ -476,12 +551,19 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
                              float *loss, void *stream) {
   if (!logits || !targets || !lse || !loss || !rows || !V) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
-  float *nll = nullptr;
-  WCU_CHECK(cudaMallocAsync((void **)&nll, sizeof(float) * rows, st));
+  uint32_t splits, vpb;
+  ce_split(rows, V, splits, vpb);
+  float *ws = nullptr; // nll[rows], part_m[splits][rows], part_s[splits][rows]
+  WCU_CHECK(pool_alloc((void **)&ws, sizeof(float) * (size_t)rows * (1 + 2 * (size_t)splits), st));
+  float *nll = ws, *pm = ws + rows, *ps = pm + (size_t)splits * rows;
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 4.0 * (double)rows * V);
-  ce_fwd_kernel<32><<<(rows + kRT - 1) / kRT, dim3(kRT, 32), 0, st>>>(logits + offset, rows, V, rs, vs,
-                                                                    targets, lse, nll);
+  ce_fwd_partial<<<dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, st>>>(
+      logits + offset, rows, V, rs, vs, vpb, pm, ps);
   int rc = after_launch();
+  if (rc == 0) {
+    ce_fwd_finish<<<(rows + 255) / 256, 256, 0, st>>>(logits + offset, rows, V, rs, vs, targets, pm, ps, splits, lse, nll);
+    rc = after_launch();
+  }
   if (rc == 0) {
     weedcu_view v;
     v.offset = 0;
@@ -490,18 +572,21 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
     v.stride[0] = 1;
     rc = weedcu_sum_real(nll, &v, -1.0f / (float)rows, loss, (void *)st);
   }
-  cudaFreeAsync(nll, st);
+  pool_free(ws, st);
   return rc;
 }
 
 int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
                              uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse,
-                             const float *dloss, float *dlogits, uint64_t d_offset, void *stream) {
+                             const float *dloss, float *dlogits, uint64_t d_offset, int accumulate,
+                             void *stream) {
   if (!logits || !targets || !lse || !dloss || !dlogits || !rows || !V) return WEEDCU_EINVAL;
   const uint64_t n = (uint64_t)rows * V;
-  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, resolve_stream(stream), 12.0 * (double)n);
-  ce_bwd_kernel<<<grid_for(n, 256, 32), 256, 0, resolve_stream(stream)>>>(
-      logits + offset, rows, V, rs, vs, targets, lse, dloss, dlogits + d_offset);
+  uint32_t splits, vpb;
+  ce_split(rows, V, splits, vpb);
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, resolve_stream(stream), (accumulate ? 12.0 : 8.0) * (double)n);
+  ce_bwd_kernel<<<dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, resolve_stream(stream)>>>(
+      logits + offset, rows, V, rs, vs, vpb, targets, lse, dloss, dlogits + d_offset, accumulate);
   return after_launch();
 }
 

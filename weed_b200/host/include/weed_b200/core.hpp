@@ -87,6 +87,10 @@ struct BackendConfig {
   int matmul_precision = WEEDCU_GEMM_FP32;
   // data-parallel: gradients are averaged over this many ranks inside the optimiser kernels
   real1 grad_scale = ONE_R1;
+  // keep bf16 operand shadows on their storages (pack once per write, not once per GEMM)
+  bool operand_cache = true;
+  // FillZeros() on device buffers is deferred until something reads the buffer (fused mode only)
+  bool lazy_zero = true;
 };
 BackendConfig &backend_config();
 
@@ -234,7 +238,32 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
   }
   virtual ~GpuStorage() { dev->SubtractAlloc(sizeof(T) * (size_t)TypedStorage<T>::size); }
   int64_t get_device_id() const override { return dev->deviceID; }
-  T *device_ptr() const { return reinterpret_cast<T *>(buffer->ptr); }
+  // Lazy zero-fill (fused mode): FillZeros() on a gradient only marks the buffer; the fill is issued
+  // by the first access that does not overwrite the whole buffer, and skipped entirely when the
+  // first consumer overwrites it (matmul / copy instead of accumulate) or nothing ever touches it.
+  // `version` counts potential writes; the bf16 operand shadows of GpuRealStorage key on it.
+  mutable bool zero_pending = false;
+  mutable uint64_t version = 0;
+  void materialize() const {
+    if (!zero_pending) return;
+    zero_pending = false;
+    const_cast<GpuStorage<T> *>(this)->fill_now(T(0));
+  }
+  virtual void fill_now(const T &v) = 0;
+  T *device_ptr() const { // read/write access
+    materialize();
+    ++version;
+    return reinterpret_cast<T *>(buffer->ptr);
+  }
+  const T *device_ptr_ro() const { // read-only access: does not invalidate shadows
+    materialize();
+    return reinterpret_cast<const T *>(buffer->ptr);
+  }
+  T *device_ptr_overwrite() const { // the caller overwrites every element
+    zero_pending = false;
+    ++version;
+    return reinterpret_cast<T *>(buffer->ptr);
+  }
   void write(const tcapint &, const T &) override { throw std::domain_error("Don't use GPU-based Storage::write()!"); }
   void add(const tcapint &, const T &) override { throw std::domain_error("Don't use GPU-based Storage::add()!"); }
   bool is_gpu() override { return true; }
@@ -243,17 +272,31 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
 struct GpuRealStorage : GpuStorage<real1> {
   GpuRealStorage(const tcapint &n, int64_t did, const bool &alloc = true) : GpuStorage<real1>(REAL_GPU_DENSE, n, did, alloc) {}
   GpuRealStorage(const std::vector<real1> &val, const int64_t &did = -1) : GpuStorage<real1>(REAL_GPU_DENSE, val, did) {}
-  void FillValue(const real1 &v) override { dev->FillValueReal(buffer, size, v); }
+  void FillValue(const real1 &v) override;
+  void fill_now(const real1 &v) override { dev->FillValueReal(buffer, size, v); }
   real1 operator[](const tcapint &idx) const override {
     if (idx >= size) throw std::invalid_argument("GpuStorage::operator[] argument out-of-bounds!");
+    materialize();
     return dev->GetReal(buffer, idx);
   }
   StoragePtr cpu() override;
+  // bf16 copies of matrix views of this storage, packed for the tensor-core GEMM (ops.cpp)
+  struct Bf16Shadow {
+    BufferPtr buf;
+    uint64_t version;
+    tcapint offset, n_fast, n_slow, s_fast, s_slow;
+  };
+  std::vector<Bf16Shadow> shadows;
 };
 struct GpuIntStorage : GpuStorage<symint> {
   GpuIntStorage(const tcapint &n, int64_t did, const bool &alloc = true) : GpuStorage<symint>(INT_GPU_DENSE, n, did, alloc) {}
   GpuIntStorage(const std::vector<symint> &val, const int64_t &did = -1) : GpuStorage<symint>(INT_GPU_DENSE, val, did) {}
-  void FillValue(const symint &v) override { dev->FillValueInt(buffer, size, v); }
+  void FillValue(const symint &v) override {
+    zero_pending = false;
+    ++version;
+    dev->FillValueInt(buffer, size, v);
+  }
+  void fill_now(const symint &v) override { dev->FillValueInt(buffer, size, v); }
   symint operator[](const tcapint &idx) const override {
     if (idx >= size) throw std::invalid_argument("GpuStorage::operator[] argument out-of-bounds!");
     return dev->GetInt(buffer, idx);
@@ -293,6 +336,7 @@ struct BaseTensor {
   tcapint get_broadcast_size() const;  // prod shape
   bool is_contiguous() const { return !offset && is_contiguous(shape, stride); }
   bool is_scalar() const;
+  bool covers_storage() const; // the view addresses every storage element exactly once
   tcapint get_storage_index(const tcapint &idx) const;
   void reshape(const std::vector<symint> &s);
   void transpose();
@@ -426,6 +470,8 @@ struct Tensor : public BaseTensor {
   static void make_mul_node(TensorPtr a, TensorPtr b, TensorPtr out);
   static TensorPtr matmul(TensorPtr a, TensorPtr b);
   static void make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out);
+  static void matmul_backward(TensorPtr a, TensorPtr b, TensorPtr out);
+  static TensorPtr linear(TensorPtr a, TensorPtr w, TensorPtr bias); // fused x W + bias, or nullptr
   static TensorPtr sub(TensorPtr a, TensorPtr b);
   static void make_sub_node(TensorPtr a, TensorPtr b, TensorPtr out);
   static TensorPtr div(TensorPtr a, TensorPtr b);
@@ -438,7 +484,11 @@ struct Tensor : public BaseTensor {
   static void make_log_node(TensorPtr a, real1 inv_log_b, TensorPtr out);
 
   // device pointer of element 0 of the underlying storage (GPU tensors only)
-  real1 *device_ptr() const;
+  real1 *device_ptr() const;          // read/write access (bumps the storage version)
+  const real1 *device_ptr_ro() const; // read-only access
+  // gradient destination: accumulate = 0 (and no zero-fill is issued) when the storage is lazily
+  // zeroed and this view covers all of it, so the kernel may store instead of add
+  real1 *device_ptr_accumulate(int &accumulate) const;
   void *stream() const;
 };
 

@@ -50,6 +50,9 @@ void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const
 void matmul(const Tensor &a, const Tensor &b, Tensor &out);
 // C (+)= A*B with the accumulate folded into the GEMM epilogue (make_matmul_node's tmp + add_in_place)
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out);
+// out = a b + bias (bias: dense [N], broadcast over rows) in one tensor-core GEMM; false (nothing
+// computed) when that kernel does not apply to these operands
+bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out);
 // `batch` independent products over 3-D views [batch, M, K] x [batch, K, N] -> [batch, M, N]
 // (the host loop of Tensor::matmul, tensor.cpp:1259-1269, as one strided-batched launch)
 void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3);

@@ -39,6 +39,12 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
   const real1 bias_correction1 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta1, (real1_s)opt.t));
   const real1 bias_correction2 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta2, (real1_s)opt.t));
   const BackendConfig &cfg = backend_config();
+  // fused path: every eligible parameter joins ONE multi-tensor launch (28 B/param; adam.hpp:84-104
+  // issues ~15 ops and ~12 temporaries per parameter)
+  std::vector<real1 *> mp, mm, mv;
+  std::vector<const real1 *> mg;
+  std::vector<uint64_t> mn;
+  void *mstream = nullptr;
   for (auto &p : params) {
     const auto it = opt.state.find(p);
     if (it == opt.state.end()) throw std::invalid_argument("Parameter passed to adam_step that was not registered with optimizer!");
@@ -46,10 +52,13 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
     TensorPtr g = p->grad;
     if (!g) throw std::invalid_argument("adam_step: parameter has no gradient");
     if (cfg.fused && flat_pair(*p, *g) && s.m->storage->size == p->storage->size && s.v->storage->size == p->storage->size) {
-      // one pass, 28 B/param: m, v, p updated in place (adam.hpp:84-104 allocates ~12 temporaries)
-      throw_on_error(weedcu_adam_step(p->device_ptr(), g->device_ptr(), s.m->device_ptr(), s.v->device_ptr(), p->storage->size, opt.lr,
-                                      opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, p->stream()),
-                     "adam_step");
+      if (mstream && mstream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
+      mstream = p->stream();
+      mp.push_back(p->device_ptr());
+      mg.push_back(g->device_ptr_ro());
+      mm.push_back(s.m->device_ptr());
+      mv.push_back(s.v->device_ptr());
+      mn.push_back(p->storage->size);
       continue;
     }
     if (cfg.grad_scale != ONE_R1) g = cfg.grad_scale * g;
@@ -60,6 +69,10 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
     tmp->match_shape(p);
     Weed::sub_in_place(*p, *tmp);
   }
+  if (!mp.empty())
+    throw_on_error(weedcu_adam_step_multi((uint32_t)mp.size(), mp.data(), mg.data(), mm.data(), mv.data(), mn.data(), opt.lr, opt.beta1,
+                                          opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, mstream),
+                   "adam_step");
 }
 
 void sgd_step(const std::vector<ParameterPtr> &params, real1 lr) {
@@ -68,7 +81,7 @@ void sgd_step(const std::vector<ParameterPtr> &params, real1 lr) {
     TensorPtr pg = p->grad;
     if (!pg) throw std::invalid_argument("sgd_step: parameter has no gradient");
     if (cfg.fused && flat_pair(*p, *pg)) {
-      throw_on_error(weedcu_sgd_step(p->device_ptr(), pg->device_ptr(), p->storage->size, lr, cfg.grad_scale, p->stream()), "sgd_step");
+      throw_on_error(weedcu_sgd_step(p->device_ptr(), pg->device_ptr_ro(), p->storage->size, lr, cfg.grad_scale, p->stream()), "sgd_step");
       continue;
     }
     TensorPtr tmp = (lr * cfg.grad_scale) * pg;
@@ -101,7 +114,7 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
     TensorPtr lse = Tensor::allocate_like(std::vector<tcapint>{rows}, *logits, DType::REAL, false, false);
     SymbolTensorPtr tg = targets->storage->device == DeviceTag::GPU ? targets : targets->cast(DeviceTag::GPU);
     const tcapint vs = logits->stride[rank - 1U];
-    throw_on_error(weedcu_cross_entropy_fwd(logits->device_ptr(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
+    throw_on_error(weedcu_cross_entropy_fwd(logits->device_ptr_ro(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
                                             lse->device_ptr(), loss->device_ptr(), logits->stream()),
                    "cross_entropy_loss");
     if (rg) {
@@ -110,9 +123,11 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
         TensorPtr loss = wloss.lock(); // the node is owned by this tensor: a strong capture would be a cycle
         if (!loss) return;
         TensorPtr dl = std::make_shared<Tensor>(*(logits->grad));
-        throw_on_error(weedcu_cross_entropy_bwd(logits->device_ptr(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
-                                                lse->device_ptr(), loss->grad->device_ptr() + loss->grad->offset, dl->device_ptr(),
-                                                dl->offset, logits->stream()),
+        int accumulate = 1;
+        real1 *dl_ptr = dl->device_ptr_accumulate(accumulate);
+        throw_on_error(weedcu_cross_entropy_bwd(logits->device_ptr_ro(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
+                                                lse->device_ptr_ro(), loss->grad->device_ptr_ro() + loss->grad->offset, dl_ptr, dl->offset,
+                                                accumulate, logits->stream()),
                        "cross_entropy_loss backward");
         logits->grad = dl;
       });

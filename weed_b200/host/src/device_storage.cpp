@@ -20,6 +20,8 @@ BackendConfig &backend_config() {
       const std::string s(e);
       c.matmul_precision = (s == "bf16") ? WEEDCU_GEMM_BF16 : WEEDCU_GEMM_FP32;
     }
+    if (const char *e = getenv("WEED_B200_OPERAND_CACHE")) c.operand_cache = atoi(e) != 0;
+    if (const char *e = getenv("WEED_B200_LAZY_ZERO")) c.lazy_zero = atoi(e) != 0;
     return c;
   }();
   return cfg;
@@ -148,7 +150,17 @@ void Storage::save(std::ostream &) const { throw std::domain_error("Storage::sav
 
 StoragePtr CpuRealStorage::gpu(const int64_t &did) { return std::make_shared<GpuRealStorage>(data, did); }
 StoragePtr CpuIntStorage::gpu(const int64_t &did) { return std::make_shared<GpuIntStorage>(data, did); }
+void GpuRealStorage::FillValue(const real1 &v) {
+  ++version;
+  if (v == ZERO_R1 && backend_config().fused && backend_config().lazy_zero) { // lazy: see GpuStorage::zero_pending
+    zero_pending = true;
+    return;
+  }
+  zero_pending = false;
+  dev->FillValueReal(buffer, size, v);
+}
 StoragePtr GpuRealStorage::cpu() {
+  materialize();
   CpuRealStoragePtr cp = std::make_shared<CpuRealStorage>(size);
   dev->LockSync(buffer, sizeof(real1) * (size_t)size, cp->data.data(), false);
   return cp;

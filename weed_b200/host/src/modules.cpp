@@ -80,6 +80,10 @@ void Linear::migrate_gpu() {
   if (bias) bias = mg.pforward(bias);
 }
 TensorPtr Linear::forward(const TensorPtr x) {
+  if (bias) {
+    TensorPtr fused = Tensor::linear(x, weight, bias);
+    if (fused) return fused;
+  }
   TensorPtr y = x >> weight;
   if (bias) y = y + bias;
   return y;
@@ -120,8 +124,8 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
   TensorPtr y = Tensor::allocate_like(x->shape, *x, DType::REAL, rg, false);
   TensorPtr mean = Tensor::allocate_like(std::vector<tcapint>{rows}, *x, DType::REAL, false, false);
   TensorPtr rstd = Tensor::allocate_like(std::vector<tcapint>{rows}, *x, DType::REAL, false, false);
-  throw_on_error(weedcu_layernorm_fwd(x->device_ptr() + x->offset, rows, features, gamma->device_ptr() + gamma->offset,
-                                      beta->device_ptr() + beta->offset, eps, y->device_ptr(), mean->device_ptr(), rstd->device_ptr(),
+  throw_on_error(weedcu_layernorm_fwd(x->device_ptr_ro() + x->offset, rows, features, gamma->device_ptr_ro() + gamma->offset,
+                                      beta->device_ptr_ro() + beta->offset, eps, y->device_ptr(), mean->device_ptr(), rstd->device_ptr(),
                                       x->stream()),
                  "LayerNorm::forward");
   if (rg) {
@@ -155,10 +159,12 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
       };
       dg = param_grad(g);
       db = param_grad(b);
-      throw_on_error(weedcu_layernorm_bwd(x->device_ptr() + x->offset, y->grad->device_ptr() + y->grad->offset, rows, F,
-                                          g->device_ptr() + g->offset, mean->device_ptr(), rstd->device_ptr(),
-                                          dx->device_ptr() + dx->offset, dg ? dg->device_ptr() + dg->offset : nullptr,
-                                          db ? db->device_ptr() + db->offset : nullptr, 0 /* reference chain */, x->stream()),
+      int accumulate = 1;
+      real1 *dx_ptr = dx->device_ptr_accumulate(accumulate);
+      throw_on_error(weedcu_layernorm_bwd(x->device_ptr_ro() + x->offset, y->grad->device_ptr_ro() + y->grad->offset, rows, F,
+                                          g->device_ptr_ro() + g->offset, mean->device_ptr_ro(), rstd->device_ptr_ro(), dx_ptr + dx->offset,
+                                          dg ? dg->device_ptr() + dg->offset : nullptr, db ? db->device_ptr() + db->offset : nullptr,
+                                          0 /* reference chain */, accumulate, x->stream()),
                      "LayerNorm backward");
       if (x->requires_grad) x->grad = dx;
       if (dg) g->grad = dg;
@@ -282,6 +288,15 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
     // becomes a contiguous [T, hd] matrix, scores/probabilities are [T, T] per pair, the scale +
     // causal mask + softmax chain (multihead_attention.cpp:319-334) is one fused kernel.
     const tcapint Bu = (tcapint)B, Tu = (tcapint)T, H = (tcapint)num_heads, hd = (tcapint)head_dim, BH = Bu * H;
+    if (cfg.matmul_precision == WEEDCU_GEMM_BF16) {
+      // one entry point: head relayout fused with the bf16 operand conversion, probabilities
+      // emitted as bf16 straight into the P V product (include/weedcu.h: weedcu_attention_fwd)
+      out = Tensor::allocate_like(std::vector<tcapint>{Bu, Tu, H * hd}, *x, DType::REAL, false, false);
+      const int rc = weedcu_attention_fwd(Q->device_ptr_ro() + Q->offset, K->device_ptr_ro() + K->offset, V->device_ptr_ro() + V->offset,
+                                          out->device_ptr(), Bu, Tu, H, hd, std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0, x->stream());
+      if (rc == 0) return W_o->forward(out);
+      if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "attention");
+    }
     auto to_heads = [&](const TensorPtr &lin) { // [B,T,(h,j)] -> [T, hd, B, H] contiguous
       TensorPtr dst = Tensor::allocate_like(std::vector<tcapint>{Tu, hd, Bu, H}, *lin, DType::REAL, false, false);
       TensorPtr src = strided_view(lin, {Tu, hd, Bu, H}, {Bu, Bu * Tu * H, 1U, Bu * Tu}, lin->offset);

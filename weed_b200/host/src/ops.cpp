@@ -28,10 +28,29 @@ inline GpuRealStorage *gpu_storage(const BaseTensor &t, const char *op) {
                                               "(move the tensor with cast(DeviceTag::GPU))");
   return static_cast<GpuRealStorage *>(t.storage.get());
 }
+// operand that is only read (keeps the storage version, so bf16 shadows stay valid)
 inline Dev dev_of(const BaseTensor &t, const char *op) {
   GpuRealStorage *s = gpu_storage(t, op);
   s->dev->Bind();
-  return Dev{s->device_ptr(), s->dev->stream};
+  return Dev{const_cast<real1 *>(s->device_ptr_ro()), s->dev->stream};
+}
+// does the view address every element of its storage exactly once?
+inline bool covers_storage(const BaseTensor &t) {
+  if (t.offset) return false;
+  tcapint expect = 1U;
+  for (size_t i = 0U; i < t.shape.size(); ++i) {
+    if (t.shape[i] == 1U) continue;
+    if (t.stride[i] != expect) return false;
+    expect *= t.shape[i];
+  }
+  return expect == t.storage->size;
+}
+// operand that is written; `overwrites_all`: the kernel stores every element of the view without
+// reading it, so a pending lazy zero-fill of a fully covered storage can be dropped
+inline Dev dev_out(const BaseTensor &t, const char *op, bool overwrites_all = false) {
+  GpuRealStorage *s = gpu_storage(t, op);
+  s->dev->Bind();
+  return Dev{(overwrites_all && covers_storage(t)) ? s->device_ptr_overwrite() : s->device_ptr(), s->dev->stream};
 }
 inline void require_real(const Tensor &t, const char *msg) {
   if (t.storage->dtype != DType::REAL) throw std::invalid_argument(msg);
@@ -119,7 +138,7 @@ void binary(int op, const Tensor &a, const Tensor &b, Tensor &out, const char *n
   const tcapint aSize = a.get_broadcast_size(), bSize = b.get_broadcast_size(), oSize = out.get_broadcast_size();
   if (aSize != bSize) throw std::invalid_argument(std::string("In ") + name + "(a, b, out), 'a' size does not match 'b' size!");
   if (aSize != oSize) throw std::invalid_argument(std::string("In ") + name + "(a, b, out), out size does not match input size!");
-  const Dev da = dev_of(a, name), db = dev_of(b, name), dout = dev_of(out, name);
+  const Dev da = dev_of(a, name), db = dev_of(b, name), dout = dev_out(out, name, true);
   weedcu_view av = a.view(), bv = b.view(), ov = out.view();
   conform_views({&ov, &av, &bv}, name);
   throw_on_error(weedcu_binary_real(op, da.ptr, &av, db.ptr, &bv, dout.ptr, &ov, dout.stream), name);
@@ -129,7 +148,6 @@ void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
   validate_all_same_device({&a, &b}, name);
   if (a.get_broadcast_size() != b.get_broadcast_size())
     throw std::invalid_argument(std::string("In ") + name + "(a, b), 'a' size does not match 'b' size!");
-  const Dev da = dev_of(a, name), db = dev_of(b, name);
   weedcu_view av = a.view(), bv = b.view();
   // Destination with broadcast (stride-0) dims: the reference's serial loop visits every flat index,
   // so each stored element is updated once per broadcast index (this is how sgd_step ends up
@@ -179,6 +197,15 @@ void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
   for (int d = 0; d < av.rank; ++d)
     if (av.shape[d] > 1U && av.stride[d] == 0U)
       throw std::domain_error(std::string(name) + ": accumulating into a broadcast destination is not supported for these shapes");
+  const Dev db = dev_of(b, name);
+  GpuRealStorage *as = gpu_storage(a, name);
+  if (op == WEEDCU_ADD && times == 1 && as->zero_pending && covers_storage(a)) {
+    // first accumulation into a lazily zeroed gradient: 0 + b is a plain copy (8 B/elem, no fill)
+    const Dev da = dev_out(a, name, true);
+    throw_on_error(weedcu_copy_real(da.ptr, &av, db.ptr, &bv, da.stream), name);
+    return;
+  }
+  const Dev da = dev_out(a, name);
   for (uint64_t t = 0; t < times; ++t)
     throw_on_error(weedcu_inplace_real(op, da.ptr, &av, db.ptr, &bv, da.stream), name);
 }
@@ -187,7 +214,7 @@ void unary(int op, real1 param, const Tensor &a, Tensor &out, const char *name) 
   validate_all_same_device({&a, &out}, name);
   if (a.get_broadcast_size() != out.get_broadcast_size())
     throw std::invalid_argument(std::string("In Weed::") + name + "(a, out), out size does not match input size!");
-  const Dev da = dev_of(a, name), dout = dev_of(out, name);
+  const Dev da = dev_of(a, name), dout = dev_out(out, name, true);
   weedcu_view av = a.view(), ov = out.view();
   conform_views({&ov, &av}, name);
   throw_on_error(weedcu_unary_real(op, param, da.ptr, &av, dout.ptr, &ov, dout.stream), name);
@@ -198,10 +225,12 @@ void unary_grad(int op, Tensor &din, const Tensor &in, const Tensor &dout, const
   const tcapint n = din.get_broadcast_size();
   if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size()))
     throw std::invalid_argument(std::string("In Weed::") + name + "(din, in, dout), sizes do not match!");
-  const Dev dd = dev_of(din, name), di = dev_of(in, name), dg = dev_of(dout, name);
+  // a lazily zeroed, fully covered din is stored to, not accumulated into (no fill, no read)
+  const int accumulate = (gpu_storage(din, name)->zero_pending && covers_storage(din)) ? 0 : 1;
+  const Dev dd = dev_out(din, name, !accumulate), di = dev_of(in, name), dg = dev_of(dout, name);
   weedcu_view dv = din.view(), iv = in.view(), gv = dout.view();
   conform_views({&dv, &iv, &gv}, name);
-  throw_on_error(weedcu_unary_grad_real(op, dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, dd.stream), name);
+  throw_on_error(weedcu_unary_grad_real(op, dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, accumulate, dd.stream), name);
 }
 
 
@@ -214,7 +243,49 @@ weedcu_mat mat_of(const Tensor &t, tcapint extra_offset = 0U, uint64_t batch_str
   return m;
 }
 
-void matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate) {
+// bf16 copy of a matrix view for the tensor-core GEMM, cached on the storage it was packed from.
+// The packed layout only depends on the memory the view addresses — [n_slow][round8(n_fast)] with
+// the smaller-stride index contiguous — so a view and its transpose share one shadow: X serves the
+// forward product and dW = X^T dY, W serves the forward product and dX = dY W^T, dY serves both
+// backward products. A shadow is stale once its storage's version moved (any potential write).
+struct Bf16Operand {
+  const uint16_t *ptr;
+  int major; // 1: the M (resp. N) index is contiguous, 0: the K index is
+  uint64_t ld;
+};
+inline uint64_t round8(uint64_t x) { return (x + 7U) & ~(uint64_t)7U; }
+bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcapint n_k, bool is_a, Bf16Operand &op) {
+  if (!s_mn || !s_k) return false; // broadcast operands take the generic path
+  GpuRealStorage *s = gpu_storage(t, "matmul");
+  const bool mn_fast = is_a ? (s_mn <= s_k) : (s_mn < s_k);
+  const tcapint n_fast = mn_fast ? n_mn : n_k, n_slow = mn_fast ? n_k : n_mn;
+  const tcapint s_fast = mn_fast ? s_mn : s_k, s_slow = mn_fast ? s_k : s_mn;
+  op.major = mn_fast ? 1 : 0;
+  op.ld = round8(n_fast);
+  const real1 *src = s->device_ptr_ro(); // (materialises a pending zero fill; keeps the version)
+  GpuRealStorage::Bf16Shadow *hit = nullptr;
+  for (GpuRealStorage::Bf16Shadow &sh : s->shadows)
+    if (sh.offset == t.offset && sh.n_fast == n_fast && sh.n_slow == n_slow && sh.s_fast == s_fast && sh.s_slow == s_slow) hit = &sh;
+  if (hit && hit->version == s->version) {
+    op.ptr = (const uint16_t *)hit->buf->ptr;
+    return true;
+  }
+  if (!hit) {
+    if (s->shadows.size() >= 4U) s->shadows.erase(s->shadows.begin());
+    s->shadows.push_back(GpuRealStorage::Bf16Shadow{s->dev->MakeBuffer(2U * (size_t)(op.ld * n_slow + 8U)), 0U, t.offset, n_fast, n_slow, s_fast, s_slow});
+    hit = &s->shadows.back();
+  }
+  s->dev->Bind();
+  // weedcu_pack_bf16(rows = mn index, cols = k index): dst_major 1 keeps rows contiguous
+  throw_on_error(weedcu_pack_bf16(src, t.offset, s_mn, s_k, n_mn, n_k, (uint16_t *)hit->buf->ptr, op.major, s->dev->stream), "pack_bf16");
+  hit->version = s->version;
+  op.ptr = (const uint16_t *)hit->buf->ptr;
+  return true;
+}
+
+// `bias` (optional): a dense [N] vector added to every row in the GEMM epilogue; when given and the
+// tensor-core path does not apply, nothing is computed and false is returned.
+bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, const Tensor *bias = nullptr) {
   validate_all_same_device({&a, &b, &out}, "MatMulKernel::matmul");
   if ((a.shape.size() != 2U) || (b.shape.size() != 2U) || (out.shape.size() != 2U))
     throw std::invalid_argument("MatMul is only for matrices with 2 indices!");
@@ -222,11 +293,31 @@ void matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate) 
   if (K != b.shape[0U]) throw std::invalid_argument("MatMul operand dimensions aren't compatible!");
   const tcapint M = a.shape[0U], N = b.shape[1U];
   if ((M != out.shape[0U]) || (N != out.shape[1U])) throw std::invalid_argument("MatMul output dimensions don't match inputs!");
-  const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dc = dev_of(out, "matmul");
+  GpuRealStorage *cs = gpu_storage(out, "matmul");
+  if (accumulate && cs->zero_pending && covers_storage(out)) accumulate = 0; // 0 + A*B: plain store, no fill
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision == WEEDCU_GEMM_BF16 && cfg.fused && cfg.operand_cache && out.stride[0U] == 1U && M >= 64U && N >= 16U && K >= 32U) {
+    // bf16 operands come from per-storage shadows: a weight is packed once per optimiser step and an
+    // activation / output gradient once per graph, not once per GEMM that reads it
+    Bf16Operand pa, pb;
+    if (bf16_operand(a, a.stride[0U], a.stride[1U], M, K, true, pa) && bf16_operand(b, b.stride[1U], b.stride[0U], N, K, false, pb)) {
+      const Dev dc = dev_out(out, "matmul", !accumulate);
+      const real1 *bias_ptr = bias ? dev_of(*bias, "matmul").ptr + bias->offset : nullptr;
+      const int rc = weedcu_gemm_bf16(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K,
+                                      accumulate, bias_ptr, dc.stream);
+      if (rc != WEEDCU_ENOSUP) {
+        throw_on_error(rc, "matmul");
+        return true;
+      }
+    }
+  }
+  if (bias) return false;
+  const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dc = dev_out(out, "matmul", !accumulate);
   const weedcu_mat am = mat_of(a), bm = mat_of(b), cm = mat_of(out);
   throw_on_error(weedcu_matmul_real(da.ptr, &am, db.ptr, &bm, dc.ptr, &cm, M, K, N, 1U, accumulate,
                                     backend_config().matmul_precision, dc.stream),
                  "matmul");
+  return true;
 }
 } // namespace
 
@@ -241,7 +332,7 @@ void copy_broadcast(Tensor &a, const Tensor &b) {
   validate_all_same_device({&a, &b}, "CopyKernel::copy_broadcast");
   if (a.get_size() != b.get_broadcast_size())
     throw std::invalid_argument("In CopyKernel::copy_broadcast(a, b), 'a' size does not match 'b' size!");
-  const Dev da = dev_of(a, "copy_broadcast"), db = dev_of(b, "copy_broadcast");
+  const Dev da = dev_out(a, "copy_broadcast", true), db = dev_of(b, "copy_broadcast");
   const weedcu_view av = a.view(), bv = b.view();
   throw_on_error(weedcu_copy_real(da.ptr, &av, db.ptr, &bv, da.stream), "copy_broadcast");
 }
@@ -271,7 +362,7 @@ static void full_reduce(const Tensor &a, Tensor &out, bool is_mean) {
   validate_all_same_device({&a, &out}, "SumKernel::sum");
   if (out.get_broadcast_size() != 1U)
     throw std::invalid_argument("In Weed::sum(a, out) or Weed::mean(a, out), out parameter is not a scalar!");
-  const Dev da = dev_of(a, "sum"), dout = dev_of(out, "sum");
+  const Dev da = dev_of(a, "sum"), dout = dev_out(out, "sum");
   const weedcu_view av = a.view();
   const real1 scale = is_mean ? (ONE_R1 / (real1)a.get_broadcast_size()) : ONE_R1;
   throw_on_error(weedcu_sum_real(da.ptr, &av, scale, dout.ptr + out.offset, dout.stream), "sum");
@@ -283,7 +374,7 @@ void reduce(const tcapint &index, const Tensor &a, Tensor &out) {
   validate_all_same_device({&a, &out}, "ReduceKernel::reduce");
   if (a.storage->dtype != out.storage->dtype) throw std::invalid_argument("Output tensor dtype mismatch in reduce!");
   if (index >= a.shape.size()) throw std::invalid_argument("reduce: axis out of range");
-  const Dev da = dev_of(a, "reduce"), dout = dev_of(out, "reduce");
+  const Dev da = dev_of(a, "reduce"), dout = dev_out(out, "reduce");
   const weedcu_view av = a.view();
   // the output is written as a dense buffer starting at out.offset, which is how the tensor built
   // by Tensor::sum(axis) (contiguous, axis extent 1) is read
@@ -296,7 +387,7 @@ void reduce_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tens
   const tcapint n = din.get_broadcast_size();
   if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size()))
     throw std::invalid_argument("In Weed::reduce_grad(din, in, dout), sizes do not match!");
-  const Dev dd = dev_of(din, "reduce_grad"), dg = dev_of(dout, "reduce_grad");
+  const Dev dd = dev_out(din, "reduce_grad"), dg = dev_of(dout, "reduce_grad");
   const weedcu_view dv = din.view(), gv = dout.view();
   throw_on_error(weedcu_reduce_grad_real(dd.ptr, &dv, dg.ptr, &gv, (int)index, backend_config().ref_index_quirks ? 1 : 0, dd.stream),
                  "reduce_grad");
@@ -305,13 +396,13 @@ void reduce_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tens
 static void softmax_fwd(int log_mode, const tcapint &index, const Tensor &a, Tensor &out, const char *name) {
   validate_all_same_device({&a, &out}, name);
   require_real(a, "Tensor dtype mismatch in softmax_forward!");
-  const Dev da = dev_of(a, name), dout = dev_of(out, name);
+  const Dev da = dev_of(a, name), dout = dev_out(out, name, true);
   const weedcu_view av = a.view(), ov = out.view();
   throw_on_error(weedcu_softmax_real(log_mode, da.ptr, &av, (int)index, dout.ptr, &ov, dout.stream), name);
 }
 static void softmax_bwd(int log_mode, const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout, const char *name) {
   validate_all_same_device({&din, &out, &dout}, name);
-  const Dev dd = dev_of(din, name), dy = dev_of(out, name), dg = dev_of(dout, name);
+  const Dev dd = dev_out(din, name), dy = dev_of(out, name), dg = dev_of(dout, name);
   const weedcu_view dv = din.view(), yv = out.view(), gv = dout.view();
   throw_on_error(weedcu_softmax_grad_real(log_mode, dd.ptr, &dv, dy.ptr, &yv, dg.ptr, &gv, (int)index, dd.stream), name);
 }
@@ -326,6 +417,7 @@ void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const
 
 void matmul(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 0); }
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 1); }
+bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out) { return matmul_impl(a, b, out, 0, &bias); }
 
 void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {
   validate_all_same_device({&a3, &b3, &out3}, "MatMulKernel::matmul_batched");
@@ -335,7 +427,7 @@ void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {
   if ((b3.shape[0U] != batch) || (out3.shape[0U] != batch)) throw std::invalid_argument("batched matmul batch mismatch");
   if (b3.shape[1U] != K) throw std::invalid_argument("batched matmul inner dim mismatch");
   if ((out3.shape[1U] != M) || (out3.shape[2U] != N)) throw std::invalid_argument("MatMul output dimensions don't match inputs!");
-  const Dev da = dev_of(a3, "matmul_batched"), db = dev_of(b3, "matmul_batched"), dc = dev_of(out3, "matmul_batched");
+  const Dev da = dev_of(a3, "matmul_batched"), db = dev_of(b3, "matmul_batched"), dc = dev_out(out3, "matmul_batched");
   const weedcu_mat am = mat_of(a3, 0U, a3.stride[0U]), bm = mat_of(b3, 0U, b3.stride[0U]), cm = mat_of(out3, 0U, out3.stride[0U]);
   throw_on_error(weedcu_matmul_real(da.ptr, &am, db.ptr, &bm, dc.ptr, &cm, M, K, N, batch, 0,
                                     backend_config().matmul_precision, dc.stream),
@@ -368,7 +460,7 @@ static const symint *sym_ptr(const SymbolTensor &s, const char *op) {
 }
 void embedding_gather(const SymbolTensor &indices, const Tensor &weight, Tensor &out) {
   validate_all_same_device({&indices, &weight, &out}, "embedding_gather");
-  const Dev dw = dev_of(weight, "embedding_gather"), dout = dev_of(out, "embedding_gather");
+  const Dev dw = dev_of(weight, "embedding_gather"), dout = dev_out(out, "embedding_gather");
   const tcapint D = weight.shape[1U], n = indices.get_broadcast_size();
   throw_on_error(weedcu_embedding_gather(sym_ptr(indices, "embedding_gather"), indices.offset, flat_stride(indices), n, dw.ptr,
                                          weight.offset, weight.stride[0U], weight.stride[1U], D, dout.ptr, out.offset,
@@ -377,7 +469,7 @@ void embedding_gather(const SymbolTensor &indices, const Tensor &weight, Tensor 
 }
 void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor &dout) {
   validate_all_same_device({&dW, &indices, &dout}, "embedding_scatter_add");
-  const Dev dw = dev_of(dW, "embedding_scatter_add"), dg = dev_of(dout, "embedding_scatter_add");
+  const Dev dw = dev_out(dW, "embedding_scatter_add"), dg = dev_of(dout, "embedding_scatter_add");
   const tcapint D = dW.shape[1U], n = indices.get_broadcast_size();
   throw_on_error(weedcu_embedding_scatter_add(dw.ptr, dW.offset, dW.stride[0U], dW.stride[1U], sym_ptr(indices, "embedding_scatter_add"),
                                               indices.offset, flat_stride(indices), n, D, dg.ptr, dout.offset, row_stride_of_rows(dout),
@@ -386,7 +478,7 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
 }
 void triu_fill(Tensor &a, const complex &val, const tcapint diagonal) {
   if (a.shape.size() != 2U) throw std::invalid_argument("triu_fill requires a 2D tensor!");
-  const Dev da = dev_of(a, "triu_fill");
+  const Dev da = dev_out(a, "triu_fill");
   const weedcu_view av = a.view();
   throw_on_error(weedcu_triu_fill_real(da.ptr, &av, val.real(), diagonal, da.stream), "triu_fill");
 }

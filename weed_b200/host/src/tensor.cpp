@@ -81,6 +81,30 @@ real1 *Tensor::device_ptr() const {
   if (!storage || storage->device != DeviceTag::GPU) throw std::domain_error("Tensor is not GPU-resident");
   return static_cast<GpuRealStorage *>(storage.get())->device_ptr();
 }
+const real1 *Tensor::device_ptr_ro() const {
+  if (!storage || storage->device != DeviceTag::GPU) throw std::domain_error("Tensor is not GPU-resident");
+  return static_cast<GpuRealStorage *>(storage.get())->device_ptr_ro();
+}
+real1 *Tensor::device_ptr_accumulate(int &accumulate) const {
+  if (!storage || storage->device != DeviceTag::GPU) throw std::domain_error("Tensor is not GPU-resident");
+  GpuRealStorage *s = static_cast<GpuRealStorage *>(storage.get());
+  if (s->zero_pending && covers_storage()) {
+    accumulate = 0;
+    return s->device_ptr_overwrite();
+  }
+  accumulate = 1;
+  return s->device_ptr();
+}
+bool BaseTensor::covers_storage() const {
+  if (offset || !storage) return false;
+  tcapint expect = 1U;
+  for (size_t i = 0U; i < shape.size(); ++i) {
+    if (shape[i] == 1U) continue;
+    if (stride[i] != expect) return false;
+    expect *= shape[i];
+  }
+  return expect == storage->size;
+}
 void *Tensor::stream() const {
   if (!storage || storage->device != DeviceTag::GPU) throw std::domain_error("Tensor is not GPU-resident");
   return static_cast<GpuRealStorage *>(storage.get())->dev->stream;
@@ -868,11 +892,57 @@ TensorPtr Tensor::matmul(TensorPtr a, TensorPtr b) { // tensor.cpp:1204-1326
   return out;
 }
 
+// Fused Linear::forward (src/modules/linear.cpp): x W + bias as ONE tensor-core GEMM with the bias
+// added in the epilogue, one autograd node instead of matmul + add. Returns nullptr when the fused
+// kernel does not apply (the caller then composes the two ops like the reference).
+TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
+  const BackendConfig &cfg = backend_config();
+  if (!cfg.fused || cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache) return nullptr;
+  if (a->shape.size() < 2U || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back()) return nullptr;
+  if (bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U] || bias->storage->device != DeviceTag::GPU) return nullptr;
+  const bool rg = a->requires_grad || w->requires_grad || bias->requires_grad;
+  const bool needs_flatten = (a->shape.size() > 2U);
+  const symint K = (symint)a->shape.back(), M = (symint)a->shape[a->shape.size() - 2], N = (symint)w->shape[1U];
+  symint batch = 1;
+  for (size_t i = 0; i < a->shape.size() - 2; ++i) batch *= (symint)a->shape[i];
+  TensorPtr a2 = a;
+  if (needs_flatten) a2 = reshape(a, {batch * M, K});
+  const tcapint as0 = a2->shape[0U];
+  TensorPtr out = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
+  if (!Weed::matmul_bias(*a2, *w, *bias, *out)) return nullptr;
+  if (needs_flatten) {
+    std::vector<symint> final_shape;
+    for (size_t i = 0; i < a->shape.size() - 2; ++i) final_shape.push_back((symint)a->shape[i]);
+    final_shape.push_back(M);
+    final_shape.push_back(N);
+    out = reshape(out, final_shape);
+  }
+  prepare_binary(out, bias, "add"); // the same match_shape mutation of the Parameter that `y + bias` performs
+  if (rg) {
+    out->make_gradient();
+    out->grad_node = std::make_shared<Node>(grad_parents({a, w, bias}), [a, w, bias, wout = std::weak_ptr<Tensor>(out)]() {
+      TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+      if (!out) return;
+      matmul_backward(a, w, out);
+      if (bias->requires_grad) {
+        TensorPtr out_grad = view_copy(out->grad);
+        accumulate(bias, out_grad, *out_grad, false);
+      }
+    });
+  }
+  return out;
+}
+
 void Tensor::make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.cpp:1328-1402
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
     if (!out) return;
+    matmul_backward(a, b, out);
+  });
+}
+void Tensor::matmul_backward(TensorPtr a, TensorPtr b, TensorPtr out) {
+  {
     TensorPtr out_grad = view_copy(out->grad);
     const bool needs_flatten = (a->shape.size() > 2U);
     const symint K = (symint)a->shape.back();
@@ -933,6 +1003,6 @@ void Tensor::make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tens
       }
       b->grad = b_grad;
     }
-  });
+  }
 }
 } // namespace Weed
