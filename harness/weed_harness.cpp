@@ -485,17 +485,33 @@ int wh_dp_broadcast_params(int64_t model) {
 // Adam instead of SGD. Returns the loss tensor handle (read it with wh_read; reading syncs).
 int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t targets) {
   WH_TRY({
+    // WH_TIMING=1 prints the host time of each phase (diagnostic for launch-bound steps)
+    static const bool timing = getenv("WH_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
     ModulePtr m = M(model);
     TensorPtr logits = m->forward(g_symbols.at(tokens));
+    const auto t1 = now();
     TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
+    const auto t2 = now();
     Tensor::backward(loss);
+    const auto t3 = now();
     const std::vector<ParameterPtr> params = m->parameters();
 #ifdef WEED_B200
     if (g_comm && g_world > 1) allreduce_gradients(params, g_comm);
 #endif
+    const auto t4 = now();
     adam_step(*g_adams.at(opt), params);
+    const auto t5 = now();
     zero_grad(params);
     m->reset_cache();
+    const auto t6 = now();
+    if (timing)
+      fprintf(stderr, "[wh] forward %.0f us, loss %.0f, backward %.0f, allreduce %.0f, adam %.0f, zero_grad %.0f\n", us(t0, t1), us(t1, t2),
+              us(t2, t3), us(t3, t4), us(t4, t5), us(t5, t6));
     return put(loss);
   })
 }

@@ -232,7 +232,8 @@ int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, f
                      void *stream);
 /* The same update for `count` parameters in ONE launch (adam_step walks a parameter list,
  * adam.hpp:70-106; a 12-layer transformer has ~150 of them, most of them tiny). Host arrays of
- * device pointers and sizes; they are copied before the call returns. */
+ * device pointers and sizes; they are copied before the call returns. g[i] == NULL stands for an
+ * all-zero gradient (a parameter nothing back-propagated into: no fill, no read). */
 int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m,
                            float *const *v, const uint64_t *n, float lr, float beta1, float beta2,
                            float eps, float bc1, float bc2, float gscale, void *stream);
@@ -293,6 +294,10 @@ int weedcu_nccl_load(const char *libnccl_path);
 int weedcu_nccl_unique_id(void *id128);      /* writes 128 bytes */
 int weedcu_nccl_init(const void *id128, int rank, int world, void **comm);
 int weedcu_nccl_destroy(void *comm);
+/* ncclGroupStart / ncclGroupEnd: the per-parameter all-reduces of one step are issued as one group
+ * (NCCL fuses them into few kernels instead of one launch per parameter). */
+int weedcu_nccl_group_start(void);
+int weedcu_nccl_group_end(void);
 int weedcu_nccl_allreduce_sum(void *comm, float *buf, uint64_t n, void *stream);
 int weedcu_nccl_broadcast(void *comm, float *buf, uint64_t n, int root, void *stream);
 

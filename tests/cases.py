@@ -534,4 +534,9 @@ BF16_CASES = [
     (384, 96, 128, "col", "col", 3, 0),
     (128, 64, 128, "batchfast", "batchfast", 4, 0),
     (1024, 512, 768, "col", "col", 1, 0),
+    # few output tiles, long K: split-K slices meeting in C by TMA reduce-add (weight-gradient shapes)
+    (256, 2048, 256, "row", "col", 1, 0),
+    (256, 2048, 256, "row", "col", 1, 1),
+    (130, 1100, 200, "col", "col", 1, 0),
+    (384, 1536, 128, "col", "row", 2, 1),
 ]

@@ -25,9 +25,15 @@ static const bool g_trace = getenv("WEEDCU_MOCK_TRACE") != nullptr; // print one
 static inline void trace_call(const char *what) {
   if (!g_trace) return;
   const char *p = strchr(what, '(');
-  fprintf(stderr, "[mock] %.*s\n", p ? (int)(p - what) : (int)strlen(what), what);
+  static auto last = std::chrono::steady_clock::now();
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[mock] %.*s +%.1fus\n", p ? (int)(p - what) : (int)strlen(what), what,
+          std::chrono::duration<double, std::micro>(now - last).count()); // host time since the previous kernel call
+  last = now;
 }
-#define RUN(expr) (++g_launches, trace_call(#expr), ((expr) == 0 ? 0 : WEEDCU_EINVAL))
+// WEEDCU_MOCK_NOCOMPUTE: skip the oracle call (results are garbage) — isolates the HOST cost of a step
+static const bool g_nocompute = getenv("WEEDCU_MOCK_NOCOMPUTE") != nullptr;
+#define RUN(expr) (++g_launches, trace_call(#expr), g_nocompute ? 0 : ((expr) == 0 ? 0 : WEEDCU_EINVAL))
 
 extern "C" {
 int weedcu_device_count(int *count) { if (!count) return WEEDCU_EINVAL; *count = 1; return 0; }
@@ -134,8 +140,11 @@ int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, f
 int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, float lr, float beta1, float beta2, float eps,
                            float bc1, float bc2, float gscale, void *) {
   ++g_launches;
-  for (uint32_t t = 0; t < count; ++t)
-    if (wo_adam_step(p[t], g[t], m[t], v[t], n[t], lr, beta1, beta2, eps, bc1, bc2, gscale) != 0) return WEEDCU_EINVAL;
+  for (uint32_t t = 0; t < count; ++t) {
+    std::vector<float> zeros;
+    if (!g[t]) zeros.assign(n[t], 0.0f); // NULL gradient = all zeros
+    if (wo_adam_step(p[t], g[t] ? g[t] : zeros.data(), m[t], v[t], n[t], lr, beta1, beta2, eps, bc1, bc2, gscale) != 0) return WEEDCU_EINVAL;
+  }
   return 0;
 }
 int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
@@ -153,6 +162,8 @@ static inline float bf16_widen(uint16_t h) {
 }
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols, uint16_t *dst, int dst_major, void *) {
   if (!src || !dst || !rows || !cols) return WEEDCU_EINVAL;
+  trace_call("pack_bf16(");
+  if (g_nocompute) return 0;
   const uint64_t ld = ((uint64_t)(dst_major ? rows : cols) + 7U) & ~(uint64_t)7U;
   for (uint32_t r = 0; r < rows; ++r)
     for (uint32_t c = 0; c < cols; ++c)
@@ -162,6 +173,9 @@ int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1
 int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
                      int accumulate, const float *col_bias, void *) {
   if (!a || !b || !c || !M || !N || !K) return WEEDCU_EINVAL;
+  trace_call("gemm_bf16(");
+  ++g_launches;
+  if (g_nocompute) return 0;
   for (uint32_t m = 0; m < M; ++m)
     for (uint32_t n = 0; n < N; ++n) {
       double sum = 0.0; // same accumulation as wo_matmul_bf16_model
@@ -171,7 +185,6 @@ int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_
       *o = accumulate ? (float)(*o + sum) : (float)sum;
       if (col_bias) *o = *o + col_bias[n];
     }
-  g_launches++;
   return 0;
 }
 int weedcu_gemm_workspace_bytes(uint32_t, uint32_t, uint32_t, uint32_t, int, uint64_t *bytes) { if (bytes) *bytes = 0; return 0; }
@@ -180,6 +193,8 @@ int weedcu_nccl_load(const char *) { return 0; }
 int weedcu_nccl_unique_id(void *id128) { if (id128) memset(id128, 0, 128); return 0; }
 int weedcu_nccl_init(const void *, int, int, void **comm) { if (comm) *comm = (void *)0x2; return 0; }
 int weedcu_nccl_destroy(void *) { return 0; }
+int weedcu_nccl_group_start(void) { return 0; }
+int weedcu_nccl_group_end(void) { return 0; }
 typedef int (*mock_allreduce_hook)(float *buf, uint64_t n);
 static mock_allreduce_hook g_allreduce_hook = nullptr, g_bcast_hook = nullptr;
 void weedcu_mock_set_collective_hooks(mock_allreduce_hook allreduce, mock_allreduce_hook bcast) { g_allreduce_hook = allreduce; g_bcast_hook = bcast; }

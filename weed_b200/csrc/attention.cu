@@ -7,7 +7,8 @@
 // Here, for q, k, v = [B, T, H*hd] column-major (b fastest):
 //   1. heads_pack   fp32 [B,T,C] -> bf16 [B*H][hd][T]   one kernel for q, k and v: the head
 //                    relayout and the fp32->bf16 operand conversion are the same pass (6 B/elem)
-//   2. tcgen05 GEMM  S[bh] = Qh Kh^T                      fp32 [T(k)][T(q)], q contiguous
+//   2. tcgen05 GEMM  S^T[bh] = Kh Qh^T                    fp32 [T(q)][T(k)], k contiguous: softmax rows
+//                                                         are contiguous runs
 //   3. softmax       scale + causal mask + softmax        reads fp32 S (only the unmasked part),
 //                    writes the probabilities as bf16 — the A operand of the next product — so P
 //                    is never stored in fp32 nor re-packed (4+2 B/elem instead of 4+4+4+2)
@@ -70,63 +71,66 @@ unheads_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32_t B
 }
 
 // ------------------------------------------------------------------------------- softmax -> bf16
-// S, P: [BH][T(k)][T(q)], q contiguous. Block = 16 queries x 32 key lanes; a thread keeps its NV
-// keys of one query in registers (all loads in flight at once). Arithmetic as the reference chain:
-// x / divisor, + mask where q + 1 <= k (triu_fill.cpp:48-56), max, exp, sum, divide.
-// With a -2^127-like mask the masked probabilities are exactly 0: key columns beyond the last
-// query of the tile are not read, only zero-filled.
-constexpr int kSmRT = 16, kSmBY = 32;
-template <int NV>
-__global__ void __launch_bounds__(kSmRT *kSmBY)
-attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict__ P, uint32_t T, float divisor,
-                         float mask_val, int causal) {
-  __shared__ float red[kSmBY][kSmRT + 1];
-  const uint32_t tx = threadIdx.x % kSmRT, ty = threadIdx.x / kSmRT;
-  const uint32_t q0 = blockIdx.x * kSmRT, q = q0 + tx;
-  const bool live = q < T;
-  const uint64_t slab = (uint64_t)blockIdx.y * T * T;
-  const float *p = S + slab + q;
-  __nv_bfloat16 *po = P + slab + q;
-  const uint32_t Lc = (causal && mask_val <= -1e30f) ? min(T, q0 + kSmRT) : T;
+// The score product is issued as S^T = Kh Qh^T, so S and P are [BH][T(q)][T(k)] with the KEY index
+// contiguous: a softmax row is one contiguous run (in a column-major tensor it would be strided,
+// SURVEY §7 hard part 7). One warp per query row, the row lives in registers (NV4 float4 per lane),
+// all reductions are warp shuffles. Arithmetic as the reference chain: x / divisor, + mask where
+// q + 1 <= k (triu_fill.cpp:48-56), max, exp, sum, divide. With a -2^127-like mask the masked
+// probabilities are exactly 0, so keys beyond the query are not read, only zero-filled.
+template <int NV4>
+__global__ void __launch_bounds__(256)
+attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict__ P, uint32_t T, uint32_t rows,
+                         float divisor, float mask_val, int causal) {
+  const uint32_t lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint32_t q = row % T;
+  const float *p = S + (uint64_t)row * T;
+  __nv_bfloat16 *po = P + (uint64_t)row * T;
+  const uint32_t Lc = (causal && mask_val <= -1e30f) ? min(T, q + 1u) : T; // keys that can be non-zero
 
-  float v[NV];
+  float4 v[NV4];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t k = ty + i * kSmBY;
-    v[i] = (live && k < Lc) ? p[(uint64_t)k * T] : 0.0f;
+  for (int i = 0; i < NV4; ++i) {
+    const uint32_t k = (i * 32 + lane) * 4;
+    v[i] = (k < Lc) ? *reinterpret_cast<const float4 *>(p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t k = ty + i * kSmBY;
-    float x = v[i] / divisor;
-    if (causal) x = x + ((q + 1u <= k) ? mask_val : 0.0f);
-    v[i] = (live && k < Lc) ? x : -INFINITY;
-    mx = fmaxf(mx, v[i]);
-  }
-  red[ty][tx] = mx;
-  __syncthreads();
+  for (int i = 0; i < NV4; ++i) {
+    const uint32_t k = (i * 32 + lane) * 4;
+    float *e = reinterpret_cast<float *>(&v[i]);
 #pragma unroll
-  for (int y = 0; y < kSmBY; ++y) mx = fmaxf(mx, red[y][tx]);
-  __syncthreads();
+    for (int j = 0; j < 4; ++j) {
+      float x = e[j] / divisor;
+      if (causal) x = x + ((q + 1u <= k + j) ? mask_val : 0.0f);
+      e[j] = (k + j < Lc) ? x : -INFINITY;
+      mx = fmaxf(mx, e[j]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = (v[i] > -INFINITY) ? expf(v[i] - mx) : 0.0f;
-    s += v[i];
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  s = 0.0f;
+  for (int i = 0; i < NV4; ++i) {
+    float *e = reinterpret_cast<float *>(&v[i]);
 #pragma unroll
-  for (int y = 0; y < kSmBY; ++y) s += red[y][tx];
-  if (!live) return;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t k = ty + i * kSmBY;
-    if (k < Lc) po[(uint64_t)k * T] = __float2bfloat16_rn(v[i] / s);
+    for (int j = 0; j < 4; ++j) {
+      e[j] = (e[j] > -INFINITY) ? expf(e[j] - mx) : 0.0f;
+      s += e[j];
+    }
   }
-  for (uint32_t k = Lc + ty; k < T; k += kSmBY) po[(uint64_t)k * T] = __float2bfloat16_rn(0.0f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const uint32_t k = (i * 32 + lane) * 4;
+    if (k < T) {
+      __nv_bfloat162 o2[2];
+      o2[0] = __floats2bfloat162_rn(v[i].x / s, v[i].y / s);
+      o2[1] = __floats2bfloat162_rn(v[i].z / s, v[i].w / s);
+      *reinterpret_cast<uint2 *>(po + k) = *reinterpret_cast<const uint2 *>(o2);
+    }
+  }
 }
 
 } // namespace weedcu
@@ -138,7 +142,7 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
                                     int causal, void *stream) {
   if (!q || !k || !v || !out || !B || !T || !H || !hd) return WEEDCU_EINVAL;
   // tensor-map constraints of the two products (16-byte row pitch) and the register softmax
-  if ((T % 8u) || T < 64u || T > 32u * kSmBY || hd < 16u || (hd % 8u) || H * hd > 65535u) return WEEDCU_ENOSUP;
+  if ((T % 8u) || T < 64u || T > 1024u || hd < 16u || (hd % 8u) || H * hd > 65535u) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   const uint64_t BH = (uint64_t)B * H, C = (uint64_t)H * hd;
   if (BH > 65535u) return WEEDCU_ENOSUP;
@@ -168,23 +172,24 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
     heads_pack_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C, 3), 256, tile_bytes, st>>>(a, B, T, H, hd, tt);
     rc = after_launch();
   }
-  if (rc == 0) // S[bh] = Qh Kh^T : A [T, hd] and B [T, hd] both with the token index contiguous
-    rc = tc::launch_gemm_bf16(qh, 1, T, head_elems, kh, 1, T, head_elems, S, T, (uint64_t)T * T, T, T, hd, (uint32_t)BH, 0, st, nullptr);
+  if (rc == 0) // S^T[bh] = Kh Qh^T (C[k, q], k contiguous): both operands have the token index contiguous
+    rc = tc::launch_gemm_bf16(kh, 1, T, head_elems, qh, 1, T, head_elems, S, T, (uint64_t)T * T, T, T, hd, (uint32_t)BH, 0, st, nullptr);
   if (rc == 0) {
     ProfScope prof(WEEDCU_PROF_SOFTMAX, st, (causal ? 4.0 : 6.0) * (double)BH * T * T);
-    const dim3 grid((T + kSmRT - 1) / kSmRT, (unsigned)BH);
+    const uint32_t rows = (uint32_t)(BH * T);
+    const unsigned grid = (rows + 7) / 8;
     const int do_mask = (causal && T > 1) ? 1 : 0;
-    const uint32_t nv = (T + kSmBY - 1) / kSmBY;
-#define WCU_SM(NV) attn_softmax_bf16_kernel<NV><<<grid, kSmRT * kSmBY, 0, st>>>(S, (__nv_bfloat16 *)P, T, divisor, mask_val, do_mask)
-    if (nv <= 4) WCU_SM(4);
-    else if (nv <= 8) WCU_SM(8);
-    else if (nv <= 16) WCU_SM(16);
-    else WCU_SM(32);
+    const uint32_t nv4 = (T + 127) / 128;
+#define WCU_SM(NV4) attn_softmax_bf16_kernel<NV4><<<grid, 256, 0, st>>>(S, (__nv_bfloat16 *)P, T, rows, divisor, mask_val, do_mask)
+    if (nv4 <= 1) WCU_SM(1);
+    else if (nv4 <= 2) WCU_SM(2);
+    else if (nv4 <= 4) WCU_SM(4);
+    else WCU_SM(8);
 #undef WCU_SM
     rc = after_launch();
   }
-  if (rc == 0) // O[bh] = P Vh : A = P [T(q), T(k)] q contiguous; B = Vh as [hd, T(k)] with k contiguous
-    rc = tc::launch_gemm_bf16(P, 1, T, (uint64_t)T * T, vh, 0, T, head_elems, oc, T, head_elems, T, hd, T, (uint32_t)BH, 0, st, nullptr);
+  if (rc == 0) // O[bh] = P Vh : A = P [T(q), T(k)] and B = Vh as [hd, T(k)], both with k contiguous
+    rc = tc::launch_gemm_bf16(P, 0, T, (uint64_t)T * T, vh, 0, T, head_elems, oc, T, head_elems, T, hd, T, (uint32_t)BH, 0, st, nullptr);
   if (rc == 0) {
     ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 8.0 * (double)B * T * C);
     unheads_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C), 256, tile_bytes, st>>>(oc, out, B, T, H, hd, tt);

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__rest
     const uint32_t nq = c.n >> 2;
     for (uint32_t i = threadIdx.x; i < nq; i += 256) {
       float4 pv = reinterpret_cast<float4 *>(c.p)[i];
-      const float4 gv = reinterpret_cast<const float4 *>(c.g)[i];
+      const float4 gv = c.g ? reinterpret_cast<const float4 *>(c.g)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 mv = reinterpret_cast<float4 *>(c.m)[i];
       float4 vv = reinterpret_cast<float4 *>(c.v)[i];
       adam_one(pv.x, gv.x, mv.x, vv.x, a);
@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__rest
       reinterpret_cast<float4 *>(c.m)[i] = mv;
       reinterpret_cast<float4 *>(c.v)[i] = vv;
     }
-    for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g[i], c.m[i], c.v[i], a);
+    for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
   } else {
-    for (uint32_t i = threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g[i], c.m[i], c.v[i], a);
+    for (uint32_t i = threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
   }
 }
 
@@ -430,11 +430,11 @@ int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *
   std::vector<AdamChunk> table;
   double total = 0.0;
   for (uint32_t t = 0; t < count; ++t) {
-    if (!p[t] || !g[t] || !m[t] || !v[t]) return WEEDCU_EINVAL;
-    const int vec = (aligned16(p[t]) && aligned16(g[t]) && aligned16(m[t]) && aligned16(v[t])) ? 1 : 0;
+    if (!p[t] || !m[t] || !v[t]) return WEEDCU_EINVAL; // g[t] == NULL: an all-zero gradient
+    const int vec = (aligned16(p[t]) && (!g[t] || aligned16(g[t])) && aligned16(m[t]) && aligned16(v[t])) ? 1 : 0;
     for (uint64_t o = 0; o < n[t]; o += kAdamChunk) {
       const uint64_t len = (n[t] - o < kAdamChunk) ? n[t] - o : kAdamChunk;
-      table.push_back(AdamChunk{p[t] + o, g[t] + o, m[t] + o, v[t] + o, (uint32_t)len, vec});
+      table.push_back(AdamChunk{p[t] + o, g[t] ? g[t] + o : nullptr, m[t] + o, v[t] + o, (uint32_t)len, vec});
     }
     total += (double)n[t];
   }

@@ -150,6 +150,7 @@ struct Params {
   uint32_t M, N, K, batch;
   uint32_t tiles_m, tiles_n;
   int accumulate;
+  uint32_t splits, kb_per_split; // split-K: work unit = (tile, k-slice); slices meet in C by TMA reduce-add
   const float *col_bias; // optional [N]: C[m,n] = sum_k A B + col_bias[n]  (Linear::forward's bias add)
   int tma_store; // C goes out through TMA (needs 16-B aligned base / leading dimension); else direct stores
 };
@@ -194,6 +195,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const uint32_t tiles_per_batch = p.tiles_m * p.tiles_n;
   const uint32_t num_tiles = tiles_per_batch * p.batch;
+  // unit u -> tile u % num_tiles, k-slice u / num_tiles: CTAs running together work on different
+  // tiles of the same slice, so their reduce-adds do not collide
+  const uint32_t num_units = num_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -220,10 +224,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================ TMA producer =====================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
         const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
         const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
           const int k0 = (int)(kb * BLOCK_K);
@@ -251,12 +257,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t ks = unit / num_tiles;
+        const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1); // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase); // TMA bytes have landed
           tcgen05_fence_after();
           const uint32_t a_s = sA + stage * L::A_BYTES, b_s = sB + stage * L::B_BYTES;
@@ -268,10 +276,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         : make_smem_desc(a_s + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc(b_s + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                         : make_smem_desc(b_s + k * (UMMA_K * 2), 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+            umma_f16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage)); // frees the smem slot once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -281,10 +289,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t q = warp & 3; // TMEM lanes [32q, 32q+32)
     const uint32_t sEpi = base + L::EPI_OFF;
     uint32_t it = 0, epi_chunk = 0;
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
       const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
       const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+      const bool add_bias = p.col_bias && ks == 0; // exactly one k-slice contributes the bias
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t m = m0 + q * 32 + lane;
@@ -301,9 +311,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f; // lane j holds the bias of column c0 + j
-          if (p.col_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
+          if (add_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
           tmem_ld_wait();
-          if (p.col_bias) {
+          if (add_bias) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
           }
@@ -318,7 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
           epi_bar_sync();
           if (leader && n0 + c0 < p.N) {
-            if (p.accumulate) tma_reduce_add_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            if (p.accumulate || p.splits > 1) tma_reduce_add_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
             else tma_store_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
             bulk_commit();
           } else if (leader) {
@@ -333,9 +343,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f;
-          if (p.col_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
+          if (add_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
           tmem_ld_wait();
-          if (p.col_bias) {
+          if (add_bias) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
           }
@@ -431,7 +441,8 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
   using L = SmemLayout<BLOCK_N, STAGES>;
   const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
-  const unsigned grid = num_tiles < (uint32_t)kNumSMs ? num_tiles : (unsigned)kNumSMs;
+  const uint32_t num_units = num_tiles * p.splits;
+  const unsigned grid = num_units < (uint32_t)kNumSMs ? num_units : (unsigned)kNumSMs;
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
@@ -470,6 +481,31 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   CUtensorMap tmC;
   p.tma_store = make_c_map(&tmC, c, M, N, ldc, batch, c_bs) ? 1 : 0;
   if (!p.tma_store) tmC = tmA; // unused by the kernel, but must be a valid descriptor
+  // Split-K when the output has too few tiles to fill 148 SMs (weight gradients: M, N = layer widths,
+  // K = batch*seq). Pick the split count with the best wave efficiency, at least 8 k-blocks a slice.
+  const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles = p.tiles_m * p.tiles_n * batch;
+  uint32_t best_s = 1;
+  if (p.tma_store && tiles < 2u * kNumSMs) {
+    double best_eff = 0.0;
+    for (uint32_t sp = 1; sp <= 16 && sp * 8u <= num_kb; ++sp) {
+      const uint32_t units = tiles * sp, waves = (units + kNumSMs - 1) / kNumSMs;
+      const double eff = (double)units / ((double)waves * kNumSMs) - 0.01 * sp; // mild preference for fewer slices
+      if (eff > best_eff) {
+        best_eff = eff;
+        best_s = sp;
+      }
+    }
+  }
+  p.kb_per_split = (num_kb + best_s - 1) / best_s;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.splits > 1 && !accumulate) { // slices meet by reduce-add: C starts from zero
+    if (batch == 1 && ldc == M) {
+      WCU_CHECK(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)M * N, st));
+    } else {
+      for (uint32_t z = 0; z < batch; ++z)
+        WCU_CHECK(cudaMemset2DAsync(c + (uint64_t)z * c_bs, ldc * sizeof(float), 0, (size_t)M * sizeof(float), N, st));
+    }
+  }
   ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch);
   if (wide) return launch_cfg<256, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
   return launch_cfg<128, 6>(tmA, tmB, tmC, p, a_major, b_major, st);

@@ -19,12 +19,14 @@ typedef int (*CommInitRankFn)(void **, int, UniqueId, int);
 typedef int (*CommDestroyFn)(void *);
 typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*BroadcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*GroupFn)();
 void *g_lib = nullptr;
 GetUniqueIdFn p_get_id = nullptr;
 CommInitRankFn p_init = nullptr;
 CommDestroyFn p_destroy = nullptr;
 AllReduceFn p_allreduce = nullptr;
 BroadcastFn p_bcast = nullptr;
+GroupFn p_group_start = nullptr, p_group_end = nullptr;
 constexpr int kNcclFloat = 7, kNcclSum = 0;
 inline int wrap(int r) { return r == 0 ? 0 : 1000 + r; }
 } // namespace
@@ -42,6 +44,8 @@ int weedcu_nccl_load(const char *path) {
   p_destroy = (CommDestroyFn)dlsym(g_lib, "ncclCommDestroy");
   p_allreduce = (AllReduceFn)dlsym(g_lib, "ncclAllReduce");
   p_bcast = (BroadcastFn)dlsym(g_lib, "ncclBroadcast");
+  p_group_start = (GroupFn)dlsym(g_lib, "ncclGroupStart");
+  p_group_end = (GroupFn)dlsym(g_lib, "ncclGroupEnd");
   if (!p_get_id || !p_init || !p_destroy || !p_allreduce || !p_bcast) {
     g_lib = nullptr;
     return WEEDCU_ENCCL;
@@ -66,6 +70,14 @@ int weedcu_nccl_init(const void *id128, int rank, int world, void **comm) {
 int weedcu_nccl_destroy(void *comm) {
   if (!g_lib) return WEEDCU_ENCCL;
   return wrap(p_destroy(comm));
+}
+int weedcu_nccl_group_start(void) {
+  if (!g_lib || !p_group_start) return WEEDCU_ENCCL;
+  return wrap(p_group_start());
+}
+int weedcu_nccl_group_end(void) {
+  if (!g_lib || !p_group_end) return WEEDCU_ENCCL;
+  return wrap(p_group_end());
 }
 int weedcu_nccl_allreduce_sum(void *comm, float *buf, uint64_t n, void *stream) {
   if (!g_lib) return WEEDCU_ENCCL;

@@ -55,7 +55,9 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
       if (mstream && mstream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
       mstream = p->stream();
       mp.push_back(p->device_ptr());
-      mg.push_back(g->device_ptr_ro());
+      // a gradient still waiting for its lazy zero-fill was never touched by backward: pass "zeros"
+      GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
+      mg.push_back(gs->zero_pending ? nullptr : g->device_ptr_ro());
       mm.push_back(s.m->device_ptr());
       mv.push_back(s.v->device_ptr());
       mn.push_back(p->storage->size);
@@ -145,11 +147,19 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
 }
 
 void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm) {
+  bool grouped = false; // one NCCL group: the per-parameter reductions are fused into few kernels
   for (const ParameterPtr &p : params) {
     if (!p->grad) continue;
     Tensor &g = *(p->grad);
+    // untouched on this rank means untouched on every rank (same graph): zero everywhere, skip
+    if (g.storage->device == DeviceTag::GPU && static_cast<GpuRealStorage *>(g.storage.get())->zero_pending) continue;
+    if (!grouped) {
+      throw_on_error(weedcu_nccl_group_start(), "allreduce_gradients");
+      grouped = true;
+    }
     throw_on_error(weedcu_nccl_allreduce_sum(comm, g.device_ptr(), g.storage->size, g.stream()), "allreduce_gradients");
   }
+  if (grouped) throw_on_error(weedcu_nccl_group_end(), "allreduce_gradients");
 }
 void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root) {
   for (const ParameterPtr &p : params)
