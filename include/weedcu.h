@@ -269,6 +269,13 @@ int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_
  * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
                      uint32_t cols, uint16_t *dst, int dst_major, void *stream);
+/* weedcu_pack_bf16 that also writes, for every index of the NON-contiguous dst dimension, the fp32 sum
+ * over the contiguous one: colsum[j] (+)= sum_i src[i, j]. Packing dY [rows = B*T, cols = N] for the
+ * backward GEMMs yields the bias gradient (the reduce node of `y + bias`, tensor.cpp:1105-1136) in
+ * the same pass. WEEDCU_ENOSUP unless the source is contiguous along the packed dimension. */
+int weedcu_pack_bf16_colsum(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
+                            uint32_t cols, uint16_t *dst, int dst_major, float *colsum, int accumulate,
+                            void *stream);
 int weedcu_gemm_workspace_bytes(uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
                                 int precision, uint64_t *bytes);
 

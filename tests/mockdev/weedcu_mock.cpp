@@ -170,6 +170,27 @@ int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1
       dst[dst_major ? (r + c * ld) : (c + r * ld)] = wo_f32_to_bf16(src[offset + (uint64_t)r * s0 + (uint64_t)c * s1]);
   return 0;
 }
+int weedcu_pack_bf16_colsum(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols, uint16_t *dst, int dst_major, float *colsum, int accumulate,
+                            void *) {
+  if (!src || !dst || !colsum || !rows || !cols) return WEEDCU_EINVAL;
+  const uint32_t n_fast = dst_major ? rows : cols, n_slow = dst_major ? cols : rows;
+  const uint64_t s_fast = dst_major ? s0 : s1, ss = dst_major ? s1 : s0;
+  if (s_fast != 1 || (n_fast % 8u) || (ss % 4u)) return WEEDCU_ENOSUP; // same envelope as the device entry
+  trace_call("pack_bf16_colsum(");
+  ++g_launches;
+  if (g_nocompute) return 0;
+  const uint64_t ld = ((uint64_t)n_fast + 7U) & ~(uint64_t)7U;
+  for (uint32_t j = 0; j < n_slow; ++j) {
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < n_fast; ++i) {
+      const float x = src[offset + (uint64_t)j * ss + i];
+      sum += x;
+      dst[(uint64_t)j * ld + i] = wo_f32_to_bf16(x);
+    }
+    colsum[j] = accumulate ? colsum[j] + sum : sum;
+  }
+  return 0;
+}
 int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
                      int accumulate, const float *col_bias, void *) {
   if (!a || !b || !c || !M || !N || !K) return WEEDCU_EINVAL;

@@ -462,8 +462,33 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
                      uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
                      const float *col_bias) {
   if (!a || !b || !c || !M || !N || !K || !batch) return WEEDCU_EINVAL;
-  const bool wide = (N > 128);
-  const uint32_t block_n = wide ? 256 : 128;
+  // Tile width and split-K are chosen together by a small cost model: a CTA processes its work units
+  // (tile, k-slice) one after the other, so the launch costs  waves x BLOCK_N x (k-blocks per slice +
+  // ~3 k-blocks of un-overlapped prologue/epilogue). Few-tile problems (weight gradients: M, N =
+  // layer widths, K = batch*seq) get split along K, slices meeting in C by TMA reduce-add; tile
+  // counts just above a multiple of 148 get a narrower tile instead of a nearly empty last wave.
+  const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool c_tma = (((uintptr_t)c) & 15u) == 0 && (ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0);
+  uint32_t block_n = 256, best_s = 1;
+  double best_cost = 1e300;
+  const uint32_t cand[3] = {256, 192, 128};
+  for (uint32_t ci = 0; ci < 3; ++ci) {
+    const uint32_t bn = cand[ci];
+    if (bn > 128 && N <= bn - 64) continue; // do not pad a narrow N into a wide tile
+    const uint32_t tiles = tiles_m * ((N + bn - 1) / bn) * batch;
+    for (uint32_t sp = 1; sp <= 16; ++sp) {
+      if (sp > 1 && (!c_tma || sp * 4u > num_kb)) break;
+      const uint32_t kb_per = (num_kb + sp - 1) / sp, units = tiles * ((num_kb + kb_per - 1) / kb_per);
+      const uint32_t waves = (units + kNumSMs - 1) / kNumSMs;
+      const double tile_eff = bn == 256 ? 1.0 : (bn == 192 ? 1.03 : 1.12); // narrower tiles re-read A more often
+      const double cost = (double)waves * bn * (kb_per + 3.0 + (sp > 1 ? 1.0 : 0.0)) * tile_eff;
+      if (cost < best_cost) {
+        best_cost = cost;
+        block_n = bn;
+        best_s = sp;
+      }
+    }
+  }
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
   if (rc) return rc;
@@ -474,27 +499,15 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   p.ldc = ldc;
   p.c_bs = c_bs;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
-  p.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_m = tiles_m;
   p.tiles_n = (N + block_n - 1) / block_n;
   p.accumulate = accumulate;
   p.col_bias = col_bias;
   CUtensorMap tmC;
   p.tma_store = make_c_map(&tmC, c, M, N, ldc, batch, c_bs) ? 1 : 0;
-  if (!p.tma_store) tmC = tmA; // unused by the kernel, but must be a valid descriptor
-  // Split-K when the output has too few tiles to fill 148 SMs (weight gradients: M, N = layer widths,
-  // K = batch*seq). Pick the split count with the best wave efficiency, at least 8 k-blocks a slice.
-  const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles = p.tiles_m * p.tiles_n * batch;
-  uint32_t best_s = 1;
-  if (p.tma_store && tiles < 2u * kNumSMs) {
-    double best_eff = 0.0;
-    for (uint32_t sp = 1; sp <= 16 && sp * 8u <= num_kb; ++sp) {
-      const uint32_t units = tiles * sp, waves = (units + kNumSMs - 1) / kNumSMs;
-      const double eff = (double)units / ((double)waves * kNumSMs) - 0.01 * sp; // mild preference for fewer slices
-      if (eff > best_eff) {
-        best_eff = eff;
-        best_s = sp;
-      }
-    }
+  if (!p.tma_store) {
+    tmC = tmA; // unused by the kernel, but must be a valid descriptor
+    best_s = 1;
   }
   p.kb_per_split = (num_kb + best_s - 1) / best_s;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
@@ -507,7 +520,8 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
     }
   }
   ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch);
-  if (wide) return launch_cfg<256, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
+  if (block_n == 256) return launch_cfg<256, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
+  if (block_n == 192) return launch_cfg<192, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
   return launch_cfg<128, 6>(tmA, tmB, tmC, p, a_major, b_major, st);
 }
 
@@ -568,6 +582,32 @@ pack_bf16_stream_kernel(const float *__restrict__ src, uint64_t s_bs, uint64_t s
   }
 }
 
+// Streaming conversion that also reduces: one block per slow index j converts the contiguous run
+// src[j*ss .. +n_fast) and leaves its fp32 sum in colsum[j] — the bias gradient (column sums of dY)
+// falls out of the pass that packs dY for the two backward GEMMs.
+__global__ void __launch_bounds__(256)
+pack_bf16_colsum_kernel(const float *__restrict__ src, uint64_t ss, uint32_t n_fast8, __nv_bfloat16 *__restrict__ dst,
+                        uint64_t ld, float *colsum, int accumulate) {
+  __shared__ float red[32];
+  const uint32_t j = blockIdx.x;
+  const float *s = src + (uint64_t)j * ss;
+  __nv_bfloat16 *d = dst + (uint64_t)j * ld;
+  float sum = 0.0f;
+  for (uint32_t i = threadIdx.x; i < n_fast8; i += 256) {
+    const float4 a = *reinterpret_cast<const float4 *>(s + 8 * i);
+    const float4 b = *reinterpret_cast<const float4 *>(s + 8 * i + 4);
+    sum += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    __nv_bfloat162 o[4];
+    o[0] = __floats2bfloat162_rn(a.x, a.y);
+    o[1] = __floats2bfloat162_rn(a.z, a.w);
+    o[2] = __floats2bfloat162_rn(b.x, b.y);
+    o[3] = __floats2bfloat162_rn(b.z, b.w);
+    *reinterpret_cast<uint4 *>(d + 8 * i) = *reinterpret_cast<const uint4 *>(o);
+  }
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) colsum[j] = accumulate ? (colsum[j] + sum) : sum;
+}
+
 int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, uint32_t rows, uint32_t cols,
                      uint16_t *dst, uint64_t d_bs, uint64_t ld, int dst_major, uint32_t batch,
                      cudaStream_t st) {
@@ -615,6 +655,20 @@ int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1
   if (!src || !dst || !rows || !cols) return WEEDCU_EINVAL;
   const uint64_t ld = round8(dst_major ? rows : cols);
   return launch_pack_bf16(src + offset, 0, s0, s1, rows, cols, dst, 0, ld, dst_major, 1, resolve_stream(stream));
+}
+
+int weedcu_pack_bf16_colsum(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
+                            uint32_t cols, uint16_t *dst, int dst_major, float *colsum, int accumulate,
+                            void *stream) {
+  if (!src || !dst || !colsum || !rows || !cols) return WEEDCU_EINVAL;
+  const uint32_t n_fast = dst_major ? rows : cols, n_slow = dst_major ? cols : rows;
+  const uint64_t s_fast = dst_major ? s0 : s1, ss = dst_major ? s1 : s0;
+  const float *base = src + offset;
+  if (s_fast != 1 || (n_fast % 8u) || (ss % 4u) || (((uintptr_t)base) & 15u) || (((uintptr_t)dst) & 15u)) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  ProfScope prof(WEEDCU_PROF_PACK, st, 6.0 * (double)rows * cols);
+  pack_bf16_colsum_kernel<<<n_slow, 256, 0, st>>>(base, ss, n_fast / 8u, (__nv_bfloat16 *)dst, round8(n_fast), colsum, accumulate);
+  return after_launch();
 }
 
 int weedcu_gemm_workspace_bytes(uint32_t M, uint32_t K, uint32_t N, uint32_t batch, int precision,

@@ -53,6 +53,9 @@ void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out);
 // out = a b + bias (bias: dense [N], broadcast over rows) in one tensor-core GEMM; false (nothing
 // computed) when that kernel does not apply to these operands
 bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out);
+// Packs dy [rows, N] into its bf16 GEMM shadow and adds its column sums into `sums` (dense [N]) in the
+// same pass — Linear's bias gradient without a separate reduction. false: nothing was done.
+bool pack_with_column_sums(const Tensor &dy, Tensor &sums);
 // `batch` independent products over 3-D views [batch, M, K] x [batch, K, N] -> [batch, M, N]
 // (the host loop of Tensor::matmul, tensor.cpp:1259-1269, as one strided-batched launch)
 void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3);

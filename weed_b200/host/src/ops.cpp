@@ -254,7 +254,10 @@ struct Bf16Operand {
   uint64_t ld;
 };
 inline uint64_t round8(uint64_t x) { return (x + 7U) & ~(uint64_t)7U; }
-bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcapint n_k, bool is_a, Bf16Operand &op) {
+// `colsum` (optional, dense [n_slow]): the pack pass also accumulates the fp32 sum over the contiguous
+// index into it; false (nothing done) if the shadow already exists or the layout cannot stream.
+bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcapint n_k, bool is_a, Bf16Operand &op,
+                  real1 *colsum = nullptr, int colsum_accumulate = 1) {
   if (!s_mn || !s_k) return false; // broadcast operands take the generic path
   GpuRealStorage *s = gpu_storage(t, "matmul");
   const bool mn_fast = is_a ? (s_mn <= s_k) : (s_mn < s_k);
@@ -267,6 +270,7 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
   for (GpuRealStorage::Bf16Shadow &sh : s->shadows)
     if (sh.offset == t.offset && sh.n_fast == n_fast && sh.n_slow == n_slow && sh.s_fast == s_fast && sh.s_slow == s_slow) hit = &sh;
   if (hit && hit->version == s->version) {
+    if (colsum) return false;
     op.ptr = (const uint16_t *)hit->buf->ptr;
     return true;
   }
@@ -277,7 +281,13 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
   }
   s->dev->Bind();
   // weedcu_pack_bf16(rows = mn index, cols = k index): dst_major 1 keeps rows contiguous
-  throw_on_error(weedcu_pack_bf16(src, t.offset, s_mn, s_k, n_mn, n_k, (uint16_t *)hit->buf->ptr, op.major, s->dev->stream), "pack_bf16");
+  if (colsum) {
+    const int rc = weedcu_pack_bf16_colsum(src, t.offset, s_mn, s_k, n_mn, n_k, (uint16_t *)hit->buf->ptr, op.major, colsum, colsum_accumulate,
+                                           s->dev->stream);
+    if (rc == WEEDCU_ENOSUP) return false; // (the shadow entry stays stale and is packed on first use)
+    throw_on_error(rc, "pack_bf16_colsum");
+  } else
+    throw_on_error(weedcu_pack_bf16(src, t.offset, s_mn, s_k, n_mn, n_k, (uint16_t *)hit->buf->ptr, op.major, s->dev->stream), "pack_bf16");
   hit->version = s->version;
   op.ptr = (const uint16_t *)hit->buf->ptr;
   return true;
@@ -418,6 +428,26 @@ void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const
 void matmul(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 0); }
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 1); }
 bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out) { return matmul_impl(a, b, out, 0, &bias); }
+bool pack_with_column_sums(const Tensor &dy, Tensor &sums) {
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || dy.shape.size() != 2U) return false;
+  const tcapint M = dy.shape[0U], N = dy.shape[1U];
+  // only when the packed layout keeps the row index contiguous (colsum then runs over rows) and the
+  // GEMMs that follow will use this very shadow (same eligibility as matmul_impl)
+  if (dy.stride[0U] != 1U || M < 64U || N < 16U || sums.storage->size != N || !covers_storage(sums)) return false;
+  GpuRealStorage *ss = gpu_storage(sums, "pack_with_column_sums");
+  const int accumulate = ss->zero_pending ? 0 : 1;
+  Bf16Operand op;
+  // probe first: device_ptr_overwrite() below drops the pending zero fill, so the pack must happen
+  GpuRealStorage *ds = gpu_storage(dy, "pack_with_column_sums");
+  for (const GpuRealStorage::Bf16Shadow &sh : ds->shadows)
+    if (sh.offset == dy.offset && sh.n_fast == M && sh.n_slow == N && sh.version == ds->version) return false;
+  if ((M % 8U) || (dy.stride[1U] % 4U) || (dy.offset % 4U)) return false;
+  real1 *sp = accumulate ? ss->device_ptr() : ss->device_ptr_overwrite();
+  if (!bf16_operand(dy, dy.stride[0U], dy.stride[1U], M, N, true, op, sp + sums.offset, accumulate))
+    throw std::runtime_error("pack_with_column_sums: streaming pack refused after the eligibility check");
+  return true;
+}
 
 void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {
   validate_all_same_device({&a3, &b3, &out3}, "MatMulKernel::matmul_batched");

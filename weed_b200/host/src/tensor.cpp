@@ -923,11 +923,22 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
     out->grad_node = std::make_shared<Node>(grad_parents({a, w, bias}), [a, w, bias, wout = std::weak_ptr<Tensor>(out)]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
       if (!out) return;
-      matmul_backward(a, w, out);
       if (bias->requires_grad) {
+        // the bias gradient (column sums of dY) rides on the pass that packs dY for the two GEMMs below
         TensorPtr out_grad = view_copy(out->grad);
-        accumulate(bias, out_grad, *out_grad, false);
+        bool done = false;
+        if (bias->grad && is_contiguous(out_grad->shape, out_grad->stride)) {
+          TensorPtr dy2 = view_copy(out_grad);
+          dy2->requires_grad = false;
+          const tcapint N = out_grad->shape.back();
+          dy2->BaseTensor::reshape({(symint)(out_grad->get_broadcast_size() / N), (symint)N});
+          TensorPtr bg = view_copy(bias->grad);
+          done = Weed::pack_with_column_sums(*dy2, *bg);
+          if (done) bias->grad = bg;
+        }
+        if (!done) accumulate(bias, out_grad, *out_grad, false);
       }
+      matmul_backward(a, w, out);
     });
   }
   return out;
