@@ -177,7 +177,10 @@ def main_reference(args):
     line = {"impl": "reference", "metric": "train samples/s (GPT-2-small shape)", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * ratio * 1000.0, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C5 GPT-2-small-shape train step (bounded CPU sample, extrapolated)", "sample": sample},
+            "config": {"workload": "C5 GPT-2-small-shape training step (untied, 163M params)", "layers": cfg["L"], "d_model": cfg["d"],
+                       "heads": cfg["H"], "d_ff": cfg["dff"], "vocab": cfg["V"], "seq_len": cfg["T"], "batch_per_gpu": cfg["B"],
+                       "global_batch": cfg["B"], "parallelism": "cpu", "optimizer": "Adam", "loss": "cross_entropy_loss",
+                       "measured_on": "bounded CPU sample, extrapolated by algorithmic FLOP", "sample": sample},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -417,8 +420,8 @@ def main_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--layers", type=int, default=0)

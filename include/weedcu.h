@@ -166,8 +166,10 @@ int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, ui
  * q + 1 <= k when causal), P = softmax_k(S), O = P V — the chain of MultiHeadAttention::forward,
  * src/modules/multihead_attention.cpp:289-345, without its transposing copies. Q, K, V and P are
  * rounded to bf16, accumulation is fp32; like the reference's batched matmul (tensor.cpp:1253-1271)
- * the result carries no autograd edge. Returns WEEDCU_ENOSUP for shapes outside T % 8 == 0,
- * 64 <= T <= 1024, hd % 8 == 0 (callers then compose the generic ops). */
+ * the result carries no autograd edge. head_dim 64 runs a flash-style kernel (scores and
+ * probabilities never leave the SM: tcgen05 + TMEM, online softmax); other head sizes store S and
+ * P (bf16) in a workspace. Returns WEEDCU_ENOSUP for shapes outside T % 8 == 0, T >= 64,
+ * hd % 8 == 0, hd >= 16 (and T <= 1024 unless hd == 64); callers then compose the generic ops. */
 int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
                          uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                          int causal, void *stream);

@@ -106,7 +106,7 @@ int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, ui
   return RUN(wo_attn_softmax_real(scores, out, batch, Tq, Tk, divisor, mask_val, causal, batch_fastest));
 }
 int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal, void *) {
-  if ((T % 8u) || T < 64u || T > 1024u || hd < 16u || (hd % 8u)) return WEEDCU_ENOSUP; // same envelope as the device entry
+  if ((T % 8u) || T < 64u || (hd != 64u && T > 1024u) || hd < 16u || (hd % 8u)) return WEEDCU_ENOSUP; // same envelope as the device entry
   return RUN(wo_attention_fwd(q, k, v, out, B, T, H, hd, divisor, mask_val, (causal && T > 1) ? 1 : 0));
 }
 int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, float *lse, float *loss, void *) {

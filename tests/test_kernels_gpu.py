@@ -65,6 +65,8 @@ def test_launch_counter_counts(gpu):
 
 ATTN_CASES = [  # B, T, H, hd, causal
     (2, 64, 2, 16, 1), (3, 128, 4, 64, 1), (1, 72, 3, 32, 1), (2, 200, 2, 64, 0), (8, 256, 2, 64, 1),
+    # head_dim 64 runs the flash kernel (scores in TMEM): full GPT-2 sequence, ragged last tiles, T > 1024
+    (1, 1024, 2, 64, 1), (1, 1160, 1, 64, 1), (2, 328, 1, 64, 0), (1, 64, 1, 64, 1),
 ]
 
 

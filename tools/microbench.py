@@ -35,11 +35,21 @@ def call(name, *args):
     check(fn(*conv, C.c_void_p(STREAM)), name)
 
 
+_BLOCK = None
+
+
 def timeit(fn, nrot, iters=20, warmup=5):
+    """Device time per launch. A long blocker kernel is queued first so that the host (ctypes call +
+    tensor-map encodes, ~10-20 us per launch from Python) runs ahead of the GPU: without it a kernel
+    shorter than the host's issue time measures the host, not the kernel."""
+    global _BLOCK
     for i in range(warmup):
         fn(i % nrot)
     torch.cuda.synchronize()
+    if _BLOCK is None:
+        _BLOCK = torch.randn(6144, 6144, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.mm(_BLOCK, _BLOCK)  # ~10 ms of fp32 work on the current (timing) stream
     e0.record()
     for i in range(iters):
         fn(i % nrot)

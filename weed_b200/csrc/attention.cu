@@ -19,8 +19,12 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace weedcu {
+// flash_attn.cu: scores kept in TMEM (head_dim 64)
+int launch_flash_attn_fwd(const uint16_t *qh, const uint16_t *kh, const uint16_t *vh, float *oc, uint32_t BH, uint32_t T,
+                          float divisor, int causal, cudaStream_t st);
 namespace tc {
 int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
                      int b_major, uint64_t ldb, uint64_t b_bs, float *c, uint64_t ldc, uint64_t c_bs,
@@ -88,6 +92,9 @@ attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict_
   __nv_bfloat16 *po = P + (uint64_t)row * T;
   const uint32_t Lc = (causal && mask_val <= -1e30f) ? min(T, q + 1u) : T; // keys that can be non-zero
 
+  // The output is bf16 (8 mantissa bits): reciprocal multiplies and ex2.approx instead of IEEE
+  // divisions / expf keep the kernel bandwidth-bound; chunks beyond Lc are skipped warp-uniformly.
+  const float inv_div = 1.0f / divisor;
   float4 v[NV4];
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
@@ -97,14 +104,16 @@ attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict_
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
-    const uint32_t k = (i * 32 + lane) * 4;
-    float *e = reinterpret_cast<float *>(&v[i]);
+    if (i * 128u < Lc) {
+      const uint32_t k = (i * 32 + lane) * 4;
+      float *e = reinterpret_cast<float *>(&v[i]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = e[j] / divisor;
-      if (causal) x = x + ((q + 1u <= k + j) ? mask_val : 0.0f);
-      e[j] = (k + j < Lc) ? x : -INFINITY;
-      mx = fmaxf(mx, e[j]);
+      for (int j = 0; j < 4; ++j) {
+        float x = e[j] * inv_div;
+        if (causal) x = x + ((q + 1u <= k + j) ? mask_val : 0.0f);
+        e[j] = (k + j < Lc) ? x : -INFINITY;
+        mx = fmaxf(mx, e[j]);
+      }
     }
   }
 #pragma unroll
@@ -113,21 +122,26 @@ attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict_
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
     float *e = reinterpret_cast<float *>(&v[i]);
+    if (i * 128u < Lc) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      e[j] = (e[j] > -INFINITY) ? expf(e[j] - mx) : 0.0f;
-      s += e[j];
+      for (int j = 0; j < 4; ++j) {
+        e[j] = __expf(e[j] - mx); // exp(-inf) = 0 for the masked tail of the chunk
+        s += e[j];
+      }
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv_s = 1.0f / s;
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
     const uint32_t k = (i * 32 + lane) * 4;
     if (k < T) {
       __nv_bfloat162 o2[2];
-      o2[0] = __floats2bfloat162_rn(v[i].x / s, v[i].y / s);
-      o2[1] = __floats2bfloat162_rn(v[i].z / s, v[i].w / s);
+      o2[0] = __floats2bfloat162_rn(v[i].x * inv_s, v[i].y * inv_s);
+      o2[1] = __floats2bfloat162_rn(v[i].z * inv_s, v[i].w * inv_s);
       *reinterpret_cast<uint2 *>(po + k) = *reinterpret_cast<const uint2 *>(o2);
     }
   }
@@ -142,13 +156,20 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
                                     int causal, void *stream) {
   if (!q || !k || !v || !out || !B || !T || !H || !hd) return WEEDCU_EINVAL;
   // tensor-map constraints of the two products (16-byte row pitch) and the register softmax
-  if ((T % 8u) || T < 64u || T > 1024u || hd < 16u || (hd % 8u) || H * hd > 65535u) return WEEDCU_ENOSUP;
+  static const bool flash_on = [] {
+    const char *e = getenv("WEEDCU_FLASH");
+    return !(e && atoi(e) == 0);
+  }();
+  // scores stay in TMEM; otherwise S and P go through HBM. The flash kernel drops masked keys
+  // outright, which equals adding mask_val only when exp(mask_val) underflows to 0 (the default -2^127)
+  const bool flash = flash_on && hd == 64u && (!causal || T == 1u || mask_val <= -1e30f);
+  if ((T % 8u) || T < 64u || (!flash && T > 1024u) || hd < 16u || (hd % 8u) || H * hd > 65535u) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   const uint64_t BH = (uint64_t)B * H, C = (uint64_t)H * hd;
   if (BH > 65535u) return WEEDCU_ENOSUP;
   const uint64_t head_elems = (uint64_t)hd * T; // per (b,h)
   const uint64_t qkv_bytes = 3 * BH * head_elems * sizeof(uint16_t);
-  const uint64_t s_bytes = BH * T * T * sizeof(float), p_bytes = BH * T * T * sizeof(uint16_t);
+  const uint64_t s_bytes = flash ? 0 : BH * T * T * sizeof(float), p_bytes = flash ? 0 : BH * T * T * sizeof(uint16_t);
   const uint64_t o_bytes = BH * head_elems * sizeof(float);
   auto up = [](uint64_t x) { return (x + 255) & ~(uint64_t)255; };
   char *ws = nullptr;
@@ -172,9 +193,16 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
     heads_pack_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C, 3), 256, tile_bytes, st>>>(a, B, T, H, hd, tt);
     rc = after_launch();
   }
-  if (rc == 0) // S^T[bh] = Kh Qh^T (C[k, q], k contiguous): both operands have the token index contiguous
+  if (rc == 0 && flash) {
+    rc = launch_flash_attn_fwd(qh, kh, vh, oc, (uint32_t)BH, T, divisor, (causal && T > 1) ? 1 : 0, st);
+    if (rc == WEEDCU_ENOSUP) {
+      pool_free(ws, st);
+      return rc;
+    }
+  }
+  if (rc == 0 && !flash) // S^T[bh] = Kh Qh^T (C[k, q], k contiguous): both operands have the token index contiguous
     rc = tc::launch_gemm_bf16(kh, 1, T, head_elems, qh, 1, T, head_elems, S, T, (uint64_t)T * T, T, T, hd, (uint32_t)BH, 0, st, nullptr);
-  if (rc == 0) {
+  if (rc == 0 && !flash) {
     ProfScope prof(WEEDCU_PROF_SOFTMAX, st, (causal ? 4.0 : 6.0) * (double)BH * T * T);
     const uint32_t rows = (uint32_t)(BH * T);
     const unsigned grid = (rows + 7) / 8;
@@ -188,7 +216,7 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
 #undef WCU_SM
     rc = after_launch();
   }
-  if (rc == 0) // O[bh] = P Vh : A = P [T(q), T(k)] and B = Vh as [hd, T(k)], both with k contiguous
+  if (rc == 0 && !flash) // O[bh] = P Vh : A = P [T(q), T(k)] and B = Vh as [hd, T(k)], both with k contiguous
     rc = tc::launch_gemm_bf16(P, 0, T, (uint64_t)T * T, vh, 0, T, head_elems, oc, T, head_elems, T, hd, T, (uint32_t)BH, 0, st, nullptr);
   if (rc == 0) {
     ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 8.0 * (double)B * T * C);
