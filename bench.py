@@ -350,7 +350,7 @@ def main_ours(args):
     roofline, breakdown = None, {}
     if rank == 0:
         names = {1: "gemm_bf16_tcgen05", 2: "gemm_f32_ffma", 3: "pack_bf16", 4: "elementwise", 5: "softmax", 6: "layernorm", 7: "cross_entropy",
-                 8: "optimizer", 9: "reduce", 10: "embedding", 11: "fill"}
+                 8: "optimizer", 9: "reduce", 10: "embedding", 11: "fill", 12: "nccl", 13: "attention_flash_tcgen05"}
         lib.weedcu_prof_enable(C.c_int(1))
         psteps = min(2, args.steps)
         for s in range(psteps):
@@ -374,7 +374,7 @@ def main_ours(args):
         if breakdown:
             top = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
             b = breakdown[top]
-            if top.startswith("gemm"):
+            if top.startswith("gemm") or top.startswith("attention"):
                 peak = peaks.get("bf16_tflops_sustained", 1400.0)
                 ach = b["work_per_step"] / (b["ms_per_step"] / 1000.0) / 1e12
                 roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

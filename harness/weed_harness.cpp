@@ -435,6 +435,7 @@ int wh_zero_grad(int64_t module) {
 namespace {
 void *g_comm = nullptr;
 int g_world = 1;
+std::unique_ptr<GradientBuckets> g_buckets;
 } // namespace
 #endif
 int wh_dp_load(const char *libnccl_path) {
@@ -497,11 +498,25 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     const auto t1 = now();
     TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
     const auto t2 = now();
-    Tensor::backward(loss);
-    const auto t3 = now();
     const std::vector<ParameterPtr> params = m->parameters();
 #ifdef WEED_B200
-    if (g_comm && g_world > 1) allreduce_gradients(params, g_comm);
+    // data parallel: bucketed gradient all-reduce on a communication stream, overlapped with the
+    // rest of the backward walk (WH_DP_OVERLAP=0: one grouped all-reduce after backward)
+    static const bool overlap = !(getenv("WH_DP_OVERLAP") && atoi(getenv("WH_DP_OVERLAP")) == 0);
+    const bool dp = g_comm && g_world > 1;
+    if (dp && overlap) {
+      if (!g_buckets) {
+        const char *bb = getenv("WH_DP_BUCKET_BYTES");
+        g_buckets.reset(bb ? new GradientBuckets(g_comm, (size_t)atoll(bb)) : new GradientBuckets(g_comm));
+      }
+      g_buckets->begin();
+    }
+#endif
+    Tensor::backward(loss);
+    const auto t3 = now();
+#ifdef WEED_B200
+    if (dp && overlap) g_buckets->finish(params);
+    else if (dp) allreduce_gradients(params, g_comm);
 #endif
     const auto t4 = now();
     adam_step(*g_adams.at(opt), params);

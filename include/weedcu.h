@@ -290,7 +290,7 @@ enum {
   WEEDCU_PROF_GEMM_TC = 1, WEEDCU_PROF_GEMM_F32 = 2, WEEDCU_PROF_PACK = 3, WEEDCU_PROF_ELEMENTWISE = 4,
   WEEDCU_PROF_SOFTMAX = 5, WEEDCU_PROF_LAYERNORM = 6, WEEDCU_PROF_CROSS_ENTROPY = 7,
   WEEDCU_PROF_OPTIMIZER = 8, WEEDCU_PROF_REDUCE = 9, WEEDCU_PROF_EMBEDDING = 10, WEEDCU_PROF_FILL = 11,
-  WEEDCU_PROF_NCCL = 12, WEEDCU_PROF_NUM_CLASSES = 13
+  WEEDCU_PROF_NCCL = 12, WEEDCU_PROF_ATTENTION = 13, WEEDCU_PROF_NUM_CLASSES = 14
 };
 int weedcu_prof_enable(int on);
 int weedcu_prof_read(int cls, double *total_ms, uint64_t *launches, double *work);

@@ -218,7 +218,9 @@ def _reduce(be, rng, shape, axis, order):
 
 
 for _shape, _axis in [([300, 70], 0), ([300, 70], 1), ([33, 1], 0), ([6, 10, 96], 2), ([6, 10, 96], 1),
-                      ([6, 10, 96], 0), ([1, 40, 64], 2), ([64, 3, 5, 7], 2), ([2048, 40], 1)]:
+                      ([6, 10, 96], 0), ([1, 40, 64], 2), ([64, 3, 5, 7], 2), ([2048, 40], 1),
+                      # contiguous axis: short (thread per output, 128-bit / scalar) and medium (warp per output)
+                      ([8, 3000], 0), ([7, 513], 0), ([200, 640], 0)]:
     for _order in (0, 1):
         @case(f"reduce_{'x'.join(map(str, _shape))}_axis{_axis}_order{_order}")
         def _c(be, rng, shape=_shape, axis=_axis, order=_order):

@@ -12,6 +12,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MOCK_DIR = os.path.join(ROOT, "tests", "mockdev")
@@ -43,13 +44,20 @@ def _single_process_reference(world):
     return np.array(losses), params
 
 
-def test_two_rank_data_parallel_matches_single_process(tmp_path):
+@pytest.mark.parametrize("overlap,bucket_bytes", [(1, 0), (1, 2048), (0, 0)],
+                         ids=["overlap_default_bucket", "overlap_2KB_buckets", "after_backward"])
+def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap, bucket_bytes):
+    """overlap=1: GradientBuckets hands gradients to the all-reduce as Tensor::backward reports them
+    final (tiny buckets force several flushes in the middle of the walk); overlap=0: one grouped
+    all-reduce after backward. Both must equal the single-process global-batch step."""
     subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
     world, port = 2, _free_port()
     procs, outs = [], []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   GLOO_SOCKET_IFNAME="lo")
+                   GLOO_SOCKET_IFNAME="lo", WH_DP_OVERLAP=str(overlap))
+        if bucket_bytes:
+            env["WH_DP_BUCKET_BYTES"] = str(bucket_bytes)
         out = str(tmp_path / f"rank{r}.json")
         outs.append(out)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dp_worker.py"), out, str(STEPS)], env=env))

@@ -73,8 +73,10 @@ ATTN_CASES = [  # B, T, H, hd, causal
 @pytest.mark.parametrize("B,T,H,hd,causal", ATTN_CASES, ids=[f"attn_B{c[0]}_T{c[1]}_H{c[2]}_hd{c[3]}_causal{c[4]}" for c in ATTN_CASES])
 def test_attention_fwd_bf16(gpu, oracle, B, T, H, hd, causal):
     """Fused attention core (heads relayout + bf16 pack, tcgen05 QK^T, softmax -> bf16 P, tcgen05 PV).
-    (1) vs the oracle model with the same bf16 rounding points: accumulation order and the odd
-    one-ulp flip of a rounded probability -> 2e-3 relative-to-max;
+    (1) vs the oracle model with the same bf16 rounding points: accumulation order and one-ulp flips
+    of rounded probabilities (the flash kernel rounds p = 2^(t - m) against the RUNNING row maximum,
+    the model against the final one, so mantissas differ by a non-power-of-two factor before the
+    rounding) -> 4e-3 relative-to-max, i.e. two bf16 ulps (2^-8);
     (2) vs the exact fp32 chain (reference arithmetic, multihead_attention.cpp:289-345): the bf16
     bound, 2e-2 relative-to-max."""
     import ctypes as C
@@ -102,7 +104,7 @@ def test_attention_fwd_bf16(gpu, oracle, B, T, H, hd, causal):
     Pm /= Pm.sum(-1, keepdims=True)
     exact = (Pm @ V).transpose(1, 3, 2, 0).reshape(-1).astype(np.float32)  # back to [B, T, H*hd] col-major
     assert np.all(np.isfinite(got))
-    assert cases.rel_err(got, model) <= 2e-3, f"vs bf16 model: {cases.rel_err(got, model):.3e}"
+    assert cases.rel_err(got, model) <= 4e-3, f"vs bf16 model: {cases.rel_err(got, model):.3e}"
     assert cases.rel_err(got, exact) <= 2e-2, f"vs fp32 chain: {cases.rel_err(got, exact):.3e}"
 
 

@@ -239,6 +239,33 @@ def bench_ew(results, peaks):
     rec("embedding_scatter_8192x768", ms, 12 * ntok * D)
 
 
+def bench_attn(results, peaks):
+    """Fused attention core at the C5 shape (B=8, H=12, T=1024, hd=64): heads_pack + flash kernel + unheads.
+    FLOP = the causal half of 4*B*H*T*T*hd (the key tiles the kernel actually visits are slightly more)."""
+    peak = peaks.get("bf16_tflops", 1590.0)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    for (B, T, H, hd, causal) in ((8, 1024, 12, 64, 1), (8, 1024, 12, 64, 0), (2, 4096, 12, 64, 1)):
+        n = B * T * H * hd
+        q, k, v, o = bufs(n, 2), bufs(n, 2), bufs(n, 2), bufs(n, 2)
+        ms = timeit(lambda i: call("attention_fwd", P(q[i]), P(k[i]), P(v[i]), P(o[i]), U32(B), U32(T), U32(H), U32(hd),
+                                   F(8.0), F(-1.701411835e38), I32(causal)), 2, iters=10, warmup=3)
+        flops = 4.0 * B * H * T * T * hd * (0.5 if causal else 1.0)
+        tf = flops / ms / 1e9
+        results.append({"kernel": f"attention_fwd_B{B}_T{T}_H{H}_hd{hd}_causal{causal}", "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+                        "frac_of_bf16_peak": round(tf / peak, 3), "note": "heads_pack + flash (tcgen05, S in TMEM) + unheads"})
+        print(f"attention_fwd_B{B}_T{T}_H{H}_hd{hd}_causal{causal:<12d} {ms:9.4f} ms  {tf:8.1f} TFLOP/s  {tf / peak:5.3f} of bf16 peak", flush=True)
+        del q, k, v, o
+    # broadcast positional-encoding gradient: [B, T*d] summed over the contiguous batch axis (4 B/elem)
+    Bq, n_out = 8, 1024 * 768
+    X = bufs(Bq * n_out, 8)
+    out = bufs(n_out, 1)[0]
+    v2 = contiguous_view([Bq, n_out])
+    ms = timeit(lambda i: call("reduce_real", P(X[i]), v2, I32(0), P(out), I32(0)), 8)
+    gbs = 4.0 * Bq * n_out / ms / 1e6
+    results.append({"kernel": "reduce_axis0_8x786432 (pos-enc grad)", "ms": round(ms, 4), "alg_GBps": round(gbs, 1), "frac_of_hbm": round(gbs / hbm, 3)})
+    print(f"{'reduce_axis0_8x786432 (pos-enc grad)':42s} {ms:9.4f} ms  {gbs:8.1f} GB/s  {gbs / hbm:5.2f} of HBM", flush=True)
+
+
 def bench_gemm(results, peaks, which):
     peak = peaks.get("bf16_tflops", 1590.0)
 
@@ -298,6 +325,8 @@ def main():
     results = []
     if args.group in ("ew", "all"):
         bench_ew(results, peaks)
+    if args.group in ("attn", "all"):
+        bench_attn(results, peaks)
     if args.group in ("gemm", "all", "f32", "tc"):
         bench_gemm(results, peaks, args.group)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -39,6 +39,54 @@ struct HeadsPackArgs {
   const float *src[3];
   __nv_bfloat16 *dst[3];
 };
+// Shared tile is [B][tt + 4] (token index contiguous, pitch = 4 mod 32 words): the 128-bit global
+// loads (4 consecutive b of one token) scatter into 4 rows without bank conflicts, and every thread
+// then emits 8 consecutive tokens of one b as ONE 16-byte bf16 store. All loads of a thread are
+// issued before the first shared-memory write (LPT independent 128-bit requests in flight).
+template <int LPT>
+__global__ void __launch_bounds__(256)
+heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
+  extern __shared__ float tile[]; // [B][tt + 4]
+  const uint32_t pitch = tt + 4u;
+  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n4 = (nt * B) >> 2; // B % 4 == 0
+  // (selects instead of indexing the parameter struct: a dynamic index would copy it to local memory)
+  const float *sp = blockIdx.z == 0 ? a.src[0] : (blockIdx.z == 1 ? a.src[1] : a.src[2]);
+  __nv_bfloat16 *dst = blockIdx.z == 0 ? a.dst[0] : (blockIdx.z == 1 ? a.dst[1] : a.dst[2]);
+  const float4 *src = reinterpret_cast<const float4 *>(sp + ((uint64_t)c * T + t0) * B);
+  float4 v[LPT];
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    v[u] = (i < n4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    if (i < n4) {
+      const uint32_t e = i << 2, t = e / B, b = e - t * B;
+      float *d = tile + b * pitch + t;
+      d[0] = v[u].x;
+      d[pitch] = v[u].y;
+      d[2 * pitch] = v[u].z;
+      d[3 * pitch] = v[u].w;
+    }
+  }
+  __syncthreads();
+  const uint32_t n8 = (nt >> 3) * B; // nt % 8 == 0 (T % 8 == 0, tt % 8 == 0)
+  for (uint32_t i = threadIdx.x; i < n8; i += 256u) {
+    const uint32_t b = i / (nt >> 3), t = (i - b * (nt >> 3)) << 3;
+    const float4 x = *reinterpret_cast<const float4 *>(tile + b * pitch + t);
+    const float4 y = *reinterpret_cast<const float4 *>(tile + b * pitch + t + 4);
+    __nv_bfloat162 o[4];
+    o[0] = __floats2bfloat162_rn(x.x, x.y);
+    o[1] = __floats2bfloat162_rn(x.z, x.w);
+    o[2] = __floats2bfloat162_rn(y.x, y.y);
+    o[3] = __floats2bfloat162_rn(y.z, y.w);
+    *reinterpret_cast<uint4 *>(dst + (((uint64_t)b * H + h) * hd + j) * T + t0 + t) = *reinterpret_cast<const uint4 *>(o);
+  }
+}
+// generic shapes (B % 4 != 0 or unaligned bases)
 __global__ void __launch_bounds__(256)
 heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [tt][B + 1]
@@ -54,6 +102,41 @@ heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t 
   for (uint32_t i = threadIdx.x; i < n; i += 256) {
     const uint32_t b = i / nt, t = i - b * nt;
     dst[(((uint64_t)b * H + h) * hd + j) * T + t0 + t] = __float2bfloat16_rn(tile[t * (B + 1) + b]);
+  }
+}
+// fp32 [B*H][hd][T] -> [B,T,C]: the inverse walk through the same [B][tt + 4] tile; 128-bit loads
+// along t, 128-bit stores of 4 consecutive b.
+template <int LPT>
+__global__ void __launch_bounds__(256)
+unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32_t B, uint32_t T, uint32_t H,
+                   uint32_t hd, uint32_t tt) {
+  extern __shared__ float tile[]; // [B][tt + 4]
+  const uint32_t pitch = tt + 4u;
+  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), q = nt >> 2, n4 = q * B; // nt % 4 == 0
+  float4 v[LPT];
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    if (i < n4) {
+      const uint32_t b = i / q, t = (i - b * q) << 2;
+      v[u] = *reinterpret_cast<const float4 *>(oc + (((uint64_t)b * H + h) * hd + j) * T + t0 + t);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    if (i < n4) {
+      const uint32_t b = i / q, t = (i - b * q) << 2;
+      *reinterpret_cast<float4 *>(tile + b * pitch + t) = v[u];
+    }
+  }
+  __syncthreads();
+  float4 *dst = reinterpret_cast<float4 *>(out + ((uint64_t)c * T + t0) * B);
+  for (uint32_t i = threadIdx.x; i < n4; i += 256u) {
+    const uint32_t e = i << 2, t = e / B, b = e - t * B;
+    const float *p = tile + b * pitch + t;
+    dst[i] = make_float4(p[0], p[pitch], p[2 * pitch], p[3 * pitch]);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -190,7 +273,15 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
   {
     ProfScope prof(WEEDCU_PROF_PACK, st, 3.0 * 6.0 * (double)B * T * C);
     HeadsPackArgs a = {{q, k, v}, {(__nv_bfloat16 *)qh, (__nv_bfloat16 *)kh, (__nv_bfloat16 *)vh}};
-    heads_pack_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C, 3), 256, tile_bytes, st>>>(a, B, T, H, hd, tt);
+    // vector path: 4096 elements (16 KB) per block = 4 x 128-bit loads per thread
+    const uint32_t vtt = (4096u / B) & ~7u;
+    if ((B % 4u) == 0 && vtt >= 8u && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(qh)) {
+      const uint32_t vt = vtt < T ? vtt : T;
+      const size_t vbytes = (size_t)B * (vt + 4u) * sizeof(float);
+      heads_pack_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C, 3), 256, vbytes, st>>>(a, B, T, H, hd, vt);
+    } else {
+      heads_pack_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C, 3), 256, tile_bytes, st>>>(a, B, T, H, hd, tt);
+    }
     rc = after_launch();
   }
   if (rc == 0 && flash) {
@@ -220,7 +311,13 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
     rc = tc::launch_gemm_bf16(P, 0, T, (uint64_t)T * T, vh, 0, T, head_elems, oc, T, head_elems, T, hd, T, (uint32_t)BH, 0, st, nullptr);
   if (rc == 0) {
     ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 8.0 * (double)B * T * C);
-    unheads_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C), 256, tile_bytes, st>>>(oc, out, B, T, H, hd, tt);
+    const uint32_t vtt = (4096u / B) & ~7u;
+    if ((B % 4u) == 0 && vtt >= 8u && aligned16(oc) && aligned16(out)) {
+      const uint32_t vt = vtt < T ? vtt : T;
+      unheads_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C), 256, (size_t)B * (vt + 4u) * sizeof(float), st>>>(oc, out, B, T, H, hd, vt);
+    } else {
+      unheads_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C), 256, tile_bytes, st>>>(oc, out, B, T, H, hd, tt);
+    }
     rc = after_launch();
   }
   pool_free(ws, st);

@@ -55,8 +55,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + OFF_BAR + 96);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t qt = q_tiles - 1u - blockIdx.x; // long (late) query tiles first
-  const uint32_t bh = blockIdx.y;
+  // blockIdx.x = (b,h), blockIdx.y counts query tiles from the last one: under a causal mask tile qt
+  // costs qt + 1 key tiles, and blocks are dispatched in linear order, so the longest tiles of ALL
+  // heads start first and the short ones fill the tail (longest-processing-time-first)
+  const uint32_t qt = q_tiles - 1u - blockIdx.y;
+  const uint32_t bh = blockIdx.x;
   const uint32_t q0 = qt * TQ;
   const uint32_t nk = causal ? (qt + 1u) : ((T + TK - 1) / TK);
 
@@ -143,6 +146,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t r = warp * 32 + lane;           // row inside the tile == TMEM lane
     const uint32_t qg = q0 + r;                    // global query index
     const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
+    const float sc = scale_log2;
     float m = -INFINITY, l = 0.0f, alpha_prev = 0.0f;
     float acc[HD];
 #pragma unroll
@@ -150,25 +154,43 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
     for (uint32_t j = 0; j < nk; ++j) {
       const uint32_t k0 = j * TK;
-      const bool edge = (causal && j == qt) || (k0 + TK > T); // tile that needs per-element masking
+      // Only the diagonal tile (causal) and a ragged last key tile need per-element masking; every
+      // other tile runs the mask-free instantiation (no predicates, no branches in the inner loops).
+      const bool edge = (causal && j == qt) || (k0 + TK > T);
+      // keys k0 + c with c < lim are visible to this row: causal -> kg <= qg, ragged -> kg < T
+      uint32_t lim = TK;
+      if (edge) {
+        const uint32_t by_t = (T > k0) ? (T - k0) : 0u;
+        const uint32_t by_q = causal ? ((qg >= k0) ? (qg - k0 + 1u) : 0u) : TK;
+        lim = min(min(by_t, by_q), TK);
+      }
       mbar_wait(s_full, j & 1u);
       tcgen05_fence_after();
-      // pass 1: row maximum of t = s * log2(e) / divisor over the unmasked keys
-      float mx = -INFINITY;
+      // pass 1: row maximum of the raw scores over the visible keys (the scale is positive, so it is
+      // applied once to the maximum); four independent chains
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < TK; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + TMEM_S + c0, v);
         tmem_ld_wait();
+        if (edge) {
 #pragma unroll
-        for (uint32_t c = 0; c < 32; ++c) {
-          const uint32_t kg = k0 + c0 + c;
-          const bool masked = edge && ((causal && kg > qg) || kg >= T);
-          if (!masked) mx = fmaxf(mx, __uint_as_float(v[c]) * scale_log2);
+          for (uint32_t c = 0; c < 32; ++c)
+            if (c0 + c >= lim) v[c] = 0xff800000u; // -inf
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 32; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(v[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = (m_new == -INFINITY) ? 0.0f : ex2(m - m_new); // m = -inf -> 0
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+      float m_new = fmaxf(m, mx);
+      if (m_new == -INFINITY) m_new = 0.0f;       // nothing visible yet: every p below is 2^(-inf) = 0
+      const float alpha = ex2(m - m_new);         // m = -inf -> 0
       // fold the previous key tile's product into the accumulator (also frees P for rewriting)
       if (j > 0) {
         mbar_wait(o_full, (j - 1u) & 1u);
@@ -182,20 +204,29 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (uint32_t c = 0; c < 32; ++c) acc[c0 + c] = acc[c0 + c] * alpha_prev + __uint_as_float(v[c]);
         }
       }
-      // pass 2: p = 2^(t - m_new), row sum, P -> shared memory (bf16, swizzled K-major)
-      float rs = 0.0f;
+      // pass 2: p = 2^(s*sc - m_new), row sum, P -> shared memory (bf16, swizzled K-major)
+      float rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, rs3 = 0.0f;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < TK; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + TMEM_S + c0, v);
         tmem_ld_wait();
+        if (edge) {
+#pragma unroll
+          for (uint32_t c = 0; c < 32; ++c)
+            if (c0 + c >= lim) v[c] = 0xff800000u; // -inf -> p = 0
+        }
         float pv[32];
 #pragma unroll
-        for (uint32_t c = 0; c < 32; ++c) {
-          const uint32_t kg = k0 + c0 + c;
-          const bool masked = edge && ((causal && kg > qg) || kg >= T);
-          pv[c] = (masked || m_new == -INFINITY) ? 0.0f : ex2(__uint_as_float(v[c]) * scale_log2 - m_new);
-          rs += pv[c];
+        for (uint32_t c = 0; c < 32; c += 4) {
+          pv[c] = ex2(fmaf(__uint_as_float(v[c]), sc, -m_new));
+          pv[c + 1] = ex2(fmaf(__uint_as_float(v[c + 1]), sc, -m_new));
+          pv[c + 2] = ex2(fmaf(__uint_as_float(v[c + 2]), sc, -m_new));
+          pv[c + 3] = ex2(fmaf(__uint_as_float(v[c + 3]), sc, -m_new));
+          rs0 += pv[c];
+          rs1 += pv[c + 1];
+          rs2 += pv[c + 2];
+          rs3 += pv[c + 3];
         }
         const uint32_t atom = c0 >> 6;                 // 64-key swizzle atom
         const uint32_t chunk0 = (c0 & 63u) >> 3;       // first 16-byte chunk of this group inside the 128-B row
@@ -208,7 +239,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           st_shared_v4(row_addr + (((chunk0 + g) ^ (r & 7u)) << 4), *reinterpret_cast<const uint4 *>(h));
         }
       }
-      l = l * alpha + rs;
+      l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_new;
       alpha_prev = alpha;
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -254,8 +285,8 @@ int launch_flash_attn_fwd(const uint16_t *qh, const uint16_t *kh, const uint16_t
   ensure_dynamic_smem((const void *)flash_attn_fwd_kernel, (int)SMEM_BYTES);
   // FLOP of the products actually issued (causal: key tiles up to the diagonal only)
   const double tiles = causal ? 0.5 * q_tiles * (q_tiles + 1.0) : (double)q_tiles * ((T + TK - 1) / TK);
-  ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * 2.0 * TQ * TK * HD * tiles * BH);
-  flash_attn_fwd_kernel<<<dim3(q_tiles, BH), NTHREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, oc, T, q_tiles,
+  ProfScope prof(WEEDCU_PROF_ATTENTION, st, 2.0 * 2.0 * TQ * TK * HD * tiles * BH);
+  flash_attn_fwd_kernel<<<dim3(BH, q_tiles), NTHREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, oc, T, q_tiles,
                                                                          1.4426950408889634f / divisor, causal);
   return after_launch();
 }

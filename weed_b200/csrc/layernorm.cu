@@ -10,314 +10,288 @@
 
 namespace weedcu {
 
-constexpr size_t kLnMaxTileBytes = 160 * 1024;
+// Both directions are split into streaming passes, because a tile kernel that loads, reduces,
+// synchronises and only then stores is latency-bound here (ncu: 0.9 TB/s of DRAM traffic with the
+// SMs 70 % idle): the normalised axis is the SLOWEST one, so per-row statistics need a cross-warp
+// reduction per row tile while everything else is plain elementwise work.
+//   pass 1 (row statistics)  block = 32 adjacent rows x BY warps striding the features: every
+//                            warp-level load is one full 128-byte line; writes 2-3 floats per row
+//   pass 2 (apply)           block = 256 x 4 adjacent rows x FB features: 128-bit loads/stores, the
+//                            per-row coefficients stay in registers across the FB features, the
+//                            second read of x (and dy) is served by the 126 MB L2
+// HBM traffic stays at the algorithmic 8 B/elem forward and 12-16 B/elem backward.
+constexpr int kLnBY = 16; // warps per row tile in the statistics kernels
+constexpr int kLnFB = 8;  // features per block in the apply kernels
 
-// Loads are issued in batches of U independent requests per thread before anything consumes them:
-// with one 4-byte load in flight per thread these kernels are latency-bound, not bandwidth-bound.
-template <int RT, int NT, bool STAGED>
-__global__ void __launch_bounds__(NT)
-layernorm_fwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
-                     const float *__restrict__ beta, float eps, float *__restrict__ y, float *__restrict__ mean,
-                     float *__restrict__ rstd) {
-  constexpr int BY = NT / RT, U = 8;
-  extern __shared__ float tile[]; // [F][RT]
-  __shared__ float red[BY][RT + 1];
-  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
-  const uint32_t r = blockIdx.x * RT + tx;
+// mean, (var + eps)^0.5 and its reciprocal per row. NV > 0: a thread keeps its <= NV features in
+// registers between the reference's two passes (mean, then mean of centred squares); NV == 0:
+// any F, the second pass re-reads x (L1/L2 hits).
+template <int NV>
+__global__ void __launch_bounds__(32 * kLnBY)
+layernorm_fwd_stats_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, float eps,
+                           float *__restrict__ mean, float *__restrict__ rstd, float *__restrict__ den_out) {
+  __shared__ float red[kLnBY][33];
+  const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 32u + tx;
   const bool live = r < rows;
   const float *p = x + r;
-
+  float v[NV > 0 ? NV : 1];
   float s = 0.0f;
-  if (live)
-    for (uint32_t f0 = ty; f0 < F; f0 += BY * U) {
-      float v[U];
+  if (NV > 0) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t f = f0 + u * BY;
-        v[u] = (f < F) ? p[(uint64_t)f * rows] : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t f = f0 + u * BY;
-        if (f < F) {
-          if (STAGED) tile[f * RT + tx] = v[u];
-          s += v[u];
-        }
-      }
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t f = ty + i * kLnBY;
+      v[i] = (live && f < F) ? p[(uint64_t)f * rows] : 0.0f;
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i];
+  } else if (live) {
+    for (uint32_t f0 = ty; f0 < F; f0 += 4 * kLnBY) {
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = (f0 + u * kLnBY < F) ? p[(uint64_t)(f0 + u * kLnBY) * rows] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s += t[u];
+    }
+  }
   red[ty][tx] = s;
   __syncthreads();
   s = 0.0f;
 #pragma unroll
-  for (int k = 0; k < BY; ++k) s += red[k][tx];
+  for (int k = 0; k < kLnBY; ++k) s += red[k][tx];
   const float mu = s / (float)F;
   __syncthreads();
-
   float q = 0.0f;
-  if (live)
-    for (uint32_t f = ty; f < F; f += BY) {
-      const float xc = (STAGED ? tile[f * RT + tx] : p[(uint64_t)f * rows]) - mu;
-      q += xc * xc;
+  if (NV > 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float xc = v[i] - mu;
+      if (ty + i * kLnBY < F) q += xc * xc;
     }
+  } else if (live) {
+    for (uint32_t f0 = ty; f0 < F; f0 += 4 * kLnBY) {
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = (f0 + u * kLnBY < F) ? p[(uint64_t)(f0 + u * kLnBY) * rows] : mu;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xc = t[u] - mu;
+        q += xc * xc;
+      }
+    }
+  }
   red[ty][tx] = q;
   __syncthreads();
-  q = 0.0f;
+  if (ty == 0 && live) {
+    q = 0.0f;
 #pragma unroll
-  for (int k = 0; k < BY; ++k) q += red[k][tx];
-  const float den = sqrtf(q / (float)F + eps); // (var + eps) ^ 0.5, layernorm.cpp:35
-  if (live) {
-    if (ty == 0) {
-      if (mean) mean[r] = mu;
-      if (rstd) rstd[r] = 1.0f / den;
+    for (int k = 0; k < kLnBY; ++k) q += red[k][tx];
+    const float den = sqrtf(q / (float)F + eps); // (var + eps) ^ 0.5, layernorm.cpp:35
+    if (mean) mean[r] = mu;
+    if (rstd) rstd[r] = 1.0f / den;
+    den_out[r] = den;
+    if (!mean) den_out[rows + r] = mu; // the apply pass needs mu even when the caller does not
+  }
+}
+
+// y = ((x - mu) / den) * gamma + beta for VEC adjacent rows x kLnFB features per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_apply_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
+                           const float *__restrict__ beta, const float *__restrict__ mean,
+                           const float *__restrict__ den, float *__restrict__ y) {
+  const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
+  if (r >= rows) return;
+  float mu[VEC], dn[VEC];
+  if (VEC == 4) {
+    *reinterpret_cast<float4 *>(mu) = *reinterpret_cast<const float4 *>(mean + r);
+    *reinterpret_cast<float4 *>(dn) = *reinterpret_cast<const float4 *>(den + r);
+  } else {
+    mu[0] = mean[r];
+    dn[0] = den[r];
+  }
+  const uint32_t f_begin = blockIdx.y * kLnFB, f_end = min(F, f_begin + kLnFB);
+  float xv[kLnFB][VEC];
+#pragma unroll
+  for (int i = 0; i < kLnFB; ++i) {
+    const uint32_t f = f_begin + i;
+    if (f < f_end) {
+      const float *src = x + (uint64_t)f * rows + r;
+      if (VEC == 4) *reinterpret_cast<float4 *>(xv[i]) = *reinterpret_cast<const float4 *>(src);
+      else xv[i][0] = *src;
     }
-    float *py = y + r;
-#pragma unroll 4
-    for (uint32_t f = ty; f < F; f += BY) {
-      const float xc = (STAGED ? tile[f * RT + tx] : p[(uint64_t)f * rows]) - mu;
-      py[(uint64_t)f * rows] = (xc / den) * gamma[f] + beta[f];
+  }
+#pragma unroll
+  for (int i = 0; i < kLnFB; ++i) {
+    const uint32_t f = f_begin + i;
+    if (f < f_end) {
+      const float g = gamma[f], b = beta[f];
+      float o[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = ((xv[i][k] - mu[k]) / dn[k]) * g + b;
+      float *dst = y + (uint64_t)f * rows + r;
+      if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
+      else *dst = o[0];
     }
   }
 }
 
-// dx (+)= rstd*(g - mean_f(g) - xhat*mean_f(g*xhat)), g = dy*gamma, xhat = (x-mean)*rstd.
-// Persistent over row tiles; column sums of dy*xhat and dy accumulate in shared memory and leave
-// as one partial row per block: part_g/part_b[blockIdx][F].
-template <int RT, int NT, bool STAGED>
-__global__ void __launch_bounds__(NT)
-layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
-                     const float *__restrict__ gamma, const float *__restrict__ mean,
-                     const float *__restrict__ rstd, float *dx, float *__restrict__ part_g,
-                     float *__restrict__ part_b, int grad_mode, int accumulate, uint32_t ntiles) {
-  constexpr int BY = NT / RT, U = 4;
-  extern __shared__ float tile[]; // colg [F], colb [F], then (STAGED) xhat [F][RT], dy [F][RT]
-  __shared__ float red_a[BY][RT + 1];
-  __shared__ float red_b[BY][RT + 1];
-  float *colg = tile, *colb = tile + F, *t_xh = tile + 2 * (size_t)F, *t_dy = t_xh + (size_t)F * RT;
-  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
-  for (uint32_t f = threadIdx.x; f < F; f += NT) colg[f] = colb[f] = 0.0f;
-
-  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const uint32_t r = t * RT + tx;
-    const bool live = r < rows;
-    const float mu = live ? mean[r] : 0.0f, rs = live ? rstd[r] : 0.0f;
-    float sg = 0.0f, sgx = 0.0f;
-    for (uint32_t f0 = ty; f0 < F; f0 += BY * U) {
+// Backward pass 1: sg = sum_f dy*gamma, sgx = sum_f g*xhat (mode 1) or sum_f xhat (mode 0) per row,
+// folded straight into the two per-row coefficients of
+//     dx (+)= (rstd * (dy*gamma) + k_x * xhat) + k_0
+// mode 1 (analytic):   dx += rs*(g - mean(g) - xh*mean(g*xh))
+// mode 0 (reference chain, see weedcu.h): dxc = g*rs + c*xc with c = -rs^3*sum(xc)/F;
+//                         dx += dxc - mean(dxc).  In xhat terms xc = xh/rs, sum(xc) = sgx/rs.
+__global__ void __launch_bounds__(32 * kLnBY)
+layernorm_bwd_rows_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
+                          const float *__restrict__ gamma, const float *__restrict__ mean,
+                          const float *__restrict__ rstd, float *__restrict__ k_x_out, float *__restrict__ k_0_out,
+                          int grad_mode) {
+  __shared__ float red_a[kLnBY][33];
+  __shared__ float red_b[kLnBY][33];
+  const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 32u + tx;
+  const bool live = r < rows;
+  const float mu = live ? mean[r] : 0.0f, rs = live ? rstd[r] : 0.0f;
+  float sg = 0.0f, sgx = 0.0f;
+  if (live) {
+    constexpr int U = 4;
+    for (uint32_t f0 = ty; f0 < F; f0 += U * kLnBY) {
       float xv[U], dv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t f = f0 + u * BY;
-        const bool ok = live && f < F;
+        const uint32_t f = f0 + u * kLnBY;
+        const bool ok = f < F;
         xv[u] = ok ? x[r + (uint64_t)f * rows] : mu;
         dv[u] = ok ? dy[r + (uint64_t)f * rows] : 0.0f;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t f = f0 + u * BY;
+        const uint32_t f = f0 + u * kLnBY;
         if (f < F) {
           const float xh = (xv[u] - mu) * rs;
-          if (STAGED) {
-            t_xh[f * RT + tx] = xh;
-            t_dy[f * RT + tx] = dv[u];
-          }
           const float g = dv[u] * gamma[f];
           sg += g;
-          sgx += grad_mode ? g * xh : xh; // mode 0 needs sum_f(xc) = sum_f(xhat)/rstd instead
+          sgx += grad_mode ? g * xh : xh;
         }
       }
     }
-    red_a[ty][tx] = sg;
-    red_b[ty][tx] = sgx;
-    __syncthreads();
+  }
+  red_a[ty][tx] = sg;
+  red_b[ty][tx] = sgx;
+  __syncthreads();
+  if (ty == 0 && live) {
     sg = sgx = 0.0f;
 #pragma unroll
-    for (int k = 0; k < BY; ++k) {
+    for (int k = 0; k < kLnBY; ++k) {
       sg += red_a[k][tx];
       sgx += red_b[k][tx];
     }
-    // mode 1 (analytic):   dx += rs*(g - mean(g) - xh*mean(g*xh))
-    // mode 0 (reference chain, see weedcu.h): dxc = g*rs + c*xc with c = -rs^3*sum(xc)/F;
-    //                         dx += dxc - mean(dxc).  In xhat terms xc = xh/rs, sum(xc) = sgx/rs.
-    float k_g, k_x, k_0;
+    float k_x, k_0;
     if (grad_mode) {
-      k_g = rs;
       k_x = -rs * (sgx / (float)F);
       k_0 = -rs * (sg / (float)F);
     } else {
       const float sx = (rs != 0.0f) ? sgx / rs : 0.0f;
       const float c = -(rs * rs * rs) * sx / (float)F;
-      k_g = rs;
       k_x = (rs != 0.0f) ? c / rs : 0.0f;
       k_0 = -((rs * sg + c * sx) / (float)F);
     }
-#pragma unroll 2
-    for (uint32_t f0 = 0; f0 < F; f0 += BY) { // uniform trip count: the shuffles below need it
-      const uint32_t f = f0 + ty;
-      const bool fv = f < F;
-      float xh = 0.0f, d = 0.0f;
-      if (fv) {
-        if (STAGED) {
-          xh = t_xh[f * RT + tx];
-          d = t_dy[f * RT + tx];
-        } else if (live) {
-          xh = (x[r + (uint64_t)f * rows] - mu) * rs;
-          d = dy[r + (uint64_t)f * rows];
-        }
-      }
-      // column partials over the RT rows of this tile (lanes tx of one ty share f)
-      float cg = d * xh, cb = d;
-#pragma unroll
-      for (int o = RT / 2; o > 0; o >>= 1) {
-        cg += __shfl_xor_sync(0xffffffffu, cg, o, RT);
-        cb += __shfl_xor_sync(0xffffffffu, cb, o, RT);
-      }
-      if (tx == 0 && fv) { // (ty, f0) owns column f: no two threads touch the same slot
-        colg[f] += cg;
-        colb[f] += cb;
-      }
-      if (live && fv) {
-        const float val = (k_g * (d * gamma[f]) + k_x * xh) + k_0;
-        float *o = dx + r + (uint64_t)f * rows;
-        *o = accumulate ? (*o + val) : val;
-      }
-    }
-    __syncthreads(); // the next tile reuses the staging tile and the reduction scratch
-  }
-  for (uint32_t f = threadIdx.x; f < F; f += NT) {
-    part_g[(uint64_t)blockIdx.x * F + f] = colg[f];
-    part_b[(uint64_t)blockIdx.x * F + f] = colb[f];
+    k_x_out[r] = k_x;
+    k_0_out[r] = k_0;
   }
 }
 
-// Register-resident variants for F <= BY*NV: a thread keeps its NV features of one row in registers,
-// so every global load of the tile is in flight at once and nothing is staged in shared memory.
-template <int RT, int BY, int NV>
-__global__ void __launch_bounds__(RT *BY)
-layernorm_fwd_reg_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
-                         const float *__restrict__ beta, float eps, float *__restrict__ y,
-                         float *__restrict__ mean, float *__restrict__ rstd) {
-  __shared__ float red[BY][RT + 1];
-  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
-  const uint32_t r = blockIdx.x * RT + tx;
+// Backward pass 2: dx for 256 x VEC adjacent rows x kLnFB features per block, and the block's share
+// of the column sums dgamma_f = sum_r dy*xhat, dbeta_f = sum_r dy, which leave as one partial row per
+// row chunk: part_g/part_b[blockIdx.x][F] (summed in a fixed order by layernorm_param_reduce_kernel).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
+                           const float *__restrict__ gamma, const float *__restrict__ mean,
+                           const float *__restrict__ rstd, const float *__restrict__ k_x, const float *__restrict__ k_0,
+                           float *dx, float *__restrict__ part_g, float *__restrict__ part_b, int accumulate) {
+  __shared__ float red[8][2 * kLnFB];
+  const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   const bool live = r < rows;
-  float v[NV];
+  float mu[VEC], rs[VEC], kx[VEC], k0[VEC];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t f = ty + i * BY;
-    v[i] = (live && f < F) ? x[r + (uint64_t)f * rows] : 0.0f;
-  }
-  float s = 0.0f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s += v[i];
-  red[ty][tx] = s;
-  __syncthreads();
-  s = 0.0f;
-#pragma unroll
-  for (int k = 0; k < BY; ++k) s += red[k][tx];
-  const float mu = s / (float)F;
-  __syncthreads();
-  float q = 0.0f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float xc = v[i] - mu;
-    if (ty + i * BY < F) q += xc * xc;
-  }
-  red[ty][tx] = q;
-  __syncthreads();
-  q = 0.0f;
-#pragma unroll
-  for (int k = 0; k < BY; ++k) q += red[k][tx];
-  const float den = sqrtf(q / (float)F + eps); // (var + eps) ^ 0.5, layernorm.cpp:35
-  if (!live) return;
-  if (ty == 0) {
-    if (mean) mean[r] = mu;
-    if (rstd) rstd[r] = 1.0f / den;
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t f = ty + i * BY;
-    if (f < F) y[r + (uint64_t)f * rows] = ((v[i] - mu) / den) * gamma[f] + beta[f];
-  }
-}
-
-template <int RT, int BY, int NV>
-__global__ void __launch_bounds__(RT *BY, (NV <= 24) ? 2 : 1)
-layernorm_bwd_reg_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
-                         const float *__restrict__ gamma, const float *__restrict__ mean,
-                         const float *__restrict__ rstd, float *dx, float *__restrict__ part_g,
-                         float *__restrict__ part_b, int grad_mode, int accumulate, uint32_t ntiles) {
-  extern __shared__ float tile[]; // colg [F], colb [F]
-  __shared__ float red_a[BY][RT + 1];
-  __shared__ float red_b[BY][RT + 1];
-  float *colg = tile, *colb = tile + F;
-  const uint32_t tx = threadIdx.x % RT, ty = threadIdx.x / RT;
-  for (uint32_t f = threadIdx.x; f < F; f += RT * BY) colg[f] = colb[f] = 0.0f;
-
-  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const uint32_t r = t * RT + tx;
-    const bool live = r < rows;
-    const float mu = live ? mean[r] : 0.0f, rs = live ? rstd[r] : 0.0f;
-    float xh[NV], d[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint32_t f = ty + i * BY;
-      const bool ok = live && f < F;
-      xh[i] = ok ? x[r + (uint64_t)f * rows] : mu;
-      d[i] = ok ? dy[r + (uint64_t)f * rows] : 0.0f;
-    }
-    float sg = 0.0f, sgx = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint32_t f = ty + i * BY;
-      xh[i] = (xh[i] - mu) * rs;
-      const float g = (f < F) ? d[i] * gamma[f] : 0.0f;
-      sg += g;
-      sgx += grad_mode ? g * xh[i] : xh[i]; // mode 0 needs sum_f(xc) = sum_f(xhat)/rstd instead
-    }
-    red_a[ty][tx] = sg;
-    red_b[ty][tx] = sgx;
-    __syncthreads();
-    sg = sgx = 0.0f;
-#pragma unroll
-    for (int k = 0; k < BY; ++k) {
-      sg += red_a[k][tx];
-      sgx += red_b[k][tx];
-    }
-    float k_g, k_x, k_0; // see layernorm_bwd_kernel
-    if (grad_mode) {
-      k_g = rs;
-      k_x = -rs * (sgx / (float)F);
-      k_0 = -rs * (sg / (float)F);
+  for (int k = 0; k < VEC; ++k) mu[k] = rs[k] = kx[k] = k0[k] = 0.0f;
+  if (live) {
+    if (VEC == 4) {
+      *reinterpret_cast<float4 *>(mu) = *reinterpret_cast<const float4 *>(mean + r);
+      *reinterpret_cast<float4 *>(rs) = *reinterpret_cast<const float4 *>(rstd + r);
+      *reinterpret_cast<float4 *>(kx) = *reinterpret_cast<const float4 *>(k_x + r);
+      *reinterpret_cast<float4 *>(k0) = *reinterpret_cast<const float4 *>(k_0 + r);
     } else {
-      const float sx = (rs != 0.0f) ? sgx / rs : 0.0f;
-      const float c = -(rs * rs * rs) * sx / (float)F;
-      k_g = rs;
-      k_x = (rs != 0.0f) ? c / rs : 0.0f;
-      k_0 = -((rs * sg + c * sx) / (float)F);
+      mu[0] = mean[r];
+      rs[0] = rstd[r];
+      kx[0] = k_x[r];
+      k0[0] = k_0[r];
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint32_t f = ty + i * BY;
-      float cg = d[i] * xh[i], cb = d[i];
-#pragma unroll
-      for (int w = RT / 2; w > 0; w >>= 1) {
-        cg += __shfl_xor_sync(0xffffffffu, cg, w, RT);
-        cb += __shfl_xor_sync(0xffffffffu, cb, w, RT);
-      }
-      if (tx == 0 && f < F) { // (ty, i) owns column f
-        colg[f] += cg;
-        colb[f] += cb;
-      }
-      if (live && f < F) {
-        const float val = (k_g * (d[i] * gamma[f]) + k_x * xh[i]) + k_0;
-        float *o = dx + r + (uint64_t)f * rows;
-        *o = accumulate ? (*o + val) : val;
-      }
-    }
-    __syncthreads(); // red_a / red_b are reused by the next tile
   }
-  for (uint32_t f = threadIdx.x; f < F; f += RT * BY) {
-    part_g[(uint64_t)blockIdx.x * F + f] = colg[f];
-    part_b[(uint64_t)blockIdx.x * F + f] = colb[f];
+  const uint32_t f_begin = blockIdx.y * kLnFB, f_end = min(F, f_begin + kLnFB);
+  float cg[kLnFB], cb[kLnFB];
+#pragma unroll
+  for (int i = 0; i < kLnFB; ++i) cg[i] = cb[i] = 0.0f;
+  if (live) {
+    constexpr int U = 4; // features whose loads are in flight together
+#pragma unroll
+    for (int i0 = 0; i0 < kLnFB; i0 += U) {
+      float xv[U][VEC], dv[U][VEC], ov[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t f = f_begin + i0 + u;
+        if (f < f_end) {
+          const uint64_t off = (uint64_t)f * rows + r;
+          if (VEC == 4) {
+            *reinterpret_cast<float4 *>(xv[u]) = *reinterpret_cast<const float4 *>(x + off);
+            *reinterpret_cast<float4 *>(dv[u]) = *reinterpret_cast<const float4 *>(dy + off);
+            if (accumulate) *reinterpret_cast<float4 *>(ov[u]) = *reinterpret_cast<const float4 *>(dx + off);
+          } else {
+            xv[u][0] = x[off];
+            dv[u][0] = dy[off];
+            if (accumulate) ov[u][0] = dx[off];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t f = f_begin + i0 + u;
+        if (f < f_end) {
+          const float gm = gamma[f];
+          float o[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float xh = (xv[u][k] - mu[k]) * rs[k];
+            const float val = (rs[k] * (dv[u][k] * gm) + kx[k] * xh) + k0[k];
+            o[k] = accumulate ? (ov[u][k] + val) : val;
+            cg[i0 + u] += dv[u][k] * xh;
+            cb[i0 + u] += dv[u][k];
+          }
+          float *dst = dx + (uint64_t)f * rows + r;
+          if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
+          else *dst = o[0];
+        }
+      }
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kLnFB; ++i) {
+    const float a = warp_sum(cg[i]), b = warp_sum(cb[i]);
+    if (lane == 0) {
+      red[warp][i] = a;
+      red[warp][kLnFB + i] = b;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kLnFB) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const uint32_t i = threadIdx.x % kLnFB, f = f_begin + i;
+    if (f < f_end) (threadIdx.x < kLnFB ? part_g : part_b)[(uint64_t)blockIdx.x * F + f] = t;
   }
 }
 
@@ -384,46 +358,6 @@ triu_fill_kernel(float *a, uint32_t t0, uint32_t t1, uint32_t s0, uint32_t s1, f
   }
 }
 
-template <int RT, int NT>
-static int ln_fwd_launch(const float *x, uint32_t rows, uint32_t F, const float *gamma,
-                         const float *beta, float eps, float *y, float *mean, float *rstd,
-                         cudaStream_t st) {
-  const unsigned grid = (rows + RT - 1) / RT;
-  const size_t bytes = (size_t)F * RT * sizeof(float);
-  if (bytes <= kLnMaxTileBytes) {
-    auto k = layernorm_fwd_kernel<RT, NT, true>;
-    ensure_dynamic_smem((const void *)k, (int)kLnMaxTileBytes);
-    k<<<grid, NT, bytes, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-  } else {
-    layernorm_fwd_kernel<RT, NT, false><<<grid, NT, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-  }
-  return after_launch();
-}
-template <int RT, int NT>
-static int ln_bwd_launch(const float *x, const float *dy, uint32_t rows, uint32_t F,
-                         const float *gamma, const float *mean, const float *rstd, float *dx,
-                         float *pg, float *pb, int grad_mode, int accumulate, uint32_t nblocks,
-                         cudaStream_t st) {
-  const uint32_t ntiles = (rows + RT - 1) / RT;
-  const size_t col_bytes = 2 * (size_t)F * sizeof(float);
-  const size_t bytes = col_bytes + 2 * (size_t)F * RT * sizeof(float);
-  if (bytes <= kLnMaxTileBytes) {
-    auto k = layernorm_bwd_kernel<RT, NT, true>;
-    ensure_dynamic_smem((const void *)k, (int)kLnMaxTileBytes);
-    k<<<nblocks, NT, bytes, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, accumulate, ntiles);
-  } else {
-    auto k = layernorm_bwd_kernel<RT, NT, false>;
-    ensure_dynamic_smem((const void *)k, (int)kLnMaxTileBytes);
-    k<<<nblocks, NT, col_bytes, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, accumulate, ntiles);
-  }
-  return after_launch();
-}
-static int pick_rt(uint32_t rows) {
-  if (rows / 32 >= 4 * kNumSMs) return 32;
-  if (rows / 16 >= 2 * kNumSMs) return 16;
-  return 8;
-}
-
 } // namespace weedcu
 
 using namespace weedcu;
@@ -435,59 +369,64 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
                          void *stream) {
   if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
+  float *tmp = nullptr; // den[rows] (+ mu[rows] when the caller does not keep the mean)
+  WCU_CHECK(pool_alloc((void **)&tmp, sizeof(float) * 2 * (size_t)rows, st));
   ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
-  if (F <= 32 * 32) { // register-resident rows: 8 rows x 32 feature lanes per block
-    const unsigned grid = (rows + 7) / 8;
-    if (F <= 32 * 8) layernorm_fwd_reg_kernel<8, 32, 8><<<grid, 256, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-    else if (F <= 32 * 16) layernorm_fwd_reg_kernel<8, 32, 16><<<grid, 256, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-    else if (F <= 32 * 24) layernorm_fwd_reg_kernel<8, 32, 24><<<grid, 256, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-    else layernorm_fwd_reg_kernel<8, 32, 32><<<grid, 256, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd);
-    return after_launch();
+  const unsigned tiles = (rows + 31u) / 32u;
+#define WCU_LN_STATS(NV) layernorm_fwd_stats_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, eps, mean, rstd, tmp)
+  if (F <= kLnBY * 16) WCU_LN_STATS(16);
+  else if (F <= kLnBY * 32) WCU_LN_STATS(32);
+  else if (F <= kLnBY * 48) WCU_LN_STATS(48);
+  else if (F <= kLnBY * 64) WCU_LN_STATS(64);
+  else WCU_LN_STATS(0);
+#undef WCU_LN_STATS
+  int rc = after_launch();
+  if (rc == 0) {
+    const float *mu = mean ? mean : tmp + rows;
+    const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
+    if ((rows % 4u) == 0 && aligned16(x) && aligned16(y) && aligned16(mu) && fgroups <= 65535u) {
+      layernorm_fwd_apply_kernel<4><<<dim3((rows / 4u + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y);
+    } else if (fgroups <= 65535u) {
+      layernorm_fwd_apply_kernel<1><<<dim3((rows + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y);
+    } else {
+      rc = WEEDCU_EINVAL;
+    }
+    if (rc == 0) rc = after_launch();
   }
-  switch (pick_rt(rows)) {
-  case 32: return ln_fwd_launch<32, 512>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
-  case 16: return ln_fwd_launch<16, 256>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
-  default: return ln_fwd_launch<8, 256>(x, rows, F, gamma, beta, eps, y, mean, rstd, st);
-  }
+  pool_free(tmp, st);
+  return rc;
 }
 
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
                          float *dgamma, float *dbeta, int grad_mode, int accumulate, void *stream) {
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !rows || !F) return WEEDCU_EINVAL;
-  if (2 * (size_t)F * sizeof(float) > kLnMaxTileBytes) return WEEDCU_EINVAL;
+  const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
+  if (fgroups > 65535u) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
-  const bool reg = F <= 32 * 32;
-  const int rt = reg ? 8 : pick_rt(rows);
-  const uint32_t ntiles = (rows + rt - 1) / rt;
-  const uint32_t nblocks = ntiles < 4u * kNumSMs ? ntiles : 4u * kNumSMs;
-  float *part = nullptr;
-  WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * 2 * (size_t)nblocks * F, st));
-  float *pg = part, *pb = part + (size_t)nblocks * F;
+  const bool vec = (rows % 4u) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd);
+  const uint32_t rows_per_block = vec ? 1024u : 256u;
+  const uint32_t nchunks = (rows + rows_per_block - 1) / rows_per_block;
+  // scratch: k_x[rows], k_0[rows] (rounded up to keep 16-byte alignment), part_g / part_b [nchunks][F]
+  const size_t rows_up = ((size_t)rows + 3) & ~(size_t)3;
+  float *scratch = nullptr;
+  WCU_CHECK(pool_alloc((void **)&scratch, sizeof(float) * (2 * rows_up + 2 * (size_t)nchunks * F), st));
+  float *kx = scratch, *k0 = scratch + rows_up, *pg = k0 + rows_up, *pb = pg + (size_t)nchunks * F;
   ProfScope prof(WEEDCU_PROF_LAYERNORM, st, (accumulate ? 16.0 : 12.0) * (double)rows * F);
-  int rc;
-  if (reg) {
-    const size_t cb = 2 * (size_t)F * sizeof(float);
-#define WCU_LN_BWD_REG(NV)                                                                          \
-  layernorm_bwd_reg_kernel<8, 32, NV><<<nblocks, 256, cb, st>>>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, \
-                                                                 accumulate, ntiles)
-    if (F <= 32 * 8) WCU_LN_BWD_REG(8);
-    else if (F <= 32 * 16) WCU_LN_BWD_REG(16);
-    else if (F <= 32 * 24) WCU_LN_BWD_REG(24);
-    else WCU_LN_BWD_REG(32);
-#undef WCU_LN_BWD_REG
+  layernorm_bwd_rows_kernel<<<(rows + 31u) / 32u, 32 * kLnBY, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, grad_mode);
+  int rc = after_launch();
+  if (rc == 0) {
+    if (vec)
+      layernorm_bwd_apply_kernel<4><<<dim3(nchunks, fgroups), 256, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
+    else
+      layernorm_bwd_apply_kernel<1><<<dim3(nchunks, fgroups), 256, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
     rc = after_launch();
-  } else
-  switch (rt) {
-  case 32: rc = ln_bwd_launch<32, 512>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, accumulate, nblocks, st); break;
-  case 16: rc = ln_bwd_launch<16, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, accumulate, nblocks, st); break;
-  default: rc = ln_bwd_launch<8, 256>(x, dy, rows, F, gamma, mean, rstd, dx, pg, pb, grad_mode, accumulate, nblocks, st); break;
   }
   if (rc == 0 && (dgamma || dbeta)) {
-    layernorm_param_reduce_kernel<<<(F + 31) / 32, 256, 0, st>>>(pg, pb, nblocks, F, dgamma, dbeta);
+    layernorm_param_reduce_kernel<<<(F + 31) / 32, 256, 0, st>>>(pg, pb, nchunks, F, dgamma, dbeta);
     rc = after_launch();
   }
-  pool_free(part, st);
+  pool_free(scratch, st);
   return rc;
 }
 

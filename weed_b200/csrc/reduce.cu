@@ -95,6 +95,53 @@ reduce_contig_kernel(const float *__restrict__ a, uint32_t L, float *__restrict_
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// Short contiguous axis (L <= 32, e.g. the batch sum behind a broadcast positional-encoding
+// gradient: [B, T*d] over B = 8): one thread per output walks its L consecutive elements in the
+// reference's serial order; adjacent threads read adjacent 4L-byte runs, so the warp's loads cover
+// one dense span (128-bit loads when L % 4 == 0).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+reduce_contig_short_kernel(const float *__restrict__ a, uint32_t L, uint32_t n_out, float *__restrict__ out) {
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const float *p = a + (uint64_t)o * L;
+  float s = 0.0f;
+  if (VEC) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    for (uint32_t i = 0; i < (L >> 2); ++i) {
+      const float4 v = q[i];
+      s += v.x;
+      s += v.y;
+      s += v.z;
+      s += v.w;
+    }
+  } else {
+    for (uint32_t i = 0; i < L; ++i) s += p[i];
+  }
+  out[o] = s;
+}
+// Medium contiguous axis (32 < L < 2048): one warp per output, 8 outputs per block.
+__global__ void __launch_bounds__(256)
+reduce_contig_warp_kernel(const float *__restrict__ a, uint32_t L, uint32_t n_out, float *__restrict__ out) {
+  const uint32_t o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= n_out) return;
+  const float *p = a + (uint64_t)o * L;
+  float s = 0.0f;
+  if ((((uintptr_t)p) & 15u) == 0) {
+    const uint32_t nq = L >> 2;
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    for (uint32_t i = lane; i < nq; i += 32) {
+      const float4 v = q[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    for (uint32_t i = (nq << 2) + lane; i < L; i += 32) s += p[i];
+  } else {
+    for (uint32_t i = lane; i < L; i += 32) s += p[i];
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[o] = s;
+}
+
 // reduce_grad, reference order (REDUCE_GRAD_HEAD, reduce.cpp:84-101): i is decomposed over the
 // NON-axis dims only, last dim fastest.
 template <int NOPS>
@@ -242,7 +289,17 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
   const bool order_free = (index_order == 0) || (big <= 1);
   if (order_free && canonical_contiguous(av, axis, inner, outer)) {
     if (inner == 1) {
-      reduce_contig_kernel<<<(unsigned)outer, 256, 0, st>>>(base, L, out);
+      if (L <= 32) {
+        const unsigned blocks = (unsigned)((outer + 255) / 256);
+        if ((L % 4u) == 0 && aligned16(base))
+          reduce_contig_short_kernel<true><<<blocks, 256, 0, st>>>(base, L, (uint32_t)outer, out);
+        else
+          reduce_contig_short_kernel<false><<<blocks, 256, 0, st>>>(base, L, (uint32_t)outer, out);
+      } else if (L < 2048 && outer >= 2 * (uint64_t)kNumSMs) {
+        reduce_contig_warp_kernel<<<(unsigned)((outer + 7) / 8), 256, 0, st>>>(base, L, (uint32_t)outer, out);
+      } else {
+        reduce_contig_kernel<<<(unsigned)outer, 256, 0, st>>>(base, L, out);
+      }
       return after_launch();
     }
     if (inner >= 32 && outer <= 65535) {

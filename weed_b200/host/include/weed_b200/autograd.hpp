@@ -2,6 +2,7 @@
 // With backend_config().fused (default) adam_step / sgd_step / cross_entropy_loss issue one fused
 // kernel per parameter / per loss; with it off they compose the same tensor ops the reference does.
 #pragma once
+#include <unordered_set>
 #include "weed_b200/ops.hpp"
 
 namespace Weed {
@@ -35,5 +36,27 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets);
 // sum-all-reduced in place on the compute stream; the 1/world average is folded into the fused
 // optimiser kernels through backend_config().grad_scale.
 void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm);
+// The same reduction overlapped with the backward walk: gradients are collected into buckets of
+// ~bucket_bytes in the order they become final (Tensor::backward's on_leaf_grad_final hook: LM head
+// first, embeddings last) and every full bucket is all-reduced as one NCCL group on a dedicated
+// communication stream while the compute stream carries on with the remaining backward kernels.
+//   GradientBuckets gb(comm);  gb.begin();  Tensor::backward(loss);  gb.finish(params);
+// finish() reduces what is left (including gradients no node touched on this rank but may have on
+// another), and makes the compute stream wait for the communication stream.
+struct GradientBuckets {
+  void *comm;
+  size_t bucket_bytes;
+  void *comm_stream = nullptr, *ev_ready = nullptr, *ev_done = nullptr;
+  std::vector<Tensor *> pending;
+  size_t pending_bytes = 0U;
+  std::unordered_set<Tensor *> reduced;
+  uint64_t buckets_launched = 0U;
+  explicit GradientBuckets(void *c, size_t bytes = 32U << 20);
+  ~GradientBuckets();
+  void begin();
+  void add(Tensor *leaf);
+  void flush();
+  void finish(const std::vector<ParameterPtr> &params);
+};
 void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root);
 } // namespace Weed

@@ -75,6 +75,7 @@ struct bad_alloc : public std::bad_alloc {
 
 // ---------------------------------------------------------------------------------------------
 // Backend switches (process-global, like the reference's pfControl / engine singletons).
+struct Tensor;
 struct BackendConfig {
   // Fused device kernels behind Tensor::gelu, LayerNorm::forward, adam_step, sgd_step,
   // cross_entropy_loss, the attention core and matmul-backward accumulation. Off = every op is
@@ -91,6 +92,10 @@ struct BackendConfig {
   bool operand_cache = true;
   // FillZeros() on device buffers is deferred until something reads the buffer (fused mode only)
   bool lazy_zero = true;
+  // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
+  // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
+  // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)
+  std::function<void(Tensor *)> on_leaf_grad_final;
 };
 BackendConfig &backend_config();
 

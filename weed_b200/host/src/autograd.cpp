@@ -161,6 +161,71 @@ void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm) {
   }
   if (grouped) throw_on_error(weedcu_nccl_group_end(), "allreduce_gradients");
 }
+GradientBuckets::GradientBuckets(void *c, size_t bytes) : comm(c), bucket_bytes(bytes) {
+  throw_on_error(weedcu_stream_create(&comm_stream), "GradientBuckets");
+  throw_on_error(weedcu_event_create(&ev_ready), "GradientBuckets");
+  throw_on_error(weedcu_event_create(&ev_done), "GradientBuckets");
+}
+GradientBuckets::~GradientBuckets() {
+  backend_config().on_leaf_grad_final = nullptr;
+  if (ev_ready) weedcu_event_destroy(ev_ready);
+  if (ev_done) weedcu_event_destroy(ev_done);
+  if (comm_stream) weedcu_stream_destroy(comm_stream);
+}
+void GradientBuckets::begin() {
+  pending.clear();
+  pending_bytes = 0U;
+  reduced.clear();
+  backend_config().on_leaf_grad_final = [this](Tensor *leaf) { add(leaf); };
+}
+void GradientBuckets::add(Tensor *leaf) {
+  if (!leaf->grad || reduced.count(leaf)) return;
+  reduced.insert(leaf);
+  pending.push_back(leaf);
+  pending_bytes += (size_t)leaf->grad->storage->size * sizeof(real1);
+  if (pending_bytes >= bucket_bytes) flush();
+}
+void GradientBuckets::flush() {
+  if (pending.empty()) return;
+  // device_ptr() materialises a pending lazy zero fill on the compute stream, so take the pointers
+  // before the event that hands the bucket to the communication stream
+  std::vector<std::pair<real1 *, size_t>> bufs;
+  void *compute = nullptr;
+  for (Tensor *leaf : pending) {
+    Tensor &g = *(leaf->grad);
+    bufs.push_back({g.device_ptr(), (size_t)g.storage->size});
+    compute = g.stream();
+  }
+  throw_on_error(weedcu_event_record(ev_ready, compute), "GradientBuckets::flush");
+  throw_on_error(weedcu_stream_wait_event(comm_stream, ev_ready), "GradientBuckets::flush");
+  throw_on_error(weedcu_nccl_group_start(), "GradientBuckets::flush");
+  for (const auto &b : bufs) throw_on_error(weedcu_nccl_allreduce_sum(comm, b.first, b.second, comm_stream), "GradientBuckets::flush");
+  throw_on_error(weedcu_nccl_group_end(), "GradientBuckets::flush");
+  ++buckets_launched;
+  pending.clear();
+  pending_bytes = 0U;
+}
+void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
+  backend_config().on_leaf_grad_final = nullptr;
+  void *compute = nullptr;
+  for (const ParameterPtr &p : params) {
+    if (!p->grad) continue;
+    compute = p->grad->stream();
+    if (reduced.count(p.get())) continue;
+    // not reached by this rank's backward walk: still reduce it unless it is untouched everywhere
+    // (same graph on every rank: a pending zero fill here means a pending zero fill there)
+    Tensor &g = *(p->grad);
+    if (g.storage->device == DeviceTag::GPU && static_cast<GpuRealStorage *>(g.storage.get())->zero_pending) continue;
+    reduced.insert(p.get());
+    pending.push_back(p.get());
+    pending_bytes += (size_t)g.storage->size * sizeof(real1);
+  }
+  flush();
+  if (compute) {
+    throw_on_error(weedcu_event_record(ev_done, comm_stream), "GradientBuckets::finish");
+    throw_on_error(weedcu_stream_wait_event(compute, ev_done), "GradientBuckets::finish");
+  }
+}
 void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root) {
   for (const ParameterPtr &p : params)
     throw_on_error(weedcu_nccl_broadcast(comm, p->device_ptr(), p->storage->size, root, p->stream()), "broadcast_parameters");

@@ -9,6 +9,7 @@
 // Fused device paths (backend_config().fused): Tensor::gelu is one kernel forward and one kernel
 // backward instead of 9 + ~20 (tensor.cpp:841-851); the matmul node accumulates dA / dB inside the
 // GEMM epilogue instead of tmp + add_in_place (tensor.cpp:1361-1400).
+#include <unordered_map>
 #include "weed_b200/ops.hpp"
 
 #include <algorithm>
@@ -352,7 +353,30 @@ void Tensor::backward(TensorPtr loss) { // tensor.cpp:371-401
       stack.pop_back();
     }
   }
-  for (auto it = topo.rbegin(); it != topo.rend(); ++it) (*it)->backward();
+  const std::function<void(Tensor *)> &on_final = backend_config().on_leaf_grad_final;
+  if (!on_final) {
+    for (auto it = topo.rbegin(); it != topo.rend(); ++it) (*it)->backward();
+    return;
+  }
+  // execution index of the last node that touches each leaf (closures replace p->grad, so the
+  // tensor — not its gradient buffer — is the key; SURVEY §7 hard part 8)
+  std::unordered_map<Tensor *, size_t> last_use;
+  size_t idx = 0;
+  for (auto it = topo.rbegin(); it != topo.rend(); ++it, ++idx)
+    for (const TensorPtr &p : (*it)->parents)
+      if (p && !p->grad_node && p->requires_grad) last_use[p.get()] = idx;
+  idx = 0;
+  for (auto it = topo.rbegin(); it != topo.rend(); ++it, ++idx) {
+    (*it)->backward();
+    for (const TensorPtr &p : (*it)->parents)
+      if (p && !p->grad_node && p->requires_grad) {
+        auto lu = last_use.find(p.get());
+        if (lu != last_use.end() && lu->second == idx) {
+          last_use.erase(lu); // a node may list the same leaf twice
+          on_final(p.get());
+        }
+      }
+  }
 }
 
 // ------------------------------------------------------------------------------ softmax family
