@@ -262,6 +262,128 @@ def test_config_c4_transformer_training_default_mode_runs_and_learns(P):
     assert np.all(np.isfinite(b)) and b[-1] < b[0]
 
 
+def kv_cache_mha_run(H, d, Hh, chunks, seed, max_len=32):
+    """MultiHeadAttention with the float KV cache (use_kv_cache, kv_quant_bits = 0 — the deterministic
+    decode configuration, SURVEY §7 hard part 6): feed the chunks one after the other, return every
+    chunk's output."""
+    m = H.module("mha", d, Hh)
+    H.init_params(m, seed)
+    H.module_set(m, "kv_quant_bits", 0)
+    H.module_set(m, "use_kv_cache", 1)
+    H.module_set(m, "max_kv_seq_len", max_len)
+    H.module_set(m, "train", 0)
+    outs = []
+    for x in chunks:  # x: [B, T_new, d] numpy
+        B, T, _ = x.shape
+        y = H.forward(m, H.tensor(np.ascontiguousarray(x.transpose(2, 1, 0)).ravel(), [B, T, d]))
+        outs.append(H.read(y))
+    H.reset()
+    return outs
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+@pytest.mark.parametrize("pattern", ["token_by_token", "two_chunks"])
+def test_mha_kv_cache_decode_matches_reference(P, R, fused, pattern):
+    """Growing float KV cache (multihead_attention.cpp:169-199,278-287) vs the reference CPU build,
+    every step's output. Patterns are the ones the reference can run [measured]: single tokens from
+    an empty cache, and two multi-token chunks (whose second chunk gets the reference's
+    [T_q, T_k] triu mask with diagonal 0, :322-328 — reproduced). A multi-token prefill followed by a
+    single token makes the reference throw "Tensor::reshape(): sizes do not match" (defect D10)."""
+    B, d, Hh = 3, 16, 4
+    rng = np.random.default_rng(123)
+    lens = [1] * 8 if pattern == "token_by_token" else [4, 4]
+    chunks = [rng.uniform(-1, 1, size=(B, t, d)).astype(np.float32) for t in lens]
+    ref = kv_cache_mha_run(R, d, Hh, chunks, 41)
+    set_mode(P, fused)
+    got = kv_cache_mha_run(P, d, Hh, chunks, 41)
+    set_mode(P, 1)
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert a.shape == b.shape
+        assert cases.rel_err(b, a) <= 2e-5, f"chunk {i}"
+
+
+def test_mha_kv_cache_prefill_then_decode_fused_equals_unfused(P):
+    """Multi-token prefill followed by single-token steps (what a serving loop does; the reference
+    throws there, D10): the fused decode path against this backend's op-for-op path."""
+    B, d, Hh = 4, 32, 4
+    rng = np.random.default_rng(124)
+    chunks = [rng.uniform(-1, 1, size=(B, 9, d)).astype(np.float32)] + [rng.uniform(-1, 1, size=(B, 1, d)).astype(np.float32) for _ in range(6)]
+    set_mode(P, 0)
+    a = kv_cache_mha_run(P, d, Hh, chunks, 43)
+    set_mode(P, 1)
+    b = kv_cache_mha_run(P, d, Hh, chunks, 43)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert cases.rel_err(v, u) <= 2e-5, f"chunk {i}"
+
+
+def greedy_decode(H, cfg, prompt, n_new, seed, prefill=True):
+    """Greedy decode through Weed's module API: Embedding - LearnedPositionalEncoding - L x
+    TransformerEncoderLayer (float KV cache) - LayerNorm - Linear; prefill the prompt, then feed the
+    arg-max token of the last position back one token at a time (config C5's decode half).
+    LearnedPositionalEncoding::forward always adds positions 0..T-1 (learned_positional_encoding.cpp:49-61),
+    so every incrementally fed token gets position 0 — reference behaviour, reproduced."""
+    V, d = cfg["V"], cfg["d"]
+    encs = [H.module("encoder", d, cfg["H"], cfg["dff"]) for _ in range(cfg["L"])]
+    mods = [H.module("embedding", V, d), H.module("posenc", cfg["T"], d)] + encs + [H.module("layernorm", d), H.module("linear", d, V, 1)]
+    model = H.module("sequential", *mods)
+    H.init_params(model, seed)
+    for e in encs:
+        H.module_set(e, "kv_quant_bits", 0)
+        H.module_set(e, "use_kv_cache", 1)
+        H.module_set(e, "max_kv_seq_len", cfg["T"])
+    H.module_set(model, "train", 0)
+    B, T0 = prompt.shape
+    tokens = [prompt[:, t].copy() for t in range(T0)]
+    logits_trace = []
+    if prefill:
+        feed, t_feed = np.ascontiguousarray(prompt.T).ravel().astype(np.int32), T0  # [B, T0] column-major (b fastest)
+    else:  # token by token (the only prompt feeding the reference's float cache survives, D10)
+        for t in range(T0 - 1):
+            H.forward_symbol(model, H.symbol(prompt[:, t].astype(np.int32), [B, 1]))
+        feed, t_feed = prompt[:, T0 - 1].astype(np.int32), 1
+    for _ in range(n_new):
+        sym = H.symbol(feed, [B, t_feed])
+        lg = H.read(H.forward_symbol(model, sym)).reshape(V, t_feed, B)  # [B, T, V] column-major
+        last = lg[:, t_feed - 1, :].T  # [B, V]
+        logits_trace.append(last.copy())
+        nxt = last.argmax(axis=1).astype(np.int32)
+        tokens.append(nxt)
+        feed, t_feed = nxt, 1
+    H.reset()
+    return np.stack(tokens, axis=1), logits_trace
+
+
+def test_greedy_decode_matches_reference(P, R):
+    """Same greedy token sequence as the reference CPU build (exact integers) and the logits of every
+    step within 2e-5 (fp32 path), for both the fused and the op-for-op host paths."""
+    cfg = dict(V=96, d=32, H=4, dff=64, L=2, T=24)
+    rng = np.random.default_rng(808)
+    prompt = rng.integers(0, cfg["V"], size=(1, 7)).astype(np.int32)  # B = 1: the reference's LayerNorm is self-consistent there (D1)
+    ref_tok, ref_lg = greedy_decode(R, cfg, prompt, 8, 17, prefill=False)
+    for fused in (1, 0):
+        set_mode(P, fused)
+        tok, lg = greedy_decode(P, cfg, prompt, 8, 17, prefill=False)
+        assert np.array_equal(tok, ref_tok), (fused, tok, ref_tok)
+        for i, (a, b) in enumerate(zip(ref_lg, lg)):
+            assert cases.rel_err(b, a) <= 2e-5, f"fused={fused} step {i}"
+    set_mode(P, 1)
+
+
+def test_greedy_decode_batched_fused_equals_unfused(P):
+    """B > 1 (where the reference itself is not self-consistent, D1): the fused decode path must
+    reproduce this backend's own op-for-op path — same tokens, logits within 2e-5."""
+    cfg = dict(V=96, d=32, H=4, dff=64, L=2, T=24)
+    rng = np.random.default_rng(809)
+    prompt = rng.integers(0, cfg["V"], size=(5, 6)).astype(np.int32)
+    set_mode(P, 0)
+    t0, l0 = greedy_decode(P, cfg, prompt, 10, 19)
+    set_mode(P, 1)
+    t1, l1 = greedy_decode(P, cfg, prompt, 10, 19)
+    assert np.array_equal(t0, t1)
+    for i, (a, b) in enumerate(zip(l0, l1)):
+        assert cases.rel_err(b, a) <= 2e-5, f"step {i}"
+
+
 def test_gpt_shape_train_step_bf16_vs_fp32(P):
     """Token model with the fused cross-entropy: bf16 tensor-core GEMMs vs the fp32 path on the same
     weights — loss after 3 steps within the stated bf16 bound (2e-2 relative)."""

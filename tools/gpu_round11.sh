@@ -1,0 +1,13 @@
+#!/bin/bash
+# 2-GPU data-parallel check: bench at N=1 and N=2 (overlapped buckets vs after-backward), NCCL debug summary
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1
+tail -n 1 gpurun_out/bench_n1.log | cut -c1-200
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2>&1
+tail -n 1 gpurun_out/bench_n2.log | cut -c1-200
+WH_DP_OVERLAP=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2_nooverlap.log 2>&1
+tail -n 1 gpurun_out/bench_n2_nooverlap.log | cut -c1-200
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.log 2>&1
+tail -n 2 gpurun_out/bench_ref_n2.log | cut -c1-200

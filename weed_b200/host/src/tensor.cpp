@@ -703,7 +703,25 @@ void accumulate(const TensorPtr &parent, const TensorPtr &like, const Tensor &co
   parent->grad = g;
   parent->reduce_grad_broadcast();
 }
+// match_shape mutates its operand in place (tensor.cpp:306-332): after `y + bias` a bias Parameter
+// permanently reads [B, T, F] with strides [0, 0, 1]. In the reference a later call with another T
+// (multi-token prefill followed by single-token decode) then broadcasts the ACTIVATION to the stale
+// extent and MultiHeadAttention::forward throws "Tensor::reshape(): sizes do not match" [measured;
+// DESIGN.md defect D10]. Here an expanded Parameter dim (stride 0, extent > 1) that disagrees with
+// its partner's extent is collapsed back to 1 before matching — a no-op whenever the reference's
+// own behaviour is well defined (same extents as before).
+void rebase_expanded_parameter(TensorPtr &p, const TensorPtr &other) {
+  if (!dynamic_cast<Parameter *>(p.get())) return;
+  const size_t mine = p->shape.size(), theirs = other->shape.size();
+  for (size_t i = 0U; i < mine; ++i) {
+    const size_t m = mine - 1U - i;
+    if (p->stride[m] || p->shape[m] <= 1U) continue;
+    if (i >= theirs || other->shape[theirs - 1U - i] != p->shape[m]) p->shape[m] = 1U;
+  }
+}
 void prepare_binary(TensorPtr &a, TensorPtr &b, const char *what) {
+  rebase_expanded_parameter(a, b);
+  rebase_expanded_parameter(b, a);
   if (!a->match_shape(b) && !b->match_shape(a)) throw std::invalid_argument(std::string("Tensor shape mismatch in ") + what + "!");
 }
 } // namespace
