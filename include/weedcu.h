@@ -141,6 +141,23 @@ int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *do
  * reference copies the buffer to the host, sum.cpp:52-67). Deterministic two-pass tree. */
 int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *stream);
 
+/* ------------------------------------------------------------------ A2 KV-cache decode
+ * MultiHeadAttention::forward with use_kv_cache and kv_quant_bits = 0
+ * (src/modules/multihead_attention.cpp:169-199, 278-287, 313-345), for q, k, v, out = [B, T_new, H*hd]
+ * column-major (the W_q / W_k / W_v outputs; b fastest) and float caches [B, H, S, hd] column-major
+ * (element (b,h,s,j) at b + B*(h + H*(s + S*j)), zero-initialised by the caller):
+ *   1. k_cache[b,h,cache_len+t,j] += k[b,t,h+H*j], same for v      (add_in_place into the slot, :282-283)
+ *   2. x[b,h,t,s] = q.k_cache / divisor, s < cache_len + T_new; when causal and T_new > 1, + mask_val
+ *      where t + 1 <= s — the [T_q, T_k] triu_fill(diagonal 1) mask of :322-328, whose query index
+ *      counts from this call's first token (reference behaviour, reproduced)
+ *   3. softmax over s, out[b,t,h+H*j] = sum_s p * v_cache[b,h,s,j]
+ * (feature c = h + H*j: the column-major reshape to {B, T, H, hd} of :155-157 makes H the fast extent)
+ * The caches are read in place (the reference copies both contiguous on every call).
+ * WEEDCU_ENOSUP for hd > 64 (callers compose the generic ops); WEEDCU_EINVAL when cache_len + T_new > S. */
+int weedcu_attention_decode(const float *q, const float *k, const float *v, float *k_cache, float *v_cache,
+                            float *out, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd, uint32_t S,
+                            uint32_t cache_len, float divisor, float mask_val, int causal, void *stream);
+
 /* ------------------------------------------------------------------ S1-S2 softmax family
  * Weed::softmax / softmax_grad (src/ops/softmax.cpp:85-138), logsoftmax / logsoftmax_grad
  * (src/ops/logsoftmax.cpp:87-149). Rows run along `axis`; all views share one shape.
@@ -162,7 +179,9 @@ int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, ui
                              uint32_t Tk, float divisor, float mask_val, int causal,
                              int batch_fastest, void *stream);
 /* Fused attention core on bf16 tensor cores for q, k, v, out = [B, T, H*hd] column-major (b fastest;
- * the layout Linear::forward leaves them in): per (b, h)  S = Q K^T / divisor (+ mask_val where
+ * the layout Linear::forward leaves them in; feature c belongs to head h = c % H, component
+ * j = c / H — the column-major reshape to {B, T, H, hd} of multihead_attention.cpp:155-157 makes H
+ * the fast extent): per (b, h)  S = Q K^T / divisor (+ mask_val where
  * q + 1 <= k when causal), P = softmax_k(S), O = P V — the chain of MultiHeadAttention::forward,
  * src/modules/multihead_attention.cpp:289-345, without its transposing copies. Q, K, V and P are
  * rounded to bf16, accumulation is fp32; like the reference's batched matmul (tensor.cpp:1253-1271)
@@ -259,6 +278,12 @@ typedef struct weedcu_mat {
 int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm,
                        float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
                        uint32_t batch, int accumulate, int precision, void *stream);
+/* Weed::matmul for M <= 16 rows (a decode step: Linear::forward on B tokens), fp32 FFMA, any operand
+ * strides, optional dense bias[N] added to every row (Linear's `y + bias`), optional C +=. The weight
+ * matrix is read once: HBM-bound on 4*K*N bytes. WEEDCU_ENOSUP for M > 16. */
+int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c,
+                         const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *bias,
+                         int accumulate, void *stream);
 /* bf16 tensor-core GEMM on operands already held in bf16 (raw uint16 bit patterns).
  * a_major / b_major: 0 = K contiguous, 1 = M (resp. N) contiguous; lda/ldb are the strides
  * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc.

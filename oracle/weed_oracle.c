@@ -589,7 +589,8 @@ int wo_matmul_bf16_model(const float *a, const wo_mat *am, const float *b, const
  * S = Q K^T, S/divisor (+ triu mask), softmax over keys, O = P V — with the rounding points of the
  * tensor-core path: Q, K, V and the probabilities P are rounded to bf16 (RNE), products are exact
  * and sums are carried in double (the device accumulates in fp32; tolerance covers the difference).
- * q, k, v, out: [B, T, H*hd] column-major (b fastest). */
+ * q, k, v, out: [B, T, H*hd] column-major (b fastest); feature c = h + H*j, because the reference
+ * reshapes to {B, T, H, hd} (:155-157) and a column-major reshape makes the first new extent fast. */
 int wo_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
                            uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                            int causal) {
@@ -607,8 +608,8 @@ int wo_attention_fwd(const float *q, const float *k, const float *v, float *out,
         for (uint32_t j = 0; j < T; ++j) {
           double sum = 0.0;
           for (uint32_t c = 0; c < hd; ++c)
-            sum += (double)bf16_round(q[b + i * sT + (uint64_t)(h * hd + c) * sC]) *
-                   (double)bf16_round(k[b + j * sT + (uint64_t)(h * hd + c) * sC]);
+            sum += (double)bf16_round(q[b + i * sT + (uint64_t)(h + H * c) * sC]) *
+                   (double)bf16_round(k[b + j * sT + (uint64_t)(h + H * c) * sC]);
           S[i + (size_t)T * j] = (float)sum;
         }
       if (wo_attn_softmax_real(S, P, 1, T, T, divisor, mask_val, causal, 0) != 0) {
@@ -621,11 +622,82 @@ int wo_attention_fwd(const float *q, const float *k, const float *v, float *out,
           double sum = 0.0;
           for (uint32_t j = 0; j < T; ++j)
             sum += (double)bf16_round(P[i + (size_t)T * j]) *
-                   (double)bf16_round(v[b + j * sT + (uint64_t)(h * hd + c) * sC]);
-          out[b + i * sT + (uint64_t)(h * hd + c) * sC] = (float)sum;
+                   (double)bf16_round(v[b + j * sT + (uint64_t)(h + H * c) * sC]);
+          out[b + i * sT + (uint64_t)(h + H * c) * sC] = (float)sum;
         }
     }
   free(S);
   free(P);
+  return 0;
+}
+
+/* MultiHeadAttention::forward with use_kv_cache, kv_quant_bits = 0 — the float cache path,
+ * src/modules/multihead_attention.cpp:278-287 (slot add_in_place + slices of the cache), :313-345
+ * (scores = Q K^T, / sqrt(hd), [T_q, T_k] triu mask when T > 1, softmax, P V, transpose back).
+ * Serial float loops in the reference's order: dot over head_dim (matmul.cpp:34-47), x / divisor,
+ * + mask (triu_fill.cpp:48-56, diagonal 1: key index > query index), max / exp / sum / divide
+ * (softmax.cpp:23-138), then sum over keys of p * v.
+ * q, k, v, out: [B, T_new, H*hd] column-major; caches [B, H, S, hd] column-major. */
+int wo_attention_decode(const float *q, const float *k, const float *v, float *k_cache, float *v_cache,
+                        float *out, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd, uint32_t S,
+                        uint32_t cache_len, float divisor, float mask_val, int causal) {
+  if ((uint64_t)cache_len + T_new > S) return -1;
+  const uint64_t BH = (uint64_t)B * H;
+  const uint32_t L = cache_len + T_new;
+  for (uint32_t b = 0; b < B; ++b)
+    for (uint32_t h = 0; h < H; ++h)
+      for (uint32_t t = 0; t < T_new; ++t)
+        for (uint32_t j = 0; j < hd; ++j) {
+          const uint64_t src = b + (uint64_t)B * (t + (uint64_t)T_new * ((uint64_t)h + (uint64_t)H * j));
+          const uint64_t dst = (b + (uint64_t)B * h) + BH * ((uint64_t)(cache_len + t) + (uint64_t)S * j);
+          k_cache[dst] = k_cache[dst] + k[src];
+          v_cache[dst] = v_cache[dst] + v[src];
+        }
+  float *x = (float *)malloc(sizeof(float) * (size_t)L);
+  if (!x) return -1;
+  const int do_mask = causal && T_new > 1;
+  for (uint32_t b = 0; b < B; ++b)
+    for (uint32_t h = 0; h < H; ++h) {
+      const uint64_t bh = b + (uint64_t)B * h;
+      for (uint32_t t = 0; t < T_new; ++t) {
+        float mx = -INFINITY;
+        for (uint32_t s = 0; s < L; ++s) {
+          float sum = 0.0f;
+          for (uint32_t j = 0; j < hd; ++j)
+            sum += q[b + (uint64_t)B * (t + (uint64_t)T_new * ((uint64_t)h + (uint64_t)H * j))] * k_cache[bh + BH * ((uint64_t)s + (uint64_t)S * j)];
+          float y = sum / divisor;
+          if (do_mask && t + 1u <= s) y = y + mask_val;
+          x[s] = y;
+          if (y > mx) mx = y;
+        }
+        float den = 0.0f;
+        for (uint32_t s = 0; s < L; ++s) {
+          x[s] = expf(x[s] - mx);
+          den += x[s];
+        }
+        for (uint32_t j = 0; j < hd; ++j) {
+          float sum = 0.0f;
+          for (uint32_t s = 0; s < L; ++s) sum += (x[s] / den) * v_cache[bh + BH * ((uint64_t)s + (uint64_t)S * j)];
+          out[b + (uint64_t)B * (t + (uint64_t)T_new * ((uint64_t)h + (uint64_t)H * j))] = sum;
+        }
+      }
+    }
+  free(x);
+  return 0;
+}
+
+/* Linear::forward on a few rows (src/modules/linear.cpp:86-100: y = x >> W; y = y + bias) = the
+ * serial-float matmul of wo_matmul_real followed by the broadcast add. */
+int wo_matmul_skinny(const float *a, const wo_mat *am, const float *b, const wo_mat *bm, float *c,
+                     const wo_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate) {
+  for (uint32_t i = 0; i < M; ++i)
+    for (uint32_t j = 0; j < N; ++j) {
+      float sum = 0.0f;
+      for (uint32_t k = 0; k < K; ++k)
+        sum += a[am->offset + (uint64_t)i * am->s0 + (uint64_t)k * am->s1] * b[bm->offset + (uint64_t)k * bm->s0 + (uint64_t)j * bm->s1];
+      if (bias) sum = sum + bias[j];
+      float *o = &c[cm->offset + (uint64_t)i * cm->s0 + (uint64_t)j * cm->s1];
+      *o = accumulate ? (*o + sum) : sum;
+    }
   return 0;
 }

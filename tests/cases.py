@@ -523,6 +523,57 @@ for _M, _K, _N, _al, _bl, _batch, _acc in [
         return _matmul(be, rng, M, K, N, al, bl, batch, acc, 0)
 
 
+# --------------------------------------------------------------------------------------- decode
+def _decode(be, rng, B, H, hd, S, steps, causal=1):
+    """KV-cache attention over a sequence of calls (cache append + attention): `steps` = T_new of
+    every call; returns every call's output and the final caches."""
+    BH = B * H
+    kc, vc = np.zeros(BH * S * hd, F32), np.zeros(BH * S * hd, F32)
+    hkc, hvc = be.buf(kc), be.buf(vc)
+    div, mask = np.float32(np.sqrt(hd)), np.float32(-1.701411835e38)
+    out, cache_len = {}, 0
+    for i, T in enumerate(steps):
+        n = B * T * H * hd
+        q, k, v = uni(rng, n), uni(rng, n), uni(rng, n)
+        hq, hk, hv, ho = be.buf(q), be.buf(k), be.buf(v), be.buf(np.zeros(n, F32))
+        be.call("attention_decode", hq, hk, hv, hkc, hvc, ho, U32(B), U32(T), U32(H), U32(hd), U32(S), U32(cache_len), div, mask, I32(causal))
+        out[f"out{i}"] = ho.get()
+        cache_len += T
+    out["k_cache"], out["v_cache"] = hkc.get(), hvc.get()
+    return out
+
+
+for _B, _H, _hd, _S, _steps in [
+        (3, 4, 4, 16, [1, 1, 1, 1, 1]),          # token by token from an empty cache
+        (2, 2, 16, 40, [6, 1, 1, 1]),            # prefill then decode (the reference throws there, D10)
+        (8, 12, 64, 300, [128, 1, 1]),           # GPT-2 heads: 96 (b,h) pairs = 3 warps of lanes, many key chunks
+        (5, 3, 8, 24, [4, 4, 4]),                # chunks with T_new > 1 after the first: [T_q, T_k] triu mask quirk
+        (1, 1, 32, 64, [33, 1]),                 # one head, partial warp
+        (4, 40, 64, 20, [1, 2, 1])]:             # BH = 160 > 128
+    @case(f"attention_decode_B{_B}_H{_H}_hd{_hd}_S{_S}_steps{'_'.join(map(str, _steps))}", tol=2e-5)
+    def _c(be, rng, B=_B, H=_H, hd=_hd, S=_S, steps=_steps):
+        return _decode(be, rng, B, H, hd, S, steps)
+
+
+for _M, _K, _N, _al, _bl, _bias, _acc in [
+        (8, 768, 96, "col", "col", 1, 0),        # a decode step of Linear(768, .) on 8 tokens
+        (1, 300, 50, "col", "col", 1, 0),
+        (16, 130, 33, "col", "col", 0, 1),
+        (3, 64, 10, "row", "row", 1, 0),
+        (5, 1000, 7, "col", "row", 0, 0)]:
+    @case(f"matmul_skinny_{_M}x{_K}x{_N}_{_al}_{_bl}_bias{_bias}_acc{_acc}", tol=2e-5)
+    def _c(be, rng, M=_M, K=_K, N=_N, al=_al, bl=_bl, bias=_bias, acc=_acc):
+        lay = lambda r, c, kind: (1, r) if kind == "col" else (c, 1)
+        as0, as1 = lay(M, K, al)
+        bs0, bs1 = lay(K, N, bl)
+        a, b, c = uni(rng, M * K + 3), uni(rng, K * N + 5), uni(rng, M * N)
+        bv = uni(rng, N)
+        ha, hb, hc, hbias = be.buf(a), be.buf(b), be.buf(c), be.buf(bv)
+        be.call("matmul_skinny", ha, _mat(3, as0, as1, 0), hb, _mat(5, bs0, bs1, 0), hc, _mat(0, 1, M, 0), U32(M), U32(K), U32(N),
+                hbias if bias else None, I32(acc))
+        return {"c": hc.get()}
+
+
 # bf16 tensor-core path: checked against the bf16-rounding model (operands RNE-rounded to bf16,
 # exact products, wide accumulation). Only the fp32 accumulation order differs -> 1e-4; the error
 # against the un-rounded fp32 product is bounded separately in test_kernels_gpu.py (<= 2e-2).

@@ -109,6 +109,17 @@ int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *
   if ((T % 8u) || T < 64u || (hd != 64u && T > 1024u) || hd < 16u || (hd % 8u)) return WEEDCU_ENOSUP; // same envelope as the device entry
   return RUN(wo_attention_fwd(q, k, v, out, B, T, H, hd, divisor, mask_val, (causal && T > 1) ? 1 : 0));
 }
+int weedcu_attention_decode(const float *q, const float *k, const float *v, float *k_cache, float *v_cache, float *out, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd,
+                            uint32_t S, uint32_t cache_len, float divisor, float mask_val, int causal, void *) {
+  if (hd > 64u) return WEEDCU_ENOSUP;
+  if ((uint64_t)cache_len + T_new > S) return WEEDCU_EINVAL;
+  return RUN(wo_attention_decode(q, k, v, k_cache, v_cache, out, B, T_new, H, hd, S, cache_len, divisor, mask_val, causal));
+}
+int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
+                         const float *bias, int accumulate, void *) {
+  if (M > 16u) return WEEDCU_ENOSUP;
+  return RUN(wo_matmul_skinny(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, bias, accumulate));
+}
 int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, float *lse, float *loss, void *) {
   return RUN(wo_cross_entropy_fwd(logits, offset, rows, V, rs, vs, targets, lse, loss));
 }

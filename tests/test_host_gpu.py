@@ -163,6 +163,25 @@ def test_multihead_attention_forward_matches_reference(P, R):
     assert cases.rel_err(outs[2], outs[0]) <= 2e-5
 
 
+def test_multihead_attention_bf16_fused_matches_reference(P, R):
+    """The tensor-core attention entry (heads relayout + bf16 Q K^T / softmax / P V) against the
+    reference's fp32 composition at the stated bf16 bound (2e-2 relative-to-max). Pins the head
+    grouping: the reference reshapes [B, T, C] -> {B, T, H, hd} column-major, i.e. head = c % H."""
+    B, T, d, Hh = 2, 64, 64, 4
+    rng = np.random.default_rng(78)
+    x = rng.uniform(-1, 1, size=B * T * d).astype(np.float32)
+    outs = []
+    for H, precision in ((R, 0), (P, 1)):
+        if H is P:
+            set_mode(P, 1, precision=precision)
+        m = H.module("mha", d, Hh)
+        H.init_params(m, 33)
+        outs.append(H.read(H.forward(m, H.tensor(x, [B, T, d], True))))
+        H.reset()
+    set_mode(P, 1)
+    assert cases.rel_err(outs[1], outs[0]) <= 2e-2
+
+
 def same_or_both_zero(ref, got, tol, what):
     """Parameters no gradient reaches (norm1, W_q/k/v: the batched attention products carry no
     grad) keep an all-zero gradient whose un-reduced shape differs between the two builds."""

@@ -29,6 +29,7 @@ test_intended_axis_sum = G.test_intended_axis_sum_differs_from_reference_only_by
 test_config_c1_xor = G.test_config_c1_xor_training_matches_reference
 test_config_c2_mlp = G.test_config_c2_tabular_mlp_training_matches_reference
 test_mha_forward = G.test_multihead_attention_forward_matches_reference
+test_mha_forward_bf16 = G.test_multihead_attention_bf16_fused_matches_reference
 test_encoder_fused_B1 = G.test_encoder_layer_fused_matches_reference_B1
 test_encoder_faithful_B4 = G.test_encoder_layer_faithful_mode_matches_reference_B4
 test_c4_faithful = G.test_config_c4_transformer_training_faithful_mode_matches_reference

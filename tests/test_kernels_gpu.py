@@ -94,7 +94,7 @@ def test_attention_fwd_bf16(gpu, oracle, B, T, H, hd, causal):
     gpu.sync()
     # exact fp32 chain in numpy: x[b, t, c] lives at b + B*t + B*T*c
     def heads(x):
-        return x.reshape(H, hd, T, B).transpose(3, 0, 2, 1).astype(np.float64)  # [B, H, T, hd]
+        return x.reshape(hd, H, T, B).transpose(3, 1, 2, 0).astype(np.float64)  # feature c = h + H*j -> [B, H, T, hd]
     Q, K, V = heads(q), heads(k), heads(v)
     S = Q @ K.transpose(0, 1, 3, 2) / float(div)
     if causal:
@@ -102,7 +102,7 @@ def test_attention_fwd_bf16(gpu, oracle, B, T, H, hd, causal):
     S = S - S.max(-1, keepdims=True)
     Pm = np.exp(S)
     Pm /= Pm.sum(-1, keepdims=True)
-    exact = (Pm @ V).transpose(1, 3, 2, 0).reshape(-1).astype(np.float32)  # back to [B, T, H*hd] col-major
+    exact = (Pm @ V).transpose(3, 1, 2, 0).reshape(-1).astype(np.float32)  # back to [B, T, H*hd] col-major (c = h + H*j)
     assert np.all(np.isfinite(got))
     assert cases.rel_err(got, model) <= 4e-3, f"vs bf16 model: {cases.rel_err(got, model):.3e}"
     assert cases.rel_err(got, exact) <= 2e-2, f"vs fp32 chain: {cases.rel_err(got, exact):.3e}"

@@ -5,6 +5,9 @@
 // P V, transpose back. The reference runs ~10 tensor ops with a full copy for every transpose.
 //
 // Here, for q, k, v = [B, T, H*hd] column-major (b fastest):
+// Feature c of a [B, T, C] tensor belongs to head h = c % H, component j = c / H: the reference
+// reshapes to {B, T, H, hd} (multihead_attention.cpp:155-157) and a column-major reshape makes the
+// FIRST new extent the fast one.
 //   1. heads_pack   fp32 [B,T,C] -> bf16 [B*H][hd][T]   one kernel for q, k and v: the head
 //                    relayout and the fp32->bf16 operand conversion are the same pass (6 B/elem)
 //   2. tcgen05 GEMM  S^T[bh] = Kh Qh^T                    fp32 [T(q)][T(k)], k contiguous: softmax rows
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256)
 heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [B][tt + 4]
   const uint32_t pitch = tt + 4u;
-  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n4 = (nt * B) >> 2; // B % 4 == 0
   // (selects instead of indexing the parameter struct: a dynamic index would copy it to local memory)
   const float *sp = blockIdx.z == 0 ? a.src[0] : (blockIdx.z == 1 ? a.src[1] : a.src[2]);
@@ -90,7 +93,7 @@ heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint3
 __global__ void __launch_bounds__(256)
 heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [tt][B + 1]
-  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n = nt * B;
   const float *src = a.src[blockIdx.z] + ((uint64_t)c * T + t0) * B;
   __nv_bfloat16 *dst = a.dst[blockIdx.z];
@@ -112,7 +115,7 @@ unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32
                    uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [B][tt + 4]
   const uint32_t pitch = tt + 4u;
-  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), q = nt >> 2, n4 = q * B; // nt % 4 == 0
   float4 v[LPT];
 #pragma unroll
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(256)
 unheads_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32_t B, uint32_t T, uint32_t H,
                uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [tt][B + 1]
-  const uint32_t c = blockIdx.y, h = c / hd, j = c - h * hd;
+  const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n = nt * B;
   for (uint32_t i = threadIdx.x; i < n; i += 256) {
     const uint32_t b = i / nt, t = i - b * nt;

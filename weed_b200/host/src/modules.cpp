@@ -325,6 +325,33 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
     return W_o->forward(out);
   }
 
+  if (cfg.fused && use_kv_cache && kv_quant_bits == 0 && num_kv_heads == num_heads && head_dim <= 64 && dense_contiguous(*Q) &&
+      dense_contiguous(*K) && dense_contiguous(*V) && x->storage->device == DeviceTag::GPU) {
+    // Float KV cache (multihead_attention.cpp:169-199, 278-287) with the attention over it as ONE
+    // entry: append K, V to their slots, scores against the cache in place, softmax, P V, output
+    // already in [B, T, H*hd] (include/weedcu.h: weedcu_attention_decode). The reference's ~15 ops
+    // copy the whole cache contiguous twice per call.
+    const tcapint Bu = (tcapint)B, Tu = (tcapint)T, H = (tcapint)num_heads, hd = (tcapint)head_dim;
+    if (!k_cache) {
+      if (!max_seq_len) max_seq_len = 2048U;
+      cache_len = 0U;
+      const std::vector<tcapint> cs{Bu, H, max_seq_len, hd};
+      k_cache = Tensor::zeros(cs, false, false, DType::REAL, x->storage->device, x->storage->get_device_id());
+      v_cache = Tensor::zeros(cs, false, false, DType::REAL, x->storage->device, x->storage->get_device_id());
+    }
+    if (k_cache->shape[0U] != Bu) throw std::invalid_argument("KV cache was allocated for another batch size; call reset_cache()");
+    if (cache_len + Tu > max_seq_len) throw std::invalid_argument("KV cache is full (slice out of range)");
+    out = Tensor::allocate_like(std::vector<tcapint>{Bu, Tu, H * hd}, *x, DType::REAL, false, false);
+    const int rc = weedcu_attention_decode(Q->device_ptr_ro() + Q->offset, K->device_ptr_ro() + K->offset, V->device_ptr_ro() + V->offset,
+                                           k_cache->device_ptr(), v_cache->device_ptr(), out->device_ptr(), Bu, Tu, H, hd, max_seq_len, cache_len,
+                                           std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0, x->stream());
+    if (rc == 0) {
+      cache_len += Tu;
+      return W_o->forward(out);
+    }
+    if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "attention decode");
+  }
+
   Q = Tensor::reshape(Q, std::vector<symint>{B, T, num_heads, head_dim});
   K = Tensor::reshape(K, std::vector<symint>{B, T, num_kv_heads, head_dim});
   V = Tensor::reshape(V, std::vector<symint>{B, T, num_kv_heads, head_dim});

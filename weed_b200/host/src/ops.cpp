@@ -321,6 +321,15 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
       }
     }
   }
+  if (cfg.fused && M <= 16U) {
+    // a handful of rows (a decode step, or a tiny training batch): the product is one pass over the
+    // weight matrix — skinny FFMA kernel at fp32 in either precision mode, bias added in the same pass
+    const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dc = dev_out(out, "matmul", !accumulate);
+    const weedcu_mat am = mat_of(a), bm = mat_of(b), cm = mat_of(out);
+    const real1 *bias_ptr = bias ? dev_of(*bias, "matmul").ptr + bias->offset : nullptr;
+    throw_on_error(weedcu_matmul_skinny(da.ptr, &am, db.ptr, &bm, dc.ptr, &cm, M, K, N, bias_ptr, accumulate, dc.stream), "matmul");
+    return true;
+  }
   if (bias) return false;
   const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dc = dev_out(out, "matmul", !accumulate);
   const weedcu_mat am = mat_of(a), bm = mat_of(b), cm = mat_of(out);

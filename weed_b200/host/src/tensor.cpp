@@ -939,8 +939,13 @@ TensorPtr Tensor::matmul(TensorPtr a, TensorPtr b) { // tensor.cpp:1204-1326
 // kernel does not apply (the caller then composes the two ops like the reference).
 TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
   const BackendConfig &cfg = backend_config();
-  if (!cfg.fused || cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache) return nullptr;
+  if (!cfg.fused) return nullptr;
   if (a->shape.size() < 2U || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back()) return nullptr;
+  // <= 16 rows (decode steps, tiny batches) take the skinny kernel in either precision mode; larger
+  // products need the bf16 tensor-core path with cached operands for the bias epilogue
+  const bool skinny = a->get_broadcast_size() / a->shape.back() <= 16U;
+  if (!skinny && (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache)) return nullptr;
+  if (a->storage->device != DeviceTag::GPU || w->storage->device != DeviceTag::GPU) return nullptr;
   if (bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U] || bias->storage->device != DeviceTag::GPU) return nullptr;
   const bool rg = a->requires_grad || w->requires_grad || bias->requires_grad;
   const bool needs_flatten = (a->shape.size() > 2U);
