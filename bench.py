@@ -203,7 +203,9 @@ def main_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank that falls out of step must fail the run, not hang it
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     P = Harness.product()
     cfg = dict(FULL)
     if args.layers:
@@ -348,18 +350,22 @@ def main_ours(args):
 
     # per-kernel-class device time (instrumented pass over the same step, CUDA events per launch)
     roofline, breakdown = None, {}
+    # every rank runs the same steps (a training step contains the gradient all-reduce: a rank that
+    # stepped alone would wait for its peers forever); only rank 0 records the per-launch events
+    psteps = min(2, args.steps)
+    if rank == 0:
+        lib.weedcu_prof_enable(C.c_int(1))
+    for s in range(psteps):
+        resident_step(s)
+    P.sync()
+    if rank == 0:
+        lib.weedcu_prof_enable(C.c_int(0))
+    for h in losses:
+        P.free(h)
+    losses.clear()
     if rank == 0:
         names = {1: "gemm_bf16_tcgen05", 2: "gemm_f32_ffma", 3: "pack_bf16", 4: "elementwise", 5: "softmax", 6: "layernorm", 7: "cross_entropy",
                  8: "optimizer", 9: "reduce", 10: "embedding", 11: "fill", 12: "nccl", 13: "attention_flash_tcgen05"}
-        lib.weedcu_prof_enable(C.c_int(1))
-        psteps = min(2, args.steps)
-        for s in range(psteps):
-            resident_step(s)
-        P.sync()
-        lib.weedcu_prof_enable(C.c_int(0))
-        for h in losses:
-            P.free(h)
-        losses.clear()
         tot = 0.0
         for cls, nm in names.items():
             t, n, w = C.c_double(), C.c_uint64(), C.c_double()

@@ -393,6 +393,45 @@ int64_t wh_forward_symbol(int64_t mh, int64_t s) {
     return put(M(mh)->forward(it->second));
   })
 }
+// Greedy decode step: arg-max token of the last position of logits [B, T, V] as a symbol handle [B, 1].
+// This repo's host library computes it on the device (Weed::argmax_last_token); the reference has no
+// arg-max, so its build reads the logits back and scans them on the host (what a Python client does).
+int64_t wh_argmax_last(int64_t logits) {
+  WH_TRY({
+    TensorPtr lg = T(logits);
+#ifdef WEED_B200
+    SymbolTensorPtr s = argmax_last_token(*lg);
+#else
+    const tcapint B = lg->shape[0U], Tn = lg->shape[1U], V = lg->shape[2U];
+    TensorPtr c = lg->cast(DeviceTag::CPU);
+    RealTensor rt(*c);
+    std::vector<symint> best(B, 0);
+    for (tcapint b = 0U; b < B; ++b) {
+      real1 bv = rt[b + B * (Tn - 1U)];
+      for (tcapint v = 1U; v < V; ++v) {
+        const real1 x = rt[b + B * ((Tn - 1U) + Tn * v)]; // flat column-major index of (b, T-1, v)
+        if (x > bv) {
+          bv = x;
+          best[b] = (symint)v;
+        }
+      }
+    }
+    SymbolTensorPtr s = std::make_shared<SymbolTensor>(best, std::vector<tcapint>{B, 1U}, false, g_dtag);
+#endif
+    g_symbols[g_next] = s;
+    return g_next++;
+  })
+}
+int wh_read_symbol(int64_t h, int32_t *out, uint32_t n) {
+  WH_TRY({
+    auto it = g_symbols.find(h);
+    if (it == g_symbols.end()) throw std::invalid_argument("bad symbol handle");
+    SymbolTensorPtr c = it->second->cast(DeviceTag::CPU);
+    if (c->get_broadcast_size() < n) throw std::invalid_argument("wh_read_symbol: symbol is smaller than n");
+    for (uint32_t i = 0; i < n; ++i) out[i] = (int32_t)(*static_cast<IntStorage *>(c->storage.get()))[c->get_storage_index(i)];
+    return 0;
+  })
+}
 // mutating helpers used by the example workloads (binary_addition_transformer.cpp:128-131)
 int wh_squeeze(int64_t h, int axis) {
   WH_TRY({

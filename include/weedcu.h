@@ -259,6 +259,14 @@ int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *
                            float *const *v, const uint64_t *n, float lr, float beta1, float beta2,
                            float eps, float bc1, float bc2, float gscale, void *stream);
 
+/* The multi-tensor update that also refreshes the bf16 GEMM operand of a weight: shadow[i] (or the
+ * whole array) may be NULL; otherwise it receives bf16(p) (RNE) at the same linear index, so the
+ * next forward pass needs no fp32 -> bf16 pack of the weights (+2 B/param instead of a 6 B/param pass). */
+int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *const *g, float *const *m,
+                                  float *const *v, const uint64_t *n, uint16_t *const *shadow, float lr,
+                                  float beta1, float beta2, float eps, float bc1, float bc2, float gscale,
+                                  void *stream);
+
 /* ------------------------------------------------------------------ G1-G4 matmul
  * Weed::matmul (src/ops/matmul.cpp:242-279; dims :95-122): C[M,N] (+)= A[M,K] * B[K,N], every
  * operand an arbitrary (offset, s0, s1) view. `batch` > 1 runs independent products with

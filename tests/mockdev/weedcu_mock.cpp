@@ -148,15 +148,21 @@ int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale
 int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float gscale, void *) {
   return RUN(wo_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gscale));
 }
-int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, float lr, float beta1, float beta2, float eps,
-                           float bc1, float bc2, float gscale, void *) {
+int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, uint16_t *const *shadow, float lr,
+                                  float beta1, float beta2, float eps, float bc1, float bc2, float gscale, void *) {
   ++g_launches;
   for (uint32_t t = 0; t < count; ++t) {
     std::vector<float> zeros;
     if (!g[t]) zeros.assign(n[t], 0.0f); // NULL gradient = all zeros
     if (wo_adam_step(p[t], g[t] ? g[t] : zeros.data(), m[t], v[t], n[t], lr, beta1, beta2, eps, bc1, bc2, gscale) != 0) return WEEDCU_EINVAL;
+    if (shadow && shadow[t])
+      for (uint64_t i = 0; i < n[t]; ++i) shadow[t][i] = wo_f32_to_bf16(p[t][i]);
   }
   return 0;
+}
+int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, float lr, float beta1, float beta2, float eps,
+                           float bc1, float bc2, float gscale, void *stream) {
+  return weedcu_adam_step_multi_shadow(count, p, g, m, v, n, nullptr, lr, beta1, beta2, eps, bc1, bc2, gscale, stream);
 }
 int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, uint32_t batch,
                        int accumulate, int precision, void *) {

@@ -362,10 +362,14 @@ def greedy_decode(H, cfg, prompt, n_new, seed, prefill=True):
         feed, t_feed = prompt[:, T0 - 1].astype(np.int32), 1
     for _ in range(n_new):
         sym = H.symbol(feed, [B, t_feed])
-        lg = H.read(H.forward_symbol(model, sym)).reshape(V, t_feed, B)  # [B, T, V] column-major
+        lg_h = H.forward_symbol(model, sym)
+        lg = H.read(lg_h).reshape(V, t_feed, B)  # [B, T, V] column-major
         last = lg[:, t_feed - 1, :].T  # [B, V]
         logits_trace.append(last.copy())
         nxt = last.argmax(axis=1).astype(np.int32)
+        # the harness' arg-max (device kernel in this repo's build, host scan in the reference build)
+        # picks the same token as numpy on the logits read back (lowest index on ties)
+        assert np.array_equal(H.read_symbol(H.argmax_last(lg_h), B), nxt)
         tokens.append(nxt)
         feed, t_feed = nxt, 1
     H.reset()

@@ -153,68 +153,90 @@ static int launch_decode_partial(const float *q, const float *kc, const float *v
 
 // ------------------------------------------------------------------------------- skinny matmul
 // C[M, N] (+)= A[M, K] B[K, N] (+ bias[n]) for M <= 16 rows (a decode step feeds B tokens): the
-// weight matrix is read exactly once, which is all the time there is to spend — N columns are split
-// over blocks (kSkCols per block), K over the 256 threads, and the M x kSkCols partial products of a
-// thread sit in registers until one block reduction. A is tiny (M x K) and stays in L1/L2.
-// Arbitrary operand strides (weights are K-contiguous: adjacent threads read adjacent k).
-constexpr int kSkCols = 4;
-template <int MM>
+// weight matrix is read exactly once, which is all the time there is to spend. A warp owns one
+// column n and a slice of K: adjacent lanes read adjacent k of B (weights are K-contiguous), keep
+// the M partial dot products in registers, and meet in one warp-shuffle reduction; KS warps that
+// share a column (split-K, chosen so that N*KS/8 blocks cover the SMs about twice) then meet in
+// shared memory. A is tiny (M x K) and stays in L1/L2. Arbitrary operand strides.
+template <int MM, int KS>
 __global__ void __launch_bounds__(256)
 skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, const float *__restrict__ b, uint32_t b_s0,
                      uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N,
                      const float *__restrict__ bias, int accumulate) {
-  __shared__ float red[8][MM * kSkCols];
-  const uint32_t n0 = blockIdx.x * kSkCols;
-  float acc[MM][kSkCols];
-#pragma unroll
-  for (int m = 0; m < MM; ++m)
-#pragma unroll
-    for (int j = 0; j < kSkCols; ++j) acc[m][j] = 0.0f;
-  for (uint32_t k = threadIdx.x; k < K; k += 256u) {
-    float bv[kSkCols], av[MM];
-#pragma unroll
-    for (int j = 0; j < kSkCols; ++j) bv[j] = (n0 + j < N) ? b[(uint64_t)k * b_s0 + (uint64_t)(n0 + j) * b_s1] : 0.0f;
-#pragma unroll
-    for (int m = 0; m < MM; ++m) av[m] = (m < (int)M) ? a[(uint64_t)m * a_s0 + (uint64_t)k * a_s1] : 0.0f;
-#pragma unroll
-    for (int m = 0; m < MM; ++m)
-#pragma unroll
-      for (int j = 0; j < kSkCols; ++j) acc[m][j] += av[m] * bv[j];
-  }
+  constexpr int COLS = 8 / KS, U = 4;
+  __shared__ float red[8][MM];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * COLS + w / KS, ks = w % KS;
+  float acc[MM];
 #pragma unroll
-  for (int m = 0; m < MM; ++m)
+  for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
+  if (n < N) {
+    const float *bp = b + (uint64_t)n * b_s1;
+    for (uint32_t k0 = ks * 32u + lane; k0 < K; k0 += 32u * KS * U) {
+      float bv[U], av[U][MM];
 #pragma unroll
-    for (int j = 0; j < kSkCols; ++j) {
-      const float s = warp_sum(acc[m][j]);
-      if (lane == 0) red[w][m * kSkCols + j] = s;
+      for (int u = 0; u < U; ++u) {
+        const uint32_t k = k0 + u * 32u * KS;
+        bv[u] = (k < K) ? bp[(uint64_t)k * b_s0] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t k = k0 + u * 32u * KS;
+#pragma unroll
+        for (int m = 0; m < MM; ++m) av[u][m] = (k < K && m < (int)M) ? a[(uint64_t)m * a_s0 + (uint64_t)k * a_s1] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int m = 0; m < MM; ++m) acc[m] += av[u][m] * bv[u];
     }
+  }
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float s = warp_sum(acc[m]);
+    if (lane == 0) red[w][m] = s;
+  }
   __syncthreads();
-  if (threadIdx.x < MM * kSkCols) {
-    const uint32_t m = threadIdx.x / kSkCols, j = threadIdx.x % kSkCols;
-    if (m < M && n0 + j < N) {
+  if (threadIdx.x < COLS * MM) {
+    const uint32_t col = threadIdx.x / MM, m = threadIdx.x % MM, nn = blockIdx.x * COLS + col;
+    if (m < M && nn < N) {
       float s = 0.0f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-      if (bias) s += bias[n0 + j];
-      float *dst = c + (uint64_t)m * c_s0 + (uint64_t)(n0 + j) * c_s1;
+      for (int k = 0; k < KS; ++k) s += red[col * KS + k][m];
+      if (bias) s += bias[nn];
+      float *dst = c + (uint64_t)m * c_s0 + (uint64_t)nn * c_s1;
       *dst = accumulate ? (*dst + s) : s;
     }
   }
+}
+
+template <int MM>
+static void skinny_launch(int ks, unsigned /*unused*/, const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0,
+                          uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias,
+                          int accumulate, cudaStream_t st) {
+#define WCU_SK(KSV)                                                                                                     \
+  skinny_matmul_kernel<MM, KSV><<<(N + (8 / KSV) - 1) / (8 / KSV), 256, 0, st>>>(a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, \
+                                                                                  N, bias, accumulate)
+  if (ks >= 8) WCU_SK(8);
+  else if (ks >= 4) WCU_SK(4);
+  else if (ks >= 2) WCU_SK(2);
+  else WCU_SK(1);
+#undef WCU_SK
 }
 
 int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0, uint32_t b_s1, float *c,
                          uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate,
                          cudaStream_t st) {
   if (M > 16u) return WEEDCU_ENOSUP;
-  const unsigned grid = (N + kSkCols - 1) / kSkCols;
+  // split K over KS warps per column until (N * KS / 8) blocks cover the SMs about twice, but keep
+  // at least 4 x 32 k per slice
+  int ks = 1;
+  while (ks < 8 && (uint64_t)N * ks / 8u < 2u * (uint64_t)kNumSMs && K / (uint32_t)(2 * ks) >= 128u) ks *= 2;
   ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K);
-#define WCU_SK(MM) skinny_matmul_kernel<MM><<<grid, 256, 0, st>>>(a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate)
-  if (M <= 2u) WCU_SK(2);
-  else if (M <= 4u) WCU_SK(4);
-  else if (M <= 8u) WCU_SK(8);
-  else WCU_SK(16);
-#undef WCU_SK
+  if (M <= 2u) skinny_launch<2>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
+  else if (M <= 4u) skinny_launch<4>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
+  else if (M <= 8u) skinny_launch<8>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
+  else skinny_launch<16>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
   return after_launch();
 }
 

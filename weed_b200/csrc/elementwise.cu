@@ -7,6 +7,7 @@
 // as used by the CPU lambdas in src/ops/commuting.cpp:27-35, in_place.cpp:27-35,
 // copy_broadcast.cpp:27-30, real_unary.cpp:47-83, abs.cpp:70-94, pow.cpp:52-77.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 #include <cstring>
 #include <mutex>
@@ -223,6 +224,7 @@ struct AdamChunk {
   float *p;
   const float *g;
   float *m, *v;
+  uint16_t *shadow; // optional bf16 copy of p at the same linear index (the GEMM operand shadow)
   uint32_t n;
   int vec;
 };
@@ -304,10 +306,22 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__rest
       reinterpret_cast<float4 *>(c.p)[i] = pv;
       reinterpret_cast<float4 *>(c.m)[i] = mv;
       reinterpret_cast<float4 *>(c.v)[i] = vv;
+      if (c.shadow) { // the updated weight leaves as fp32 and as the bf16 GEMM operand in the same pass
+        __nv_bfloat162 o[2];
+        o[0] = __floats2bfloat162_rn(pv.x, pv.y);
+        o[1] = __floats2bfloat162_rn(pv.z, pv.w);
+        reinterpret_cast<uint2 *>(c.shadow)[i] = *reinterpret_cast<const uint2 *>(o);
+      }
     }
-    for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+    for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) {
+      adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+      if (c.shadow) reinterpret_cast<__nv_bfloat16 *>(c.shadow)[i] = __float2bfloat16_rn(c.p[i]);
+    }
   } else {
-    for (uint32_t i = threadIdx.x; i < c.n; i += 256) adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+    for (uint32_t i = threadIdx.x; i < c.n; i += 256) {
+      adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+      if (c.shadow) reinterpret_cast<__nv_bfloat16 *>(c.shadow)[i] = __float2bfloat16_rn(c.p[i]);
+    }
   }
 }
 
@@ -418,6 +432,12 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
 int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m,
                            float *const *v, const uint64_t *n, float lr, float beta1, float beta2,
                            float eps, float bc1, float bc2, float gscale, void *stream) {
+  return weedcu_adam_step_multi_shadow(count, p, g, m, v, n, nullptr, lr, beta1, beta2, eps, bc1, bc2, gscale, stream);
+}
+
+int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *const *g, float *const *m,
+                                  float *const *v, const uint64_t *n, uint16_t *const *shadow, float lr, float beta1,
+                                  float beta2, float eps, float bc1, float bc2, float gscale, void *stream) {
   if (!count) return 0;
   if (!p || !g || !m || !v || !n) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
@@ -428,15 +448,17 @@ int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *
   static std::mutex table_mutex;
   std::lock_guard<std::mutex> lock(table_mutex);
   std::vector<AdamChunk> table;
-  double total = 0.0;
+  double total = 0.0, shadowed = 0.0;
   for (uint32_t t = 0; t < count; ++t) {
     if (!p[t] || !m[t] || !v[t]) return WEEDCU_EINVAL; // g[t] == NULL: an all-zero gradient
-    const int vec = (aligned16(p[t]) && (!g[t] || aligned16(g[t])) && aligned16(m[t]) && aligned16(v[t])) ? 1 : 0;
+    uint16_t *sh = shadow ? shadow[t] : nullptr;
+    const int vec = (aligned16(p[t]) && (!g[t] || aligned16(g[t])) && aligned16(m[t]) && aligned16(v[t]) && (!sh || aligned16(sh))) ? 1 : 0;
     for (uint64_t o = 0; o < n[t]; o += kAdamChunk) {
       const uint64_t len = (n[t] - o < kAdamChunk) ? n[t] - o : kAdamChunk;
-      table.push_back(AdamChunk{p[t] + o, g[t] ? g[t] + o : nullptr, m[t] + o, v[t] + o, (uint32_t)len, vec});
+      table.push_back(AdamChunk{p[t] + o, g[t] ? g[t] + o : nullptr, m[t] + o, v[t] + o, sh ? sh + o : nullptr, (uint32_t)len, vec});
     }
     total += (double)n[t];
+    if (sh) shadowed += (double)n[t];
   }
   if (table.empty()) return 0;
   const bool same = table.size() == host_table.size() &&
@@ -455,7 +477,7 @@ int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *
     WCU_CHECK(cudaStreamSynchronize(st)); // pageable source: make the staging copy complete
   }
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
-  ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total);
+  ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total + 2.0 * shadowed);
   adam_multi_kernel<<<(unsigned)host_table.size(), 256, 0, st>>>(dev_table, a);
   return after_launch();
 }

@@ -165,6 +165,17 @@ class Harness:
     def forward_symbol(self, m, s):
         return self._ck(self.lib.wh_forward_symbol(C.c_int64(m), C.c_int64(s)))
 
+    def argmax_last(self, logits):
+        """Arg-max token of the last position of logits [B, T, V] -> symbol handle [B, 1]."""
+        self.lib.wh_argmax_last.restype = C.c_int64
+        return self._ck(self.lib.wh_argmax_last(C.c_int64(logits)))
+
+    def read_symbol(self, h, n):
+        out = np.zeros(n, np.int32)
+        self.lib.wh_read_symbol.restype = C.c_int
+        self._ck(self.lib.wh_read_symbol(C.c_int64(h), out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_uint32(n)))
+        return out
+
     def squeeze(self, h, axis):
         self._ck(self.lib.wh_squeeze(C.c_int64(h), C.c_int(axis)))
 

@@ -62,5 +62,9 @@ void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3);
 
 void embedding_gather(const SymbolTensor &indices, const Tensor &weight, Tensor &out);
 void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor &dout);
+// Greedy decoding (no reference counterpart: Weed has axis max but no arg-max, SURVEY §7 hard part 9):
+// logits [B, T, V] -> the arg-max token of the LAST position of every sequence as a device
+// SymbolTensor [B, 1] that can be fed straight back into Sequential::forward. Lowest index wins ties.
+SymbolTensorPtr argmax_last_token(const Tensor &logits);
 void triu_fill(Tensor &a, const complex &val, const tcapint diagonal = 1);
 } // namespace Weed

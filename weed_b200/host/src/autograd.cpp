@@ -44,6 +44,10 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
   std::vector<real1 *> mp, mm, mv;
   std::vector<const real1 *> mg;
   std::vector<uint64_t> mn;
+  // bf16 GEMM operand shadow of a weight that is a plain linear copy of the parameter (dense, leading
+  // dimension a multiple of 8): the update kernel refreshes it in the same pass
+  std::vector<uint16_t *> msh;
+  std::vector<std::pair<GpuRealStorage *, size_t>> refreshed;
   void *mstream = nullptr;
   for (auto &p : params) {
     const auto it = opt.state.find(p);
@@ -55,6 +59,18 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
       if (mstream && mstream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
       mstream = p->stream();
       mp.push_back(p->device_ptr());
+      uint16_t *sh = nullptr;
+      if (cfg.operand_cache && cfg.matmul_precision == WEEDCU_GEMM_BF16) {
+        GpuRealStorage *ps = static_cast<GpuRealStorage *>(p->storage.get());
+        for (size_t k = 0U; k < ps->shadows.size() && !sh; ++k) {
+          const GpuRealStorage::Bf16Shadow &c = ps->shadows[k];
+          if (c.offset == 0U && c.s_fast == 1U && c.s_slow == c.n_fast && (c.n_fast % 8U) == 0U && (uint64_t)c.n_fast * c.n_slow == ps->size) {
+            sh = (uint16_t *)c.buf->ptr;
+            refreshed.push_back({ps, k});
+          }
+        }
+      }
+      msh.push_back(sh);
       // a gradient still waiting for its lazy zero-fill was never touched by backward: pass "zeros"
       GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
       mg.push_back(gs->zero_pending ? nullptr : g->device_ptr_ro());
@@ -72,9 +88,11 @@ void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
     Weed::sub_in_place(*p, *tmp);
   }
   if (!mp.empty())
-    throw_on_error(weedcu_adam_step_multi((uint32_t)mp.size(), mp.data(), mg.data(), mm.data(), mv.data(), mn.data(), opt.lr, opt.beta1,
-                                          opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, mstream),
+    throw_on_error(weedcu_adam_step_multi_shadow((uint32_t)mp.size(), mp.data(), mg.data(), mm.data(), mv.data(), mn.data(), msh.data(), opt.lr,
+                                                 opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, mstream),
                    "adam_step");
+  // the shadows written by the kernel describe the parameter as it is now (device_ptr() above moved the version)
+  for (const auto &r : refreshed) r.first->shadows[r.second].version = r.first->version;
 }
 
 void sgd_step(const std::vector<ParameterPtr> &params, real1 lr) {

@@ -515,6 +515,20 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
                                               dout.stride.back(), dw.stream),
                  "embedding_scatter_add");
 }
+SymbolTensorPtr argmax_last_token(const Tensor &logits) {
+  if (logits.shape.size() != 3U) throw std::invalid_argument("argmax_last_token expects logits [B, T, V]");
+  const tcapint B = logits.shape[0U], T = logits.shape[1U], V = logits.shape[2U];
+  const Dev dl = dev_of(logits, "argmax_last_token");
+  SymbolTensorPtr out = std::make_shared<SymbolTensor>(std::vector<tcapint>{B, 1U}, std::vector<tcapint>{1U, B}, false, DeviceTag::GPU,
+                                                       logits.storage->get_device_id(), false);
+  GpuIntStorage *os = dynamic_cast<GpuIntStorage *>(out->storage.get());
+  if (!os) throw std::domain_error("argmax_last_token: output is not on the GPU");
+  // a size-1 extent carries stride 0 (base_tensor.hpp:282-292): use the dense strides of [B, T, V]
+  const tcapint sb = B > 1U ? logits.stride[0U] : 1U, st = T > 1U ? logits.stride[1U] : 0U, sv = V > 1U ? logits.stride[2U] : 0U;
+  throw_on_error(weedcu_argmax_rows(dl.ptr, (uint64_t)logits.offset + (uint64_t)(T - 1U) * st, B, V, sb, sv, os->device_ptr_overwrite(), dl.stream),
+                 "argmax_last_token");
+  return out;
+}
 void triu_fill(Tensor &a, const complex &val, const tcapint diagonal) {
   if (a.shape.size() != 2U) throw std::invalid_argument("triu_fill requires a 2D tensor!");
   const Dev da = dev_out(a, "triu_fill");
