@@ -204,6 +204,17 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
                              const float *dloss, float *dlogits, uint64_t d_offset, int accumulate,
                              void *stream); /* accumulate == 0: dlogits = ... (not read) */
 
+/* cross_entropy backward fused with the preparation of the Linear backward that consumes dlogits
+ * (Tensor::matmul_backward packs dY for its two tensor-core GEMMs and the bias node sums its columns,
+ * tensor.cpp:1105-1136,1361-1400): one pass writes dlogits (fp32, exactly as weedcu_cross_entropy_bwd
+ * with rs = 1, vs = rows), dlogits_bf16[v*rows + r] = bf16(dlogits) and colsum[v] = sum_r dlogits[r,v]
+ * (stored, not accumulated; deterministic order). 10-14 B/elem instead of 8-12 + 6 + 4.
+ * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned. */
+int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
+                                  const int32_t *targets, const float *lse, const float *dloss,
+                                  float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,
+                                  float *colsum, void *stream);
+
 /* ------------------------------------------------------------------ L1 LayerNorm (fused)
  * LayerNorm::forward (src/modules/layernorm.cpp:29-42): x[rows, F] with row stride 1 and
  * feature stride `rows` (last axis is slowest in col-major). y = (x-mean)/sqrt(var+eps)*gamma+beta,

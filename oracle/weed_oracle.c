@@ -701,3 +701,22 @@ int wo_matmul_skinny(const float *a, const wo_mat *am, const float *b, const wo_
     }
   return 0;
 }
+
+/* wo_cross_entropy_bwd followed by what Tensor::matmul_backward's bf16 path and the bias node do with
+ * dlogits: the RNE bf16 copy (wo_f32_to_bf16) and the column sums (reduce over rows, reduce.cpp:17-38). */
+int wo_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
+                              const int32_t *targets, const float *lse, const float *dloss, float *dlogits,
+                              uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum) {
+  const int rc = wo_cross_entropy_bwd(logits, offset, rows, V, 1, rows, targets, lse, dloss, dlogits, d_offset, accumulate);
+  if (rc) return rc;
+  for (uint32_t v = 0; v < V; ++v) {
+    float s = 0.0f;
+    for (uint32_t r = 0; r < rows; ++r) {
+      const float d = dlogits[d_offset + r + (uint64_t)v * rows];
+      dlogits_bf16[r + (uint64_t)v * rows] = wo_f32_to_bf16(d);
+      s += d;
+    }
+    colsum[v] = s;
+  }
+  return 0;
+}

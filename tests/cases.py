@@ -346,6 +346,28 @@ def _ce(be, rng, rows, V, acc=1):
     return {"lse": hlse.get(), "loss": hloss.get(), "dlogits": hdl.get()}
 
 
+def _ce_pack(be, rng, rows, V, acc):
+    logits = uni(rng, rows * V, -5, 5)
+    tg = rng.integers(0, V, size=rows).astype(np.int32)
+    hl, ht = be.buf(logits), be.buf(tg)
+    hlse, hloss = be.buf(np.zeros(rows, F32)), be.buf(np.zeros(1, F32))
+    be.call("cross_entropy_fwd", hl, U64(0), U32(rows), U32(V), U32(1), U32(rows), ht, hlse, hloss)
+    hdl, hg = be.buf(uni(rng, rows * V)), be.buf(np.full(1, 0.7, F32))
+    hsh, hcs = be.buf(np.zeros(rows * V, np.uint16)), be.buf(np.full(V, 3.0, F32))
+    be.call("cross_entropy_bwd_pack", hl, U64(0), U32(rows), U32(V), ht, hlse, hg, hdl, U64(0), I32(acc), hsh, hcs)
+    d = hdl.get()
+    # the bf16 copy is compared as the float it widens to (a one-ulp fp32 difference in dlogits may flip a rounding)
+    sh = (hsh.get().astype(np.uint32) << 16).view(np.float32)
+    return {"dlogits": d, "shadow": sh, "colsum": hcs.get()}
+
+
+for _rows, _V, _acc in [(48, 1000, 1), (1032, 77, 0), (2048, 40, 1)]:
+    @case(f"cross_entropy_bwd_pack_{_rows}x{_V}_acc{_acc}", tol=4e-3 if False else 2e-5)
+    def _c(be, rng, rows=_rows, V=_V, acc=_acc):
+        out = _ce_pack(be, rng, rows, V, acc)
+        return out
+
+
 @case("cross_entropy_48x1000", tol=2e-5)
 def _c(be, rng):
     return _ce(be, rng, 48, 1000)
@@ -392,6 +414,13 @@ for _rows, _F in [(40, 24), (5, 8), (300, 64), (5000, 16), (9600, 12)]:
 @case("layernorm_8192x768_store", tol=3e-5)
 def _c(be, rng):  # GPT-2 shape; accumulate = 0 (dx overwritten); persistent blocks loop over row tiles
     return _ln(be, rng, 8192, 768, 0, acc=0)
+
+
+for _rows, _F, _why in [(8, 768, "decode_step_single_launch"), (130, 1000, "single_launch_ragged"), (1026, 72, "odd_rows_scalar_apply"),
+                        (516, 1100, "features_beyond_register_tile"), (4100, 24, "vector_apply_ragged_chunk")]:
+    @case(f"layernorm_{_rows}x{_F}_{_why}", tol=3e-5)
+    def _c(be, rng, rows=_rows, F=_F):
+        return _ln(be, rng, rows, F, 1)
 
 
 @case("layernorm_20000x40_multi_tile", tol=3e-5)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# 2-GPU data-parallel check with tight timeouts: overlapped buckets vs after-backward vs N=1
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2>&1
+echo "rc=$?"; tail -n 1 gpurun_out/bench_n2.log | cut -c1-260
+WH_DP_OVERLAP=0 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2_nooverlap.log 2>&1
+echo "rc=$?"; tail -n 1 gpurun_out/bench_n2_nooverlap.log | cut -c1-260
+timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1
+tail -n 1 gpurun_out/bench_n1.log | cut -c1-200

@@ -153,56 +153,76 @@ static int launch_decode_partial(const float *q, const float *kc, const float *v
 
 // ------------------------------------------------------------------------------- skinny matmul
 // C[M, N] (+)= A[M, K] B[K, N] (+ bias[n]) for M <= 16 rows (a decode step feeds B tokens): the
-// weight matrix is read exactly once, which is all the time there is to spend. A warp owns one
-// column n and a slice of K: adjacent lanes read adjacent k of B (weights are K-contiguous), keep
-// the M partial dot products in registers, and meet in one warp-shuffle reduction; KS warps that
-// share a column (split-K, chosen so that N*KS/8 blocks cover the SMs about twice) then meet in
-// shared memory. A is tiny (M x K) and stays in L1/L2. Arbitrary operand strides.
-template <int MM, int KS>
+// weight matrix is read exactly once, which is all the time there is to spend. A block owns CW = 8
+// output columns; its 8 warps split K; inside a warp adjacent lanes take adjacent k (weights are
+// K-contiguous: every B load is a full 128-byte line), a lane loads its M values of A once per k
+// (128-bit loads when A is M-contiguous) and uses them for all 8 columns: 2 + 8 loads per 64 FMAs.
+// The MM x 8 partial dots of a lane meet in a halving butterfly (2*MM*8 - 2 shuffles instead of
+// 5 per value), then the 8 warps meet in shared memory. Arbitrary operand strides.
+constexpr int kSkCW = 8;
+template <int MM, bool AVEC>
 __global__ void __launch_bounds__(256)
 skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, const float *__restrict__ b, uint32_t b_s0,
                      uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N,
                      const float *__restrict__ bias, int accumulate) {
-  constexpr int COLS = 8 / KS, U = 4;
-  __shared__ float red[8][MM];
+  constexpr int NV = MM * kSkCW; // partial sums per lane
+  __shared__ float red[8][NV];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  const uint32_t n = blockIdx.x * COLS + w / KS, ks = w % KS;
-  float acc[MM];
+  const uint32_t n0 = blockIdx.x * kSkCW;
+  float acc[NV]; // acc[m * kSkCW + j]
 #pragma unroll
-  for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
-  if (n < N) {
-    const float *bp = b + (uint64_t)n * b_s1;
-    for (uint32_t k0 = ks * 32u + lane; k0 < K; k0 += 32u * KS * U) {
-      float bv[U], av[U][MM];
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+  constexpr int U = (MM <= 8) ? 2 : 1; // k-steps whose loads are issued together (latency, not bandwidth, is the enemy here)
+  for (uint32_t k0 = w * 32u + lane; k0 < K; k0 += 256u * U) {
+    float bv[U][kSkCW], av[U][MM];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t k = k0 + u * 32u * KS;
-        bv[u] = (k < K) ? bp[(uint64_t)k * b_s0] : 0.0f;
+    for (int u = 0; u < U; ++u) {
+      const uint32_t k = k0 + 256u * u;
+      const bool kok = k < K;
+#pragma unroll
+      for (int j = 0; j < kSkCW; ++j) bv[u][j] = (kok && n0 + j < N) ? b[(uint64_t)k * b_s0 + (uint64_t)(n0 + j) * b_s1] : 0.0f;
+      if (AVEC) { // a_s0 == 1, 16-byte aligned columns, M == MM
+#pragma unroll
+        for (int m = 0; m < MM; m += 4)
+          *reinterpret_cast<float4 *>(&av[u][m]) = kok ? *reinterpret_cast<const float4 *>(a + (uint64_t)k * a_s1 + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int m = 0; m < MM; ++m) av[u][m] = (kok && m < (int)M) ? a[(uint64_t)m * a_s0 + (uint64_t)k * a_s1] : 0.0f;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t k = k0 + u * 32u * KS;
-#pragma unroll
-        for (int m = 0; m < MM; ++m) av[u][m] = (k < K && m < (int)M) ? a[(uint64_t)m * a_s0 + (uint64_t)k * a_s1] : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int m = 0; m < MM; ++m) acc[m] += av[u][m] * bv[u];
     }
-  }
 #pragma unroll
-  for (int m = 0; m < MM; ++m) {
-    const float s = warp_sum(acc[m]);
-    if (lane == 0) red[w][m] = s;
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int m = 0; m < MM; ++m)
+#pragma unroll
+        for (int j = 0; j < kSkCW; ++j) acc[m * kSkCW + j] += av[u][m] * bv[u][j];
   }
+  // halving butterfly: after the step with offset o a lane keeps half of its values, each now the
+  // sum over the lane pair; after 5 steps lane L holds NV/32 complete sums, the values with index
+  // base(L) + i, base = sum over steps of (lane bit set ? half : 0)
+  uint32_t base = 0;
+#pragma unroll
+  for (int o = 16, cnt = NV; o >= 1; o >>= 1, cnt >>= 1) {
+    const int half = cnt >> 1;
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? acc[i] : acc[i + half];
+      const float keep = up ? acc[i + half] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+    if (up) base += half;
+  }
+  constexpr int LEFT = NV / 32; // MM >= 4 -> LEFT >= 1
+#pragma unroll
+  for (int i = 0; i < LEFT; ++i) red[w][base + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < COLS * MM) {
-    const uint32_t col = threadIdx.x / MM, m = threadIdx.x % MM, nn = blockIdx.x * COLS + col;
+  if (threadIdx.x < NV) {
+    const uint32_t m = threadIdx.x / kSkCW, j = threadIdx.x % kSkCW, nn = n0 + j;
     if (m < M && nn < N) {
       float s = 0.0f;
 #pragma unroll
-      for (int k = 0; k < KS; ++k) s += red[col * KS + k][m];
+      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
       if (bias) s += bias[nn];
       float *dst = c + (uint64_t)m * c_s0 + (uint64_t)nn * c_s1;
       *dst = accumulate ? (*dst + s) : s;
@@ -210,33 +230,25 @@ skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, 
   }
 }
 
-template <int MM>
-static void skinny_launch(int ks, unsigned /*unused*/, const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0,
-                          uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias,
-                          int accumulate, cudaStream_t st) {
-#define WCU_SK(KSV)                                                                                                     \
-  skinny_matmul_kernel<MM, KSV><<<(N + (8 / KSV) - 1) / (8 / KSV), 256, 0, st>>>(a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, \
-                                                                                  N, bias, accumulate)
-  if (ks >= 8) WCU_SK(8);
-  else if (ks >= 4) WCU_SK(4);
-  else if (ks >= 2) WCU_SK(2);
-  else WCU_SK(1);
-#undef WCU_SK
-}
-
 int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0, uint32_t b_s1, float *c,
                          uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate,
                          cudaStream_t st) {
   if (M > 16u) return WEEDCU_ENOSUP;
-  // split K over KS warps per column until (N * KS / 8) blocks cover the SMs about twice, but keep
-  // at least 4 x 32 k per slice
-  int ks = 1;
-  while (ks < 8 && (uint64_t)N * ks / 8u < 2u * (uint64_t)kNumSMs && K / (uint32_t)(2 * ks) >= 128u) ks *= 2;
+  const unsigned grid = (N + kSkCW - 1) / kSkCW;
   ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K);
-  if (M <= 2u) skinny_launch<2>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
-  else if (M <= 4u) skinny_launch<4>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
-  else if (M <= 8u) skinny_launch<8>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
-  else skinny_launch<16>(ks, 0, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate, st);
+#define WCU_SK(MM, AV) skinny_matmul_kernel<MM, AV><<<grid, 256, 0, st>>>(a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate)
+  const bool avec_ok = a_s0 == 1u && (a_s1 % 4u) == 0 && aligned16(a);
+  if (M <= 4u) {
+    if (avec_ok && M == 4u) WCU_SK(4, true);
+    else WCU_SK(4, false);
+  } else if (M <= 8u) {
+    if (avec_ok && M == 8u) WCU_SK(8, true);
+    else WCU_SK(8, false);
+  } else {
+    if (avec_ok && M == 16u) WCU_SK(16, true);
+    else WCU_SK(16, false);
+  }
+#undef WCU_SK
   return after_launch();
 }
 

@@ -7,6 +7,7 @@
 // so RT adjacent rows are tiled against all F features, staged once in shared memory, and the
 // reference's two-pass statistics (mean, then mean of centred squares) run from the staged copy.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace weedcu {
 
@@ -91,6 +92,64 @@ layernorm_fwd_stats_kernel(const float *__restrict__ x, uint32_t rows, uint32_t 
     if (rstd) rstd[r] = 1.0f / den;
     den_out[r] = den;
     if (!mean) den_out[rows + r] = mu; // the apply pass needs mu even when the caller does not
+  }
+}
+
+// Few rows (a decode step normalises B tokens): statistics and output in ONE launch, the row tile
+// lives in registers exactly as in layernorm_fwd_stats_kernel<NV>.
+template <int NV>
+__global__ void __launch_bounds__(32 * kLnBY)
+layernorm_fwd_small_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
+                           const float *__restrict__ beta, float eps, float *__restrict__ y, float *__restrict__ mean,
+                           float *__restrict__ rstd) {
+  __shared__ float red[kLnBY][33];
+  // gamma / beta staged once: with a single resident block, 2 x NV dependent global loads per thread
+  // in the output loop would each expose the full L2 latency
+  __shared__ float s_gamma[kLnBY * NV], s_beta[kLnBY * NV];
+  const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 32u + tx;
+  const bool live = r < rows;
+  float v[NV];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t f = ty + i * kLnBY;
+    v[i] = (live && f < F) ? x[r + (uint64_t)f * rows] : 0.0f;
+  }
+  for (uint32_t f = threadIdx.x; f < F; f += 32u * kLnBY) {
+    s_gamma[f] = gamma[f];
+    s_beta[f] = beta[f];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i];
+  red[ty][tx] = s;
+  __syncthreads();
+  s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kLnBY; ++k) s += red[k][tx];
+  const float mu = s / (float)F;
+  __syncthreads();
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float xc = v[i] - mu;
+    if (ty + i * kLnBY < F) q += xc * xc;
+  }
+  red[ty][tx] = q;
+  __syncthreads();
+  q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kLnBY; ++k) q += red[k][tx];
+  const float den = sqrtf(q / (float)F + eps); // (var + eps) ^ 0.5, layernorm.cpp:35
+  if (!live) return;
+  if (ty == 0) {
+    if (mean) mean[r] = mu;
+    if (rstd) rstd[r] = 1.0f / den;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t f = ty + i * kLnBY;
+    if (f < F) y[r + (uint64_t)f * rows] = ((v[i] - mu) / den) * s_gamma[f] + s_beta[f];
   }
 }
 
@@ -369,6 +428,22 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
                          void *stream) {
   if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
+  // WEEDCU_LN_SINGLE=1 (experiment switch): the single-launch register-tile kernel for any row count
+  static const bool single_always = [] {
+    const char *e = getenv("WEEDCU_LN_SINGLE");
+    return e && atoi(e) != 0;
+  }();
+  if ((rows <= 256u || single_always) && F <= (uint32_t)kLnBY * 64u) { // decode-sized inputs: one launch
+    ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
+    const unsigned tiles = (rows + 31u) / 32u;
+#define WCU_LN_SMALL(NV) layernorm_fwd_small_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd)
+    if (F <= kLnBY * 16) WCU_LN_SMALL(16);
+    else if (F <= kLnBY * 32) WCU_LN_SMALL(32);
+    else if (F <= kLnBY * 48) WCU_LN_SMALL(48);
+    else WCU_LN_SMALL(64);
+#undef WCU_LN_SMALL
+    return after_launch();
+  }
   float *tmp = nullptr; // den[rows] (+ mu[rows] when the caller does not keep the mean)
   WCU_CHECK(pool_alloc((void **)&tmp, sizeof(float) * 2 * (size_t)rows, st));
   ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);

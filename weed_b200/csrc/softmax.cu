@@ -12,6 +12,7 @@
 // BY warps split the columns, the tile is staged once in shared memory (<= 200 KB) and the three
 // reference passes (max, sum exp, normalise) run out of that staging copy.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace weedcu {
 
@@ -260,7 +261,7 @@ softmax_contig_bwd(float *din, const float *__restrict__ out, const float *__res
 // range is split over blockIdx.y so that the grid fills the GPU whatever `rows` is; each block keeps
 // an online (max, sum exp) per row over its slice, `ce_fwd_finish` merges the slices, gathers the
 // target logit and writes lse[r] and nll[r] = x[r,target] - lse[r] (loss = -mean).
-constexpr int kCeRT = 32, kCeBY = 8, kCeU = 4;
+constexpr int kCeRT = 32, kCeBY = 8, kCeU = 8; // 8 independent 128-B row loads in flight per thread (64 KB per SM at 8 resident blocks)
 __global__ void __launch_bounds__(kCeRT * kCeBY)
 ce_fwd_partial(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
                uint32_t v_per_block, float *__restrict__ part_m, float *__restrict__ part_s) {
@@ -359,6 +360,84 @@ ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
     }
   }
 }
+// Backward fused with what the Linear that produced the logits needs next (its matmul_backward packs
+// dY to bf16 for the two tensor-core GEMMs and sums its columns for the bias gradient): ONE pass
+// writes dlogits (fp32), its bf16 GEMM operand copy and per-row-chunk column partial sums.
+// block = 256 threads x 4 adjacent rows, kCePackCols vocab columns; logits / dlogits are [rows, V]
+// with rows contiguous (rs == 1, vs == rows, rows % 8 == 0, 16-byte aligned).
+constexpr int kCePackCols = 8;
+__global__ void __launch_bounds__(256)
+ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const int32_t *__restrict__ targets,
+                   const float *__restrict__ lse, const float *__restrict__ dloss, float *dlogits, int accumulate,
+                   __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  __shared__ float red[8][kCePackCols];
+  const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  const bool live = r < rows;
+  const uint32_t j0 = blockIdx.y * kCePackCols;
+  const float g = dloss[0] / (float)rows;
+  float cs[kCePackCols];
+#pragma unroll
+  for (int i = 0; i < kCePackCols; ++i) cs[i] = 0.0f;
+  if (live) {
+    const float4 l4 = *reinterpret_cast<const float4 *>(lse + r);
+    const int4 t4 = *reinterpret_cast<const int4 *>(targets + r);
+    constexpr int U = 4;
+#pragma unroll
+    for (int i0 = 0; i0 < kCePackCols; i0 += U) {
+      float4 xv[U], dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + i0 + u;
+        if (j < V) {
+          const uint64_t off = (uint64_t)j * rows + r;
+          xv[u] = *reinterpret_cast<const float4 *>(x + off);
+          dv[u] = accumulate ? *reinterpret_cast<const float4 *>(dlogits + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + i0 + u;
+        if (j < V) {
+          float4 o;
+          o.x = dv[u].x + (expf(xv[u].x - l4.x) - (((uint32_t)t4.x == j) ? 1.0f : 0.0f)) * g;
+          o.y = dv[u].y + (expf(xv[u].y - l4.y) - (((uint32_t)t4.y == j) ? 1.0f : 0.0f)) * g;
+          o.z = dv[u].z + (expf(xv[u].z - l4.z) - (((uint32_t)t4.z == j) ? 1.0f : 0.0f)) * g;
+          o.w = dv[u].w + (expf(xv[u].w - l4.w) - (((uint32_t)t4.w == j) ? 1.0f : 0.0f)) * g;
+          const uint64_t off = (uint64_t)j * rows + r;
+          *reinterpret_cast<float4 *>(dlogits + off) = o;
+          __nv_bfloat162 h[2];
+          h[0] = __floats2bfloat162_rn(o.x, o.y);
+          h[1] = __floats2bfloat162_rn(o.z, o.w);
+          *reinterpret_cast<uint2 *>(shadow + off) = *reinterpret_cast<const uint2 *>(h);
+          cs[i0 + u] += (o.x + o.y) + (o.z + o.w);
+        }
+      }
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kCePackCols; ++i) {
+    const float t = warp_sum(cs[i]);
+    if (lane == 0) red[w][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kCePackCols && j0 + threadIdx.x < V) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    part[(uint64_t)blockIdx.x * V + j0 + threadIdx.x] = t;
+  }
+}
+// colsum[j] (+)= sum_c part[c][j] in a fixed order
+__global__ void __launch_bounds__(256)
+ce_colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t V, float *__restrict__ colsum) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= V) return;
+  float t = 0.0f;
+  for (uint32_t c = 0; c < nchunks; ++c) t += part[(uint64_t)c * V + j];
+  colsum[j] = t;
+}
+
 // vocab slices so that (row tiles) x (slices) is ~8 blocks per SM
 static void ce_split(uint32_t rows, uint32_t V, uint32_t &splits, uint32_t &v_per_block) {
   const uint32_t row_tiles = (rows + kCeRT - 1) / kCeRT;
@@ -588,6 +667,29 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
   ce_bwd_kernel<<<dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, resolve_stream(stream)>>>(
       logits + offset, rows, V, rs, vs, vpb, targets, lse, dloss, dlogits + d_offset, accumulate);
   return after_launch();
+}
+
+int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, const int32_t *targets,
+                                  const float *lse, const float *dloss, float *dlogits, uint64_t d_offset, int accumulate,
+                                  uint16_t *dlogits_bf16, float *colsum, void *stream) {
+  if (!logits || !targets || !lse || !dloss || !dlogits || !dlogits_bf16 || !colsum || !rows || !V) return WEEDCU_EINVAL;
+  const float *x = logits + offset;
+  float *d = dlogits + d_offset;
+  if ((rows % 8u) || !aligned16(x) || !aligned16(d) || !aligned16(lse) || !aligned16(targets) || !aligned16(dlogits_bf16)) return WEEDCU_ENOSUP;
+  const uint32_t nchunks = (rows + 1023u) / 1024u, cgroups = (V + kCePackCols - 1) / kCePackCols;
+  if (cgroups > 65535u) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  float *part = nullptr;
+  WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 14.0 : 10.0) * (double)rows * V);
+  ce_bwd_pack_kernel<<<dim3(nchunks, cgroups), 256, 0, st>>>(x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
+  int rc = after_launch();
+  if (rc == 0) {
+    ce_colsum_finish_kernel<<<(V + 255u) / 256u, 256, 0, st>>>(part, nchunks, V, colsum);
+    rc = after_launch();
+  }
+  pool_free(part, st);
+  return rc;
 }
 
 } // extern "C"
