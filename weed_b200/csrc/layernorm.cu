@@ -428,12 +428,9 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
                          void *stream) {
   if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
-  // WEEDCU_LN_SINGLE=1 (experiment switch): the single-launch register-tile kernel for any row count
-  static const bool single_always = [] {
-    const char *e = getenv("WEEDCU_LN_SINGLE");
-    return e && atoi(e) != 0;
-  }();
-  if ((rows <= 256u || single_always) && F <= (uint32_t)kLnBY * 64u) { // decode-sized inputs: one launch
+  // (the single-launch register-tile kernel was also measured at 8192 x 768: 24.1 us against 22.9 us
+  // for the two streaming passes, so large inputs keep the two passes)
+  if (rows <= 256u && F <= (uint32_t)kLnBY * 64u) { // decode-sized inputs: one launch
     ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
     const unsigned tiles = (rows + 31u) / 32u;
 #define WCU_LN_SMALL(NV) layernorm_fwd_small_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd)

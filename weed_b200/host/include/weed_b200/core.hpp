@@ -292,6 +292,11 @@ struct GpuRealStorage : GpuStorage<real1> {
     tcapint offset, n_fast, n_slow, s_fast, s_slow;
   };
   std::vector<Bf16Shadow> shadows;
+  // column sums of the [n_fast, n_slow] matrix this storage holds, left by a producer that had the
+  // values in registers anyway (the fused cross-entropy backward); valid while colsum_version == version
+  BufferPtr colsum;
+  uint64_t colsum_version = 0U;
+  tcapint colsum_n = 0U;
 };
 struct GpuIntStorage : GpuStorage<symint> {
   GpuIntStorage(const tcapint &n, int64_t did, const bool &alloc = true) : GpuStorage<symint>(INT_GPU_DENSE, n, did, alloc) {}

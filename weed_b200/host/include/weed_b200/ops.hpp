@@ -66,5 +66,11 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
 // logits [B, T, V] -> the arg-max token of the LAST position of every sequence as a device
 // SymbolTensor [B, 1] that can be fed straight back into Sequential::forward. Lowest index wins ties.
 SymbolTensorPtr argmax_last_token(const Tensor &logits);
+// Fused cross-entropy backward that also leaves dlogits' bf16 GEMM shadow and its column sums on the
+// gradient's storage (include/weedcu.h: weedcu_cross_entropy_bwd_pack), so that the Linear node that
+// consumes dlogits next neither re-reads it to pack nor to sum. False (nothing done) when the bf16
+// operand path is off or the layout is not the dense [rows, V] one.
+bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, const Tensor &lse, const Tensor &dloss, Tensor &dlogits,
+                            tcapint rows, tcapint V);
 void triu_fill(Tensor &a, const complex &val, const tcapint diagonal = 1);
 } // namespace Weed

@@ -143,6 +143,11 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
         TensorPtr loss = wloss.lock(); // the node is owned by this tensor: a strong capture would be a cycle
         if (!loss) return;
         TensorPtr dl = std::make_shared<Tensor>(*(logits->grad));
+        if (vs == rows && Tensor::is_contiguous(dl->shape, dl->stride) && dl->storage->device == DeviceTag::GPU &&
+            Weed::cross_entropy_bwd_pack(*logits, *tg, *lse, *(loss->grad), *dl, rows, V)) {
+          logits->grad = dl;
+          return;
+        }
         int accumulate = 1;
         real1 *dl_ptr = dl->device_ptr_accumulate(accumulate);
         throw_on_error(weedcu_cross_entropy_bwd(logits->device_ptr_ro(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,

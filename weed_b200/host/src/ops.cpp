@@ -450,11 +450,66 @@ bool pack_with_column_sums(const Tensor &dy, Tensor &sums) {
   // probe first: device_ptr_overwrite() below drops the pending zero fill, so the pack must happen
   GpuRealStorage *ds = gpu_storage(dy, "pack_with_column_sums");
   for (const GpuRealStorage::Bf16Shadow &sh : ds->shadows)
-    if (sh.offset == dy.offset && sh.n_fast == M && sh.n_slow == N && sh.version == ds->version) return false;
+    if (sh.offset == dy.offset && sh.n_fast == M && sh.n_slow == N && sh.version == ds->version) {
+      // already packed; if its producer also left the column sums, they only need adding in
+      if (!ds->colsum || ds->colsum_version != ds->version || ds->colsum_n != N) return false;
+      ds->dev->Bind();
+      if (accumulate) {
+        weedcu_view v;
+        v.offset = 0U;
+        v.rank = 1;
+        v.shape[0] = N;
+        v.stride[0] = 1U;
+        weedcu_view sv = v;
+        sv.offset = sums.offset;
+        throw_on_error(weedcu_inplace_real(WEEDCU_ADD, ss->device_ptr(), &sv, (const real1 *)ds->colsum->ptr, &v, ds->dev->stream), "pack_with_column_sums");
+      } else {
+        throw_on_error(weedcu_memcpy_d2d(ss->device_ptr_overwrite() + sums.offset, ds->colsum->ptr, sizeof(real1) * (size_t)N, ds->dev->stream),
+                       "pack_with_column_sums");
+      }
+      return true;
+    }
   if ((M % 8U) || (dy.stride[1U] % 4U) || (dy.offset % 4U)) return false;
   real1 *sp = accumulate ? ss->device_ptr() : ss->device_ptr_overwrite();
   if (!bf16_operand(dy, dy.stride[0U], dy.stride[1U], M, N, true, op, sp + sums.offset, accumulate))
     throw std::runtime_error("pack_with_column_sums: streaming pack refused after the eligibility check");
+  return true;
+}
+
+static const symint *sym_ptr(const SymbolTensor &s, const char *op);
+bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, const Tensor &lse, const Tensor &dloss, Tensor &dlogits,
+                            tcapint rows, tcapint V) {
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache) return false;
+  // same eligibility as the tensor-core GEMMs that will read the shadow (matmul_impl) + the kernel's alignment rules
+  if ((rows % 8U) || rows < 64U || V < 16U || (dlogits.offset % 4U) || (logits.offset % 4U)) return false;
+  GpuRealStorage *ds = gpu_storage(dlogits, "cross_entropy_bwd_pack");
+  const int accumulate = (ds->zero_pending && covers_storage(dlogits)) ? 0 : 1;
+  GpuRealStorage::Bf16Shadow *hit = nullptr;
+  for (GpuRealStorage::Bf16Shadow &sh : ds->shadows)
+    if (sh.offset == dlogits.offset && sh.n_fast == rows && sh.n_slow == V && sh.s_fast == 1U && sh.s_slow == rows) hit = &sh;
+  if (!hit) {
+    if (ds->shadows.size() >= 4U) ds->shadows.erase(ds->shadows.begin());
+    ds->shadows.push_back(GpuRealStorage::Bf16Shadow{ds->dev->MakeBuffer(2U * ((size_t)rows * V + 8U)), 0U, dlogits.offset, rows, V, 1U, rows});
+    hit = &ds->shadows.back();
+  }
+  if (!ds->colsum || ds->colsum_n != V) {
+    ds->colsum = ds->dev->MakeBuffer(sizeof(real1) * (size_t)V);
+    ds->colsum_n = V;
+  }
+  const Dev dl = dev_of(logits, "cross_entropy_bwd_pack"), dlse = dev_of(lse, "cross_entropy_bwd_pack"), dg = dev_of(dloss, "cross_entropy_bwd_pack");
+  real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
+  const int rc = weedcu_cross_entropy_bwd_pack(dl.ptr, logits.offset, rows, V, sym_ptr(targets, "cross_entropy_bwd_pack") + targets.offset, dlse.ptr + lse.offset,
+                                               dg.ptr + dloss.offset, out, dlogits.offset, accumulate, (uint16_t *)hit->buf->ptr,
+                                               (real1 *)ds->colsum->ptr, ds->dev->stream);
+  if (rc == WEEDCU_ENOSUP) {
+    // nothing was launched; the caller's plain kernel must see the pending zero fill again if we dropped it
+    if (!accumulate) ds->FillZeros();
+    return false;
+  }
+  throw_on_error(rc, "cross_entropy_bwd_pack");
+  hit->version = ds->version;
+  ds->colsum_version = ds->version;
   return true;
 }
 
