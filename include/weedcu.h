@@ -122,6 +122,11 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
                            const weedcu_view *inv, const float *dout, const weedcu_view *doutv,
                            int accumulate, void *stream);
 
+/* Tensor::gelu forward on a dense tensor (tensor.cpp:841-851, as weedcu_unary_real(WEEDCU_GELU)) that also
+ * writes y_bf16[i] = bf16(y[i]): the GEMM operand of the Linear that follows (ff2). n % 4 == 0,
+ * 16-byte aligned x / y, 8-byte aligned y_bf16; otherwise WEEDCU_ENOSUP. */
+int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream);
+
 /* ------------------------------------------------------------------ R1-R2 reductions
  * Weed::reduce (src/ops/reduce.cpp:17-38,60-66): out[o] = sum_j a[base(o) + j*stride[axis]];
  * `a` must be contiguous (Tensor::sum makes it so, src/tensors/tensor.cpp:626), out is a dense
@@ -222,6 +227,13 @@ int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t
 int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma,
                          const float *beta, float eps, float *y, float *mean, float *rstd,
                          void *stream);
+/* The same forward that also writes y_bf16[i] = bf16(y[i]) (RNE) at the same linear index: for rows % 8 == 0
+ * that is exactly the tensor-core GEMM operand of the Linear that consumes y, so no fp32 -> bf16 pack
+ * pass follows (10 B/elem instead of 8 + 6). WEEDCU_ENOSUP (nothing done) for rows % 8 != 0, rows <= 256
+ * or unaligned buffers. y_bf16 == NULL is weedcu_layernorm_fwd. */
+int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma,
+                              const float *beta, float eps, float *y, float *mean, float *rstd,
+                              uint16_t *y_bf16, void *stream);
 /* dx += ..., dgamma[F] += sum_rows dy*xhat, dbeta[F] += sum_rows dy.
  * grad_mode 0 reproduces what the reference's autograd chain computes: its div node omits dout on
  *   the denominator branch (src/tensors/tensor.cpp:1506-1521), so the variance path contributes

@@ -720,3 +720,24 @@ int wo_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t row
   }
   return 0;
 }
+
+/* The bf16-emitting forms of LayerNorm::forward and Tensor::gelu: the fp32 result of the plain
+ * restatement plus its RNE bf16 copy at the same linear index (wo_f32_to_bf16). */
+int wo_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta,
+                          float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16) {
+  const int rc = wo_layernorm_fwd(x, rows, F, gamma, beta, eps, y, mean, rstd);
+  if (rc == 0 && y_bf16)
+    for (uint64_t i = 0; i < (uint64_t)rows * F; ++i) y_bf16[i] = wo_f32_to_bf16(y[i]);
+  return rc;
+}
+int wo_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n) {
+  wo_view v;
+  memset(&v, 0, sizeof(v));
+  v.rank = 1;
+  v.shape[0] = (uint32_t)n;
+  v.stride[0] = 1;
+  const int rc = wo_unary_real(7 /* GELU */, 0.0f, x, &v, y, &v);
+  if (rc == 0)
+    for (uint64_t i = 0; i < n; ++i) y_bf16[i] = wo_f32_to_bf16(y[i]);
+  return rc;
+}

@@ -301,6 +301,13 @@ for _lm, _nm in ((0, "softmax"), (1, "logsoftmax")):
     def _c(be, rng, lm=_lm):  # 40 x 3000 x 4 B > staging budget: online two-pass path
         return _softmax(be, rng, lm, [40, 3000], 1)
 
+    # >= 2^22 elements: the two streaming passes (row statistics split over column ranges, 128-bit apply);
+    # an odd row count takes the scalar apply, outer > 1 the per-slab indexing
+    for _shape, _axis in [([2048, 2100], 1), ([2050, 2050], 1), ([1024, 70, 64], 1), ([64, 40, 1700], 2)]:
+        @case(f"{_nm}_two_pass_{'x'.join(map(str, _shape))}_axis{_axis}")
+        def _c(be, rng, lm=_lm, shape=_shape, axis=_axis):
+            return _softmax(be, rng, lm, shape, axis)
+
     @case(f"{_nm}_noncontiguous_input")
     def _c(be, rng, lm=_lm):
         return _softmax(be, rng, lm, [12, 20], 1, stride=[24, 1])
@@ -424,6 +431,35 @@ for _rows, _F, _why in [(8, 768, "decode_step_single_launch"), (130, 1000, "sing
     @case(f"layernorm_{_rows}x{_F}_{_why}", tol=3e-5)
     def _c(be, rng, rows=_rows, F=_F):
         return _ln(be, rng, rows, F, 1)
+
+
+def _rne_ok(values, shadow_u16):
+    u = values.view(np.uint32).astype(np.uint64)
+    want = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return np.array([1.0 if np.array_equal(shadow_u16, want) else 0.0], F32)
+
+
+@case("layernorm_fwd_bf16_1032x72", tol=3e-5)
+def _c(be, rng):  # forward that also emits the bf16 GEMM operand copy of y
+    rows, F = 1032, 72
+    x = uni(rng, rows * F, -2, 2)
+    gamma, beta = uni(rng, F, 0.5, 1.5), uni(rng, F)
+    hx, hg, hb = be.buf(x), be.buf(gamma), be.buf(beta)
+    hy, hm, hr = be.buf(np.zeros_like(x)), be.buf(np.zeros(rows, F32)), be.buf(np.zeros(rows, F32))
+    hs = be.buf(np.zeros(rows * F, np.uint16))
+    be.call("layernorm_fwd_bf16", hx, U32(rows), U32(F), hg, hb, F32(np.finfo(np.float32).eps / 4), hy, hm, hr, hs)
+    y = hy.get()
+    return {"y": y, "mean": hm.get(), "rstd": hr.get(), "shadow_is_rne_of_y": _rne_ok(y, hs.get())}
+
+
+@case("gelu_fwd_bf16_4100")
+def _c(be, rng):
+    n = 4100
+    x = uni(rng, n, -4, 4)
+    hx, hy, hs = be.buf(x), be.buf(np.zeros(n, F32)), be.buf(np.zeros(n, np.uint16))
+    be.call("gelu_fwd_bf16", hx, hy, hs, U64(n))
+    y = hy.get()
+    return {"y": y, "shadow_is_rne_of_y": _rne_ok(y, hs.get())}
 
 
 @case("layernorm_20000x40_multi_tile", tol=3e-5)

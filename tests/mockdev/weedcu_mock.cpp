@@ -127,6 +127,15 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
                              float *dlogits, uint64_t d_offset, int accumulate, void *) {
   return RUN(wo_cross_entropy_bwd(logits, offset, rows, V, rs, vs, targets, lse, dloss, dlogits, d_offset, accumulate));
 }
+int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16,
+                              void *) {
+  if (y_bf16 && ((rows % 8u) || rows <= 256u)) return WEEDCU_ENOSUP;
+  return RUN(wo_layernorm_fwd_bf16(x, rows, F, gamma, beta, eps, y, mean, rstd, y_bf16));
+}
+int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *) {
+  if (n % 4u) return WEEDCU_ENOSUP;
+  return RUN(wo_gelu_fwd_bf16(x, y, y_bf16, n));
+}
 int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss, float *dlogits,
                                   uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *) {
   if (rows % 8u) return WEEDCU_ENOSUP;

@@ -7,6 +7,7 @@
 // so RT adjacent rows are tiled against all F features, staged once in shared memory, and the
 // reference's two-pass statistics (mean, then mean of centred squares) run from the staged copy.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace weedcu {
@@ -158,7 +159,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_apply_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
                            const float *__restrict__ beta, const float *__restrict__ mean,
-                           const float *__restrict__ den, float *__restrict__ y) {
+                           const float *__restrict__ den, float *__restrict__ y, __nv_bfloat16 *__restrict__ yb) {
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   if (r >= rows) return;
   float mu[VEC], dn[VEC];
@@ -191,6 +192,12 @@ layernorm_fwd_apply_kernel(const float *__restrict__ x, uint32_t rows, uint32_t 
       float *dst = y + (uint64_t)f * rows + r;
       if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
       else *dst = o[0];
+      if (VEC == 4 && yb) { // bf16 copy at the same linear index: the next Linear's GEMM operand, no pack pass
+        __nv_bfloat162 h[2];
+        h[0] = __floats2bfloat162_rn(o[0], o[VEC > 1 ? 1 : 0]);
+        h[1] = __floats2bfloat162_rn(o[VEC > 2 ? 2 : 0], o[VEC > 3 ? 3 : 0]);
+        *reinterpret_cast<uint2 *>(yb + (uint64_t)f * rows + r) = *reinterpret_cast<const uint2 *>(h);
+      }
     }
   }
 }
@@ -426,7 +433,14 @@ extern "C" {
 int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma,
                          const float *beta, float eps, float *y, float *mean, float *rstd,
                          void *stream) {
+  return weedcu_layernorm_fwd_bf16(x, rows, F, gamma, beta, eps, y, mean, rstd, nullptr, stream);
+}
+
+int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps,
+                              float *y, float *mean, float *rstd, uint16_t *y_bf16, void *stream) {
   if (!x || !gamma || !beta || !y || !rows || !F) return WEEDCU_EINVAL;
+  // the bf16 copy rides on the vectorised apply pass only
+  if (y_bf16 && ((rows % 8u) || rows <= 256u || !aligned16(x) || !aligned16(y) || !aligned16(y_bf16) || (mean && !aligned16(mean)))) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   // (the single-launch register-tile kernel was also measured at 8192 x 768: 24.1 us against 22.9 us
   // for the two streaming passes, so large inputs keep the two passes)
@@ -443,7 +457,7 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
   }
   float *tmp = nullptr; // den[rows] (+ mu[rows] when the caller does not keep the mean)
   WCU_CHECK(pool_alloc((void **)&tmp, sizeof(float) * 2 * (size_t)rows, st));
-  ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
+  ProfScope prof(WEEDCU_PROF_LAYERNORM, st, (y_bf16 ? 10.0 : 8.0) * (double)rows * F);
   const unsigned tiles = (rows + 31u) / 32u;
 #define WCU_LN_STATS(NV) layernorm_fwd_stats_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, eps, mean, rstd, tmp)
   if (F <= kLnBY * 16) WCU_LN_STATS(16);
@@ -457,9 +471,9 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
     const float *mu = mean ? mean : tmp + rows;
     const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
     if ((rows % 4u) == 0 && aligned16(x) && aligned16(y) && aligned16(mu) && fgroups <= 65535u) {
-      layernorm_fwd_apply_kernel<4><<<dim3((rows / 4u + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y);
+      layernorm_fwd_apply_kernel<4><<<dim3((rows / 4u + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y, (__nv_bfloat16 *)y_bf16);
     } else if (fgroups <= 65535u) {
-      layernorm_fwd_apply_kernel<1><<<dim3((rows + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y);
+      layernorm_fwd_apply_kernel<1><<<dim3((rows + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y, nullptr);
     } else {
       rc = WEEDCU_EINVAL;
     }

@@ -133,6 +133,122 @@ softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
     for (uint32_t j = Lc + ty; j < L; j += BY) po[(uint64_t)j * inner] = 0.0f;
 }
 
+// ----------------------------------------------------------------------------- forward, two streaming passes
+// For long rows and big tensors the staged tile kernel above is latency-bound (load, reduce,
+// synchronise, only then store: 0.37 of HBM at [8,12,1024,1024], 0.07 once a row no longer fits the
+// tile). Same split as LayerNorm: pass 1 leaves the online (max, sum exp) of every row — block = 32
+// adjacent rows x 16 warps striding the columns, 8 full-line loads in flight per thread, the vocab /
+// key range split over blockIdx.z so the grid fills the GPU whatever the row count; pass 2 is plain
+// 128-bit elementwise work. 12 B/elem of traffic (8 when the tensor fits the 126 MB L2).
+constexpr int kSmBY = 16, kSmU = 8, kSmCols = 8;
+__global__ void __launch_bounds__(32 * kSmBY)
+softmax_rows_partial_kernel(const float *__restrict__ a, uint32_t inner, uint32_t L, uint32_t cols_per_split,
+                            float *__restrict__ part_m, float *__restrict__ part_s) {
+  __shared__ float red_m[kSmBY][33];
+  __shared__ float red_s[kSmBY][33];
+  const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 32u + tx;
+  const bool live = r < inner;
+  const uint64_t slab = (uint64_t)blockIdx.y * inner * L;
+  const float *p = a + slab + r;
+  const uint32_t j_begin = blockIdx.z * cols_per_split, j_end = min(L, j_begin + cols_per_split);
+  float mx = -INFINITY, s = 0.0f;
+  if (live)
+    for (uint32_t j0 = j_begin + ty; j0 < j_end; j0 += kSmBY * kSmU) {
+      float v[kSmU];
+#pragma unroll
+      for (int u = 0; u < kSmU; ++u) {
+        const uint32_t j = j0 + u * kSmBY;
+        v[u] = (j < j_end) ? p[(uint64_t)j * inner] : -INFINITY;
+      }
+      float m8 = v[0];
+#pragma unroll
+      for (int u = 1; u < kSmU; ++u) m8 = fmaxf(m8, v[u]);
+      if (m8 > mx) { // rescale the running sum once per batch
+        s *= expf(mx - m8);
+        mx = m8;
+      }
+      if (mx > -INFINITY) {
+#pragma unroll
+        for (int u = 0; u < kSmU; ++u) s += expf(v[u] - mx);
+      }
+    }
+  red_m[ty][tx] = mx;
+  red_s[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && live) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int y = 0; y < kSmBY; ++y) M = fmaxf(M, red_m[y][tx]);
+    float S = 0.0f;
+#pragma unroll
+    for (int y = 0; y < kSmBY; ++y) {
+      const float my = red_m[y][tx];
+      if (my > -INFINITY) S += red_s[y][tx] * expf(my - M);
+    }
+    const uint64_t row = (uint64_t)blockIdx.y * inner + r, n_rows = (uint64_t)gridDim.y * inner;
+    part_m[(uint64_t)blockIdx.z * n_rows + row] = M;
+    part_s[(uint64_t)blockIdx.z * n_rows + row] = S;
+  }
+}
+// merge the column splits: M[row], S[row] (or log S for log-softmax)
+template <bool LOG>
+__global__ void __launch_bounds__(256)
+softmax_rows_finish_kernel(const float *__restrict__ part_m, const float *__restrict__ part_s, uint32_t splits, uint64_t n_rows,
+                           float *__restrict__ row_m, float *__restrict__ row_s) {
+  const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  float M = -INFINITY;
+  for (uint32_t k = 0; k < splits; ++k) M = fmaxf(M, part_m[(uint64_t)k * n_rows + row]);
+  float S = 0.0f;
+  for (uint32_t k = 0; k < splits; ++k) {
+    const float my = part_m[(uint64_t)k * n_rows + row];
+    if (my > -INFINITY) S += part_s[(uint64_t)k * n_rows + row] * expf(my - M);
+  }
+  row_m[row] = M;
+  row_s[row] = LOG ? logf(S) : S;
+}
+// out = exp(x - M) / S   or   (x - M) - log S ; VEC adjacent rows x kSmCols columns per thread
+template <bool LOG, int VEC>
+__global__ void __launch_bounds__(256)
+softmax_apply_kernel(const float *__restrict__ a, float *__restrict__ out, uint32_t inner, uint32_t L,
+                     const float *__restrict__ row_m, const float *__restrict__ row_s) {
+  const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
+  if (r >= inner) return;
+  const uint64_t slab = (uint64_t)blockIdx.z * inner * L, rbase = (uint64_t)blockIdx.z * inner + r;
+  float M[VEC], S[VEC];
+  if (VEC == 4) {
+    *reinterpret_cast<float4 *>(M) = *reinterpret_cast<const float4 *>(row_m + rbase);
+    *reinterpret_cast<float4 *>(S) = *reinterpret_cast<const float4 *>(row_s + rbase);
+  } else {
+    M[0] = row_m[rbase];
+    S[0] = row_s[rbase];
+  }
+  const uint32_t j_begin = blockIdx.y * kSmCols, j_end = min(L, j_begin + kSmCols);
+  float xv[kSmCols][VEC];
+#pragma unroll
+  for (int i = 0; i < kSmCols; ++i) {
+    const uint32_t j = j_begin + i;
+    if (j < j_end) {
+      const float *src = a + slab + (uint64_t)j * inner + r;
+      if (VEC == 4) *reinterpret_cast<float4 *>(xv[i]) = *reinterpret_cast<const float4 *>(src);
+      else xv[i][0] = *src;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSmCols; ++i) {
+    const uint32_t j = j_begin + i;
+    if (j < j_end) {
+      float o[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = LOG ? ((xv[i][k] - M[k]) - S[k]) : (expf(xv[i][k] - M[k]) / S[k]);
+      float *dst = out + slab + (uint64_t)j * inner + r;
+      if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
+      else *dst = o[0];
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- forward, contiguous
 // inner == 1: each row is L contiguous floats; one block per row.
 template <bool LOG>
@@ -521,6 +637,42 @@ static int softmax_fwd_impl(const float *a, const weedcu_view *av, int axis, flo
     if (inner == 1) {
       softmax_contig_fwd<LOG><<<(unsigned)outer, 256, 0, st>>>(pa, po, L);
       return after_launch();
+    }
+    // big problems: two streaming passes (row statistics, then elementwise); small ones (a few tiles,
+    // short rows) stay on the single staged-tile kernel, where one launch matters more than overlap
+    const uint64_t n_rows64 = inner * outer;
+    if (inner >= 32 && outer <= 65535 && (uint64_t)total >= (1u << 22) && L >= 64) {
+      const uint32_t row_tiles = (uint32_t)((inner + 31) / 32);
+      uint32_t splits = (uint32_t)((4ull * kNumSMs + (uint64_t)row_tiles * outer - 1) / ((uint64_t)row_tiles * outer));
+      const uint32_t max_splits = (L + kSmBY * kSmU - 1) / (kSmBY * kSmU);
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+      if (splits > 65535u) splits = 65535u;
+      uint32_t cps = (L + splits - 1) / splits;
+      cps = (cps + kSmBY * kSmU - 1) / (kSmBY * kSmU) * (kSmBY * kSmU);
+      splits = (L + cps - 1) / cps;
+      const uint32_t cgroups = (L + kSmCols - 1) / kSmCols;
+      if (cgroups <= 65535u && splits <= 65535u) {
+        float *ws = nullptr; // part_m, part_s [splits][rows]; row_m, row_s [rows]
+        const uint64_t rows_up = (n_rows64 + 3) & ~(uint64_t)3;
+        WCU_CHECK(pool_alloc((void **)&ws, sizeof(float) * (2 * (size_t)splits * n_rows64 + 2 * rows_up), st));
+        float *pm = ws, *ps = pm + (size_t)splits * n_rows64, *rm = ps + (size_t)splits * n_rows64, *rs = rm + rows_up;
+        softmax_rows_partial_kernel<<<dim3(row_tiles, (unsigned)outer, splits), 32 * kSmBY, 0, st>>>(pa, (uint32_t)inner, L, cps, pm, ps);
+        int rc = after_launch();
+        if (rc == 0) {
+          softmax_rows_finish_kernel<LOG><<<(unsigned)((n_rows64 + 255) / 256), 256, 0, st>>>(pm, ps, splits, n_rows64, rm, rs);
+          rc = after_launch();
+        }
+        if (rc == 0) {
+          if ((inner % 4) == 0 && aligned16(pa) && aligned16(po))
+            softmax_apply_kernel<LOG, 4><<<dim3((unsigned)((inner / 4 + 255) / 256), cgroups, (unsigned)outer), 256, 0, st>>>(pa, po, (uint32_t)inner, L, rm, rs);
+          else
+            softmax_apply_kernel<LOG, 1><<<dim3((unsigned)((inner + 255) / 256), cgroups, (unsigned)outer), 256, 0, st>>>(pa, po, (uint32_t)inner, L, rm, rs);
+          rc = after_launch();
+        }
+        pool_free(ws, st);
+        return rc;
+      }
     }
     if (outer <= 65535) return launch_strided_fwd<LOG>(pa, po, (uint32_t)inner, L, (uint32_t)outer, PlainLoad(), st);
   }

@@ -66,6 +66,21 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
 // logits [B, T, V] -> the arg-max token of the LAST position of every sequence as a device
 // SymbolTensor [B, 1] that can be fed straight back into Sequential::forward. Lowest index wins ties.
 SymbolTensorPtr argmax_last_token(const Tensor &logits);
+// Producer-side bf16 operand shadows. A kernel that is about to overwrite the dense tensor `out` may
+// also emit bf16(out) at the same linear index; when the Linear that consumes `out` next views it as
+// [rows, cols] (rows contiguous, rows % 8 == 0) that copy IS its tensor-core GEMM operand and the pack
+// pass disappears. begin_ returns the buffer to fill (nullptr: bf16 path off or layout not eligible);
+// end_ is called after the producing kernel has been issued through out's write accessor.
+struct OutputShadow {
+  GpuRealStorage *storage = nullptr;
+  size_t index = 0U;
+  uint16_t *ptr = nullptr;
+};
+OutputShadow begin_output_shadow(const Tensor &out, tcapint cols);
+void end_output_shadow(const OutputShadow &os);
+// LayerNorm::forward's fused kernel / Tensor::gelu's forward with the shadow emitted when eligible
+void layernorm_forward(const Tensor &x, tcapint rows, tcapint features, const Tensor &gamma, const Tensor &beta, real1 eps, Tensor &y, Tensor &mean,
+                       Tensor &rstd);
 // Fused cross-entropy backward that also leaves dlogits' bf16 GEMM shadow and its column sums on the
 // gradient's storage (include/weedcu.h: weedcu_cross_entropy_bwd_pack), so that the Linear node that
 // consumes dlogits next neither re-reads it to pack nor to sum. False (nothing done) when the bf16

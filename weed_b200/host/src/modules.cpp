@@ -124,10 +124,7 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
   TensorPtr y = Tensor::allocate_like(x->shape, *x, DType::REAL, rg, false);
   TensorPtr mean = Tensor::allocate_like(std::vector<tcapint>{rows}, *x, DType::REAL, false, false);
   TensorPtr rstd = Tensor::allocate_like(std::vector<tcapint>{rows}, *x, DType::REAL, false, false);
-  throw_on_error(weedcu_layernorm_fwd(x->device_ptr_ro() + x->offset, rows, features, gamma->device_ptr_ro() + gamma->offset,
-                                      beta->device_ptr_ro() + beta->offset, eps, y->device_ptr(), mean->device_ptr(), rstd->device_ptr(),
-                                      x->stream()),
-                 "LayerNorm::forward");
+  Weed::layernorm_forward(*x, rows, features, *gamma, *beta, eps, *y, *mean, *rstd);
   if (rg) {
     ParameterPtr g = gamma, b = beta;
     std::vector<TensorPtr> parents;

@@ -362,7 +362,71 @@ void tanh(const Tensor &a, Tensor &out) { unary(WEEDCU_TANH, 0, a, out, "tanh");
 void sin(const Tensor &a, Tensor &out) { unary(WEEDCU_SIN, 0, a, out, "sin"); }
 void cos(const Tensor &a, Tensor &out) { unary(WEEDCU_COS, 0, a, out, "cos"); }
 void abs(const Tensor &a, Tensor &out) { unary(WEEDCU_ABS, 0, a, out, "abs"); }
-void gelu(const Tensor &a, Tensor &out) { unary(WEEDCU_GELU, 0, a, out, "gelu"); }
+OutputShadow begin_output_shadow(const Tensor &out, tcapint cols) {
+  OutputShadow os;
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || !cols) return os;
+  if (out.storage->device != DeviceTag::GPU || out.offset || !covers_storage(out)) return os;
+  const tcapint n = out.storage->size;
+  if (n % cols) return os;
+  const tcapint rows = n / cols;
+  // what matmul_impl / bf16_operand will ask for: A = [rows, cols], rows contiguous, tensor-core eligible
+  if ((rows % 8U) || rows < 64U || cols < 32U) return os;
+  GpuRealStorage *s = gpu_storage(out, "output shadow");
+  for (size_t k = 0U; k < s->shadows.size(); ++k) {
+    const GpuRealStorage::Bf16Shadow &c = s->shadows[k];
+    if (c.offset == 0U && c.n_fast == rows && c.n_slow == cols && c.s_fast == 1U && c.s_slow == rows) {
+      os.storage = s;
+      os.index = k;
+      os.ptr = (uint16_t *)c.buf->ptr;
+      return os;
+    }
+  }
+  if (s->shadows.size() >= 4U) s->shadows.erase(s->shadows.begin());
+  s->shadows.push_back(GpuRealStorage::Bf16Shadow{s->dev->MakeBuffer(2U * ((size_t)rows * cols + 8U)), 0U, 0U, rows, cols, 1U, rows});
+  os.storage = s;
+  os.index = s->shadows.size() - 1U;
+  os.ptr = (uint16_t *)s->shadows.back().buf->ptr;
+  return os;
+}
+void end_output_shadow(const OutputShadow &os) {
+  if (os.storage) os.storage->shadows[os.index].version = os.storage->version;
+}
+
+void gelu(const Tensor &a, Tensor &out) {
+  // dense input and output of the same layout: the forward can leave the bf16 operand of the Linear
+  // that follows (ff2 reads [B*T, d_ff]) in the same pass
+  if (a.shape.size() >= 2U && a.shape == out.shape && a.stride == out.stride && !a.offset && covers_storage(a) && a.storage->device == DeviceTag::GPU) {
+    const OutputShadow os = begin_output_shadow(out, out.shape.back());
+    if (os.ptr) {
+      const Dev da = dev_of(a, "gelu"), dout = dev_out(out, "gelu", true);
+      const int rc = weedcu_gelu_fwd_bf16(da.ptr, dout.ptr, os.ptr, out.storage->size, dout.stream);
+      if (rc == 0) {
+        end_output_shadow(os);
+        return;
+      }
+      if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "gelu");
+    }
+  }
+  unary(WEEDCU_GELU, 0, a, out, "gelu");
+}
+void layernorm_forward(const Tensor &x, tcapint rows, tcapint features, const Tensor &gamma, const Tensor &beta, real1 eps, Tensor &y, Tensor &mean,
+                       Tensor &rstd) {
+  const Dev dx = dev_of(x, "LayerNorm::forward"), dg = dev_of(gamma, "LayerNorm::forward"), db = dev_of(beta, "LayerNorm::forward");
+  const OutputShadow os = begin_output_shadow(y, features);
+  const Dev dy = dev_out(y, "LayerNorm::forward", true), dm = dev_out(mean, "LayerNorm::forward", true), dr = dev_out(rstd, "LayerNorm::forward", true);
+  if (os.ptr) {
+    const int rc = weedcu_layernorm_fwd_bf16(dx.ptr + x.offset, rows, features, dg.ptr + gamma.offset, db.ptr + beta.offset, eps, dy.ptr, dm.ptr, dr.ptr,
+                                             os.ptr, dy.stream);
+    if (rc == 0) {
+      end_output_shadow(os);
+      return;
+    }
+    if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "LayerNorm::forward");
+  }
+  throw_on_error(weedcu_layernorm_fwd(dx.ptr + x.offset, rows, features, dg.ptr + gamma.offset, db.ptr + beta.offset, eps, dy.ptr, dm.ptr, dr.ptr, dy.stream),
+                 "LayerNorm::forward");
+}
 void pow(const Tensor &a, const real1 &p, Tensor &out) { unary(WEEDCU_POW, p, a, out, "pow"); }
 void exp(const Tensor &a, const real1 &b, Tensor &out) { unary(WEEDCU_EXP, (real1)std::log((real1_s)b), a, out, "exp"); }
 void log(const Tensor &a, const real1 &b, Tensor &out) {
