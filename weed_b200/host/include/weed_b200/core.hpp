@@ -389,6 +389,10 @@ struct Tensor : public BaseTensor {
   NodePtr grad_node;
   TensorPtr grad;
   bool requires_grad = false;
+  // how many autograd Nodes list this tensor as a parent (= how many gradient contributions it will
+  // receive); a non-leaf with exactly one lets Tensor::add's backward hand it the incoming gradient
+  // buffer instead of a copy (tensor.cpp: adopt_incoming_gradient)
+  uint32_t consumers = 0U;
 
   Tensor() {}
   Tensor(const std::vector<tcapint> &shp, const std::vector<tcapint> &str, const bool &rg = false, const bool &s = true,
@@ -524,7 +528,10 @@ struct Node {
   std::vector<TensorPtr> parents;
   std::function<void()> backward;
   Node(const std::vector<TensorPtr> &p, const std::function<void()> &b) : parents(p), backward(b) {
-    for (auto &t : parents) t->make_gradient();
+    for (auto &t : parents) {
+      t->make_gradient();
+      ++t->consumers;
+    }
   }
 };
 

@@ -734,14 +734,37 @@ TensorPtr Tensor::add(TensorPtr a, TensorPtr b) { // tensor.cpp:1084-1103
   if (rg) make_add_node(a, b, out);
   return out;
 }
+// d(a + b)/da = 1: the parent's gradient contribution IS out's gradient. When the parent is a non-leaf
+// that only this node feeds (consumers == 1: nothing else will ever accumulate into its gradient) and
+// its own gradient buffer is still an untouched lazy zero fill of the same dense layout, the parent
+// simply adopts out's gradient buffer, read-only, instead of a 8 B/elem copy — the residual adds of
+// a transformer block hand [B,T,d] gradients to the W_o / ff2 outputs this way. out's gradient is
+// complete when its node runs and nothing writes that buffer afterwards (a parent with a second
+// consumer, which WILL be accumulated into, still gets its own copy), so intermediate gradients
+// stay readable. Leaves never adopt: their gradients persist across steps (zero_grad, optimiser).
+static bool adopt_incoming_gradient(const TensorPtr &parent, const TensorPtr &out_grad) {
+  if (!backend_config().fused || !backend_config().lazy_zero) return false;
+  if (!parent->grad_node || parent->consumers != 1U || !parent->grad || parent.get() == out_grad.get()) return false;
+  const TensorPtr &g = parent->grad;
+  if (g->storage->device != DeviceTag::GPU || out_grad->storage->device != DeviceTag::GPU || g->storage->dtype != DType::REAL) return false;
+  if (g->shape != out_grad->shape || g->stride != out_grad->stride || g->shape != parent->shape) return false;
+  if (g->offset || out_grad->offset || g->storage->size != out_grad->storage->size) return false;
+  if (!dense_like(*g, g->shape) || g->get_broadcast_size() != g->storage->size) return false;
+  GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
+  if (!gs->zero_pending) return false; // something already accumulated here
+  TensorPtr adopted = view_copy(out_grad);
+  adopted->requires_grad = g->requires_grad;
+  parent->grad = adopted;
+  return true;
+}
 void Tensor::make_add_node(TensorPtr a, TensorPtr b, TensorPtr out) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
     if (!out) return;
     TensorPtr out_grad = view_copy(out->grad);
-    if (a->requires_grad) accumulate(a, out_grad, *out_grad, false);
-    if (b->requires_grad) accumulate(b, out_grad, *out_grad, false);
+    if (a->requires_grad && !adopt_incoming_gradient(a, out_grad)) accumulate(a, out_grad, *out_grad, false);
+    if (b->requires_grad && !adopt_incoming_gradient(b, out_grad)) accumulate(b, out_grad, *out_grad, false);
   });
 }
 TensorPtr Tensor::sub(TensorPtr a, TensorPtr b) { // tensor.cpp:1404-1423
