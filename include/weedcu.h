@@ -323,6 +323,14 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
 int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
                      uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
                      int accumulate, const float *col_bias, void *stream);
+/* `groups` (1..3) products A * B_g -> C_g (+ col_bias_g) that share the A operand and all dimensions
+ * (the W_q / W_k / W_v projections of one activation, multihead_attention.cpp:151-153) as ONE launch
+ * of the same kernel: bit-identical to `groups` weedcu_gemm_bf16 calls, one prologue instead of three.
+ * b, c, col_bias: host arrays of `groups` device pointers (col_bias or its entries may be NULL). */
+int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups,
+                             const uint16_t *const *b, int b_major, uint64_t ldb, float *const *c, uint64_t ldc,
+                             uint32_t M, uint32_t N, uint32_t K, int accumulate, const float *const *col_bias,
+                             void *stream);
 /* strided fp32 -> packed bf16 (round-to-nearest-even); dst is a dense [rows, cols] matrix whose
  * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,

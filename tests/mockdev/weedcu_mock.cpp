@@ -239,6 +239,15 @@ int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_
     }
   return 0;
 }
+int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b, int b_major, uint64_t ldb, float *const *c, uint64_t ldc,
+                             uint32_t M, uint32_t N, uint32_t K, int accumulate, const float *const *col_bias, void *stream) {
+  if (!groups || groups > 3 || !b || !c) return WEEDCU_EINVAL;
+  for (uint32_t g = 0; g < groups; ++g) {
+    const int rc = weedcu_gemm_bf16(a, a_major, lda, b[g], b_major, ldb, c[g], ldc, M, N, K, accumulate, col_bias ? col_bias[g] : nullptr, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
 int weedcu_gemm_workspace_bytes(uint32_t, uint32_t, uint32_t, uint32_t, int, uint64_t *bytes) { if (bytes) *bytes = 0; return 0; }
 // collectives: single-process identity (world size 1); the gloo world_size-2 tests patch these from Python
 int weedcu_nccl_load(const char *) { return 0; }

@@ -144,3 +144,33 @@ def test_gemm_bf16_col_bias_epilogue(gpu, oracle, M, N, K):
     B = bf(b).reshape(N, K).T.astype(np.float64)
     want = (A @ B + bias[None, :].astype(np.float64)).astype(np.float32)
     assert cases.rel_err(got, want) <= 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(8192, 768, 768, 3), (300, 200, 96, 2), (1024, 130, 256, 3), (256, 64, 64, 1)])
+def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups):
+    """weedcu_gemm_bf16_grouped (the W_q / W_k / W_v projections as one launch) is bit-identical to
+    `groups` weedcu_gemm_bf16 calls: same tiles, same k order, only the tile loop is shared."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K + groups)
+    r8 = lambda x: (x + 7) // 8 * 8
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a = rng.uniform(-1, 1, M * K).astype(np.float32)
+    ha = gpu.buf(a)
+    pa = gpu.buf(np.zeros(r8(M) * K + 8, np.uint16))
+    gpu.call("pack_bf16", ha, U64(0), U32(1), U32(M), U32(M), U32(K), pa, I32(1))
+    pbs, biases, sep, grp = [], [], [], []
+    for g in range(groups):
+        b = rng.uniform(-1, 1, K * N).astype(np.float32)
+        hb = gpu.buf(b)
+        pb = gpu.buf(np.zeros(r8(K) * N + 8, np.uint16))
+        gpu.call("pack_bf16", hb, U64(0), U32(K), U32(1), U32(N), U32(K), pb, I32(0))
+        pbs.append(pb)
+        biases.append(gpu.buf(rng.uniform(-2, 2, N).astype(np.float32)))
+        sep.append(gpu.buf(np.zeros(M * N, np.float32)))
+        grp.append(gpu.buf(np.full(M * N, 5.0, np.float32)))
+        gpu.call("gemm_bf16", pa, I32(1), U64(r8(M)), pb, I32(0), U64(r8(K)), sep[g], U64(M), U32(M), U32(N), U32(K), I32(0), biases[g])
+    PtrArr = C.c_void_p * groups
+    gpu.call("gemm_bf16_grouped", pa, I32(1), U64(r8(M)), U32(groups), PtrArr(*[p.ptr for p in pbs]), I32(0), U64(r8(K)),
+             PtrArr(*[c.ptr for c in grp]), U64(M), U32(M), U32(N), U32(K), I32(0), PtrArr(*[b.ptr for b in biases]))
+    for g in range(groups):
+        assert np.array_equal(sep[g].get(), grp[g].get()), f"group {g}"

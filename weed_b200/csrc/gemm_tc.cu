@@ -30,6 +30,15 @@ struct Params {
   uint32_t splits, kb_per_split; // split-K: work unit = (tile, k-slice); slices meet in C by TMA reduce-add
   const float *col_bias; // optional [N]: C[m,n] = sum_k A B + col_bias[n]  (Linear::forward's bias add)
   int tma_store; // C goes out through TMA (needs 16-B aligned base / leading dimension); else direct stores
+  // grouped launch: `groups` products that share A (Q / K / V projections of one activation): tile
+  // column tn belongs to group tn / tiles_n_group; each group has its own B map, C map / pointer, bias
+  uint32_t groups, tiles_n_group;
+  float *c_grp[3];
+  const float *bias_grp[3];
+};
+constexpr uint32_t kMaxGroups = 3;
+struct alignas(64) TensorMaps {
+  CUtensorMap m[kMaxGroups];
 };
 
 constexpr uint32_t EPI_COLS = 32;                             // columns per epilogue chunk
@@ -46,8 +55,8 @@ template <uint32_t BLOCK_N, uint32_t STAGES> struct SmemLayout {
 // A_MN / B_MN: operand is MN-major (1) or K-major (0).
 template <uint32_t BLOCK_N, uint32_t STAGES, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, Params p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TensorMaps tmBs,
+                 const __grid_constant__ TensorMaps tmCs, Params p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   constexpr uint32_t NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 32)    ? 32
@@ -78,7 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBs.m[0]) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < STAGES; ++s) {
@@ -104,7 +113,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
         const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
-        const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
+        const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+        const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+        const CUtensorMap *tmB = &tmBs.m[grp];
         const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -121,9 +132,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (B_MN) {
 #pragma unroll
             for (uint32_t i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_3d(b_dst + i * (64 * BLOCK_K * 2), &tmB, full_bar(stage), (int)(n0 + 64 * i), k0, (int)z);
+              tma_load_3d(b_dst + i * (64 * BLOCK_K * 2), tmB, full_bar(stage), (int)(n0 + 64 * i), k0, (int)z);
           } else {
-            tma_load_3d(b_dst, &tmB, full_bar(stage), k0, (int)n0, (int)z);
+            tma_load_3d(b_dst, tmB, full_bar(stage), k0, (int)n0, (int)z);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -169,9 +180,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
-      const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (t / p.tiles_m) * BLOCK_N;
+      const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+      const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+      const CUtensorMap *tmC = &tmCs.m[grp];
+      const float *col_bias = p.groups > 1 ? p.bias_grp[grp] : p.col_bias;
+      float *c_base = p.groups > 1 ? p.c_grp[grp] : p.c;
       const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
-      const bool add_bias = p.col_bias && ks == 0; // exactly one k-slice contributes the bias
+      const bool add_bias = col_bias && ks == 0; // exactly one k-slice contributes the bias
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t m = m0 + q * 32 + lane;
@@ -188,7 +203,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f; // lane j holds the bias of column c0 + j
-          if (add_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
+          if (add_bias && n0 + c0 + lane < p.N) bias_lane = col_bias[n0 + c0 + lane];
           tmem_ld_wait();
           if (add_bias) {
 #pragma unroll
@@ -205,22 +220,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
           epi_bar_sync();
           if (leader && n0 + c0 < p.N) {
-            if (p.accumulate || p.splits > 1) tma_reduce_add_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
-            else tma_store_3d(&tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            if (p.accumulate || p.splits > 1) tma_reduce_add_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            else tma_store_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
             bulk_commit();
           } else if (leader) {
             bulk_commit(); // keep the group count in step with the buffer rotation
           }
         }
       } else {
-        float *crow = p.c + (uint64_t)z * p.c_bs + m;
+        float *crow = c_base + (uint64_t)z * p.c_bs + m;
         const bool full_tile = (m0 + BLOCK_M <= p.M) && (n0 + BLOCK_N <= p.N);
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f;
-          if (add_bias && n0 + c0 + lane < p.N) bias_lane = p.col_bias[n0 + c0 + lane];
+          if (add_bias && n0 + c0 + lane < p.N) bias_lane = col_bias[n0 + c0 + lane];
           tmem_ld_wait();
           if (add_bias) {
 #pragma unroll
@@ -313,7 +328,7 @@ static bool make_c_map(CUtensorMap *map, float *c, uint64_t M, uint64_t N, uint6
 }
 
 template <uint32_t BLOCK_N, uint32_t STAGES>
-static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const Params &p, int a_major,
+static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
                       int b_major, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
@@ -324,7 +339,7 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
   {                                                                                                \
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
     ensure_dynamic_smem((const void *)k, (int)smem);                                               \
-    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, p);                                          \
+    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmBs, tmCs, p);                                        \
   }
   if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
   else if (a_major) WCU_TC_LAUNCH(1, 0)
@@ -334,25 +349,31 @@ static int launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUte
   return after_launch();
 }
 
-int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
-                     int b_major, uint64_t ldb, uint64_t b_bs, float *c, uint64_t ldc, uint64_t c_bs,
-                     uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
-                     const float *col_bias) {
-  if (!a || !b || !c || !M || !N || !K || !batch) return WEEDCU_EINVAL;
+// `groups` (<= 3) products A x B_g -> C_g (+ bias_g) that share the A operand and every dimension run
+// as ONE launch: their tiles join one persistent tile loop, so the ~10 us of per-launch prologue /
+// exposed last epilogue is paid once and the tail wave is filled by the other groups' tiles.
+int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, uint32_t groups,
+                             const uint16_t *const *b, int b_major, uint64_t ldb, uint64_t b_bs, float *const *c, uint64_t ldc,
+                             uint64_t c_bs, uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
+                             const float *const *col_bias) {
+  if (!a || !b || !c || !M || !N || !K || !batch || !groups || groups > kMaxGroups) return WEEDCU_EINVAL;
+  for (uint32_t g = 0; g < groups; ++g)
+    if (!b[g] || !c[g]) return WEEDCU_EINVAL;
   // Tile width and split-K are chosen together by a small cost model: a CTA processes its work units
   // (tile, k-slice) one after the other, so the launch costs  waves x BLOCK_N x (k-blocks per slice +
   // ~3 k-blocks of un-overlapped prologue/epilogue). Few-tile problems (weight gradients: M, N =
   // layer widths, K = batch*seq) get split along K, slices meeting in C by TMA reduce-add; tile
   // counts just above a multiple of 148 get a narrower tile instead of a nearly empty last wave.
   const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
-  const bool c_tma = (((uintptr_t)c) & 15u) == 0 && (ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0);
+  bool c_tma = (ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0);
+  for (uint32_t g = 0; g < groups; ++g) c_tma = c_tma && (((uintptr_t)c[g]) & 15u) == 0;
   uint32_t block_n = 256, best_s = 1;
   double best_cost = 1e300;
   const uint32_t cand[3] = {256, 192, 128};
   for (uint32_t ci = 0; ci < 3; ++ci) {
     const uint32_t bn = cand[ci];
     if (bn > 128 && N <= bn - 64) continue; // do not pad a narrow N into a wide tile
-    const uint32_t tiles = tiles_m * ((N + bn - 1) / bn) * batch;
+    const uint32_t tiles = tiles_m * ((N + bn - 1) / bn) * groups * batch;
     for (uint32_t sp = 1; sp <= 16; ++sp) {
       if (sp > 1 && (!c_tma || sp * 4u > num_kb)) break;
       const uint32_t kb_per = (num_kb + sp - 1) / sp, units = tiles * ((num_kb + kb_per - 1) / kb_per);
@@ -366,40 +387,62 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
       }
     }
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA;
+  TensorMaps tmBs, tmCs;
   int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, b, b_major, N, K, ldb, batch, b_bs, block_n);
-  if (rc) return rc;
   Params p;
-  p.c = c;
+  p.c = c[0];
   p.ldc = ldc;
   p.c_bs = c_bs;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.tiles_m = tiles_m;
-  p.tiles_n = (N + block_n - 1) / block_n;
+  p.tiles_n_group = (N + block_n - 1) / block_n;
+  p.tiles_n = p.tiles_n_group * groups;
+  p.groups = groups;
   p.accumulate = accumulate;
-  p.col_bias = col_bias;
-  CUtensorMap tmC;
-  p.tma_store = make_c_map(&tmC, c, M, N, ldc, batch, c_bs) ? 1 : 0;
+  p.col_bias = col_bias ? col_bias[0] : nullptr;
+  p.tma_store = 1;
+  for (uint32_t g = 0; g < kMaxGroups; ++g) {
+    const uint32_t src = g < groups ? g : 0;
+    rc = make_operand_map(&tmBs.m[g], b[src], b_major, N, K, ldb, batch, b_bs, block_n);
+    if (rc) return rc;
+    if (p.tma_store && !make_c_map(&tmCs.m[g], c[src], M, N, ldc, batch, c_bs)) p.tma_store = 0;
+    p.c_grp[g] = c[src];
+    p.bias_grp[g] = col_bias ? col_bias[src] : nullptr;
+  }
   if (!p.tma_store) {
-    tmC = tmA; // unused by the kernel, but must be a valid descriptor
+    for (uint32_t g = 0; g < kMaxGroups; ++g) tmCs.m[g] = tmA; // unused by the kernel, but must be valid descriptors
     best_s = 1;
   }
   p.kb_per_split = (num_kb + best_s - 1) / best_s;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits > 1 && !accumulate) { // slices meet by reduce-add: C starts from zero
-    if (batch == 1 && ldc == M) {
-      WCU_CHECK(cudaMemsetAsync(c, 0, sizeof(float) * (size_t)M * N, st));
-    } else {
-      for (uint32_t z = 0; z < batch; ++z)
-        WCU_CHECK(cudaMemset2DAsync(c + (uint64_t)z * c_bs, ldc * sizeof(float), 0, (size_t)M * sizeof(float), N, st));
+    for (uint32_t g = 0; g < groups; ++g) {
+      if (batch == 1 && ldc == M) {
+        WCU_CHECK(cudaMemsetAsync(c[g], 0, sizeof(float) * (size_t)M * N, st));
+      } else {
+        for (uint32_t z = 0; z < batch; ++z)
+          WCU_CHECK(cudaMemset2DAsync(c[g] + (uint64_t)z * c_bs, ldc * sizeof(float), 0, (size_t)M * sizeof(float), N, st));
+      }
     }
   }
-  ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch);
-  if (block_n == 256) return launch_cfg<256, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
-  if (block_n == 192) return launch_cfg<192, 4>(tmA, tmB, tmC, p, a_major, b_major, st);
-  return launch_cfg<128, 6>(tmA, tmB, tmC, p, a_major, b_major, st);
+  ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch * groups);
+  if (block_n == 256) return launch_cfg<256, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  if (block_n == 192) return launch_cfg<192, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  return launch_cfg<128, 6>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+}
+
+int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
+                     int b_major, uint64_t ldb, uint64_t b_bs, float *c, uint64_t ldc, uint64_t c_bs,
+                     uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
+                     const float *col_bias) {
+  if (!a || !b || !c) return WEEDCU_EINVAL;
+  const uint16_t *bs[1] = {b};
+  float *cs[1] = {c};
+  const float *biases[1] = {col_bias};
+  return launch_gemm_bf16_grouped(a, a_major, lda, a_bs, 1, bs, b_major, ldb, b_bs, cs, ldc, c_bs, M, N, K, batch, accumulate, st,
+                                  col_bias ? biases : nullptr);
 }
 
 } // namespace tc
@@ -525,6 +568,13 @@ int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_
                      int accumulate, const float *col_bias, void *stream) {
   return tc::launch_gemm_bf16(a, a_major, lda, 0, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
                               resolve_stream(stream), col_bias);
+}
+
+int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b,
+                             int b_major, uint64_t ldb, float *const *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                             int accumulate, const float *const *col_bias, void *stream) {
+  return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, groups, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
+                                      resolve_stream(stream), col_bias);
 }
 
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,

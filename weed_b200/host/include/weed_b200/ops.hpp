@@ -66,6 +66,10 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
 // logits [B, T, V] -> the arg-max token of the LAST position of every sequence as a device
 // SymbolTensor [B, 1] that can be fed straight back into Sequential::forward. Lowest index wins ties.
 SymbolTensorPtr argmax_last_token(const Tensor &logits);
+// outs[g] = a * ws[g] + biases[g] for up to three weights of one shape as ONE grouped tensor-core launch
+// (the W_q / W_k / W_v projections); false (nothing computed) when the bf16 operand path does not apply.
+bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
+                         const std::vector<Tensor *> &outs);
 // Producer-side bf16 operand shadows. A kernel that is about to overwrite the dense tensor `out` may
 // also emit bf16(out) at the same linear index; when the Linear that consumes `out` next views it as
 // [rows, cols] (rows contiguous, rows % 8 == 0) that copy IS its tensor-core GEMM operand and the pack

@@ -271,7 +271,22 @@ void MultiHeadAttention::migrate_gpu() {
 
 TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attention.cpp:145-356
   const symint B = (symint)x->shape[0], T = (symint)x->shape[1];
-  TensorPtr Q = W_q->forward(x), K = W_k->forward(x), V = W_v->forward(x);
+  // the three projections read the same x: one grouped tensor-core launch when the bf16 path applies
+  // (each output keeps the node Linear::forward would give it), otherwise three Linear::forward calls
+  TensorPtr Q, K, V;
+  if (W_q->bias && W_k->bias && W_v->bias) {
+    const std::vector<TensorPtr> qkv = Tensor::linear_grouped(x, {W_q->weight, W_k->weight, W_v->weight}, {W_q->bias, W_k->bias, W_v->bias});
+    if (qkv.size() == 3U) {
+      Q = qkv[0];
+      K = qkv[1];
+      V = qkv[2];
+    }
+  }
+  if (!Q) {
+    Q = W_q->forward(x);
+    K = W_k->forward(x);
+    V = W_v->forward(x);
+  }
   if (use_kv_cache && kv_quant_bits > 0)
     throw std::domain_error("4-bit TurboQuant KV cache (multihead_attention.cpp:205-277) is host-loop code outside this backend's "
                             "scope; construct with kv_quant_bits = 0 or set use_kv_cache = false");

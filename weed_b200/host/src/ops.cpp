@@ -501,6 +501,43 @@ void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const
 void matmul(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 0); }
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 1); }
 bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out) { return matmul_impl(a, b, out, 0, &bias); }
+bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
+                         const std::vector<Tensor *> &outs) {
+  const BackendConfig &cfg = backend_config();
+  const size_t G = ws.size();
+  if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || G < 2U || G > 3U || biases.size() != G || outs.size() != G) return false;
+  if (a.shape.size() != 2U) return false;
+  const tcapint M = a.shape[0U], K = a.shape[1U], N = ws[0]->shape[1U];
+  if (M < 64U || N < 16U || K < 32U) return false;
+  for (size_t g = 0U; g < G; ++g) {
+    const Tensor &w = *ws[g], &o = *outs[g], &bi = *biases[g];
+    if (w.shape.size() != 2U || w.shape[0U] != K || w.shape[1U] != N || w.stride != ws[0]->stride) return false;
+    if (o.shape.size() != 2U || o.shape[0U] != M || o.shape[1U] != N || o.stride[0U] != 1U || o.stride[1U] != outs[0]->stride[1U] || !covers_storage(o)) return false;
+    if (bi.storage->size != N || bi.storage->device != DeviceTag::GPU) return false;
+  }
+  validate_all_same_device({&a, ws[0], outs[0]}, "matmul_bias_grouped");
+  Bf16Operand pa, pb[3];
+  if (!bf16_operand(a, a.stride[0U], a.stride[1U], M, K, true, pa)) return false;
+  for (size_t g = 0U; g < G; ++g) {
+    if (!bf16_operand(*ws[g], ws[g]->stride[1U], ws[g]->stride[0U], N, K, false, pb[g])) return false;
+    if (pb[g].major != pb[0].major || pb[g].ld != pb[0].ld) return false;
+  }
+  const uint16_t *bptr[3];
+  real1 *cptr[3];
+  const real1 *biasptr[3];
+  void *stream = nullptr;
+  for (size_t g = 0U; g < G; ++g) {
+    const Dev dc = dev_out(*outs[g], "matmul_bias_grouped", true);
+    stream = dc.stream;
+    bptr[g] = pb[g].ptr;
+    cptr[g] = dc.ptr + outs[g]->offset;
+    biasptr[g] = dev_of(*biases[g], "matmul_bias_grouped").ptr + biases[g]->offset;
+  }
+  const int rc = weedcu_gemm_bf16_grouped(pa.ptr, pa.major, pa.ld, (uint32_t)G, bptr, pb[0].major, pb[0].ld, cptr, outs[0]->stride[1U], M, N, K, 0, biasptr, stream);
+  if (rc == WEEDCU_ENOSUP) return false;
+  throw_on_error(rc, "matmul_bias_grouped");
+  return true;
+}
 bool pack_with_column_sums(const Tensor &dy, Tensor &sums) {
   const BackendConfig &cfg = backend_config();
   if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || dy.shape.size() != 2U) return false;

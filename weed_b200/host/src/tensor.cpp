@@ -980,6 +980,13 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
   const tcapint as0 = a2->shape[0U];
   TensorPtr out = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
   if (!Weed::matmul_bias(*a2, *w, *bias, *out)) return nullptr;
+  return finish_linear(a, w, bias, out, rg);
+}
+
+// everything Tensor::linear does after the product: final shape, the Parameter mutation of `y + bias`, the node
+TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg) {
+  const bool needs_flatten = (a->shape.size() > 2U);
+  const symint M = (symint)a->shape[a->shape.size() - 2], N = (symint)w->shape[1U];
   if (needs_flatten) {
     std::vector<symint> final_shape;
     for (size_t i = 0; i < a->shape.size() - 2; ++i) final_shape.push_back((symint)a->shape[i]);
@@ -1012,6 +1019,42 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
     });
   }
   return out;
+}
+
+std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases) {
+  const BackendConfig &cfg = backend_config();
+  const size_t G = ws.size();
+  if (!cfg.fused || cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache || G < 2U || G > 3U || biases.size() != G) return {};
+  if (a->shape.size() < 2U || a->storage->device != DeviceTag::GPU) return {};
+  for (size_t g = 0U; g < G; ++g) {
+    const TensorPtr &w = ws[g], &bias = biases[g];
+    if (!w || !bias || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back() || w->shape != ws[0]->shape) return {};
+    if (w->storage->device != DeviceTag::GPU || bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U] ||
+        bias->storage->device != DeviceTag::GPU)
+      return {};
+  }
+  if (a->get_broadcast_size() / a->shape.back() <= 16U) return {}; // decode steps take the skinny kernel per layer
+  const bool needs_flatten = (a->shape.size() > 2U);
+  const symint K = (symint)a->shape.back(), M = (symint)a->shape[a->shape.size() - 2], N = (symint)ws[0]->shape[1U];
+  symint batch = 1;
+  for (size_t i = 0; i < a->shape.size() - 2; ++i) batch *= (symint)a->shape[i];
+  TensorPtr a2 = a;
+  if (needs_flatten) a2 = reshape(a, {batch * M, K});
+  const tcapint as0 = a2->shape[0U];
+  std::vector<TensorPtr> outs(G);
+  std::vector<bool> rgs(G);
+  std::vector<const Tensor *> wp(G), bp(G);
+  std::vector<Tensor *> op(G);
+  for (size_t g = 0U; g < G; ++g) {
+    rgs[g] = a->requires_grad || ws[g]->requires_grad || biases[g]->requires_grad;
+    outs[g] = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rgs[g], false);
+    wp[g] = ws[g].get();
+    bp[g] = biases[g].get();
+    op[g] = outs[g].get();
+  }
+  if (!Weed::matmul_bias_grouped(*a2, wp, bp, op)) return {};
+  for (size_t g = 0U; g < G; ++g) outs[g] = finish_linear(a, ws[g], biases[g], outs[g], rgs[g]);
+  return outs;
 }
 
 void Tensor::make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.cpp:1328-1402
