@@ -197,6 +197,12 @@ int weedcu_attn_softmax_real(const float *scores, float *out, uint32_t batch, ui
 int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
                          uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                          int causal, void *stream);
+/* The same entry that also writes out_bf16[i] = bf16(out[i]) (RNE) at the same linear index: the A operand
+ * of the W_o product that follows (no pack pass). out_bf16 == NULL is weedcu_attention_fwd;
+ * WEEDCU_ENOSUP additionally when B % 4 != 0 or out is not 16-byte aligned. */
+int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v, float *out, uint16_t *out_bf16,
+                                 uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
+                                 int causal, void *stream);
 /* Fused cross-entropy over logits[rows, V] (row stride rs, vocab stride vs):
  * cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34) = -mean_rows lsm[row, target].
  * fwd writes per-row log-sum-exp (lse[rows]) and the scalar loss; bwd does

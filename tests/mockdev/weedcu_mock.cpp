@@ -109,6 +109,14 @@ int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *
   if ((T % 8u) || T < 64u || (hd != 64u && T > 1024u) || hd < 16u || (hd % 8u)) return WEEDCU_ENOSUP; // same envelope as the device entry
   return RUN(wo_attention_fwd(q, k, v, out, B, T, H, hd, divisor, mask_val, (causal && T > 1) ? 1 : 0));
 }
+int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v, float *out, uint16_t *out_bf16, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor,
+                                 float mask_val, int causal, void *stream) {
+  if (out_bf16 && (B % 4u)) return WEEDCU_ENOSUP;
+  const int rc = weedcu_attention_fwd(q, k, v, out, B, T, H, hd, divisor, mask_val, causal, stream);
+  if (rc == 0 && out_bf16 && !g_nocompute)
+    for (uint64_t i = 0; i < (uint64_t)B * T * H * hd; ++i) out_bf16[i] = wo_f32_to_bf16(out[i]);
+  return rc;
+}
 int weedcu_attention_decode(const float *q, const float *k, const float *v, float *k_cache, float *v_cache, float *out, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd,
                             uint32_t S, uint32_t cache_len, float divisor, float mask_val, int causal, void *) {
   if (hd > 64u) return WEEDCU_ENOSUP;

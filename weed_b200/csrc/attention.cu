@@ -111,8 +111,8 @@ heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t 
 // along t, 128-bit stores of 4 consecutive b.
 template <int LPT>
 __global__ void __launch_bounds__(256)
-unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32_t B, uint32_t T, uint32_t H,
-                   uint32_t hd, uint32_t tt) {
+unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, __nv_bfloat16 *__restrict__ outb, uint32_t B,
+                   uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
   extern __shared__ float tile[]; // [B][tt + 4]
   const uint32_t pitch = tt + 4u;
   const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
@@ -139,7 +139,14 @@ unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32
   for (uint32_t i = threadIdx.x; i < n4; i += 256u) {
     const uint32_t e = i << 2, t = e / B, b = e - t * B;
     const float *p = tile + b * pitch + t;
-    dst[i] = make_float4(p[0], p[pitch], p[2 * pitch], p[3 * pitch]);
+    const float4 o = make_float4(p[0], p[pitch], p[2 * pitch], p[3 * pitch]);
+    dst[i] = o;
+    if (outb) { // bf16 copy at the same linear index: the A operand of the W_o product that follows
+      __nv_bfloat162 h2[2];
+      h2[0] = __floats2bfloat162_rn(o.x, o.y);
+      h2[1] = __floats2bfloat162_rn(o.z, o.w);
+      reinterpret_cast<uint2 *>(outb + ((uint64_t)c * T + t0) * B)[i] = *reinterpret_cast<const uint2 *>(h2);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
@@ -240,7 +247,14 @@ using namespace weedcu;
 extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *out, uint32_t B,
                                     uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                                     int causal, void *stream) {
+  return weedcu_attention_fwd_bf16out(q, k, v, out, nullptr, B, T, H, hd, divisor, mask_val, causal, stream);
+}
+
+extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v, float *out, uint16_t *out_bf16,
+                                            uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
+                                            int causal, void *stream) {
   if (!q || !k || !v || !out || !B || !T || !H || !hd) return WEEDCU_EINVAL;
+  if (out_bf16 && ((B % 4u) || !aligned16(out) || (((uintptr_t)out_bf16) & 7u))) return WEEDCU_ENOSUP; // rides on the vectorised relayout only
   // tensor-map constraints of the two products (16-byte row pitch) and the register softmax
   static const bool flash_on = [] {
     const char *e = getenv("WEEDCU_FLASH");
@@ -317,11 +331,13 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
     const uint32_t vtt = (4096u / B) & ~7u;
     if ((B % 4u) == 0 && vtt >= 8u && aligned16(oc) && aligned16(out)) {
       const uint32_t vt = vtt < T ? vtt : T;
-      unheads_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C), 256, (size_t)B * (vt + 4u) * sizeof(float), st>>>(oc, out, B, T, H, hd, vt);
+      unheads_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C), 256, (size_t)B * (vt + 4u) * sizeof(float), st>>>(oc, out, (__nv_bfloat16 *)out_bf16, B, T, H, hd, vt);
+    } else if (out_bf16) {
+      rc = WEEDCU_ENOSUP; // (checked up front for the same conditions; kept as a guard)
     } else {
       unheads_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C), 256, tile_bytes, st>>>(oc, out, B, T, H, hd, tt);
     }
-    rc = after_launch();
+    if (rc == 0) rc = after_launch();
   }
   pool_free(ws, st);
   return rc;

@@ -304,9 +304,15 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
       // one entry point: head relayout fused with the bf16 operand conversion, probabilities
       // emitted as bf16 straight into the P V product (include/weedcu.h: weedcu_attention_fwd)
       out = Tensor::allocate_like(std::vector<tcapint>{Bu, Tu, H * hd}, *x, DType::REAL, false, false);
-      const int rc = weedcu_attention_fwd(Q->device_ptr_ro() + Q->offset, K->device_ptr_ro() + K->offset, V->device_ptr_ro() + V->offset,
-                                          out->device_ptr(), Bu, Tu, H, hd, std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0, x->stream());
-      if (rc == 0) return W_o->forward(out);
+      // the relayout back to [B, T, C] also leaves the bf16 operand of the W_o product (no pack pass)
+      const OutputShadow os = (Bu % 4U) == 0U ? begin_output_shadow(*out, H * hd) : OutputShadow();
+      int rc = weedcu_attention_fwd_bf16out(Q->device_ptr_ro() + Q->offset, K->device_ptr_ro() + K->offset, V->device_ptr_ro() + V->offset,
+                                            out->device_ptr(), os.ptr, Bu, Tu, H, hd, std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0,
+                                            x->stream());
+      if (rc == 0) {
+        end_output_shadow(os);
+        return W_o->forward(out);
+      }
       if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "attention");
     }
     auto to_heads = [&](const TensorPtr &lin) { // [B,T,(h,j)] -> [T, hd, B, H] contiguous
