@@ -126,6 +126,12 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
  * writes y_bf16[i] = bf16(y[i]): the GEMM operand of the Linear that follows (ff2). n % 4 == 0,
  * 16-byte aligned x / y, 8-byte aligned y_bf16; otherwise WEEDCU_ENOSUP. */
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream);
+/* gelu_grad (tensor.cpp:841-851 backward; as weedcu_unary_grad_real(WEEDCU_GELU)) on a dense [rows, cols]
+ * matrix with rows contiguous, fused with the preparation of the Linear backward that consumes din:
+ * din (+)= dout * gelu'(in), din_bf16[i] = bf16(din[i]), colsum[c] = sum_r din[r, c] (stored; fixed order).
+ * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned. */
+int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols,
+                          int accumulate, uint16_t *din_bf16, float *colsum, void *stream);
 
 /* ------------------------------------------------------------------ R1-R2 reductions
  * Weed::reduce (src/ops/reduce.cpp:17-38,60-66): out[o] = sum_j a[base(o) + j*stride[axis]];

@@ -741,3 +741,25 @@ int wo_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) y_bf16[i] = wo_f32_to_bf16(y[i]);
   return rc;
 }
+
+/* gelu_grad followed by the bf16 copy and the column sums the next Linear backward takes of din. */
+int wo_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,
+                      uint16_t *din_bf16, float *colsum) {
+  wo_view v;
+  memset(&v, 0, sizeof(v));
+  v.rank = 1;
+  v.shape[0] = rows * cols;
+  v.stride[0] = 1;
+  const int rc = wo_unary_grad_real(7 /* GELU */, din, &v, in, &v, dout, &v, accumulate);
+  if (rc) return rc;
+  for (uint32_t c = 0; c < cols; ++c) {
+    float s = 0.0f;
+    for (uint32_t r = 0; r < rows; ++r) {
+      const float d = din[r + (uint64_t)c * rows];
+      din_bf16[r + (uint64_t)c * rows] = wo_f32_to_bf16(d);
+      s += d;
+    }
+    colsum[c] = s;
+  }
+  return 0;
+}

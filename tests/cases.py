@@ -462,6 +462,17 @@ def _c(be, rng):
     return {"y": y, "shadow_is_rne_of_y": _rne_ok(y, hs.get())}
 
 
+for _rows, _cols, _acc in [(1032, 50, 0), (2048, 24, 1)]:
+    @case(f"gelu_grad_pack_{_rows}x{_cols}_acc{_acc}", tol=2e-5)
+    def _c(be, rng, rows=_rows, cols=_cols, acc=_acc):
+        n = rows * cols
+        hd, hx, hg = be.buf(uni(rng, n)), be.buf(uni(rng, n, -4, 4)), be.buf(uni(rng, n))
+        hs, hc = be.buf(np.zeros(n, np.uint16)), be.buf(np.full(cols, 3.0, F32))
+        be.call("gelu_grad_pack", hd, hx, hg, U32(rows), U32(cols), I32(acc), hs, hc)
+        d = hd.get()
+        return {"din": d, "shadow_is_rne_of_din": _rne_ok(d, hs.get()), "colsum": hc.get()}
+
+
 @case("layernorm_20000x40_multi_tile", tol=3e-5)
 def _c(be, rng):  # more row tiles than blocks: the per-block column sums span several tiles
     return _ln(be, rng, 20000, 40, 1)

@@ -144,6 +144,10 @@ int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n,
   if (n % 4u) return WEEDCU_ENOSUP;
   return RUN(wo_gelu_fwd_bf16(x, y, y_bf16, n));
 }
+int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate, uint16_t *din_bf16, float *colsum, void *) {
+  if (rows % 8u) return WEEDCU_ENOSUP;
+  return RUN(wo_gelu_grad_pack(din, in, dout, rows, cols, accumulate, din_bf16, colsum));
+}
 int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss, float *dlogits,
                                   uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *) {
   if (rows % 8u) return WEEDCU_ENOSUP;

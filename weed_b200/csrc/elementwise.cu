@@ -239,6 +239,79 @@ gelu_fwd_bf16_kernel(const float *__restrict__ x, float *__restrict__ y, __nv_bf
   }
 }
 
+// GELU backward fused with what the Linear behind it needs next: din (+)= dout * gelu'(in) for a dense
+// [rows, cols] matrix (rows contiguous), plus the bf16 GEMM operand copy of din and its column sums
+// (that Linear's bias gradient). Same block shape as the LayerNorm / cross-entropy apply passes:
+// 256 threads x 4 adjacent rows x 8 columns, column partials per row chunk.
+constexpr int kGgCols = 8;
+__global__ void __launch_bounds__(256)
+gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__restrict__ dout, uint32_t rows, uint32_t cols,
+                      int accumulate, __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  __shared__ float red[8][kGgCols];
+  const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * 4u;
+  const bool live = r < rows;
+  const uint32_t j0 = blockIdx.y * kGgCols;
+  float cs[kGgCols];
+#pragma unroll
+  for (int i = 0; i < kGgCols; ++i) cs[i] = 0.0f;
+  if (live) {
+    constexpr int U = 4;
+#pragma unroll
+    for (int i0 = 0; i0 < kGgCols; i0 += U) {
+      float4 xv[U], gv[U], dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + i0 + u;
+        if (j < cols) {
+          const uint64_t off = (uint64_t)j * rows + r;
+          xv[u] = *reinterpret_cast<const float4 *>(in + off);
+          gv[u] = *reinterpret_cast<const float4 *>(dout + off);
+          dv[u] = accumulate ? *reinterpret_cast<const float4 *>(din + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + i0 + u;
+        if (j < cols) {
+          float4 o;
+          o.x = dv[u].x + gv[u].x * gelu_dfdx(xv[u].x);
+          o.y = dv[u].y + gv[u].y * gelu_dfdx(xv[u].y);
+          o.z = dv[u].z + gv[u].z * gelu_dfdx(xv[u].z);
+          o.w = dv[u].w + gv[u].w * gelu_dfdx(xv[u].w);
+          const uint64_t off = (uint64_t)j * rows + r;
+          *reinterpret_cast<float4 *>(din + off) = o;
+          __nv_bfloat162 h[2];
+          h[0] = __floats2bfloat162_rn(o.x, o.y);
+          h[1] = __floats2bfloat162_rn(o.z, o.w);
+          *reinterpret_cast<uint2 *>(shadow + off) = *reinterpret_cast<const uint2 *>(h);
+          cs[i0 + u] += (o.x + o.y) + (o.z + o.w);
+        }
+      }
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kGgCols; ++i) {
+    const float t = warp_sum(cs[i]);
+    if (lane == 0) red[w][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kGgCols && j0 + threadIdx.x < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    part[(uint64_t)blockIdx.x * cols + j0 + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t cols, float *__restrict__ colsum) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float t = 0.0f;
+  for (uint32_t c = 0; c < nchunks; ++c) t += part[(uint64_t)c * cols + j];
+  colsum[j] = t;
+}
+
 // ------------------------------------------------------------------------------- optimisers
 struct AdamChunk {
   float *p;
@@ -447,6 +520,26 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
     WCU_GRAD_CASE(WEEDCU_COS)
   }
   return WEEDCU_EINVAL;
+}
+
+int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,
+                          uint16_t *din_bf16, float *colsum, void *stream) {
+  if (!din || !in || !dout || !din_bf16 || !colsum || !rows || !cols) return WEEDCU_EINVAL;
+  if ((rows % 8u) || !aligned16(din) || !aligned16(in) || !aligned16(dout) || !aligned16(din_bf16)) return WEEDCU_ENOSUP;
+  const uint32_t nchunks = (rows + 1023u) / 1024u, cgroups = (cols + kGgCols - 1) / kGgCols;
+  if (cgroups > 65535u) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  float *part = nullptr;
+  WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * cols, st));
+  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (accumulate ? 18.0 : 14.0) * (double)rows * cols);
+  gelu_grad_pack_kernel<<<dim3(nchunks, cgroups), 256, 0, st>>>(din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
+  int rc = after_launch();
+  if (rc == 0) {
+    colsum_finish_kernel<<<(cols + 255u) / 256u, 256, 0, st>>>(part, nchunks, cols, colsum);
+    rc = after_launch();
+  }
+  pool_free(part, st);
+  return rc;
 }
 
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream) {

@@ -439,7 +439,45 @@ void tanh_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(W
 void sin_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_SIN, din, in, dout, "sin_grad"); }
 void cos_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_COS, din, in, dout, "cos_grad"); }
 void abs_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_ABS, din, in, dout, "abs_grad"); }
-void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) { unary_grad(WEEDCU_GELU, din, in, dout, "gelu_grad"); }
+void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) {
+  // din = gradient of the pre-activation [.., d_ff] that ff1's Linear node consumes next: leave its bf16
+  // GEMM operand copy and its column sums (ff1's bias gradient) on the storage in the same pass
+  // (include/weedcu.h: weedcu_gelu_grad_pack; picked up by pack_with_column_sums / bf16_operand)
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision == WEEDCU_GEMM_BF16 && cfg.fused && cfg.operand_cache && din.shape.size() >= 2U && din.shape == in.shape &&
+      din.shape == dout.shape && din.stride == in.stride && din.stride == dout.stride && !din.offset && !in.offset && !dout.offset &&
+      covers_storage(din) && covers_storage(in) && covers_storage(dout) && din.storage->device == DeviceTag::GPU) {
+    const tcapint cols = din.shape.back(), rows = din.storage->size / cols;
+    if ((rows % 8U) == 0U && rows >= 64U && cols >= 16U) {
+      validate_all_same_device({&din, &in, &dout}, "gelu_grad");
+      GpuRealStorage *ds = gpu_storage(din, "gelu_grad");
+      const int accumulate = ds->zero_pending ? 0 : 1;
+      GpuRealStorage::Bf16Shadow *hit = nullptr;
+      for (GpuRealStorage::Bf16Shadow &sh : ds->shadows)
+        if (sh.offset == 0U && sh.n_fast == rows && sh.n_slow == cols && sh.s_fast == 1U && sh.s_slow == rows) hit = &sh;
+      if (!hit) {
+        if (ds->shadows.size() >= 4U) ds->shadows.erase(ds->shadows.begin());
+        ds->shadows.push_back(GpuRealStorage::Bf16Shadow{ds->dev->MakeBuffer(2U * ((size_t)rows * cols + 8U)), 0U, 0U, rows, cols, 1U, rows});
+        hit = &ds->shadows.back();
+      }
+      if (!ds->colsum || ds->colsum_n != cols) {
+        ds->colsum = ds->dev->MakeBuffer(sizeof(real1) * (size_t)cols);
+        ds->colsum_n = cols;
+      }
+      const Dev di = dev_of(in, "gelu_grad"), dg = dev_of(dout, "gelu_grad");
+      real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
+      const int rc = weedcu_gelu_grad_pack(out, di.ptr, dg.ptr, rows, cols, accumulate, (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr, ds->dev->stream);
+      if (rc == 0) {
+        hit->version = ds->version;
+        ds->colsum_version = ds->version;
+        return;
+      }
+      if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "gelu_grad");
+      if (!accumulate) ds->FillZeros(); // nothing was launched: restore the pending zero fill the plain kernel relies on
+    }
+  }
+  unary_grad(WEEDCU_GELU, din, in, dout, "gelu_grad");
+}
 
 static void full_reduce(const Tensor &a, Tensor &out, bool is_mean) {
   validate_all_same_device({&a, &out}, "SumKernel::sum");
