@@ -14,6 +14,3 @@ timeout 600 python tools/decode_bench.py > gpurun_out/decode_fp32.log 2>&1
 tail -n 1 gpurun_out/decode_fp32.log | cut -c1-300
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r01_launches_final.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-clocks > gpurun_out/bench_ncu.log 2>&1
 tail -1 gpurun_out/bench_ncu.log | cut -c1-100
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16_kernel|flash_attn|layernorm_fwd_stats|layernorm_fwd_apply|layernorm_bwd_rows|layernorm_bwd_apply|ce_bwd_pack|ce_fwd_partial|adam_multi|gelu_fwd_bf16|heads_pack_vec|pack_bf16_colsum" --launch-skip 1400 -c 60 -f -o gpurun_out/r01_full_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-clocks > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log | cut -c1-200
-ls -la gpurun_out/*.ncu-rep
