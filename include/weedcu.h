@@ -343,6 +343,12 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
                              const uint16_t *const *b, int b_major, uint64_t ldb, float *const *c, uint64_t ldc,
                              uint32_t M, uint32_t N, uint32_t K, int accumulate, const float *const *col_bias,
                              void *stream);
+/* Tile family of the bf16 tensor-core GEMM: 0 = cost model over single-CTA 128 x N tiles and CTA-pair
+ * (tcgen05 cta_group::2, two SMs of a TPC on one 256 x N tile) kernels (default; env WEEDCU_GEMM_MODE),
+ * 1 = single-CTA tiles only, 2 = CTA pairs wherever the operands allow,
+ * pair * 1000000 + BLOCK_N * 1000 + splits = one forced configuration (tuning sweeps). Results of the
+ * families differ only by fp32 summation order across split-K slices. */
+int weedcu_gemm_set_mode(int mode);
 /* strided fp32 -> packed bf16 (round-to-nearest-even); dst is a dense [rows, cols] matrix whose
  * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,

@@ -146,14 +146,82 @@ def test_gemm_bf16_col_bias_epilogue(gpu, oracle, M, N, K):
     assert cases.rel_err(got, want) <= 1e-4
 
 
+def _bf16_bits(x):
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def _bf16_widen(bits):
+    return (bits.astype(np.uint32) << 16).view(np.float32)
+
+
+def _operand(rng, mn, k, major):
+    """bf16 [mn, k] operand in the layout weedcu_gemm_bf16 takes: major 1 = mn contiguous, 0 = k contiguous;
+    returns (device array with the padded leading dimension, ld, exact fp64 values)."""
+    r8 = lambda x: (x + 7) // 8 * 8
+    bits = _bf16_bits(rng.uniform(-1, 1, (mn, k)))
+    ld = r8(mn) if major else r8(k)
+    dev = np.zeros((k, ld) if major else (mn, ld), np.uint16)
+    if major:
+        dev[:, :mn] = bits.T
+    else:
+        dev[:, :k] = bits
+    return dev.reshape(-1), ld, _bf16_widen(bits).astype(np.float64)
+
+
+PAIR_CASES = [  # M, N, K, a_major, b_major, mode (pair * 1e6 + BLOCK_N * 1e3 + splits), accumulate, bias
+    (256, 256, 64, 1, 0, 1256001, 0, 0), (256, 256, 64, 0, 0, 1256001, 0, 0), (256, 256, 64, 1, 1, 1256001, 0, 0),
+    (1024, 512, 768, 1, 0, 1256001, 0, 1), (1024, 512, 768, 1, 1, 1256001, 1, 0), (1024, 512, 768, 0, 0, 1256001, 0, 0),
+    (1024, 384, 768, 1, 0, 1192001, 0, 1), (1024, 384, 768, 0, 0, 1192001, 1, 0),
+    (1024, 384, 512, 1, 0, 1128001, 0, 1), (1024, 384, 512, 1, 1, 1128001, 0, 0), (1024, 384, 512, 0, 0, 1128001, 1, 0),
+    (768, 1000, 2048, 0, 0, 1256004, 0, 0), (768, 1000, 2048, 0, 0, 1256004, 1, 0), (768, 520, 1024, 1, 1, 1128002, 0, 0),
+    (300, 200, 96, 1, 0, 1256001, 0, 1), (900, 330, 200, 1, 1, 1256001, 0, 0), (388, 520, 136, 0, 0, 1192001, 0, 1),
+    (8192, 768, 768, 1, 0, 1256001, 0, 1), (8192, 3072, 768, 1, 0, 1192001, 0, 1), (8192, 768, 3072, 1, 1, 1128001, 1, 0),
+    (4104, 1544, 264, 1, 0, 0, 0, 1), (4104, 1544, 264, 1, 1, 2, 1, 0), (768, 3072, 8192, 0, 0, 2, 1, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,am,bm,mode,acc,bias", PAIR_CASES, ids=[f"{c[0]}x{c[1]}x{c[2]}_a{c[3]}b{c[4]}_mode{c[5]}_acc{c[6]}_bias{c[7]}" for c in PAIR_CASES])
+def test_gemm_bf16_cta_pair_matches_model(gpu, M, N, K, am, bm, mode, acc, bias):
+    """The cta_group::2 kernel (two SMs on one 256 x BLOCK_N tile, leader-issued MMA, remote barrier
+    arrivals) against the exact product of the bf16-rounded operands: every operand majorness, all three
+    tile widths, split-K slices meeting by reduce-add, C +=, the bias epilogue, ragged edges where the
+    peer CTA's half of a tile is partly or wholly out of range."""
+    import ctypes as C
+    rng = np.random.default_rng(M * 7 + N * 3 + K + mode)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, A = _operand(rng, M, K, am)
+    b_dev, ldb, B = _operand(rng, N, K, bm)
+    c0 = rng.uniform(-1, 1, M * N).astype(np.float32) if acc else np.full(M * N, 7.0, np.float32)
+    hb = rng.uniform(-2, 2, N).astype(np.float32)
+    pa, pb, hc, hbias = gpu.buf(a_dev), gpu.buf(b_dev), gpu.buf(c0), gpu.buf(hb)
+    assert gpu.lib.weedcu_gemm_set_mode(C.c_int(mode)) == 0
+    try:
+        gpu.call("gemm_bf16", pa, I32(am), U64(lda), pb, I32(bm), U64(ldb), hc, U64(M), U32(M), U32(N), U32(K), I32(acc),
+                 hbias if bias else C.c_void_p(0))
+        got = hc.get().reshape(N, M).T
+        gpu.sync()
+    finally:
+        gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
+    want = A @ B.T
+    if bias:
+        want = want + hb[None, :].astype(np.float64)
+    if acc:
+        want = want + c0.reshape(N, M).T.astype(np.float64)
+    assert np.all(np.isfinite(got))
+    assert cases.rel_err(got, want.astype(np.float32)) <= 1e-4
+
+
+@pytest.mark.parametrize("mode", [256001, 192001, 1256001, 1128001])
 @pytest.mark.parametrize("M,N,K,groups", [(8192, 768, 768, 3), (300, 200, 96, 2), (1024, 130, 256, 3), (256, 64, 64, 1)])
-def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups):
+def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups, mode):
     """weedcu_gemm_bf16_grouped (the W_q / W_k / W_v projections as one launch) is bit-identical to
     `groups` weedcu_gemm_bf16 calls: same tiles, same k order, only the tile loop is shared."""
     import ctypes as C
     rng = np.random.default_rng(M + N + K + groups)
     r8 = lambda x: (x + 7) // 8 * 8
     U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    gpu.lib.weedcu_gemm_set_mode(C.c_int(mode))  # one fixed tile configuration (single-CTA or CTA-pair) for both sides
     a = rng.uniform(-1, 1, M * K).astype(np.float32)
     ha = gpu.buf(a)
     pa = gpu.buf(np.zeros(r8(M) * K + 8, np.uint16))
@@ -172,5 +240,6 @@ def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups):
     PtrArr = C.c_void_p * groups
     gpu.call("gemm_bf16_grouped", pa, I32(1), U64(r8(M)), U32(groups), PtrArr(*[p.ptr for p in pbs]), I32(0), U64(r8(K)),
              PtrArr(*[c.ptr for c in grp]), U64(M), U32(M), U32(N), U32(K), I32(0), PtrArr(*[b.ptr for b in biases]))
+    gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
     for g in range(groups):
         assert np.array_equal(sep[g].get(), grp[g].get()), f"group {g}"

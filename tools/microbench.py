@@ -307,6 +307,69 @@ def bench_gemm(results, peaks, which):
             rec(f"matmul_real_bf16_incl_pack_M{M}_N{N}_K{K}", ms, 2.0 * M * N * K, "pack fp32->bf16 + tcgen05")
 
 
+def bench_tune(results, peaks):
+    """Tile-configuration sweep over the GEMM shapes of the C5 step: every (family, BLOCK_N, splits)
+    forced through weedcu_gemm_set_mode, next to what the cost model picks (mode 0). The table is
+    what gemm_tc.cu's tile_cost_us() is calibrated against."""
+    peak = peaks.get("bf16_tflops", 1590.0)
+    r8 = lambda x: (x + 7) // 8 * 8
+    # (label, M, N, K, a_major, b_major, accumulate, groups)
+    shapes = [("qkv_fwd_grouped", 8192, 768, 768, 1, 0, 0, 3), ("wo_fwd", 8192, 768, 768, 1, 0, 0, 1), ("ff1_fwd", 8192, 3072, 768, 1, 0, 0, 1),
+              ("ff2_fwd", 8192, 768, 3072, 1, 0, 0, 1), ("head_fwd", 8192, 50257, 768, 1, 0, 0, 1),
+              ("wo_dA", 8192, 768, 768, 1, 1, 0, 1), ("ff1_dA", 8192, 768, 3072, 1, 1, 0, 1), ("ff2_dA", 8192, 3072, 768, 1, 1, 0, 1),
+              ("head_dA", 8192, 768, 50257, 1, 1, 0, 1),
+              ("wo_dB", 768, 768, 8192, 0, 0, 1, 1), ("ff1_dB", 768, 3072, 8192, 0, 0, 1, 1), ("ff2_dB", 3072, 768, 8192, 0, 0, 1, 1),
+              ("head_dB", 768, 50257, 8192, 0, 0, 1, 1), ("square_4096", 4096, 4096, 4096, 1, 0, 0, 1), ("square_8192", 8192, 8192, 8192, 1, 0, 0, 1)]
+    for (label, M, N, K, am, bm, acc, groups) in shapes:
+        lda, ldb = r8(M if am else K), r8(N if bm else K)
+        a = torch.randn(lda * (K if am else M), device="cuda").to(torch.bfloat16)
+        bs = [torch.randn(ldb * (K if bm else N), device="cuda").to(torch.bfloat16) for _ in range(groups)]
+        cs = [torch.zeros(M * N, device="cuda") for _ in range(groups)]
+        PtrArr = C.c_void_p * groups
+        bp, cp = PtrArr(*[t.data_ptr() for t in bs]), PtrArr(*[t.data_ptr() for t in cs])
+
+        def run(i):
+            call("gemm_bf16_grouped", P(a), I32(am), U64(lda), U32(groups), bp, I32(bm), U64(ldb), cp, U64(M), U32(M), U32(N), U32(K), I32(acc),
+                 C.c_void_p(0))
+
+        flops = 2.0 * M * N * K * groups
+        tiles128 = ((M + 127) // 128) * ((N + 127) // 128) * groups
+        split_list = (1,) if tiles128 > 4 * 148 else (1, 2, 3, 4, 6, 8)
+        modes = [0, 1, 2]
+        for pair in (0, 1):
+            for bn in (256, 192, 128):
+                if pair and bn == 192 and bm:
+                    continue
+                if bn > 128 and N <= bn - 64:
+                    continue
+                for sp in split_list:
+                    if sp > 1 and sp * 4 > (K + 63) // 64:
+                        continue
+                    modes.append(pair * 1000000 + bn * 1000 + sp)
+                    if not pair and sp == 1:
+                        modes.append(bn * 1000 + 100 + sp)      # variant 1: direct stores, no staging
+                        if bn == 256:
+                            modes.append(bn * 1000 + 200 + sp)  # variant 2: 4 stages + 2 staging buffers
+        best = None
+        for mode in modes:
+            lib.weedcu_gemm_set_mode(C.c_int(mode))
+            try:
+                ms = timeit(run, 1, iters=8, warmup=2)
+            except Exception as e:  # an unsupported forced configuration says so
+                print(f"tune_{label:18s} mode {mode:8d}  unsupported ({e})", flush=True)
+                continue
+            finally:
+                lib.weedcu_gemm_set_mode(C.c_int(0))
+            tf = flops / ms / 1e9
+            results.append({"kernel": f"tune_{label}", "mode": mode, "ms": round(ms, 4), "TFLOPs": round(tf, 1), "frac_of_bf16_peak": round(tf / peak, 3)})
+            print(f"tune_{label:18s} mode {mode:8d}  {ms * 1000:9.2f} us  {tf:8.1f} TFLOP/s  {tf / peak:5.3f}", flush=True)
+            if mode >= 1000 and (best is None or ms < best[1]):
+                best = (mode, ms)
+        if best:
+            print(f"tune_{label:18s} BEST forced mode {best[0]} at {best[1] * 1000:.2f} us", flush=True)
+        del a, bs, cs
+
+
 def main():
     global lib, STREAM
     ap = argparse.ArgumentParser()
@@ -327,6 +390,8 @@ def main():
         bench_ew(results, peaks)
     if args.group in ("attn", "all"):
         bench_attn(results, peaks)
+    if args.group == "tune":
+        bench_tune(results, peaks)
     if args.group in ("gemm", "all", "f32", "tc"):
         bench_gemm(results, peaks, args.group)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -14,6 +14,7 @@
 //             MMA warp --tmem_full[a]--> epilogue warps --tmem_empty[a]--> MMA warp (2 TMEM accs)
 // so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace weedcu {
 namespace tc {
@@ -44,20 +45,27 @@ struct alignas(64) TensorMaps {
 constexpr uint32_t EPI_COLS = 32;                             // columns per epilogue chunk
 constexpr uint32_t EPI_BUF_BYTES = EPI_COLS * BLOCK_M * 4;    // one [32 cols][128 rows] fp32 staging buffer
 
-template <uint32_t BLOCK_N, uint32_t STAGES> struct SmemLayout {
+// EPI_BUFS staging buffers: the TMA store of chunk i must have finished READING its buffer before chunk
+// i + EPI_BUFS may refill it, and that read-completion arrives ~2000 cycles after the issue while the
+// TMA unit is busy with the operand loads (ncu: the leader's cp.async.bulk.wait_group.read and the
+// other epilogue warps' barrier wait behind it were the top stalls, and the MMA warp spun on
+// tmem_empty). Two buffers therefore capped the epilogue at one 16 KB chunk per ~1250 cycles —
+// 6.5 us per 128 x 256 tile, longer than the 12 k-blocks of a K = 768 product; four keep 64 KB in flight.
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS> struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t EPI_OFF = STAGES * (A_BYTES + B_BYTES);
-  static constexpr uint32_t BAR_OFF = EPI_OFF + 2 * EPI_BUF_BYTES;
-  static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t BAR_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;
+  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 2 * EPI_BUFS; // full/empty, tmem full/empty, staging full/empty
+  static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
 };
 
 // A_MN / B_MN: operand is MN-major (1) or K-major (0).
-template <uint32_t BLOCK_N, uint32_t STAGES, int A_MN, int B_MN>
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS, int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TensorMaps tmBs,
                  const __grid_constant__ TensorMaps tmCs, Params p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
   constexpr uint32_t NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 32)    ? 32
                                  : (NUM_ACC * BLOCK_N <= 64)  ? 64
@@ -75,9 +83,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto empty_bar = [&](uint32_t s) { return bars + 8 * (STAGES + s); };
   auto tfull_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + a); };
   auto tempty_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + 2 + a); };
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + (2 * STAGES + 4) * 8);
+  auto efull_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + b); };            // staging buffer b holds a finished chunk
+  auto eempty_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + EPI_BUFS + b); }; // its TMA store has finished reading it
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + L::NUM_BARS * 8);
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role loops below stay on the uniform datapath
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const uint32_t tiles_per_batch = p.tiles_m * p.tiles_n;
   const uint32_t num_tiles = tiles_per_batch * p.batch;
@@ -98,6 +109,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
     }
+    for (uint32_t b = 0; b < EPI_BUFS; ++b) {
+      mbar_init(efull_bar(b), 4);
+      mbar_init(eempty_bar(b), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32((const void *)tmem_slot), TMEM_COLS);
@@ -106,19 +121,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The producer and MMA loops are run by their WHOLE warp with one elected lane issuing: loop state,
+  // barrier addresses and descriptors then live in uniform registers. With `if (lane == 0)` around the
+  // loop every operand of every UTMALDG / UTCHMMA went through an R2UR.BROADCAST and the single issuing
+  // thread needed ~0.3 us per k-block — as long as the four MMAs of a 128 x 192 tile (ncu: the MMA warp
+  // never waited on a barrier, its samples were all issue latency).
   if (warp == 0) {
     // ================================ TMA producer =====================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
-        const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
-        const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
-        const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
-        const CUtensorMap *tmB = &tmBs.m[grp];
-        const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-        for (uint32_t kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
+      const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+      const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+      const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+      const CUtensorMap *tmB = &tmBs.m[grp];
+      const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+      for (uint32_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_fast(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(stage), L::A_BYTES + L::B_BYTES);
           const int k0 = (int)(kb * BLOCK_K);
           const uint32_t a_dst = sA + stage * L::A_BYTES, b_dst = sB + stage * L::B_BYTES;
@@ -136,41 +156,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             tma_load_3d(b_dst, tmB, full_bar(stage), k0, (int)n0, (int)z);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-        const uint32_t ks = unit / num_tiles;
-        const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-        const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1); // epilogue has drained this accumulator
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // K-major: 16 k-elements = 32 B inside the 128-B swizzle row; SBO = 8 rows * 128 B.
+    // MN-major: 16 k-rows of 128 B = 2048 B; LBO = next 64-wide MN block (BLOCK_K rows).
+    // The descriptor's address field counts 16-byte units: stage and k-step advance it by constants.
+    const uint64_t adesc0 = A_MN ? make_smem_desc(sA, BLOCK_K * 128, 1024) : make_smem_desc(sA, 16, 1024);
+    const uint64_t bdesc0 = B_MN ? make_smem_desc(sB, BLOCK_K * 128, 1024) : make_smem_desc(sB, 16, 1024);
+    constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ks = unit / num_tiles;
+      const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+      const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+      mbar_wait_fast(tempty_bar(acc), acc_phase ^ 1); // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (uint32_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_fast(full_bar(stage), phase); // TMA bytes have landed
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (uint32_t kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase); // TMA bytes have landed
-          tcgen05_fence_after();
-          const uint32_t a_s = sA + stage * L::A_BYTES, b_s = sB + stage * L::B_BYTES;
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)(stage * (L::A_BYTES >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)(stage * (L::B_BYTES >> 4));
+          umma_f16(d_tmem, ad, bd, idesc, kb != kb0 ? 1u : 0u);
 #pragma unroll
-          for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // K-major: 16 k-elements = 32 B inside the 128-B swizzle row; SBO = 8 rows * 128 B.
-            // MN-major: 16 k-rows of 128 B = 2048 B; LBO = next 64-wide MN block (BLOCK_K rows).
-            const uint64_t adesc = A_MN ? make_smem_desc(a_s + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                        : make_smem_desc(a_s + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_s + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                        : make_smem_desc(b_s + k * (UMMA_K * 2), 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) ? 1u : 0u);
-          }
+          for (uint32_t k = 1; k < BLOCK_K / UMMA_K; ++k) umma_f16(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, 1u);
           umma_commit(empty_bar(stage)); // frees the smem slot once these MMAs retire
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ store warp: staging buffers -> C through TMA ======
+    if (lane == 0 && p.tma_store) {
+      const uint32_t sEpi = base + L::EPI_OFF;
+      uint32_t epi_chunk = 0;
+      for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const uint32_t tile = unit % num_tiles;
+        const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+        const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+        const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+        const CUtensorMap *tmC = &tmCs.m[grp];
+        const bool reduce = p.accumulate || p.splits > 1;
+        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+          const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
+          mbar_wait(efull_bar(eb), (epi_chunk / EPI_BUFS) & 1u);
+          if (n0 + c0 < p.N) { // TMA clips rows/columns beyond M/N
+            if (reduce) tma_reduce_add_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            else tma_store_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+          }
+          bulk_commit(); // (possibly empty) group: keeps the group count in step with the buffer rotation
+          if (epi_chunk >= EPI_BUFS - 1) {
+            bulk_wait_read<EPI_BUFS - 1>(); // chunk epi_chunk - (EPI_BUFS - 1) has been read out of its buffer
+            mbar_arrive(eempty_bar((epi_chunk + 1) % EPI_BUFS));
+          }
         }
       }
+      bulk_wait_all(); // smem must outlive the last store
     }
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue: TMEM -> registers -> global C ==========
@@ -191,15 +241,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t m = m0 + q * 32 + lane;
       if (p.tma_store) {
-        // TMEM -> registers -> [32 cols][128 rows] fp32 staging tile -> one TMA store (or TMA
-        // reduce-add when accumulating) per 32-column chunk. Two staging buffers: the store of chunk
-        // i drains while chunk i+1 is read out of TMEM. TMA clips rows/columns beyond M/N.
-        const bool leader = (threadIdx.x == EPI_WARP0 * 32);
+        // TMEM -> registers -> [32 cols][128 rows] fp32 staging tile; the store warp (warp 3) turns each
+        // finished buffer into one TMA store (or reduce-add). The four epilogue warps never meet: a warp
+        // owns rows [32q, 32q+32) of every buffer and hands over through the buffer's mbarriers.
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
-          const uint32_t buf = sEpi + (epi_chunk & 1u) * EPI_BUF_BYTES;
-          if (leader) bulk_wait_read_1(); // the store issued two chunks ago has finished reading `buf`
-          epi_bar_sync();
+          const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f; // lane j holds the bias of column c0 + j
@@ -214,18 +261,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
+          mbar_wait(eempty_bar(eb), ((epi_chunk / EPI_BUFS) & 1u) ^ 1u); // the store that last used `buf` has read it
           const uint32_t dst = buf + (q * 32 + lane) * 4;
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
           fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
-          epi_bar_sync();
-          if (leader && n0 + c0 < p.N) {
-            if (p.accumulate || p.splits > 1) tma_reduce_add_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
-            else tma_store_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
-            bulk_commit();
-          } else if (leader) {
-            bulk_commit(); // keep the group count in step with the buffer rotation
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(efull_bar(eb));
         }
       } else {
         float *crow = c_base + (uint64_t)z * p.c_bs + m;
@@ -260,13 +302,237 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
     }
-    if (p.tma_store && threadIdx.x == EPI_WARP0 * 32) bulk_wait_all(); // smem must outlive the last store
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ CTA pairs
+// gemm_bf16_pair_kernel: the same pipelines on `tcgen05.mma.cta_group::2`. The two CTAs of a
+// cluster (the two SMs of one TPC) own a 256 x BLOCK_N tile: CTA r stages rows [128r, 128r+128) of
+// A and columns [r*BLOCK_N/2, ...) of B in its own shared memory, the leader (rank 0) issues one
+// M = 256 MMA that reads both halves, and each CTA's TMEM receives its 128 rows x BLOCK_N columns.
+// Per k-block an SM now pulls 16 KB + BLOCK_N*64 B through L2 for 128 x BLOCK_N x 64 MACs — 128
+// FLOP/B at BLOCK_N = 256 against 85 for the single-CTA 128 x 256 tile, which is what lifts the
+// K <= 3072 products off the L2 -> SM bandwidth limit (~6300 B/clk chip-wide).
+//   full[s]   : leader's barrier, armed with both CTAs' bytes; the peer's TMA credits it remotely
+//   empty[s]  : one per CTA, released by the leader's multicast tcgen05.commit
+//   tfull[a]  : one per CTA, multicast commit after a tile's last MMA
+//   tempty[a] : leader's barrier, 8 arrivals = 4 epilogue warps x 2 CTAs (peer arrives remotely)
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS> struct PairSmemLayout {
+  static constexpr uint32_t HALF_N = BLOCK_N / 2;
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr uint32_t EPI_OFF = STAGES * (A_BYTES + B_BYTES);
+  static constexpr uint32_t BAR_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;
+  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 2 * EPI_BUFS; // full/empty, tmem full/empty, staging full/empty
+  static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+};
+
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS, int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TensorMaps tmBs,
+                      const __grid_constant__ TensorMaps tmCs, Params p) {
+  using L = PairSmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "pair tile width");
+  static_assert(!B_MN || (L::HALF_N % 64 == 0), "an MN-major B half must be whole 64-column swizzle blocks");
+  constexpr uint32_t PAIR_M = 2 * BLOCK_M;
+  constexpr uint32_t NUM_ACC = 2;
+  constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * L::A_BYTES;
+  const uint32_t bars = base + L::BAR_OFF;
+  auto full_bar = [&](uint32_t s) { return bars + 8 * s; };
+  auto empty_bar = [&](uint32_t s) { return bars + 8 * (STAGES + s); };
+  auto tfull_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + a); };
+  auto tempty_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + 2 + a); };
+  auto efull_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + b); };            // staging buffer b holds a finished chunk
+  auto eempty_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + EPI_BUFS + b); }; // its TMA store has finished reading it
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + L::NUM_BARS * 8);
+
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank(), cid = cluster_id_x(), ncl = num_clusters_x();
+  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t tiles_per_batch = p.tiles_m * p.tiles_n;
+  const uint32_t num_tiles = tiles_per_batch * p.batch;
+  const uint32_t num_units = num_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBs.m[0]) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8); // 4 epilogue warps of each CTA of the pair
+    }
+    for (uint32_t b = 0; b < EPI_BUFS; ++b) {
+      mbar_init(efull_bar(b), 4);
+      mbar_init(eempty_bar(b), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32((const void *)tmem_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all(); // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ==========================
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t unit = cid; unit < num_units; unit += ncl) {
+      const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
+      const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+      const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+      const uint32_t m0 = (t % p.tiles_m) * PAIR_M + rank * BLOCK_M;
+      const uint32_t n0 = (tn - grp * p.tiles_n_group) * BLOCK_N + rank * L::HALF_N;
+      const CUtensorMap *tmB = &tmBs.m[grp];
+      const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+      for (uint32_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_fast(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (L::A_BYTES + L::B_BYTES));
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          const int k0 = (int)(kb * BLOCK_K);
+          const uint32_t a_dst = sA + stage * L::A_BYTES, b_dst = sB + stage * L::B_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (uint32_t i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_3d_pair(a_dst + i * (64 * BLOCK_K * 2), &tmA, lead_full, (int)(m0 + 64 * i), k0, (int)z);
+          } else {
+            tma_load_3d_pair(a_dst, &tmA, lead_full, k0, (int)m0, (int)z);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (uint32_t i = 0; i < L::HALF_N / 64; ++i)
+              tma_load_3d_pair(b_dst + i * (64 * BLOCK_K * 2), tmB, lead_full, (int)(n0 + 64 * i), k0, (int)z);
+          } else {
+            tma_load_3d_pair(b_dst, tmB, lead_full, k0, (int)n0, (int)z);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ======================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR_M, BLOCK_N, A_MN, B_MN);
+      const uint64_t adesc0 = A_MN ? make_smem_desc(sA, BLOCK_K * 128, 1024) : make_smem_desc(sA, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(sB, BLOCK_K * 128, 1024) : make_smem_desc(sB, 16, 1024);
+      constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
+        const uint32_t ks = unit / num_tiles;
+        const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+        mbar_wait_fast(tempty_bar(acc), acc_phase ^ 1); // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_fast(full_bar(stage), phase); // both halves have landed
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)(stage * (L::A_BYTES >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(stage * (L::B_BYTES >> 4));
+            umma_f16_pair(d_tmem, ad, bd, idesc, kb != kb0 ? 1u : 0u);
+#pragma unroll
+            for (uint32_t k = 1; k < BLOCK_K / UMMA_K; ++k) umma_f16_pair(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, 1u);
+            umma_commit_pair(empty_bar(stage)); // frees this slot in both CTAs
+            if (kb == kb1 - 1) umma_commit_pair(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ store warp (both CTAs, own 128 rows) ==============
+    if (lane == 0) {
+      const uint32_t sEpi = base + L::EPI_OFF;
+      uint32_t epi_chunk = 0;
+      for (uint32_t unit = cid; unit < num_units; unit += ncl) {
+        const uint32_t tile = unit % num_tiles;
+        const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
+        const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+        const uint32_t m0 = (t % p.tiles_m) * PAIR_M + rank * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+        const CUtensorMap *tmC = &tmCs.m[grp];
+        const bool reduce = p.accumulate || p.splits > 1;
+        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+          const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
+          mbar_wait(efull_bar(eb), (epi_chunk / EPI_BUFS) & 1u);
+          if (n0 + c0 < p.N && m0 < p.M) {
+            if (reduce) tma_reduce_add_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+            else tma_store_3d(tmC, buf, (int)m0, (int)(n0 + c0), (int)z);
+          }
+          bulk_commit();
+          if (epi_chunk >= EPI_BUFS - 1) {
+            bulk_wait_read<EPI_BUFS - 1>();
+            mbar_arrive(eempty_bar((epi_chunk + 1) % EPI_BUFS));
+          }
+        }
+      }
+      bulk_wait_all();
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================================ epilogue (both CTAs, own 128 rows) ================
+    const uint32_t q = warp & 3;
+    const uint32_t sEpi = base + L::EPI_OFF;
+    uint32_t it = 0, epi_chunk = 0;
+    for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
+      const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
+      const uint32_t t = tile % tiles_per_batch;
+      const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
+      const uint32_t n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+      const float *col_bias = p.groups > 1 ? p.bias_grp[grp] : p.col_bias;
+      const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
+      const bool add_bias = col_bias && ks == 0;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+        const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+        float bias_lane = 0.0f;
+        if (add_bias && n0 + c0 + lane < p.N) bias_lane = col_bias[n0 + c0 + lane];
+        tmem_ld_wait();
+        if (add_bias) {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
+        }
+        if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the leader's MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        }
+        mbar_wait(eempty_bar(eb), ((epi_chunk / EPI_BUFS) & 1u) ^ 1u);
+        const uint32_t dst = buf + (q * 32 + lane) * 4;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(efull_bar(eb));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all(); // the peer's shared memory and TMEM stay alive until the leader's last MMA is consumed
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -327,17 +593,18 @@ static bool make_c_map(CUtensorMap *map, float *c, uint64_t M, uint64_t N, uint6
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <uint32_t BLOCK_N, uint32_t STAGES>
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS>
 static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
                       int b_major, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
+  static_assert(L::TOTAL + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
   const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t num_units = num_tiles * p.splits;
   const unsigned grid = num_units < (uint32_t)kNumSMs ? num_units : (unsigned)kNumSMs;
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
-    auto k = gemm_bf16_kernel<BLOCK_N, STAGES, AM, BM_>;                                           \
+    auto k = gemm_bf16_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                           \
     ensure_dynamic_smem((const void *)k, (int)smem);                                               \
     k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmBs, tmCs, p);                                        \
   }
@@ -347,6 +614,75 @@ static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const Tens
   else WCU_TC_LAUNCH(0, 0)
 #undef WCU_TC_LAUNCH
   return after_launch();
+}
+
+template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS>
+static int launch_pair_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
+                           int b_major, cudaStream_t st) {
+  using L = PairSmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
+  static_assert(L::TOTAL + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
+  const uint32_t smem = L::TOTAL + 1024;
+  const uint32_t num_units = p.tiles_m * p.tiles_n * p.batch * p.splits;
+  const unsigned pairs = num_units < (uint32_t)(kNumSMs / 2) ? num_units : (unsigned)(kNumSMs / 2);
+#define WCU_TC_LAUNCH(AM, BM_)                                                                     \
+  {                                                                                                \
+    auto k = gemm_bf16_pair_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                      \
+    ensure_dynamic_smem((const void *)k, (int)smem);                                               \
+    k<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmBs, tmCs, p);                                   \
+  }
+  if constexpr ((BLOCK_N / 2) % 64 == 0) {
+    if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
+    else if (a_major) WCU_TC_LAUNCH(1, 0)
+    else if (b_major) WCU_TC_LAUNCH(0, 1)
+    else WCU_TC_LAUNCH(0, 0)
+  } else { // 96-column halves exist for a K-major B only
+    if (b_major) return WEEDCU_ENOSUP;
+    if (a_major) WCU_TC_LAUNCH(1, 0)
+    else WCU_TC_LAUNCH(0, 0)
+  }
+#undef WCU_TC_LAUNCH
+  return after_launch();
+}
+
+// Tile configuration: single-CTA 128 x {256,192,128} tiles or CTA-pair 256 x {256,192,128} tiles, and
+// the split-K factor. mode 0 = cost model over both families, 1 = single-CTA only, 2 = pairs only,
+// >= 1000 = forced (pair * 1e6 + BLOCK_N * 1e3 + splits) for the tuning sweep of tools/microbench.py.
+static int g_gemm_mode = -1;
+static int gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char *e = getenv("WEEDCU_GEMM_MODE");
+    g_gemm_mode = e ? atoi(e) : 0;
+  }
+  return g_gemm_mode;
+}
+void set_gemm_mode(int mode) { g_gemm_mode = mode < 0 ? 0 : mode; }
+
+struct TileCfg {
+  int pair;
+  uint32_t bn, splits;
+  int variant; // tuning sweeps: 1 = direct stores instead of staged TMA stores, 2 = 4 stages + 2 staging buffers (BLOCK_N 256)
+};
+
+// Estimated launch duration in microseconds. A CTA runs its work units (tile, k-slice) back to back
+// with the epilogue of unit i hidden behind the k-loop of unit i+1, so a wave costs
+// max(k-loop, epilogue); the k-loop runs at the slower of the tensor pipe and the L2 -> SM feed
+// (16 KB of A plus BLOCK_N x 128 B of B per k-block, half the B bytes per SM in a CTA pair).
+static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, uint32_t num_kb, uint32_t groups, uint32_t batch,
+                           int accumulate, uint64_t c_elems) {
+  const uint32_t tiles_m = c.pair ? (tiles_m128 + 1) / 2 : tiles_m128;
+  const uint32_t tiles = tiles_m * ((N + c.bn - 1) / c.bn) * groups * batch;
+  const uint32_t kb_per = (num_kb + c.splits - 1) / c.splits, units = tiles * ((num_kb + kb_per - 1) / kb_per);
+  const uint32_t slots = c.pair ? kNumSMs / 2 : kNumSMs;
+  const uint32_t waves = (units + slots - 1) / slots;
+  const double t_mma = c.bn * (0.41 / 256.0);
+  const double t_l2 = (16384.0 + c.bn * (c.pair ? 64.0 : 128.0)) / 99.0e3;
+  const double t_kb = t_mma > t_l2 ? t_mma : t_l2;
+  const bool red = accumulate || c.splits > 1;
+  const double t_epi = c.bn * 512.0 / 33.0e3 * (red ? 1.5 : 1.0);
+  const double loop = kb_per * t_kb;
+  double us = waves * (loop > t_epi ? loop : t_epi) + 3.0 * t_kb + t_epi + 2.0;
+  if (c.splits > 1 && !accumulate) us += 2.0 + (double)c_elems * 4.0 / 5.0e6; // zero-fill before the reduce-adds
+  return us;
 }
 
 // `groups` (<= 3) products A x B_g -> C_g (+ bias_g) that share the A operand and every dimension run
@@ -359,34 +695,47 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   if (!a || !b || !c || !M || !N || !K || !batch || !groups || groups > kMaxGroups) return WEEDCU_EINVAL;
   for (uint32_t g = 0; g < groups; ++g)
     if (!b[g] || !c[g]) return WEEDCU_EINVAL;
-  // Tile width and split-K are chosen together by a small cost model: a CTA processes its work units
-  // (tile, k-slice) one after the other, so the launch costs  waves x BLOCK_N x (k-blocks per slice +
-  // ~3 k-blocks of un-overlapped prologue/epilogue). Few-tile problems (weight gradients: M, N =
-  // layer widths, K = batch*seq) get split along K, slices meeting in C by TMA reduce-add; tile
-  // counts just above a multiple of 148 get a narrower tile instead of a nearly empty last wave.
-  const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  // Tile family, tile width and split-K are chosen together by the cost model above. Few-tile
+  // problems (weight gradients: M, N = layer widths, K = batch*seq) get split along K, slices
+  // meeting in C by TMA reduce-add; tile counts just above a multiple of the slot count get a
+  // narrower tile instead of a nearly empty last wave.
+  const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles_m128 = (M + BLOCK_M - 1) / BLOCK_M;
   bool c_tma = (ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0);
   for (uint32_t g = 0; g < groups; ++g) c_tma = c_tma && (((uintptr_t)c[g]) & 15u) == 0;
-  uint32_t block_n = 256, best_s = 1;
-  double best_cost = 1e300;
-  const uint32_t cand[3] = {256, 192, 128};
-  for (uint32_t ci = 0; ci < 3; ++ci) {
-    const uint32_t bn = cand[ci];
-    if (bn > 128 && N <= bn - 64) continue; // do not pad a narrow N into a wide tile
-    const uint32_t tiles = tiles_m * ((N + bn - 1) / bn) * groups * batch;
-    for (uint32_t sp = 1; sp <= 16; ++sp) {
-      if (sp > 1 && (!c_tma || sp * 4u > num_kb)) break;
-      const uint32_t kb_per = (num_kb + sp - 1) / sp, units = tiles * ((num_kb + kb_per - 1) / kb_per);
-      const uint32_t waves = (units + kNumSMs - 1) / kNumSMs;
-      const double tile_eff = bn == 256 ? 1.0 : (bn == 192 ? 1.03 : 1.12); // narrower tiles re-read A more often
-      const double cost = (double)waves * bn * (kb_per + 3.0 + (sp > 1 ? 1.0 : 0.0)) * tile_eff;
-      if (cost < best_cost) {
-        best_cost = cost;
-        block_n = bn;
-        best_s = sp;
+  const int mode = gemm_mode();
+  TileCfg best = {0, 256, 1, 0};
+  if (mode >= 1000) {
+    best.pair = mode / 1000000;
+    best.bn = (uint32_t)(mode / 1000) % 1000u;
+    best.variant = (mode / 100) % 10;
+    best.splits = (uint32_t)mode % 100u;
+    if (best.pair > 1 || (best.bn != 256 && best.bn != 192 && best.bn != 128) || !best.splits) return WEEDCU_EINVAL;
+    if (best.pair && (!c_tma || (best.bn == 192 && b_major))) return WEEDCU_ENOSUP;
+    if (!c_tma) best.splits = 1;
+  } else {
+    double best_cost = 1e300;
+    const uint32_t cand[3] = {256, 192, 128};
+    for (int pair = 0; pair < 2; ++pair) {
+      if ((pair == 0 && mode == 2 && c_tma && M > BLOCK_M) || (pair == 1 && (mode == 1 || !c_tma || M <= BLOCK_M))) continue;
+      for (uint32_t ci = 0; ci < 3; ++ci) {
+        const uint32_t bn = cand[ci];
+        if (bn > 128 && N <= bn - 64) continue; // do not pad a narrow N into a wide tile
+        if (pair && bn == 192 && b_major) continue;
+        for (uint32_t sp = 1; sp <= 16; ++sp) {
+          if (sp > 1 && (!c_tma || sp * 4u > num_kb)) break;
+          const TileCfg cfg = {pair, bn, sp, 0};
+          const double cost = tile_cost_us(cfg, tiles_m128, N, num_kb, groups, batch, accumulate, (uint64_t)M * N * groups * batch);
+          if (cost < best_cost) {
+            best_cost = cost;
+            best = cfg;
+          }
+        }
       }
     }
   }
+  const uint32_t block_n = best.bn;
+  uint32_t best_s = best.splits;
+  const uint32_t tiles_m = best.pair ? (tiles_m128 + 1) / 2 : tiles_m128;
   CUtensorMap tmA;
   TensorMaps tmBs, tmCs;
   int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
@@ -405,13 +754,15 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   p.tma_store = 1;
   for (uint32_t g = 0; g < kMaxGroups; ++g) {
     const uint32_t src = g < groups ? g : 0;
-    rc = make_operand_map(&tmBs.m[g], b[src], b_major, N, K, ldb, batch, b_bs, block_n);
+    rc = make_operand_map(&tmBs.m[g], b[src], b_major, N, K, ldb, batch, b_bs, best.pair ? block_n / 2 : block_n);
     if (rc) return rc;
     if (p.tma_store && !make_c_map(&tmCs.m[g], c[src], M, N, ldc, batch, c_bs)) p.tma_store = 0;
     p.c_grp[g] = c[src];
     p.bias_grp[g] = col_bias ? col_bias[src] : nullptr;
   }
+  if (best.variant == 1 && !best.pair) p.tma_store = 0;
   if (!p.tma_store) {
+    if (best.pair) return WEEDCU_ENOSUP; // unreachable: pairs are only chosen when C meets the TMA rules
     for (uint32_t g = 0; g < kMaxGroups; ++g) tmCs.m[g] = tmA; // unused by the kernel, but must be valid descriptors
     best_s = 1;
   }
@@ -428,9 +779,17 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
     }
   }
   ProfScope prof(WEEDCU_PROF_GEMM_TC, st, 2.0 * (double)M * N * K * batch * groups);
-  if (block_n == 256) return launch_cfg<256, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
-  if (block_n == 192) return launch_cfg<192, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
-  return launch_cfg<128, 6>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  if (best.pair) {
+    if (block_n == 256) return launch_pair_cfg<256, 5, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+    if (block_n == 192) return launch_pair_cfg<192, 5, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+    return launch_pair_cfg<128, 6, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  }
+  if (block_n == 256) {
+    if (best.variant == 2) return launch_cfg<256, 4, 2>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+    return launch_cfg<256, 3, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  }
+  if (block_n == 192) return launch_cfg<192, 4, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
+  return launch_cfg<128, 5, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
 }
 
 int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, const uint16_t *b,
@@ -575,6 +934,11 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
                              int accumulate, const float *const *col_bias, void *stream) {
   return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, groups, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
                                       resolve_stream(stream), col_bias);
+}
+
+int weedcu_gemm_set_mode(int mode) {
+  tc::set_gemm_mode(mode);
+  return 0;
 }
 
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,
