@@ -324,6 +324,19 @@ def main_ours(args):
     for h in losses:
         P.free(h)
     losses.clear()
+    # host issue time of one step with an EMPTY launch queue (issue_ms_per_step above includes the time
+    # the host spends blocked on the full queue once it is ~1000 launches ahead of the device)
+    unblocked = []
+    for s in range(3):
+        P.sync()
+        t0 = time.perf_counter()
+        resident_step(s)
+        unblocked.append((time.perf_counter() - t0) * 1000.0)
+    P.sync()
+    for h in losses:
+        P.free(h)
+    losses.clear()
+    host["issue_ms_per_step_unblocked"] = float(np.median(unblocked))
     ms_per_step = ms / args.steps
     value = cfg["B"] * world / (ms_per_step / 1000.0)
 

@@ -348,8 +348,6 @@ def bench_tune(results, peaks):
                     modes.append(pair * 1000000 + bn * 1000 + sp)
                     if not pair and sp == 1:
                         modes.append(bn * 1000 + 100 + sp)      # variant 1: direct stores, no staging
-                        if bn == 256:
-                            modes.append(bn * 1000 + 200 + sp)  # variant 2: 4 stages + 2 staging buffers
         best = None
         for mode in modes:
             lib.weedcu_gemm_set_mode(C.c_int(mode))

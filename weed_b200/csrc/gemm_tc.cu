@@ -660,13 +660,16 @@ void set_gemm_mode(int mode) { g_gemm_mode = mode < 0 ? 0 : mode; }
 struct TileCfg {
   int pair;
   uint32_t bn, splits;
-  int variant; // tuning sweeps: 1 = direct stores instead of staged TMA stores, 2 = 4 stages + 2 staging buffers (BLOCK_N 256)
+  int variant; // tuning sweeps: 1 = direct stores instead of staged TMA stores (single-CTA kernels)
 };
 
-// Estimated launch duration in microseconds. A CTA runs its work units (tile, k-slice) back to back
-// with the epilogue of unit i hidden behind the k-loop of unit i+1, so a wave costs
-// max(k-loop, epilogue); the k-loop runs at the slower of the tensor pipe and the L2 -> SM feed
-// (16 KB of A plus BLOCK_N x 128 B of B per k-block, half the B bytes per SM in a CTA pair).
+// Estimated launch duration in microseconds, calibrated on the tile-configuration sweep of
+// tools/microbench.py --group tune (profiles/r01_tune_v12.log). A CTA runs its work units (tile,
+// k-slice) back to back with the epilogue of unit i hidden behind the k-loop of unit i+1, so a wave
+// costs max(k-loop, epilogue). Measured per-k-block times: the single-CTA kernels are bound by shared-
+// memory bandwidth (TMA fills plus the MMA's operand reads: 96 KB per 128 x 256 x 64 block against
+// 128 B/clk), the CTA pairs halve the B bytes per SM and run at the tensor pipe's sustained rate for
+// BLOCK_N >= 192. The epilogue floor is the ~0.75 us a 16 KB chunk takes through shared memory.
 static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, uint32_t num_kb, uint32_t groups, uint32_t batch,
                            int accumulate, uint64_t c_elems) {
   const uint32_t tiles_m = c.pair ? (tiles_m128 + 1) / 2 : tiles_m128;
@@ -674,14 +677,15 @@ static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, ui
   const uint32_t kb_per = (num_kb + c.splits - 1) / c.splits, units = tiles * ((num_kb + kb_per - 1) / kb_per);
   const uint32_t slots = c.pair ? kNumSMs / 2 : kNumSMs;
   const uint32_t waves = (units + slots - 1) / slots;
-  const double t_mma = c.bn * (0.41 / 256.0);
-  const double t_l2 = (16384.0 + c.bn * (c.pair ? 64.0 : 128.0)) / 99.0e3;
-  const double t_kb = t_mma > t_l2 ? t_mma : t_l2;
-  const bool red = accumulate || c.splits > 1;
-  const double t_epi = c.bn * 512.0 / 33.0e3 * (red ? 1.5 : 1.0);
+  const double t_kb = c.pair ? (c.bn == 256 ? 0.417 : c.bn == 192 ? 0.334 : 0.267) : (c.bn == 256 ? 0.4425 : c.bn == 192 ? 0.385 : 0.296);
+  // `accumulate` is deliberately NOT an input: C = AB into a zero-filled buffer and C += AB must pick the
+  // same tiles and k-slices so that the lazy zero-fill of gradients stays a pure scheduling change
+  // (tests/test_host_gpu.py::test_operand_cache_and_lazy_zero_change_nothing).
+  (void)accumulate;
+  const double t_epi = c.bn * (c.pair ? 0.0236 : 0.0263) * (c.splits > 1 ? 1.25 : 1.0);
   const double loop = kb_per * t_kb;
-  double us = waves * (loop > t_epi ? loop : t_epi) + 3.0 * t_kb + t_epi + 2.0;
-  if (c.splits > 1 && !accumulate) us += 2.0 + (double)c_elems * 4.0 / 5.0e6; // zero-fill before the reduce-adds
+  double us = waves * (loop > t_epi ? loop : t_epi) + 4.0 + 0.5 * (loop < t_epi ? loop : t_epi);
+  if (c.splits > 1) us += 3.0 + (double)c_elems * 4.0 / 5.0e6; // zero-fill before the reduce-adds
   return us;
 }
 
@@ -784,10 +788,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
     if (block_n == 192) return launch_pair_cfg<192, 5, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
     return launch_pair_cfg<128, 6, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
   }
-  if (block_n == 256) {
-    if (best.variant == 2) return launch_cfg<256, 4, 2>(tmA, tmBs, tmCs, p, a_major, b_major, st);
-    return launch_cfg<256, 3, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
-  }
+  if (block_n == 256) return launch_cfg<256, 4, 2>(tmA, tmBs, tmCs, p, a_major, b_major, st); // 3 stages + 4 buffers measured slower
   if (block_n == 192) return launch_cfg<192, 4, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
   return launch_cfg<128, 5, 4>(tmA, tmBs, tmCs, p, a_major, b_major, st);
 }
