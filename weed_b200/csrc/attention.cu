@@ -49,6 +49,7 @@ struct HeadsPackArgs {
 template <int LPT>
 __global__ void __launch_bounds__(256)
 heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // [B][tt + 4]
   const uint32_t pitch = tt + 4u;
   const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
@@ -92,6 +93,7 @@ heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint3
 // generic shapes (B % 4 != 0 or unaligned bases)
 __global__ void __launch_bounds__(256)
 heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // [tt][B + 1]
   const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n = nt * B;
@@ -113,6 +115,7 @@ template <int LPT>
 __global__ void __launch_bounds__(256)
 unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, __nv_bfloat16 *__restrict__ outb, uint32_t B,
                    uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // [B][tt + 4]
   const uint32_t pitch = tt + 4u;
   const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
@@ -152,6 +155,7 @@ unheads_vec_kernel(const float *__restrict__ oc, float *__restrict__ out, __nv_b
 __global__ void __launch_bounds__(256)
 unheads_kernel(const float *__restrict__ oc, float *__restrict__ out, uint32_t B, uint32_t T, uint32_t H,
                uint32_t hd, uint32_t tt) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // [tt][B + 1]
   const uint32_t c = blockIdx.y, h = c % H, j = c / H; // column-major reshape [.., C] -> [.., H, hd]: c = h + H*j
   const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n = nt * B;
@@ -178,6 +182,7 @@ template <int NV4>
 __global__ void __launch_bounds__(256)
 attn_softmax_bf16_kernel(const float *__restrict__ S, __nv_bfloat16 *__restrict__ P, uint32_t T, uint32_t rows,
                          float divisor, float mask_val, int causal) {
+  pdl_grid_sync();
   const uint32_t lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const uint32_t q = row % T;
@@ -295,9 +300,9 @@ extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, cons
     if ((B % 4u) == 0 && vtt >= 8u && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(qh)) {
       const uint32_t vt = vtt < T ? vtt : T;
       const size_t vbytes = (size_t)B * (vt + 4u) * sizeof(float);
-      heads_pack_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C, 3), 256, vbytes, st>>>(a, B, T, H, hd, vt);
+      launch_k(heads_pack_vec_kernel<4>, dim3((T + vt - 1) / vt, (unsigned)C, 3), dim3(256), vbytes, st, a, B, T, H, hd, vt);
     } else {
-      heads_pack_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C, 3), 256, tile_bytes, st>>>(a, B, T, H, hd, tt);
+      launch_k(heads_pack_kernel, dim3((T + tt - 1) / tt, (unsigned)C, 3), dim3(256), tile_bytes, st, a, B, T, H, hd, tt);
     }
     rc = after_launch();
   }
@@ -316,7 +321,7 @@ extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, cons
     const unsigned grid = (rows + 7) / 8;
     const int do_mask = (causal && T > 1) ? 1 : 0;
     const uint32_t nv4 = (T + 127) / 128;
-#define WCU_SM(NV4) attn_softmax_bf16_kernel<NV4><<<grid, 256, 0, st>>>(S, (__nv_bfloat16 *)P, T, rows, divisor, mask_val, do_mask)
+#define WCU_SM(NV4) launch_k(attn_softmax_bf16_kernel<NV4>, dim3(grid), dim3(256), 0, st, S, (__nv_bfloat16 *)P, T, rows, divisor, mask_val, do_mask)
     if (nv4 <= 1) WCU_SM(1);
     else if (nv4 <= 2) WCU_SM(2);
     else if (nv4 <= 4) WCU_SM(4);
@@ -331,11 +336,11 @@ extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, cons
     const uint32_t vtt = (4096u / B) & ~7u;
     if ((B % 4u) == 0 && vtt >= 8u && aligned16(oc) && aligned16(out)) {
       const uint32_t vt = vtt < T ? vtt : T;
-      unheads_vec_kernel<4><<<dim3((T + vt - 1) / vt, (unsigned)C), 256, (size_t)B * (vt + 4u) * sizeof(float), st>>>(oc, out, (__nv_bfloat16 *)out_bf16, B, T, H, hd, vt);
+      launch_k(unheads_vec_kernel<4>, dim3((T + vt - 1) / vt, (unsigned)C), dim3(256), (size_t)B * (vt + 4u) * sizeof(float), st, oc, out, (__nv_bfloat16 *)out_bf16, B, T, H, hd, vt);
     } else if (out_bf16) {
       rc = WEEDCU_ENOSUP; // (checked up front for the same conditions; kept as a guard)
     } else {
-      unheads_kernel<<<dim3((T + tt - 1) / tt, (unsigned)C), 256, tile_bytes, st>>>(oc, out, B, T, H, hd, tt);
+      launch_k(unheads_kernel, dim3((T + tt - 1) / tt, (unsigned)C), dim3(256), tile_bytes, st, oc, out, B, T, H, hd, tt);
     }
     if (rc == 0) rc = after_launch();
   }

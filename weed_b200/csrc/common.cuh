@@ -24,6 +24,38 @@ cudaError_t pool_free(void *ptr, cudaStream_t st);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel, not once per launch
 void ensure_dynamic_smem(const void *kernel, int bytes);
 
+// Programmatic dependent launch: every kernel of this library is launched with the programmatic-stream-
+// serialization attribute and starts with pdl_grid_sync(): it lets the NEXT kernel of the stream be
+// scheduled as soon as all of this grid's blocks are resident (griddepcontrol.launch_dependents) and
+// then waits until the PREVIOUS grid has completed and flushed (griddepcontrol.wait) before touching
+// memory. Launch latency, block scheduling and per-kernel set-up (barrier init, TMEM allocation,
+// tensor-map prefetch) thereby overlap the tail of the preceding kernel instead of following its
+// completion. Experimental and OFF by default (WEEDCU_PDL=1 enables it): see pdl_enabled() in runtime.cu.
+bool pdl_enabled();
+// Only a kernel that directly follows another kernel OF THIS LIBRARY takes the attribute: after a
+// memset / memcpy / event / allocation on the stream (note_stream_op) the next launch is a plain one,
+// so its ordering against those operations is the ordinary stream order.
+void note_stream_op();
+bool pdl_take_edge(); // true when the previous stream operation was one of our kernels; marks "kernel" for the next
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_take_edge() ? 1u : 0u;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); // errors surface in after_launch()
+}
+
 // Optional per-class event timing (weedcu_prof_*). A scope brackets the launches issued while it
 // is alive; when profiling is off it costs one predictable branch.
 bool prof_on();

@@ -23,6 +23,7 @@ namespace weedcu {
 __global__ void __launch_bounds__(256)
 kv_append_kernel(const float *__restrict__ k, const float *__restrict__ v, float *k_cache, float *v_cache, uint32_t B,
                  uint32_t T_new, uint32_t H, uint32_t hd, uint32_t S, uint32_t cache_len) {
+  pdl_grid_sync();
   const uint64_t BH = (uint64_t)B * H, total = BH * T_new * hd;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t b = (uint32_t)(i % B);
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(32 * kDecWarps)
 attn_decode_partial_kernel(const float *__restrict__ q, const float *__restrict__ k_cache, const float *__restrict__ v_cache,
                            float *__restrict__ part, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd, uint32_t S,
                            uint32_t L, uint32_t KC, float divisor, float mask_val, int causal) {
+  pdl_grid_sync();
   extern __shared__ float sm[]; // [kDecWarps][HDM + 2][32]
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const uint32_t BH = B * H, bh = blockIdx.x * 32u + lane, t = blockIdx.z, c = blockIdx.y;
@@ -119,6 +121,7 @@ attn_decode_partial_kernel(const float *__restrict__ q, const float *__restrict_
 __global__ void __launch_bounds__(256)
 attn_decode_combine_kernel(const float *__restrict__ part, float *__restrict__ out, uint32_t B, uint32_t T_new, uint32_t H,
                            uint32_t hd, uint32_t n_chunks) {
+  pdl_grid_sync();
   const uint32_t BH = B * H;
   const uint64_t total = (uint64_t)BH * hd * T_new, i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -147,7 +150,7 @@ static int launch_decode_partial(const float *q, const float *kc, const float *v
   const size_t smem = sizeof(float) * kDecWarps * (HDM + 2) * 32;
   ensure_dynamic_smem((const void *)kern, (int)smem);
   const dim3 grid((B * H + 31u) / 32u, n_chunks, T_new);
-  kern<<<grid, 32 * kDecWarps, smem, st>>>(q, kc, vc, part, B, T_new, H, hd, S, L, KC, divisor, mask_val, causal);
+  launch_k(kern, dim3(grid), dim3(32 * kDecWarps), smem, st, q, kc, vc, part, B, T_new, H, hd, S, L, KC, divisor, mask_val, causal);
   return after_launch();
 }
 
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256)
 skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, const float *__restrict__ b, uint32_t b_s0,
                      uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N,
                      const float *__restrict__ bias, int accumulate) {
+  pdl_grid_sync();
   constexpr int NV = MM * kSkCW; // partial sums per lane
   __shared__ float red[8][NV];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -236,7 +240,7 @@ int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const flo
   if (M > 16u) return WEEDCU_ENOSUP;
   const unsigned grid = (N + kSkCW - 1) / kSkCW;
   ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K);
-#define WCU_SK(MM, AV) skinny_matmul_kernel<MM, AV><<<grid, 256, 0, st>>>(a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate)
+#define WCU_SK(MM, AV) launch_k(skinny_matmul_kernel<MM, AV>, dim3(grid), dim3(256), 0, st, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate)
   const bool avec_ok = a_s0 == 1u && (a_s1 % 4u) == 0 && aligned16(a);
   if (M <= 4u) {
     if (avec_ok && M == 4u) WCU_SK(4, true);
@@ -269,7 +273,7 @@ int weedcu_attention_decode(const float *q, const float *k, const float *v, floa
   {
     ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 2.0 * 12.0 * (double)BH * T_new * hd);
     const uint64_t total = (uint64_t)BH * T_new * hd;
-    kv_append_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(k, v, k_cache, v_cache, B, T_new, H, hd, S, cache_len);
+    launch_k(kv_append_kernel, dim3(grid_for(total, 256, 8)), dim3(256), 0, st, k, v, k_cache, v_cache, B, T_new, H, hd, S, cache_len);
     const int rc = after_launch();
     if (rc) return rc;
   }
@@ -297,7 +301,7 @@ int weedcu_attention_decode(const float *q, const float *k, const float *v, floa
     else rc = launch_decode_partial<64>(q, k_cache, v_cache, part, B, T_new, H, hd, S, L, KC, n_chunks, divisor, mask_val, do_mask, st);
     if (rc == 0) {
       const uint64_t total = (uint64_t)BH * hd * T_new;
-      attn_decode_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, out, B, T_new, H, hd, n_chunks);
+      launch_k(attn_decode_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, part, out, B, T_new, H, hd, n_chunks);
       rc = after_launch();
     }
   }

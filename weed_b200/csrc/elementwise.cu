@@ -23,6 +23,7 @@ template <int NIN> struct EwPtrs {
 // One thread = one element. Handles any rank <= 8 / any strides.
 template <int NIN, class F>
 __global__ void __launch_bounds__(256) ew_scalar_kernel(IndexSpace<NIN + 1> sp, EwPtrs<NIN> p, F f) {
+  pdl_grid_sync();
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sp.n; i += stride) {
     uint64_t off[NIN + 1];
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) ew_scalar_kernel(IndexSpace<NIN + 1> sp, 
 // dim-0 stride in {0,1}, 16-byte aligned bases and (for stride-1 operands) higher strides % 4 == 0.
 template <int NIN, class F>
 __global__ void __launch_bounds__(256) ew_vec4_kernel(IndexSpace<NIN + 1> sp, EwPtrs<NIN> p, F f) {
+  pdl_grid_sync();
   const uint32_t nq = sp.n >> 2, s0q = sp.shape[0] >> 2;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
@@ -128,10 +130,10 @@ static int launch_ew(const weedcu_view *const *views, const float *const *ins, f
   ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, moved);
   if (vec) {
     const unsigned grid = grid_for(sp.n >> 2, 256, 16);
-    ew_vec4_kernel<NIN, F><<<grid, 256, 0, st>>>(sp, p, f);
+    launch_k(ew_vec4_kernel<NIN, F>, dim3(grid), dim3(256), 0, st, sp, p, f);
   } else {
     const unsigned grid = grid_for(sp.n, 256, 32);
-    ew_scalar_kernel<NIN, F><<<grid, 256, 0, st>>>(sp, p, f);
+    launch_k(ew_scalar_kernel<NIN, F>, dim3(grid), dim3(256), 0, st, sp, p, f);
   }
   return after_launch();
 }
@@ -203,6 +205,7 @@ template <typename T> struct alignas(16) Quad { T x, y, z, w; };
 
 template <typename T>
 __global__ void __launch_bounds__(256) fill_kernel(T *p, uint64_t n, T v) {
+  pdl_grid_sync();
   // body in 128-bit stores; head/tail elements handled by the first warp of block 0
   const uintptr_t addr = (uintptr_t)p;
   uint64_t head = ((16 - (addr & 15)) & 15) / sizeof(T);
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(256) fill_kernel(T *p, uint64_t n, T v) {
 // 8 + 2 B/elem instead of 8 + a 6 B/elem pack pass. Dense inputs, 4 elements per thread.
 __global__ void __launch_bounds__(256)
 gelu_fwd_bf16_kernel(const float *__restrict__ x, float *__restrict__ y, __nv_bfloat16 *__restrict__ yb, uint64_t n4) {
+  pdl_grid_sync();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4 *>(x)[i];
@@ -247,6 +251,7 @@ constexpr int kGgCols = 8;
 __global__ void __launch_bounds__(256)
 gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__restrict__ dout, uint32_t rows, uint32_t cols,
                       int accumulate, __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  pdl_grid_sync();
   __shared__ float red[8][kGgCols];
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * 4u;
   const bool live = r < rows;
@@ -305,6 +310,7 @@ gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__r
 }
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t cols, float *__restrict__ colsum) {
+  pdl_grid_sync();
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   float t = 0.0f;
@@ -326,6 +332,7 @@ constexpr uint64_t kAdamChunk = 32768; // elements per block of the multi-tensor
 __global__ void __launch_bounds__(256)
 sgd_kernel(float *__restrict__ p, const float *__restrict__ g, uint64_t n, float lr, float gscale,
            bool vec) {
+  pdl_grid_sync();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (vec) {
@@ -359,6 +366,7 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
             float *__restrict__ v, uint64_t n, AdamArgs a, bool vec) {
+  pdl_grid_sync();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (vec) {
@@ -384,6 +392,7 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
 
 // One block per chunk of one parameter: `count` parameters updated by a single launch.
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__restrict__ table, AdamArgs a) {
+  pdl_grid_sync();
   const AdamChunk c = table[blockIdx.x];
   if (c.vec) {
     const uint32_t nq = c.n >> 2;
@@ -428,13 +437,13 @@ int weedcu_fill_real(float *p, uint64_t n, float value, void *stream) {
   if (!p) return WEEDCU_EINVAL;
   if (!n) return 0;
   ProfScope prof(WEEDCU_PROF_FILL, resolve_stream(stream), 4.0 * n);
-  fill_kernel<float><<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, n, value);
+  launch_k(fill_kernel<float>, dim3(grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, resolve_stream(stream), p, n, value);
   return after_launch();
 }
 int weedcu_fill_int(int32_t *p, uint64_t n, int32_t value, void *stream) {
   if (!p) return WEEDCU_EINVAL;
   if (!n) return 0;
-  fill_kernel<int32_t><<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, n, value);
+  launch_k(fill_kernel<int32_t>, dim3(grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, resolve_stream(stream), p, n, value);
   return after_launch();
 }
 
@@ -532,10 +541,10 @@ int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * cols, st));
   ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (accumulate ? 18.0 : 14.0) * (double)rows * cols);
-  gelu_grad_pack_kernel<<<dim3(nchunks, cgroups), 256, 0, st>>>(din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
+  launch_k(gelu_grad_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
   int rc = after_launch();
   if (rc == 0) {
-    colsum_finish_kernel<<<(cols + 255u) / 256u, 256, 0, st>>>(part, nchunks, cols, colsum);
+    launch_k(colsum_finish_kernel, dim3((cols + 255u) / 256u), dim3(256), 0, st, part, nchunks, cols, colsum);
     rc = after_launch();
   }
   pool_free(part, st);
@@ -547,7 +556,7 @@ int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n,
   if ((n % 4u) || !aligned16(x) || !aligned16(y) || (((uintptr_t)y_bf16) & 7u)) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 10.0 * (double)n);
-  gelu_fwd_bf16_kernel<<<grid_for(n / 4u, 256, 16), 256, 0, st>>>(x, y, (__nv_bfloat16 *)y_bf16, n / 4u);
+  launch_k(gelu_fwd_bf16_kernel, dim3(grid_for(n / 4u, 256, 16)), dim3(256), 0, st, x, y, (__nv_bfloat16 *)y_bf16, n / 4u);
   return after_launch();
 }
 
@@ -594,13 +603,14 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
       dev_capacity = table.size();
     }
     host_table.swap(table); // the async copy reads host_table, which outlives it
+    note_stream_op();
     WCU_CHECK(cudaMemcpyAsync(dev_table, host_table.data(), host_table.size() * sizeof(AdamChunk),
                               cudaMemcpyHostToDevice, st));
     WCU_CHECK(cudaStreamSynchronize(st)); // pageable source: make the staging copy complete
   }
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
   ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total + 2.0 * shadowed);
-  adam_multi_kernel<<<(unsigned)host_table.size(), 256, 0, st>>>(dev_table, a);
+  launch_k(adam_multi_kernel, dim3((unsigned)host_table.size()), dim3(256), 0, st, dev_table, a);
   return after_launch();
 }
 
@@ -609,7 +619,7 @@ int weedcu_sgd_step(float *p, const float *g, uint64_t n, float lr, float gscale
   if (!n) return 0;
   const bool vec = aligned16(p) && aligned16(g);
   ProfScope prof(WEEDCU_PROF_OPTIMIZER, resolve_stream(stream), 12.0 * n);
-  sgd_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, n, lr, gscale,
+  launch_k(sgd_kernel, dim3(grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, resolve_stream(stream), p, g, n, lr, gscale,
                                                                                vec);
   return after_launch();
 }
@@ -622,7 +632,7 @@ int weedcu_adam_step(float *p, const float *g, float *m, float *v, uint64_t n, f
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
   const bool vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
   ProfScope prof(WEEDCU_PROF_OPTIMIZER, resolve_stream(stream), 28.0 * n);
-  adam_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, resolve_stream(stream)>>>(p, g, m, v, n, a,
+  launch_k(adam_kernel, dim3(grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, resolve_stream(stream), p, g, m, v, n, a,
                                                                                 vec);
   return after_launch();
 }

@@ -84,6 +84,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync(); // set-up above is CTA-local; operands written by the previous kernel are read below
 
   if (warp == 4) {
     // ================================ TMA producer =====================================
@@ -286,7 +287,7 @@ int launch_flash_attn_fwd(const uint16_t *qh, const uint16_t *kh, const uint16_t
   // FLOP of the products actually issued (causal: key tiles up to the diagonal only)
   const double tiles = causal ? 0.5 * q_tiles * (q_tiles + 1.0) : (double)q_tiles * ((T + TK - 1) / TK);
   ProfScope prof(WEEDCU_PROF_ATTENTION, st, 2.0 * 2.0 * TQ * TK * HD * tiles * BH);
-  flash_attn_fwd_kernel<<<dim3(BH, q_tiles), NTHREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, oc, T, q_tiles,
+  launch_k(flash_attn_fwd_kernel, dim3(BH, q_tiles), dim3(NTHREADS), SMEM_BYTES, st, tmQ, tmK, tmV, oc, T, q_tiles,
                                                                          1.4426950408889634f / divisor, causal);
   return after_launch();
 }

@@ -26,6 +26,7 @@ struct GemmArgs {
 template <bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(GemmArgs g) {
+  pdl_grid_sync();
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   const uint32_t tid = threadIdx.x;
@@ -135,6 +136,7 @@ gemm_f32_kernel(GemmArgs g) {
 // decode GEMV): one thread per output, K serial; adjacent threads walk m so A reads coalesce.
 __global__ void __launch_bounds__(256)
 gemm_f32_thin_kernel(GemmArgs g) {
+  pdl_grid_sync();
   const uint64_t total = (uint64_t)g.M * g.N;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -167,17 +169,17 @@ int launch_gemm_f32(const float *a, const weedcu_mat *am, const float *b, const 
   if ((uint64_t)M * N * (uint64_t)K <= (1ull << 22) || N <= 4 || M <= 4) {
     if ((uint64_t)M * N <= (1ull << 24) && (N <= 4 || M <= 4 || (uint64_t)M * N * K <= (1ull << 18))) {
       const uint64_t total = (uint64_t)M * N;
-      gemm_f32_thin_kernel<<<dim3((unsigned)((total + 255) / 256), 1, batch), 256, 0, st>>>(g);
+      launch_k(gemm_f32_thin_kernel, dim3((unsigned)((total + 255) / 256), 1, batch), dim3(256), 0, st, g);
       return after_launch();
     }
   }
   const dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
   if (grid.y > 65535) return WEEDCU_EINVAL;
   const bool a_k = (am->s1 == 1 && am->s0 != 1), b_k = (bm->s0 == 1 && bm->s1 != 1);
-  if (a_k && b_k) gemm_f32_kernel<true, true><<<grid, 256, 0, st>>>(g);
-  else if (a_k) gemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(g);
-  else if (b_k) gemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(g);
-  else gemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  if (a_k && b_k) launch_k(gemm_f32_kernel<true, true>, dim3(grid), dim3(256), 0, st, g);
+  else if (a_k) launch_k(gemm_f32_kernel<true, false>, dim3(grid), dim3(256), 0, st, g);
+  else if (b_k) launch_k(gemm_f32_kernel<false, true>, dim3(grid), dim3(256), 0, st, g);
+  else launch_k(gemm_f32_kernel<false, false>, dim3(grid), dim3(256), 0, st, g);
   return after_launch();
 }
 

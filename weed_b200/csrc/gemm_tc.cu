@@ -65,6 +65,7 @@ template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS, int A_MN, int B_
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TensorMaps tmBs,
                  const __grid_constant__ TensorMaps tmCs, Params p) {
+  
   using L = SmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
   constexpr uint32_t NUM_ACC = (2 * BLOCK_N <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (NUM_ACC * BLOCK_N <= 32)    ? 32
@@ -120,6 +121,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync(); // everything above touched only this CTA's shared memory, TMEM and kernel parameters
 
   // The producer and MMA loops are run by their WHOLE warp with one elected lane issuing: loop state,
   // barrier addresses and descriptors then live in uniform registers. With `if (lane == 0)` around the
@@ -337,6 +339,7 @@ template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS, int A_MN, int B_
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TensorMaps tmBs,
                       const __grid_constant__ TensorMaps tmCs, Params p) {
+  
   using L = PairSmemLayout<BLOCK_N, STAGES, EPI_BUFS>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "pair tile width");
   static_assert(!B_MN || (L::HALF_N % 64 == 0), "an MN-major B half must be whole 64-column swizzle blocks");
@@ -388,6 +391,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all(); // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync(); // everything above touched only the pair's shared memory, TMEM and kernel parameters
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ==========================
@@ -606,7 +610,7 @@ static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const Tens
   {                                                                                                \
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                           \
     ensure_dynamic_smem((const void *)k, (int)smem);                                               \
-    k<<<grid, NUM_THREADS, smem, st>>>(tmA, tmBs, tmCs, p);                                        \
+    launch_k(k, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmBs, tmCs, p);                                        \
   }
   if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
   else if (a_major) WCU_TC_LAUNCH(1, 0)
@@ -628,7 +632,7 @@ static int launch_pair_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const
   {                                                                                                \
     auto k = gemm_bf16_pair_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                      \
     ensure_dynamic_smem((const void *)k, (int)smem);                                               \
-    k<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmBs, tmCs, p);                                   \
+    launch_k(k, dim3(2 * pairs), dim3(NUM_THREADS), smem, st, tmA, tmBs, tmCs, p);                                   \
   }
   if constexpr ((BLOCK_N / 2) % 64 == 0) {
     if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
@@ -773,6 +777,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   p.kb_per_split = (num_kb + best_s - 1) / best_s;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits > 1 && !accumulate) { // slices meet by reduce-add: C starts from zero
+    note_stream_op();
     for (uint32_t g = 0; g < groups; ++g) {
       if (batch == 1 && ldc == M) {
         WCU_CHECK(cudaMemsetAsync(c[g], 0, sizeof(float) * (size_t)M * N, st));
@@ -816,6 +821,7 @@ __global__ void __launch_bounds__(256)
 pack_bf16_kernel(const float *__restrict__ src, uint64_t s_bs, uint32_t s0, uint32_t s1, uint32_t rows,
                  uint32_t cols, __nv_bfloat16 *__restrict__ dst, uint64_t d_bs, uint64_t ld, int dst_major,
                  int src_rowfast) {
+  pdl_grid_sync();
   __shared__ float tile[32][33]; // tile[r][c]
   const uint32_t r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float *s = src + (uint64_t)blockIdx.z * s_bs;
@@ -846,6 +852,7 @@ pack_bf16_kernel(const float *__restrict__ src, uint64_t s_bs, uint32_t s0, uint
 __global__ void __launch_bounds__(256)
 pack_bf16_stream_kernel(const float *__restrict__ src, uint64_t s_bs, uint64_t ss, uint32_t n_fast8,
                         uint32_t n_slow, __nv_bfloat16 *__restrict__ dst, uint64_t d_bs, uint64_t ld) {
+  pdl_grid_sync();
   const float *s = src + (uint64_t)blockIdx.z * s_bs;
   __nv_bfloat16 *d = dst + (uint64_t)blockIdx.z * d_bs;
   const uint64_t total = (uint64_t)n_fast8 * n_slow, stride = (uint64_t)gridDim.x * blockDim.x;
@@ -868,6 +875,7 @@ pack_bf16_stream_kernel(const float *__restrict__ src, uint64_t s_bs, uint64_t s
 __global__ void __launch_bounds__(256)
 pack_bf16_colsum_kernel(const float *__restrict__ src, uint64_t ss, uint32_t n_fast8, __nv_bfloat16 *__restrict__ dst,
                         uint64_t ld, float *colsum, int accumulate) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const uint32_t j = blockIdx.x;
   const float *s = src + (uint64_t)j * ss;
@@ -901,12 +909,12 @@ int launch_pack_bf16(const float *src, uint64_t s_bs, uint32_t s0, uint32_t s1, 
     if (s_fast == 1 && (n_fast % 8u) == 0 && (ss % 4u) == 0 && (s_bs % 4u) == 0 && (d_bs % 8u) == 0 &&
         (((uintptr_t)src) & 15u) == 0 && (((uintptr_t)dst) & 15u) == 0) {
       const uint64_t total = (uint64_t)(n_fast / 8u) * n_slow;
-      pack_bf16_stream_kernel<<<dim3(grid_for(total, 256, 16), 1, batch), 256, 0, st>>>(
+      launch_k(pack_bf16_stream_kernel, dim3(grid_for(total, 256, 16), 1, batch), dim3(256), 0, st, 
           src, s_bs, ss, n_fast / 8u, n_slow, (__nv_bfloat16 *)dst, d_bs, ld);
       return after_launch();
     }
   }
-  pack_bf16_kernel<<<grid, 256, 0, st>>>(src, s_bs, s0, s1, rows, cols, (__nv_bfloat16 *)dst, d_bs, ld,
+  launch_k(pack_bf16_kernel, dim3(grid), dim3(256), 0, st, src, s_bs, s0, s1, rows, cols, (__nv_bfloat16 *)dst, d_bs, ld,
                                          dst_major, src_rowfast);
   return after_launch();
 }
@@ -959,7 +967,7 @@ int weedcu_pack_bf16_colsum(const float *src, uint64_t offset, uint32_t s0, uint
   if (s_fast != 1 || (n_fast % 8u) || (ss % 4u) || (((uintptr_t)base) & 15u) || (((uintptr_t)dst) & 15u)) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   ProfScope prof(WEEDCU_PROF_PACK, st, 6.0 * (double)rows * cols);
-  pack_bf16_colsum_kernel<<<n_slow, 256, 0, st>>>(base, ss, n_fast / 8u, (__nv_bfloat16 *)dst, round8(n_fast), colsum, accumulate);
+  launch_k(pack_bf16_colsum_kernel, dim3(n_slow), dim3(256), 0, st, base, ss, n_fast / 8u, (__nv_bfloat16 *)dst, round8(n_fast), colsum, accumulate);
   return after_launch();
 }
 

@@ -32,6 +32,7 @@ template <int NV>
 __global__ void __launch_bounds__(32 * kLnBY)
 layernorm_fwd_stats_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, float eps,
                            float *__restrict__ mean, float *__restrict__ rstd, float *__restrict__ den_out) {
+  pdl_grid_sync();
   __shared__ float red[kLnBY][33];
   const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
   const uint32_t r = blockIdx.x * 32u + tx;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(32 * kLnBY)
 layernorm_fwd_small_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
                            const float *__restrict__ beta, float eps, float *__restrict__ y, float *__restrict__ mean,
                            float *__restrict__ rstd) {
+  pdl_grid_sync();
   __shared__ float red[kLnBY][33];
   // gamma / beta staged once: with a single resident block, 2 x NV dependent global loads per thread
   // in the output loop would each expose the full L2 latency
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_apply_kernel(const float *__restrict__ x, uint32_t rows, uint32_t F, const float *__restrict__ gamma,
                            const float *__restrict__ beta, const float *__restrict__ mean,
                            const float *__restrict__ den, float *__restrict__ y, __nv_bfloat16 *__restrict__ yb) {
+  pdl_grid_sync();
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   if (r >= rows) return;
   float mu[VEC], dn[VEC];
@@ -213,6 +216,7 @@ layernorm_bwd_rows_kernel(const float *__restrict__ x, const float *__restrict__
                           const float *__restrict__ gamma, const float *__restrict__ mean,
                           const float *__restrict__ rstd, float *__restrict__ k_x_out, float *__restrict__ k_0_out,
                           int grad_mode) {
+  pdl_grid_sync();
   __shared__ float red_a[kLnBY][33];
   __shared__ float red_b[kLnBY][33];
   const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
@@ -277,6 +281,7 @@ layernorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict_
                            const float *__restrict__ gamma, const float *__restrict__ mean,
                            const float *__restrict__ rstd, const float *__restrict__ k_x, const float *__restrict__ k_0,
                            float *dx, float *__restrict__ part_g, float *__restrict__ part_b, int accumulate) {
+  pdl_grid_sync();
   __shared__ float red[8][2 * kLnFB];
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   const bool live = r < rows;
@@ -365,6 +370,7 @@ layernorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict_
 __global__ void __launch_bounds__(256)
 layernorm_param_reduce_kernel(const float *__restrict__ part_g, const float *__restrict__ part_b,
                               uint32_t nblocks, uint32_t F, float *dgamma, float *dbeta) {
+  pdl_grid_sync();
   __shared__ float sg[8][33], sb[8][33];
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const uint32_t f = blockIdx.x * 32 + tx;
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(256)
 embedding_gather_kernel(const int32_t *__restrict__ idx, uint32_t idx_stride, uint32_t n,
                         const float *__restrict__ W, uint32_t w_s0, uint32_t w_s1, uint32_t D,
                         float *__restrict__ out, uint32_t o_s0, uint32_t o_s1) {
+  pdl_grid_sync();
   const uint64_t total = (uint64_t)n * D, stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     const uint32_t i = (uint32_t)(t % n), d = (uint32_t)(t / n);
@@ -406,6 +413,7 @@ __global__ void __launch_bounds__(256)
 embedding_scatter_kernel(float *dW, uint32_t w_s0, uint32_t w_s1, const int32_t *__restrict__ idx,
                          uint32_t idx_stride, uint32_t n, uint32_t D, const float *__restrict__ dout,
                          uint32_t o_s0, uint32_t o_s1) {
+  pdl_grid_sync();
   const uint64_t total = (uint64_t)n * D, stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     const uint32_t i = (uint32_t)(t % n), d = (uint32_t)(t / n);
@@ -417,6 +425,7 @@ embedding_scatter_kernel(float *dW, uint32_t w_s0, uint32_t w_s1, const int32_t 
 __global__ void __launch_bounds__(256)
 triu_fill_kernel(float *a, uint32_t t0, uint32_t t1, uint32_t s0, uint32_t s1, float val,
                  uint32_t diagonal) {
+  pdl_grid_sync();
   const uint64_t total = (uint64_t)t0 * t1, stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     const uint32_t i = (uint32_t)(t % t0), j = (uint32_t)(t / t0);
@@ -447,7 +456,7 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
   if (rows <= 256u && F <= (uint32_t)kLnBY * 64u) { // decode-sized inputs: one launch
     ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
     const unsigned tiles = (rows + 31u) / 32u;
-#define WCU_LN_SMALL(NV) layernorm_fwd_small_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, gamma, beta, eps, y, mean, rstd)
+#define WCU_LN_SMALL(NV) launch_k(layernorm_fwd_small_kernel<NV>, dim3(tiles), dim3(32 * kLnBY), 0, st, x, rows, F, gamma, beta, eps, y, mean, rstd)
     if (F <= kLnBY * 16) WCU_LN_SMALL(16);
     else if (F <= kLnBY * 32) WCU_LN_SMALL(32);
     else if (F <= kLnBY * 48) WCU_LN_SMALL(48);
@@ -459,7 +468,7 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
   WCU_CHECK(pool_alloc((void **)&tmp, sizeof(float) * 2 * (size_t)rows, st));
   ProfScope prof(WEEDCU_PROF_LAYERNORM, st, (y_bf16 ? 10.0 : 8.0) * (double)rows * F);
   const unsigned tiles = (rows + 31u) / 32u;
-#define WCU_LN_STATS(NV) layernorm_fwd_stats_kernel<NV><<<tiles, 32 * kLnBY, 0, st>>>(x, rows, F, eps, mean, rstd, tmp)
+#define WCU_LN_STATS(NV) launch_k(layernorm_fwd_stats_kernel<NV>, dim3(tiles), dim3(32 * kLnBY), 0, st, x, rows, F, eps, mean, rstd, tmp)
   if (F <= kLnBY * 16) WCU_LN_STATS(16);
   else if (F <= kLnBY * 32) WCU_LN_STATS(32);
   else if (F <= kLnBY * 48) WCU_LN_STATS(48);
@@ -471,9 +480,9 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
     const float *mu = mean ? mean : tmp + rows;
     const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
     if ((rows % 4u) == 0 && aligned16(x) && aligned16(y) && aligned16(mu) && fgroups <= 65535u) {
-      layernorm_fwd_apply_kernel<4><<<dim3((rows / 4u + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y, (__nv_bfloat16 *)y_bf16);
+      launch_k(layernorm_fwd_apply_kernel<4>, dim3((rows / 4u + 255u) / 256u, fgroups), dim3(256), 0, st, x, rows, F, gamma, beta, mu, tmp, y, (__nv_bfloat16 *)y_bf16);
     } else if (fgroups <= 65535u) {
-      layernorm_fwd_apply_kernel<1><<<dim3((rows + 255u) / 256u, fgroups), 256, 0, st>>>(x, rows, F, gamma, beta, mu, tmp, y, nullptr);
+      launch_k(layernorm_fwd_apply_kernel<1>, dim3((rows + 255u) / 256u, fgroups), dim3(256), 0, st, x, rows, F, gamma, beta, mu, tmp, y, nullptr);
     } else {
       rc = WEEDCU_EINVAL;
     }
@@ -499,17 +508,17 @@ int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_
   WCU_CHECK(pool_alloc((void **)&scratch, sizeof(float) * (2 * rows_up + 2 * (size_t)nchunks * F), st));
   float *kx = scratch, *k0 = scratch + rows_up, *pg = k0 + rows_up, *pb = pg + (size_t)nchunks * F;
   ProfScope prof(WEEDCU_PROF_LAYERNORM, st, (accumulate ? 16.0 : 12.0) * (double)rows * F);
-  layernorm_bwd_rows_kernel<<<(rows + 31u) / 32u, 32 * kLnBY, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, grad_mode);
+  launch_k(layernorm_bwd_rows_kernel, dim3((rows + 31u) / 32u), dim3(32 * kLnBY), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, grad_mode);
   int rc = after_launch();
   if (rc == 0) {
     if (vec)
-      layernorm_bwd_apply_kernel<4><<<dim3(nchunks, fgroups), 256, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
+      launch_k(layernorm_bwd_apply_kernel<4>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
     else
-      layernorm_bwd_apply_kernel<1><<<dim3(nchunks, fgroups), 256, 0, st>>>(x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
+      launch_k(layernorm_bwd_apply_kernel<1>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
     rc = after_launch();
   }
   if (rc == 0 && (dgamma || dbeta)) {
-    layernorm_param_reduce_kernel<<<(F + 31) / 32, 256, 0, st>>>(pg, pb, nchunks, F, dgamma, dbeta);
+    launch_k(layernorm_param_reduce_kernel, dim3((F + 31) / 32), dim3(256), 0, st, pg, pb, nchunks, F, dgamma, dbeta);
     rc = after_launch();
   }
   pool_free(scratch, st);
@@ -522,7 +531,7 @@ int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_s
                             void *stream) {
   if (!idx || !W || !out || !n || !D) return WEEDCU_EINVAL;
   ProfScope prof(WEEDCU_PROF_EMBEDDING, resolve_stream(stream), 8.0 * (double)n * D);
-  embedding_gather_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
+  launch_k(embedding_gather_kernel, dim3(grid_for((uint64_t)n * D, 256, 32)), dim3(256), 0, resolve_stream(stream), 
       idx + idx_off, idx_stride, n, W + w_off, w_s0, w_s1, D, out + o_off, o_s0, o_s1);
   return after_launch();
 }
@@ -533,7 +542,7 @@ int weedcu_embedding_scatter_add(float *dW, uint64_t w_off, uint32_t w_s0, uint3
                                  uint32_t o_s0, uint32_t o_s1, void *stream) {
   if (!dW || !idx || !dout || !n || !D) return WEEDCU_EINVAL;
   ProfScope prof(WEEDCU_PROF_EMBEDDING, resolve_stream(stream), 12.0 * (double)n * D);
-  embedding_scatter_kernel<<<grid_for((uint64_t)n * D, 256, 32), 256, 0, resolve_stream(stream)>>>(
+  launch_k(embedding_scatter_kernel, dim3(grid_for((uint64_t)n * D, 256, 32)), dim3(256), 0, resolve_stream(stream), 
       dW + w_off, w_s0, w_s1, idx + idx_off, idx_stride, n, D, dout + o_off, o_s0, o_s1);
   return after_launch();
 }
@@ -543,7 +552,7 @@ int weedcu_triu_fill_real(float *a, const weedcu_view *av, float val, uint32_t d
   if (!a || !av || av->rank != 2) return WEEDCU_EINVAL;
   const uint64_t total = (uint64_t)av->shape[0] * av->shape[1];
   if (!total) return WEEDCU_EINVAL;
-  triu_fill_kernel<<<grid_for(total, 256, 16), 256, 0, resolve_stream(stream)>>>(
+  launch_k(triu_fill_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, resolve_stream(stream), 
       a + av->offset, av->shape[0], av->shape[1], av->stride[0], av->stride[1], val, diagonal);
   return after_launch();
 }

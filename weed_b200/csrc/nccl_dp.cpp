@@ -10,6 +10,7 @@
 namespace weedcu {
 cudaStream_t resolve_stream(void *s);
 void count_launch(int n);
+void note_stream_op(); // the next kernel of this library launches plainly (no programmatic-dependent-launch edge)
 }
 
 namespace {
@@ -77,16 +78,19 @@ int weedcu_nccl_group_start(void) {
 }
 int weedcu_nccl_group_end(void) {
   if (!g_lib || !p_group_end) return WEEDCU_ENCCL;
+  weedcu::note_stream_op();
   return wrap(p_group_end());
 }
 int weedcu_nccl_allreduce_sum(void *comm, float *buf, uint64_t n, void *stream) {
   if (!g_lib) return WEEDCU_ENCCL;
   weedcu::count_launch(1);
+  weedcu::note_stream_op();
   return wrap(p_allreduce(buf, buf, (size_t)n, kNcclFloat, kNcclSum, comm, weedcu::resolve_stream(stream)));
 }
 int weedcu_nccl_broadcast(void *comm, float *buf, uint64_t n, int root, void *stream) {
   if (!g_lib) return WEEDCU_ENCCL;
   weedcu::count_launch(1);
+  weedcu::note_stream_op();
   return wrap(p_bcast(buf, buf, (size_t)n, kNcclFloat, root, comm, weedcu::resolve_stream(stream)));
 }
 

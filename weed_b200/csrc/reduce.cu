@@ -20,6 +20,7 @@ struct ReduceView {
 __global__ void __launch_bounds__(256)
 reduce_generic_kernel(const float *__restrict__ a, ReduceView v, uint32_t n_out, float *__restrict__ out,
                       int index_order) {
+  pdl_grid_sync();
   const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_out) return;
   uint64_t base = 0;
@@ -49,6 +50,7 @@ reduce_generic_kernel(const float *__restrict__ a, ReduceView v, uint32_t n_out,
 template <int BY>
 __global__ void __launch_bounds__(32 * BY)
 reduce_strided_kernel(const float *__restrict__ a, uint32_t inner, uint32_t L, float *__restrict__ out) {
+  pdl_grid_sync();
   __shared__ float part[BY][33];
   const uint32_t ii = blockIdx.x * 32 + threadIdx.x;
   const uint64_t slab = (uint64_t)blockIdx.y * inner * L;
@@ -77,6 +79,7 @@ reduce_strided_kernel(const float *__restrict__ a, uint32_t inner, uint32_t L, f
 // Case "contiguous axis" (inner == 1): one block per output, 128-bit loads along the axis.
 __global__ void __launch_bounds__(256)
 reduce_contig_kernel(const float *__restrict__ a, uint32_t L, float *__restrict__ out) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const float *p = a + (uint64_t)blockIdx.x * L;
   float s = 0.0f;
@@ -102,6 +105,7 @@ reduce_contig_kernel(const float *__restrict__ a, uint32_t L, float *__restrict_
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 reduce_contig_short_kernel(const float *__restrict__ a, uint32_t L, uint32_t n_out, float *__restrict__ out) {
+  pdl_grid_sync();
   const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_out) return;
   const float *p = a + (uint64_t)o * L;
@@ -123,6 +127,7 @@ reduce_contig_short_kernel(const float *__restrict__ a, uint32_t L, uint32_t n_o
 // Medium contiguous axis (32 < L < 2048): one warp per output, 8 outputs per block.
 __global__ void __launch_bounds__(256)
 reduce_contig_warp_kernel(const float *__restrict__ a, uint32_t L, uint32_t n_out, float *__restrict__ out) {
+  pdl_grid_sync();
   const uint32_t o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= n_out) return;
   const float *p = a + (uint64_t)o * L;
@@ -148,6 +153,7 @@ template <int NOPS>
 __global__ void __launch_bounds__(256)
 reduce_grad_reforder_kernel(float *din, IndexSpace<NOPS> sp_din, ReduceView dims,
                             const float *__restrict__ dout, ReduceView dv) {
+  pdl_grid_sync();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sp_din.n) return;
   uint64_t o = 0;
@@ -170,6 +176,7 @@ reduce_grad_reforder_kernel(float *din, IndexSpace<NOPS> sp_din, ReduceView dims
 template <int NOPS>
 __global__ void __launch_bounds__(256)
 sum_pass1_kernel(const float *__restrict__ a, IndexSpace<NOPS> sp, bool linear_vec, float *__restrict__ partial) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float s0 = 0.0f, s1 = 0.0f;
   const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +210,7 @@ sum_pass1_kernel(const float *__restrict__ a, IndexSpace<NOPS> sp, bool linear_v
 }
 __global__ void __launch_bounds__(1024)
 sum_pass2_kernel(const float *__restrict__ partial, uint32_t n, float scale, float *__restrict__ out) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float s = 0.0f;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
@@ -217,6 +225,7 @@ template <int BY>
 __global__ void __launch_bounds__(32 * BY)
 argmax_rows_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
                    int32_t *__restrict__ out) {
+  pdl_grid_sync();
   __shared__ float mv[BY][33];
   __shared__ uint32_t mi[BY][33];
   const uint32_t r = blockIdx.x * 32 + threadIdx.x;
@@ -292,13 +301,13 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
       if (L <= 32) {
         const unsigned blocks = (unsigned)((outer + 255) / 256);
         if ((L % 4u) == 0 && aligned16(base))
-          reduce_contig_short_kernel<true><<<blocks, 256, 0, st>>>(base, L, (uint32_t)outer, out);
+          launch_k(reduce_contig_short_kernel<true>, dim3(blocks), dim3(256), 0, st, base, L, (uint32_t)outer, out);
         else
-          reduce_contig_short_kernel<false><<<blocks, 256, 0, st>>>(base, L, (uint32_t)outer, out);
+          launch_k(reduce_contig_short_kernel<false>, dim3(blocks), dim3(256), 0, st, base, L, (uint32_t)outer, out);
       } else if (L < 2048 && outer >= 2 * (uint64_t)kNumSMs) {
-        reduce_contig_warp_kernel<<<(unsigned)((outer + 7) / 8), 256, 0, st>>>(base, L, (uint32_t)outer, out);
+        launch_k(reduce_contig_warp_kernel, dim3((unsigned)((outer + 7) / 8)), dim3(256), 0, st, base, L, (uint32_t)outer, out);
       } else {
-        reduce_contig_kernel<<<(unsigned)outer, 256, 0, st>>>(base, L, out);
+        launch_k(reduce_contig_kernel, dim3((unsigned)outer), dim3(256), 0, st, base, L, out);
       }
       return after_launch();
     }
@@ -306,9 +315,9 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
       dim3 grid((unsigned)((inner + 31) / 32), (unsigned)outer);
       const uint64_t blocks = (uint64_t)grid.x * grid.y;
       if (L >= 64 && blocks < 4 * kNumSMs) {
-        reduce_strided_kernel<16><<<grid, dim3(32, 16), 0, st>>>(base, (uint32_t)inner, L, out);
+        launch_k(reduce_strided_kernel<16>, dim3(grid), dim3(32, 16), 0, st, base, (uint32_t)inner, L, out);
       } else {
-        reduce_strided_kernel<4><<<grid, dim3(32, 4), 0, st>>>(base, (uint32_t)inner, L, out);
+        launch_k(reduce_strided_kernel<4>, dim3(grid), dim3(32, 4), 0, st, base, (uint32_t)inner, L, out);
       }
       return after_launch();
     }
@@ -320,7 +329,7 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
     v.shape[d] = d < av->rank ? av->shape[d] : 1;
     v.stride[d] = d < av->rank ? av->stride[d] : 0;
   }
-  reduce_generic_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(base, v, (uint32_t)n_out, out,
+  launch_k(reduce_generic_kernel, dim3((unsigned)((n_out + 255) / 256)), dim3(256), 0, st, base, v, (uint32_t)n_out, out,
                                                                        index_order);
   return after_launch();
 }
@@ -366,7 +375,7 @@ int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *do
     dv.shape[d] = sp.shape[d];
     dv.stride[d] = d < doutv->rank ? doutv->stride[d] : 0;
   }
-  reduce_grad_reforder_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, resolve_stream(stream)>>>(
+  launch_k(reduce_grad_reforder_kernel<1>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, resolve_stream(stream), 
       din + dinv->offset, sp, dims, dout + doutv->offset, dv);
   return after_launch();
 }
@@ -388,10 +397,10 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
   float *partial = nullptr;
   WCU_CHECK(pool_alloc((void **)&partial, sizeof(float) * blocks, st));
   ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * sp.n);
-  sum_pass1_kernel<1><<<blocks, 256, 0, st>>>(base, sp, vec, partial);
+  launch_k(sum_pass1_kernel<1>, dim3(blocks), dim3(256), 0, st, base, sp, vec, partial);
   int rc = after_launch();
   if (rc == 0) {
-    sum_pass2_kernel<<<1, 1024, 0, st>>>(partial, blocks, scale, out);
+    launch_k(sum_pass2_kernel, dim3(1), dim3(1024), 0, st, partial, blocks, scale, out);
     rc = after_launch();
   }
   pool_free(partial, st);
@@ -401,7 +410,7 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
 int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs,
                        uint32_t vs, int32_t *out, void *stream) {
   if (!x || !out || !rows || !V) return WEEDCU_EINVAL;
-  argmax_rows_kernel<16><<<(rows + 31) / 32, dim3(32, 16), 0, resolve_stream(stream)>>>(
+  launch_k(argmax_rows_kernel<16>, dim3((rows + 31) / 32), dim3(32, 16), 0, resolve_stream(stream), 
       x + offset, rows, V, rs, vs, out);
   return after_launch();
 }

@@ -53,6 +53,7 @@ template <bool LOG, int RT, int BY, bool STAGED, class LD>
 __global__ void __launch_bounds__(RT * BY)
 softmax_strided_fwd(const float *a, float *out, uint32_t inner, uint32_t L,
                     LD ld) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // [L][RT] when STAGED
   __shared__ float red_m[BY][RT + 1];
   __shared__ float red_s[BY][RT + 1];
@@ -144,6 +145,7 @@ constexpr int kSmBY = 16, kSmU = 8, kSmCols = 8;
 __global__ void __launch_bounds__(32 * kSmBY)
 softmax_rows_partial_kernel(const float *__restrict__ a, uint32_t inner, uint32_t L, uint32_t cols_per_split,
                             float *__restrict__ part_m, float *__restrict__ part_s) {
+  pdl_grid_sync();
   __shared__ float red_m[kSmBY][33];
   __shared__ float red_s[kSmBY][33];
   const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
@@ -196,6 +198,7 @@ template <bool LOG>
 __global__ void __launch_bounds__(256)
 softmax_rows_finish_kernel(const float *__restrict__ part_m, const float *__restrict__ part_s, uint32_t splits, uint64_t n_rows,
                            float *__restrict__ row_m, float *__restrict__ row_s) {
+  pdl_grid_sync();
   const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
   float M = -INFINITY;
@@ -213,6 +216,7 @@ template <bool LOG, int VEC>
 __global__ void __launch_bounds__(256)
 softmax_apply_kernel(const float *__restrict__ a, float *__restrict__ out, uint32_t inner, uint32_t L,
                      const float *__restrict__ row_m, const float *__restrict__ row_s) {
+  pdl_grid_sync();
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   if (r >= inner) return;
   const uint64_t slab = (uint64_t)blockIdx.z * inner * L, rbase = (uint64_t)blockIdx.z * inner + r;
@@ -254,6 +258,7 @@ softmax_apply_kernel(const float *__restrict__ a, float *__restrict__ out, uint3
 template <bool LOG>
 __global__ void __launch_bounds__(256)
 softmax_contig_fwd(const float *__restrict__ a, float *__restrict__ out, uint32_t L) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const float *p = a + (uint64_t)blockIdx.x * L;
   float *po = out + (uint64_t)blockIdx.x * L;
@@ -287,6 +292,7 @@ __device__ __forceinline__ uint64_t row_base(const RowView &v, uint32_t o) {
 template <bool LOG>
 __global__ void __launch_bounds__(128)
 softmax_generic_fwd(const float *__restrict__ a, RowView av, float *__restrict__ out, RowView ov, uint32_t n_rows) {
+  pdl_grid_sync();
   const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_rows) return;
   const uint32_t L = av.shape[av.axis];
@@ -306,6 +312,7 @@ template <bool LOG>
 __global__ void __launch_bounds__(128)
 softmax_generic_bwd(float *din, RowView iv, const float *__restrict__ out, RowView ov,
                     const float *__restrict__ dout, RowView dv, uint32_t n_rows) {
+  pdl_grid_sync();
   const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_rows) return;
   const uint32_t L = iv.shape[iv.axis];
@@ -327,6 +334,7 @@ template <bool LOG, int BY, bool STAGED>
 __global__ void __launch_bounds__(kRT * BY)
 softmax_strided_bwd(float *din, const float *__restrict__ out, const float *__restrict__ dout,
                     uint32_t inner, uint32_t L) {
+  pdl_grid_sync();
   extern __shared__ float tile[]; // STAGED: [2][L][kRT]  (out, dout)
   __shared__ float red[BY][kRT + 1];
   const uint32_t tx = threadIdx.x, ty = threadIdx.y;
@@ -361,6 +369,7 @@ softmax_strided_bwd(float *din, const float *__restrict__ out, const float *__re
 template <bool LOG>
 __global__ void __launch_bounds__(256)
 softmax_contig_bwd(float *din, const float *__restrict__ out, const float *__restrict__ dout, uint32_t L) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const uint64_t b = (uint64_t)blockIdx.x * L;
   float acc = 0.0f;
@@ -381,6 +390,7 @@ constexpr int kCeRT = 32, kCeBY = 8, kCeU = 8; // 8 independent 128-B row loads 
 __global__ void __launch_bounds__(kCeRT * kCeBY)
 ce_fwd_partial(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
                uint32_t v_per_block, float *__restrict__ part_m, float *__restrict__ part_s) {
+  pdl_grid_sync();
   __shared__ float red_m[kCeBY][kCeRT + 1];
   __shared__ float red_s[kCeBY][kCeRT + 1];
   const uint32_t tx = threadIdx.x, ty = threadIdx.y;
@@ -431,6 +441,7 @@ ce_fwd_finish(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
               const int32_t *__restrict__ targets, const float *__restrict__ part_m,
               const float *__restrict__ part_s, uint32_t splits, float *__restrict__ lse,
               float *__restrict__ nll) {
+  pdl_grid_sync();
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float M = -INFINITY;
@@ -451,6 +462,7 @@ __global__ void __launch_bounds__(kCeRT * kCeBY)
 ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
               uint32_t v_per_block, const int32_t *__restrict__ targets, const float *__restrict__ lse,
               const float *__restrict__ dloss, float *dlogits, int accumulate) {
+  pdl_grid_sync();
   const uint32_t r = blockIdx.x * kCeRT + threadIdx.x;
   if (r >= rows) return;
   const uint32_t v0 = blockIdx.y * v_per_block, v1 = min(V, v0 + v_per_block);
@@ -486,6 +498,7 @@ __global__ void __launch_bounds__(256)
 ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const int32_t *__restrict__ targets,
                    const float *__restrict__ lse, const float *__restrict__ dloss, float *dlogits, int accumulate,
                    __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  pdl_grid_sync();
   __shared__ float red[8][kCePackCols];
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * 4u;
   const bool live = r < rows;
@@ -547,6 +560,7 @@ ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const
 // colsum[j] (+)= sum_c part[c][j] in a fixed order
 __global__ void __launch_bounds__(256)
 ce_colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t V, float *__restrict__ colsum) {
+  pdl_grid_sync();
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= V) return;
   float t = 0.0f;
@@ -604,7 +618,7 @@ static void launch_strided_fwd_cfg(const float *a, float *out, uint32_t inner, u
   auto k = softmax_strided_fwd<LOG, RT, BY, STAGED, LD>;
   if (tile_bytes > 48 * 1024)
     ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
-  k<<<grid, dim3(RT, BY), tile_bytes, st>>>(a, out, inner, L, ld);
+  launch_k(k, dim3(grid), dim3(RT, BY), tile_bytes, st, a, out, inner, L, ld);
 }
 
 template <bool LOG, class LD>
@@ -635,7 +649,7 @@ static int softmax_fwd_impl(const float *a, const weedcu_view *av, int axis, flo
     const float *pa = a + av->offset;
     float *po = out + ov->offset;
     if (inner == 1) {
-      softmax_contig_fwd<LOG><<<(unsigned)outer, 256, 0, st>>>(pa, po, L);
+      launch_k(softmax_contig_fwd<LOG>, dim3((unsigned)outer), dim3(256), 0, st, pa, po, L);
       return after_launch();
     }
     // big problems: two streaming passes (row statistics, then elementwise); small ones (a few tiles,
@@ -657,17 +671,17 @@ static int softmax_fwd_impl(const float *a, const weedcu_view *av, int axis, flo
         const uint64_t rows_up = (n_rows64 + 3) & ~(uint64_t)3;
         WCU_CHECK(pool_alloc((void **)&ws, sizeof(float) * (2 * (size_t)splits * n_rows64 + 2 * rows_up), st));
         float *pm = ws, *ps = pm + (size_t)splits * n_rows64, *rm = ps + (size_t)splits * n_rows64, *rs = rm + rows_up;
-        softmax_rows_partial_kernel<<<dim3(row_tiles, (unsigned)outer, splits), 32 * kSmBY, 0, st>>>(pa, (uint32_t)inner, L, cps, pm, ps);
+        launch_k(softmax_rows_partial_kernel, dim3(row_tiles, (unsigned)outer, splits), dim3(32 * kSmBY), 0, st, pa, (uint32_t)inner, L, cps, pm, ps);
         int rc = after_launch();
         if (rc == 0) {
-          softmax_rows_finish_kernel<LOG><<<(unsigned)((n_rows64 + 255) / 256), 256, 0, st>>>(pm, ps, splits, n_rows64, rm, rs);
+          launch_k(softmax_rows_finish_kernel<LOG>, dim3((unsigned)((n_rows64 + 255) / 256)), dim3(256), 0, st, pm, ps, splits, n_rows64, rm, rs);
           rc = after_launch();
         }
         if (rc == 0) {
           if ((inner % 4) == 0 && aligned16(pa) && aligned16(po))
-            softmax_apply_kernel<LOG, 4><<<dim3((unsigned)((inner / 4 + 255) / 256), cgroups, (unsigned)outer), 256, 0, st>>>(pa, po, (uint32_t)inner, L, rm, rs);
+            launch_k(softmax_apply_kernel<LOG, 4>, dim3((unsigned)((inner / 4 + 255) / 256), cgroups, (unsigned)outer), dim3(256), 0, st, pa, po, (uint32_t)inner, L, rm, rs);
           else
-            softmax_apply_kernel<LOG, 1><<<dim3((unsigned)((inner + 255) / 256), cgroups, (unsigned)outer), 256, 0, st>>>(pa, po, (uint32_t)inner, L, rm, rs);
+            launch_k(softmax_apply_kernel<LOG, 1>, dim3((unsigned)((inner + 255) / 256), cgroups, (unsigned)outer), dim3(256), 0, st, pa, po, (uint32_t)inner, L, rm, rs);
           rc = after_launch();
         }
         pool_free(ws, st);
@@ -679,7 +693,7 @@ static int softmax_fwd_impl(const float *a, const weedcu_view *av, int axis, flo
   RowView ra, ro;
   to_rowview(av, axis, ra);
   to_rowview(ov, axis, ro);
-  softmax_generic_fwd<LOG><<<(n_rows + 127) / 128, 128, 0, st>>>(a, ra, out, ro, n_rows);
+  launch_k(softmax_generic_fwd<LOG>, dim3((n_rows + 127) / 128), dim3(128), 0, st, a, ra, out, ro, n_rows);
   return after_launch();
 }
 
@@ -696,7 +710,7 @@ static int softmax_bwd_impl(float *din, const weedcu_view *iv, const float *out,
     float *pd = din + iv->offset;
     const float *py = out + ov->offset, *pg = dout + dv->offset;
     if (inner == 1) {
-      softmax_contig_bwd<LOG><<<(unsigned)outer, 256, 0, st>>>(pd, py, pg, L);
+      launch_k(softmax_contig_bwd<LOG>, dim3((unsigned)outer), dim3(256), 0, st, pd, py, pg, L);
       return after_launch();
     }
     if (outer <= 65535) {
@@ -706,14 +720,14 @@ static int softmax_bwd_impl(float *din, const weedcu_view *iv, const float *out,
         if (L >= 256) {
           auto k = softmax_strided_bwd<LOG, 32, true>;
           ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
-          k<<<grid, dim3(kRT, 32), tile_bytes, st>>>(pd, py, pg, (uint32_t)inner, L);
+          launch_k(k, dim3(grid), dim3(kRT, 32), tile_bytes, st, pd, py, pg, (uint32_t)inner, L);
         } else {
           auto k = softmax_strided_bwd<LOG, 8, true>;
           ensure_dynamic_smem((const void *)k, (int)kMaxTileBytes);
-          k<<<grid, dim3(kRT, 8), tile_bytes, st>>>(pd, py, pg, (uint32_t)inner, L);
+          launch_k(k, dim3(grid), dim3(kRT, 8), tile_bytes, st, pd, py, pg, (uint32_t)inner, L);
         }
       } else {
-        softmax_strided_bwd<LOG, 32, false><<<grid, dim3(kRT, 32), 0, st>>>(pd, py, pg, (uint32_t)inner, L);
+        launch_k(softmax_strided_bwd<LOG, 32, false>, dim3(grid), dim3(kRT, 32), 0, st, pd, py, pg, (uint32_t)inner, L);
       }
       return after_launch();
     }
@@ -722,7 +736,7 @@ static int softmax_bwd_impl(float *din, const weedcu_view *iv, const float *out,
   to_rowview(iv, axis, ri);
   to_rowview(ov, axis, ro);
   to_rowview(dv, axis, rd);
-  softmax_generic_bwd<LOG><<<(n_rows + 127) / 128, 128, 0, st>>>(din, ri, out, ro, dout, rd, n_rows);
+  launch_k(softmax_generic_bwd<LOG>, dim3((n_rows + 127) / 128), dim3(128), 0, st, din, ri, out, ro, dout, rd, n_rows);
   return after_launch();
 }
 
@@ -788,11 +802,11 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
   WCU_CHECK(pool_alloc((void **)&ws, sizeof(float) * (size_t)rows * (1 + 2 * (size_t)splits), st));
   float *nll = ws, *pm = ws + rows, *ps = pm + (size_t)splits * rows;
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 4.0 * (double)rows * V);
-  ce_fwd_partial<<<dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, st>>>(
+  launch_k(ce_fwd_partial, dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, st, 
       logits + offset, rows, V, rs, vs, vpb, pm, ps);
   int rc = after_launch();
   if (rc == 0) {
-    ce_fwd_finish<<<(rows + 255) / 256, 256, 0, st>>>(logits + offset, rows, V, rs, vs, targets, pm, ps, splits, lse, nll);
+    launch_k(ce_fwd_finish, dim3((rows + 255) / 256), dim3(256), 0, st, logits + offset, rows, V, rs, vs, targets, pm, ps, splits, lse, nll);
     rc = after_launch();
   }
   if (rc == 0) {
@@ -816,7 +830,7 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
   uint32_t splits, vpb;
   ce_split(rows, V, splits, vpb);
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, resolve_stream(stream), (accumulate ? 12.0 : 8.0) * (double)n);
-  ce_bwd_kernel<<<dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, resolve_stream(stream)>>>(
+  launch_k(ce_bwd_kernel, dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, resolve_stream(stream), 
       logits + offset, rows, V, rs, vs, vpb, targets, lse, dloss, dlogits + d_offset, accumulate);
   return after_launch();
 }
@@ -834,10 +848,10 @@ int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 14.0 : 10.0) * (double)rows * V);
-  ce_bwd_pack_kernel<<<dim3(nchunks, cgroups), 256, 0, st>>>(x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
+  launch_k(ce_bwd_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
   int rc = after_launch();
   if (rc == 0) {
-    ce_colsum_finish_kernel<<<(V + 255u) / 256u, 256, 0, st>>>(part, nchunks, V, colsum);
+    launch_k(ce_colsum_finish_kernel, dim3((V + 255u) / 256u), dim3(256), 0, st, part, nchunks, V, colsum);
     rc = after_launch();
   }
   pool_free(part, st);
