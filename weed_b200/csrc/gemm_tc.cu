@@ -583,6 +583,21 @@ int make_operand_map(CUtensorMap *map, const uint16_t *ptr, int major, uint64_t 
   return r == CUDA_SUCCESS ? 0 : WEEDCU_ENOSUP;
 }
 
+int make_plain_map_2d(CUtensorMap *map, const void *ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return WEEDCU_ENOSUP;
+  if ((((uintptr_t)ptr) & 15u) || (outer_stride_bytes % 16) || ((box_inner * (uint32_t)elem_bytes) % 16) || box_inner > 256 || box_outer > 256)
+    return WEEDCU_ENOSUP;
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t dims[2] = {inner, outer}, strides[1] = {outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer}, estr[2] = {1, 1};
+  return enc(map, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : WEEDCU_ENOSUP;
+}
+
 // fp32 C [M, N] (+batch) column-major with leading dimension ldc: TMA box = 128 rows x 32 columns,
 // no swizzle (the staging tile in shared memory is plain [col][row]). Needs a 16-B aligned base and
 // 16-B multiples for the column / batch strides; otherwise the kernel stores C directly.

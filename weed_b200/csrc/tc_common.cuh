@@ -73,6 +73,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 // smem -> global tile store through TMA (clips at the tensor edges); `.add` variant reduces into C
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -219,6 +229,10 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32
 // bf16 matrix [mn, k] per batch as a 3-D tensor map with 128-B swizzle. major 0: k contiguous (ld =
 // stride of the mn index), box = {64 k, box_mn}; major 1: mn contiguous (ld = stride of the k
 // index), box = {64 mn, 64 k}. WEEDCU_ENOSUP when the 16-byte alignment rules of TMA are not met.
+// plain (unswizzled) 2-D map over a matrix whose inner index is contiguous: dims {inner, outer}, outer stride in BYTES
+// (a multiple of 16), box {box_inner, box_outer} (box_inner * elem_bytes a multiple of 16, each <= 256).
+int make_plain_map_2d(CUtensorMap *map, const void *ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
 int make_operand_map(CUtensorMap *map, const uint16_t *ptr, int major, uint64_t mn, uint64_t k, uint64_t ld,
                      uint64_t batch, uint64_t batch_stride, uint32_t box_mn);
 
