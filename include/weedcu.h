@@ -129,7 +129,8 @@ int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n,
 /* gelu_grad (tensor.cpp:841-851 backward; as weedcu_unary_grad_real(WEEDCU_GELU)) on a dense [rows, cols]
  * matrix with rows contiguous, fused with the preparation of the Linear backward that consumes din:
  * din (+)= dout * gelu'(in), din_bf16[i] = bf16(din[i]), colsum[c] = sum_r din[r, c] (stored; fixed order).
- * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned. */
+ * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned.
+ * din may be NULL when accumulate == 0 (bf16 copy and column sums only; weedcu_unary_grad_real gives the fp32 values). */
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols,
                           int accumulate, uint16_t *din_bf16, float *colsum, void *stream);
 
@@ -226,7 +227,9 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
  * tensor.cpp:1105-1136,1361-1400): one pass writes dlogits (fp32, exactly as weedcu_cross_entropy_bwd
  * with rs = 1, vs = rows), dlogits_bf16[v*rows + r] = bf16(dlogits) and colsum[v] = sum_r dlogits[r,v]
  * (stored, not accumulated; deterministic order). 10-14 B/elem instead of 8-12 + 6 + 4.
- * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned. */
+ * WEEDCU_ENOSUP unless rows % 8 == 0 and all buffers are 16-byte aligned.
+ * dlogits may be NULL when accumulate == 0: only the bf16 operand copy and the column sums are written
+ * (10 -> 6 B/elem); the caller then owns producing the fp32 values on demand (weedcu_cross_entropy_bwd). */
 int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V,
                                   const int32_t *targets, const float *lse, const float *dloss,
                                   float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,

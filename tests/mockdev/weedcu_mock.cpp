@@ -147,11 +147,21 @@ int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n,
 }
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate, uint16_t *din_bf16, float *colsum, void *) {
   if (rows % 8u) return WEEDCU_ENOSUP;
+  if (!din) { // operand copy + column sums only (the fp32 values are materialised on demand by the host)
+    if (accumulate) return WEEDCU_EINVAL;
+    std::vector<float> tmp((size_t)rows * cols);
+    return RUN(wo_gelu_grad_pack(tmp.data(), in, dout, rows, cols, 0, din_bf16, colsum));
+  }
   return RUN(wo_gelu_grad_pack(din, in, dout, rows, cols, accumulate, din_bf16, colsum));
 }
 int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss, float *dlogits,
                                   uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *) {
   if (rows % 8u) return WEEDCU_ENOSUP;
+  if (!dlogits) {
+    if (accumulate) return WEEDCU_EINVAL;
+    std::vector<float> tmp((size_t)rows * V);
+    return RUN(wo_cross_entropy_bwd_pack(logits, offset, rows, V, targets, lse, dloss, tmp.data(), 0, 0, dlogits_bf16, colsum));
+  }
   return RUN(wo_cross_entropy_bwd_pack(logits, offset, rows, V, targets, lse, dloss, dlogits, d_offset, accumulate, dlogits_bf16, colsum));
 }
 int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, void *) {

@@ -481,3 +481,62 @@ def test_operand_cache_and_lazy_zero_change_nothing(P):
         P.config("operand_cache", 1)
         P.config("lazy_zero", 1)
         set_mode(P, 1)
+
+
+def test_deferred_gradients_change_nothing(P):
+    """BackendConfig::defer_grads: the fused cross-entropy backward and the fused GELU backward leave only the
+    bf16 GEMM operand copy + column sums of their gradient; the fp32 values are produced when something reads
+    them. Reading those gradients afterwards, every parameter gradient and the loss must equal the run that
+    writes them eagerly (bit for bit on the serial mock; on the GPU up to float-atomic order in the embedding
+    scatter), and a second read must not recompute."""
+    B, T, V, d = 2, 64, 512, 64
+
+    def run(defer):
+        set_mode(P, 1, precision=1)
+        P.config("defer_grads", defer)
+        rng = np.random.default_rng(4100)
+        tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        targets = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        # (a) cross-entropy: logits of an Embedding - Linear model
+        model = P.module("sequential", P.module("embedding", V, d), P.module("linear", d, V, 1))
+        P.init_params(model, 2200)
+        tok = P.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+        tgt = P.symbol(np.ascontiguousarray(targets.T).ravel(), [B, T])
+        logits = P.forward_symbol(model, tok)
+        loss = P.cross_entropy(logits, tgt)
+        P.backward(loss)
+        pg = [P.read_storage(P.grad(P.param(model, i))).copy() for i in range(P.param_count(model))]
+        dl1 = P.read_storage(P.grad(logits)).copy()   # materialised on demand when deferred
+        dl2 = P.read_storage(P.grad(logits)).copy()
+        lv = float(P.read(loss)[0])
+        # (b) GELU: x - Linear - gelu - Linear - mean; h is the pre-activation whose gradient is deferred
+        x = P.tensor(rng.uniform(-1, 1, size=128 * d).astype(np.float32), [128, d], requires_grad=True)
+        l1, l2 = P.module("linear", d, 4 * d, 1), P.module("linear", 4 * d, d, 1)
+        P.init_params(l1, 2300)
+        P.init_params(l2, 2301)
+        h = P.forward(l1, x)
+        y = P.op("gelu", [h])
+        z = P.forward(l2, y)
+        m = P.op("mean", [z])
+        P.backward(m)
+        gx = P.read_storage(P.grad(x)).copy()
+        gw = [P.read_storage(P.grad(P.param(l1, i))).copy() for i in range(P.param_count(l1))]
+        gh = P.read_storage(P.grad(h)).copy()
+        P.reset()
+        return lv, pg, dl1, dl2, gx, gw, gh
+
+    exact = "mock" in os.path.basename(P.path)
+    try:
+        ref = run(0)
+        got = run(1)
+    finally:
+        P.config("defer_grads", 1)
+        set_mode(P, 1)
+    assert np.array_equal(got[2], got[3]), "second read of the deferred gradient differs from the first"
+    assert np.abs(ref[2]).max() > 0 and np.abs(ref[6]).max() > 0
+    flat = lambda r: [np.asarray([r[0]])] + r[1] + [r[2], r[4]] + r[5] + [r[6]]
+    for i, (a, b) in enumerate(zip(flat(ref), flat(got))):
+        if exact:
+            assert np.array_equal(a, b), f"item {i} differs with deferred gradients"
+        else:
+            assert cases.rel_err(b, a) <= 1e-6, f"item {i}: {cases.rel_err(b, a):.2e}"

@@ -284,7 +284,7 @@ gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__r
           o.z = dv[u].z + gv[u].z * gelu_dfdx(xv[u].z);
           o.w = dv[u].w + gv[u].w * gelu_dfdx(xv[u].w);
           const uint64_t off = (uint64_t)j * rows + r;
-          *reinterpret_cast<float4 *>(din + off) = o;
+          if (din) *reinterpret_cast<float4 *>(din + off) = o; // NULL: operand copy + column sums only
           __nv_bfloat162 h[2];
           h[0] = __floats2bfloat162_rn(o.x, o.y);
           h[1] = __floats2bfloat162_rn(o.z, o.w);
@@ -533,14 +533,15 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
 
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,
                           uint16_t *din_bf16, float *colsum, void *stream) {
-  if (!din || !in || !dout || !din_bf16 || !colsum || !rows || !cols) return WEEDCU_EINVAL;
-  if ((rows % 8u) || !aligned16(din) || !aligned16(in) || !aligned16(dout) || !aligned16(din_bf16)) return WEEDCU_ENOSUP;
+  if (!in || !dout || !din_bf16 || !colsum || !rows || !cols) return WEEDCU_EINVAL;
+  if (!din && accumulate) return WEEDCU_EINVAL; // nothing to accumulate into
+  if ((rows % 8u) || (din && !aligned16(din)) || !aligned16(in) || !aligned16(dout) || !aligned16(din_bf16)) return WEEDCU_ENOSUP;
   const uint32_t nchunks = (rows + 1023u) / 1024u, cgroups = (cols + kGgCols - 1) / kGgCols;
   if (cgroups > 65535u) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * cols, st));
-  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (accumulate ? 18.0 : 14.0) * (double)rows * cols);
+  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (accumulate ? 18.0 : (din ? 14.0 : 10.0)) * (double)rows * cols);
   launch_k(gelu_grad_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
   int rc = after_launch();
   if (rc == 0) {

@@ -533,7 +533,7 @@ ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const
           o.z = dv[u].z + (expf(xv[u].z - l4.z) - (((uint32_t)t4.z == j) ? 1.0f : 0.0f)) * g;
           o.w = dv[u].w + (expf(xv[u].w - l4.w) - (((uint32_t)t4.w == j) ? 1.0f : 0.0f)) * g;
           const uint64_t off = (uint64_t)j * rows + r;
-          *reinterpret_cast<float4 *>(dlogits + off) = o;
+          if (dlogits) *reinterpret_cast<float4 *>(dlogits + off) = o; // NULL: operand copy + column sums only
           __nv_bfloat162 h[2];
           h[0] = __floats2bfloat162_rn(o.x, o.y);
           h[1] = __floats2bfloat162_rn(o.z, o.w);
@@ -838,16 +838,17 @@ int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows
 int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, const int32_t *targets,
                                   const float *lse, const float *dloss, float *dlogits, uint64_t d_offset, int accumulate,
                                   uint16_t *dlogits_bf16, float *colsum, void *stream) {
-  if (!logits || !targets || !lse || !dloss || !dlogits || !dlogits_bf16 || !colsum || !rows || !V) return WEEDCU_EINVAL;
+  if (!logits || !targets || !lse || !dloss || !dlogits_bf16 || !colsum || !rows || !V) return WEEDCU_EINVAL;
+  if (!dlogits && accumulate) return WEEDCU_EINVAL; // nothing to accumulate into
   const float *x = logits + offset;
-  float *d = dlogits + d_offset;
-  if ((rows % 8u) || !aligned16(x) || !aligned16(d) || !aligned16(lse) || !aligned16(targets) || !aligned16(dlogits_bf16)) return WEEDCU_ENOSUP;
+  float *d = dlogits ? dlogits + d_offset : nullptr;
+  if ((rows % 8u) || !aligned16(x) || (d && !aligned16(d)) || !aligned16(lse) || !aligned16(targets) || !aligned16(dlogits_bf16)) return WEEDCU_ENOSUP;
   const uint32_t nchunks = (rows + 1023u) / 1024u, cgroups = (V + kCePackCols - 1) / kCePackCols;
   if (cgroups > 65535u) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
-  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 14.0 : 10.0) * (double)rows * V);
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 14.0 : (d ? 10.0 : 6.0)) * (double)rows * V);
   launch_k(ce_bwd_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
   int rc = after_launch();
   if (rc == 0) {

@@ -92,6 +92,9 @@ struct BackendConfig {
   bool operand_cache = true;
   // FillZeros() on device buffers is deferred until something reads the buffer (fused mode only)
   bool lazy_zero = true;
+  // gradients whose only readers are bf16 GEMM operands + column sums (dlogits of the fused cross-entropy,
+  // the GELU input gradient) are not written in fp32 until something reads them (GpuStorage::deferred_values)
+  bool defer_grads = true;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)
@@ -249,7 +252,19 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
   // `version` counts potential writes; the bf16 operand shadows of GpuRealStorage key on it.
   mutable bool zero_pending = false;
   mutable uint64_t version = 0;
+  // Deferred values (fused mode, BackendConfig::defer_grads): a producer that already left everything its
+  // consumers read — the bf16 GEMM operand copy and the column sums — may skip writing the fp32 values and
+  // register how to compute them instead. The first access that needs the fp32 buffer runs it (a full
+  // overwrite that does not count as a write: the shadows stay valid); a full overwrite or fill drops it.
+  mutable std::function<void()> deferred_values;
   void materialize() const {
+    if (deferred_values) {
+      std::function<void()> f;
+      f.swap(deferred_values);
+      zero_pending = false;
+      f();
+      return;
+    }
     if (!zero_pending) return;
     zero_pending = false;
     const_cast<GpuStorage<T> *>(this)->fill_now(T(0));
@@ -265,6 +280,7 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
     return reinterpret_cast<const T *>(buffer->ptr);
   }
   T *device_ptr_overwrite() const { // the caller overwrites every element
+    deferred_values = nullptr;
     zero_pending = false;
     ++version;
     return reinterpret_cast<T *>(buffer->ptr);

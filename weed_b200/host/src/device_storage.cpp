@@ -22,6 +22,7 @@ BackendConfig &backend_config() {
     }
     if (const char *e = getenv("WEED_B200_OPERAND_CACHE")) c.operand_cache = atoi(e) != 0;
     if (const char *e = getenv("WEED_B200_LAZY_ZERO")) c.lazy_zero = atoi(e) != 0;
+    if (const char *e = getenv("WEED_B200_DEFER_GRADS")) c.defer_grads = atoi(e) != 0;
     return c;
   }();
   return cfg;
@@ -152,6 +153,7 @@ StoragePtr CpuRealStorage::gpu(const int64_t &did) { return std::make_shared<Gpu
 StoragePtr CpuIntStorage::gpu(const int64_t &did) { return std::make_shared<GpuIntStorage>(data, did); }
 void GpuRealStorage::FillValue(const real1 &v) {
   ++version;
+  deferred_values = nullptr;
   if (v == ZERO_R1 && backend_config().fused && backend_config().lazy_zero) { // lazy: see GpuStorage::zero_pending
     zero_pending = true;
     return;

@@ -265,15 +265,15 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
   const tcapint s_fast = mn_fast ? s_mn : s_k, s_slow = mn_fast ? s_k : s_mn;
   op.major = mn_fast ? 1 : 0;
   op.ld = round8(n_fast);
-  const real1 *src = s->device_ptr_ro(); // (materialises a pending zero fill; keeps the version)
   GpuRealStorage::Bf16Shadow *hit = nullptr;
   for (GpuRealStorage::Bf16Shadow &sh : s->shadows)
     if (sh.offset == t.offset && sh.n_fast == n_fast && sh.n_slow == n_slow && sh.s_fast == s_fast && sh.s_slow == s_slow) hit = &sh;
-  if (hit && hit->version == s->version) {
+  if (hit && hit->version == s->version) { // (a current shadow is served without touching the fp32 buffer: deferred values stay deferred)
     if (colsum) return false;
     op.ptr = (const uint16_t *)hit->buf->ptr;
     return true;
   }
+  const real1 *src = s->device_ptr_ro(); // (materialises a pending zero fill / deferred values; keeps the version)
   if (!hit) {
     if (s->shadows.size() >= 4U) s->shadows.erase(s->shadows.begin());
     s->shadows.push_back(GpuRealStorage::Bf16Shadow{s->dev->MakeBuffer(2U * (size_t)(op.ld * n_slow + 8U)), 0U, t.offset, n_fast, n_slow, s_fast, s_slow});
@@ -465,11 +465,30 @@ void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) {
         ds->colsum_n = cols;
       }
       const Dev di = dev_of(in, "gelu_grad"), dg = dev_of(dout, "gelu_grad");
+      const bool defer = !accumulate && cfg.defer_grads;
       real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
-      const int rc = weedcu_gelu_grad_pack(out, di.ptr, dg.ptr, rows, cols, accumulate, (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr, ds->dev->stream);
+      const int rc = weedcu_gelu_grad_pack(defer ? nullptr : out, di.ptr, dg.ptr, rows, cols, accumulate, (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr,
+                                           ds->dev->stream);
       if (rc == 0) {
         hit->version = ds->version;
         ds->colsum_version = ds->version;
+        if (defer) {
+          // every reader of this gradient in a training step (ff1's dA / dB products, its bias gradient) is served by
+          // the shadow and the column sums; the fp32 values are produced only if something else asks for them
+          StoragePtr in_s = in.storage, dout_s = dout.storage;
+          const tcapint n = rows * cols;
+          ds->deferred_values = [ds, in_s, dout_s, n]() {
+            weedcu_view v;
+            memset(&v, 0, sizeof(v));
+            v.rank = 1;
+            v.shape[0] = n;
+            v.stride[0] = 1U;
+            ds->dev->Bind();
+            throw_on_error(weedcu_unary_grad_real(WEEDCU_GELU, (real1 *)ds->buffer->ptr, &v, static_cast<GpuRealStorage *>(in_s.get())->device_ptr_ro(), &v,
+                                                  static_cast<GpuRealStorage *>(dout_s.get())->device_ptr_ro(), &v, 0, ds->dev->stream),
+                           "gelu_grad (deferred)");
+          };
+        }
         return;
       }
       if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "gelu_grad");
@@ -637,9 +656,10 @@ bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, c
     ds->colsum_n = V;
   }
   const Dev dl = dev_of(logits, "cross_entropy_bwd_pack"), dlse = dev_of(lse, "cross_entropy_bwd_pack"), dg = dev_of(dloss, "cross_entropy_bwd_pack");
+  const bool defer = !accumulate && cfg.defer_grads && covers_storage(dlogits);
   real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
   const int rc = weedcu_cross_entropy_bwd_pack(dl.ptr, logits.offset, rows, V, sym_ptr(targets, "cross_entropy_bwd_pack") + targets.offset, dlse.ptr + lse.offset,
-                                               dg.ptr + dloss.offset, out, dlogits.offset, accumulate, (uint16_t *)hit->buf->ptr,
+                                               dg.ptr + dloss.offset, defer ? nullptr : out, dlogits.offset, accumulate, (uint16_t *)hit->buf->ptr,
                                                (real1 *)ds->colsum->ptr, ds->dev->stream);
   if (rc == WEEDCU_ENOSUP) {
     // nothing was launched; the caller's plain kernel must see the pending zero fill again if we dropped it
@@ -649,6 +669,21 @@ bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, c
   throw_on_error(rc, "cross_entropy_bwd_pack");
   hit->version = ds->version;
   ds->colsum_version = ds->version;
+  if (defer) {
+    // the LM head's backward reads dlogits only through the bf16 shadow and the column sums: 1.65 GB of fp32 per
+    // step at the GPT-2 shape are written only if something else reads this gradient
+    StoragePtr l_s = logits.storage, t_s = targets.storage, lse_s = lse.storage, g_s = dloss.storage;
+    const tcapint l_off = logits.offset, t_off = targets.offset, lse_off = lse.offset, g_off = dloss.offset, d_off = dlogits.offset;
+    ds->deferred_values = [ds, l_s, t_s, lse_s, g_s, l_off, t_off, lse_off, g_off, d_off, rows, V]() {
+      ds->dev->Bind();
+      throw_on_error(weedcu_cross_entropy_bwd(static_cast<GpuRealStorage *>(l_s.get())->device_ptr_ro(), l_off, rows, V, 1U, rows,
+                                              static_cast<GpuIntStorage *>(t_s.get())->device_ptr_ro() + t_off,
+                                              static_cast<GpuRealStorage *>(lse_s.get())->device_ptr_ro() + lse_off,
+                                              static_cast<GpuRealStorage *>(g_s.get())->device_ptr_ro() + g_off, (real1 *)ds->buffer->ptr, d_off, 0,
+                                              ds->dev->stream),
+                     "cross_entropy_loss backward (deferred)");
+    };
+  }
   return true;
 }
 
