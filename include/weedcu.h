@@ -124,7 +124,8 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
 
 /* Tensor::gelu forward on a dense tensor (tensor.cpp:841-851, as weedcu_unary_real(WEEDCU_GELU)) that also
  * writes y_bf16[i] = bf16(y[i]): the GEMM operand of the Linear that follows (ff2). n % 4 == 0,
- * 16-byte aligned x / y, 8-byte aligned y_bf16; otherwise WEEDCU_ENOSUP. */
+ * 16-byte aligned x / y, 8-byte aligned y_bf16; otherwise WEEDCU_ENOSUP. y may be NULL (bf16 copy only:
+ * 10 -> 6 B/elem; weedcu_unary_real(WEEDCU_GELU) gives the fp32 values when something needs them). */
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream);
 /* gelu_grad (tensor.cpp:841-851 backward; as weedcu_unary_grad_real(WEEDCU_GELU)) on a dense [rows, cols]
  * matrix with rows contiguous, fused with the preparation of the Linear backward that consumes din:

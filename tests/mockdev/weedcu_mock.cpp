@@ -143,6 +143,10 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
 }
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *) {
   if (n % 4u) return WEEDCU_ENOSUP;
+  if (!y) { // bf16 operand copy only
+    std::vector<float> tmp((size_t)n);
+    return RUN(wo_gelu_fwd_bf16(x, tmp.data(), y_bf16, n));
+  }
   return RUN(wo_gelu_fwd_bf16(x, y, y_bf16, n));
 }
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate, uint16_t *din_bf16, float *colsum, void *) {

@@ -522,8 +522,9 @@ def test_deferred_gradients_change_nothing(P):
         gx = P.read_storage(P.grad(x)).copy()
         gw = [P.read_storage(P.grad(P.param(l1, i))).copy() for i in range(P.param_count(l1))]
         gh = P.read_storage(P.grad(h)).copy()
+        yv = P.read_storage(y).copy()                # the GELU output itself is deferred too (ff2 only reads its bf16 copy)
         P.reset()
-        return lv, pg, dl1, dl2, gx, gw, gh
+        return lv, pg, dl1, dl2, gx, gw, gh, yv
 
     exact = "mock" in os.path.basename(P.path)
     try:
@@ -534,7 +535,7 @@ def test_deferred_gradients_change_nothing(P):
         set_mode(P, 1)
     assert np.array_equal(got[2], got[3]), "second read of the deferred gradient differs from the first"
     assert np.abs(ref[2]).max() > 0 and np.abs(ref[6]).max() > 0
-    flat = lambda r: [np.asarray([r[0]])] + r[1] + [r[2], r[4]] + r[5] + [r[6]]
+    flat = lambda r: [np.asarray([r[0]])] + r[1] + [r[2], r[4]] + r[5] + [r[6], r[7]]
     for i, (a, b) in enumerate(zip(flat(ref), flat(got))):
         if exact:
             assert np.array_equal(a, b), f"item {i} differs with deferred gradients"

@@ -235,7 +235,7 @@ gelu_fwd_bf16_kernel(const float *__restrict__ x, float *__restrict__ y, __nv_bf
     o.y = gelu_fwd(v.y);
     o.z = gelu_fwd(v.z);
     o.w = gelu_fwd(v.w);
-    reinterpret_cast<float4 *>(y)[i] = o;
+    if (y) reinterpret_cast<float4 *>(y)[i] = o; // NULL: bf16 operand copy only
     __nv_bfloat162 h[2];
     h[0] = __floats2bfloat162_rn(o.x, o.y);
     h[1] = __floats2bfloat162_rn(o.z, o.w);
@@ -553,10 +553,10 @@ int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32
 }
 
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream) {
-  if (!x || !y || !y_bf16 || !n) return WEEDCU_EINVAL;
-  if ((n % 4u) || !aligned16(x) || !aligned16(y) || (((uintptr_t)y_bf16) & 7u)) return WEEDCU_ENOSUP;
+  if (!x || !y_bf16 || !n) return WEEDCU_EINVAL;
+  if ((n % 4u) || !aligned16(x) || (y && !aligned16(y)) || (((uintptr_t)y_bf16) & 7u)) return WEEDCU_ENOSUP;
   cudaStream_t st = resolve_stream(stream);
-  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 10.0 * (double)n);
+  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (y ? 10.0 : 6.0) * (double)n);
   launch_k(gelu_fwd_bf16_kernel, dim3(grid_for(n / 4u, 256, 16)), dim3(256), 0, st, x, y, (__nv_bfloat16 *)y_bf16, n / 4u);
   return after_launch();
 }

@@ -400,9 +400,30 @@ void gelu(const Tensor &a, Tensor &out) {
     const OutputShadow os = begin_output_shadow(out, out.shape.back());
     if (os.ptr) {
       const Dev da = dev_of(a, "gelu"), dout = dev_out(out, "gelu", true);
-      const int rc = weedcu_gelu_fwd_bf16(da.ptr, dout.ptr, os.ptr, out.storage->size, dout.stream);
+      const bool defer = backend_config().defer_grads && covers_storage(out);
+      const int rc = weedcu_gelu_fwd_bf16(da.ptr, defer ? nullptr : dout.ptr, os.ptr, out.storage->size, dout.stream);
       if (rc == 0) {
         end_output_shadow(os);
+        if (defer) {
+          // in a transformer layer y = gelu(h) is read by ff2's forward product and by ff2's weight-gradient product,
+          // both through the bf16 shadow; the GELU backward needs h only. The fp32 y is computed if something else reads it
+          // (from h, which must not have been written in between: checked, not assumed).
+          GpuRealStorage *ys = gpu_storage(out, "gelu");
+          StoragePtr a_s = a.storage;
+          const uint64_t a_version = static_cast<GpuRealStorage *>(a_s.get())->version;
+          const tcapint n = out.storage->size;
+          ys->deferred_values = [ys, a_s, a_version, n]() {
+            GpuRealStorage *as = static_cast<GpuRealStorage *>(a_s.get());
+            if (as->version != a_version) throw std::runtime_error("gelu: the input was modified before the deferred fp32 output was read");
+            weedcu_view v;
+            memset(&v, 0, sizeof(v));
+            v.rank = 1;
+            v.shape[0] = n;
+            v.stride[0] = 1U;
+            ys->dev->Bind();
+            throw_on_error(weedcu_unary_real(WEEDCU_GELU, 0, as->device_ptr_ro(), &v, (real1 *)ys->buffer->ptr, &v, ys->dev->stream), "gelu (deferred)");
+          };
+        }
         return;
       }
       if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "gelu");
@@ -477,7 +498,10 @@ void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) {
           // the shadow and the column sums; the fp32 values are produced only if something else asks for them
           StoragePtr in_s = in.storage, dout_s = dout.storage;
           const tcapint n = rows * cols;
-          ds->deferred_values = [ds, in_s, dout_s, n]() {
+          const uint64_t in_v = static_cast<GpuRealStorage *>(in_s.get())->version, dout_v = static_cast<GpuRealStorage *>(dout_s.get())->version;
+          ds->deferred_values = [ds, in_s, dout_s, n, in_v, dout_v]() {
+            if (static_cast<GpuRealStorage *>(in_s.get())->version != in_v || static_cast<GpuRealStorage *>(dout_s.get())->version != dout_v)
+              throw std::runtime_error("gelu_grad: an input was modified before the deferred fp32 gradient was read");
             weedcu_view v;
             memset(&v, 0, sizeof(v));
             v.rank = 1;
@@ -674,7 +698,10 @@ bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, c
     // step at the GPT-2 shape are written only if something else reads this gradient
     StoragePtr l_s = logits.storage, t_s = targets.storage, lse_s = lse.storage, g_s = dloss.storage;
     const tcapint l_off = logits.offset, t_off = targets.offset, lse_off = lse.offset, g_off = dloss.offset, d_off = dlogits.offset;
-    ds->deferred_values = [ds, l_s, t_s, lse_s, g_s, l_off, t_off, lse_off, g_off, d_off, rows, V]() {
+    const uint64_t l_v = static_cast<GpuRealStorage *>(l_s.get())->version, g_v = static_cast<GpuRealStorage *>(g_s.get())->version;
+    ds->deferred_values = [ds, l_s, t_s, lse_s, g_s, l_off, t_off, lse_off, g_off, d_off, rows, V, l_v, g_v]() {
+      if (static_cast<GpuRealStorage *>(l_s.get())->version != l_v || static_cast<GpuRealStorage *>(g_s.get())->version != g_v)
+        throw std::runtime_error("cross_entropy_loss: logits or the loss gradient were modified before the deferred fp32 gradient was read");
       ds->dev->Bind();
       throw_on_error(weedcu_cross_entropy_bwd(static_cast<GpuRealStorage *>(l_s.get())->device_ptr_ro(), l_off, rows, V, 1U, rows,
                                               static_cast<GpuIntStorage *>(t_s.get())->device_ptr_ro() + t_off,
