@@ -452,7 +452,15 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
-    sys.exit(main_reference(args) if args.impl == "reference" else main_ours(args))
+    # stdout carries exactly ONE JSON line: native libraries that write to fd 1 (NCCL's version banner at
+    # communicator creation) are sent to stderr while the run lasts
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
+    rc = main_reference(args) if args.impl == "reference" else main_ours(args)
+    sys.stdout.flush()
+    sys.exit(rc)
 
 
 if __name__ == "__main__":
