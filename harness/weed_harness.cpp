@@ -114,6 +114,7 @@ int wh_config(const char *name, double value) {
     else if (n == "operand_cache") c.operand_cache = value != 0;
     else if (n == "lazy_zero") c.lazy_zero = value != 0;
     else if (n == "defer_grads") c.defer_grads = value != 0;
+    else if (n == "cow_grads") c.cow_grads = value != 0;
     else throw std::invalid_argument("unknown config key");
     return 0;
   })

@@ -260,6 +260,12 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
                          float *dgamma, float *dbeta, int grad_mode, int accumulate, void *stream);
+/* weedcu_layernorm_bwd with the old values of dx read from a second buffer: dx = dx_in + (LayerNorm input gradient);
+ * dx_in == dx accumulates in place, dx_in == NULL stores. Lets a gradient that shares another tensor's buffer
+ * copy-on-write be accumulated into without being copied first (12 + 4 B/elem either way). */
+int weedcu_layernorm_bwd_from(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma,
+                              const float *mean, const float *rstd, const float *dx_in, float *dx, float *dgamma,
+                              float *dbeta, int grad_mode, void *stream);
 
 /* ------------------------------------------------------------------ M1-M2 embedding, mask
  * Weed::embedding_gather / embedding_scatter_add (src/ops/embedding.cpp:56-110):

@@ -175,6 +175,11 @@ int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_
                          int grad_mode, int accumulate, void *) {
   return RUN(wo_layernorm_bwd(x, dy, rows, F, gamma, mean, rstd, dx, dgamma, dbeta, grad_mode, accumulate));
 }
+int weedcu_layernorm_bwd_from(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma, const float *mean, const float *rstd, const float *dx_in, float *dx,
+                              float *dgamma, float *dbeta, int grad_mode, void *) {
+  if (dx_in && dx_in != dx) memcpy(dx, dx_in, sizeof(float) * (size_t)rows * F); // then accumulate in place, as the oracle does
+  return RUN(wo_layernorm_bwd(x, dy, rows, F, gamma, mean, rstd, dx, dgamma, dbeta, grad_mode, dx_in ? 1 : 0));
+}
 int weedcu_embedding_gather(const int32_t *idx, uint64_t idx_off, uint32_t idx_stride, uint32_t n, const float *W, uint64_t w_off, uint32_t w_s0, uint32_t w_s1, uint32_t D, float *out,
                             uint64_t o_off, uint32_t o_s0, uint32_t o_s1, void *) {
   return RUN(wo_embedding_gather(idx, idx_off, idx_stride, n, W, w_off, w_s0, w_s1, D, out, o_off, o_s0, o_s1));

@@ -541,3 +541,70 @@ def test_deferred_gradients_change_nothing(P):
             assert np.array_equal(a, b), f"item {i} differs with deferred gradients"
         else:
             assert cases.rel_err(b, a) <= 1e-6, f"item {i}: {cases.rel_err(b, a):.2e}"
+
+
+def test_cow_gradients_change_nothing(P):
+    """BackendConfig::cow_grads: the first contribution to a multi-consumer parent's gradient that is a plain copy
+    of another gradient (the residual add) shares that buffer copy-on-write, and the LayerNorm backward that then
+    accumulates into it reads the shared buffer and writes a private one. Every gradient - including the
+    intermediates that share - and three Adam steps of a transformer must equal the copying run."""
+    d = 64
+
+    def small(cow):
+        set_mode(P, 1, precision=1)
+        P.config("cow_grads", cow)
+        rng = np.random.default_rng(5100)
+        x = P.tensor(rng.uniform(-1, 1, size=128 * d).astype(np.float32), [128, d], requires_grad=True)
+        lin, ln = P.module("linear", d, d, 1), P.module("layernorm", d)
+        P.init_params(lin, 2400)
+        h = P.forward(lin, x)
+        y = P.forward(ln, h)
+        z = P.op("add", [h, y])          # h feeds the LayerNorm and the add: its gradient starts as a share of dz
+        w = P.op("mul_scalar", [z], floats=[3.0])
+        m = P.op("mean", [w])
+        P.backward(m)
+        out = [P.read_storage(P.grad(t)).copy() for t in (z, y, h, x)]
+        out += [P.read_storage(P.grad(P.param(lin, i))).copy() for i in range(P.param_count(lin))]
+        out += [P.read_storage(P.grad(P.param(ln, i))).copy() for i in range(P.param_count(ln))]
+        out.append(P.read_storage(P.grad(z)).copy())  # still dz after h's gradient was accumulated into
+        P.reset()
+        return out
+
+    def train(cow):
+        set_mode(P, 1, precision=1)
+        P.config("cow_grads", cow)
+        B, T, V, L = 2, 64, 512, 2
+        rng = np.random.default_rng(5200)
+        tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        targets = rng.integers(0, V, size=(B, T)).astype(np.int32)
+        mods = [P.module("embedding", V, d), P.module("posenc", T, d)] + [P.module("encoder", d, 4, 4 * d) for _ in range(L)]
+        mods += [P.module("layernorm", d), P.module("linear", d, V, 1)]
+        model = P.module("sequential", *mods)
+        P.init_params(model, 2500)
+        opt = P.adam(model, 1e-3)
+        tok = P.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+        tgt = P.symbol(np.ascontiguousarray(targets.T).ravel(), [B, T])
+        losses = [float(P.read(P.train_step_tokens(model, opt, tok, tgt))[0]) for _ in range(3)]
+        params = [P.read_storage(P.param(model, i)).copy() for i in range(P.param_count(model))]
+        P.reset()
+        return np.array(losses), params
+
+    exact = "mock" in os.path.basename(P.path)
+    try:
+        s0, s1 = small(0), small(1)
+        (l0, p0), (l1, p1) = train(0), train(1)
+    finally:
+        P.config("cow_grads", 1)
+        set_mode(P, 1)
+    for i, (a, b) in enumerate(zip(s0, s1)):
+        assert np.abs(a).max() > 0
+        assert np.array_equal(a, b) if exact else cases.rel_err(b, a) <= 1e-6, f"gradient {i} differs with copy-on-write sharing"
+    assert np.array_equal(s1[0], s1[-1])
+    if exact:
+        assert np.array_equal(l0, l1)
+        for a, b in zip(p0, p1):
+            assert np.array_equal(a, b)
+    else:
+        assert np.max(np.abs(l0 - l1) / np.abs(l0)) <= 1e-6
+        for a, b in zip(p0, p1):
+            assert np.mean(np.abs(a - b)) <= 1e-6 and np.max(np.abs(a - b)) <= 4e-3

@@ -37,6 +37,7 @@ test_c4_default = G.test_config_c4_transformer_training_default_mode_runs_and_le
 test_gpt_shape_bf16_vs_fp32 = G.test_gpt_shape_train_step_bf16_vs_fp32
 test_operand_cache_and_lazy_zero = G.test_operand_cache_and_lazy_zero_change_nothing
 test_deferred_gradients = G.test_deferred_gradients_change_nothing
+test_cow_gradients = G.test_cow_gradients_change_nothing
 test_mha_kv_cache_decode = G.test_mha_kv_cache_decode_matches_reference
 test_mha_kv_cache_prefill = G.test_mha_kv_cache_prefill_then_decode_fused_equals_unfused
 test_greedy_decode = G.test_greedy_decode_matches_reference

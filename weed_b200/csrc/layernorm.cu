@@ -280,9 +280,10 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, uint32_t rows, uint32_t F,
                            const float *__restrict__ gamma, const float *__restrict__ mean,
                            const float *__restrict__ rstd, const float *__restrict__ k_x, const float *__restrict__ k_0,
-                           float *dx, float *__restrict__ part_g, float *__restrict__ part_b, int accumulate) {
+                           const float *dx_in, float *dx, float *__restrict__ part_g, float *__restrict__ part_b) {
   pdl_grid_sync();
   __shared__ float red[8][2 * kLnFB];
+  const bool accumulate = dx_in != nullptr; // dx = dx_in + ...; dx_in may be dx itself (in place) or another buffer
   const uint32_t r = (blockIdx.x * 256u + threadIdx.x) * VEC;
   const bool live = r < rows;
   float mu[VEC], rs[VEC], kx[VEC], k0[VEC];
@@ -318,11 +319,11 @@ layernorm_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict_
           if (VEC == 4) {
             *reinterpret_cast<float4 *>(xv[u]) = *reinterpret_cast<const float4 *>(x + off);
             *reinterpret_cast<float4 *>(dv[u]) = *reinterpret_cast<const float4 *>(dy + off);
-            if (accumulate) *reinterpret_cast<float4 *>(ov[u]) = *reinterpret_cast<const float4 *>(dx + off);
+            if (accumulate) *reinterpret_cast<float4 *>(ov[u]) = *reinterpret_cast<const float4 *>(dx_in + off);
           } else {
             xv[u][0] = x[off];
             dv[u][0] = dy[off];
-            if (accumulate) ov[u][0] = dx[off];
+            if (accumulate) ov[u][0] = dx_in[off];
           }
         }
       }
@@ -498,11 +499,18 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
 int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_t F,
                          const float *gamma, const float *mean, const float *rstd, float *dx,
                          float *dgamma, float *dbeta, int grad_mode, int accumulate, void *stream) {
+  return weedcu_layernorm_bwd_from(x, dy, rows, F, gamma, mean, rstd, accumulate ? dx : nullptr, dx, dgamma, dbeta, grad_mode, stream);
+}
+
+int weedcu_layernorm_bwd_from(const float *x, const float *dy, uint32_t rows, uint32_t F, const float *gamma, const float *mean,
+                              const float *rstd, const float *dx_in, float *dx, float *dgamma, float *dbeta, int grad_mode,
+                              void *stream) {
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !rows || !F) return WEEDCU_EINVAL;
+  const int accumulate = dx_in ? 1 : 0;
   const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
   if (fgroups > 65535u) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
-  const bool vec = (rows % 4u) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(rstd);
+  const bool vec = (rows % 4u) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && (!dx_in || aligned16(dx_in)) && aligned16(mean) && aligned16(rstd);
   const uint32_t rows_per_block = vec ? 1024u : 256u;
   const uint32_t nchunks = (rows + rows_per_block - 1) / rows_per_block;
   // scratch: k_x[rows], k_0[rows] (rounded up to keep 16-byte alignment), part_g / part_b [nchunks][F]
@@ -515,9 +523,9 @@ int weedcu_layernorm_bwd(const float *x, const float *dy, uint32_t rows, uint32_
   int rc = after_launch();
   if (rc == 0) {
     if (vec)
-      launch_k(layernorm_bwd_apply_kernel<4>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
+      launch_k(layernorm_bwd_apply_kernel<4>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx_in, dx, pg, pb);
     else
-      launch_k(layernorm_bwd_apply_kernel<1>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx, pg, pb, accumulate);
+      launch_k(layernorm_bwd_apply_kernel<1>, dim3(nchunks, fgroups), dim3(256), 0, st, x, dy, rows, F, gamma, mean, rstd, kx, k0, dx_in, dx, pg, pb);
     rc = after_launch();
   }
   if (rc == 0 && (dgamma || dbeta)) {

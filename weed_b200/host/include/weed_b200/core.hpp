@@ -95,6 +95,9 @@ struct BackendConfig {
   // gradients whose only readers are bf16 GEMM operands + column sums (dlogits of the fused cross-entropy,
   // the GELU input gradient) are not written in fp32 until something reads them (GpuStorage::deferred_values)
   bool defer_grads = true;
+  // a gradient whose first contribution is a plain copy of another complete gradient shares its buffer
+  // copy-on-write instead (GpuStorage::cow)
+  bool cow_grads = true;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)
@@ -130,6 +133,7 @@ struct GpuDevice {
   BufferPtr MakeBuffer(size_t bytes, const void *host_ptr = nullptr);
   // blocking device->host read (reference LockSync, gpu_device.cpp:388-420)
   bool LockSync(BufferPtr buffer, size_t bytes, void *dst, bool allow_lock = false);
+  void CopyBuffer(const BufferPtr &dst, const BufferPtr &src, size_t bytes); // stream-ordered device-to-device copy
   void UnlockSync(BufferPtr, void *) {}
   void ClearRealBuffer(BufferPtr buffer, size_t n);
   void FillOnesReal(BufferPtr buffer, size_t n);
@@ -232,7 +236,35 @@ typedef std::shared_ptr<CpuIntStorage> CpuIntStoragePtr;
 
 template <typename T> struct GpuStorage : TypedStorage<T> {
   GpuDevicePtr dev;
-  BufferPtr buffer;
+  mutable BufferPtr buffer;
+  // Copy-on-write sharing of the device buffer between storages (BackendConfig::cow_grads): the first
+  // contribution to a lazily zeroed gradient that is a plain copy of another complete gradient (d(a + b)/da = 1
+  // for a parent with several consumers) shares that gradient's buffer instead of copying 8 B/elem. Every
+  // access goes through device_ptr*(): reads see the shared buffer, the first write gives the writer a
+  // private buffer (copied, or fresh when the write overwrites everything), so neither storage can observe
+  // the other's later writes. Storages that share hold the same token; alone again == not shared.
+  mutable std::shared_ptr<char> cow;
+  bool buffer_shared() const { return cow && cow.use_count() > 1; }
+  void unshare(bool keep_contents) const {
+    if (!buffer_shared()) {
+      cow.reset();
+      return;
+    }
+    BufferPtr fresh = dev->MakeBuffer(sizeof(T) * (size_t)TypedStorage<T>::size);
+    if (keep_contents) dev->CopyBuffer(fresh, buffer, sizeof(T) * (size_t)TypedStorage<T>::size);
+    buffer = fresh;
+    cow.reset();
+  }
+  // this storage := src's current contents, without a copy. Both must be the same size on the same device.
+  void share_buffer_from(const GpuStorage<T> &src) {
+    src.materialize();
+    if (!src.cow) src.cow = std::make_shared<char>(0);
+    cow = src.cow;
+    buffer = src.buffer;
+    deferred_values = nullptr;
+    zero_pending = false;
+    ++version;
+  }
   GpuStorage(StorageType st, tcapint n, int64_t did, bool alloc = true) : TypedStorage<T>(st, DeviceTag::GPU, n) {
     dev = CUDAEngine::Instance().GetWeedDevice(did);
     dev->AddAlloc(sizeof(T) * (size_t)n);
@@ -262,16 +294,19 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
       std::function<void()> f;
       f.swap(deferred_values);
       zero_pending = false;
+      unshare(false);
       f();
       return;
     }
     if (!zero_pending) return;
     zero_pending = false;
+    unshare(false);
     const_cast<GpuStorage<T> *>(this)->fill_now(T(0));
   }
   virtual void fill_now(const T &v) = 0;
   T *device_ptr() const { // read/write access
     materialize();
+    unshare(true);
     ++version;
     return reinterpret_cast<T *>(buffer->ptr);
   }
@@ -282,6 +317,7 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
   T *device_ptr_overwrite() const { // the caller overwrites every element
     deferred_values = nullptr;
     zero_pending = false;
+    unshare(false);
     ++version;
     return reinterpret_cast<T *>(buffer->ptr);
   }
@@ -523,6 +559,10 @@ struct Tensor : public BaseTensor {
   // gradient destination: accumulate = 0 (and no zero-fill is issued) when the storage is lazily
   // zeroed and this view covers all of it, so the kernel may store instead of add
   real1 *device_ptr_accumulate(int &accumulate) const;
+  // as device_ptr_accumulate for kernels that can read the old values from one buffer and write the sums to another:
+  // a copy-on-write shared gradient is then accumulated into out of place (src = the shared buffer, kept alive by `keep`)
+  // instead of being copied first. src == nullptr: nothing to add to (plain store).
+  real1 *device_ptr_accumulate_from(const real1 *&src, BufferPtr &keep) const;
   void *stream() const;
 };
 

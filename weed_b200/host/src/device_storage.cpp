@@ -23,6 +23,7 @@ BackendConfig &backend_config() {
     if (const char *e = getenv("WEED_B200_OPERAND_CACHE")) c.operand_cache = atoi(e) != 0;
     if (const char *e = getenv("WEED_B200_LAZY_ZERO")) c.lazy_zero = atoi(e) != 0;
     if (const char *e = getenv("WEED_B200_DEFER_GRADS")) c.defer_grads = atoi(e) != 0;
+    if (const char *e = getenv("WEED_B200_COW_GRADS")) c.cow_grads = atoi(e) != 0;
     return c;
   }();
   return cfg;
@@ -151,6 +152,10 @@ void Storage::save(std::ostream &) const { throw std::domain_error("Storage::sav
 
 StoragePtr CpuRealStorage::gpu(const int64_t &did) { return std::make_shared<GpuRealStorage>(data, did); }
 StoragePtr CpuIntStorage::gpu(const int64_t &did) { return std::make_shared<GpuIntStorage>(data, did); }
+void GpuDevice::CopyBuffer(const BufferPtr &dst, const BufferPtr &src, size_t bytes) {
+  Bind();
+  throw_on_error(weedcu_memcpy_d2d(dst->ptr, src->ptr, bytes, stream), "GpuDevice::CopyBuffer");
+}
 void GpuRealStorage::FillValue(const real1 &v) {
   ++version;
   deferred_values = nullptr;
@@ -159,6 +164,7 @@ void GpuRealStorage::FillValue(const real1 &v) {
     return;
   }
   zero_pending = false;
+  unshare(false);
   dev->FillValueReal(buffer, size, v);
 }
 StoragePtr GpuRealStorage::cpu() {

@@ -156,12 +156,16 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
       };
       dg = param_grad(g);
       db = param_grad(b);
-      int accumulate = 1;
-      real1 *dx_ptr = dx->device_ptr_accumulate(accumulate);
-      throw_on_error(weedcu_layernorm_bwd(x->device_ptr_ro() + x->offset, y->grad->device_ptr_ro() + y->grad->offset, rows, F,
-                                          g->device_ptr_ro() + g->offset, mean->device_ptr_ro(), rstd->device_ptr_ro(), dx_ptr + dx->offset,
-                                          dg ? dg->device_ptr() + dg->offset : nullptr, db ? db->device_ptr() + db->offset : nullptr,
-                                          0 /* reference chain */, accumulate, x->stream()),
+      // dx = (what dx already holds) + this contribution; a dx that shares the residual gradient's buffer copy-on-write
+      // (the add node in front of this LayerNorm) is read from there and written to a private buffer: no copy
+      const real1 *dx_src = nullptr;
+      BufferPtr keep;
+      real1 *dx_ptr = dx->device_ptr_accumulate_from(dx_src, keep);
+      throw_on_error(weedcu_layernorm_bwd_from(x->device_ptr_ro() + x->offset, y->grad->device_ptr_ro() + y->grad->offset, rows, F,
+                                               g->device_ptr_ro() + g->offset, mean->device_ptr_ro(), rstd->device_ptr_ro(),
+                                               dx_src ? dx_src + dx->offset : nullptr, dx_ptr + dx->offset,
+                                               dg ? dg->device_ptr() + dg->offset : nullptr, db ? db->device_ptr() + db->offset : nullptr,
+                                               0 /* reference chain */, x->stream()),
                      "LayerNorm backward");
       if (x->requires_grad) x->grad = dx;
       if (dg) g->grad = dg;

@@ -200,7 +200,14 @@ void in_place(int op, Tensor &a, const Tensor &b, const char *name) {
   const Dev db = dev_of(b, name);
   GpuRealStorage *as = gpu_storage(a, name);
   if (op == WEEDCU_ADD && times == 1 && as->zero_pending && covers_storage(a)) {
-    // first accumulation into a lazily zeroed gradient: 0 + b is a plain copy (8 B/elem, no fill)
+    // first accumulation into a lazily zeroed gradient: 0 + b is a plain copy (8 B/elem, no fill) — or no copy at all
+    // when b is a whole dense storage of the same layout: a then shares b's buffer copy-on-write
+    if (backend_config().cow_grads && backend_config().fused && b.storage.get() != a.storage.get() && a.shape == b.shape && a.stride == b.stride &&
+        covers_storage(b) && a.storage->size == b.storage->size && b.storage->device == DeviceTag::GPU &&
+        a.storage->get_device_id() == b.storage->get_device_id()) {
+      as->share_buffer_from(*gpu_storage(b, name));
+      return;
+    }
     const Dev da = dev_out(a, name, true);
     throw_on_error(weedcu_copy_real(da.ptr, &av, db.ptr, &bv, da.stream), name);
     return;

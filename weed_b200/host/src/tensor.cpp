@@ -96,6 +96,19 @@ real1 *Tensor::device_ptr_accumulate(int &accumulate) const {
   accumulate = 1;
   return s->device_ptr();
 }
+real1 *Tensor::device_ptr_accumulate_from(const real1 *&src, BufferPtr &keep) const {
+  if (!storage || storage->device != DeviceTag::GPU) throw std::domain_error("Tensor is not GPU-resident");
+  GpuRealStorage *s = static_cast<GpuRealStorage *>(storage.get());
+  if (!s->zero_pending && !s->deferred_values && s->buffer_shared() && covers_storage()) {
+    keep = s->buffer; // the other sharers' buffer: read from it, write the sums into a fresh private one
+    src = reinterpret_cast<const real1 *>(keep->ptr);
+    return s->device_ptr_overwrite();
+  }
+  int accumulate = 1;
+  real1 *p = device_ptr_accumulate(accumulate);
+  src = accumulate ? p : nullptr;
+  return p;
+}
 bool BaseTensor::covers_storage() const {
   if (offset || !storage) return false;
   tcapint expect = 1U;
