@@ -59,12 +59,14 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // Optional per-class event timing (weedcu_prof_*). A scope brackets the launches issued while it
 // is alive; when profiling is off it costs one predictable branch.
 bool prof_on();
+void note_kernel_class(int cls); // the class of the launches that follow (WEEDCU_PDL_CLASSES bisects by it)
 int prof_begin(int cls, cudaStream_t st, double work);
 void prof_end(int idx, cudaStream_t st);
 struct ProfScope {
   int idx;
   cudaStream_t st;
   ProfScope(int cls, cudaStream_t s, double work) : idx(-1), st(s) {
+    note_kernel_class(cls);
     if (prof_on()) idx = prof_begin(cls, s, work);
   }
   ~ProfScope() {

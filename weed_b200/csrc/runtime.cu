@@ -235,9 +235,27 @@ bool pdl_enabled() {
 }
 
 static bool g_prev_is_kernel = false;
+static int g_kernel_class = 0;
 void note_stream_op() { g_prev_is_kernel = false; }
+void note_kernel_class(int cls) { g_kernel_class = cls; }
 bool pdl_take_edge() {
-  const bool take = g_prev_is_kernel && pdl_enabled();
+  // WEEDCU_PDL_CLASSES: bit c set = launches of profiling class c (weedcu.h WEEDCU_PROF_*) may take the edge
+  static long mask = -2;
+  if (mask == -2) {
+    const char *e = getenv("WEEDCU_PDL_CLASSES");
+    mask = e ? strtol(e, nullptr, 0) : -1;
+  }
+  // WEEDCU_PDL_EDGE="p,c": only launches of class c that directly follow a launch of class p take the edge (bisecting)
+  static int edge_p = -2, edge_c = -2;
+  static int prev_class = 0;
+  if (edge_p == -2) {
+    const char *e = getenv("WEEDCU_PDL_EDGE");
+    edge_p = edge_c = -1;
+    if (e) sscanf(e, "%d,%d", &edge_p, &edge_c);
+  }
+  bool take = g_prev_is_kernel && pdl_enabled() && ((mask >> (g_kernel_class & 31)) & 1L);
+  if (edge_p >= 0 && !(prev_class == edge_p && g_kernel_class == edge_c)) take = false;
+  prev_class = g_kernel_class;
   g_prev_is_kernel = true;
   return take;
 }
