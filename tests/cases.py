@@ -473,6 +473,25 @@ for _rows, _cols, _acc in [(1032, 50, 0), (2048, 24, 1)]:
         return {"din": d, "shadow_is_rne_of_din": _rne_ok(d, hs.get()), "colsum": hc.get()}
 
 
+for _rows, _F in [(8200, 768), (4096, 520), (1028, 1024), (2052, 96)]:
+    @case(f"layernorm_{_rows}x{_F}_large_ragged", tol=3e-5)
+    def _c(be, rng, rows=_rows, F=_F):  # large inputs with a ragged last row tile / feature group
+        return _ln(be, rng, rows, F, 1)
+
+
+@case("layernorm_fwd_bf16_8200x768", tol=3e-5)
+def _c(be, rng):
+    rows, F = 8200, 768
+    x = uni(rng, rows * F, -2, 2)
+    gamma, beta = uni(rng, F, 0.5, 1.5), uni(rng, F)
+    hx, hg, hb = be.buf(x), be.buf(gamma), be.buf(beta)
+    hy, hm, hr = be.buf(np.zeros_like(x)), be.buf(np.zeros(rows, F32)), be.buf(np.zeros(rows, F32))
+    hs = be.buf(np.zeros(rows * F, np.uint16))
+    be.call("layernorm_fwd_bf16", hx, U32(rows), U32(F), hg, hb, F32(np.finfo(np.float32).eps / 4), hy, hm, hr, hs)
+    y = hy.get()
+    return {"y": y, "mean": hm.get(), "rstd": hr.get(), "shadow_is_rne_of_y": _rne_ok(y, hs.get())}
+
+
 @case("layernorm_20000x40_multi_tile", tol=3e-5)
 def _c(be, rng):  # more row tiles than blocks: the per-block column sums span several tiles
     return _ln(be, rng, 20000, 40, 1)

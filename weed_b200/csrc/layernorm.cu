@@ -456,7 +456,10 @@ int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const f
   // for the two streaming passes, and a TMA-staged one-pass kernel — 32-row x F slab in shared memory,
   // two blocks per SM, in-place normalise, TMA store — at 20.5 us against 21.0 us (36.9 against 25.9 us
   // at F = 1024, one block per SM): every block sits in the same load / compute / store phase at the same
-  // time, so the phases do not overlap; large inputs keep the two passes)
+  // time, so the phases do not overlap. Cluster variants that split the features of a row tile over 4 or 8
+  // CTAs with the partial sums exchanged through distributed shared memory (values in registers, x read
+  // once, 3-4 CTAs per SM) measured 28.9 us (32-row tiles, cluster of 4) and 32.4 us (128-row tiles with
+  // 128-bit loads, cluster of 8). Large inputs keep the two passes)
   if (rows <= 256u && F <= (uint32_t)kLnBY * 64u) { // decode-sized inputs: one launch
     ProfScope prof(WEEDCU_PROF_LAYERNORM, st, 8.0 * (double)rows * F);
     const unsigned tiles = (rows + 31u) / 32u;
