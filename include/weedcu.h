@@ -337,6 +337,12 @@ int weedcu_matmul_real(const float *a, const weedcu_mat *am, const float *b, con
 int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c,
                          const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *bias,
                          int accumulate, void *stream);
+/* `groups` (1..3) skinny products A * B_g (+ bias_g) -> C_g that share A, M, K, N and the strides of bm / cm (whose
+ * offsets are added to every b[g] / c[g]) as ONE launch: the W_q / W_k / W_v projections of a decode step
+ * (multihead_attention.cpp:151-153). Same arithmetic as `groups` weedcu_matmul_skinny calls; C is stored. */
+int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b,
+                                 const weedcu_mat *bm, float *const *c, const weedcu_mat *cm, uint32_t M, uint32_t K,
+                                 uint32_t N, const float *const *bias, void *stream);
 /* bf16 tensor-core GEMM on operands already held in bf16 (raw uint16 bit patterns).
  * a_major / b_major: 0 = K contiguous, 1 = M (resp. N) contiguous; lda/ldb are the strides
  * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc.

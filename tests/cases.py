@@ -539,6 +539,17 @@ def _c(be, rng):
     return {"idx": ho.get()}
 
 
+@case("argmax_rows_decode_shape_ties_across_slices", tol=0.0)
+def _c(be, rng):  # 8 rows x GPT-2 vocabulary: the scan is split over vocabulary slices; ties in different slices
+    rows, V = 8, 50257
+    x = uni(rng, rows * V)
+    x[2 + 40000 * rows] = x[2 + 123 * rows] = x[2 + 50256 * rows] = 7.0
+    x[5 + 50256 * rows] = 9.0
+    hx, ho = be.buf(x), be.buf(np.zeros(rows, np.int32))
+    be.call("argmax_rows", hx, U64(0), U32(rows), U32(V), U32(1), U32(rows), ho)
+    return {"idx": ho.get()}
+
+
 # --------------------------------------------------------------------------------------- optimisers
 @case("sgd_step")
 def _c(be, rng):

@@ -129,6 +129,15 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
   if (M > 16u) return WEEDCU_ENOSUP;
   return RUN(wo_matmul_skinny(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, bias, accumulate));
 }
+int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b, const weedcu_mat *bm, float *const *c, const weedcu_mat *cm, uint32_t M,
+                                 uint32_t K, uint32_t N, const float *const *bias, void *stream) {
+  if (!groups || groups > 3u || !b || !c) return WEEDCU_EINVAL;
+  for (uint32_t g = 0; g < groups; ++g) {
+    const int rc = weedcu_matmul_skinny(a, am, b[g], bm, c[g], cm, M, K, N, bias ? bias[g] : nullptr, 0, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
 int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, float *lse, float *loss, void *) {
   return RUN(wo_cross_entropy_fwd(logits, offset, rows, V, rs, vs, targets, lse, loss));
 }

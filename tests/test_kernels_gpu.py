@@ -243,3 +243,27 @@ def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups, mode):
     gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
     for g in range(groups):
         assert np.array_equal(sep[g].get(), grp[g].get()), f"group {g}"
+
+
+@pytest.mark.parametrize("M,K,N,groups", [(8, 768, 768, 3), (8, 768, 96, 2), (3, 70, 37, 3), (16, 130, 33, 1)])
+def test_matmul_skinny_grouped_equals_separate_launches(gpu, M, K, N, groups):
+    """weedcu_matmul_skinny_grouped (the W_q / W_k / W_v projections of a decode step as one launch, blockIdx.y = product)
+    is bit-identical to `groups` weedcu_matmul_skinny calls."""
+    import ctypes as C
+    rng = np.random.default_rng(M + K + N + groups)
+    U32 = C.c_uint32
+    a = rng.uniform(-1, 1, M * K + 4).astype(np.float32)
+    ha = gpu.buf(a)
+    am, bm, cm = cases._mat(4, 1, M, 0), cases._mat(8, 1, K, 0), cases._mat(0, 1, M, 0)
+    hbs, hbias, sep, grp = [], [], [], []
+    for g in range(groups):
+        hbs.append(gpu.buf(rng.uniform(-1, 1, K * N + 8).astype(np.float32)))
+        hbias.append(gpu.buf(rng.uniform(-2, 2, N).astype(np.float32)))
+        sep.append(gpu.buf(np.zeros(M * N, np.float32)))
+        grp.append(gpu.buf(np.full(M * N, 5.0, np.float32)))
+        gpu.call("matmul_skinny", ha, am, hbs[g], bm, sep[g], cm, U32(M), U32(K), U32(N), hbias[g], C.c_int(0))
+    PtrArr = C.c_void_p * groups
+    gpu.call("matmul_skinny_grouped", ha, am, U32(groups), PtrArr(*[b.ptr for b in hbs]), bm, PtrArr(*[c.ptr for c in grp]), cm,
+             U32(M), U32(K), U32(N), PtrArr(*[b.ptr for b in hbias]))
+    for g in range(groups):
+        assert np.array_equal(sep[g].get(), grp[g].get()), f"group {g}"

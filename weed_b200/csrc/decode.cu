@@ -128,9 +128,13 @@ attn_decode_combine_kernel(const float *__restrict__ part, float *__restrict__ o
   const uint32_t bh = (uint32_t)(i % BH);
   const uint64_t r = i / BH;
   const uint32_t j = (uint32_t)(r % hd), t = (uint32_t)(r / hd);
+  // (both loops unrolled by 8: a decode step has 16-32 chunks and the loads of one unrolled group are independent —
+  // rolled, every chunk cost a dependent L2 round trip and this tiny merge took 13.6 us)
   float M = -INFINITY;
+#pragma unroll 8
   for (uint32_t c = 0; c < n_chunks; ++c) M = fmaxf(M, part[((uint64_t)(c * T_new + t) * (hd + 2u) + hd) * BH + bh]);
   float num = 0.0f, den = 0.0f;
+#pragma unroll 8
   for (uint32_t c = 0; c < n_chunks; ++c) {
     const float *p = part + ((uint64_t)(c * T_new + t) * (hd + 2u)) * BH + bh;
     const float mc = p[(uint64_t)hd * BH];
@@ -163,12 +167,20 @@ static int launch_decode_partial(const float *q, const float *kc, const float *v
 // The MM x 8 partial dots of a lane meet in a halving butterfly (2*MM*8 - 2 shuffles instead of
 // 5 per value), then the 8 warps meet in shared memory. Arbitrary operand strides.
 constexpr int kSkCW = 8;
+struct SkinnyGroups {
+  const float *b[3];
+  float *c[3];
+  const float *bias[3];
+};
 template <int MM, bool AVEC>
 __global__ void __launch_bounds__(256)
-skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, const float *__restrict__ b, uint32_t b_s0,
-                     uint32_t b_s1, float *c, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N,
-                     const float *__restrict__ bias, int accumulate) {
+skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, SkinnyGroups grp, uint32_t b_s0,
+                     uint32_t b_s1, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, int accumulate) {
   pdl_grid_sync();
+  // blockIdx.y = product of a grouped launch (the W_q / W_k / W_v projections of one decode step share A)
+  const float *__restrict__ b = grp.b[blockIdx.y];
+  float *c = grp.c[blockIdx.y];
+  const float *__restrict__ bias = grp.bias[blockIdx.y];
   constexpr int NV = MM * kSkCW; // partial sums per lane
   __shared__ float red[8][NV];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -176,7 +188,8 @@ skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, 
   float acc[NV]; // acc[m * kSkCW + j]
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-  constexpr int U = (MM <= 8) ? 2 : 1; // k-steps whose loads are issued together (latency, not bandwidth, is the enemy here)
+  constexpr int U = (MM <= 8) ? 4 : 2; // k-steps whose loads are issued together (latency, not bandwidth, is the enemy here:
+                                       // K = 768 is one round of 3 live steps, K = 3072 three rounds instead of six)
   for (uint32_t k0 = w * 32u + lane; k0 < K; k0 += 256u * U) {
     float bv[U][kSkCW], av[U][MM];
 #pragma unroll
@@ -234,13 +247,12 @@ skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, 
   }
 }
 
-int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0, uint32_t b_s1, float *c,
-                         uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate,
-                         cudaStream_t st) {
+static int launch_skinny_groups(const float *a, uint32_t a_s0, uint32_t a_s1, const SkinnyGroups &grp, uint32_t groups, uint32_t b_s0, uint32_t b_s1,
+                                uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, int accumulate, cudaStream_t st) {
   if (M > 16u) return WEEDCU_ENOSUP;
-  const unsigned grid = (N + kSkCW - 1) / kSkCW;
-  ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K);
-#define WCU_SK(MM, AV) launch_k(skinny_matmul_kernel<MM, AV>, dim3(grid), dim3(256), 0, st, a, a_s0, a_s1, b, b_s0, b_s1, c, c_s0, c_s1, M, K, N, bias, accumulate)
+  const dim3 grid((N + kSkCW - 1) / kSkCW, groups);
+  ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K * groups);
+#define WCU_SK(MM, AV) launch_k(skinny_matmul_kernel<MM, AV>, grid, dim3(256), 0, st, a, a_s0, a_s1, grp, b_s0, b_s1, c_s0, c_s1, M, K, N, accumulate)
   const bool avec_ok = a_s0 == 1u && (a_s1 % 4u) == 0 && aligned16(a);
   if (M <= 4u) {
     if (avec_ok && M == 4u) WCU_SK(4, true);
@@ -254,6 +266,12 @@ int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const flo
   }
 #undef WCU_SK
   return after_launch();
+}
+int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0, uint32_t b_s1, float *c,
+                         uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate,
+                         cudaStream_t st) {
+  SkinnyGroups grp = {{b, b, b}, {c, c, c}, {bias, bias, bias}};
+  return launch_skinny_groups(a, a_s0, a_s1, grp, 1, b_s0, b_s1, c_s0, c_s1, M, K, N, accumulate, st);
 }
 
 } // namespace weedcu
@@ -315,6 +333,21 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
   if (!a || !am || !b || !bm || !c || !cm || !M || !K || !N) return WEEDCU_EINVAL;
   return launch_skinny_matmul(a + am->offset, am->s0, am->s1, b + bm->offset, bm->s0, bm->s1, c + cm->offset, cm->s0, cm->s1, M,
                               K, N, bias, accumulate, resolve_stream(stream));
+}
+
+int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b, const weedcu_mat *bm,
+                                 float *const *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *const *bias,
+                                 void *stream) {
+  if (!a || !am || !b || !bm || !c || !cm || !M || !K || !N || !groups || groups > 3u) return WEEDCU_EINVAL;
+  SkinnyGroups grp;
+  for (uint32_t g = 0; g < 3u; ++g) {
+    const uint32_t s = g < groups ? g : 0u;
+    if (!b[s] || !c[s]) return WEEDCU_EINVAL;
+    grp.b[g] = b[s] + bm->offset;
+    grp.c[g] = c[s] + cm->offset;
+    grp.bias[g] = bias ? bias[s] : nullptr;
+  }
+  return launch_skinny_groups(a + am->offset, am->s0, am->s1, grp, groups, bm->s0, bm->s1, cm->s0, cm->s1, M, K, N, 0, resolve_stream(stream));
 }
 
 } // extern "C"

@@ -221,19 +221,23 @@ sum_pass2_kernel(const float *__restrict__ partial, uint32_t n, float scale, flo
 // ------------------------------------------------------------------------ argmax over rows
 // logits[rows, V] with row stride rs (normally 1) and vocab stride vs: 32 rows x BY slices per
 // block, lowest index wins ties (matches a serial first-max scan).
+// The vocabulary is split over gridDim.y slices so that a decode step's 8 x 50257 scan fills the chip
+// (one block took 347 us, a fifth of the step); a slice leaves (value, index) per row, the merge kernel
+// keeps the serial-scan winner: larger value, lowest index on ties, slices in ascending order.
 template <int BY>
 __global__ void __launch_bounds__(32 * BY)
-argmax_rows_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
-                   int32_t *__restrict__ out) {
+argmax_rows_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, uint32_t v_per_slice,
+                   float *__restrict__ part_v, uint32_t *__restrict__ part_i) {
   pdl_grid_sync();
   __shared__ float mv[BY][33];
   __shared__ uint32_t mi[BY][33];
   const uint32_t r = blockIdx.x * 32 + threadIdx.x;
+  const uint32_t v_begin = blockIdx.y * v_per_slice, v_end = min(V, v_begin + v_per_slice);
   float best = -INFINITY;
   uint32_t bi = 0xffffffffu;
   if (r < rows) {
     const float *p = x + (uint64_t)r * rs;
-    for (uint32_t v = threadIdx.y; v < V; v += BY) {
+    for (uint32_t v = v_begin + threadIdx.y; v < v_end; v += BY) {
       const float y = p[(uint64_t)v * vs];
       if (y > best || bi == 0xffffffffu) {
         best = y;
@@ -248,13 +252,32 @@ argmax_rows_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint3
     for (int y = 1; y < BY; ++y) {
       const float c = mv[y][threadIdx.x];
       const uint32_t ci = mi[y][threadIdx.x];
-      if (ci != 0xffffffffu && (c > best || (c == best && ci < bi))) {
+      if (ci != 0xffffffffu && (bi == 0xffffffffu || c > best || (c == best && ci < bi))) {
         best = c;
         bi = ci;
       }
     }
-    out[r] = (int32_t)bi;
+    part_v[(uint64_t)blockIdx.y * rows + r] = best;
+    part_i[(uint64_t)blockIdx.y * rows + r] = bi;
   }
+}
+__global__ void __launch_bounds__(256)
+argmax_merge_kernel(const float *__restrict__ part_v, const uint32_t *__restrict__ part_i, uint32_t rows, uint32_t slices,
+                    int32_t *__restrict__ out) {
+  pdl_grid_sync();
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float best = part_v[r];
+  uint32_t bi = part_i[r];
+  for (uint32_t s = 1; s < slices; ++s) {
+    const float c = part_v[(uint64_t)s * rows + r];
+    const uint32_t ci = part_i[(uint64_t)s * rows + r];
+    if (ci != 0xffffffffu && (bi == 0xffffffffu || c > best || (c == best && ci < bi))) {
+      best = c;
+      bi = ci;
+    }
+  }
+  out[r] = (int32_t)bi;
 }
 
 static bool canonical_contiguous(const weedcu_view *v, int axis, uint64_t &inner, uint64_t &outer) {
@@ -410,9 +433,25 @@ int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *o
 int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs,
                        uint32_t vs, int32_t *out, void *stream) {
   if (!x || !out || !rows || !V) return WEEDCU_EINVAL;
-  launch_k(argmax_rows_kernel<16>, dim3((rows + 31) / 32), dim3(32, 16), 0, resolve_stream(stream), 
-      x + offset, rows, V, rs, vs, out);
-  return after_launch();
+  cudaStream_t st = resolve_stream(stream);
+  const uint32_t row_tiles = (rows + 31) / 32;
+  uint32_t slices = (2u * (uint32_t)kNumSMs + row_tiles - 1) / row_tiles; // ~2 blocks per SM in total
+  const uint32_t max_slices = (V + 255u) / 256u;                          // at least 16 values per thread of a slice
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1u) slices = 1u;
+  const uint32_t v_per_slice = (V + slices - 1) / slices;
+  slices = (V + v_per_slice - 1) / v_per_slice;
+  float *ws = nullptr;
+  WCU_CHECK(pool_alloc((void **)&ws, 8ull * slices * rows, st));
+  uint32_t *wi = reinterpret_cast<uint32_t *>(ws + (size_t)slices * rows);
+  launch_k(argmax_rows_kernel<16>, dim3(row_tiles, slices), dim3(32, 16), 0, st, x + offset, rows, V, rs, vs, v_per_slice, ws, wi);
+  int rc = after_launch();
+  if (rc == 0) {
+    launch_k(argmax_merge_kernel, dim3((rows + 255u) / 256u), dim3(256), 0, st, (const float *)ws, (const uint32_t *)wi, rows, slices, out);
+    rc = after_launch();
+  }
+  pool_free(ws, st);
+  return rc;
 }
 
 } // extern "C"

@@ -70,6 +70,8 @@ SymbolTensorPtr argmax_last_token(const Tensor &logits);
 // (the W_q / W_k / W_v projections); false (nothing computed) when the bf16 operand path does not apply.
 bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
                          const std::vector<Tensor *> &outs);
+bool matmul_skinny_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
+                           const std::vector<Tensor *> &outs);
 // Producer-side bf16 operand shadows. A kernel that is about to overwrite the dense tensor `out` may
 // also emit bf16(out) at the same linear index; when the Linear that consumes `out` next views it as
 // [rows, cols] (rows contiguous, rows % 8 == 0) that copy IS its tensor-core GEMM operand and the pack

@@ -626,6 +626,36 @@ bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws,
   throw_on_error(rc, "matmul_bias_grouped");
   return true;
 }
+// The same for a handful of rows (a decode step): one skinny launch for the group, fp32 in either precision mode.
+bool matmul_skinny_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
+                           const std::vector<Tensor *> &outs) {
+  const BackendConfig &cfg = backend_config();
+  const size_t G = ws.size();
+  if (!cfg.fused || G < 2U || G > 3U || biases.size() != G || outs.size() != G || a.shape.size() != 2U) return false;
+  const tcapint M = a.shape[0U], K = a.shape[1U], N = ws[0]->shape[1U];
+  if (M > 16U) return false;
+  for (size_t g = 0U; g < G; ++g) {
+    const Tensor &w = *ws[g], &o = *outs[g], &bi = *biases[g];
+    if (w.shape.size() != 2U || w.shape[0U] != K || w.shape[1U] != N || w.stride != ws[0]->stride || w.offset != ws[0]->offset) return false;
+    if (o.shape.size() != 2U || o.shape[0U] != M || o.shape[1U] != N || o.stride != outs[0]->stride || o.offset != outs[0]->offset) return false;
+    if (bi.storage->size != N || bi.storage->device != DeviceTag::GPU) return false;
+  }
+  validate_all_same_device({&a, ws[0], outs[0]}, "matmul_skinny_grouped");
+  const Dev da = dev_of(a, "matmul_skinny_grouped");
+  const weedcu_mat am = mat_of(a), bm = mat_of(*ws[0]), cm = mat_of(*outs[0]);
+  const real1 *bptr[3], *biasptr[3];
+  real1 *cptr[3];
+  void *stream = nullptr;
+  for (size_t g = 0U; g < G; ++g) {
+    bptr[g] = dev_of(*ws[g], "matmul_skinny_grouped").ptr;
+    const Dev dc = dev_out(*outs[g], "matmul_skinny_grouped", true);
+    stream = dc.stream;
+    cptr[g] = dc.ptr;
+    biasptr[g] = dev_of(*biases[g], "matmul_skinny_grouped").ptr + biases[g]->offset;
+  }
+  throw_on_error(weedcu_matmul_skinny_grouped(da.ptr, &am, (uint32_t)G, bptr, &bm, cptr, &cm, M, K, N, biasptr, stream), "matmul_skinny_grouped");
+  return true;
+}
 bool pack_with_column_sums(const Tensor &dy, Tensor &sums) {
   const BackendConfig &cfg = backend_config();
   if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || dy.shape.size() != 2U) return false;

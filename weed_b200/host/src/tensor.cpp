@@ -1037,8 +1037,12 @@ TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, Tensor
 std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases) {
   const BackendConfig &cfg = backend_config();
   const size_t G = ws.size();
-  if (!cfg.fused || cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache || G < 2U || G > 3U || biases.size() != G) return {};
+  if (!cfg.fused || G < 2U || G > 3U || biases.size() != G) return {};
   if (a->shape.size() < 2U || a->storage->device != DeviceTag::GPU) return {};
+  // a handful of rows (a decode step): one grouped skinny launch at fp32 in either precision mode; otherwise the grouped
+  // tensor-core launch, which needs the bf16 operand shadows
+  const bool skinny = a->get_broadcast_size() / a->shape.back() <= 16U;
+  if (!skinny && (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache)) return {};
   for (size_t g = 0U; g < G; ++g) {
     const TensorPtr &w = ws[g], &bias = biases[g];
     if (!w || !bias || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back() || w->shape != ws[0]->shape) return {};
@@ -1046,7 +1050,6 @@ std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<Ten
         bias->storage->device != DeviceTag::GPU)
       return {};
   }
-  if (a->get_broadcast_size() / a->shape.back() <= 16U) return {}; // decode steps take the skinny kernel per layer
   const bool needs_flatten = (a->shape.size() > 2U);
   const symint K = (symint)a->shape.back(), M = (symint)a->shape[a->shape.size() - 2], N = (symint)ws[0]->shape[1U];
   symint batch = 1;
@@ -1065,7 +1068,7 @@ std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<Ten
     bp[g] = biases[g].get();
     op[g] = outs[g].get();
   }
-  if (!Weed::matmul_bias_grouped(*a2, wp, bp, op)) return {};
+  if (!(skinny ? Weed::matmul_skinny_grouped(*a2, wp, bp, op) : Weed::matmul_bias_grouped(*a2, wp, bp, op))) return {};
   for (size_t g = 0U; g < G; ++g) outs[g] = finish_linear(a, ws[g], biases[g], outs[g], rgs[g]);
   return outs;
 }
