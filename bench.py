@@ -406,6 +406,14 @@ def main_ours(args):
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                             "share_of_step": b["ms_per_step"] / ms_per_step, "launches_per_step": b["launches_per_step"]}
             roofline["instrumented_ms_per_step"] = tot
+            # DRAM bytes per launch of this kernel class from the committed ncu capture of the same command
+            # (tools/ncu_summary.py traffic -> profiles/kernel_traffic.json); null when no capture covers the class
+            tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+            if os.path.exists(tpath):
+                tr = json.load(open(tpath)).get(top)
+                if tr:
+                    roofline["traffic"] = tr["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = tr["source"]
             # The instrumented pass brackets every launch with two event records; the classes then sum to more than the
             # un-instrumented step although the same kernels run back to back. That excess, spread evenly over the launches,
             # is taken off each class for the *_net figures (frac / achieved stay the raw, conservative ones).

@@ -9,6 +9,7 @@ serialised): per-kernel launch count, total time and SHARE of the listed time.
 `full`: selected raw metrics of every launch in an `ncu --set full` report (read with
 `ncu -i ... --page raw --csv`, which needs no GPU)."""
 import csv
+import os
 import io
 import re
 import subprocess
@@ -55,6 +56,25 @@ WANT = [
 ]
 
 
+def traffic(path, out_path):
+    """Per-launch DRAM bytes (read + write) of the GEMM kernels from an ncu CSV log with dram__bytes_read.sum and
+    dram__bytes_write.sum (--metrics ..., -k regex:gemm_bf16, one step) -> profiles/kernel_traffic.json for bench.py."""
+    import json
+    rows = [l for l in open(path) if l.startswith('"')]
+    rd = csv.DictReader(io.StringIO("".join(rows)))
+    per_id, unit_scale = defaultdict(float), {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rd:
+        if r["Metric Name"] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            continue
+        per_id[r["ID"]] += float(r["Metric Value"].replace(",", "")) * unit_scale.get(r["Metric Unit"], 1.0)
+    n = len(per_id)
+    avg = sum(per_id.values()) / max(1, n)
+    data = {"gemm_bf16_tcgen05": {"dram_bytes_per_launch": avg, "launches": n,
+                                  "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over {n} gemm_bf16 launches of one bench step ({os.path.basename(path)})"}}
+    json.dump(data, open(out_path, "w"), indent=1)
+    print(json.dumps(data))
+
+
 def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -77,5 +97,8 @@ def full(path):
         print(f"  -> dram traffic {(rd + wr) / 1e6:.2f} MB in {t_s * 1e6:.1f} us = {(rd + wr) / t_s / 1e9:.0f} GB/s")
 
 
+if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[1] == "traffic":
+    traffic(sys.argv[2], sys.argv[3])
+    sys.exit(0)
 if __name__ == "__main__":
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
