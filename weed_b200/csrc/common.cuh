@@ -25,12 +25,11 @@ cudaError_t pool_free(void *ptr, cudaStream_t st);
 void ensure_dynamic_smem(const void *kernel, int bytes);
 
 // Programmatic dependent launch: every kernel of this library is launched with the programmatic-stream-
-// serialization attribute and starts with pdl_grid_sync(): it lets the NEXT kernel of the stream be
-// scheduled as soon as all of this grid's blocks are resident (griddepcontrol.launch_dependents) and
-// then waits until the PREVIOUS grid has completed and flushed (griddepcontrol.wait) before touching
-// memory. Launch latency, block scheduling and per-kernel set-up (barrier init, TMEM allocation,
+// serialization attribute and starts with pdl_grid_sync(): it waits until the PREVIOUS grid has completed
+// and flushed (griddepcontrol.wait) before touching memory, and then lets the NEXT kernel of the stream be
+// scheduled while this one runs (griddepcontrol.launch_dependents). Launch latency, block scheduling and per-kernel set-up (barrier init, TMEM allocation,
 // tensor-map prefetch) thereby overlap the tail of the preceding kernel instead of following its
-// completion. Experimental and OFF by default (WEEDCU_PDL=1 enables it): see pdl_enabled() in runtime.cu.
+// completion; stream order of every memory access is unchanged. WEEDCU_PDL=0 launches plainly.
 bool pdl_enabled();
 // Only a kernel that directly follows another kernel OF THIS LIBRARY takes the attribute: after a
 // memset / memcpy / event / allocation on the stream (note_stream_op) the next launch is a plain one,
@@ -38,8 +37,10 @@ bool pdl_enabled();
 void note_stream_op();
 bool pdl_take_edge(); // true when the previous stream operation was one of our kernels; marks "kernel" for the next
 __device__ __forceinline__ void pdl_grid_sync() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // wait first, then release the dependents: a kernel's successor may be scheduled while it runs, but never while
+  // it is itself still waiting (chains of not-yet-started kernels piling up behind one another)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {

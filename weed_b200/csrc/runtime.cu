@@ -225,11 +225,11 @@ void pool_release_cached_locked() {
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
-    // opt-in: measured -0.22 ms/step (11.43 -> 11.22) with every launch chained, but one of three bench
-    // runs with mixed plain / chained launches did not finish and the all-chained run's loss drifted
-    // (a zero-fill memset ahead of a split-K GEMM is not a grid the wait covers) — see DESIGN.md §4
+    // on by default (WEEDCU_PDL=0 launches plainly). History: with launch_dependents issued BEFORE griddepcontrol.wait,
+    // not-yet-started kernels piled up behind one another (a chain fill -> cross-entropy backward read a stale value,
+    // one run did not finish); waiting first fixed both
     const char *e = getenv("WEEDCU_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = (e && e[0] == '0') ? 0 : 1;
   }
   return on != 0;
 }
