@@ -359,6 +359,14 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
                              const uint16_t *const *b, int b_major, uint64_t ldb, float *const *c, uint64_t ldc,
                              uint32_t M, uint32_t N, uint32_t K, int accumulate, const float *const *col_bias,
                              void *stream);
+/* weedcu_gemm_bf16 with a residual: C = (A * B + col_bias) + residual, residual [M, N] fp32 column-major with leading
+ * dimension ldr, added in the epilogue in that order — the `x + Linear(...)` of a transformer block
+ * (src/modules/transformer_encoder_layer.cpp:63-125: Linear::forward, then Tensor::add) as one kernel: bit-identical to
+ * weedcu_gemm_bf16 followed by weedcu_binary_real(ADD), without writing and re-reading the Linear output. C is stored
+ * (no accumulate); WEEDCU_ENOSUP when C does not meet the TMA store rules. col_bias may be NULL. */
+int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
+                              uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                              const float *col_bias, const float *residual, uint64_t ldr, void *stream);
 /* Tile family of the bf16 tensor-core GEMM: 0 = cost model over single-CTA 128 x N tiles and CTA-pair
  * (tcgen05 cta_group::2, two SMs of a TPC on one 256 x N tile) kernels (default; env WEEDCU_GEMM_MODE),
  * 1 = single-CTA tiles only, 2 = CTA pairs wherever the operands allow,

@@ -280,6 +280,15 @@ int weedcu_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, const uint16_
     }
   return 0;
 }
+int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
+                              const float *col_bias, const float *residual, uint64_t ldr, void *stream) {
+  if (!residual) return WEEDCU_EINVAL;
+  const int rc = weedcu_gemm_bf16(a, a_major, lda, b, b_major, ldb, c, ldc, M, N, K, 0, col_bias, stream);
+  if (rc || g_nocompute) return rc;
+  for (uint32_t n = 0; n < N; ++n)
+    for (uint32_t m = 0; m < M; ++m) c[m + (uint64_t)n * ldc] = c[m + (uint64_t)n * ldc] + residual[m + (uint64_t)n * ldr];
+  return 0;
+}
 int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b, int b_major, uint64_t ldb, float *const *c, uint64_t ldc,
                              uint32_t M, uint32_t N, uint32_t K, int accumulate, const float *const *col_bias, void *stream) {
   if (!groups || groups > 3 || !b || !c) return WEEDCU_EINVAL;

@@ -267,3 +267,32 @@ def test_matmul_skinny_grouped_equals_separate_launches(gpu, M, K, N, groups):
              U32(M), U32(K), U32(N), PtrArr(*[b.ptr for b in hbias]))
     for g in range(groups):
         assert np.array_equal(sep[g].get(), grp[g].get()), f"group {g}"
+
+
+@pytest.mark.parametrize("mode", [0, 256001, 1256001, 1192001, 1128002])
+@pytest.mark.parametrize("M,N,K", [(8192, 768, 768), (1024, 520, 264), (388, 200, 96)])
+def test_gemm_bf16_residual_equals_gemm_then_add(gpu, M, N, K, mode):
+    """weedcu_gemm_bf16_residual (the `x + Linear(...)` of a transformer block with the add in the GEMM epilogue) is
+    bit-identical to weedcu_gemm_bf16 followed by the fp32 add, in the single-CTA and the CTA-pair kernels, with the
+    bias, ragged tiles and split-K slices (only the first slice adds bias and residual)."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, _ = _operand(rng, M, K, 1)
+    b_dev, ldb, _ = _operand(rng, N, K, 0)
+    res = rng.uniform(-3, 3, M * N).astype(np.float32)
+    bias = rng.uniform(-2, 2, N).astype(np.float32)
+    pa, pb, hres, hbias = gpu.buf(a_dev), gpu.buf(b_dev), gpu.buf(res), gpu.buf(bias)
+    plain, fused = gpu.buf(np.zeros(M * N, np.float32)), gpu.buf(np.full(M * N, 9.0, np.float32))
+    gpu.lib.weedcu_gemm_set_mode(C.c_int(mode))
+    try:
+        gpu.call("gemm_bf16", pa, I32(1), U64(lda), pb, I32(0), U64(ldb), plain, U64(M), U32(M), U32(N), U32(K), I32(0), hbias)
+        gpu.call("gemm_bf16_residual", pa, I32(1), U64(lda), pb, I32(0), U64(ldb), fused, U64(M), U32(M), U32(N), U32(K), hbias, hres, U64(M))
+        want = plain.get() + res
+        got = fused.get()
+    finally:
+        gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
+    if mode % 100 > 1:  # split-K: the slice that adds the residual is reduce-added in a different order than C + residual
+        assert cases.rel_err(got, want) <= 1e-6
+    else:
+        assert np.array_equal(got, want)

@@ -30,6 +30,10 @@ struct Params {
   int accumulate;
   uint32_t splits, kb_per_split; // split-K: work unit = (tile, k-slice); slices meet in C by TMA reduce-add
   const float *col_bias; // optional [N]: C[m,n] = sum_k A B + col_bias[n]  (Linear::forward's bias add)
+  // optional [M, N] column-major with leading dimension ldr: C = (A B + bias) + residual — the `x + Linear(...)` of a
+  // transformer block (transformer_encoder_layer.cpp:63-125) without writing the Linear output and re-reading it
+  const float *residual;
+  uint64_t ldr;
   int tma_store; // C goes out through TMA (needs 16-B aligned base / leading dimension); else direct stores
   // grouped launch: `groups` products that share A (Q / K / V projections of one activation): tile
   // column tn belongs to group tn / tiles_n_group; each group has its own B map, C map / pointer, bias
@@ -239,9 +243,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float *c_base = p.groups > 1 ? p.c_grp[grp] : p.c;
       const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
       const bool add_bias = col_bias && ks == 0; // exactly one k-slice contributes the bias
+      const uint32_t m = m0 + q * 32 + lane;
+      // residual of the chunk being processed (lane = row: every column is one coalesced 128-byte read per warp); the
+      // first chunk's loads are issued before the wait for the accumulator, the next chunk's behind the current staging
+      const bool has_res = p.residual && ks == 0 && m < p.M;
+      float rv[32];
+      auto load_res = [&](uint32_t c0) {
+        const float *res = p.residual + (uint64_t)z * p.c_bs + m + (uint64_t)(n0 + c0) * p.ldr;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
+      };
+      if (has_res) load_res(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t m = m0 + q * 32 + lane;
       if (p.tma_store) {
         // TMEM -> registers -> [32 cols][128 rows] fp32 staging tile; the store warp (warp 3) turns each
         // finished buffer into one TMA store (or reduce-add). The four epilogue warps never meet: a warp
@@ -257,6 +271,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (add_bias) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
+          }
+          if (has_res) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + rv[j]);
+            if (c0 + EPI_COLS < BLOCK_N) load_res(c0 + EPI_COLS); // next chunk's residual: in flight behind this chunk's staging
           }
           if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the MMA warp early
             tcgen05_fence_before();
@@ -497,12 +516,21 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t it = 0, epi_chunk = 0;
     for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
-      const uint32_t t = tile % tiles_per_batch;
+      const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
       const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
       const uint32_t n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
+      const uint32_t m = (t % p.tiles_m) * PAIR_M + rank * BLOCK_M + q * 32 + lane; // this thread's row of C
       const float *col_bias = p.groups > 1 ? p.bias_grp[grp] : p.col_bias;
       const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
       const bool add_bias = col_bias && ks == 0;
+      const bool has_res = p.residual && ks == 0 && m < p.M;
+      float rv[32];
+      auto load_res = [&](uint32_t c0) {
+        const float *res = p.residual + (uint64_t)z * p.c_bs + m + (uint64_t)(n0 + c0) * p.ldr;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
+      };
+      if (has_res) load_res(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -516,6 +544,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (add_bias) {
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
+        }
+        if (has_res) {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + rv[j]);
+          if (c0 + EPI_COLS < BLOCK_N) load_res(c0 + EPI_COLS);
         }
         if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the leader's MMA warp
           tcgen05_fence_before();
@@ -714,8 +747,9 @@ static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, ui
 int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, uint32_t groups,
                              const uint16_t *const *b, int b_major, uint64_t ldb, uint64_t b_bs, float *const *c, uint64_t ldc,
                              uint64_t c_bs, uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
-                             const float *const *col_bias) {
+                             const float *const *col_bias, const float *residual, uint64_t ldr) {
   if (!a || !b || !c || !M || !N || !K || !batch || !groups || groups > kMaxGroups) return WEEDCU_EINVAL;
+  if (residual && (groups != 1 || batch != 1 || accumulate)) return WEEDCU_EINVAL;
   for (uint32_t g = 0; g < groups; ++g)
     if (!b[g] || !c[g]) return WEEDCU_EINVAL;
   // Tile family, tile width and split-K are chosen together by the cost model above. Few-tile
@@ -774,6 +808,8 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   p.groups = groups;
   p.accumulate = accumulate;
   p.col_bias = col_bias ? col_bias[0] : nullptr;
+  p.residual = residual;
+  p.ldr = ldr;
   p.tma_store = 1;
   for (uint32_t g = 0; g < kMaxGroups; ++g) {
     const uint32_t src = g < groups ? g : 0;
@@ -784,6 +820,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
     p.bias_grp[g] = col_bias ? col_bias[src] : nullptr;
   }
   if (best.variant == 1 && !best.pair) p.tma_store = 0;
+  if (!p.tma_store && residual) return WEEDCU_ENOSUP; // the residual add lives in the staged epilogue only
   if (!p.tma_store) {
     if (best.pair) return WEEDCU_ENOSUP; // unreachable: pairs are only chosen when C meets the TMA rules
     for (uint32_t g = 0; g < kMaxGroups; ++g) tmCs.m[g] = tmA; // unused by the kernel, but must be valid descriptors
@@ -792,11 +829,14 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   p.kb_per_split = (num_kb + best_s - 1) / best_s;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits > 1 && !accumulate) { // slices meet by reduce-add: C starts from zero
-    note_stream_op();
     for (uint32_t g = 0; g < groups; ++g) {
       if (batch == 1 && ldc == M) {
-        WCU_CHECK(cudaMemsetAsync(c[g], 0, sizeof(float) * (size_t)M * N, st));
+        // our own fill kernel, not cudaMemsetAsync: it chains with the launches around it (programmatic dependent
+        // launch), a memset node would force plain launches on both sides
+        const int rc = weedcu_fill_real(c[g], (uint64_t)M * N, 0.0f, (void *)st);
+        if (rc) return rc;
       } else {
+        note_stream_op();
         for (uint32_t z = 0; z < batch; ++z)
           WCU_CHECK(cudaMemset2DAsync(c[g] + (uint64_t)z * c_bs, ldc * sizeof(float), 0, (size_t)M * sizeof(float), N, st));
       }
@@ -822,7 +862,7 @@ int launch_gemm_bf16(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs
   float *cs[1] = {c};
   const float *biases[1] = {col_bias};
   return launch_gemm_bf16_grouped(a, a_major, lda, a_bs, 1, bs, b_major, ldb, b_bs, cs, ldc, c_bs, M, N, K, batch, accumulate, st,
-                                  col_bias ? biases : nullptr);
+                                  col_bias ? biases : nullptr, nullptr, 0);
 }
 
 } // namespace tc
@@ -957,7 +997,18 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
                              int b_major, uint64_t ldb, float *const *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
                              int accumulate, const float *const *col_bias, void *stream) {
   return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, groups, b, b_major, ldb, 0, c, ldc, 0, M, N, K, 1, accumulate,
-                                      resolve_stream(stream), col_bias);
+                                      resolve_stream(stream), col_bias, nullptr, 0);
+}
+
+int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c,
+                              uint64_t ldc, uint32_t M, uint32_t N, uint32_t K, const float *col_bias, const float *residual,
+                              uint64_t ldr, void *stream) {
+  if (!a || !b || !c || !residual) return WEEDCU_EINVAL;
+  const uint16_t *bs[1] = {b};
+  float *cs[1] = {c};
+  const float *biases[1] = {col_bias};
+  return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, 1, bs, b_major, ldb, 0, cs, ldc, 0, M, N, K, 1, 0, resolve_stream(stream),
+                                      col_bias ? biases : nullptr, residual, ldr);
 }
 
 int weedcu_gemm_set_mode(int mode) {

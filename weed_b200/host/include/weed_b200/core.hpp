@@ -537,10 +537,11 @@ struct Tensor : public BaseTensor {
   static TensorPtr matmul(TensorPtr a, TensorPtr b);
   static void make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out);
   static void matmul_backward(TensorPtr a, TensorPtr b, TensorPtr out);
-  static TensorPtr linear(TensorPtr a, TensorPtr w, TensorPtr bias); // fused x W + bias, or nullptr
+  // fused x W + bias (+ residual: the `x + Linear(...)` of a transformer block in the same kernel), or nullptr
+  static TensorPtr linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr residual = nullptr);
   // the same for two or three Linear layers reading one input (W_q / W_k / W_v): one grouped launch,
   // each output with exactly the autograd node Tensor::linear would give it; empty when not eligible
-  static TensorPtr finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg);
+  static TensorPtr finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg, TensorPtr residual = nullptr);
   static std::vector<TensorPtr> linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases);
   static TensorPtr sub(TensorPtr a, TensorPtr b);
   static void make_sub_node(TensorPtr a, TensorPtr b, TensorPtr out);

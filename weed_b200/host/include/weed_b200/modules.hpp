@@ -81,6 +81,9 @@ struct Linear : public Module {
   void migrate_cpu() override;
   void migrate_gpu() override;
   TensorPtr forward(const TensorPtr x) override;
+  // residual + forward(x): one kernel when the fused tensor-core path applies (the residual rides in the GEMM
+  // epilogue), otherwise exactly Tensor::add(residual, forward(x)) as TransformerEncoderLayer::forward composes it
+  TensorPtr forward_add(const TensorPtr x, const TensorPtr residual);
   std::vector<ParameterPtr> parameters() override;
 };
 typedef std::shared_ptr<Linear> LinearPtr;
@@ -154,6 +157,9 @@ struct MultiHeadAttention : public Module {
   void migrate_cpu() override;
   void migrate_gpu() override;
   TensorPtr forward(const TensorPtr x) override;
+  // residual + forward(x) with the add folded into the output projection (Linear::forward_add)
+  TensorPtr forward_add(const TensorPtr x, const TensorPtr residual);
+  TensorPtr fuse_residual; // set for the duration of forward_add: the W_o projection adds it
 };
 typedef std::shared_ptr<MultiHeadAttention> MultiHeadAttentionPtr;
 

@@ -52,7 +52,7 @@ void matmul(const Tensor &a, const Tensor &b, Tensor &out);
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out);
 // out = a b + bias (bias: dense [N], broadcast over rows) in one tensor-core GEMM; false (nothing
 // computed) when that kernel does not apply to these operands
-bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out);
+bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out, const Tensor *residual = nullptr);
 // Packs dy [rows, N] into its bf16 GEMM shadow and adds its column sums into `sums` (dense [N]) in the
 // same pass — Linear's bias gradient without a separate reduction. false: nothing was done.
 bool pack_with_column_sums(const Tensor &dy, Tensor &sums);

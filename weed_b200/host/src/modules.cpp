@@ -88,6 +88,13 @@ TensorPtr Linear::forward(const TensorPtr x) {
   if (bias) y = y + bias;
   return y;
 }
+TensorPtr Linear::forward_add(const TensorPtr x, const TensorPtr residual) {
+  if (bias && backend_config().fused) {
+    TensorPtr fused = Tensor::linear(x, weight, bias, residual);
+    if (fused) return fused;
+  }
+  return residual + forward(x);
+}
 std::vector<ParameterPtr> Linear::parameters() {
   if (bias) return {weight, bias};
   return {weight};
@@ -315,7 +322,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
                                             x->stream());
       if (rc == 0) {
         end_output_shadow(os);
-        return W_o->forward(out);
+        return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
       }
       if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "attention");
     }
@@ -344,7 +351,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
     TensorPtr dst = strided_view(out, {Bu, Tu, H, hd}, {1U, Bu, Bu * Tu, Bu * Tu * H}, 0U);
     TensorPtr src = strided_view(oc, {Bu, Tu, H, hd}, {Tu * hd, 1U, Tu * hd * Bu, Tu}, 0U);
     Weed::copy_broadcast(*dst, *src);
-    return W_o->forward(out);
+    return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
   }
 
   if (cfg.fused && use_kv_cache && kv_quant_bits == 0 && num_kv_heads == num_heads && head_dim <= 64 && dense_contiguous(*Q) &&
@@ -369,7 +376,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
                                            std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0, x->stream());
     if (rc == 0) {
       cache_len += Tu;
-      return W_o->forward(out);
+      return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
     }
     if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "attention decode");
   }
@@ -427,7 +434,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
   out = Tensor::transpose(out, 1, 2);
   const symint attn_dim = (symint)num_heads * (symint)head_dim;
   out = Tensor::reshape(out, {B, T, attn_dim});
-  return W_o->forward(out);
+  return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
 }
 
 // ------------------------------------------------------------------------------------- encoder layer
@@ -469,16 +476,24 @@ void TransformerEncoderLayer::migrate_gpu() {
 // Pre-norm block, transformer_encoder_layer.cpp:63-125. The reference's per-sublayer
 // migrate_gpu()/migrate_cpu() "telescoping" is offload for small VRAM; with 180 GB of HBM3e the
 // parameters simply stay resident.
+TensorPtr MultiHeadAttention::forward_add(const TensorPtr x, const TensorPtr residual) {
+  struct Guard {
+    TensorPtr &slot;
+    ~Guard() { slot = nullptr; }
+  } guard{fuse_residual};
+  fuse_residual = residual;
+  return forward(x);
+}
 TensorPtr TransformerEncoderLayer::forward(const TensorPtr x_) {
   TensorPtr x = x_->storage->device == DeviceTag::GPU ? x_ : x_->cast(DeviceTag::GPU);
   TensorPtr x1 = norm1->forward(x);
-  x1 = self_attn->forward(x1);
-  x1 = x + x1;
+  // x + self_attn(...) and x1 + ff2(...): the two residual adds (transformer_encoder_layer.cpp:63-125) ride in the
+  // epilogue of the W_o / ff2 product when the fused path applies; forward_add composes Linear + add otherwise
+  x1 = self_attn->forward_add(x1, x);
   TensorPtr ff = norm2->forward(x1);
   ff = ff1->forward(ff);
   ff = activation->forward(ff);
-  ff = ff2->forward(ff);
-  return x1 + ff;
+  return ff2->forward_add(ff, x1);
 }
 
 // ------------------------------------------------------------------------------------- Sequential

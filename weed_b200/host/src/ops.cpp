@@ -302,7 +302,7 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
 
 // `bias` (optional): a dense [N] vector added to every row in the GEMM epilogue; when given and the
 // tensor-core path does not apply, nothing is computed and false is returned.
-bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, const Tensor *bias = nullptr) {
+bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, const Tensor *bias = nullptr, const Tensor *residual = nullptr) {
   validate_all_same_device({&a, &b, &out}, "MatMulKernel::matmul");
   if ((a.shape.size() != 2U) || (b.shape.size() != 2U) || (out.shape.size() != 2U))
     throw std::invalid_argument("MatMul is only for matrices with 2 indices!");
@@ -320,14 +320,20 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
     if (bf16_operand(a, a.stride[0U], a.stride[1U], M, K, true, pa) && bf16_operand(b, b.stride[1U], b.stride[0U], N, K, false, pb)) {
       const Dev dc = dev_out(out, "matmul", !accumulate);
       const real1 *bias_ptr = bias ? dev_of(*bias, "matmul").ptr + bias->offset : nullptr;
-      const int rc = weedcu_gemm_bf16(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K,
-                                      accumulate, bias_ptr, dc.stream);
+      int rc;
+      if (residual) // [M, N] with the layout of `out`, added after the bias in the epilogue
+        rc = weedcu_gemm_bf16_residual(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K, bias_ptr,
+                                       dev_of(*residual, "matmul").ptr + residual->offset, out.stride[1U], dc.stream);
+      else
+        rc = weedcu_gemm_bf16(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K, accumulate, bias_ptr,
+                              dc.stream);
       if (rc != WEEDCU_ENOSUP) {
         throw_on_error(rc, "matmul");
         return true;
       }
     }
   }
+  if (residual) return false; // only the tensor-core epilogue adds a residual: the caller composes Linear + add
   if (cfg.fused && M <= 16U) {
     // a handful of rows (a decode step, or a tiny training batch): the product is one pass over the
     // weight matrix — skinny FFMA kernel at fp32 in either precision mode, bias added in the same pass
@@ -588,7 +594,9 @@ void logsoftmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const
 
 void matmul(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 0); }
 void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out) { matmul_impl(a, b, out, 1); }
-bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out) { return matmul_impl(a, b, out, 0, &bias); }
+bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out, const Tensor *residual) {
+  return matmul_impl(a, b, out, 0, &bias, residual);
+}
 bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
                          const std::vector<Tensor *> &outs) {
   const BackendConfig &cfg = backend_config();

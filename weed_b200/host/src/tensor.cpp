@@ -973,7 +973,7 @@ TensorPtr Tensor::matmul(TensorPtr a, TensorPtr b) { // tensor.cpp:1204-1326
 // Fused Linear::forward (src/modules/linear.cpp): x W + bias as ONE tensor-core GEMM with the bias
 // added in the epilogue, one autograd node instead of matmul + add. Returns nullptr when the fused
 // kernel does not apply (the caller then composes the two ops like the reference).
-TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
+TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr residual) {
   const BackendConfig &cfg = backend_config();
   if (!cfg.fused) return nullptr;
   if (a->shape.size() < 2U || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back()) return nullptr;
@@ -983,7 +983,15 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
   if (!skinny && (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.operand_cache)) return nullptr;
   if (a->storage->device != DeviceTag::GPU || w->storage->device != DeviceTag::GPU) return nullptr;
   if (bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U] || bias->storage->device != DeviceTag::GPU) return nullptr;
-  const bool rg = a->requires_grad || w->requires_grad || bias->requires_grad;
+  if (residual) {
+    // the residual must be the dense column-major tensor the result will be: same leading extents as `a`, last extent N
+    if (skinny || residual->storage->device != DeviceTag::GPU || residual->shape.size() != a->shape.size() || !is_contiguous(residual->shape, residual->stride))
+      return nullptr;
+    for (size_t i = 0; i + 1U < a->shape.size(); ++i)
+      if (residual->shape[i] != a->shape[i]) return nullptr;
+    if (residual->shape.back() != w->shape[1U]) return nullptr;
+  }
+  const bool rg = a->requires_grad || w->requires_grad || bias->requires_grad || (residual && residual->requires_grad);
   const bool needs_flatten = (a->shape.size() > 2U);
   const symint K = (symint)a->shape.back(), M = (symint)a->shape[a->shape.size() - 2], N = (symint)w->shape[1U];
   symint batch = 1;
@@ -992,12 +1000,12 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias) {
   if (needs_flatten) a2 = reshape(a, {batch * M, K});
   const tcapint as0 = a2->shape[0U];
   TensorPtr out = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
-  if (!Weed::matmul_bias(*a2, *w, *bias, *out)) return nullptr;
-  return finish_linear(a, w, bias, out, rg);
+  if (!Weed::matmul_bias(*a2, *w, *bias, *out, residual.get())) return nullptr;
+  return finish_linear(a, w, bias, out, rg, residual);
 }
 
 // everything Tensor::linear does after the product: final shape, the Parameter mutation of `y + bias`, the node
-TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg) {
+TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg, TensorPtr residual) {
   const bool needs_flatten = (a->shape.size() > 2U);
   const symint M = (symint)a->shape[a->shape.size() - 2], N = (symint)w->shape[1U];
   if (needs_flatten) {
@@ -1010,9 +1018,15 @@ TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, Tensor
   prepare_binary(out, bias, "add"); // the same match_shape mutation of the Parameter that `y + bias` performs
   if (rg) {
     out->make_gradient();
-    out->grad_node = std::make_shared<Node>(grad_parents({a, w, bias}), [a, w, bias, wout = std::weak_ptr<Tensor>(out)]() {
+    std::vector<TensorPtr> parents{a, w, bias};
+    if (residual) parents.push_back(residual);
+    out->grad_node = std::make_shared<Node>(grad_parents(parents), [a, w, bias, residual, wout = std::weak_ptr<Tensor>(out)]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
       if (!out) return;
+      if (residual && residual->requires_grad) { // d(residual + y)/d residual = 1: what the add node of `x + Linear(...)` does
+        TensorPtr out_grad = view_copy(out->grad);
+        if (!adopt_incoming_gradient(residual, out_grad)) accumulate(residual, out_grad, *out_grad, false);
+      }
       if (bias->requires_grad) {
         // the bias gradient (column sums of dY) rides on the pass that packs dY for the two GEMMs below
         TensorPtr out_grad = view_copy(out->grad);
