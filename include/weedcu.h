@@ -343,6 +343,11 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
 int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b,
                                  const weedcu_mat *bm, float *const *c, const weedcu_mat *cm, uint32_t M, uint32_t K,
                                  uint32_t N, const float *const *bias, void *stream);
+/* weedcu_matmul_skinny with a residual laid out like C (same cm, including its offset): C = (A * B + bias) + residual,
+ * stored — the `x + Linear(...)` of a transformer block on a decode step. bias may be NULL. */
+int weedcu_matmul_skinny_residual(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c,
+                                  const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *bias,
+                                  const float *residual, void *stream);
 /* bf16 tensor-core GEMM on operands already held in bf16 (raw uint16 bit patterns).
  * a_major / b_major: 0 = K contiguous, 1 = M (resp. N) contiguous; lda/ldb are the strides
  * (in elements) of the non-contiguous index. C is fp32, column-major with leading dim ldc.

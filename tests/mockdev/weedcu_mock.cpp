@@ -129,6 +129,18 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
   if (M > 16u) return WEEDCU_ENOSUP;
   return RUN(wo_matmul_skinny(a, MAT(am), b, MAT(bm), c, MAT(cm), M, K, N, bias, accumulate));
 }
+int weedcu_matmul_skinny_residual(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
+                                  const float *bias, const float *residual, void *stream) {
+  if (!residual) return WEEDCU_EINVAL;
+  const int rc = weedcu_matmul_skinny(a, am, b, bm, c, cm, M, K, N, bias, 0, stream);
+  if (rc || g_nocompute) return rc;
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      const uint64_t o = cm->offset + (uint64_t)m * cm->s0 + (uint64_t)n * cm->s1;
+      c[o] = c[o] + residual[o];
+    }
+  return 0;
+}
 int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b, const weedcu_mat *bm, float *const *c, const weedcu_mat *cm, uint32_t M,
                                  uint32_t K, uint32_t N, const float *const *bias, void *stream) {
   if (!groups || groups > 3u || !b || !c) return WEEDCU_EINVAL;

@@ -296,3 +296,20 @@ def test_gemm_bf16_residual_equals_gemm_then_add(gpu, M, N, K, mode):
         assert cases.rel_err(got, want) <= 1e-6
     else:
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(8, 768, 768, 1), (8, 3072, 768, 1), (5, 70, 37, 0), (16, 130, 33, 1)])
+def test_matmul_skinny_residual_equals_skinny_then_add(gpu, M, K, N, bias):
+    """weedcu_matmul_skinny_residual (x + Linear(...) of a decode step in one launch) == weedcu_matmul_skinny + fp32 add."""
+    import ctypes as C
+    rng = np.random.default_rng(M + K + N)
+    U32 = C.c_uint32
+    ha = gpu.buf(rng.uniform(-1, 1, M * K).astype(np.float32))
+    hb = gpu.buf(rng.uniform(-1, 1, K * N).astype(np.float32))
+    res = rng.uniform(-3, 3, M * N).astype(np.float32)
+    hres, hbias = gpu.buf(res), gpu.buf(rng.uniform(-2, 2, N).astype(np.float32))
+    plain, fused = gpu.buf(np.zeros(M * N, np.float32)), gpu.buf(np.full(M * N, 9.0, np.float32))
+    am, bm, cm = cases._mat(0, 1, M, 0), cases._mat(0, 1, K, 0), cases._mat(0, 1, M, 0)
+    gpu.call("matmul_skinny", ha, am, hb, bm, plain, cm, U32(M), U32(K), U32(N), hbias if bias else None, C.c_int(0))
+    gpu.call("matmul_skinny_residual", ha, am, hb, bm, fused, cm, U32(M), U32(K), U32(N), hbias if bias else None, hres)
+    assert np.array_equal(fused.get(), plain.get() + res)

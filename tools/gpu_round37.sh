@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu -k "argmax or layernorm or skinny or decode or greedy or kv_cache" > gpurun_out/decode_tests.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu -k "argmax or layernorm or skinny or decode or greedy or kv_cache or encoder or residual" > gpurun_out/decode_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/decode_tests.log
 timeout 600 python tools/decode_bench.py > gpurun_out/r01_decode_fp32_v13.json 2> gpurun_out/decode.err
 echo "decode rc=$?"; python - <<'PY'

@@ -171,9 +171,10 @@ struct SkinnyGroups {
   const float *b[3];
   float *c[3];
   const float *bias[3];
+  const float *residual[3]; // optional, laid out like c: c = (a b + bias) + residual
 };
 template <int MM, bool AVEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MM <= 8 && AVEC) ? 2 : 1) // the decode variant (8 rows, vector A loads) at <= 128 registers: 2 blocks per SM
 skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, SkinnyGroups grp, uint32_t b_s0,
                      uint32_t b_s1, uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, int accumulate) {
   pdl_grid_sync();
@@ -181,6 +182,7 @@ skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, 
   const float *__restrict__ b = grp.b[blockIdx.y];
   float *c = grp.c[blockIdx.y];
   const float *__restrict__ bias = grp.bias[blockIdx.y];
+  const float *__restrict__ residual = grp.residual[blockIdx.y];
   constexpr int NV = MM * kSkCW; // partial sums per lane
   __shared__ float red[8][NV];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -241,6 +243,7 @@ skinny_matmul_kernel(const float *__restrict__ a, uint32_t a_s0, uint32_t a_s1, 
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
       if (bias) s += bias[nn];
+      if (residual) s += residual[(uint64_t)m * c_s0 + (uint64_t)nn * c_s1];
       float *dst = c + (uint64_t)m * c_s0 + (uint64_t)nn * c_s1;
       *dst = accumulate ? (*dst + s) : s;
     }
@@ -270,7 +273,7 @@ static int launch_skinny_groups(const float *a, uint32_t a_s0, uint32_t a_s1, co
 int launch_skinny_matmul(const float *a, uint32_t a_s0, uint32_t a_s1, const float *b, uint32_t b_s0, uint32_t b_s1, float *c,
                          uint32_t c_s0, uint32_t c_s1, uint32_t M, uint32_t K, uint32_t N, const float *bias, int accumulate,
                          cudaStream_t st) {
-  SkinnyGroups grp = {{b, b, b}, {c, c, c}, {bias, bias, bias}};
+  SkinnyGroups grp = {{b, b, b}, {c, c, c}, {bias, bias, bias}, {nullptr, nullptr, nullptr}};
   return launch_skinny_groups(a, a_s0, a_s1, grp, 1, b_s0, b_s1, c_s0, c_s1, M, K, N, accumulate, st);
 }
 
@@ -335,6 +338,15 @@ int weedcu_matmul_skinny(const float *a, const weedcu_mat *am, const float *b, c
                               K, N, bias, accumulate, resolve_stream(stream));
 }
 
+int weedcu_matmul_skinny_residual(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm, float *c, const weedcu_mat *cm,
+                                  uint32_t M, uint32_t K, uint32_t N, const float *bias, const float *residual, void *stream) {
+  if (!a || !am || !b || !bm || !c || !cm || !residual || !M || !K || !N) return WEEDCU_EINVAL;
+  const float *bb = b + bm->offset, *rr = residual + cm->offset;
+  float *cc = c + cm->offset;
+  SkinnyGroups grp = {{bb, bb, bb}, {cc, cc, cc}, {bias, bias, bias}, {rr, rr, rr}};
+  return launch_skinny_groups(a + am->offset, am->s0, am->s1, grp, 1, bm->s0, bm->s1, cm->s0, cm->s1, M, K, N, 0, resolve_stream(stream));
+}
+
 int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t groups, const float *const *b, const weedcu_mat *bm,
                                  float *const *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N, const float *const *bias,
                                  void *stream) {
@@ -346,6 +358,7 @@ int weedcu_matmul_skinny_grouped(const float *a, const weedcu_mat *am, uint32_t 
     grp.b[g] = b[s] + bm->offset;
     grp.c[g] = c[s] + cm->offset;
     grp.bias[g] = bias ? bias[s] : nullptr;
+    grp.residual[g] = nullptr;
   }
   return launch_skinny_groups(a + am->offset, am->s0, am->s1, grp, groups, bm->s0, bm->s1, cm->s0, cm->s1, M, K, N, 0, resolve_stream(stream));
 }

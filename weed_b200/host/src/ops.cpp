@@ -333,7 +333,20 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
       }
     }
   }
-  if (residual) return false; // only the tensor-core epilogue adds a residual: the caller composes Linear + add
+  if (cfg.fused && M <= 16U && residual) { // decode step: the residual rides in the skinny kernel's final add
+    // (Tensor::linear has checked that the residual is the dense column-major tensor `out` becomes after its reshape)
+    if (out.stride[0U] != 1U || out.stride[1U] != M || residual->get_broadcast_size() != (tcapint)M * N) return false;
+    const Dev da = dev_of(a, "matmul"), db = dev_of(b, "matmul"), dr = dev_of(*residual, "matmul"), dc = dev_out(out, "matmul", true);
+    const weedcu_mat am = mat_of(a), bm = mat_of(b);
+    weedcu_mat cm = mat_of(out);
+    // residual and C share one mat descriptor: fold their (possibly different) offsets into the pointers
+    const uint64_t c_off = cm.offset, r_off = residual->offset;
+    cm.offset = 0U;
+    const real1 *bias_ptr = bias ? dev_of(*bias, "matmul").ptr + bias->offset : nullptr;
+    throw_on_error(weedcu_matmul_skinny_residual(da.ptr, &am, db.ptr, &bm, dc.ptr + c_off, &cm, M, K, N, bias_ptr, dr.ptr + r_off, dc.stream), "matmul");
+    return true;
+  }
+  if (residual) return false; // no other path adds a residual: the caller composes Linear + add
   if (cfg.fused && M <= 16U) {
     // a handful of rows (a decode step, or a tiny training batch): the product is one pass over the
     // weight matrix — skinny FFMA kernel at fp32 in either precision mode, bias added in the same pass

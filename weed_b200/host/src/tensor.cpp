@@ -985,7 +985,7 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr res
   if (bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U] || bias->storage->device != DeviceTag::GPU) return nullptr;
   if (residual) {
     // the residual must be the dense column-major tensor the result will be: same leading extents as `a`, last extent N
-    if (skinny || residual->storage->device != DeviceTag::GPU || residual->shape.size() != a->shape.size() || !is_contiguous(residual->shape, residual->stride))
+    if (residual->storage->device != DeviceTag::GPU || residual->shape.size() != a->shape.size() || !is_contiguous(residual->shape, residual->stride))
       return nullptr;
     for (size_t i = 0; i + 1U < a->shape.size(); ++i)
       if (residual->shape[i] != a->shape[i]) return nullptr;
