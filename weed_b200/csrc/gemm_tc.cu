@@ -734,7 +734,10 @@ static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, ui
   // same tiles and k-slices so that the lazy zero-fill of gradients stays a pure scheduling change
   // (tests/test_host_gpu.py::test_operand_cache_and_lazy_zero_change_nothing).
   (void)accumulate;
-  const double t_epi = c.bn * (c.pair ? 0.0236 : 0.0263) * (c.splits > 1 ? 1.25 : 1.0);
+  // per-tile epilogue floor measured on the LM-head product (N = 50257, K = 768): 6.04 / 4.66 / 3.39 us for CTA-pair
+  // tiles of width 256 / 192 / 128, 6.69 / 5.29 / 3.90 us for single-CTA tiles
+  const double epi_us = c.pair ? (c.bn == 256 ? 6.04 : c.bn == 192 ? 4.66 : 3.39) : (c.bn == 256 ? 6.69 : c.bn == 192 ? 5.29 : 3.90);
+  const double t_epi = epi_us * (c.splits > 1 ? 1.25 : 1.0);
   const double loop = kb_per * t_kb;
   double us = waves * (loop > t_epi ? loop : t_epi) + 4.0 + 0.5 * (loop < t_epi ? loop : t_epi);
   if (c.splits > 1) us += 3.0 + (double)c_elems * 4.0 / 5.0e6; // zero-fill before the reduce-adds
