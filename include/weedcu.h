@@ -56,6 +56,9 @@ const char *weedcu_error_string(int code);
 void *weedcu_default_stream(void);          /* per-device compute stream, created on demand */
 int weedcu_set_default_stream(void *stream);/* adopt an external stream (e.g. torch's) */
 int weedcu_stream_create(void **stream);
+/* high != 0: the highest stream priority of the device — blocks of kernels queued on it are scheduled ahead of the
+ * compute stream's as SMs free up (the communication stream of the data-parallel gradient all-reduce) */
+int weedcu_stream_create_priority(void **stream, int high);
 int weedcu_stream_destroy(void *stream);
 int weedcu_stream_sync(void *stream);       /* GpuDevice::clFinish */
 int weedcu_stream_wait_event(void *stream, void *event);

@@ -51,6 +51,7 @@ const char *weedcu_error_string(int code) { return code == 0 ? "ok" : (code == W
 void *weedcu_default_stream(void) { return (void *)0x1; }
 int weedcu_set_default_stream(void *) { return 0; }
 int weedcu_stream_create(void **stream) { if (!stream) return WEEDCU_EINVAL; *stream = (void *)0x1; return 0; }
+int weedcu_stream_create_priority(void **stream, int) { return weedcu_stream_create(stream); }
 int weedcu_stream_destroy(void *) { return 0; }
 int weedcu_stream_sync(void *) { return 0; }
 int weedcu_stream_wait_event(void *, void *) { return 0; }

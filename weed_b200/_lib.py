@@ -76,7 +76,7 @@ def check(rc, what="weedcu call"):
 # every symbol include/weedcu.h declares (kept in sync by tests/test_abi_cpu.py)
 SYMBOLS = """
 weedcu_device_count weedcu_set_device weedcu_get_device weedcu_device_info weedcu_error_string
-weedcu_default_stream weedcu_set_default_stream weedcu_stream_create weedcu_stream_destroy
+weedcu_default_stream weedcu_set_default_stream weedcu_stream_create weedcu_stream_create_priority weedcu_stream_destroy
 weedcu_stream_sync weedcu_stream_wait_event weedcu_event_create weedcu_event_destroy
 weedcu_event_record weedcu_event_sync weedcu_event_elapsed_ms weedcu_malloc weedcu_free weedcu_pool_trim
 weedcu_mem_info weedcu_host_alloc weedcu_host_free weedcu_memcpy_h2d weedcu_memcpy_d2h

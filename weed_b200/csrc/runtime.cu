@@ -143,6 +143,16 @@ int weedcu_stream_create(void **stream) {
   *stream = (void *)st;
   return 0;
 }
+int weedcu_stream_create_priority(void **stream, int high) {
+  if (!stream) return WEEDCU_EINVAL;
+  int least = 0, greatest = 0;
+  WCU_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest)); // numerically lower = higher priority
+  cudaStream_t st;
+  WCU_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, high ? greatest : least));
+  configure_pool(current_device());
+  *stream = (void *)st;
+  return 0;
+}
 int weedcu_stream_destroy(void *stream) {
   WCU_CHECK(cudaStreamDestroy((cudaStream_t)stream));
   return 0;

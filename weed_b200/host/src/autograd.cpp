@@ -185,7 +185,9 @@ void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm) {
   if (grouped) throw_on_error(weedcu_nccl_group_end(), "allreduce_gradients");
 }
 GradientBuckets::GradientBuckets(void *c, size_t bytes) : comm(c), bucket_bytes(bytes) {
-  throw_on_error(weedcu_stream_create(&comm_stream), "GradientBuckets");
+  // highest priority: the all-reduce kernels' blocks are scheduled ahead of the backward kernels' as SMs free up, so the
+  // collective of a bucket runs WHILE the rest of backward does instead of queueing behind it
+  throw_on_error(weedcu_stream_create_priority(&comm_stream, 1), "GradientBuckets");
   throw_on_error(weedcu_event_create(&ev_ready), "GradientBuckets");
   throw_on_error(weedcu_event_create(&ev_done), "GradientBuckets");
 }
