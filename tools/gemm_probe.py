@@ -1,5 +1,5 @@
 """One bf16 GEMM shape under one tile configuration, a few launches — the target of `ncu --set full
---import-source on` captures (tools/gpu_round20.sh).  python tools/gemm_probe.py M N K a_major b_major acc mode"""
+--import-source on` captures (tools/gpu_runs/gpu_round20.sh).  python tools/gemm_probe.py M N K a_major b_major acc mode"""
 import ctypes as C
 import os
 import sys
