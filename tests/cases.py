@@ -393,6 +393,12 @@ def _c(be, rng):  # accumulate = 0: dlogits is overwritten (vocab split over sev
     return _ce(be, rng, 300, 2000, acc=0)
 
 
+for _rows, _V in [(1028, 300), (2048, 1000), (516, 50257)]:
+    @case(f"cross_entropy_{_rows}x{_V}_vec4_rows", tol=2e-5)
+    def _c(be, rng, rows=_rows, V=_V):  # forward with 4 adjacent rows per thread (128-row tiles, ragged last tile / vocabulary slice)
+        return _ce(be, rng, rows, V)
+
+
 @case("cross_entropy_33x50257", tol=2e-5)
 def _c(be, rng):  # GPT-2 vocabulary, ragged row tile
     return _ce(be, rng, 33, 50257)

@@ -436,6 +436,69 @@ ce_fwd_partial(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t 
     part_s[(uint64_t)blockIdx.y * rows + r] = S;
   }
 }
+// The same for rs == 1, rows % 4 == 0: a thread owns 4 adjacent rows (one 128-bit load per vocabulary entry), a warp
+// reads 512 contiguous bytes and a block covers 128 rows — with 32-row tiles every 128-byte line of a tile sits in a
+// different DRAM page and the pass ran at 4.4 TB/s.
+__global__ void __launch_bounds__(kCeRT * kCeBY)
+ce_fwd_partial_vec4(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t vs, uint32_t v_per_block,
+                    float *__restrict__ part_m, float *__restrict__ part_s) {
+  pdl_grid_sync();
+  __shared__ __align__(16) float red_m[kCeBY][4 * kCeRT];
+  __shared__ __align__(16) float red_s[kCeBY][4 * kCeRT];
+  const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+  const uint32_t r = (blockIdx.x * kCeRT + tx) * 4u;
+  const bool live = r < rows;
+  const uint32_t v0 = blockIdx.y * v_per_block, v1 = min(V, v0 + v_per_block);
+  const float *p = x + r;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, s[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 4; // 4 x 128-bit loads in flight per thread
+  if (live)
+    for (uint32_t j0 = v0 + ty; j0 < v1; j0 += kCeBY * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + u * kCeBY;
+        v[u] = (j < v1) ? *reinterpret_cast<const float4 *>(p + (uint64_t)j * vs) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = k == 0 ? v[u].x : k == 1 ? v[u].y : k == 2 ? v[u].z : v[u].w;
+        float m4 = e[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) m4 = fmaxf(m4, e[u]);
+        if (m4 > mx[k]) { // rescale the running sum once per batch
+          s[k] *= expf(mx[k] - m4);
+          mx[k] = m4;
+        }
+        if (mx[k] > -INFINITY) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) s[k] += expf(e[u] - mx[k]);
+        }
+      }
+    }
+  *reinterpret_cast<float4 *>(&red_m[ty][4 * tx]) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+  *reinterpret_cast<float4 *>(&red_s[ty][4 * tx]) = make_float4(s[0], s[1], s[2], s[3]);
+  __syncthreads();
+  const uint32_t t = ty * kCeRT + tx; // 256 threads, 128 rows: the first 128 merge one row each
+  if (t < 4 * kCeRT) {
+    const uint32_t rr = blockIdx.x * 4 * kCeRT + t;
+    if (rr < rows) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int y = 0; y < kCeBY; ++y) M = fmaxf(M, red_m[y][t]);
+      float S = 0.0f;
+#pragma unroll
+      for (int y = 0; y < kCeBY; ++y) {
+        const float my = red_m[y][t];
+        if (my > -INFINITY) S += red_s[y][t] * expf(my - M);
+      }
+      part_m[(uint64_t)blockIdx.y * rows + rr] = M;
+      part_s[(uint64_t)blockIdx.y * rows + rr] = S;
+    }
+  }
+}
 __global__ void __launch_bounds__(256)
 ce_fwd_finish(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
               const int32_t *__restrict__ targets, const float *__restrict__ part_m,
@@ -797,12 +860,27 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
   if (!logits || !targets || !lse || !loss || !rows || !V) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
   uint32_t splits, vpb;
-  ce_split(rows, V, splits, vpb);
+  const bool vec4 = rs == 1u && (rows % 4u) == 0 && rows >= 512u && (vs % 4u) == 0 && aligned16(logits + offset);
+  if (vec4) { // 128-row tiles: four times fewer row tiles, so four times more vocabulary slices for the same block count
+    const uint32_t row_tiles = (rows + 4 * kCeRT - 1) / (4 * kCeRT);
+    uint32_t want = (8u * kNumSMs + row_tiles - 1) / row_tiles;
+    const uint32_t max_splits = (V + kCeBY * 4 - 1) / (kCeBY * 4);
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    vpb = (V + want - 1) / want;
+    vpb = (vpb + kCeBY * 4 - 1) / (kCeBY * 4) * (kCeBY * 4);
+    splits = (V + vpb - 1) / vpb;
+  } else {
+    ce_split(rows, V, splits, vpb);
+  }
   float *ws = nullptr; // nll[rows], part_m[splits][rows], part_s[splits][rows]
   WCU_CHECK(pool_alloc((void **)&ws, sizeof(float) * (size_t)rows * (1 + 2 * (size_t)splits), st));
   float *nll = ws, *pm = ws + rows, *ps = pm + (size_t)splits * rows;
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 4.0 * (double)rows * V);
-  launch_k(ce_fwd_partial, dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, st, 
+  if (vec4)
+    launch_k(ce_fwd_partial_vec4, dim3((rows + 4 * kCeRT - 1) / (4 * kCeRT), splits), dim3(kCeRT, kCeBY), 0, st, logits + offset, rows, V, vs, vpb, pm, ps);
+  else
+    launch_k(ce_fwd_partial, dim3((rows + kCeRT - 1) / kCeRT, splits), dim3(kCeRT, kCeBY), 0, st, 
       logits + offset, rows, V, rs, vs, vpb, pm, ps);
   int rc = after_launch();
   if (rc == 0) {
