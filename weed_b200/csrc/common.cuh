@@ -35,7 +35,7 @@ bool pdl_enabled();
 // memset / memcpy / event / allocation on the stream (note_stream_op) the next launch is a plain one,
 // so its ordering against those operations is the ordinary stream order.
 void note_stream_op();
-bool pdl_take_edge(); // true when the previous stream operation was one of our kernels; marks "kernel" for the next
+bool pdl_take_edge(cudaStream_t st); // true when the previous operation of this library was one of our kernels on the SAME stream; marks "kernel" for the next
 __device__ __forceinline__ void pdl_grid_sync() {
   // wait first, then release the dependents: a kernel's successor may be scheduled while it runs, but never while
   // it is itself still waiting (chains of not-yet-started kernels piling up behind one another)
@@ -53,7 +53,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
-  cfg.numAttrs = pdl_take_edge() ? 1u : 0u;
+  cfg.numAttrs = pdl_take_edge(st) ? 1u : 0u;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...); // errors surface in after_launch()
 }
 

@@ -244,11 +244,15 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+// One issuing thread per process (the reference's model): plain globals. The edge is only taken when the
+// previous launch of this library went to the same stream, so a second stream (the communication stream, another
+// device's compute stream) never inherits a chain it is not part of.
 static bool g_prev_is_kernel = false;
+static cudaStream_t g_prev_stream = nullptr;
 static int g_kernel_class = 0;
 void note_stream_op() { g_prev_is_kernel = false; }
 void note_kernel_class(int cls) { g_kernel_class = cls; }
-bool pdl_take_edge() {
+bool pdl_take_edge(cudaStream_t st) {
   // WEEDCU_PDL_CLASSES: bit c set = launches of profiling class c (weedcu.h WEEDCU_PROF_*) may take the edge
   static long mask = -2;
   if (mask == -2) {
@@ -263,7 +267,8 @@ bool pdl_take_edge() {
     edge_p = edge_c = -1;
     if (e) sscanf(e, "%d,%d", &edge_p, &edge_c);
   }
-  bool take = g_prev_is_kernel && pdl_enabled() && ((mask >> (g_kernel_class & 31)) & 1L);
+  bool take = g_prev_is_kernel && g_prev_stream == st && pdl_enabled() && ((mask >> (g_kernel_class & 31)) & 1L);
+  g_prev_stream = st;
   if (edge_p >= 0 && !(prev_class == edge_p && g_kernel_class == edge_c)) take = false;
   prev_class = g_kernel_class;
   g_prev_is_kernel = true;
