@@ -115,6 +115,7 @@ int wh_config(const char *name, double value) {
     else if (n == "lazy_zero") c.lazy_zero = value != 0;
     else if (n == "defer_grads") c.defer_grads = value != 0;
     else if (n == "cow_grads") c.cow_grads = value != 0;
+    else if (n == "pdl") weedcu_set_pdl(value != 0 ? 1 : 0);
     else throw std::invalid_argument("unknown config key");
     return 0;
   })
@@ -476,6 +477,7 @@ int wh_zero_grad(int64_t module) {
 namespace {
 void *g_comm = nullptr;
 int g_world = 1;
+bool g_dp_active = true;
 std::unique_ptr<GradientBuckets> g_buckets;
 } // namespace
 #endif
@@ -510,6 +512,18 @@ int wh_dp_init(const void *id128, int rank, int world) {
   return -1;
 #endif
 }
+// switch the gradient exchange off / on again for this process (bench.py --check-dp: rank 0 repeats the run alone on
+// the global batch); the 1/world gradient scale follows
+int wh_dp_set_active(int active) {
+#ifdef WEED_B200
+  g_dp_active = active != 0;
+  backend_config().grad_scale = (g_dp_active && g_comm && g_world > 1) ? ONE_R1 / (real1)g_world : ONE_R1;
+  return 0;
+#else
+  (void)active;
+  return -1;
+#endif
+}
 int wh_dp_broadcast_params(int64_t model) {
 #ifdef WEED_B200
   WH_TRY({
@@ -540,17 +554,22 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
     const auto t2 = now();
     const std::vector<ParameterPtr> params = m->parameters();
+    bool chained = false;
 #ifdef WEED_B200
     // data parallel: bucketed gradient all-reduce on a communication stream, overlapped with the
     // rest of the backward walk (WH_DP_OVERLAP=0: one grouped all-reduce after backward)
     static const bool overlap = !(getenv("WH_DP_OVERLAP") && atoi(getenv("WH_DP_OVERLAP")) == 0);
-    const bool dp = g_comm && g_world > 1;
+    const bool dp = g_comm && g_world > 1 && g_dp_active;
     if (dp && overlap) {
       if (!g_buckets) {
         const char *bb = getenv("WH_DP_BUCKET_BYTES");
         g_buckets.reset(bb ? new GradientBuckets(g_comm, (size_t)atoll(bb)) : new GradientBuckets(g_comm));
       }
-      g_buckets->begin();
+      // WH_DP_CHAIN_ADAM=0: all-reduce only; the optimiser runs after the last bucket as one launch
+      static const bool chain = !(getenv("WH_DP_CHAIN_ADAM") && atoi(getenv("WH_DP_CHAIN_ADAM")) == 0);
+      chained = chain;
+      if (chain) g_buckets->begin(*g_adams.at(opt), params);
+      else g_buckets->begin();
     }
 #endif
     Tensor::backward(loss);
@@ -560,7 +579,7 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     else if (dp) allreduce_gradients(params, g_comm);
 #endif
     const auto t4 = now();
-    adam_step(*g_adams.at(opt), params);
+    if (!chained) adam_step(*g_adams.at(opt), params);
     const auto t5 = now();
     zero_grad(params);
     m->reset_cache();

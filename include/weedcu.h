@@ -82,6 +82,10 @@ int weedcu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int weedcu_launch_count(uint64_t *count);   /* kernels launched by this library so far */
+/* Programmatic dependent launch between consecutive kernels of this library on one stream (on by default; env WEEDCU_PDL=0).
+ * on = 0 / 1 sets it for the launches that follow; on < 0 only queries. Returns the previous setting. No reference
+ * counterpart: the reference's FIFO waits on the host per launch (src/devices/gpu_device.cpp:296-305). */
+int weedcu_set_pdl(int on);
 int weedcu_host_stats(double *malloc_ms, uint64_t *mallocs, double *free_ms, uint64_t *frees);
 
 /* ------------------------------------------------------------------ F1 fills

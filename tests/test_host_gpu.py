@@ -608,3 +608,216 @@ def test_cow_gradients_change_nothing(P):
         assert np.max(np.abs(l0 - l1) / np.abs(l0)) <= 1e-6
         for a, b in zip(p0, p1):
             assert np.mean(np.abs(a - b)) <= 1e-6 and np.max(np.abs(a - b)) <= 4e-3
+
+
+# ------------------------------------------------------------------------------------ round 2: parity at B > 1
+def test_view_of_graph_tensor_keeps_owner_alive(P, R):
+    """A view copy (transpose / reshape) of a tensor that has a grad_node must keep that tensor alive: the node's
+    closure reaches its output weakly, and when only the view survived the whole upstream gradient used to be
+    dropped silently. mean(transpose(relu(w * x))) with the relu handle freed, against the reference."""
+    outs = []
+    for H in (R, P):
+        if H is P:
+            set_mode(P, 1)
+        w = H.tensor([1.0, -2.0, 3.0, 4.0], [2, 2], True)
+        x = H.tensor([1.0, 2.0, 3.0, 4.0], [2, 2])
+        r = H.op("relu", [H.op("mul", [w, x])])
+        t = H.op("transpose", [r])
+        H.free(r)
+        H.backward(H.op("mean", [t]))
+        outs.append(H.read_storage(H.grad(w)).copy())
+        H.reset()
+    assert np.abs(outs[0]).max() > 0
+    assert np.array_equal(outs[0], outs[1]), outs
+
+
+def _token_model(H, cfg, seed):
+    mods = [H.module("embedding", cfg["V"], cfg["d"]), H.module("posenc", cfg["T"], cfg["d"])]
+    mods += [H.module("encoder", cfg["d"], cfg["H"], cfg["dff"]) for _ in range(cfg["L"])]
+    mods += [H.module("layernorm", cfg["d"]), H.module("linear", cfg["d"], cfg["V"], 1)]
+    model = H.module("sequential", *mods)
+    return model, H.init_params(model, seed)
+
+
+def _token_model_grads(P, cfg, B, seed, precision):
+    """forward + fused cross-entropy + backward of the token model in the product's default (fused) mode"""
+    import fp64_model as F
+    set_mode(P, 1, precision=precision)
+    rng = np.random.default_rng(seed)
+    tokens = rng.integers(0, cfg["V"], size=(B, cfg["T"])).astype(np.int32)
+    targets = rng.integers(0, cfg["V"], size=(B, cfg["T"])).astype(np.int32)
+    model, weights = _token_model(P, cfg, seed + 1)
+    tok = P.symbol(F.uncol(tokens), [B, cfg["T"]])
+    tgt = P.symbol(F.uncol(targets), [B, cfg["T"]])
+    logits = P.forward_symbol(model, tok)
+    loss = P.cross_entropy(logits, tgt)
+    P.backward(loss)
+    got_loss = float(P.read(loss)[0])
+    got_logits = F.col(P.read(logits), [B, cfg["T"], cfg["V"]])
+    grads = []
+    for i in range(P.param_count(model)):
+        g = P.grad(P.param(model, i))
+        grads.append(P.read_storage(g).astype(np.float64) if g else None)
+    P.reset()
+    set_mode(P, 1)
+    return tokens, targets, weights, got_loss, got_logits, grads
+
+
+def _compare_with_arbiter(cfg, tokens, targets, weights, got_loss, got_logits, grads, bf16, tol_loss, tol, tol_deep=None):
+    import fp64_model as F
+    loss, logits, ref_grads = F.token_model(weights, cfg, tokens, targets, bf16=bf16)
+    assert abs(got_loss - loss) <= tol_loss * abs(loss), (got_loss, loss)
+    worst = {"logits": cases.rel_err(got_logits, logits)}
+    assert worst["logits"] <= tol, worst
+    n_checked = 0
+    for i, (g, r) in enumerate(zip(grads, ref_grads)):
+        r = np.asarray(r).ravel()
+        if g is None or g.size != r.size:  # parameters no gradient reaches keep an un-reduced all-zero gradient
+            assert not np.any(r) and (g is None or not np.any(g)), f"param {i}"
+            continue
+        if not np.any(r):
+            assert not np.any(g), f"param {i}: the arbiter's gradient is zero (no grad through the attention core)"
+            continue
+        worst[f"g{i}"] = cases.rel_err(g, r)
+        n_checked += 1
+    # gradients at the far end of the chain (embedding, positions, all layers but the last) have passed through
+    # 2 LayerNorm backwards per layer, whose reference chain carries a rounding-level sum_f(xc) term (D3): fp32
+    # rounding alone reaches ~2.7e-5 there on the serial oracle, so they get tol_deep
+    first_shallow = 2 + 16 * (cfg["L"] - 1)
+    bad = {k: v for k, v in worst.items() if v > (tol if (k == "logits" or int(k[1:]) >= first_shallow or tol_deep is None) else tol_deep)}
+    assert not bad, bad
+    assert n_checked >= 8 + 10 * cfg["L"] // 2
+    return worst
+
+
+def test_token_model_fused_fp32_matches_fp64_arbiter_B3(P):
+    """The benchmarked configuration's code path (fused LayerNorm / attention / GELU / cross-entropy / GEMM-accumulate,
+    intended indexing) at B > 1, where the reference itself cannot run (D1, D5): forward logits, loss and EVERY
+    parameter gradient against the independent fp64 numpy restatement (tests/fp64_model.py), <= 2e-5 rel-to-max (5e-5 for the gradients behind the last layer)."""
+    cfg = dict(V=96, d=32, H=4, dff=64, L=2, T=16)
+    run = _token_model_grads(P, cfg, 3, 6100, precision=0)
+    _compare_with_arbiter(cfg, *run, bf16=False, tol_loss=1e-6, tol=2e-5, tol_deep=5e-5)
+
+
+def test_token_model_fused_bf16_matches_fp64_bf16_arbiter_B4(P):
+    """Same at tensor-core-eligible shapes in the bf16 mode bench.py runs (flash attention, operand shadows, deferred
+    values, residual / bias epilogues, split-K): against the fp64 restatement with bf16-rounded GEMM operands.
+    Bound: 1e-2 rel-to-max per tensor (2.5 bf16 ulps), loss 1e-4. Two correct bf16 implementations do not agree better
+    than ~3e-3: the model rounds the attention probabilities against the final row maximum, the kernel against a running
+    one, and every later operand whose fp32 value moved by 1e-4 has a ~2 % chance of rounding to the other bf16
+    neighbour (measured worst 4.0e-3 on the oracle-backed mock, loss 1.5e-6)."""
+    cfg = dict(V=1000, d=128, H=2, dff=512, L=2, T=128)
+    run = _token_model_grads(P, cfg, 4, 6200, precision=1)
+    _compare_with_arbiter(cfg, *run, bf16=True, tol_loss=1e-4, tol=1e-2)
+
+
+def test_encoder_layer_fused_matches_fp64_arbiter_B4(P):
+    """One TransformerEncoderLayer forward + backward (loss = sum(y * w)) at B = 4 in the default fused mode against the
+    fp64 arbiter (the reference permutes LayerNorm's row statistics for B > 1, reduce.cpp:17-31)."""
+    import fp64_model as F
+    B, T, d, Hh = 4, 12, 16, 2
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, size=(B, T, d)).astype(np.float32)
+    w = rng.uniform(-1, 1, size=(B, T, d)).astype(np.float32)
+    set_mode(P, 1)
+    enc = P.module("encoder", d, Hh, 2 * d)
+    weights = P.init_params(enc, 11)
+    xt = P.tensor(F.uncol(x), [B, T, d], True)
+    wt = P.tensor(F.uncol(w), [B, T, d])
+    y = P.forward(enc, xt)
+    P.backward(P.op("sum", [P.op("mul", [y, wt])]))
+    got_y = F.col(P.read(y), [B, T, d])
+    grads = [P.read_storage(P.grad(P.param(enc, i))).astype(np.float64) for i in range(P.param_count(enc))]
+    P.reset()
+    p = F.encoder_params(weights, d, 2 * d)
+    ops = F.Ops(False)
+    ref_y, cache = F.encoder_fwd(ops, x.astype(np.float64), p, Hh)
+    _, ref_g = F.encoder_bwd(ops, w.astype(np.float64), p, cache)
+    assert cases.rel_err(got_y, ref_y) <= 2e-5
+    for i, k in enumerate(F.ENC_PARAMS):
+        r = F.uncol(ref_g[k]) if ref_g[k].ndim == 2 else ref_g[k]
+        if grads[i].size != r.size or not np.any(r):
+            assert not np.any(grads[i]) and not np.any(r), k
+            continue
+        assert cases.rel_err(grads[i], r) <= 2e-5, (k, cases.rel_err(grads[i], r))
+
+
+def test_config_c2_tabular_mlp_full_rows_matches_reference(P, R):
+    """Config C2 at its stated size: x[65536, 13], Linear(13,26)-Tanh-Linear(26,1), bci_with_logits_loss,
+    Adam lr 1e-3, 20 fixed steps — loss trajectory and final parameters against the compiled reference CPU build."""
+    set_mode(P, 1)
+    rng = np.random.default_rng(1003)
+    rows = 65536
+    x = rng.uniform(-1, 1, size=(rows, 13)).astype(np.float32)
+    y = (rng.uniform(size=rows) > 0.5).astype(np.float32)
+    a, pa = train_mlp(R, x, y, [13, 26, 1], 20, 1e-3)
+    b, pb = train_mlp(P, x, y, [13, 26, 1], 20, 1e-3)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-3, (a[-3:], b[-3:])
+    for u, v in zip(pa, pb):
+        assert cases.rel_err(v, u) <= 1e-3
+
+
+def transformer_losses_scaled(H, B, T, V, d, heads, dff, steps, seed):
+    """transformer_losses() with every dimension of the C4 scale-up as a parameter"""
+    rng = np.random.default_rng(seed)
+    tokens = rng.integers(0, V, size=(B, T)).astype(np.int32)
+    tlen = T // 2
+    target = (rng.uniform(size=(B, tlen)) > 0.5).astype(np.float32)
+    model = H.module("sequential", H.module("embedding", V, d), H.module("posenc", T, d), H.module("encoder", d, heads, dff),
+                     H.module("linear", d, 1, 1))
+    H.init_params(model, seed + 1)
+    opt = H.adam(model, 1e-3)
+    tok = H.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
+    tgt = H.tensor(np.ascontiguousarray(target.T).ravel(), [B, tlen])
+    losses = []
+    for _ in range(steps):
+        logits = H.forward_symbol(model, tok)
+        H.squeeze(logits, 2)
+        pred = H.op("slice", [logits], ints=[1, T - tlen, tlen])
+        loss = H.op("bci_with_logits_loss", [pred, tgt])
+        H.backward(loss)
+        H.adam_step(opt, model)
+        losses.append(float(np.sum(H.read(loss))))
+        H.zero_grad(model)
+        H.module_set(model, "reset_cache", 1)
+    H.reset()
+    return np.array(losses)
+
+
+def test_config_c4_scaled_dims_B1_matches_reference(P, R):
+    """Config C4 at the scaled-up dimensions of SURVEY §8(d) (vocab 512, d 512, 8 heads, d_ff 2048, T 128) with B = 1 —
+    the batch size at which the reference is self-consistent — in the DEFAULT fused mode, fp32 GEMMs: 3 Adam steps,
+    loss within 1e-3 relative of the compiled reference CPU build."""
+    a = transformer_losses_scaled(R, 1, 128, 512, 512, 8, 2048, 3, 50)
+    set_mode(P, 1)
+    b = transformer_losses_scaled(P, 1, 128, 512, 512, 8, 2048, 3, 50)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-3, (a, b)
+
+
+def test_pdl_on_off_same_losses_12_layers(P):
+    """Programmatic dependent launch is a pure scheduling change: 10 Adam steps of a 12-layer token model give the same
+    loss trajectory with WEEDCU_PDL off and on (round 1 found a trigger-before-wait order that drifted the loss by
+    7e-4 by eye; this pins it). Bound 2e-5: split-K reduce-adds and the embedding scatter use float atomics, so two
+    runs are equal only up to summation order."""
+    cfg = dict(V=1000, d=128, H=2, dff=512, L=12, T=128, B=4)
+    import bench
+
+    def run(pdl):
+        set_mode(P, 1, precision=1)
+        P.config("pdl", pdl)
+        model, _ = bench.build_model(P, cfg)
+        opt = P.adam(model, 1e-3)
+        tok, tgt = bench.make_tokens(cfg, 3000)
+        st, sg = P.symbol(tok, [cfg["B"], cfg["T"]]), P.symbol(tgt, [cfg["B"], cfg["T"]])
+        out = [float(P.read(P.train_step_tokens(model, opt, st, sg))[0]) for _ in range(10)]
+        P.reset()
+        return np.array(out)
+
+    try:
+        off, on, on2 = run(0), run(1), run(1)
+    finally:
+        P.config("pdl", 1)
+        set_mode(P, 1)
+    assert np.all(np.isfinite(off)) and off[-1] < off[0]
+    assert np.max(np.abs(on - off) / np.abs(off)) <= 2e-5, (off, on)
+    assert np.max(np.abs(on2 - on) / np.abs(on)) <= 2e-5, (on, on2)

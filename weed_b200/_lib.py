@@ -80,7 +80,7 @@ weedcu_default_stream weedcu_set_default_stream weedcu_stream_create weedcu_stre
 weedcu_stream_sync weedcu_stream_wait_event weedcu_event_create weedcu_event_destroy
 weedcu_event_record weedcu_event_sync weedcu_event_elapsed_ms weedcu_malloc weedcu_free weedcu_pool_trim
 weedcu_mem_info weedcu_host_alloc weedcu_host_free weedcu_memcpy_h2d weedcu_memcpy_d2h
-weedcu_memcpy_d2d weedcu_launch_count weedcu_host_stats weedcu_fill_real weedcu_fill_int weedcu_binary_real
+weedcu_memcpy_d2d weedcu_launch_count weedcu_set_pdl weedcu_host_stats weedcu_fill_real weedcu_fill_int weedcu_binary_real
 weedcu_inplace_real weedcu_copy_real weedcu_unary_real weedcu_unary_grad_real weedcu_reduce_real
 weedcu_reduce_grad_real weedcu_sum_real weedcu_softmax_real weedcu_softmax_grad_real
 weedcu_attn_softmax_real weedcu_attention_fwd weedcu_attention_fwd_bf16out weedcu_attention_decode weedcu_matmul_skinny weedcu_matmul_skinny_grouped weedcu_matmul_skinny_residual weedcu_cross_entropy_fwd weedcu_cross_entropy_bwd weedcu_cross_entropy_bwd_pack weedcu_layernorm_fwd weedcu_layernorm_fwd_bf16 weedcu_gelu_fwd_bf16 weedcu_gelu_grad_pack

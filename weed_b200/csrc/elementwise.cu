@@ -573,10 +573,16 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
   if (!count) return 0;
   if (!p || !g || !m || !v || !n) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
-  // chunk table, kept on the device between calls while the parameter list does not change
-  static std::vector<AdamChunk> host_table;
-  static AdamChunk *dev_table = nullptr;
-  static size_t dev_capacity = 0;
+  // Chunk tables stay on the device between calls, keyed by (stream, contents): a training step that updates its
+  // parameters bucket by bucket (data parallel: one launch per reduced gradient bucket, on the communication stream)
+  // re-uses one cached table per bucket, and two optimisers / devices / streams never share one. Only a table seen
+  // for the first time is uploaded (one blocking copy from pageable memory).
+  struct CachedTable {
+    cudaStream_t stream;
+    std::vector<AdamChunk> host;
+    AdamChunk *dev;
+  };
+  static std::vector<CachedTable> cache; // most recently used last
   static std::mutex table_mutex;
   std::lock_guard<std::mutex> lock(table_mutex);
   std::vector<AdamChunk> table;
@@ -593,25 +599,33 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
     if (sh) shadowed += (double)n[t];
   }
   if (table.empty()) return 0;
-  const bool same = table.size() == host_table.size() &&
-                    memcmp(table.data(), host_table.data(), table.size() * sizeof(AdamChunk)) == 0;
-  if (!same) {
-    if (table.size() > dev_capacity) {
-      if (dev_table) pool_free(dev_table, st);
-      dev_table = nullptr;
-      dev_capacity = 0;
-      WCU_CHECK(pool_alloc((void **)&dev_table, table.size() * sizeof(AdamChunk), st));
-      dev_capacity = table.size();
+  size_t hit = cache.size();
+  for (size_t i = 0; i < cache.size(); ++i)
+    if (cache[i].stream == st && cache[i].host.size() == table.size() &&
+        memcmp(cache[i].host.data(), table.data(), table.size() * sizeof(AdamChunk)) == 0) {
+      hit = i;
+      break;
     }
-    host_table.swap(table); // the async copy reads host_table, which outlives it
+  if (hit == cache.size()) {
+    if (cache.size() >= 64) { // oldest entry goes back to the pool on the stream it was used on
+      pool_free(cache.front().dev, cache.front().stream);
+      cache.erase(cache.begin());
+    }
+    CachedTable e{st, std::move(table), nullptr};
+    WCU_CHECK(pool_alloc((void **)&e.dev, e.host.size() * sizeof(AdamChunk), st));
     note_stream_op();
-    WCU_CHECK(cudaMemcpyAsync(dev_table, host_table.data(), host_table.size() * sizeof(AdamChunk),
-                              cudaMemcpyHostToDevice, st));
+    WCU_CHECK(cudaMemcpyAsync(e.dev, e.host.data(), e.host.size() * sizeof(AdamChunk), cudaMemcpyHostToDevice, st));
     WCU_CHECK(cudaStreamSynchronize(st)); // pageable source: make the staging copy complete
+    cache.push_back(std::move(e));
+  } else if (hit + 1 != cache.size()) {
+    CachedTable e = std::move(cache[hit]);
+    cache.erase(cache.begin() + (long)hit);
+    cache.push_back(std::move(e));
   }
+  const CachedTable &use = cache.back();
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
   ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total + 2.0 * shadowed);
-  launch_k(adam_multi_kernel, dim3((unsigned)host_table.size()), dim3(256), 0, st, dev_table, a);
+  launch_k(adam_multi_kernel, dim3((unsigned)use.host.size()), dim3(256), 0, st, use.dev, a);
   return after_launch();
 }
 

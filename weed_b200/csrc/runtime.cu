@@ -232,8 +232,9 @@ void pool_release_cached_locked() {
 }
 } // namespace
 
+static int g_pdl_on = -1;
 bool pdl_enabled() {
-  static int on = -1;
+  int &on = g_pdl_on;
   if (on < 0) {
     // on by default (WEEDCU_PDL=0 launches plainly). History: with launch_dependents issued BEFORE griddepcontrol.wait,
     // not-yet-started kernels piled up behind one another (a chain fill -> cross-entropy backward read a stale value,
@@ -411,6 +412,14 @@ int weedcu_prof_read(int cls, double *total_ms, uint64_t *launches, double *work
     *work += p.work;
   }
   return 0;
+}
+int weedcu_set_pdl(int on) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  if (on >= 0) {
+    g_pdl_on = on ? 1 : 0;
+    note_stream_op(); // the next launch starts a fresh chain
+  }
+  return prev;
 }
 int weedcu_launch_count(uint64_t *count) {
   if (!count) return WEEDCU_EINVAL;

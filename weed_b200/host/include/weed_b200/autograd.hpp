@@ -22,6 +22,21 @@ struct Adam {
   }
 };
 void adam_step(Adam &opt, const std::vector<ParameterPtr> &params);
+// adam_step in pieces, for callers that update parameters group by group within one step (GradientBuckets):
+//   adam_begin_step (t += 1, this step's bias corrections) ; per group: adam_collect -> adam_launch ; adam_slow for the
+//   parameters adam_collect hands back because the fused multi-tensor kernel cannot take them
+struct AdamBatch {
+  std::vector<real1 *> p, m, v;
+  std::vector<const real1 *> g;
+  std::vector<uint64_t> n;
+  std::vector<uint16_t *> shadow;
+  std::vector<std::pair<StoragePtr, BufferPtr>> refreshed; // (parameter storage, shadow buffer) rewritten by the launch
+  void *stream = nullptr;
+};
+void adam_begin_step(Adam &opt, real1 &bias_correction1, real1 &bias_correction2);
+void adam_collect(Adam &opt, const std::vector<ParameterPtr> &params, AdamBatch &batch, std::vector<ParameterPtr> &slow);
+void adam_launch(Adam &opt, AdamBatch &batch, real1 bias_correction1, real1 bias_correction2, void *stream);
+void adam_slow(Adam &opt, const ParameterPtr &p, real1 bias_correction1, real1 bias_correction2);
 void sgd_step(const std::vector<ParameterPtr> &params, real1 lr);
 void zero_grad(const std::vector<ParameterPtr> &params);
 
@@ -40,7 +55,9 @@ void allreduce_gradients(const std::vector<ParameterPtr> &params, void *comm);
 // ~bucket_bytes in the order they become final (Tensor::backward's on_leaf_grad_final hook: LM head
 // first, embeddings last) and every full bucket is all-reduced as one NCCL group on a dedicated
 // communication stream while the compute stream carries on with the remaining backward kernels.
-//   GradientBuckets gb(comm);  gb.begin();  Tensor::backward(loss);  gb.finish(params);
+//   GradientBuckets gb(comm);  gb.begin();  Tensor::backward(loss);  gb.finish(params);  adam_step(opt, params);
+// or, with the optimiser chained onto the buckets:
+//   gb.begin(opt, params);  Tensor::backward(loss);  gb.finish(params);
 // finish() reduces what is left (including gradients no node touched on this rank but may have on
 // another), and makes the compute stream wait for the communication stream.
 struct GradientBuckets {
@@ -51,9 +68,17 @@ struct GradientBuckets {
   size_t pending_bytes = 0U;
   std::unordered_set<Tensor *> reduced;
   uint64_t buckets_launched = 0U;
+  // chained optimiser (begin(opt, params)): each bucket's parameters are updated by the fused Adam kernel on the
+  // communication stream right behind the bucket's all-reduce, so only the last bucket's update is left on the
+  // critical path; finish() then replaces adam_step for this step
+  Adam *chained = nullptr;
+  real1 bc1 = ONE_R1, bc2 = ONE_R1;
+  std::unordered_map<Tensor *, ParameterPtr> owners;
+  std::vector<ParameterPtr> slow;
   explicit GradientBuckets(void *c, size_t bytes = 32U << 20);
   ~GradientBuckets();
   void begin();
+  void begin(Adam &opt, const std::vector<ParameterPtr> &params);
   void add(Tensor *leaf);
   void flush();
   void finish(const std::vector<ParameterPtr> &params);

@@ -106,6 +106,8 @@ struct BackendConfig {
 BackendConfig &backend_config();
 
 void throw_on_error(int rc, const char *what);
+// an autograd closure found its output tensor destroyed (only possible for a stack copy of a graph tensor): never silent
+[[noreturn]] void node_owner_lost();
 
 // ---------------------------------------------------------------------------------------------
 // Device layer (reference include/devices/gpu_device.hpp, include/common/oclengine.hpp)
@@ -437,10 +439,14 @@ typedef std::shared_ptr<Tensor> TensorPtr;
 
 #define SCALAR(v, o) std::make_shared<Weed::Tensor>(v, false, o->storage->device, o->storage->get_device_id())
 
-struct Tensor : public BaseTensor {
+struct Tensor : public BaseTensor, public std::enable_shared_from_this<Tensor> {
   NodePtr grad_node;
   TensorPtr grad;
   bool requires_grad = false;
+  // A copy of a tensor that has a grad_node (reshape / transpose / flatten / operator[] / chunk views) shares that node, and
+  // the node's closure reaches its output through a weak pointer (a strong one would be a cycle, DESIGN.md defect D7). The
+  // copy therefore keeps the node's owner alive: if only the view survives, backward still finds the output tensor.
+  TensorPtr view_owner;
   // how many autograd Nodes list this tensor as a parent (= how many gradient contributions it will
   // receive); a non-leaf with exactly one lets Tensor::add's backward hand it the incoming gradient
   // buffer instead of a copy (tensor.cpp: adopt_incoming_gradient)
@@ -461,6 +467,16 @@ struct Tensor : public BaseTensor {
     grad_node = cp.grad_node;
     grad = cp.grad;
     requires_grad = cp.requires_grad;
+    view_owner = nullptr;
+    if (cp.grad_node && &cp != this) view_owner = cp.view_owner ? cp.view_owner : cp.owner_ptr();
+  }
+  // shared_ptr to this tensor when it is owned by one (null for a stack object)
+  TensorPtr owner_ptr() const {
+    try {
+      return std::const_pointer_cast<Tensor>(shared_from_this());
+    } catch (const std::bad_weak_ptr &) {
+      return nullptr;
+    }
   }
   static TensorPtr clone(const TensorPtr &a);
   void make_gradient(const bool &force_sparse = false);

@@ -34,65 +34,88 @@ void Adam::register_parameter(ParameterPtr p) {
   state[p] = s;
 }
 
-void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
+void adam_begin_step(Adam &opt, real1 &bias_correction1, real1 &bias_correction2) {
   opt.t += 1;
-  const real1 bias_correction1 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta1, (real1_s)opt.t));
-  const real1 bias_correction2 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta2, (real1_s)opt.t));
+  bias_correction1 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta1, (real1_s)opt.t));
+  bias_correction2 = (real1)(ONE_R1 - std::pow((real1_s)opt.beta2, (real1_s)opt.t));
+}
+
+// fused path: every eligible parameter joins ONE multi-tensor launch (28 B/param; adam.hpp:84-104 issues ~15 ops and
+// ~12 temporaries per parameter). Collecting takes the device pointers — which may issue pending lazy zero fills on
+// the compute stream — so it is separate from the launch: the data-parallel path collects before it hands a bucket
+// to the communication stream and launches there after the all-reduce.
+void adam_collect(Adam &opt, const std::vector<ParameterPtr> &params, AdamBatch &b, std::vector<ParameterPtr> &slow) {
   const BackendConfig &cfg = backend_config();
-  // fused path: every eligible parameter joins ONE multi-tensor launch (28 B/param; adam.hpp:84-104
-  // issues ~15 ops and ~12 temporaries per parameter)
-  std::vector<real1 *> mp, mm, mv;
-  std::vector<const real1 *> mg;
-  std::vector<uint64_t> mn;
-  // bf16 GEMM operand shadow of a weight that is a plain linear copy of the parameter (dense, leading
-  // dimension a multiple of 8): the update kernel refreshes it in the same pass
-  std::vector<uint16_t *> msh;
-  std::vector<std::pair<GpuRealStorage *, size_t>> refreshed;
-  void *mstream = nullptr;
   for (auto &p : params) {
     const auto it = opt.state.find(p);
     if (it == opt.state.end()) throw std::invalid_argument("Parameter passed to adam_step that was not registered with optimizer!");
     AdamState &s = it->second;
     TensorPtr g = p->grad;
     if (!g) throw std::invalid_argument("adam_step: parameter has no gradient");
-    if (cfg.fused && flat_pair(*p, *g) && s.m->storage->size == p->storage->size && s.v->storage->size == p->storage->size) {
-      if (mstream && mstream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
-      mstream = p->stream();
-      mp.push_back(p->device_ptr());
-      uint16_t *sh = nullptr;
-      if (cfg.operand_cache && cfg.matmul_precision == WEEDCU_GEMM_BF16) {
-        GpuRealStorage *ps = static_cast<GpuRealStorage *>(p->storage.get());
-        for (size_t k = 0U; k < ps->shadows.size() && !sh; ++k) {
-          const GpuRealStorage::Bf16Shadow &c = ps->shadows[k];
-          if (c.offset == 0U && c.s_fast == 1U && c.s_slow == c.n_fast && (c.n_fast % 8U) == 0U && (uint64_t)c.n_fast * c.n_slow == ps->size) {
-            sh = (uint16_t *)c.buf->ptr;
-            refreshed.push_back({ps, k});
-          }
-        }
-      }
-      msh.push_back(sh);
-      // a gradient still waiting for its lazy zero-fill was never touched by backward: pass "zeros"
-      GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
-      mg.push_back(gs->zero_pending ? nullptr : g->device_ptr_ro());
-      mm.push_back(s.m->device_ptr());
-      mv.push_back(s.v->device_ptr());
-      mn.push_back(p->storage->size);
+    if (!(cfg.fused && flat_pair(*p, *g) && s.m->storage->size == p->storage->size && s.v->storage->size == p->storage->size)) {
+      slow.push_back(p);
       continue;
     }
-    if (cfg.grad_scale != ONE_R1) g = cfg.grad_scale * g;
-    s.m = opt.beta1 * s.m + (ONE_R1 - opt.beta1) * g;
-    s.v = opt.beta2 * s.v + (ONE_R1 - opt.beta2) * g * g;
-    TensorPtr tmp = opt.lr * s.m / (bias_correction1 * (((s.v / bias_correction2) ^ ((real1)0.5)) + opt.eps));
-    p->match_shape(tmp);
-    tmp->match_shape(p);
-    Weed::sub_in_place(*p, *tmp);
+    if (b.stream && b.stream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
+    b.stream = p->stream();
+    b.p.push_back(p->device_ptr());
+    // bf16 GEMM operand shadow of a weight that is a plain linear copy of the parameter (dense, leading
+    // dimension a multiple of 8): the update kernel refreshes it in the same pass
+    uint16_t *sh = nullptr;
+    if (cfg.operand_cache && cfg.matmul_precision == WEEDCU_GEMM_BF16) {
+      GpuRealStorage *ps = static_cast<GpuRealStorage *>(p->storage.get());
+      for (size_t k = 0U; k < ps->shadows.size() && !sh; ++k) {
+        const GpuRealStorage::Bf16Shadow &c = ps->shadows[k];
+        if (c.offset == 0U && c.s_fast == 1U && c.s_slow == c.n_fast && (c.n_fast % 8U) == 0U && (uint64_t)c.n_fast * c.n_slow == ps->size) {
+          sh = (uint16_t *)c.buf->ptr;
+          b.refreshed.push_back({p->storage, c.buf});
+        }
+      }
+    }
+    b.shadow.push_back(sh);
+    // a gradient still waiting for its lazy zero-fill was never touched by backward: pass "zeros"
+    GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
+    b.g.push_back(gs->zero_pending ? nullptr : g->device_ptr_ro());
+    b.m.push_back(s.m->device_ptr());
+    b.v.push_back(s.v->device_ptr());
+    b.n.push_back(p->storage->size);
   }
-  if (!mp.empty())
-    throw_on_error(weedcu_adam_step_multi_shadow((uint32_t)mp.size(), mp.data(), mg.data(), mm.data(), mv.data(), mn.data(), msh.data(), opt.lr,
-                                                 opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2, cfg.grad_scale, mstream),
-                   "adam_step");
-  // the shadows written by the kernel describe the parameter as it is now (device_ptr() above moved the version)
-  for (const auto &r : refreshed) r.first->shadows[r.second].version = r.first->version;
+}
+void adam_launch(Adam &opt, AdamBatch &b, real1 bias_correction1, real1 bias_correction2, void *stream) {
+  if (b.p.empty()) return;
+  throw_on_error(weedcu_adam_step_multi_shadow((uint32_t)b.p.size(), b.p.data(), b.g.data(), b.m.data(), b.v.data(), b.n.data(), b.shadow.data(),
+                                               opt.lr, opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2,
+                                               backend_config().grad_scale, stream ? stream : b.stream),
+                 "adam_step");
+  // the shadows written by the kernel describe the parameter as it is now (device_ptr() in adam_collect moved the version)
+  for (const auto &r : b.refreshed) {
+    GpuRealStorage *ps = static_cast<GpuRealStorage *>(r.first.get());
+    for (GpuRealStorage::Bf16Shadow &c : ps->shadows)
+      if (c.buf == r.second) c.version = ps->version;
+  }
+}
+// the reference's composition (adam.hpp:84-104), one parameter
+void adam_slow(Adam &opt, const ParameterPtr &p, real1 bias_correction1, real1 bias_correction2) {
+  const BackendConfig &cfg = backend_config();
+  AdamState &s = opt.state.at(p);
+  TensorPtr g = p->grad;
+  if (cfg.grad_scale != ONE_R1) g = cfg.grad_scale * g;
+  s.m = opt.beta1 * s.m + (ONE_R1 - opt.beta1) * g;
+  s.v = opt.beta2 * s.v + (ONE_R1 - opt.beta2) * g * g;
+  TensorPtr tmp = opt.lr * s.m / (bias_correction1 * (((s.v / bias_correction2) ^ ((real1)0.5)) + opt.eps));
+  p->match_shape(tmp);
+  tmp->match_shape(p);
+  Weed::sub_in_place(*p, *tmp);
+}
+
+void adam_step(Adam &opt, const std::vector<ParameterPtr> &params) {
+  real1 bc1, bc2;
+  adam_begin_step(opt, bc1, bc2);
+  AdamBatch batch;
+  std::vector<ParameterPtr> slow;
+  adam_collect(opt, params, batch, slow);
+  for (const ParameterPtr &p : slow) adam_slow(opt, p, bc1, bc2);
+  adam_launch(opt, batch, bc1, bc2, nullptr);
 }
 
 void sgd_step(const std::vector<ParameterPtr> &params, real1 lr) {
@@ -141,7 +164,7 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
       loss->make_gradient();
       loss->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{logits}, [logits, tg, lse, wloss = std::weak_ptr<Tensor>(loss), rows, V, vs]() {
         TensorPtr loss = wloss.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-        if (!loss) return;
+        if (!loss) node_owner_lost();
         TensorPtr dl = std::make_shared<Tensor>(*(logits->grad));
         if (vs == rows && Tensor::is_contiguous(dl->shape, dl->stride) && dl->storage->device == DeviceTag::GPU &&
             Weed::cross_entropy_bwd_pack(*logits, *tg, *lse, *(loss->grad), *dl, rows, V)) {
@@ -203,8 +226,17 @@ void GradientBuckets::begin() {
   reduced.clear();
   backend_config().on_leaf_grad_final = [this](Tensor *leaf) { add(leaf); };
 }
+void GradientBuckets::begin(Adam &opt, const std::vector<ParameterPtr> &params) {
+  begin();
+  chained = &opt;
+  owners.clear();
+  slow.clear();
+  for (const ParameterPtr &p : params) owners[p.get()] = p;
+  adam_begin_step(opt, bc1, bc2);
+}
 void GradientBuckets::add(Tensor *leaf) {
   if (!leaf->grad || reduced.count(leaf)) return;
+  if (chained && !owners.count(leaf)) return; // not one of the optimiser's parameters: nothing to exchange for it
   reduced.insert(leaf);
   pending.push_back(leaf);
   pending_bytes += (size_t)leaf->grad->storage->size * sizeof(real1);
@@ -213,7 +245,8 @@ void GradientBuckets::add(Tensor *leaf) {
 void GradientBuckets::flush() {
   if (pending.empty()) return;
   // device_ptr() materialises a pending lazy zero fill on the compute stream, so take the pointers
-  // before the event that hands the bucket to the communication stream
+  // (the gradients' and, when the optimiser is chained, everything its update touches) before the
+  // event that hands the bucket to the communication stream
   std::vector<std::pair<real1 *, size_t>> bufs;
   void *compute = nullptr;
   for (Tensor *leaf : pending) {
@@ -221,11 +254,21 @@ void GradientBuckets::flush() {
     bufs.push_back({g.device_ptr(), (size_t)g.storage->size});
     compute = g.stream();
   }
+  AdamBatch batch;
+  if (chained) {
+    std::vector<ParameterPtr> ps;
+    for (Tensor *leaf : pending) ps.push_back(owners.at(leaf));
+    adam_collect(*chained, ps, batch, slow);
+  }
   throw_on_error(weedcu_event_record(ev_ready, compute), "GradientBuckets::flush");
   throw_on_error(weedcu_stream_wait_event(comm_stream, ev_ready), "GradientBuckets::flush");
   throw_on_error(weedcu_nccl_group_start(), "GradientBuckets::flush");
   for (const auto &b : bufs) throw_on_error(weedcu_nccl_allreduce_sum(comm, b.first, b.second, comm_stream), "GradientBuckets::flush");
   throw_on_error(weedcu_nccl_group_end(), "GradientBuckets::flush");
+  // bucket reduced -> its parameters are updated right behind it on the communication stream, while the compute
+  // stream carries on with the rest of backward (SURVEY 8e "fusion opportunity"): a parameter is only read by the
+  // nodes that list it as a parent, and all of those were issued before ev_ready
+  if (chained) adam_launch(*chained, batch, bc1, bc2, comm_stream);
   ++buckets_launched;
   pending.clear();
   pending_bytes = 0U;
@@ -233,6 +276,7 @@ void GradientBuckets::flush() {
 void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
   backend_config().on_leaf_grad_final = nullptr;
   void *compute = nullptr;
+  std::vector<ParameterPtr> untouched;
   for (const ParameterPtr &p : params) {
     if (!p->grad) continue;
     compute = p->grad->stream();
@@ -240,15 +284,34 @@ void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
     // not reached by this rank's backward walk: still reduce it unless it is untouched everywhere
     // (same graph on every rank: a pending zero fill here means a pending zero fill there)
     Tensor &g = *(p->grad);
-    if (g.storage->device == DeviceTag::GPU && static_cast<GpuRealStorage *>(g.storage.get())->zero_pending) continue;
+    if (g.storage->device == DeviceTag::GPU && static_cast<GpuRealStorage *>(g.storage.get())->zero_pending) {
+      untouched.push_back(p);
+      continue;
+    }
     reduced.insert(p.get());
     pending.push_back(p.get());
     pending_bytes += (size_t)g.storage->size * sizeof(real1);
   }
   flush();
+  if (chained && !untouched.empty()) {
+    // zero gradients still decay the moments (adam.hpp:84-104): one more launch behind the last bucket
+    AdamBatch batch;
+    adam_collect(*chained, untouched, batch, slow);
+    if (compute) {
+      throw_on_error(weedcu_event_record(ev_ready, compute), "GradientBuckets::finish");
+      throw_on_error(weedcu_stream_wait_event(comm_stream, ev_ready), "GradientBuckets::finish");
+    }
+    adam_launch(*chained, batch, bc1, bc2, comm_stream);
+  }
   if (compute) {
     throw_on_error(weedcu_event_record(ev_done, comm_stream), "GradientBuckets::finish");
     throw_on_error(weedcu_stream_wait_event(compute, ev_done), "GradientBuckets::finish");
+  }
+  if (chained) {
+    for (const ParameterPtr &p : slow) adam_slow(*chained, p, bc1, bc2); // parameters the fused kernel cannot take: reference composition
+    chained = nullptr;
+    owners.clear();
+    slow.clear();
   }
 }
 void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root) {

@@ -31,6 +31,10 @@ BackendConfig &backend_config() {
 
 // Non-zero weedcu_* return -> the exception types the reference throws at the same points
 // (bad_alloc: include/devices/pool_item.hpp:32-40; runtime_error: gpu_device.cpp:137-178).
+void node_owner_lost() {
+  throw std::logic_error("autograd: the output tensor of a graph node was destroyed before backward reached it (a view of it "
+                         "outlived its owner without a shared_ptr; DESIGN.md defect D7)");
+}
 void throw_on_error(int rc, const char *what) {
   if (rc == 0) return;
   const std::string msg = std::string(what) + ": " + weedcu_error_string(rc);

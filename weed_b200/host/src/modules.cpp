@@ -141,7 +141,7 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
     y->make_gradient();
     y->grad_node = std::make_shared<Node>(parents, [x, g, b, wy = std::weak_ptr<Tensor>(y), mean, rstd, rows, F]() {
       TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-      if (!y) return;
+      if (!y) node_owner_lost();
       // one kernel: dx += ..., dgamma += sum_rows dy*xhat, dbeta += sum_rows dy (16 B/elem)
       TensorPtr dx, dg, db;
       if (x->requires_grad) {
@@ -205,7 +205,7 @@ TensorPtr Embedding::forward(const SymbolTensorPtr indices_) { // embedding.cpp:
     out->make_gradient();
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{w}, [indices, w, wout = std::weak_ptr<Tensor>(out)]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-      if (!out) return;
+      if (!out) node_owner_lost();
       TensorPtr dW = view_copy(w->grad);
       TensorPtr dout = view_copy(out->grad);
       dW->match_shape(w);

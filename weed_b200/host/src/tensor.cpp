@@ -259,7 +259,7 @@ TensorPtr Tensor::contiguous(const TensorPtr a) { // tensor.hpp:319-331 (zeros +
     out->make_gradient();
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-      if (!out) return;
+      if (!out) node_owner_lost();
       TensorPtr a_grad = view_copy(a->grad);
       TensorPtr out_grad = view_copy(out->grad);
       a_grad->match_shape(out_grad);
@@ -405,7 +405,7 @@ void Tensor::make_softmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, wout = std::weak_ptr<Tensor>(out), axis]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr x_grad = full_grad(x);
     Weed::softmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
     settle_grad(x, x_grad);
@@ -423,7 +423,7 @@ void Tensor::make_logsoftmax_node(TensorPtr x, TensorPtr out, symint axis) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, wout = std::weak_ptr<Tensor>(out), axis]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr x_grad = full_grad(x);
     Weed::logsoftmax_grad((tcapint)axis, *x_grad, *out, *(out->grad));
     settle_grad(x, x_grad);
@@ -444,7 +444,7 @@ void Tensor::make_row_slice_node(TensorPtr a, TensorPtr out, const tcapint &row)
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), row]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr keep = a_grad->grad; // slicing must not register new nodes
     const bool rg = a_grad->requires_grad;
@@ -471,7 +471,7 @@ void Tensor::make_slice_node(TensorPtr a, TensorPtr out, const int64_t &axis, co
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), axis, start]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     // reference: zero tmp of a's shape, add dout into the window, add tmp into a_grad
     // (tensor.cpp:528-553). Equivalent and one pass: add dout into the window of a_grad directly.
     TensorPtr a_grad = view_copy(a->grad);
@@ -500,7 +500,7 @@ void Tensor::make_sum_node(TensorPtr a, TensorPtr out) { // tensor.cpp:568-581: 
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr out_grad = view_copy(out->grad);
     out_grad->match_shape(a_grad);
@@ -519,7 +519,7 @@ void Tensor::make_mean_node(TensorPtr a, TensorPtr out) { // tensor.cpp:596-612:
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr a_grad = view_copy(a->grad);
     TensorPtr out_grad = view_copy(out->grad);
     out_grad->match_shape(a_grad);
@@ -556,7 +556,7 @@ void Tensor::make_sum_node(TensorPtr a, TensorPtr out, const tcapint &axis) { //
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), axis]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr dx = view_copy(a->grad);
     TensorPtr dy = view_copy(out->grad);
     if (dy->shape.size() < a->shape.size()) dy->unsqueeze(axis); // re-insert the reduced axis
@@ -595,7 +595,7 @@ TensorPtr unary_op(TensorPtr a, UnaryFwd fwd, UnaryBwd bwd, bool uses_output) {
     out->make_gradient();
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), bwd, uses_output]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-      if (!out) return;
+      if (!out) node_owner_lost();
       TensorPtr a_grad = full_grad(a);
       bwd(*a_grad, uses_output ? *out : *a, *(out->grad));
       settle_grad(a, a_grad);
@@ -615,7 +615,7 @@ TensorPtr Tensor::cos(TensorPtr a) { return unary_op(a, Weed::cos, Weed::cos_gra
     out->make_gradient();                                                                          \
     out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() { \
       TensorPtr out = wout.lock(); /* the node is owned by this tensor: a strong capture would be a cycle */ \
-      if (!out) return; \
+      if (!out) node_owner_lost(); \
       TensorPtr a_grad = full_grad(a);                                                             \
       bwd(*a_grad, *src, *(out->grad));                                                            \
       settle_grad(a, a_grad);                                                                      \
@@ -774,7 +774,7 @@ void Tensor::make_add_node(TensorPtr a, TensorPtr b, TensorPtr out) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad && !adopt_incoming_gradient(a, out_grad)) accumulate(a, out_grad, *out_grad, false);
     if (b->requires_grad && !adopt_incoming_gradient(b, out_grad)) accumulate(b, out_grad, *out_grad, false);
@@ -792,7 +792,7 @@ void Tensor::make_sub_node(TensorPtr a, TensorPtr b, TensorPtr out) {
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad) accumulate(a, out_grad, *out_grad, false);
     if (b->requires_grad) accumulate(b, out_grad, *out_grad, true);
@@ -810,7 +810,7 @@ void Tensor::make_mul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr out_grad = view_copy(out->grad);
     auto side = [&](const TensorPtr &p, const TensorPtr &other) {
       TensorPtr tmp = Tensor::allocate_like(out_grad->shape, *out_grad, DType::REAL, false, false);
@@ -833,7 +833,7 @@ void Tensor::make_div_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tensor.
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     TensorPtr out_grad = view_copy(out->grad);
     if (a->requires_grad) { // da += dout / b
       TensorPtr tmp = Tensor::allocate_like(out_grad->shape, *out_grad, DType::REAL, false, false);
@@ -861,7 +861,7 @@ void Tensor::make_pow_node(TensorPtr x, real1 p, TensorPtr y) { // tensor.cpp:15
   y->make_gradient();
   y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, p, wy = std::weak_ptr<Tensor>(y)]() {
     TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!y) return;
+    if (!y) node_owner_lost();
     TensorPtr dy = view_copy(y->grad);
     TensorPtr _x = view_copy(x), _y = view_copy(y);
     _y->match_shape(_x);
@@ -886,7 +886,7 @@ void Tensor::make_exp_node(TensorPtr x, real1 log_b, TensorPtr y) { // tensor.cp
   y->make_gradient();
   y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, log_b, wy = std::weak_ptr<Tensor>(y)]() {
     TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!y) return;
+    if (!y) node_owner_lost();
     TensorPtr dy = view_copy(y->grad);
     dy->match_shape(y);
     TensorPtr dy_v = SCALAR(log_b, dy) * dy;
@@ -906,7 +906,7 @@ void Tensor::make_log_node(TensorPtr x, real1 inv_log_b, TensorPtr y) { // tenso
   y->make_gradient();
   y->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{x}, [x, inv_log_b, wy = std::weak_ptr<Tensor>(y)]() {
     TensorPtr y = wy.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!y) return;
+    if (!y) node_owner_lost();
     TensorPtr dy = view_copy(y->grad);
     dy->match_shape(x);
     TensorPtr dy_v = SCALAR(inv_log_b, dy) * dy;
@@ -1022,7 +1022,7 @@ TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, Tensor
     if (residual) parents.push_back(residual);
     out->grad_node = std::make_shared<Node>(grad_parents(parents), [a, w, bias, residual, wout = std::weak_ptr<Tensor>(out)]() {
       TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-      if (!out) return;
+      if (!out) node_owner_lost();
       if (residual && residual->requires_grad) { // d(residual + y)/d residual = 1: what the add node of `x + Linear(...)` does
         TensorPtr out_grad = view_copy(out->grad);
         if (!adopt_incoming_gradient(residual, out_grad)) accumulate(residual, out_grad, *out_grad, false);
@@ -1091,7 +1091,7 @@ void Tensor::make_matmul_node(TensorPtr a, TensorPtr b, TensorPtr out) { // tens
   out->make_gradient();
   out->grad_node = std::make_shared<Node>(grad_parents({a, b}), [a, b, wout = std::weak_ptr<Tensor>(out)]() {
     TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
-    if (!out) return;
+    if (!out) node_owner_lost();
     matmul_backward(a, b, out);
   });
 }
