@@ -151,6 +151,13 @@ def pick_sample(budget_s, gflops=0.25):
     return best or dict(FULL, L=1, T=32, B=1, V=1024)
 
 
+def reference_budget(steps, warmup):
+    """Per-step CPU budget of the bounded reference sample: the driver's `--impl reference --steps K --warmup W` run has to
+    end within a few minutes, so the sample shrinks with K + W. cpu_baseline (one step inside our arm) uses the SAME
+    sample, so the record holds one CPU configuration, not two."""
+    return min(30.0, max(3.0, 150.0 / max(1, steps + warmup)))
+
+
 def cpu_baseline(cfg_full, steps=1, warmup=0, budget_s=20.0):
     small = pick_sample(budget_s)
     t, loss = reference_run(small, steps, warmup)
@@ -158,7 +165,8 @@ def cpu_baseline(cfg_full, steps=1, warmup=0, budget_s=20.0):
     return {"value": cfg_full["B"] / (t * ratio), "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
             "sample": (f"unmodified reference CPU build (oracle/_ref), 1 train step on L={small['L']} T={small['T']} B={small['B']} "
                        f"V={small['V']} d=768 dff=3072: {t:.2f} s/step measured ({step_flops(small) / t / 1e9:.2f} GFLOP/s, loss {loss:.3f}); "
-                       f"extrapolated x{ratio:.0f} by algorithmic FLOP to the full config; WEED_BLAS=OFF; par_for runs serial below "
+                       f"extrapolated x{ratio:.0f} by algorithmic FLOP to the full config (optimistic for the CPU: its step is dominated by "
+                       f"per-op overhead that grows with tokens, not FLOP); WEED_BLAS=OFF; par_for runs serial below "
                        f"2*2^18 items so most ops use 1 of the {os.cpu_count()} threads")}, t
 
 
@@ -167,8 +175,7 @@ def main_reference(args):
     if rank != 0:
         return 0
     cfg = dict(FULL)
-    budget = min(30.0, max(3.0, 150.0 / max(1, args.steps + args.warmup)))
-    small = pick_sample(budget)
+    small = pick_sample(reference_budget(args.steps, args.warmup))
     t, loss = reference_run(small, args.steps, args.warmup)
     ratio = step_flops(cfg) / step_flops(small)
     value = cfg["B"] / (t * ratio)
@@ -185,6 +192,101 @@ def main_reference(args):
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------------- parity legs
+def loss_trajectory(P, cfg, precision, steps, pdl=1, seed=2000, lr=1e-4):
+    """`steps` seeded training steps from the seeded initial weights; returns the loss of every step. Everything built
+    here is released again."""
+    mark = P.mark()
+    P.config("matmul_precision", precision)
+    P.config("pdl", pdl)
+    model, _ = build_model(P, cfg, seed)
+    opt = P.adam(model, lr)
+    out = []
+    for s in range(steps):
+        tok, tgt = make_tokens(cfg, 9000 + s)
+        st, sg = P.symbol(tok, [cfg["B"], cfg["T"]]), P.symbol(tgt, [cfg["B"], cfg["T"]])
+        h = P.train_step_tokens(model, opt, st, sg)
+        out.append(float(P.read(h)[0]))
+        for x in (h, st, sg):
+            P.free(x)
+    P.release_since(mark)
+    P.config("pdl", 1)
+    return out
+
+
+def parity_legs(P, cfg, steps=5):
+    """Full-shape correctness evidence for the configuration being timed (VERDICT r1 #1d/e): the bf16 tensor-core run
+    against the fp32 FpMath run of the same seeded steps, and programmatic dependent launch on against off."""
+    bf16 = loss_trajectory(P, cfg, GEMM_BF16, steps, pdl=1)
+    bf16_nopdl = loss_trajectory(P, cfg, GEMM_BF16, steps, pdl=0)
+    fp32 = loss_trajectory(P, cfg, GEMM_FP32, steps, pdl=1)
+    rel = lambda a, b: float(max(abs(x - y) / abs(y) for x, y in zip(a, b)))
+    return {"steps": steps, "loss_bf16": bf16, "loss_fp32": fp32, "loss_bf16_pdl_off": bf16_nopdl,
+            "loss_rel_diff_bf16_vs_fp32": rel(bf16, fp32), "bf16_loss_bound": BF16_LOSS_BOUND,
+            "within_bf16_bound": rel(bf16, fp32) <= BF16_LOSS_BOUND,
+            "loss_rel_diff_pdl_on_vs_off": rel(bf16, bf16_nopdl), "pdl_bound": 2e-5, "pdl_equal": rel(bf16, bf16_nopdl) <= 2e-5}
+
+
+# stated bf16 bound on the loss of the benchmarked configuration after 5 seeded steps (north_star: "a stated looser bound
+# for bf16"); measured on B200 in round 2: see profiles/README.md
+BF16_LOSS_BOUND = 2e-3
+
+
+# ----------------------------------------------------------------------------------- data-parallel equality
+def check_dp(P, args, cfg, rank, world, dist, torch):
+    """N ranks on a global batch of GB sequences (GB / N per rank, gradients all-reduced, Adam chained per bucket) against
+    ONE rank on the same GB sequences: per-step loss <= 1e-3 relative, parameter checksums <= 1e-5 relative."""
+    steps = 3
+    GB = args.batch * world if args.batch else 16
+    assert GB % world == 0
+    Bl = GB // world
+    gcfg, lcfg = dict(cfg, B=GB), dict(cfg, B=Bl)
+    T = cfg["T"]
+
+    def run(c, shard):
+        mark = P.mark()
+        model, n_params = build_model(P, c)
+        if shard is not None and world > 1:
+            assert P.lib.wh_dp_broadcast_params(C.c_int64(model)) == 0
+        opt = P.adam(model, 1e-4)
+        losses = []
+        for s in range(steps):
+            tok, tgt = make_tokens(gcfg, 11000 + s)
+            if shard is not None:
+                tok = np.ascontiguousarray(tok.reshape(T, GB)[:, shard * Bl:(shard + 1) * Bl]).ravel()
+                tgt = np.ascontiguousarray(tgt.reshape(T, GB)[:, shard * Bl:(shard + 1) * Bl]).ravel()
+            st, sg = P.symbol(tok, [c["B"], T]), P.symbol(tgt, [c["B"], T])
+            h = P.train_step_tokens(model, opt, st, sg)
+            losses.append(float(P.read(h)[0]))
+            for x in (h, st, sg):
+                P.free(x)
+        sums = []
+        for i in range(P.param_count(model)):
+            w = P.read_storage(P.param(model, i)).astype(np.float64)
+            sums.append((float(w.sum()), float(np.abs(w).sum()), float(np.abs(w).max())))
+        P.release_since(mark)
+        return losses, np.array(sums)
+
+    dp_losses, dp_sums = run(lcfg, rank)
+    t = torch.tensor(dp_losses, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)
+    dp_losses = (t / world).cpu().tolist()  # equal shards: the mean of the rank means is the global mean
+    result = None
+    if rank == 0:
+        P.lib.wh_dp_set_active(C.c_int(0))
+        one_losses, one_sums = run(gcfg, None)
+        P.lib.wh_dp_set_active(C.c_int(1))
+        loss_rel = float(max(abs(a - b) / abs(b) for a, b in zip(dp_losses, one_losses)))
+        # checksums: sum of values and sum of magnitudes per parameter, relative to the sum of magnitudes
+        chk = float(np.max(np.abs(dp_sums[:, :2] - one_sums[:, :2]) / np.maximum(one_sums[:, 1:2], 1e-30)))
+        result = {"check_dp": True, "n_gpus": world, "global_batch": GB, "batch_per_gpu": Bl, "steps": steps, "loss_dp": dp_losses,
+                  "loss_single": one_losses, "loss_rel_diff": loss_rel, "param_checksum_rel_diff": chk, "loss_bound": 1e-3,
+                  "checksum_bound": 1e-5, "ok": bool(loss_rel <= 1e-3 and chk <= 1e-5), "layers": cfg["L"], "vocab": cfg["V"],
+                  "seq_len": T, "adam_chained_per_bucket": os.environ.get("WH_DP_CHAIN_ADAM", "1") != "0"}
+    dist.barrier()
+    return result
 
 
 # ----------------------------------------------------------------------------------- our arm
@@ -233,6 +335,14 @@ def main_ours(args):
         dist.broadcast(uid, 0)
         host = (C.c_uint8 * 128)(*uid.cpu().tolist())
         assert P.lib.wh_dp_init(host, C.c_int(rank), C.c_int(world)) == 0, P.lib.wh_last_error()
+
+    if args.check_dp:
+        assert world > 1, "--check-dp compares N > 1 ranks against one rank: launch under torchrun"
+        res = check_dp(P, args, cfg, rank, world, dist, torch)
+        if rank == 0:
+            print(json.dumps(res))
+        dist.destroy_process_group()
+        return 0 if (rank != 0 or res["ok"]) else 1
 
     model, n_params = build_model(P, cfg)
     if world > 1:
@@ -428,9 +538,19 @@ def main_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu, _ = cpu_baseline(cfg)
+            cpu, _ = cpu_baseline(cfg, budget_s=reference_budget(args.steps, args.warmup))
         except Exception as e:  # the oracle build is optional on a box without oracle/_ref
             cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        P.free(st)
+        P.free(sg)
+        for a, b in pairs:
+            P.free(a)
+            P.free(b)
+        parity = parity_legs(P, cfg)
+        P.config("matmul_precision", precision)
 
     if rank == 0:
         line = {"metric": "train samples/s (GPT-2-small shape)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -442,7 +562,7 @@ def main_ours(args):
                            "loss": "fused cross-entropy", "gemm": "bf16 tcgen05 operands, fp32 accumulate/outputs" if precision == GEMM_BF16 else "fp32 FFMA",
                            "non_gemm": "fp32", "autograd": "reference semantics (batched attention products carry no grad, tensor.cpp:1253-1271)",
                            "l2": "working set >> 126 MB L2 (activations ~10 GB/step); no flush needed", "algorithmic_tflop_per_step": step_flops(cfg) / 1e12,
-                           "loss_first": first_loss, "loss_last": last_loss},
+                           "loss_first": first_loss, "loss_last": last_loss, "parity": parity},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 2 * ntok * 4, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(n1.value - n0.value), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -466,6 +586,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--vocab", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-shape bf16-vs-fp32 / PDL on-vs-off loss legs")
+    ap.add_argument("--check-dp", action="store_true",
+                    help="N ranks on a global batch vs one rank on the same batch (loss <= 1e-3, parameter checksum <= 1e-5)")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -29,6 +29,7 @@
 
 #include <chrono>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <string>
 
@@ -94,6 +95,19 @@ int wh_reset() {
   g_symbols.clear();
   g_modules.clear();
   g_adams.clear();
+  return 0;
+}
+// handle bookkeeping for callers that build several models in one process (bench.py's parity legs): everything created
+// since `mark` is dropped
+int64_t wh_mark() { return g_next; }
+int wh_release_since(int64_t mark) {
+  auto drop = [mark](auto &m) {
+    for (auto it = m.begin(); it != m.end();) it = (it->first >= mark) ? m.erase(it) : std::next(it);
+  };
+  drop(g_tensors);
+  drop(g_symbols);
+  drop(g_adams);
+  drop(g_modules);
   return 0;
 }
 int wh_free(int64_t h) {

@@ -129,6 +129,14 @@ class Harness:
     def reset(self):
         self.lib.wh_reset()
 
+    def mark(self):
+        self.lib.wh_mark.restype = C.c_int64
+        return self.lib.wh_mark()
+
+    def release_since(self, mark):
+        """Drop every tensor / symbol / module / optimiser handle created since mark()."""
+        self.lib.wh_release_since(C.c_int64(mark))
+
     def config(self, name, value):
         self._ck(self.lib.wh_config(name.encode(), C.c_double(value)))
 
