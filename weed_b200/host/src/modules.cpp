@@ -118,7 +118,12 @@ void LayerNorm::migrate_gpu() {
 TensorPtr LayerNorm::forward(const TensorPtr x) {
   const BackendConfig &cfg = backend_config();
   const size_t rank = x->shape.size();
-  const bool fusable = cfg.fused && !cfg.ref_index_quirks && x->storage->device == DeviceTag::GPU && rank >= 2U &&
+  // the reference's axis reduce permutes its outputs when two non-axis extents exceed 1 (defect D1); with at most one
+  // (B == 1, or rank 2) its indexing is the intended one and the fused kernels reproduce it in the faithful mode too
+  size_t wide = 0U;
+  for (size_t i = 0U; i + 1U < rank; ++i)
+    if (x->shape[i] > 1U) ++wide;
+  const bool fusable = cfg.fused && (!cfg.ref_index_quirks || wide <= 1U) && x->storage->device == DeviceTag::GPU && rank >= 2U &&
                        x->shape[rank - 1U] == features && dense_contiguous(*x) && gamma->storage->size == features &&
                        beta->storage->size == features;
   if (!fusable) { // the reference's composition, layernorm.cpp:29-42
@@ -199,6 +204,8 @@ TensorPtr Embedding::forward(const SymbolTensorPtr indices_) { // embedding.cpp:
   std::vector<tcapint> out_shape = indices->shape;
   out_shape.push_back(embedding_dim);
   TensorPtr out = Tensor::allocate_like(out_shape, Tensor::full_contiguous_stride(out_shape), *weight, DType::REAL, weight->requires_grad, false);
+  // faithful mode: with [1, T] indices the reference writes slot 0 only (D6) and the rest keeps the zero fill of its allocation
+  if (backend_config().ref_index_quirks) out->storage->FillZeros();
   Weed::embedding_gather(*indices, *weight, *out);
   if (weight->requires_grad) {
     ParameterPtr w = weight;

@@ -791,6 +791,7 @@ void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {
 // which is 0 when the leading extent is 1 (e.g. indices [1, T]) and then gathers token 0 only;
 // for dense tensors the flat token index has stride 1, which is what is meant.
 static tcapint flat_stride(const BaseTensor &t) {
+  if (backend_config().ref_index_quirks) return t.stride[0U]; // defect D6 reproduced: [1, T] indices read token 0 for every slot
   tcapint expect = 1U;
   bool dense = true;
   for (size_t i = 0U; i < t.shape.size(); ++i) {
@@ -801,6 +802,7 @@ static tcapint flat_stride(const BaseTensor &t) {
   return dense ? 1U : t.stride[0U];
 }
 static tcapint row_stride_of_rows(const BaseTensor &t) { // all dims but the last form the token index
+  if (backend_config().ref_index_quirks) return t.stride[0U]; // (and write every row to slot 0 when the leading extent is 1)
   BaseTensor lead;
   lead.shape.assign(t.shape.begin(), t.shape.end() - 1);
   lead.stride.assign(t.stride.begin(), t.stride.end() - 1);
