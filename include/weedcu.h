@@ -257,6 +257,14 @@ int weedcu_layernorm_fwd(const float *x, uint32_t rows, uint32_t F, const float 
 int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma,
                               const float *beta, float eps, float *y, float *mean, float *rstd,
                               uint16_t *y_bf16, void *stream);
+/* weedcu_layernorm_fwd_bf16 for an x whose row statistics already exist as per-column-tile partials (mean_t, M2_t) left by
+ * the epilogue of the GEMM that produced x (weedcu_gemm_bf16_ex, row_stats 1; tile t covers features
+ * [t * tile_cols, min(F, (t + 1) * tile_cols))): one pass over x instead of two. Same result as the two-pass kernel up to
+ * fp32 rounding of the merge (LayerNorm::forward, src/modules/layernorm.cpp:29-42). mean / rstd / y_bf16 may be NULL.
+ * WEEDCU_ENOSUP unless rows % 4 == 0 and the pointers are 16-byte aligned. */
+int weedcu_layernorm_fwd_stats(const float *x, uint32_t rows, uint32_t F, const float *stats, uint32_t tiles, uint32_t tile_cols,
+                               const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16,
+                               void *stream);
 /* dx += ..., dgamma[F] += sum_rows dy*xhat, dbeta[F] += sum_rows dy.
  * grad_mode 0 reproduces what the reference's autograd chain computes: its div node omits dout on
  *   the denominator branch (src/tensors/tensor.cpp:1506-1521), so the variance path contributes
@@ -379,6 +387,43 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
 int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
                               uint64_t ldb, float *c, uint64_t ldc, uint32_t M, uint32_t N, uint32_t K,
                               const float *col_bias, const float *residual, uint64_t ldr, void *stream);
+/* Extended epilogue of the tensor-core GEMM: everything the consumers of a Linear output read is left by the product's own
+ * epilogue, from the accumulator registers, instead of by extra passes over C.
+ *   c        fp32 output [M, N] column-major (leading dimension ldc), or NULL when only the bf16 copy is wanted
+ *   c_bf16   bf16 copy of the output [M, N] column-major (leading dimension ldc_bf16, a multiple of 8), or NULL: the GEMM
+ *            operand copy (Bf16 shadow) of C that the next Linear / the attention relayout reads
+ *   epi->col_bias, epi->residual / ldr: as weedcu_gemm_bf16 / weedcu_gemm_bf16_residual (Linear::forward's bias add,
+ *            src/modules/linear.cpp:86-100; the `x + Linear(...)` of transformer_encoder_layer.cpp:63-125)
+ *   epi->activation 1: c_bf16 = bf16(gelu(value)) while c keeps the pre-activation (Tensor::gelu, src/tensors/tensor.cpp:841-851,
+ *            of a value that is rounded to bf16 right after: hardware tanh, 2^-11 relative)
+ *   epi->row_stats 1: stats[t][m] = (mean, M2 = sum (x - mean)^2) of row m over the columns of column tile t — the partials of
+ *            LayerNorm::forward's two means (src/modules/layernorm.cpp:29-42), merged by weedcu_layernorm_fwd_stats
+ *   epi->row_stats 2: stats[t][m] = (max, sum exp(x - max)) of row m over tile t — the log-sum-exp partials of
+ *            cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34), merged by weedcu_cross_entropy_fwd_stats
+ *   *epi->stats_tiles / *epi->stats_tile_cols (host, written before the call returns): number of column tiles and their
+ *            width; tile t covers columns [t * cols, min(N, (t + 1) * cols)). stats holds stats_capacity_tiles * M * 2 floats
+ *            (>= ceil(N / 128) tiles is always enough).
+ * C is stored (no accumulate, no split-K). WEEDCU_ENOSUP when the outputs do not meet the TMA store rules. */
+typedef struct weedcu_gemm_epilogue {
+  const float *col_bias;
+  const float *residual;
+  uint64_t ldr;
+  int activation;
+  int row_stats;
+  float *stats;
+  uint32_t stats_capacity_tiles;
+  uint32_t *stats_tiles;
+  uint32_t *stats_tile_cols;
+} weedcu_gemm_epilogue;
+int weedcu_gemm_bf16_ex(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c,
+                        uint64_t ldc, uint16_t *c_bf16, uint64_t ldc_bf16, uint32_t M, uint32_t N, uint32_t K,
+                        const weedcu_gemm_epilogue *epi, void *stream);
+/* weedcu_gemm_bf16_grouped whose outputs leave the kernel as bf16 only (c_bf16[g]: [M, N] column-major, leading dimension
+ * ldc_bf16): the W_q / W_k / W_v projections, whose only reader is the attention core's head relayout
+ * (src/modules/multihead_attention.cpp:151-157). */
+int weedcu_gemm_bf16_grouped_bf16out(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b,
+                                     int b_major, uint64_t ldb, uint16_t *const *c_bf16, uint64_t ldc_bf16, uint32_t M, uint32_t N,
+                                     uint32_t K, const float *const *col_bias, void *stream);
 /* Tile family of the bf16 tensor-core GEMM: 0 = cost model over single-CTA 128 x N tiles and CTA-pair
  * (tcgen05 cta_group::2, two SMs of a TPC on one 256 x N tile) kernels (default; env WEEDCU_GEMM_MODE),
  * 1 = single-CTA tiles only, 2 = CTA pairs wherever the operands allow,

@@ -13,6 +13,7 @@ extern "C" {
 }
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -158,6 +159,11 @@ int weedcu_cross_entropy_fwd(const float *logits, uint64_t offset, uint32_t rows
 int weedcu_cross_entropy_bwd(const float *logits, uint64_t offset, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs, const int32_t *targets, const float *lse, const float *dloss,
                              float *dlogits, uint64_t d_offset, int accumulate, void *) {
   return RUN(wo_cross_entropy_bwd(logits, offset, rows, V, rs, vs, targets, lse, dloss, dlogits, d_offset, accumulate));
+}
+int weedcu_layernorm_fwd_stats(const float *x, uint32_t rows, uint32_t F, const float *stats, uint32_t tiles, uint32_t tile_cols, const float *gamma,
+                               const float *beta, float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16, void *stream) {
+  if (!stats || !tiles || (uint64_t)tiles * tile_cols < F || (rows % 4u)) return rows % 4u ? WEEDCU_ENOSUP : WEEDCU_EINVAL;
+  return weedcu_layernorm_fwd_bf16(x, rows, F, gamma, beta, eps, y, mean, rstd, y_bf16, stream); // the partials only save a pass
 }
 int weedcu_layernorm_fwd_bf16(const float *x, uint32_t rows, uint32_t F, const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16,
                               void *) {
@@ -308,6 +314,78 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
   if (!groups || groups > 3 || !b || !c) return WEEDCU_EINVAL;
   for (uint32_t g = 0; g < groups; ++g) {
     const int rc = weedcu_gemm_bf16(a, a_major, lda, b[g], b_major, ldb, c[g], ldc, M, N, K, accumulate, col_bias ? col_bias[g] : nullptr, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+// extended epilogue: the plain product, then every extra output from the fp32 values (column tiles of 256)
+int weedcu_gemm_bf16_ex(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint16_t *c_bf16,
+                        uint64_t ldc_bf16, uint32_t M, uint32_t N, uint32_t K, const weedcu_gemm_epilogue *epi, void *stream) {
+  if (!a || !b || (!c && !c_bf16)) return WEEDCU_EINVAL;
+  if (c_bf16 && (ldc_bf16 % 8)) return WEEDCU_ENOSUP;
+  if (c && (ldc % 4)) return WEEDCU_ENOSUP;
+  std::vector<float> tmp;
+  float *out = c;
+  uint64_t ld = ldc;
+  if (!out) {
+    tmp.resize((size_t)M * N);
+    out = tmp.data();
+    ld = M;
+  }
+  int rc = weedcu_gemm_bf16(a, a_major, lda, b, b_major, ldb, out, ld, M, N, K, 0, epi ? epi->col_bias : nullptr, stream);
+  if (rc || g_nocompute) return rc;
+  if (epi && epi->residual)
+    for (uint32_t n = 0; n < N; ++n)
+      for (uint32_t m = 0; m < M; ++m) out[m + (uint64_t)n * ld] = out[m + (uint64_t)n * ld] + epi->residual[m + (uint64_t)n * epi->ldr];
+  if (c_bf16) {
+    wo_view v;
+    memset(&v, 0, sizeof(v));
+    v.rank = 1;
+    v.shape[0] = M;
+    v.stride[0] = 1;
+    std::vector<float> col(M);
+    for (uint32_t n = 0; n < N; ++n) {
+      const float *src = out + (uint64_t)n * ld;
+      if (epi && epi->activation) {
+        wo_unary_real(7 /* GELU */, 0.0f, src, &v, col.data(), &v);
+        src = col.data();
+      }
+      for (uint32_t m = 0; m < M; ++m) c_bf16[m + (uint64_t)n * ldc_bf16] = wo_f32_to_bf16(src[m]);
+    }
+  }
+  if (epi && epi->row_stats) {
+    const uint32_t cols = 256, tiles = (N + cols - 1) / cols;
+    if (!epi->stats || tiles > epi->stats_capacity_tiles) return WEEDCU_EINVAL;
+    for (uint32_t t = 0; t < tiles; ++t) {
+      const uint32_t n0 = t * cols, n1 = (n0 + cols < N) ? n0 + cols : N;
+      for (uint32_t m = 0; m < M; ++m) {
+        double a0 = 0.0, a1 = 0.0;
+        if (epi->row_stats == 1) {
+          for (uint32_t n = n0; n < n1; ++n) a0 += out[m + (uint64_t)n * ld];
+          a0 /= (double)(n1 - n0);
+          for (uint32_t n = n0; n < n1; ++n) a1 += (out[m + (uint64_t)n * ld] - a0) * (out[m + (uint64_t)n * ld] - a0);
+        } else {
+          a0 = -1.0 / 0.0;
+          for (uint32_t n = n0; n < n1; ++n) a0 = out[m + (uint64_t)n * ld] > a0 ? out[m + (uint64_t)n * ld] : a0;
+          for (uint32_t n = n0; n < n1; ++n) a1 += exp((double)out[m + (uint64_t)n * ld] - a0);
+        }
+        epi->stats[2 * ((uint64_t)t * M + m)] = (float)a0;
+        epi->stats[2 * ((uint64_t)t * M + m) + 1] = (float)a1;
+      }
+    }
+    if (epi->stats_tiles) *epi->stats_tiles = tiles;
+    if (epi->stats_tile_cols) *epi->stats_tile_cols = tiles == 1 ? N : cols;
+  }
+  return 0;
+}
+int weedcu_gemm_bf16_grouped_bf16out(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b, int b_major, uint64_t ldb,
+                                     uint16_t *const *c_bf16, uint64_t ldc_bf16, uint32_t M, uint32_t N, uint32_t K, const float *const *col_bias, void *stream) {
+  if (!groups || groups > 3 || !b || !c_bf16) return WEEDCU_EINVAL;
+  for (uint32_t g = 0; g < groups; ++g) {
+    weedcu_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.col_bias = col_bias ? col_bias[g] : nullptr;
+    const int rc = weedcu_gemm_bf16_ex(a, a_major, lda, b[g], b_major, ldb, nullptr, 0, c_bf16[g], ldc_bf16, M, N, K, &e, stream);
     if (rc) return rc;
   }
   return 0;

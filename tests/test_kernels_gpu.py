@@ -313,3 +313,117 @@ def test_matmul_skinny_residual_equals_skinny_then_add(gpu, M, K, N, bias):
     gpu.call("matmul_skinny", ha, am, hb, bm, plain, cm, U32(M), U32(K), U32(N), hbias if bias else None, C.c_int(0))
     gpu.call("matmul_skinny_residual", ha, am, hb, bm, fused, cm, U32(M), U32(K), U32(N), hbias if bias else None, hres)
     assert np.array_equal(fused.get(), plain.get() + res)
+
+
+EX_SHAPES = [(8192, 768, 768), (1024, 520, 264), (388, 200, 96), (2048, 5003, 128)]
+
+
+def _merge_ln(stats, tiles, cols, N):
+    """Chan merge of per-tile (mean, M2) partials -> (mean, variance) per row, in fp64"""
+    n, mean, m2 = 0.0, 0.0, 0.0
+    for t in range(tiles):
+        cnt = min(N, (t + 1) * cols) - t * cols
+        mt, m2t = stats[t, :, 0].astype(np.float64), stats[t, :, 1].astype(np.float64)
+        tot = n + cnt
+        delta = mt - mean
+        mean = mean + delta * cnt / tot
+        m2 = m2 + m2t + delta * delta * n * cnt / tot
+        n = tot
+    return mean, m2 / N
+
+
+@pytest.mark.parametrize("mode", [0, 256001, 1256001, 1192001, 1128001])
+@pytest.mark.parametrize("M,N,K", EX_SHAPES)
+def test_gemm_bf16_ex_epilogue(gpu, M, N, K, mode):
+    """weedcu_gemm_bf16_ex: the extended epilogue of the tensor-core GEMM in every tile family.
+    (a) fp32 C + bias + residual + LayerNorm partials: C bit-identical to weedcu_gemm_bf16_residual, merged (mean, var) == numpy on C.
+    (b) bf16-only output + log-sum-exp partials: bf16 copy == RNE(bf16) of the plain product, merged lse == numpy.
+    (c) fp32 C + bf16 copy of gelu(C): C bit-identical, copy within 2 bf16 ulps of bf16(gelu(C)) (hardware tanh)."""
+    import ctypes as C
+    from weed_b200._lib import GemmEpilogue
+    rng = np.random.default_rng(M + N + K + 11)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, _ = _operand(rng, M, K, 1)
+    b_dev, ldb, _ = _operand(rng, N, K, 0)
+    res = rng.uniform(-3, 3, M * N).astype(np.float32)
+    bias = rng.uniform(-2, 2, N).astype(np.float32)
+    pa, pb, hres, hbias = gpu.buf(a_dev), gpu.buf(b_dev), gpu.buf(res), gpu.buf(bias)
+    plain, plain_res = gpu.buf(np.zeros(M * N, np.float32)), gpu.buf(np.zeros(M * N, np.float32))
+    cap = (N + 127) // 128
+    r8 = (M + 7) // 8 * 8
+    if M % 8:
+        pytest.skip("bf16 outputs need a leading dimension that is a multiple of 8 == M for a dense operand copy")
+    gpu.lib.weedcu_gemm_set_mode(C.c_int(mode))
+    try:
+        gpu.call("gemm_bf16", pa, I32(1), U64(lda), pb, I32(0), U64(ldb), plain, U64(M), U32(M), U32(N), U32(K), I32(0), hbias)
+        gpu.call("gemm_bf16_residual", pa, I32(1), U64(lda), pb, I32(0), U64(ldb), plain_res, U64(M), U32(M), U32(N), U32(K), hbias, hres, U64(M))
+        want, want_res = plain.get().reshape(N, M), plain_res.get().reshape(N, M)
+
+        def run(c, c16, **kw):
+            tiles, cols = U32(0), U32(0)
+            stats = gpu.buf(np.full(cap * M * 2, np.nan, np.float32))
+            e = GemmEpilogue(col_bias=hbias.ptr, residual=kw.get("residual", 0), ldr=M, activation=kw.get("act", 0), row_stats=kw.get("stats", 0),
+                             stats=stats.ptr, stats_capacity_tiles=cap, stats_tiles=C.pointer(tiles), stats_tile_cols=C.pointer(cols))
+            gpu.call("gemm_bf16_ex", pa, I32(1), U64(lda), pb, I32(0), U64(ldb), c, U64(M), c16, U64(r8), U32(M), U32(N), U32(K), e)
+            return stats.get().reshape(cap, M, 2), tiles.value, cols.value
+
+        # (a)
+        c = gpu.buf(np.full(M * N, 9.0, np.float32))
+        st, tiles, cols = run(c, None, residual=hres.ptr, stats=1)
+        assert np.array_equal(c.get().reshape(N, M), want_res)
+        assert tiles == (N + cols - 1) // cols and tiles <= cap
+        mean, var = _merge_ln(st, tiles, cols, N)
+        w64 = want_res.astype(np.float64)
+        assert np.max(np.abs(mean - w64.mean(0))) <= 1e-6 * np.abs(w64).max()
+        assert np.max(np.abs(var - w64.var(0)) / w64.var(0)) <= 1e-5
+        # (b)
+        c16 = gpu.buf(np.full(r8 * N, 0x7FC0, np.uint16))
+        st, tiles, cols = run(None, c16, stats=2)
+        assert np.array_equal(c16.get().reshape(N, r8)[:, :M], _bf16_bits(want))
+        mx = np.max(st[:tiles, :, 0], axis=0).astype(np.float64)
+        ssum = np.sum(st[:tiles, :, 1].astype(np.float64) * np.exp(st[:tiles, :, 0].astype(np.float64) - mx[None, :]), axis=0)
+        lse = mx + np.log(ssum)
+        w64 = want.astype(np.float64)
+        ref_lse = w64.max(0) + np.log(np.exp(w64 - w64.max(0)[None, :]).sum(0))
+        assert np.max(np.abs(lse - ref_lse)) <= 2e-6 * np.abs(ref_lse).max()
+        # (c)
+        c = gpu.buf(np.full(M * N, 9.0, np.float32))
+        c16 = gpu.buf(np.full(r8 * N, 0x7FC0, np.uint16))
+        run(c, c16, act=1)
+        assert np.array_equal(c.get().reshape(N, M), want)
+        x = want.astype(np.float64)
+        g = 0.5 * x * (1.0 + np.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+        got = _bf16_widen(c16.get().reshape(N, r8)[:, :M]).astype(np.float64)
+        assert np.max(np.abs(got - g) / np.maximum(np.abs(g), 0.25)) <= 2 ** -7   # 2 ulps of bf16 (ulp = 2^-8 relative), floor at 0.25
+    finally:
+        gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
+
+
+@pytest.mark.parametrize("mode", [0, 256001, 1256001, 1128001])
+@pytest.mark.parametrize("M,N,K,groups", [(8192, 768, 768, 3), (1024, 136, 256, 2)])
+def test_gemm_bf16_grouped_bf16out(gpu, M, N, K, groups, mode):
+    """weedcu_gemm_bf16_grouped_bf16out == RNE(bf16) of weedcu_gemm_bf16_grouped's fp32 outputs, bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K + groups + 5)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, _ = _operand(rng, M, K, 1)
+    pa = gpu.buf(a_dev)
+    pbs, biases, f32, b16 = [], [], [], []
+    ldb = None
+    for g in range(groups):
+        b_dev, ldb, _ = _operand(rng, N, K, 0)
+        pbs.append(gpu.buf(b_dev))
+        biases.append(gpu.buf(rng.uniform(-2, 2, N).astype(np.float32)))
+        f32.append(gpu.buf(np.zeros(M * N, np.float32)))
+        b16.append(gpu.buf(np.full(M * N, 0x7FC0, np.uint16)))
+    PtrArr = C.c_void_p * groups
+    gpu.lib.weedcu_gemm_set_mode(C.c_int(mode))
+    try:
+        gpu.call("gemm_bf16_grouped", pa, I32(1), U64(lda), U32(groups), PtrArr(*[p.ptr for p in pbs]), I32(0), U64(ldb),
+                 PtrArr(*[c.ptr for c in f32]), U64(M), U32(M), U32(N), U32(K), I32(0), PtrArr(*[b.ptr for b in biases]))
+        gpu.call("gemm_bf16_grouped_bf16out", pa, I32(1), U64(lda), U32(groups), PtrArr(*[p.ptr for p in pbs]), I32(0), U64(ldb),
+                 PtrArr(*[c.ptr for c in b16]), U64(M), U32(M), U32(N), U32(K), PtrArr(*[b.ptr for b in biases]))
+        for g in range(groups):
+            assert np.array_equal(b16[g].get(), _bf16_bits(f32[g].get())), f"group {g}"
+    finally:
+        gpu.lib.weedcu_gemm_set_mode(C.c_int(0))

@@ -40,7 +40,91 @@ struct Params {
   uint32_t groups, tiles_n_group;
   float *c_grp[3];
   const float *bias_grp[3];
+  // extended epilogue (weedcu_gemm_bf16_ex); all zero = the plain fp32 epilogue above.
+  // out_mode 0: fp32 C. 1: bf16 only — C is not written, the staging buffers and the C tensor maps carry bf16 (the operand
+  // copy the next GEMM / relayout reads). 2: fp32 C through the staging buffers + a bf16 copy stored directly.
+  // act 1: the bf16 copy holds gelu(value) (C keeps the pre-activation the GELU backward needs).
+  // stats_kind 1: per row, (mean, M2) of this tile's columns (LayerNorm partials, merged by the consumer);
+  // stats_kind 2: per row, (max, sum exp(x - max)) of this tile's columns (log-sum-exp partials of the cross-entropy).
+  int out_mode, act, stats_kind;
+  __nv_bfloat16 *c16;
+  uint64_t ldc16;
+  float2 *row_stats; // [tiles_n][M]
 };
+
+// per-thread running row statistics across the 32-column chunks of one tile
+struct RowStats {
+  float a, b, n;
+};
+__device__ __forceinline__ void row_stats_update(int kind, RowStats &s, const uint32_t (&r)[32], uint32_t valid) {
+  if (valid == 0) return;
+  if (kind == 1) { // Chan's parallel update with this chunk's (count, mean, M2)
+    float sum = 0.0f;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) sum += (j < valid) ? __uint_as_float(r[j]) : 0.0f;
+    const float cnt = (float)valid, mean_c = sum / cnt;
+    float m2 = 0.0f;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+      const float d = __uint_as_float(r[j]) - mean_c;
+      m2 += (j < valid) ? d * d : 0.0f;
+    }
+    const float n = s.n + cnt, delta = mean_c - s.a;
+    s.a += delta * (cnt / n);
+    s.b += m2 + delta * delta * (s.n * cnt / n);
+    s.n = n;
+  } else { // online (max, sum exp)
+    float mx = -INFINITY;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) mx = fmaxf(mx, (j < valid) ? __uint_as_float(r[j]) : -INFINITY);
+    if (mx > s.a) {
+      s.b *= __expf(s.a - mx);
+      s.a = mx;
+    }
+    float e = 0.0f;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) e += (j < valid) ? __expf(__uint_as_float(r[j]) - s.a) : 0.0f;
+    s.b += e;
+    s.n += (float)valid;
+  }
+}
+// Tensor::gelu (reference src/tensors/tensor.cpp:841-851) for a value that is rounded to bf16 right after: MUFU tanh
+// (2^-11 relative) instead of the ~40-instruction tanhf — the four epilogue warps have one issue slot each
+__device__ __forceinline__ float gelu_for_bf16(float x) {
+  const float k1 = 0.044715f, k2 = 0.7978845608028654f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k2 * (x + k1 * (x * x) * x)));
+  return (0.5f * x) * (1.0f + t);
+}
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+// what the extended epilogue does with one finished chunk (bias / residual already added): statistics, then either the
+// bf16 staging tile (out_mode 1; returns true: the fp32 staging store is skipped) or the direct bf16 copy (out_mode 2)
+__device__ __forceinline__ bool epilogue_ext_chunk(const Params &p, const uint32_t (&r)[32], RowStats &rs, uint32_t m, uint32_t n_chunk0,
+                                                   uint32_t z, uint32_t buf, uint32_t row_in_tile) {
+  const uint32_t valid = n_chunk0 < p.N ? min(32u, p.N - n_chunk0) : 0u;
+  if (p.stats_kind) row_stats_update(p.stats_kind, rs, r, valid);
+  if (p.out_mode == 1) {
+    const uint32_t dst = buf + row_in_tile * 2;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+      const float v = __uint_as_float(r[j]);
+      st_shared_b16(dst + j * (BLOCK_M * 2), __bfloat16_as_ushort(__float2bfloat16_rn(p.act ? gelu_for_bf16(v) : v)));
+    }
+    return true;
+  }
+  if (p.out_mode == 2 && m < p.M) {
+    __nv_bfloat16 *d16 = p.c16 + (uint64_t)z * p.c_bs + m + (uint64_t)n_chunk0 * p.ldc16;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+      const float v = __uint_as_float(r[j]);
+      if (j < valid) d16[(uint64_t)j * p.ldc16] = __float2bfloat16_rn(p.act ? gelu_for_bf16(v) : v);
+    }
+  }
+  return false;
+}
+
 constexpr uint32_t kMaxGroups = 3;
 struct alignas(64) TensorMaps {
   CUtensorMap m[kMaxGroups];
@@ -254,6 +338,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
       };
       if (has_res) load_res(0);
+      const bool ext = (p.out_mode | p.stats_kind) != 0;
+      RowStats rs = {p.stats_kind == 2 ? -INFINITY : 0.0f, 0.0f, 0.0f};
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (p.tma_store) {
@@ -283,13 +369,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           mbar_wait(eempty_bar(eb), ((epi_chunk / EPI_BUFS) & 1u) ^ 1u); // the store that last used `buf` has read it
-          const uint32_t dst = buf + (q * 32 + lane) * 4;
+          if (!ext || !epilogue_ext_chunk(p, r, rs, m, n0 + c0, z, buf, q * 32 + lane)) {
+            const uint32_t dst = buf + (q * 32 + lane) * 4;
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+            for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+          }
           fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(efull_bar(eb));
         }
+        if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)tn * p.M + m] = make_float2(rs.a, rs.b);
       } else {
         float *crow = c_base + (uint64_t)z * p.c_bs + m;
         const bool full_tile = (m0 + BLOCK_M <= p.M) && (n0 + BLOCK_N <= p.N);
@@ -531,6 +620,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
       };
       if (has_res) load_res(0);
+      const bool ext = (p.out_mode | p.stats_kind) != 0;
+      RowStats rs = {p.stats_kind == 2 ? -INFINITY : 0.0f, 0.0f, 0.0f};
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -556,13 +647,16 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
         }
         mbar_wait(eempty_bar(eb), ((epi_chunk / EPI_BUFS) & 1u) ^ 1u);
-        const uint32_t dst = buf + (q * 32 + lane) * 4;
+        if (!ext || !epilogue_ext_chunk(p, r, rs, m, n0 + c0, z, buf, q * 32 + lane)) {
+          const uint32_t dst = buf + (q * 32 + lane) * 4;
 #pragma unroll
-        for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+          for (uint32_t j = 0; j < 32; ++j) st_shared_f32(dst + j * (BLOCK_M * 4), r[j]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(efull_bar(eb));
       }
+      if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)tn * p.M + m] = make_float2(rs.a, rs.b);
     }
   }
   tcgen05_fence_before();
@@ -645,6 +739,18 @@ static bool make_c_map(CUtensorMap *map, float *c, uint64_t M, uint64_t N, uint6
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the same box over a bf16 C (out_mode 1): the staging tile is [32 cols][128 rows] of 2-byte elements
+static bool make_c16_map(CUtensorMap *map, uint16_t *c, uint64_t M, uint64_t N, uint64_t ldc, uint64_t batch, uint64_t c_bs) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  if ((((uintptr_t)c) & 15u) || (ldc % 8) || (batch > 1 && (c_bs % 8))) return false;
+  cuuint64_t dims[3] = {M, N, batch};
+  cuuint64_t strides[2] = {ldc * 2, (batch > 1 ? c_bs : ldc * N) * 2};
+  cuuint32_t box[3] = {BLOCK_M, EPI_COLS, 1}, estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)c, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS>
 static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
                       int b_major, cudaStream_t st) {
@@ -709,6 +815,8 @@ static int gemm_mode() {
 }
 void set_gemm_mode(int mode) { g_gemm_mode = mode < 0 ? 0 : mode; }
 
+static int g_last_block_n = 0; // tile width of the most recent launch (reported with the row statistics)
+int last_block_n() { return g_last_block_n; }
 struct TileCfg {
   int pair;
   uint32_t bn, splits;
@@ -747,21 +855,40 @@ static double tile_cost_us(const TileCfg &c, uint32_t tiles_m128, uint32_t N, ui
 // `groups` (<= 3) products A x B_g -> C_g (+ bias_g) that share the A operand and every dimension run
 // as ONE launch: their tiles join one persistent tile loop, so the ~10 us of per-launch prologue /
 // exposed last epilogue is paid once and the tail wave is filled by the other groups' tiles.
+// extended epilogue of one launch (see Params): c16[g] = bf16 output of group g
+struct EpiExt {
+  int out_mode = 0, act = 0, stats_kind = 0;
+  uint16_t *c16[kMaxGroups] = {nullptr, nullptr, nullptr};
+  uint64_t ldc16 = 0;
+  float *row_stats = nullptr;
+  uint32_t stats_capacity_tiles = 0, *stats_tiles = nullptr;
+};
 int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint64_t a_bs, uint32_t groups,
                              const uint16_t *const *b, int b_major, uint64_t ldb, uint64_t b_bs, float *const *c, uint64_t ldc,
                              uint64_t c_bs, uint32_t M, uint32_t N, uint32_t K, uint32_t batch, int accumulate, cudaStream_t st,
-                             const float *const *col_bias, const float *residual, uint64_t ldr) {
-  if (!a || !b || !c || !M || !N || !K || !batch || !groups || groups > kMaxGroups) return WEEDCU_EINVAL;
+                             const float *const *col_bias, const float *residual, uint64_t ldr, const EpiExt *ext = nullptr) {
+  if (!a || !b || !M || !N || !K || !batch || !groups || groups > kMaxGroups) return WEEDCU_EINVAL;
+  const bool bf16_only = ext && ext->out_mode == 1;
+  if (!c && !bf16_only) return WEEDCU_EINVAL;
   if (residual && (groups != 1 || batch != 1 || accumulate)) return WEEDCU_EINVAL;
+  if (ext) {
+    if (accumulate || batch != 1) return WEEDCU_EINVAL;
+    if ((ext->stats_kind || ext->out_mode == 2) && groups != 1) return WEEDCU_EINVAL;
+    if (ext->out_mode && (ext->ldc16 % 8)) return WEEDCU_ENOSUP;
+    for (uint32_t g = 0; g < groups; ++g)
+      if (ext->out_mode && (!ext->c16[g] || (((uintptr_t)ext->c16[g]) & 15u))) return WEEDCU_EINVAL;
+    if (ext->stats_kind && (!ext->row_stats || !ext->stats_tiles)) return WEEDCU_EINVAL;
+  }
   for (uint32_t g = 0; g < groups; ++g)
-    if (!b[g] || !c[g]) return WEEDCU_EINVAL;
+    if (!b[g] || (!bf16_only && !c[g])) return WEEDCU_EINVAL;
   // Tile family, tile width and split-K are chosen together by the cost model above. Few-tile
   // problems (weight gradients: M, N = layer widths, K = batch*seq) get split along K, slices
   // meeting in C by TMA reduce-add; tile counts just above a multiple of the slot count get a
   // narrower tile instead of a nearly empty last wave.
   const uint32_t num_kb = (K + BLOCK_K - 1) / BLOCK_K, tiles_m128 = (M + BLOCK_M - 1) / BLOCK_M;
-  bool c_tma = (ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0);
-  for (uint32_t g = 0; g < groups; ++g) c_tma = c_tma && (((uintptr_t)c[g]) & 15u) == 0;
+  bool c_tma = bf16_only || ((ldc % 4) == 0 && (batch == 1 || (c_bs % 4) == 0));
+  for (uint32_t g = 0; g < groups && !bf16_only; ++g) c_tma = c_tma && (((uintptr_t)c[g]) & 15u) == 0;
+  if (ext && !c_tma) return WEEDCU_ENOSUP; // the extended epilogue lives in the staged (TMA) path only
   const int mode = gemm_mode();
   TileCfg best = {0, 256, 1, 0};
   if (mode >= 1000) {
@@ -782,7 +909,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
         if (bn > 128 && N <= bn - 64) continue; // do not pad a narrow N into a wide tile
         if (pair && bn == 192 && b_major) continue;
         for (uint32_t sp = 1; sp <= 16; ++sp) {
-          if (sp > 1 && (!c_tma || sp * 4u > num_kb)) break;
+          if (sp > 1 && (!c_tma || ext || sp * 4u > num_kb)) break; // (statistics / converted outputs need whole dot products)
           const TileCfg cfg = {pair, bn, sp, 0};
           const double cost = tile_cost_us(cfg, tiles_m128, N, num_kb, groups, batch, accumulate, (uint64_t)M * N * groups * batch);
           if (cost < best_cost) {
@@ -794,15 +921,24 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
     }
   }
   const uint32_t block_n = best.bn;
+  g_last_block_n = (int)block_n;
   uint32_t best_s = best.splits;
   const uint32_t tiles_m = best.pair ? (tiles_m128 + 1) / 2 : tiles_m128;
   CUtensorMap tmA;
   TensorMaps tmBs, tmCs;
   int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
   if (rc) return rc;
+  if (ext && ext->stats_kind && (N + block_n - 1) / block_n > ext->stats_capacity_tiles) return WEEDCU_EINVAL;
+  if (ext) best_s = 1;
   Params p;
-  p.c = c[0];
+  p.c = bf16_only ? nullptr : c[0];
   p.ldc = ldc;
+  p.out_mode = ext ? ext->out_mode : 0;
+  p.act = ext ? ext->act : 0;
+  p.stats_kind = ext ? ext->stats_kind : 0;
+  p.c16 = ext ? (__nv_bfloat16 *)ext->c16[0] : nullptr;
+  p.ldc16 = ext ? ext->ldc16 : 0;
+  p.row_stats = ext ? (float2 *)ext->row_stats : nullptr;
   p.c_bs = c_bs;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.tiles_m = tiles_m;
@@ -818,12 +954,16 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
     const uint32_t src = g < groups ? g : 0;
     rc = make_operand_map(&tmBs.m[g], b[src], b_major, N, K, ldb, batch, b_bs, best.pair ? block_n / 2 : block_n);
     if (rc) return rc;
-    if (p.tma_store && !make_c_map(&tmCs.m[g], c[src], M, N, ldc, batch, c_bs)) p.tma_store = 0;
-    p.c_grp[g] = c[src];
+    if (bf16_only) {
+      if (!make_c16_map(&tmCs.m[g], ext->c16[src], M, N, ext->ldc16, batch, c_bs)) return WEEDCU_ENOSUP;
+    } else if (p.tma_store && !make_c_map(&tmCs.m[g], c[src], M, N, ldc, batch, c_bs))
+      p.tma_store = 0;
+    p.c_grp[g] = bf16_only ? nullptr : c[src];
     p.bias_grp[g] = col_bias ? col_bias[src] : nullptr;
   }
-  if (best.variant == 1 && !best.pair) p.tma_store = 0;
-  if (!p.tma_store && residual) return WEEDCU_ENOSUP; // the residual add lives in the staged epilogue only
+  if (best.variant == 1 && !best.pair && !ext) p.tma_store = 0;
+  if (!p.tma_store && (residual || ext)) return WEEDCU_ENOSUP; // the residual add / extended epilogue live in the staged epilogue only
+  if (ext && ext->stats_tiles) *ext->stats_tiles = p.tiles_n;
   if (!p.tma_store) {
     if (best.pair) return WEEDCU_ENOSUP; // unreachable: pairs are only chosen when C meets the TMA rules
     for (uint32_t g = 0; g < kMaxGroups; ++g) tmCs.m[g] = tmA; // unused by the kernel, but must be valid descriptors
@@ -1012,6 +1152,49 @@ int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, cons
   const float *biases[1] = {col_bias};
   return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, 1, bs, b_major, ldb, 0, cs, ldc, 0, M, N, K, 1, 0, resolve_stream(stream),
                                       col_bias ? biases : nullptr, residual, ldr);
+}
+
+int weedcu_gemm_bf16_ex(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c,
+                        uint64_t ldc, uint16_t *c_bf16, uint64_t ldc_bf16, uint32_t M, uint32_t N, uint32_t K,
+                        const weedcu_gemm_epilogue *epi, void *stream) {
+  if (!a || !b || (!c && !c_bf16)) return WEEDCU_EINVAL;
+  tc::EpiExt ext;
+  ext.out_mode = c_bf16 ? (c ? 2 : 1) : 0;
+  ext.c16[0] = c_bf16;
+  ext.ldc16 = ldc_bf16;
+  uint32_t tiles = 0;
+  if (epi) {
+    ext.act = epi->activation;
+    ext.stats_kind = epi->row_stats;
+    ext.row_stats = epi->stats;
+    ext.stats_capacity_tiles = epi->stats_capacity_tiles;
+    ext.stats_tiles = &tiles;
+    if (ext.act && !c_bf16) return WEEDCU_EINVAL; // the activation only exists on the bf16 copy
+    if (ext.stats_kind < 0 || ext.stats_kind > 2 || ext.act < 0 || ext.act > 1) return WEEDCU_EINVAL;
+  }
+  const uint16_t *bs[1] = {b};
+  float *cs[1] = {c};
+  const float *biases[1] = {epi ? epi->col_bias : nullptr};
+  const int rc = tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, 1, bs, b_major, ldb, 0, cs, ldc, 0, M, N, K, 1, 0, resolve_stream(stream),
+                                              biases[0] ? biases : nullptr, epi ? epi->residual : nullptr, epi ? epi->ldr : 0, &ext);
+  if (rc == 0 && epi && epi->row_stats) {
+    if (epi->stats_tiles) *epi->stats_tiles = tiles;
+    if (epi->stats_tile_cols) *epi->stats_tile_cols = tiles ? (tiles == 1 ? N : (uint32_t)tc::last_block_n()) : 0;
+  }
+  return rc;
+}
+
+int weedcu_gemm_bf16_grouped_bf16out(const uint16_t *a, int a_major, uint64_t lda, uint32_t groups, const uint16_t *const *b,
+                                     int b_major, uint64_t ldb, uint16_t *const *c_bf16, uint64_t ldc_bf16, uint32_t M, uint32_t N,
+                                     uint32_t K, const float *const *col_bias, void *stream) {
+  if (!a || !b || !c_bf16 || !groups || groups > tc::kMaxGroups) return WEEDCU_EINVAL;
+  tc::EpiExt ext;
+  ext.out_mode = 1;
+  ext.ldc16 = ldc_bf16;
+  for (uint32_t g = 0; g < groups; ++g) ext.c16[g] = c_bf16[g];
+  float *cs[3] = {nullptr, nullptr, nullptr};
+  return tc::launch_gemm_bf16_grouped(a, a_major, lda, 0, groups, b, b_major, ldb, 0, cs, 0, 0, M, N, K, 1, 0, resolve_stream(stream), col_bias,
+                                      nullptr, 0, &ext);
 }
 
 int weedcu_gemm_set_mode(int mode) {
