@@ -130,6 +130,8 @@ int wh_config(const char *name, double value) {
     else if (n == "defer_grads") c.defer_grads = value != 0;
     else if (n == "cow_grads") c.cow_grads = value != 0;
     else if (n == "pdl") weedcu_set_pdl(value != 0 ? 1 : 0);
+    else if (n == "epilogue_stats") c.epilogue_stats = value != 0;
+    else if (n == "lm_head_min_cols") c.lm_head_min_cols = (tcapint)value;
     else throw std::invalid_argument("unknown config key");
     return 0;
   })

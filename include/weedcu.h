@@ -218,6 +218,12 @@ int weedcu_attention_fwd(const float *q, const float *k, const float *v, float *
 int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v, float *out, uint16_t *out_bf16,
                                  uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                                  int causal, void *stream);
+/* weedcu_attention_fwd_bf16out whose q, k, v arrive as bf16 [B, T, H*hd] column-major (the operand copies the grouped
+ * W_q / W_k / W_v product wrote, weedcu_gemm_bf16_grouped_bf16out): the head relayout reads 2 B/elem instead of 4 and the
+ * fp32 projections are never written. Same rounding points as the fp32-input entry (q, k, v are rounded to bf16 there
+ * too). WEEDCU_ENOSUP unless B % 8 == 0 and the pointers are 16-byte aligned. */
+int weedcu_attention_fwd_bf16in(const uint16_t *q_bf16, const uint16_t *k_bf16, const uint16_t *v_bf16, float *out, uint16_t *out_bf16,
+                                uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal, void *stream);
 /* Fused cross-entropy over logits[rows, V] (row stride rs, vocab stride vs):
  * cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34) = -mean_rows lsm[row, target].
  * fwd writes per-row log-sum-exp (lse[rows]) and the scalar loss; bwd does
@@ -242,6 +248,18 @@ int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t
                                   const int32_t *targets, const float *lse, const float *dloss,
                                   float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,
                                   float *colsum, void *stream);
+/* cross_entropy_loss forward (include/autograd/cross_entropy_loss.hpp:21-34) from the log-sum-exp partials the LM head's
+ * GEMM epilogue left (weedcu_gemm_bf16_ex, row_stats 2; stats[t][row] = (max, sum exp) of column tile t) — the logits are not
+ * read at all. The target logit of each row is recomputed as the same bf16 x bf16 -> fp32 dot product (+ col_bias) from
+ * the GEMM's operands a [rows, K] / b [V, K] (majors and leading dimensions as in weedcu_gemm_bf16). lse[row], *loss as
+ * weedcu_cross_entropy_fwd. */
+int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda,
+                                   const uint16_t *b, int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets,
+                                   float *lse, float *loss, void *stream);
+/* weedcu_cross_entropy_bwd_pack reading the bf16 copy of the logits ([rows, V] dense, rows contiguous) instead of fp32. */
+int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse,
+                                         const float *dloss, float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,
+                                         float *colsum, void *stream);
 
 /* ------------------------------------------------------------------ L1 LayerNorm (fused)
  * LayerNorm::forward (src/modules/layernorm.cpp:29-42): x[rows, F] with row stride 1 and

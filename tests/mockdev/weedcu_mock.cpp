@@ -121,6 +121,20 @@ int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v,
     for (uint64_t i = 0; i < (uint64_t)B * T * H * hd; ++i) out_bf16[i] = wo_f32_to_bf16(out[i]);
   return rc;
 }
+int weedcu_attention_fwd_bf16in(const uint16_t *q, const uint16_t *k, const uint16_t *v, float *out, uint16_t *out_bf16, uint32_t B, uint32_t T, uint32_t H, uint32_t hd,
+                                float divisor, float mask_val, int causal, void *stream) {
+  if (!q || !k || !v) return WEEDCU_EINVAL;
+  if (B % 8u) return WEEDCU_ENOSUP;
+  const size_t n = (size_t)B * T * H * hd;
+  std::vector<float> wq(n), wk(n), wv(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t a = (uint32_t)q[i] << 16, b = (uint32_t)k[i] << 16, c = (uint32_t)v[i] << 16;
+    memcpy(&wq[i], &a, 4);
+    memcpy(&wk[i], &b, 4);
+    memcpy(&wv[i], &c, 4);
+  }
+  return weedcu_attention_fwd_bf16out(wq.data(), wk.data(), wv.data(), out, out_bf16, B, T, H, hd, divisor, mask_val, causal, stream);
+}
 int weedcu_attention_decode(const float *q, const float *k, const float *v, float *k_cache, float *v_cache, float *out, uint32_t B, uint32_t T_new, uint32_t H, uint32_t hd,
                             uint32_t S, uint32_t cache_len, float divisor, float mask_val, int causal, void *) {
   if (hd > 64u) return WEEDCU_ENOSUP;
@@ -317,6 +331,38 @@ int weedcu_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint3
     if (rc) return rc;
   }
   return 0;
+}
+int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b,
+                                   int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets, float *lse, float *loss, void *) {
+  if (!stats || !tiles || !a || !b || !targets || !lse || !loss) return WEEDCU_EINVAL;
+  trace_call("cross_entropy_fwd_stats(");
+  ++g_launches;
+  if (g_nocompute) return 0;
+  double total = 0.0;
+  for (uint32_t r = 0; r < rows; ++r) {
+    double M = -1.0 / 0.0, S = 0.0;
+    for (uint32_t t = 0; t < tiles; ++t) M = stats[2 * ((uint64_t)t * rows + r)] > M ? stats[2 * ((uint64_t)t * rows + r)] : M;
+    for (uint32_t t = 0; t < tiles; ++t) S += (double)stats[2 * ((uint64_t)t * rows + r) + 1] * exp((double)stats[2 * ((uint64_t)t * rows + r)] - M);
+    const uint32_t tg = (uint32_t)targets[r];
+    if (tg >= V) return WEEDCU_EINVAL;
+    double xt = 0.0;
+    for (uint32_t k = 0; k < K; ++k)
+      xt += (double)bf16_widen(a[a_major ? (r + k * lda) : (k + r * lda)]) * (double)bf16_widen(b[b_major ? (tg + k * ldb) : (k + tg * ldb)]);
+    float x32 = (float)xt;
+    if (col_bias) x32 = x32 + col_bias[tg];
+    const float l = (float)(M + log(S));
+    lse[r] = l;
+    total += (double)(x32 - l);
+  }
+  *loss = (float)(-total / rows);
+  return 0;
+}
+int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss,
+                                         float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *stream) {
+  if (!logits_bf16) return WEEDCU_EINVAL;
+  std::vector<float> wide((size_t)rows * V);
+  for (size_t i = 0; i < wide.size(); ++i) wide[i] = bf16_widen(logits_bf16[i]);
+  return weedcu_cross_entropy_bwd_pack(wide.data(), 0, rows, V, targets, lse, dloss, dlogits, d_offset, accumulate, dlogits_bf16, colsum, stream);
 }
 // extended epilogue: the plain product, then every extra output from the fp32 values (column tiles of 256)
 int weedcu_gemm_bf16_ex(const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major, uint64_t ldb, float *c, uint64_t ldc, uint16_t *c_bf16,

@@ -44,9 +44,10 @@ test_greedy_decode = G.test_greedy_decode_matches_reference
 test_greedy_decode_batched = G.test_greedy_decode_batched_fused_equals_unfused
 test_view_keeps_owner = G.test_view_of_graph_tensor_keeps_owner_alive
 test_token_model_fp64_arbiter = G.test_token_model_fused_fp32_matches_fp64_arbiter_B3
-test_token_model_bf16_arbiter = G.test_token_model_fused_bf16_matches_fp64_bf16_arbiter_B4
+test_token_model_bf16_arbiter = G.test_token_model_fused_bf16_matches_fp64_bf16_arbiter_B8
 test_encoder_fp64_arbiter = G.test_encoder_layer_fused_matches_fp64_arbiter_B4
 test_c4_scaled_B1 = G.test_config_c4_scaled_dims_B1_matches_reference
+test_gemm_epilogue_fusions = G.test_gemm_epilogue_fusions_match_unfused_passes
 
 
 def test_training_steps_do_not_leak_device_buffers(P):

@@ -90,6 +90,57 @@ heads_pack_vec_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint3
     *reinterpret_cast<uint4 *>(dst + (((uint64_t)b * H + h) * hd + j) * T + t0 + t) = *reinterpret_cast<const uint4 *>(o);
   }
 }
+// The same relayout when q, k, v arrive as bf16 [B,T,C] already (the W_q / W_k / W_v products wrote only their bf16 copy,
+// weedcu_gemm_bf16_grouped_bf16out): 4 B/elem instead of 6. B % 8 == 0: a 128-bit load is 8 consecutive b of one token.
+struct HeadsPackArgs16 {
+  const __nv_bfloat16 *src[3];
+  __nv_bfloat16 *dst[3];
+};
+template <int LPT>
+__global__ void __launch_bounds__(256)
+heads_pack_vec16_kernel(HeadsPackArgs16 a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
+  pdl_grid_sync();
+  extern __shared__ float tile[]; // [B][tt + 4]
+  const uint32_t pitch = tt + 4u;
+  const uint32_t c = blockIdx.y, h = c % H, j = c / H;
+  const uint32_t t0 = blockIdx.x * tt, nt = min(tt, T - t0), n8 = (nt * B) >> 3;
+  const __nv_bfloat16 *sp = blockIdx.z == 0 ? a.src[0] : (blockIdx.z == 1 ? a.src[1] : a.src[2]);
+  __nv_bfloat16 *dst = blockIdx.z == 0 ? a.dst[0] : (blockIdx.z == 1 ? a.dst[1] : a.dst[2]);
+  const uint4 *src = reinterpret_cast<const uint4 *>(sp + ((uint64_t)c * T + t0) * B);
+  uint4 v[LPT];
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    v[u] = (i < n8) ? src[i] : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int u = 0; u < LPT; ++u) {
+    const uint32_t i = threadIdx.x + u * 256u;
+    if (i < n8) {
+      const uint32_t e = i << 3, t = e / B, b = e - t * B;
+      float *d = tile + b * pitch + t;
+      const __nv_bfloat162 *p2 = reinterpret_cast<const __nv_bfloat162 *>(&v[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        d[(2 * k) * pitch] = __low2float(p2[k]);
+        d[(2 * k + 1) * pitch] = __high2float(p2[k]);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t m8 = (nt >> 3) * B;
+  for (uint32_t i = threadIdx.x; i < m8; i += 256u) {
+    const uint32_t b = i / (nt >> 3), t = (i - b * (nt >> 3)) << 3;
+    const float4 x = *reinterpret_cast<const float4 *>(tile + b * pitch + t);
+    const float4 y = *reinterpret_cast<const float4 *>(tile + b * pitch + t + 4);
+    __nv_bfloat162 o[4];
+    o[0] = __floats2bfloat162_rn(x.x, x.y);
+    o[1] = __floats2bfloat162_rn(x.z, x.w);
+    o[2] = __floats2bfloat162_rn(y.x, y.y);
+    o[3] = __floats2bfloat162_rn(y.z, y.w);
+    *reinterpret_cast<uint4 *>(dst + (((uint64_t)b * H + h) * hd + j) * T + t0 + t) = *reinterpret_cast<const uint4 *>(o);
+  }
+}
 // generic shapes (B % 4 != 0 or unaligned bases)
 __global__ void __launch_bounds__(256)
 heads_pack_kernel(HeadsPackArgs a, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, uint32_t tt) {
@@ -255,10 +306,26 @@ extern "C" int weedcu_attention_fwd(const float *q, const float *k, const float 
   return weedcu_attention_fwd_bf16out(q, k, v, out, nullptr, B, T, H, hd, divisor, mask_val, causal, stream);
 }
 
+static int attention_fwd_impl(const float *q, const float *k, const float *v, const uint16_t *q16, const uint16_t *k16, const uint16_t *v16, float *out,
+                              uint16_t *out_bf16, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal,
+                              void *stream);
 extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, const float *v, float *out, uint16_t *out_bf16,
                                             uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val,
                                             int causal, void *stream) {
-  if (!q || !k || !v || !out || !B || !T || !H || !hd) return WEEDCU_EINVAL;
+  if (!q || !k || !v) return WEEDCU_EINVAL;
+  return attention_fwd_impl(q, k, v, nullptr, nullptr, nullptr, out, out_bf16, B, T, H, hd, divisor, mask_val, causal, stream);
+}
+extern "C" int weedcu_attention_fwd_bf16in(const uint16_t *q_bf16, const uint16_t *k_bf16, const uint16_t *v_bf16, float *out, uint16_t *out_bf16,
+                                           uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal,
+                                           void *stream) {
+  if (!q_bf16 || !k_bf16 || !v_bf16) return WEEDCU_EINVAL;
+  if ((B % 8u) || !aligned16(q_bf16) || !aligned16(k_bf16) || !aligned16(v_bf16)) return WEEDCU_ENOSUP;
+  return attention_fwd_impl(nullptr, nullptr, nullptr, q_bf16, k_bf16, v_bf16, out, out_bf16, B, T, H, hd, divisor, mask_val, causal, stream);
+}
+static int attention_fwd_impl(const float *q, const float *k, const float *v, const uint16_t *q16, const uint16_t *k16, const uint16_t *v16, float *out,
+                              uint16_t *out_bf16, uint32_t B, uint32_t T, uint32_t H, uint32_t hd, float divisor, float mask_val, int causal,
+                              void *stream) {
+  if (!out || !B || !T || !H || !hd) return WEEDCU_EINVAL;
   if (out_bf16 && ((B % 4u) || !aligned16(out) || (((uintptr_t)out_bf16) & 7u))) return WEEDCU_ENOSUP; // rides on the vectorised relayout only
   // tensor-map constraints of the two products (16-byte row pitch) and the register softmax
   static const bool flash_on = [] {
@@ -292,7 +359,19 @@ extern "C" int weedcu_attention_fwd_bf16out(const float *q, const float *k, cons
     return WEEDCU_ENOSUP;
   }
   int rc;
-  {
+  if (q16) {
+    ProfScope prof(WEEDCU_PROF_PACK, st, 3.0 * 4.0 * (double)B * T * C);
+    HeadsPackArgs16 a = {{(const __nv_bfloat16 *)q16, (const __nv_bfloat16 *)k16, (const __nv_bfloat16 *)v16},
+                         {(__nv_bfloat16 *)qh, (__nv_bfloat16 *)kh, (__nv_bfloat16 *)vh}};
+    const uint32_t vtt = (4096u / B) & ~7u;
+    if (vtt < 8u || !aligned16(qh)) {
+      pool_free(ws, st);
+      return WEEDCU_ENOSUP;
+    }
+    const uint32_t vt = vtt < T ? vtt : T;
+    launch_k(heads_pack_vec16_kernel<2>, dim3((T + vt - 1) / vt, (unsigned)C, 3), dim3(256), (size_t)B * (vt + 4u) * sizeof(float), st, a, B, T, H, hd, vt);
+    rc = after_launch();
+  } else {
     ProfScope prof(WEEDCU_PROF_PACK, st, 3.0 * 6.0 * (double)B * T * C);
     HeadsPackArgs a = {{q, k, v}, {(__nv_bfloat16 *)qh, (__nv_bfloat16 *)kh, (__nv_bfloat16 *)vh}};
     // vector path: 4096 elements (16 KB) per block = 4 x 128-bit loads per thread

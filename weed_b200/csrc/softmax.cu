@@ -520,6 +520,48 @@ ce_fwd_finish(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
   lse[r] = M + log_s;
   nll[r] = (xt - M) - log_s; // = lsm[r, target]
 }
+// Forward from the log-sum-exp partials the LM head's GEMM epilogue left (weedcu_gemm_bf16_ex, row_stats 2): merge the
+// per-column-tile (max, sum exp), and recompute the ONE logit the loss needs per row — the target column — as the same
+// bf16 x bf16 -> fp32 dot product (+ bias) the tensor cores formed, from the GEMM's own operands. Thread per row.
+__global__ void __launch_bounds__(128)
+ce_fwd_stats_finish(const float2 *__restrict__ stats, uint32_t tiles, uint32_t rows, uint32_t V, const __nv_bfloat16 *__restrict__ a, int a_major,
+                    uint64_t lda, const __nv_bfloat16 *__restrict__ b, int b_major, uint64_t ldb, uint32_t K, const float *__restrict__ bias,
+                    const int32_t *__restrict__ targets, float *__restrict__ lse, float *__restrict__ nll) {
+  pdl_grid_sync();
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float M = -INFINITY;
+  for (uint32_t t = 0; t < tiles; ++t) M = fmaxf(M, stats[(uint64_t)t * rows + r].x);
+  float S = 0.0f;
+  for (uint32_t t = 0; t < tiles; ++t) {
+    const float2 p = stats[(uint64_t)t * rows + r];
+    if (p.x > -INFINITY) S += p.y * expf(p.x - M);
+  }
+  const float log_s = logf(S);
+  const uint32_t t = (uint32_t)targets[r];
+  float xt = NAN;
+  if (t < V) {
+    const __nv_bfloat16 *ap = a_major ? a + r : a + (uint64_t)r * lda;
+    const __nv_bfloat16 *bp = b_major ? b + t : b + (uint64_t)t * ldb;
+    const uint64_t as = a_major ? lda : 1u, bs = b_major ? ldb : 1u;
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    uint32_t k = 0;
+    if (!b_major && (ldb % 8u) == 0 && ((((uintptr_t)b) & 15u) == 0)) { // K-major weights: 8 k per 128-bit load
+      for (; k + 8 <= K; k += 8) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(bp + k);
+        const __nv_bfloat162 *w2 = reinterpret_cast<const __nv_bfloat162 *>(&w);
+        acc0 += __bfloat162float(ap[(uint64_t)(k + 0) * as]) * __low2float(w2[0]) + __bfloat162float(ap[(uint64_t)(k + 1) * as]) * __high2float(w2[0]);
+        acc1 += __bfloat162float(ap[(uint64_t)(k + 2) * as]) * __low2float(w2[1]) + __bfloat162float(ap[(uint64_t)(k + 3) * as]) * __high2float(w2[1]);
+        acc2 += __bfloat162float(ap[(uint64_t)(k + 4) * as]) * __low2float(w2[2]) + __bfloat162float(ap[(uint64_t)(k + 5) * as]) * __high2float(w2[2]);
+        acc3 += __bfloat162float(ap[(uint64_t)(k + 6) * as]) * __low2float(w2[3]) + __bfloat162float(ap[(uint64_t)(k + 7) * as]) * __high2float(w2[3]);
+      }
+    }
+    for (; k < K; ++k) acc0 += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[(uint64_t)k * bs]);
+    xt = ((acc0 + acc1) + (acc2 + acc3)) + (bias ? bias[t] : 0.0f);
+  }
+  lse[r] = M + log_s;
+  nll[r] = (xt - M) - log_s;
+}
 // dlogits[r,v] (+)= (exp(x - lse[r]) - onehot) * dloss/rows ; block = 32 rows x 8 vocab lanes.
 __global__ void __launch_bounds__(kCeRT * kCeBY)
 ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t rs, uint32_t vs,
@@ -557,8 +599,16 @@ ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
 // block = 256 threads x 4 adjacent rows, kCePackCols vocab columns; logits / dlogits are [rows, V]
 // with rows contiguous (rs == 1, vs == rows, rows % 8 == 0, 16-byte aligned).
 constexpr int kCePackCols = 8;
+// four adjacent rows of column j: fp32 logits, or their bf16 copy (the LM head's epilogue wrote only that)
+__device__ __forceinline__ float4 ce_load4(const float *x, uint64_t off) { return *reinterpret_cast<const float4 *>(x + off); }
+__device__ __forceinline__ float4 ce_load4(const __nv_bfloat16 *x, uint64_t off) {
+  const uint2 u = *reinterpret_cast<const uint2 *>(x + off);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+template <typename XT>
 __global__ void __launch_bounds__(256)
-ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const int32_t *__restrict__ targets,
+ce_bwd_pack_kernel(const XT *__restrict__ x, uint32_t rows, uint32_t V, const int32_t *__restrict__ targets,
                    const float *__restrict__ lse, const float *__restrict__ dloss, float *dlogits, int accumulate,
                    __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
   pdl_grid_sync();
@@ -582,7 +632,7 @@ ce_bwd_pack_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, const
         const uint32_t j = j0 + i0 + u;
         if (j < V) {
           const uint64_t off = (uint64_t)j * rows + r;
-          xv[u] = *reinterpret_cast<const float4 *>(x + off);
+          xv[u] = ce_load4(x, off);
           dv[u] = accumulate ? *reinterpret_cast<const float4 *>(dlogits + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -927,7 +977,55 @@ int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 14.0 : (d ? 10.0 : 6.0)) * (double)rows * V);
-  launch_k(ce_bwd_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
+  launch_k(ce_bwd_pack_kernel<float>, dim3(nchunks, cgroups), dim3(256), 0, st, x, rows, V, targets, lse, dloss, d, accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
+  int rc = after_launch();
+  if (rc == 0) {
+    launch_k(ce_colsum_finish_kernel, dim3((V + 255u) / 256u), dim3(256), 0, st, part, nchunks, V, colsum);
+    rc = after_launch();
+  }
+  pool_free(part, st);
+  return rc;
+}
+
+int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda,
+                                   const uint16_t *b, int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets,
+                                   float *lse, float *loss, void *stream) {
+  if (!stats || !tiles || !rows || !V || !a || !b || !K || !targets || !lse || !loss) return WEEDCU_EINVAL;
+  if (!aligned16(stats)) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  float *nll = nullptr;
+  WCU_CHECK(pool_alloc((void **)&nll, sizeof(float) * (size_t)rows, st));
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 8.0 * (double)rows * tiles + 2.0 * (double)rows * K * 2.0);
+  launch_k(ce_fwd_stats_finish, dim3((rows + 127u) / 128u), dim3(128), 0, st, (const float2 *)stats, tiles, rows, V, (const __nv_bfloat16 *)a, a_major, lda,
+           (const __nv_bfloat16 *)b, b_major, ldb, K, col_bias, targets, lse, nll);
+  int rc = after_launch();
+  if (rc == 0) {
+    weedcu_view v;
+    v.offset = 0;
+    v.rank = 1;
+    v.shape[0] = rows;
+    v.stride[0] = 1;
+    rc = weedcu_sum_real(nll, &v, -1.0f / (float)rows, loss, (void *)st);
+  }
+  pool_free(nll, st);
+  return rc;
+}
+
+int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse,
+                                         const float *dloss, float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,
+                                         float *colsum, void *stream) {
+  if (!logits_bf16 || !targets || !lse || !dloss || !dlogits_bf16 || !colsum || !rows || !V) return WEEDCU_EINVAL;
+  if (!dlogits && accumulate) return WEEDCU_EINVAL;
+  float *d = dlogits ? dlogits + d_offset : nullptr;
+  if ((rows % 8u) || (((uintptr_t)logits_bf16) & 7u) || (d && !aligned16(d)) || !aligned16(lse) || !aligned16(targets) || !aligned16(dlogits_bf16)) return WEEDCU_ENOSUP;
+  const uint32_t nchunks = (rows + 1023u) / 1024u, cgroups = (V + kCePackCols - 1) / kCePackCols;
+  if (cgroups > 65535u) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  float *part = nullptr;
+  WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
+  ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 12.0 : (d ? 8.0 : 4.0)) * (double)rows * V);
+  launch_k(ce_bwd_pack_kernel<__nv_bfloat16>, dim3(nchunks, cgroups), dim3(256), 0, st, (const __nv_bfloat16 *)logits_bf16, rows, V, targets, lse, dloss, d,
+           accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
   int rc = after_launch();
   if (rc == 0) {
     launch_k(ce_colsum_finish_kernel, dim3((V + 255u) / 256u), dim3(256), 0, st, part, nchunks, V, colsum);

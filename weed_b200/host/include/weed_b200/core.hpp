@@ -98,6 +98,13 @@ struct BackendConfig {
   // a gradient whose first contribution is a plain copy of another complete gradient shares its buffer
   // copy-on-write instead (GpuStorage::cow)
   bool cow_grads = true;
+  // the tensor-core GEMM's extended epilogue (weedcu_gemm_bf16_ex) leaves what the consumer of a Linear output reads:
+  // LayerNorm row partials behind the residual products, GELU + the bf16 operand copy behind ff1, log-sum-exp partials and
+  // bf16-only logits behind the LM head, bf16-only Q / K / V
+  bool epilogue_stats = true;
+  // a Linear with at least this many output features whose output takes part in autograd is treated as an LM head: bf16-only
+  // logits + log-sum-exp partials from the GEMM epilogue, fp32 logits only if something reads them
+  tcapint lm_head_min_cols = 4096U;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)
@@ -351,6 +358,26 @@ struct GpuRealStorage : GpuStorage<real1> {
   BufferPtr colsum;
   uint64_t colsum_version = 0U;
   tcapint colsum_n = 0U;
+  // per-row statistics of the [rows, cols] matrix this storage holds, left as per-column-tile partials by the epilogue of
+  // the GEMM that produced it (weedcu_gemm_bf16_ex): kind 1 = (mean, M2) for LayerNorm::forward, kind 2 = (max, sum exp)
+  // for cross_entropy_loss; valid while row_stats_version == version
+  // the bf16 operands of the product that wrote this storage's bf16 copy without writing the fp32 values (the LM head's
+  // logits): what the deferred fp32 values and the cross-entropy's target logit are recomputed from
+  struct GemmSource {
+    BufferPtr a, b;
+    int a_major = 0, b_major = 0;
+    uint64_t lda = 0U, ldb = 0U;
+    uint32_t M = 0U, N = 0U, K = 0U;
+    StoragePtr w_storage, bias_storage; // the weight whose shadow `b` is (rewritten in place by the optimiser) and the bias
+    uint64_t w_version = 0U, bias_version = 0U;
+    tcapint bias_offset = 0U;
+  };
+  std::shared_ptr<GemmSource> gemm_source;
+  BufferPtr row_stats;
+  int row_stats_kind = 0;
+  uint32_t row_stats_tiles = 0U, row_stats_tile_cols = 0U;
+  tcapint row_stats_rows = 0U, row_stats_cols = 0U;
+  uint64_t row_stats_version = 0U;
 };
 struct GpuIntStorage : GpuStorage<symint> {
   GpuIntStorage(const tcapint &n, int64_t did, const bool &alloc = true) : GpuStorage<symint>(INT_GPU_DENSE, n, did, alloc) {}
@@ -540,6 +567,10 @@ struct Tensor : public BaseTensor, public std::enable_shared_from_this<Tensor> {
   static TensorPtr tanh(TensorPtr a);
   static void make_tanh_node(TensorPtr a, TensorPtr out);
   static TensorPtr gelu(const TensorPtr x);
+  static void make_gelu_node(TensorPtr a, TensorPtr out);
+  // gelu(a w + bias) with the activation in the tensor-core GEMM's epilogue (same two autograd nodes as Linear::forward +
+  // Tensor::gelu), or nullptr when that kernel does not apply
+  static TensorPtr linear_gelu(TensorPtr a, TensorPtr w, TensorPtr bias);
   static TensorPtr relu(TensorPtr a);
   static void make_relu_node(TensorPtr a, TensorPtr out);
   static TensorPtr sin(TensorPtr a);
@@ -558,7 +589,7 @@ struct Tensor : public BaseTensor, public std::enable_shared_from_this<Tensor> {
   // the same for two or three Linear layers reading one input (W_q / W_k / W_v): one grouped launch,
   // each output with exactly the autograd node Tensor::linear would give it; empty when not eligible
   static TensorPtr finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr out, bool rg, TensorPtr residual = nullptr);
-  static std::vector<TensorPtr> linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases);
+  static std::vector<TensorPtr> linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases, bool bf16_only = false);
   static TensorPtr sub(TensorPtr a, TensorPtr b);
   static void make_sub_node(TensorPtr a, TensorPtr b, TensorPtr out);
   static TensorPtr div(TensorPtr a, TensorPtr b);

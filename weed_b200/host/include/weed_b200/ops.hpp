@@ -53,6 +53,14 @@ void matmul_accumulate(const Tensor &a, const Tensor &b, Tensor &out);
 // out = a b + bias (bias: dense [N], broadcast over rows) in one tensor-core GEMM; false (nothing
 // computed) when that kernel does not apply to these operands
 bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &out, const Tensor *residual = nullptr);
+// h = a w + bias (fp32, kept for the GELU backward) and the bf16 GEMM operand copy of y = gelu(h) from ONE tensor-core GEMM
+// (weedcu_gemm_bf16_ex, activation 1); y's fp32 values are deferred. false: nothing was done.
+bool matmul_bias_gelu(const Tensor &a, const Tensor &w, const Tensor &bias, Tensor &h, Tensor &y);
+// LM head: out = a w + bias leaves the kernel as its bf16 copy + per-row log-sum-exp partials only (fp32 values deferred:
+// recomputed by the plain GEMM if something reads them). false: nothing was done.
+bool matmul_bias_lse(const Tensor &a, const Tensor &w, const Tensor &bias, Tensor &out);
+// cross_entropy_loss forward for logits produced by matmul_bias_lse: no pass over the logits. false: nothing was done.
+bool cross_entropy_fwd_from_stats(const Tensor &logits, const SymbolTensor &targets, Tensor &lse, Tensor &loss, tcapint rows, tcapint V);
 // Packs dy [rows, N] into its bf16 GEMM shadow and adds its column sums into `sums` (dense [N]) in the
 // same pass — Linear's bias gradient without a separate reduction. false: nothing was done.
 bool pack_with_column_sums(const Tensor &dy, Tensor &sums);
@@ -68,8 +76,14 @@ void embedding_scatter_add(Tensor &dW, const SymbolTensor &indices, const Tensor
 SymbolTensorPtr argmax_last_token(const Tensor &logits);
 // outs[g] = a * ws[g] + biases[g] for up to three weights of one shape as ONE grouped tensor-core launch
 // (the W_q / W_k / W_v projections); false (nothing computed) when the bf16 operand path does not apply.
+// bf16_only: the caller reads the outputs only through their bf16 operand copies (the attention core): the fp32 values are
+// not written unless something else reads them
 bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
-                         const std::vector<Tensor *> &outs);
+                         const std::vector<Tensor *> &outs, bool bf16_only = false);
+// MultiHeadAttention::forward's fused core on bf16 tensor cores (weedcu_attention_fwd_bf16out / _bf16in); returns the
+// weedcu code (WEEDCU_ENOSUP: not eligible, nothing launched)
+int attention_forward_bf16(const Tensor &q, const Tensor &k, const Tensor &v, Tensor &out, uint16_t *out_bf16, tcapint B, tcapint T, tcapint H, tcapint hd,
+                           real1 divisor, real1 mask_val, int causal);
 bool matmul_skinny_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
                            const std::vector<Tensor *> &outs);
 // Producer-side bf16 operand shadows. A kernel that is about to overwrite the dense tensor `out` may

@@ -157,9 +157,11 @@ TensorPtr cross_entropy_loss(TensorPtr logits, SymbolTensorPtr targets) {
     TensorPtr lse = Tensor::allocate_like(std::vector<tcapint>{rows}, *logits, DType::REAL, false, false);
     SymbolTensorPtr tg = targets->storage->device == DeviceTag::GPU ? targets : targets->cast(DeviceTag::GPU);
     const tcapint vs = logits->stride[rank - 1U];
-    throw_on_error(weedcu_cross_entropy_fwd(logits->device_ptr_ro(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
-                                            lse->device_ptr(), loss->device_ptr(), logits->stream()),
-                   "cross_entropy_loss");
+    // logits straight from an LM head whose epilogue left the log-sum-exp partials: no pass over the logits at all
+    if (!(vs == rows && Weed::cross_entropy_fwd_from_stats(*logits, *tg, *lse, *loss, rows, V)))
+      throw_on_error(weedcu_cross_entropy_fwd(logits->device_ptr_ro(), logits->offset, rows, V, 1U, vs, tg->device_ptr() + tg->offset,
+                                              lse->device_ptr(), loss->device_ptr(), logits->stream()),
+                     "cross_entropy_loss");
     if (rg) {
       loss->make_gradient();
       loss->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{logits}, [logits, tg, lse, wloss = std::weak_ptr<Tensor>(loss), rows, V, vs]() {

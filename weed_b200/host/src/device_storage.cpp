@@ -24,6 +24,7 @@ BackendConfig &backend_config() {
     if (const char *e = getenv("WEED_B200_LAZY_ZERO")) c.lazy_zero = atoi(e) != 0;
     if (const char *e = getenv("WEED_B200_DEFER_GRADS")) c.defer_grads = atoi(e) != 0;
     if (const char *e = getenv("WEED_B200_COW_GRADS")) c.cow_grads = atoi(e) != 0;
+    if (const char *e = getenv("WEED_B200_EPILOGUE")) c.epilogue_stats = atoi(e) != 0;
     return c;
   }();
   return cfg;

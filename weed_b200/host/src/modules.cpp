@@ -293,7 +293,12 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
   // (each output keeps the node Linear::forward would give it), otherwise three Linear::forward calls
   TensorPtr Q, K, V;
   if (W_q->bias && W_k->bias && W_v->bias) {
-    const std::vector<TensorPtr> qkv = Tensor::linear_grouped(x, {W_q->weight, W_k->weight, W_v->weight}, {W_q->bias, W_k->bias, W_v->bias});
+    // when the fused tensor-core attention core follows, it is the projections' only reader and takes their bf16 copies
+    const BackendConfig &c0 = backend_config();
+    const bool core_reads_bf16 = c0.fused && c0.matmul_precision == WEEDCU_GEMM_BF16 && !use_kv_cache && num_kv_heads == num_heads && head_dim == 64 &&
+                                 (x->shape[0] % 8U) == 0U && x->shape.size() == 3U && (x->shape[1] % 8U) == 0U && x->shape[1] >= 64U;
+    const std::vector<TensorPtr> qkv =
+        Tensor::linear_grouped(x, {W_q->weight, W_k->weight, W_v->weight}, {W_q->bias, W_k->bias, W_v->bias}, core_reads_bf16);
     if (qkv.size() == 3U) {
       Q = qkv[0];
       K = qkv[1];
@@ -324,9 +329,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
       out = Tensor::allocate_like(std::vector<tcapint>{Bu, Tu, H * hd}, *x, DType::REAL, false, false);
       // the relayout back to [B, T, C] also leaves the bf16 operand of the W_o product (no pack pass)
       const OutputShadow os = (Bu % 4U) == 0U ? begin_output_shadow(*out, H * hd) : OutputShadow();
-      int rc = weedcu_attention_fwd_bf16out(Q->device_ptr_ro() + Q->offset, K->device_ptr_ro() + K->offset, V->device_ptr_ro() + V->offset,
-                                            out->device_ptr(), os.ptr, Bu, Tu, H, hd, std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0,
-                                            x->stream());
+      int rc = Weed::attention_forward_bf16(*Q, *K, *V, *out, os.ptr, Bu, Tu, H, hd, std::sqrt((real1)head_dim), mask_val, (T > 1) ? 1 : 0);
       if (rc == 0) {
         end_output_shadow(os);
         return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
@@ -498,9 +501,11 @@ TensorPtr TransformerEncoderLayer::forward(const TensorPtr x_) {
   // epilogue of the W_o / ff2 product when the fused path applies; forward_add composes Linear + add otherwise
   x1 = self_attn->forward_add(x1, x);
   TensorPtr ff = norm2->forward(x1);
-  ff = ff1->forward(ff);
-  ff = activation->forward(ff);
-  return ff2->forward_add(ff, x1);
+  TensorPtr act;
+  // ff1 followed by GELU: the activation rides in the epilogue of ff1's product (Tensor::linear_gelu)
+  if (ff1->bias && dynamic_cast<GeLU *>(activation.get())) act = Tensor::linear_gelu(ff, ff1->weight, ff1->bias);
+  if (!act) act = activation->forward(ff1->forward(ff));
+  return ff2->forward_add(act, x1);
 }
 
 // ------------------------------------------------------------------------------------- Sequential

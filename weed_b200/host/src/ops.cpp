@@ -256,6 +256,7 @@ weedcu_mat mat_of(const Tensor &t, tcapint extra_offset = 0U, uint64_t batch_str
 // forward product and dW = X^T dY, W serves the forward product and dX = dY W^T, dY serves both
 // backward products. A shadow is stale once its storage's version moved (any potential write).
 struct Bf16Operand {
+  BufferPtr buf; // keeps the shadow alive for as long as the operand is used (a later pack may evict it from its storage)
   const uint16_t *ptr;
   int major; // 1: the M (resp. N) index is contiguous, 0: the K index is
   uint64_t ld;
@@ -277,6 +278,7 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
     if (sh.offset == t.offset && sh.n_fast == n_fast && sh.n_slow == n_slow && sh.s_fast == s_fast && sh.s_slow == s_slow) hit = &sh;
   if (hit && hit->version == s->version) { // (a current shadow is served without touching the fp32 buffer: deferred values stay deferred)
     if (colsum) return false;
+    op.buf = hit->buf;
     op.ptr = (const uint16_t *)hit->buf->ptr;
     return true;
   }
@@ -296,6 +298,7 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
   } else
     throw_on_error(weedcu_pack_bf16(src, t.offset, s_mn, s_k, n_mn, n_k, (uint16_t *)hit->buf->ptr, op.major, s->dev->stream), "pack_bf16");
   hit->version = s->version;
+  op.buf = hit->buf;
   op.ptr = (const uint16_t *)hit->buf->ptr;
   return true;
 }
@@ -321,7 +324,32 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
       const Dev dc = dev_out(out, "matmul", !accumulate);
       const real1 *bias_ptr = bias ? dev_of(*bias, "matmul").ptr + bias->offset : nullptr;
       int rc;
-      if (residual) // [M, N] with the layout of `out`, added after the bias in the epilogue
+      if (residual && cfg.epilogue_stats && !out.offset && covers_storage(out) && N <= 8U * 128U) {
+        // the residual sum is what the next LayerNorm normalises: its epilogue leaves the per-row (mean, M2) partials, and
+        // LayerNorm::forward skips its statistics pass over the tensor (layernorm_forward below)
+        BufferPtr stats = cs->dev->MakeBuffer(sizeof(real1) * 2U * (size_t)M * 8U);
+        uint32_t tiles = 0U, tile_cols = 0U;
+        weedcu_gemm_epilogue epi;
+        memset(&epi, 0, sizeof(epi));
+        epi.col_bias = bias_ptr;
+        epi.residual = dev_of(*residual, "matmul").ptr + residual->offset;
+        epi.ldr = out.stride[1U];
+        epi.row_stats = 1;
+        epi.stats = (float *)stats->ptr;
+        epi.stats_capacity_tiles = 8U;
+        epi.stats_tiles = &tiles;
+        epi.stats_tile_cols = &tile_cols;
+        rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr, out.stride[1U], nullptr, 0U, M, N, K, &epi, dc.stream);
+        if (rc == 0) {
+          cs->row_stats = stats;
+          cs->row_stats_kind = 1;
+          cs->row_stats_tiles = tiles;
+          cs->row_stats_tile_cols = tile_cols;
+          cs->row_stats_rows = M;
+          cs->row_stats_cols = N;
+          cs->row_stats_version = cs->version;
+        }
+      } else if (residual) // [M, N] with the layout of `out`, added after the bias in the epilogue
         rc = weedcu_gemm_bf16_residual(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K, bias_ptr,
                                        dev_of(*residual, "matmul").ptr + residual->offset, out.stride[1U], dc.stream);
       else
@@ -419,6 +447,9 @@ void end_output_shadow(const OutputShadow &os) {
   if (os.storage) os.storage->shadows[os.index].version = os.storage->version;
 }
 
+namespace {
+void defer_gelu_values(GpuRealStorage *ys, const StoragePtr &a_s, tcapint n);
+}
 void gelu(const Tensor &a, Tensor &out) {
   // dense input and output of the same layout: the forward can leave the bf16 operand of the Linear
   // that follows (ff2 reads [B*T, d_ff]) in the same pass
@@ -430,26 +461,9 @@ void gelu(const Tensor &a, Tensor &out) {
       const int rc = weedcu_gelu_fwd_bf16(da.ptr, defer ? nullptr : dout.ptr, os.ptr, out.storage->size, dout.stream);
       if (rc == 0) {
         end_output_shadow(os);
-        if (defer) {
-          // in a transformer layer y = gelu(h) is read by ff2's forward product and by ff2's weight-gradient product,
-          // both through the bf16 shadow; the GELU backward needs h only. The fp32 y is computed if something else reads it
-          // (from h, which must not have been written in between: checked, not assumed).
-          GpuRealStorage *ys = gpu_storage(out, "gelu");
-          StoragePtr a_s = a.storage;
-          const uint64_t a_version = static_cast<GpuRealStorage *>(a_s.get())->version;
-          const tcapint n = out.storage->size;
-          ys->deferred_values = [ys, a_s, a_version, n]() {
-            GpuRealStorage *as = static_cast<GpuRealStorage *>(a_s.get());
-            if (as->version != a_version) throw std::runtime_error("gelu: the input was modified before the deferred fp32 output was read");
-            weedcu_view v;
-            memset(&v, 0, sizeof(v));
-            v.rank = 1;
-            v.shape[0] = n;
-            v.stride[0] = 1U;
-            ys->dev->Bind();
-            throw_on_error(weedcu_unary_real(WEEDCU_GELU, 0, as->device_ptr_ro(), &v, (real1 *)ys->buffer->ptr, &v, ys->dev->stream), "gelu (deferred)");
-          };
-        }
+        // in a transformer layer y = gelu(h) is read by ff2's forward product and by ff2's weight-gradient product, both
+        // through the bf16 shadow; the GELU backward needs h only. The fp32 y is computed if something else reads it
+        if (defer) defer_gelu_values(gpu_storage(out, "gelu"), a.storage, out.storage->size);
         return;
       }
       if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "gelu");
@@ -462,6 +476,20 @@ void layernorm_forward(const Tensor &x, tcapint rows, tcapint features, const Te
   const Dev dx = dev_of(x, "LayerNorm::forward"), dg = dev_of(gamma, "LayerNorm::forward"), db = dev_of(beta, "LayerNorm::forward");
   const OutputShadow os = begin_output_shadow(y, features);
   const Dev dy = dev_out(y, "LayerNorm::forward", true), dm = dev_out(mean, "LayerNorm::forward", true), dr = dev_out(rstd, "LayerNorm::forward", true);
+  {
+    // x straight out of a residual GEMM whose epilogue left the row partials: one pass instead of two
+    GpuRealStorage *xs = gpu_storage(x, "LayerNorm::forward");
+    if (xs->row_stats && xs->row_stats_kind == 1 && xs->row_stats_version == xs->version && !x.offset && xs->row_stats_rows == rows &&
+        xs->row_stats_cols == features && (uint64_t)rows * features == xs->size) {
+      const int rc = weedcu_layernorm_fwd_stats(dx.ptr, rows, features, (const float *)xs->row_stats->ptr, xs->row_stats_tiles, xs->row_stats_tile_cols,
+                                                dg.ptr + gamma.offset, db.ptr + beta.offset, eps, dy.ptr, dm.ptr, dr.ptr, os.ptr, dy.stream);
+      if (rc == 0) {
+        if (os.ptr) end_output_shadow(os);
+        return;
+      }
+      if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "LayerNorm::forward");
+    }
+  }
   if (os.ptr) {
     const int rc = weedcu_layernorm_fwd_bf16(dx.ptr + x.offset, rows, features, dg.ptr + gamma.offset, db.ptr + beta.offset, eps, dy.ptr, dm.ptr, dr.ptr,
                                              os.ptr, dy.stream);
@@ -474,6 +502,146 @@ void layernorm_forward(const Tensor &x, tcapint rows, tcapint features, const Te
   throw_on_error(weedcu_layernorm_fwd(dx.ptr + x.offset, rows, features, dg.ptr + gamma.offset, db.ptr + beta.offset, eps, dy.ptr, dm.ptr, dr.ptr, dy.stream),
                  "LayerNorm::forward");
 }
+namespace {
+// y = gelu(a) was left as its bf16 GEMM operand copy only: the fp32 values are computed from `a` if something reads them
+// (and `a` must not have been written in between: checked, not assumed)
+void defer_gelu_values(GpuRealStorage *ys, const StoragePtr &a_s, tcapint n) {
+  const uint64_t a_version = static_cast<GpuRealStorage *>(a_s.get())->version;
+  ys->deferred_values = [ys, a_s, a_version, n]() {
+    GpuRealStorage *as = static_cast<GpuRealStorage *>(a_s.get());
+    if (as->version != a_version) throw std::runtime_error("gelu: the input was modified before the deferred fp32 output was read");
+    weedcu_view v;
+    memset(&v, 0, sizeof(v));
+    v.rank = 1;
+    v.shape[0] = n;
+    v.stride[0] = 1U;
+    ys->dev->Bind();
+    throw_on_error(weedcu_unary_real(WEEDCU_GELU, 0, as->device_ptr_ro(), &v, (real1 *)ys->buffer->ptr, &v, ys->dev->stream), "gelu (deferred)");
+  };
+}
+// `cs` received only the bf16 copy of a w + bias: remember the operands, and produce the fp32 values on demand with the
+// plain product of the same operands (bit-identical to what Linear::forward writes without this path), as long as the
+// weights have not been updated since
+void defer_linear_output(GpuRealStorage *cs, const Bf16Operand &pa, const Bf16Operand &pb, tcapint M, tcapint N, tcapint K, const Tensor &w,
+                         const Tensor &bias) {
+  std::shared_ptr<GpuRealStorage::GemmSource> src = std::make_shared<GpuRealStorage::GemmSource>();
+  src->a = pa.buf;
+  src->b = pb.buf;
+  src->a_major = pa.major;
+  src->b_major = pb.major;
+  src->lda = pa.ld;
+  src->ldb = pb.ld;
+  src->M = M;
+  src->N = N;
+  src->K = K;
+  src->w_storage = w.storage;
+  src->bias_storage = bias.storage;
+  src->w_version = static_cast<GpuRealStorage *>(w.storage.get())->version;
+  src->bias_version = static_cast<GpuRealStorage *>(bias.storage.get())->version;
+  src->bias_offset = bias.offset;
+  cs->gemm_source = src;
+  cs->deferred_values = [cs, src]() {
+    GpuRealStorage *ws = static_cast<GpuRealStorage *>(src->w_storage.get()), *bs = static_cast<GpuRealStorage *>(src->bias_storage.get());
+    if (ws->version != src->w_version || bs->version != src->bias_version)
+      throw std::runtime_error("Linear: the weights were modified before the deferred fp32 output was read");
+    cs->dev->Bind();
+    throw_on_error(weedcu_gemm_bf16((const uint16_t *)src->a->ptr, src->a_major, src->lda, (const uint16_t *)src->b->ptr, src->b_major, src->ldb,
+                                    (real1 *)cs->buffer->ptr, src->M, src->M, src->N, src->K, 0, bs->device_ptr_ro() + src->bias_offset, cs->dev->stream),
+                   "Linear (deferred fp32 output)");
+  };
+}
+bool tensor_core_linear_ok(const Tensor &a, const Tensor &w, const Tensor &bias, const Tensor &out) {
+  const BackendConfig &cfg = backend_config();
+  if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || !cfg.epilogue_stats || !cfg.defer_grads) return false;
+  if (a.shape.size() != 2U || w.shape.size() != 2U || out.shape.size() != 2U || a.shape[1U] != w.shape[0U]) return false;
+  const tcapint M = a.shape[0U], K = a.shape[1U], N = w.shape[1U];
+  if (out.shape[0U] != M || out.shape[1U] != N || out.stride[0U] != 1U || out.stride[1U] != M || out.offset || !covers_storage(out)) return false;
+  if ((M % 8U) || M < 64U || N < 32U || K < 32U) return false;
+  if (bias.storage->size != N || bias.storage->device != DeviceTag::GPU) return false;
+  return true;
+}
+} // namespace
+
+bool matmul_bias_gelu(const Tensor &a, const Tensor &w, const Tensor &bias, Tensor &h, Tensor &y) {
+  if (!tensor_core_linear_ok(a, w, bias, h)) return false;
+  if (y.shape != h.shape || y.stride != h.stride || y.offset || !covers_storage(y)) return false;
+  validate_all_same_device({&a, &w, &h, &y}, "matmul_bias_gelu");
+  const tcapint M = a.shape[0U], K = a.shape[1U], N = w.shape[1U];
+  Bf16Operand pa, pb;
+  if (!bf16_operand(a, a.stride[0U], a.stride[1U], M, K, true, pa) || !bf16_operand(w, w.stride[1U], w.stride[0U], N, K, false, pb)) return false;
+  const OutputShadow os = begin_output_shadow(y, N);
+  if (!os.ptr) return false;
+  const Dev dh = dev_out(h, "matmul_bias_gelu", true);
+  GpuRealStorage *ys = gpu_storage(y, "matmul_bias_gelu");
+  ys->device_ptr_overwrite(); // y's fp32 values are not written here: deferred below
+  weedcu_gemm_epilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.col_bias = dev_of(bias, "matmul_bias_gelu").ptr + bias.offset;
+  epi.activation = 1;
+  const int rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dh.ptr, h.stride[1U], os.ptr, M, M, N, K, &epi, dh.stream);
+  if (rc == WEEDCU_ENOSUP) return false; // (nothing was launched; both outputs are about to be overwritten by the caller's fallback)
+  throw_on_error(rc, "matmul_bias_gelu");
+  end_output_shadow(os);
+  defer_gelu_values(ys, h.storage, h.storage->size);
+  return true;
+}
+
+bool matmul_bias_lse(const Tensor &a, const Tensor &w, const Tensor &bias, Tensor &out) {
+  if (!tensor_core_linear_ok(a, w, bias, out)) return false;
+  validate_all_same_device({&a, &w, &out}, "matmul_bias_lse");
+  const tcapint M = a.shape[0U], K = a.shape[1U], N = w.shape[1U];
+  Bf16Operand pa, pb;
+  if (!bf16_operand(a, a.stride[0U], a.stride[1U], M, K, true, pa) || !bf16_operand(w, w.stride[1U], w.stride[0U], N, K, false, pb)) return false;
+  const OutputShadow os = begin_output_shadow(out, N);
+  if (!os.ptr) return false;
+  GpuRealStorage *cs = gpu_storage(out, "matmul_bias_lse");
+  cs->dev->Bind();
+  cs->device_ptr_overwrite();
+  const uint32_t cap = (N + 127U) / 128U;
+  BufferPtr stats = cs->dev->MakeBuffer(sizeof(real1) * 2U * (size_t)M * cap);
+  uint32_t tiles = 0U, tile_cols = 0U;
+  weedcu_gemm_epilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.col_bias = dev_of(bias, "matmul_bias_lse").ptr + bias.offset;
+  epi.row_stats = 2;
+  epi.stats = (float *)stats->ptr;
+  epi.stats_capacity_tiles = cap;
+  epi.stats_tiles = &tiles;
+  epi.stats_tile_cols = &tile_cols;
+  const int rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, nullptr, 0U, os.ptr, M, M, N, K, &epi, cs->dev->stream);
+  if (rc == WEEDCU_ENOSUP) return false;
+  throw_on_error(rc, "matmul_bias_lse");
+  end_output_shadow(os);
+  cs->row_stats = stats;
+  cs->row_stats_kind = 2;
+  cs->row_stats_tiles = tiles;
+  cs->row_stats_tile_cols = tile_cols;
+  cs->row_stats_rows = M;
+  cs->row_stats_cols = N;
+  cs->row_stats_version = cs->version;
+  defer_linear_output(cs, pa, pb, M, N, K, w, bias);
+  return true;
+}
+
+static const symint *sym_ptr(const SymbolTensor &s, const char *op);
+bool cross_entropy_fwd_from_stats(const Tensor &logits, const SymbolTensor &targets, Tensor &lse, Tensor &loss, tcapint rows, tcapint V) {
+  GpuRealStorage *ls = gpu_storage(logits, "cross_entropy_loss");
+  if (!ls->row_stats || ls->row_stats_kind != 2 || ls->row_stats_version != ls->version || !ls->gemm_source || logits.offset ||
+      ls->row_stats_rows != rows || ls->row_stats_cols != V)
+    return false;
+  const GpuRealStorage::GemmSource &src = *ls->gemm_source;
+  GpuRealStorage *ws = static_cast<GpuRealStorage *>(src.w_storage.get()), *bs = static_cast<GpuRealStorage *>(src.bias_storage.get());
+  if (ws->version != src.w_version || bs->version != src.bias_version) return false;
+  ls->dev->Bind();
+  const Dev dl = dev_out(lse, "cross_entropy_loss", true), dloss = dev_out(loss, "cross_entropy_loss", true);
+  throw_on_error(weedcu_cross_entropy_fwd_stats((const float *)ls->row_stats->ptr, ls->row_stats_tiles, rows, V, (const uint16_t *)src.a->ptr, src.a_major, src.lda,
+                                                (const uint16_t *)src.b->ptr, src.b_major, src.ldb, src.K, bs->device_ptr_ro() + src.bias_offset,
+                                                sym_ptr(targets, "cross_entropy_loss") + targets.offset, dl.ptr + lse.offset, dloss.ptr + loss.offset,
+                                                ls->dev->stream),
+                 "cross_entropy_loss");
+  return true;
+}
+
 void pow(const Tensor &a, const real1 &p, Tensor &out) { unary(WEEDCU_POW, p, a, out, "pow"); }
 void exp(const Tensor &a, const real1 &b, Tensor &out) { unary(WEEDCU_EXP, (real1)std::log((real1_s)b), a, out, "exp"); }
 void log(const Tensor &a, const real1 &b, Tensor &out) {
@@ -611,7 +779,7 @@ bool matmul_bias(const Tensor &a, const Tensor &b, const Tensor &bias, Tensor &o
   return matmul_impl(a, b, out, 0, &bias, residual);
 }
 bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws, const std::vector<const Tensor *> &biases,
-                         const std::vector<Tensor *> &outs) {
+                         const std::vector<Tensor *> &outs, bool bf16_only) {
   const BackendConfig &cfg = backend_config();
   const size_t G = ws.size();
   if (cfg.matmul_precision != WEEDCU_GEMM_BF16 || !cfg.fused || !cfg.operand_cache || G < 2U || G > 3U || biases.size() != G || outs.size() != G) return false;
@@ -635,6 +803,34 @@ bool matmul_bias_grouped(const Tensor &a, const std::vector<const Tensor *> &ws,
   real1 *cptr[3];
   const real1 *biasptr[3];
   void *stream = nullptr;
+  if (bf16_only && cfg.epilogue_stats && cfg.defer_grads && (M % 8U) == 0U && N >= 32U) {
+    // the outputs' only reader is the attention core's head relayout, which takes the bf16 operand copies: the products
+    // write those and nothing else (fp32 values deferred, like the LM head's logits)
+    OutputShadow os[3];
+    uint16_t *c16[3];
+    bool ok = true;
+    for (size_t g = 0U; g < G && ok; ++g) {
+      os[g] = begin_output_shadow(*outs[g], N);
+      ok = os[g].ptr != nullptr;
+      c16[g] = os[g].ptr;
+      bptr[g] = pb[g].ptr;
+      biasptr[g] = dev_of(*biases[g], "matmul_bias_grouped").ptr + biases[g]->offset;
+    }
+    if (ok) {
+      GpuRealStorage *first = gpu_storage(*outs[0], "matmul_bias_grouped");
+      first->dev->Bind();
+      for (size_t g = 0U; g < G; ++g) gpu_storage(*outs[g], "matmul_bias_grouped")->device_ptr_overwrite();
+      const int rc = weedcu_gemm_bf16_grouped_bf16out(pa.ptr, pa.major, pa.ld, (uint32_t)G, bptr, pb[0].major, pb[0].ld, c16, M, M, N, K, biasptr, first->dev->stream);
+      if (rc == 0) {
+        for (size_t g = 0U; g < G; ++g) {
+          end_output_shadow(os[g]);
+          defer_linear_output(gpu_storage(*outs[g], "matmul_bias_grouped"), pa, pb[g], M, N, K, *ws[g], *biases[g]);
+        }
+        return true;
+      }
+      if (rc != WEEDCU_ENOSUP) throw_on_error(rc, "matmul_bias_grouped");
+    }
+  }
   for (size_t g = 0U; g < G; ++g) {
     const Dev dc = dev_out(*outs[g], "matmul_bias_grouped", true);
     stream = dc.stream;
@@ -716,7 +912,6 @@ bool pack_with_column_sums(const Tensor &dy, Tensor &sums) {
   return true;
 }
 
-static const symint *sym_ptr(const SymbolTensor &s, const char *op);
 bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, const Tensor &lse, const Tensor &dloss, Tensor &dlogits,
                             tcapint rows, tcapint V) {
   const BackendConfig &cfg = backend_config();
@@ -737,12 +932,25 @@ bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, c
     ds->colsum = ds->dev->MakeBuffer(sizeof(real1) * (size_t)V);
     ds->colsum_n = V;
   }
-  const Dev dl = dev_of(logits, "cross_entropy_bwd_pack"), dlse = dev_of(lse, "cross_entropy_bwd_pack"), dg = dev_of(dloss, "cross_entropy_bwd_pack");
+  // logits whose fp32 values are still deferred (the LM head's epilogue wrote the bf16 copy only): read that copy
+  GpuRealStorage *lgs = gpu_storage(logits, "cross_entropy_bwd_pack");
+  const uint16_t *logits_bf16 = nullptr;
+  if (lgs->deferred_values && !logits.offset)
+    for (const GpuRealStorage::Bf16Shadow &sh : lgs->shadows)
+      if (sh.offset == 0U && sh.n_fast == rows && sh.n_slow == V && sh.s_fast == 1U && sh.s_slow == rows && sh.version == lgs->version)
+        logits_bf16 = (const uint16_t *)sh.buf->ptr;
+  const Dev dlse = dev_of(lse, "cross_entropy_bwd_pack"), dg = dev_of(dloss, "cross_entropy_bwd_pack");
   const bool defer = !accumulate && cfg.defer_grads && covers_storage(dlogits);
   real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
-  const int rc = weedcu_cross_entropy_bwd_pack(dl.ptr, logits.offset, rows, V, sym_ptr(targets, "cross_entropy_bwd_pack") + targets.offset, dlse.ptr + lse.offset,
-                                               dg.ptr + dloss.offset, defer ? nullptr : out, dlogits.offset, accumulate, (uint16_t *)hit->buf->ptr,
-                                               (real1 *)ds->colsum->ptr, ds->dev->stream);
+  int rc;
+  if (logits_bf16)
+    rc = weedcu_cross_entropy_bwd_pack_bf16in(logits_bf16, rows, V, sym_ptr(targets, "cross_entropy_bwd_pack") + targets.offset, dlse.ptr + lse.offset,
+                                              dg.ptr + dloss.offset, defer ? nullptr : out, dlogits.offset, accumulate, (uint16_t *)hit->buf->ptr,
+                                              (real1 *)ds->colsum->ptr, ds->dev->stream);
+  else
+    rc = weedcu_cross_entropy_bwd_pack(dev_of(logits, "cross_entropy_bwd_pack").ptr, logits.offset, rows, V, sym_ptr(targets, "cross_entropy_bwd_pack") + targets.offset,
+                                       dlse.ptr + lse.offset, dg.ptr + dloss.offset, defer ? nullptr : out, dlogits.offset, accumulate,
+                                       (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr, ds->dev->stream);
   if (rc == WEEDCU_ENOSUP) {
     // nothing was launched; the caller's plain kernel must see the pending zero fill again if we dropped it
     if (!accumulate) ds->FillZeros();
@@ -770,6 +978,28 @@ bool cross_entropy_bwd_pack(const Tensor &logits, const SymbolTensor &targets, c
     };
   }
   return true;
+}
+
+// the bf16 attention entry; q / k / v whose fp32 values are deferred behind a current bf16 copy are read through that copy
+int attention_forward_bf16(const Tensor &q, const Tensor &k, const Tensor &v, Tensor &out, uint16_t *out_bf16, tcapint B, tcapint T, tcapint H, tcapint hd,
+                           real1 divisor, real1 mask_val, int causal) {
+  auto current_copy = [&](const Tensor &t) -> const uint16_t * {
+    GpuRealStorage *s = gpu_storage(t, "attention");
+    const tcapint rows = B * T, cols = H * hd;
+    if (!s->deferred_values || t.offset) return nullptr;
+    for (const GpuRealStorage::Bf16Shadow &sh : s->shadows)
+      if (sh.offset == 0U && sh.n_fast == rows && sh.n_slow == cols && sh.s_fast == 1U && sh.s_slow == rows && sh.version == s->version)
+        return (const uint16_t *)sh.buf->ptr;
+    return nullptr;
+  };
+  const uint16_t *q16 = current_copy(q), *k16 = current_copy(k), *v16 = current_copy(v);
+  const Dev dout = dev_out(out, "attention", true);
+  if (q16 && k16 && v16) {
+    const int rc = weedcu_attention_fwd_bf16in(q16, k16, v16, dout.ptr, out_bf16, B, T, H, hd, divisor, mask_val, causal, dout.stream);
+    if (rc != WEEDCU_ENOSUP) return rc;
+  }
+  return weedcu_attention_fwd_bf16out(dev_of(q, "attention").ptr + q.offset, dev_of(k, "attention").ptr + k.offset, dev_of(v, "attention").ptr + v.offset,
+                                      dout.ptr, out_bf16, B, T, H, hd, divisor, mask_val, causal, dout.stream);
 }
 
 void matmul_batched(const Tensor &a3, const Tensor &b3, Tensor &out3) {

@@ -629,6 +629,16 @@ WEED_NODE_ONLY(make_sin_node, Weed::sin_grad, a)
 WEED_NODE_ONLY(make_cos_node, Weed::cos_grad, a)
 #undef WEED_NODE_ONLY
 
+void Tensor::make_gelu_node(TensorPtr a, TensorPtr out) { // the node unary_op gives the fused Tensor::gelu
+  out->make_gradient();
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) node_owner_lost();
+    TensorPtr a_grad = full_grad(a);
+    Weed::gelu_grad(*a_grad, *a, *(out->grad));
+    settle_grad(a, a_grad);
+  });
+}
 TensorPtr Tensor::gelu(const TensorPtr x) { // tensor.cpp:841-851
   if (backend_config().fused) return unary_op(x, Weed::gelu, Weed::gelu_grad, false);
   const real1 k0 = real1(0.5), k1 = real1(0.044715), k2 = real1(0.7978845608028654);
@@ -1000,8 +1010,35 @@ TensorPtr Tensor::linear(TensorPtr a, TensorPtr w, TensorPtr bias, TensorPtr res
   if (needs_flatten) a2 = reshape(a, {batch * M, K});
   const tcapint as0 = a2->shape[0U];
   TensorPtr out = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
-  if (!Weed::matmul_bias(*a2, *w, *bias, *out, residual.get())) return nullptr;
+  // a vocabulary-sized output that takes part in autograd is the LM head in front of cross_entropy_loss: its epilogue leaves
+  // the bf16 copy the backward reads and the log-sum-exp partials the loss reads; the 4 B/elem fp32 logits are not written
+  const bool lm_head = !residual && !skinny && rg && cfg.epilogue_stats && (tcapint)N >= cfg.lm_head_min_cols;
+  if (!(lm_head && Weed::matmul_bias_lse(*a2, *w, *bias, *out)) && !Weed::matmul_bias(*a2, *w, *bias, *out, residual.get())) return nullptr;
   return finish_linear(a, w, bias, out, rg, residual);
+}
+
+// gelu(x W + bias) with the activation in the GEMM epilogue: the pre-activation h keeps the Linear node, y = gelu(h) the
+// GELU node, exactly as Linear::forward followed by Tensor::gelu builds them; nullptr when the fused kernel does not apply
+TensorPtr Tensor::linear_gelu(TensorPtr a, TensorPtr w, TensorPtr bias) {
+  const BackendConfig &cfg = backend_config();
+  if (!cfg.fused || !cfg.epilogue_stats || cfg.matmul_precision != WEEDCU_GEMM_BF16) return nullptr;
+  if (a->shape.size() < 2U || w->shape.size() != 2U || (symint)w->shape[0U] != (symint)a->shape.back()) return nullptr;
+  if (a->storage->device != DeviceTag::GPU || w->storage->device != DeviceTag::GPU || bias->storage->device != DeviceTag::GPU) return nullptr;
+  if (bias->storage->size != w->shape[1U] || bias->get_size() != w->shape[1U]) return nullptr;
+  const bool rg = a->requires_grad || w->requires_grad || bias->requires_grad;
+  const symint K = (symint)a->shape.back(), M = (symint)a->shape[a->shape.size() - 2], N = (symint)w->shape[1U];
+  symint batch = 1;
+  for (size_t i = 0; i < a->shape.size() - 2; ++i) batch *= (symint)a->shape[i];
+  TensorPtr a2 = a;
+  if (a->shape.size() > 2U) a2 = reshape(a, {batch * M, K});
+  const tcapint as0 = a2->shape[0U];
+  TensorPtr h = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
+  TensorPtr y = allocate_like(std::vector<tcapint>{as0, (tcapint)N}, std::vector<tcapint>{1U, as0}, *a2, DType::REAL, rg, false);
+  if (!Weed::matmul_bias_gelu(*a2, *w, *bias, *h, *y)) return nullptr;
+  h = finish_linear(a, w, bias, h, rg);
+  if (h->shape.size() != 2U) y->BaseTensor::reshape(std::vector<symint>(h->shape.begin(), h->shape.end()));
+  if (rg) make_gelu_node(h, y);
+  return y;
 }
 
 // everything Tensor::linear does after the product: final shape, the Parameter mutation of `y + bias`, the node
@@ -1048,7 +1085,7 @@ TensorPtr Tensor::finish_linear(TensorPtr a, TensorPtr w, TensorPtr bias, Tensor
   return out;
 }
 
-std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases) {
+std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<TensorPtr> &ws, const std::vector<TensorPtr> &biases, bool bf16_only) {
   const BackendConfig &cfg = backend_config();
   const size_t G = ws.size();
   if (!cfg.fused || G < 2U || G > 3U || biases.size() != G) return {};
@@ -1082,7 +1119,7 @@ std::vector<TensorPtr> Tensor::linear_grouped(TensorPtr a, const std::vector<Ten
     bp[g] = biases[g].get();
     op[g] = outs[g].get();
   }
-  if (!(skinny ? Weed::matmul_skinny_grouped(*a2, wp, bp, op) : Weed::matmul_bias_grouped(*a2, wp, bp, op))) return {};
+  if (!(skinny ? Weed::matmul_skinny_grouped(*a2, wp, bp, op) : Weed::matmul_bias_grouped(*a2, wp, bp, op, bf16_only))) return {};
   for (size_t g = 0U; g < G; ++g) outs[g] = finish_linear(a, ws[g], biases[g], outs[g], rgs[g]);
   return outs;
 }
