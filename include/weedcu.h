@@ -256,6 +256,12 @@ int weedcu_cross_entropy_bwd_pack(const float *logits, uint64_t offset, uint32_t
 int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda,
                                    const uint16_t *b, int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets,
                                    float *lse, float *loss, void *stream);
+/* cross_entropy_loss forward reading the bf16 copy of the logits ([rows, V] dense, rows contiguous, rows % 8 == 0; what
+ * weedcu_gemm_bf16_ex leaves when the fp32 logits are not written): 2 B/elem instead of 4. The target logit of each row is
+ * recomputed exactly from the product's operands as in weedcu_cross_entropy_fwd_stats. */
+int weedcu_cross_entropy_fwd_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda,
+                                    const uint16_t *b, int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets,
+                                    float *lse, float *loss, void *stream);
 /* weedcu_cross_entropy_bwd_pack reading the bf16 copy of the logits ([rows, V] dense, rows contiguous) instead of fp32. */
 int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse,
                                          const float *dloss, float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16,
@@ -419,8 +425,9 @@ int weedcu_gemm_bf16_residual(const uint16_t *a, int a_major, uint64_t lda, cons
  *   epi->row_stats 2: stats[t][m] = (max, sum exp(x - max)) of row m over tile t — the log-sum-exp partials of
  *            cross_entropy_loss (include/autograd/cross_entropy_loss.hpp:21-34), merged by weedcu_cross_entropy_fwd_stats
  *   *epi->stats_tiles / *epi->stats_tile_cols (host, written before the call returns): number of column tiles and their
- *            width; tile t covers columns [t * cols, min(N, (t + 1) * cols)). stats holds stats_capacity_tiles * M * 2 floats
- *            (>= ceil(N / 128) tiles is always enough).
+ *            width; partial t covers columns [t * cols, min(N, (t + 1) * cols)) (empty when t * cols >= N: it then holds
+ *            (0, 0) resp. (-inf, 0)). stats holds stats_capacity_tiles * M * 2 floats (>= 2 * ceil(N / 128) is always enough: the
+ *            kernel leaves one partial per half of a >= 128-wide column tile).
  * C is stored (no accumulate, no split-K). WEEDCU_ENOSUP when the outputs do not meet the TMA store rules. */
 typedef struct weedcu_gemm_epilogue {
   const float *col_bias;

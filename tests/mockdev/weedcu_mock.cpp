@@ -357,6 +357,20 @@ int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t 
   *loss = (float)(-total / rows);
   return 0;
 }
+int weedcu_cross_entropy_fwd_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda, const uint16_t *b, int b_major,
+                                    uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets, float *lse, float *loss, void *stream) {
+  if (!logits_bf16) return WEEDCU_EINVAL;
+  if (rows % 8u) return WEEDCU_ENOSUP;
+  std::vector<float> stats(2 * (size_t)rows); // one partial per row over the whole vocabulary
+  for (uint32_t r = 0; r < rows; ++r) {
+    double M = -1.0 / 0.0, S = 0.0;
+    for (uint32_t v = 0; v < V; ++v) M = bf16_widen(logits_bf16[r + (uint64_t)v * rows]) > M ? bf16_widen(logits_bf16[r + (uint64_t)v * rows]) : M;
+    for (uint32_t v = 0; v < V; ++v) S += exp((double)bf16_widen(logits_bf16[r + (uint64_t)v * rows]) - M);
+    stats[2 * (size_t)r] = (float)M;
+    stats[2 * (size_t)r + 1] = (float)S;
+  }
+  return weedcu_cross_entropy_fwd_stats(stats.data(), 1, rows, V, a, a_major, lda, b, b_major, ldb, K, col_bias, targets, lse, loss, stream);
+}
 int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss,
                                          float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *stream) {
   if (!logits_bf16) return WEEDCU_EINVAL;

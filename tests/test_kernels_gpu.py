@@ -323,6 +323,8 @@ def _merge_ln(stats, tiles, cols, N):
     n, mean, m2 = 0.0, 0.0, 0.0
     for t in range(tiles):
         cnt = min(N, (t + 1) * cols) - t * cols
+        if cnt <= 0:
+            continue
         mt, m2t = stats[t, :, 0].astype(np.float64), stats[t, :, 1].astype(np.float64)
         tot = n + cnt
         delta = mt - mean
@@ -349,7 +351,7 @@ def test_gemm_bf16_ex_epilogue(gpu, M, N, K, mode):
     bias = rng.uniform(-2, 2, N).astype(np.float32)
     pa, pb, hres, hbias = gpu.buf(a_dev), gpu.buf(b_dev), gpu.buf(res), gpu.buf(bias)
     plain, plain_res = gpu.buf(np.zeros(M * N, np.float32)), gpu.buf(np.zeros(M * N, np.float32))
-    cap = (N + 127) // 128
+    cap = 2 * ((N + 127) // 128)
     r8 = (M + 7) // 8 * 8
     if M % 8:
         pytest.skip("bf16 outputs need a leading dimension that is a multiple of 8 == M for a dense operand copy")
@@ -371,7 +373,7 @@ def test_gemm_bf16_ex_epilogue(gpu, M, N, K, mode):
         c = gpu.buf(np.full(M * N, 9.0, np.float32))
         st, tiles, cols = run(c, None, residual=hres.ptr, stats=1)
         assert np.array_equal(c.get().reshape(N, M), want_res)
-        assert tiles == (N + cols - 1) // cols and tiles <= cap
+        assert tiles >= (N + cols - 1) // cols and tiles <= cap
         mean, var = _merge_ln(st, tiles, cols, N)
         w64 = want_res.astype(np.float64)
         assert np.max(np.abs(mean - w64.mean(0))) <= 1e-6 * np.abs(w64).max()

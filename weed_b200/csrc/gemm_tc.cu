@@ -19,8 +19,16 @@
 namespace weedcu {
 namespace tc {
 
-constexpr uint32_t NUM_THREADS = 256;
-constexpr uint32_t EPI_WARP0 = 4;  // warps 4..7 = epilogue (warpgroup-aligned: TMEM lane quarter = warp % 4)
+// Warps 4..11 = epilogue, two per scheduler. A warp may only read the TMEM lane quarter warp % 4, so warps w and w + 4
+// share a quarter and split the tile's columns: group 0 (warps 4..7) takes the left half of the tile, group 1 (warps 8..11)
+// the right half. One epilogue warp per scheduler was latency-bound on its own dependent instruction chain (ncu: 4 warps at
+// ~0.3 IPC each; the per-chunk cost did not move with the bytes stored) and that chain, not the stores, was the ~6 us
+// "epilogue floor" per 256-wide tile that held the K = 768 products at 0.35-0.6 of the tensor peak.
+constexpr uint32_t NUM_THREADS = 384;
+constexpr uint32_t EPI_WARP0 = 4;
+constexpr uint32_t EPI_GROUPS = 2;
+// staging slot s of a tile (the order the store warp drains them): group s % 2, chunk (s / 2) + (s % 2) * (chunks / 2)
+__device__ __forceinline__ uint32_t slot_chunk(uint32_t s, uint32_t chunks) { return (s >> 1) + (s & 1u) * (chunks >> 1); }
 
 struct Params {
   float *c;
@@ -56,35 +64,40 @@ struct Params {
 struct RowStats {
   float a, b, n;
 };
+// The epilogue warps are latency-bound (one warp per scheduler walking a dependent chain per chunk), so every reduction
+// below runs on four independent accumulators: a 32-long serial FADD chain per chunk cost ~20 % of the K = 768 products.
 __device__ __forceinline__ void row_stats_update(int kind, RowStats &s, const uint32_t (&r)[32], uint32_t valid) {
   if (valid == 0) return;
   if (kind == 1) { // Chan's parallel update with this chunk's (count, mean, M2)
-    float sum = 0.0f;
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) sum += (j < valid) ? __uint_as_float(r[j]) : 0.0f;
-    const float cnt = (float)valid, mean_c = sum / cnt;
-    float m2 = 0.0f;
+    for (uint32_t j = 0; j < 32; ++j) a4[j & 3u] += (j < valid) ? __uint_as_float(r[j]) : 0.0f;
+    const float cnt = (float)valid, mean_c = ((a4[0] + a4[1]) + (a4[2] + a4[3])) / cnt;
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (uint32_t j = 0; j < 32; ++j) {
       const float d = __uint_as_float(r[j]) - mean_c;
-      m2 += (j < valid) ? d * d : 0.0f;
+      q4[j & 3u] += (j < valid) ? d * d : 0.0f;
     }
+    const float m2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     const float n = s.n + cnt, delta = mean_c - s.a;
     s.a += delta * (cnt / n);
     s.b += m2 + delta * delta * (s.n * cnt / n);
     s.n = n;
   } else { // online (max, sum exp)
-    float mx = -INFINITY;
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) mx = fmaxf(mx, (j < valid) ? __uint_as_float(r[j]) : -INFINITY);
+    for (uint32_t j = 0; j < 32; ++j) m4[j & 3u] = fmaxf(m4[j & 3u], (j < valid) ? __uint_as_float(r[j]) : -INFINITY);
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     if (mx > s.a) {
       s.b *= __expf(s.a - mx);
       s.a = mx;
     }
-    float e = 0.0f;
+    const float base = s.a;
+    float e4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) e += (j < valid) ? __expf(__uint_as_float(r[j]) - s.a) : 0.0f;
-    s.b += e;
+    for (uint32_t j = 0; j < 32; ++j) e4[j & 3u] += (j < valid) ? __expf(__uint_as_float(r[j]) - base) : 0.0f;
+    s.b += (e4[0] + e4[1]) + (e4[2] + e4[3]);
     s.n += (float)valid;
   }
 }
@@ -96,34 +109,47 @@ __device__ __forceinline__ float gelu_for_bf16(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k2 * (x + k1 * (x * x) * x)));
   return (0.5f * x) * (1.0f + t);
 }
-__device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
 // what the extended epilogue does with one finished chunk (bias / residual already added): statistics, then either the
-// bf16 staging tile (out_mode 1; returns true: the fp32 staging store is skipped) or the direct bf16 copy (out_mode 2)
+// bf16 staging tile (out_mode 1; returns true: the fp32 staging store is skipped) or the direct bf16 copy (out_mode 2).
+// All values are converted before the first store, and adjacent lanes (rows m, m + 1) swap one value per column pair so
+// that every store carries two bf16 rows in one 32-bit word: 16 stores per chunk instead of 32 sub-word ones.
 __device__ __forceinline__ bool epilogue_ext_chunk(const Params &p, const uint32_t (&r)[32], RowStats &rs, uint32_t m, uint32_t n_chunk0,
                                                    uint32_t z, uint32_t buf, uint32_t row_in_tile) {
   const uint32_t valid = n_chunk0 < p.N ? min(32u, p.N - n_chunk0) : 0u;
   if (p.stats_kind) row_stats_update(p.stats_kind, rs, r, valid);
-  if (p.out_mode == 1) {
-    const uint32_t dst = buf + row_in_tile * 2;
+  if (p.out_mode == 0) return false;
+  float v[32];
+  if (p.act) {
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) {
-      const float v = __uint_as_float(r[j]);
-      st_shared_b16(dst + j * (BLOCK_M * 2), __bfloat16_as_ushort(__float2bfloat16_rn(p.act ? gelu_for_bf16(v) : v)));
-    }
+    for (uint32_t j = 0; j < 32; ++j) v[j] = gelu_for_bf16(__uint_as_float(r[j]));
+  } else {
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  }
+  const uint32_t odd = row_in_tile & 1u;
+  uint32_t w[16]; // w[i]: column 2i + odd, rows (m & ~1, m | 1) as bf16x2
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i) {
+    const float got = __shfl_xor_sync(0xffffffffu, odd ? v[2 * i] : v[2 * i + 1], 1);
+    const __nv_bfloat162 h = odd ? __floats2bfloat162_rn(got, v[2 * i + 1]) : __floats2bfloat162_rn(v[2 * i], got);
+    w[i] = *reinterpret_cast<const uint32_t *>(&h);
+  }
+  if (p.out_mode == 1) {
+    const uint32_t dst = buf + (row_in_tile & ~1u) * 2 + odd * (BLOCK_M * 2);
+#pragma unroll
+    for (uint32_t i = 0; i < 16; ++i) st_shared_f32(dst + i * (2 * BLOCK_M * 2), w[i]);
     return true;
   }
-  if (p.out_mode == 2 && m < p.M) {
-    __nv_bfloat16 *d16 = p.c16 + (uint64_t)z * p.c_bs + m + (uint64_t)n_chunk0 * p.ldc16;
+  // out_mode 2: rows (m & ~1, m | 1) of one column are 4 contiguous bytes of the dense bf16 copy (M % 8 == 0)
+  if ((m | 1u) < p.M) {
+    uint32_t *d16 = reinterpret_cast<uint32_t *>(p.c16 + (uint64_t)z * p.c_bs + (m & ~1u) + (uint64_t)(n_chunk0 + odd) * p.ldc16);
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) {
-      const float v = __uint_as_float(r[j]);
-      if (j < valid) d16[(uint64_t)j * p.ldc16] = __float2bfloat16_rn(p.act ? gelu_for_bf16(v) : v);
-    }
+    for (uint32_t i = 0; i < 16; ++i)
+      if (2 * i + odd < valid) d16[(uint64_t)i * p.ldc16] = w[i]; // (2 columns further = ldc16 32-bit words)
   }
   return false;
 }
+
 
 constexpr uint32_t kMaxGroups = 3;
 struct alignas(64) TensorMaps {
@@ -196,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 4 * EPI_GROUPS); // one arrive per epilogue warp
     }
     for (uint32_t b = 0; b < EPI_BUFS; ++b) {
       mbar_init(efull_bar(b), 4);
@@ -296,7 +322,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t m0 = (t % p.tiles_m) * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
         const CUtensorMap *tmC = &tmCs.m[grp];
         const bool reduce = p.accumulate || p.splits > 1;
-        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+        for (uint32_t sl = 0; sl < BLOCK_N / EPI_COLS; ++sl, ++epi_chunk) {
+          const uint32_t c0 = slot_chunk(sl, BLOCK_N / EPI_COLS) * EPI_COLS;
           const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
           mbar_wait(efull_bar(eb), (epi_chunk / EPI_BUFS) & 1u);
           if (n0 + c0 < p.N) { // TMA clips rows/columns beyond M/N
@@ -315,8 +342,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue: TMEM -> registers -> global C ==========
     const uint32_t q = warp & 3; // TMEM lanes [32q, 32q+32)
+    const uint32_t eg = (warp - EPI_WARP0) >> 2; // column half of the tile this warp drains
+    constexpr uint32_t CHUNKS = BLOCK_N / EPI_COLS;
     const uint32_t sEpi = base + L::EPI_OFF;
-    uint32_t it = 0, epi_chunk = 0;
+    uint32_t it = 0;
     for (uint32_t unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
@@ -337,7 +366,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
       };
-      if (has_res) load_res(0);
+      if (has_res) load_res(slot_chunk(eg, CHUNKS) * EPI_COLS);
       const bool ext = (p.out_mode | p.stats_kind) != 0;
       RowStats rs = {p.stats_kind == 2 ? -INFINITY : 0.0f, 0.0f, 0.0f};
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -347,23 +376,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // finished buffer into one TMA store (or reduce-add). The four epilogue warps never meet: a warp
         // owns rows [32q, 32q+32) of every buffer and hands over through the buffer's mbarriers.
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+        for (uint32_t sl = eg; sl < CHUNKS; sl += EPI_GROUPS) {
+          const uint32_t c0 = slot_chunk(sl, CHUNKS) * EPI_COLS, epi_chunk = it * CHUNKS + sl;
           const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
-          float bias_lane = 0.0f; // lane j holds the bias of column c0 + j
-          if (add_bias && n0 + c0 + lane < p.N) bias_lane = col_bias[n0 + c0 + lane];
+          // the 32 column biases: eight warp-uniform 128-bit loads when aligned and in range (a third fewer epilogue
+          // instructions than one value per lane + 32 shuffles), else lane j holds the bias of column c0 + j
+          const bool bias_vec = add_bias && n0 + c0 + 32u <= p.N && ((((uintptr_t)(col_bias + n0 + c0)) & 15u) == 0);
+          float4 b4[8];
+          float bias_lane = 0.0f;
+          if (bias_vec) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4 *>(col_bias + n0 + c0) + j);
+          } else if (add_bias && n0 + c0 + lane < p.N) {
+            bias_lane = col_bias[n0 + c0 + lane];
+          }
           tmem_ld_wait();
-          if (add_bias) {
+          if (bias_vec) {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+              r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4[j].x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4[j].y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4[j].z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4[j].w);
+            }
+          } else if (add_bias) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
           }
           if (has_res) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + rv[j]);
-            if (c0 + EPI_COLS < BLOCK_N) load_res(c0 + EPI_COLS); // next chunk's residual: in flight behind this chunk's staging
+            if (sl + EPI_GROUPS < CHUNKS) load_res(c0 + EPI_COLS); // next chunk's residual: in flight behind this chunk's staging
           }
-          if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the MMA warp early
+          if (sl + EPI_GROUPS >= CHUNKS) { // this warp's share of the accumulator is read: hand it back to the MMA warp early
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -378,12 +425,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(efull_bar(eb));
         }
-        if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)tn * p.M + m] = make_float2(rs.a, rs.b);
+        if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)(tn * EPI_GROUPS + eg) * p.M + m] = make_float2(rs.a, rs.b);
       } else {
         float *crow = c_base + (uint64_t)z * p.c_bs + m;
         const bool full_tile = (m0 + BLOCK_M <= p.M) && (n0 + BLOCK_N <= p.N);
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (uint32_t c0 = eg * (BLOCK_N / EPI_GROUPS); c0 < (eg + 1u) * (BLOCK_N / EPI_GROUPS); c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
           float bias_lane = 0.0f;
@@ -486,7 +533,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8); // 4 epilogue warps of each CTA of the pair
+      mbar_init(tempty_bar(a), 8 * EPI_GROUPS); // the epilogue warps of both CTAs of the pair
     }
     for (uint32_t b = 0; b < EPI_BUFS; ++b) {
       mbar_init(efull_bar(b), 4);
@@ -582,7 +629,8 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t m0 = (t % p.tiles_m) * PAIR_M + rank * BLOCK_M, n0 = (tn - grp * p.tiles_n_group) * BLOCK_N;
         const CUtensorMap *tmC = &tmCs.m[grp];
         const bool reduce = p.accumulate || p.splits > 1;
-        for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+        for (uint32_t sl = 0; sl < BLOCK_N / EPI_COLS; ++sl, ++epi_chunk) {
+          const uint32_t c0 = slot_chunk(sl, BLOCK_N / EPI_COLS) * EPI_COLS;
           const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
           mbar_wait(efull_bar(eb), (epi_chunk / EPI_BUFS) & 1u);
           if (n0 + c0 < p.N && m0 < p.M) {
@@ -601,8 +649,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue (both CTAs, own 128 rows) ================
     const uint32_t q = warp & 3;
+    const uint32_t eg = (warp - EPI_WARP0) >> 2; // column half of the tile this warp drains
+    constexpr uint32_t CHUNKS = BLOCK_N / EPI_COLS;
     const uint32_t sEpi = base + L::EPI_OFF;
-    uint32_t it = 0, epi_chunk = 0;
+    uint32_t it = 0;
     for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
@@ -619,29 +669,45 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (uint32_t j = 0; j < 32; ++j) rv[j] = (n0 + c0 + j < p.N) ? res[(uint64_t)j * p.ldr] : 0.0f;
       };
-      if (has_res) load_res(0);
+      if (has_res) load_res(slot_chunk(eg, CHUNKS) * EPI_COLS);
       const bool ext = (p.out_mode | p.stats_kind) != 0;
       RowStats rs = {p.stats_kind == 2 ? -INFINITY : 0.0f, 0.0f, 0.0f};
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += EPI_COLS, ++epi_chunk) {
+      for (uint32_t sl = eg; sl < CHUNKS; sl += EPI_GROUPS) {
+        const uint32_t c0 = slot_chunk(sl, CHUNKS) * EPI_COLS, epi_chunk = it * CHUNKS + sl;
         const uint32_t eb = epi_chunk % EPI_BUFS, buf = sEpi + eb * EPI_BUF_BYTES;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BLOCK_N + c0, r);
+        const bool bias_vec = add_bias && n0 + c0 + 32u <= p.N && ((((uintptr_t)(col_bias + n0 + c0)) & 15u) == 0);
+        float4 b4[8];
         float bias_lane = 0.0f;
-        if (add_bias && n0 + c0 + lane < p.N) bias_lane = col_bias[n0 + c0 + lane];
+        if (bias_vec) {
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4 *>(col_bias + n0 + c0) + j);
+        } else if (add_bias && n0 + c0 + lane < p.N) {
+          bias_lane = col_bias[n0 + c0 + lane];
+        }
         tmem_ld_wait();
-        if (add_bias) {
+        if (bias_vec) {
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) {
+            r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + b4[j].x);
+            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b4[j].y);
+            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b4[j].z);
+            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b4[j].w);
+          }
+        } else if (add_bias) {
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j));
         }
         if (has_res) {
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + rv[j]);
-          if (c0 + EPI_COLS < BLOCK_N) load_res(c0 + EPI_COLS);
+          if (sl + EPI_GROUPS < CHUNKS) load_res(c0 + EPI_COLS);
         }
-        if (c0 + EPI_COLS == BLOCK_N) { // accumulator fully read: hand it back to the leader's MMA warp
+        if (sl + EPI_GROUPS >= CHUNKS) { // this warp's share of the accumulator is read: hand it back to the leader's MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
@@ -656,7 +722,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(efull_bar(eb));
       }
-      if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)tn * p.M + m] = make_float2(rs.a, rs.b);
+      if (p.stats_kind && m < p.M) p.row_stats[(uint64_t)(tn * EPI_GROUPS + eg) * p.M + m] = make_float2(rs.a, rs.b);
     }
   }
   tcgen05_fence_before();
@@ -928,7 +994,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   TensorMaps tmBs, tmCs;
   int rc = make_operand_map(&tmA, a, a_major, M, K, lda, batch, a_bs, BLOCK_M);
   if (rc) return rc;
-  if (ext && ext->stats_kind && (N + block_n - 1) / block_n > ext->stats_capacity_tiles) return WEEDCU_EINVAL;
+  if (ext && ext->stats_kind && EPI_GROUPS * ((N + block_n - 1) / block_n) > ext->stats_capacity_tiles) return WEEDCU_EINVAL;
   if (ext) best_s = 1;
   Params p;
   p.c = bf16_only ? nullptr : c[0];
@@ -963,7 +1029,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   }
   if (best.variant == 1 && !best.pair && !ext) p.tma_store = 0;
   if (!p.tma_store && (residual || ext)) return WEEDCU_ENOSUP; // the residual add / extended epilogue live in the staged epilogue only
-  if (ext && ext->stats_tiles) *ext->stats_tiles = p.tiles_n;
+  if (ext && ext->stats_tiles) *ext->stats_tiles = p.tiles_n * EPI_GROUPS; // every column tile leaves one partial per epilogue group
   if (!p.tma_store) {
     if (best.pair) return WEEDCU_ENOSUP; // unreachable: pairs are only chosen when C meets the TMA rules
     for (uint32_t g = 0; g < kMaxGroups; ++g) tmCs.m[g] = tmA; // unused by the kernel, but must be valid descriptors
@@ -1179,7 +1245,7 @@ int weedcu_gemm_bf16_ex(const uint16_t *a, int a_major, uint64_t lda, const uint
                                               biases[0] ? biases : nullptr, epi ? epi->residual : nullptr, epi ? epi->ldr : 0, &ext);
   if (rc == 0 && epi && epi->row_stats) {
     if (epi->stats_tiles) *epi->stats_tiles = tiles;
-    if (epi->stats_tile_cols) *epi->stats_tile_cols = tiles ? (tiles == 1 ? N : (uint32_t)tc::last_block_n()) : 0;
+    if (epi->stats_tile_cols) *epi->stats_tile_cols = (uint32_t)tc::last_block_n() / tc::EPI_GROUPS; // the half tile one epilogue group drains
   }
   return rc;
 }

@@ -261,7 +261,7 @@ layernorm_fwd_apply_stats_kernel(const float *__restrict__ x, uint32_t rows, uin
   if (r >= rows) return;
   float mu[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
   float n = 0.0f;
-  for (uint32_t t = 0; t < tiles; ++t) {
+  for (uint32_t t = 0; t < tiles && t * tile_cols < F; ++t) { // (trailing partials beyond F are empty)
     const float cnt = (float)(min(F, (t + 1u) * tile_cols) - t * tile_cols), tot = n + cnt;
     const float4 a = *reinterpret_cast<const float4 *>(stats + (uint64_t)t * rows + r);      // rows r, r+1
     const float4 b = *reinterpret_cast<const float4 *>(stats + (uint64_t)t * rows + r + 2u); // rows r+2, r+3
@@ -613,7 +613,7 @@ int weedcu_layernorm_fwd_stats(const float *x, uint32_t rows, uint32_t F, const 
                                const float *gamma, const float *beta, float eps, float *y, float *mean, float *rstd, uint16_t *y_bf16,
                                void *stream) {
   if (!x || !stats || !gamma || !beta || !y || !rows || !F || !tiles || !tile_cols) return WEEDCU_EINVAL;
-  if ((uint64_t)tiles * tile_cols < F || (uint64_t)(tiles - 1u) * tile_cols >= F) return WEEDCU_EINVAL; // the tiles must cover [0, F) exactly
+  if ((uint64_t)tiles * tile_cols < F) return WEEDCU_EINVAL; // the tiles must cover [0, F)
   const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
   if ((rows % 4u) || !aligned16(x) || !aligned16(y) || !aligned16(stats) || (y_bf16 && !aligned16(y_bf16)) || (mean && !aligned16(mean)) ||
       (rstd && !aligned16(rstd)) || fgroups > 65535u)

@@ -520,6 +520,76 @@ ce_fwd_finish(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
   lse[r] = M + log_s;
   nll[r] = (xt - M) - log_s; // = lsm[r, target]
 }
+// Online (max, sum exp) partials from the bf16 copy of the logits ([rows, V], rows contiguous, rows % 8 == 0): a thread
+// owns 8 adjacent rows (one 128-bit load per vocabulary entry), a block 256 rows x a vocabulary slice. 2 B/elem read
+// instead of 4; partials in the (max, sum) pair layout ce_fwd_stats_finish merges.
+__global__ void __launch_bounds__(kCeRT * kCeBY)
+ce_fwd_partial_bf16(const __nv_bfloat16 *__restrict__ x, uint32_t rows, uint32_t V, uint32_t v_per_block, float2 *__restrict__ part) {
+  pdl_grid_sync();
+  __shared__ __align__(16) float red_m[kCeBY][8 * kCeRT];
+  __shared__ __align__(16) float red_s[kCeBY][8 * kCeRT];
+  const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+  const uint32_t r = (blockIdx.x * kCeRT + tx) * 8u;
+  const bool live = r < rows;
+  const uint32_t v0 = blockIdx.y * v_per_block, v1 = min(V, v0 + v_per_block);
+  float mx[8], s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mx[k] = -INFINITY;
+    s[k] = 0.0f;
+  }
+  constexpr int U = 4;
+  if (live)
+    for (uint32_t j0 = v0 + ty; j0 < v1; j0 += kCeBY * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = j0 + u * kCeBY;
+        v[u] = (j < v1) ? *reinterpret_cast<const uint4 *>(x + (uint64_t)j * rows + r) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u); // -inf
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t w = (k < 2) ? v[u].x : (k < 4) ? v[u].y : (k < 6) ? v[u].z : v[u].w;
+          e[u] = __uint_as_float((k & 1) ? (w & 0xffff0000u) : (w << 16));
+        }
+        float m4 = e[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) m4 = fmaxf(m4, e[u]);
+        if (m4 > mx[k]) {
+          s[k] *= expf(mx[k] - m4);
+          mx[k] = m4;
+        }
+        if (mx[k] > -INFINITY) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) s[k] += expf(e[u] - mx[k]);
+        }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red_m[ty][8 * tx + k] = mx[k];
+    red_s[ty][8 * tx + k] = s[k];
+  }
+  __syncthreads();
+  const uint32_t t = ty * kCeRT + tx; // 256 threads, 256 rows: each merges one row
+  const uint32_t rr = blockIdx.x * 8 * kCeRT + t;
+  if (rr < rows) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int y = 0; y < kCeBY; ++y) M = fmaxf(M, red_m[y][t]);
+    float S = 0.0f;
+#pragma unroll
+    for (int y = 0; y < kCeBY; ++y) {
+      const float my = red_m[y][t];
+      if (my > -INFINITY) S += red_s[y][t] * expf(my - M);
+    }
+    part[(uint64_t)blockIdx.y * rows + rr] = make_float2(M, S);
+  }
+}
+
 // Forward from the log-sum-exp partials the LM head's GEMM epilogue left (weedcu_gemm_bf16_ex, row_stats 2): merge the
 // per-column-tile (max, sum exp), and recompute the ONE logit the loss needs per row — the target column — as the same
 // bf16 x bf16 -> fp32 dot product (+ bias) the tensor cores formed, from the GEMM's own operands. Thread per row.
@@ -1031,6 +1101,34 @@ int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t r
     launch_k(ce_colsum_finish_kernel, dim3((V + 255u) / 256u), dim3(256), 0, st, part, nchunks, V, colsum);
     rc = after_launch();
   }
+  pool_free(part, st);
+  return rc;
+}
+
+int weedcu_cross_entropy_fwd_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const uint16_t *a, int a_major, uint64_t lda,
+                                    const uint16_t *b, int b_major, uint64_t ldb, uint32_t K, const float *col_bias, const int32_t *targets,
+                                    float *lse, float *loss, void *stream) {
+  if (!logits_bf16 || !rows || !V || !a || !b || !K || !targets || !lse || !loss) return WEEDCU_EINVAL;
+  if ((rows % 8u) || !aligned16(logits_bf16)) return WEEDCU_ENOSUP;
+  cudaStream_t st = resolve_stream(stream);
+  const uint32_t row_tiles = (rows + 8 * kCeRT - 1) / (8 * kCeRT);
+  uint32_t want = (8u * kNumSMs + row_tiles - 1) / row_tiles;
+  const uint32_t max_splits = (V + kCeBY * 4 - 1) / (kCeBY * 4);
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  uint32_t vpb = (V + want - 1) / want;
+  vpb = (vpb + kCeBY * 4 - 1) / (kCeBY * 4) * (kCeBY * 4);
+  const uint32_t splits = (V + vpb - 1) / vpb;
+  float2 *part = nullptr;
+  WCU_CHECK(pool_alloc((void **)&part, sizeof(float2) * (size_t)rows * splits, st));
+  int rc;
+  {
+    ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 2.0 * (double)rows * V);
+    launch_k(ce_fwd_partial_bf16, dim3(row_tiles, splits), dim3(kCeRT, kCeBY), 0, st, (const __nv_bfloat16 *)logits_bf16, rows, V, vpb, part);
+    rc = after_launch();
+  }
+  if (rc == 0)
+    rc = weedcu_cross_entropy_fwd_stats((const float *)part, splits, rows, V, a, a_major, lda, b, b_major, ldb, K, col_bias, targets, lse, loss, stream);
   pool_free(part, st);
   return rc;
 }

@@ -327,7 +327,7 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
       if (residual && cfg.epilogue_stats && !out.offset && covers_storage(out) && N <= 8U * 128U) {
         // the residual sum is what the next LayerNorm normalises: its epilogue leaves the per-row (mean, M2) partials, and
         // LayerNorm::forward skips its statistics pass over the tensor (layernorm_forward below)
-        BufferPtr stats = cs->dev->MakeBuffer(sizeof(real1) * 2U * (size_t)M * 8U);
+        BufferPtr stats = cs->dev->MakeBuffer(sizeof(real1) * 2U * (size_t)M * 16U); // <= 2 * ceil(N / 128) partials per row
         uint32_t tiles = 0U, tile_cols = 0U;
         weedcu_gemm_epilogue epi;
         memset(&epi, 0, sizeof(epi));
@@ -336,7 +336,7 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
         epi.ldr = out.stride[1U];
         epi.row_stats = 1;
         epi.stats = (float *)stats->ptr;
-        epi.stats_capacity_tiles = 8U;
+        epi.stats_capacity_tiles = 16U;
         epi.stats_tiles = &tiles;
         epi.stats_tile_cols = &tile_cols;
         rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr, out.stride[1U], nullptr, 0U, M, N, K, &epi, dc.stream);
@@ -597,28 +597,15 @@ bool matmul_bias_lse(const Tensor &a, const Tensor &w, const Tensor &bias, Tenso
   GpuRealStorage *cs = gpu_storage(out, "matmul_bias_lse");
   cs->dev->Bind();
   cs->device_ptr_overwrite();
-  const uint32_t cap = (N + 127U) / 128U;
-  BufferPtr stats = cs->dev->MakeBuffer(sizeof(real1) * 2U * (size_t)M * cap);
-  uint32_t tiles = 0U, tile_cols = 0U;
+  // (log-sum-exp partials from this epilogue were measured too: 412 M exps on the eight epilogue warps cost +320 us on
+  //  the 8192 x 50257 product, more than the 2 B/elem pass over the bf16 logits that replaces them)
   weedcu_gemm_epilogue epi;
   memset(&epi, 0, sizeof(epi));
   epi.col_bias = dev_of(bias, "matmul_bias_lse").ptr + bias.offset;
-  epi.row_stats = 2;
-  epi.stats = (float *)stats->ptr;
-  epi.stats_capacity_tiles = cap;
-  epi.stats_tiles = &tiles;
-  epi.stats_tile_cols = &tile_cols;
   const int rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, nullptr, 0U, os.ptr, M, M, N, K, &epi, cs->dev->stream);
   if (rc == WEEDCU_ENOSUP) return false;
   throw_on_error(rc, "matmul_bias_lse");
   end_output_shadow(os);
-  cs->row_stats = stats;
-  cs->row_stats_kind = 2;
-  cs->row_stats_tiles = tiles;
-  cs->row_stats_tile_cols = tile_cols;
-  cs->row_stats_rows = M;
-  cs->row_stats_cols = N;
-  cs->row_stats_version = cs->version;
   defer_linear_output(cs, pa, pb, M, N, K, w, bias);
   return true;
 }
@@ -626,19 +613,23 @@ bool matmul_bias_lse(const Tensor &a, const Tensor &w, const Tensor &bias, Tenso
 static const symint *sym_ptr(const SymbolTensor &s, const char *op);
 bool cross_entropy_fwd_from_stats(const Tensor &logits, const SymbolTensor &targets, Tensor &lse, Tensor &loss, tcapint rows, tcapint V) {
   GpuRealStorage *ls = gpu_storage(logits, "cross_entropy_loss");
-  if (!ls->row_stats || ls->row_stats_kind != 2 || ls->row_stats_version != ls->version || !ls->gemm_source || logits.offset ||
-      ls->row_stats_rows != rows || ls->row_stats_cols != V)
-    return false;
+  if (!ls->deferred_values || !ls->gemm_source || logits.offset) return false;
   const GpuRealStorage::GemmSource &src = *ls->gemm_source;
+  if (src.M != rows || src.N != V) return false;
   GpuRealStorage *ws = static_cast<GpuRealStorage *>(src.w_storage.get()), *bs = static_cast<GpuRealStorage *>(src.bias_storage.get());
   if (ws->version != src.w_version || bs->version != src.bias_version) return false;
+  const uint16_t *logits_bf16 = nullptr;
+  for (const GpuRealStorage::Bf16Shadow &sh : ls->shadows)
+    if (sh.offset == 0U && sh.n_fast == rows && sh.n_slow == V && sh.s_fast == 1U && sh.s_slow == rows && sh.version == ls->version)
+      logits_bf16 = (const uint16_t *)sh.buf->ptr;
+  if (!logits_bf16) return false;
   ls->dev->Bind();
   const Dev dl = dev_out(lse, "cross_entropy_loss", true), dloss = dev_out(loss, "cross_entropy_loss", true);
-  throw_on_error(weedcu_cross_entropy_fwd_stats((const float *)ls->row_stats->ptr, ls->row_stats_tiles, rows, V, (const uint16_t *)src.a->ptr, src.a_major, src.lda,
-                                                (const uint16_t *)src.b->ptr, src.b_major, src.ldb, src.K, bs->device_ptr_ro() + src.bias_offset,
-                                                sym_ptr(targets, "cross_entropy_loss") + targets.offset, dl.ptr + lse.offset, dloss.ptr + loss.offset,
-                                                ls->dev->stream),
-                 "cross_entropy_loss");
+  const int rc = weedcu_cross_entropy_fwd_bf16in(logits_bf16, rows, V, (const uint16_t *)src.a->ptr, src.a_major, src.lda, (const uint16_t *)src.b->ptr, src.b_major,
+                                                 src.ldb, src.K, bs->device_ptr_ro() + src.bias_offset, sym_ptr(targets, "cross_entropy_loss") + targets.offset,
+                                                 dl.ptr + lse.offset, dloss.ptr + loss.offset, ls->dev->stream);
+  if (rc == WEEDCU_ENOSUP) return false;
+  throw_on_error(rc, "cross_entropy_loss");
   return true;
 }
 
