@@ -839,7 +839,8 @@ def test_gemm_epilogue_fusions_match_unfused_passes(P):
     bf16-only logits + log-sum-exp partials from the LM head. Against the same model with those passes run separately:
     the loss (computed from fp32-accurate statistics either way) within 2e-6, every parameter gradient within the bf16
     bound 5e-3 rel-to-max (the LM-head path forms dlogits from bf16-rounded logits), and the deferred fp32 logits read
-    back afterwards equal to the eagerly written ones (same GEMM: 1e-6)."""
+    back afterwards (the plain product recomputed on demand) within the same bound of the eagerly written ones — the
+    activations in front of the head already differ at the bf16 level (hardware tanh in ff1's epilogue)."""
     cfg = dict(V=1000, d=128, H=2, dff=512, L=2, T=128)
 
     def run(on):
@@ -854,7 +855,7 @@ def test_gemm_epilogue_fusions_match_unfused_passes(P):
     _, _, _, loss0, logits0, g0 = run(0)
     _, _, _, loss1, logits1, g1 = run(1)
     assert abs(loss1 - loss0) <= 2e-6 * abs(loss0), (loss0, loss1)
-    assert cases.rel_err(logits1, logits0) <= 1e-6
+    assert cases.rel_err(logits1, logits0) <= 5e-3
     checked = 0
     for i, (a, b) in enumerate(zip(g0, g1)):
         if a is None or b is None or a.size != b.size or not np.any(a):

@@ -429,3 +429,44 @@ def test_gemm_bf16_grouped_bf16out(gpu, M, N, K, groups, mode):
             assert np.array_equal(b16[g].get(), _bf16_bits(f32[g].get())), f"group {g}"
     finally:
         gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
+
+
+@pytest.mark.parametrize("rows,V,K", [(1024, 5003, 64), (256, 1000, 136), (8192, 2048, 768)])
+def test_cross_entropy_on_bf16_logits(gpu, rows, V, K):
+    """weedcu_cross_entropy_fwd_bf16in / _bwd_pack_bf16in: the loss path when the LM head's epilogue wrote only the bf16 copy
+    of the logits. lse from the bf16 logits, the target logit recomputed exactly from the product's bf16 operands
+    (+ bias), dlogits = (exp(l - lse) - onehot) * dloss / rows with its RNE bf16 copy and column sums — against numpy."""
+    import ctypes as C
+    rng = np.random.default_rng(rows + V + K)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, A = _operand(rng, rows, K, 1)
+    b_dev, ldb, B = _operand(rng, V, K, 0)
+    bias = rng.uniform(-2, 2, V).astype(np.float32)
+    exact = A @ B.T + bias[None, :].astype(np.float64)                 # [rows, V]
+    l16_bits = _bf16_bits(exact.astype(np.float32))
+    l16 = _bf16_widen(l16_bits).astype(np.float64)
+    tg = rng.integers(0, V, size=rows).astype(np.int32)
+    pa, pb, hbias, ht = gpu.buf(a_dev), gpu.buf(b_dev), gpu.buf(bias), gpu.buf(tg)
+    hl16 = gpu.buf(np.ascontiguousarray(l16_bits.T).reshape(-1))       # column-major [rows, V]: rows contiguous
+    hlse, hloss = gpu.buf(np.zeros(rows, np.float32)), gpu.buf(np.zeros(1, np.float32))
+    gpu.call("cross_entropy_fwd_bf16in", hl16, U32(rows), U32(V), pa, I32(1), U64(lda), pb, I32(0), U64(ldb), U32(K), hbias, ht, hlse, hloss)
+    m = l16.max(1)
+    ref_lse = m + np.log(np.exp(l16 - m[:, None]).sum(1))
+    got_lse = hlse.get().astype(np.float64)
+    assert np.max(np.abs(got_lse - ref_lse)) <= 2e-6 * np.abs(ref_lse).max()
+    ref_loss = np.mean(ref_lse - exact[np.arange(rows), tg])
+    assert abs(float(hloss.get()[0]) - ref_loss) <= 2e-6 * abs(ref_loss)
+    for acc in (0, 1):
+        d0 = rng.uniform(-1, 1, rows * V).astype(np.float32)
+        hd, hg = gpu.buf(d0), gpu.buf(np.full(1, 0.7, np.float32))
+        hsh, hcs = gpu.buf(np.zeros(rows * V, np.uint16)), gpu.buf(np.full(V, 3.0, np.float32))
+        gpu.call("cross_entropy_bwd_pack_bf16in", hl16, U32(rows), U32(V), ht, hlse, hg, hd, U64(0), I32(acc), hsh, hcs)
+        d = hd.get()
+        onehot = np.zeros((rows, V))
+        onehot[np.arange(rows), tg] = 1.0
+        want = (np.exp(l16 - got_lse[:, None]) - onehot) * (0.7 / rows)
+        if acc:
+            want = want + d0.reshape(V, rows).T
+        assert cases.rel_err(d.reshape(V, rows).T, want) <= 2e-5
+        assert np.array_equal(hsh.get(), _bf16_bits(d))
+        assert cases.rel_err(hcs.get(), d.reshape(V, rows).sum(1)) <= 2e-5

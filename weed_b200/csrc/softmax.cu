@@ -559,12 +559,12 @@ ce_fwd_partial_bf16(const __nv_bfloat16 *__restrict__ x, uint32_t rows, uint32_t
 #pragma unroll
         for (int u = 1; u < U; ++u) m4 = fmaxf(m4, e[u]);
         if (m4 > mx[k]) {
-          s[k] *= expf(mx[k] - m4);
+          s[k] *= __expf(mx[k] - m4);
           mx[k] = m4;
         }
         if (mx[k] > -INFINITY) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) s[k] += expf(e[u] - mx[k]);
+          for (int u = 0; u < U; ++u) s[k] += __expf(e[u] - mx[k]);
         }
       }
     }
@@ -590,45 +590,52 @@ ce_fwd_partial_bf16(const __nv_bfloat16 *__restrict__ x, uint32_t rows, uint32_t
   }
 }
 
-// Forward from the log-sum-exp partials the LM head's GEMM epilogue left (weedcu_gemm_bf16_ex, row_stats 2): merge the
-// per-column-tile (max, sum exp), and recompute the ONE logit the loss needs per row — the target column — as the same
-// bf16 x bf16 -> fp32 dot product (+ bias) the tensor cores formed, from the GEMM's own operands. Thread per row.
-__global__ void __launch_bounds__(128)
+// Forward from per-row log-sum-exp partials (from the LM head's GEMM epilogue, weedcu_gemm_bf16_ex row_stats 2, or from
+// ce_fwd_partial_bf16): merge the (max, sum exp) pairs, and recompute the ONE logit the loss needs per row — the target
+// column — as the same bf16 x bf16 -> fp32 dot product (+ bias) the tensor cores formed, from the GEMM's own operands.
+// Block = 32 adjacent rows x 8 k-slices (a warp reads 32 adjacent rows of one k: coalesced for the MN-major activations).
+__global__ void __launch_bounds__(256)
 ce_fwd_stats_finish(const float2 *__restrict__ stats, uint32_t tiles, uint32_t rows, uint32_t V, const __nv_bfloat16 *__restrict__ a, int a_major,
                     uint64_t lda, const __nv_bfloat16 *__restrict__ b, int b_major, uint64_t ldb, uint32_t K, const float *__restrict__ bias,
                     const int32_t *__restrict__ targets, float *__restrict__ lse, float *__restrict__ nll) {
   pdl_grid_sync();
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float M = -INFINITY;
-  for (uint32_t t = 0; t < tiles; ++t) M = fmaxf(M, stats[(uint64_t)t * rows + r].x);
-  float S = 0.0f;
-  for (uint32_t t = 0; t < tiles; ++t) {
-    const float2 p = stats[(uint64_t)t * rows + r];
-    if (p.x > -INFINITY) S += p.y * expf(p.x - M);
-  }
-  const float log_s = logf(S);
-  const uint32_t t = (uint32_t)targets[r];
-  float xt = NAN;
-  if (t < V) {
+  __shared__ float red[8][33];
+  const uint32_t rx = threadIdx.x & 31u, kx = threadIdx.x >> 5;
+  const uint32_t r = blockIdx.x * 32u + rx;
+  const bool live = r < rows;
+  const uint32_t t = live ? (uint32_t)targets[r] : 0u;
+  float acc = 0.0f;
+  if (live && t < V) {
     const __nv_bfloat16 *ap = a_major ? a + r : a + (uint64_t)r * lda;
     const __nv_bfloat16 *bp = b_major ? b + t : b + (uint64_t)t * ldb;
     const uint64_t as = a_major ? lda : 1u, bs = b_major ? ldb : 1u;
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-    uint32_t k = 0;
-    if (!b_major && (ldb % 8u) == 0 && ((((uintptr_t)b) & 15u) == 0)) { // K-major weights: 8 k per 128-bit load
-      for (; k + 8 <= K; k += 8) {
-        const uint4 w = *reinterpret_cast<const uint4 *>(bp + k);
-        const __nv_bfloat162 *w2 = reinterpret_cast<const __nv_bfloat162 *>(&w);
-        acc0 += __bfloat162float(ap[(uint64_t)(k + 0) * as]) * __low2float(w2[0]) + __bfloat162float(ap[(uint64_t)(k + 1) * as]) * __high2float(w2[0]);
-        acc1 += __bfloat162float(ap[(uint64_t)(k + 2) * as]) * __low2float(w2[1]) + __bfloat162float(ap[(uint64_t)(k + 3) * as]) * __high2float(w2[1]);
-        acc2 += __bfloat162float(ap[(uint64_t)(k + 4) * as]) * __low2float(w2[2]) + __bfloat162float(ap[(uint64_t)(k + 5) * as]) * __high2float(w2[2]);
-        acc3 += __bfloat162float(ap[(uint64_t)(k + 6) * as]) * __low2float(w2[3]) + __bfloat162float(ap[(uint64_t)(k + 7) * as]) * __high2float(w2[3]);
-      }
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t k = kx;
+    for (; k + 24u < K; k += 32u) { // 4 independent products in flight
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) a4[u] += __bfloat162float(ap[(uint64_t)(k + 8u * u) * as]) * __bfloat162float(bp[(uint64_t)(k + 8u * u) * bs]);
     }
-    for (; k < K; ++k) acc0 += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[(uint64_t)k * bs]);
-    xt = ((acc0 + acc1) + (acc2 + acc3)) + (bias ? bias[t] : 0.0f);
+    for (; k < K; k += 8u) a4[0] += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[(uint64_t)k * bs]);
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
+  red[kx][rx] = acc;
+  __syncthreads();
+  if (kx != 0 || !live) return;
+  float xt = NAN;
+  if (t < V) {
+    float dot = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) dot += red[y][rx];
+    xt = dot + (bias ? bias[t] : 0.0f);
+  }
+  float M = -INFINITY;
+  for (uint32_t i = 0; i < tiles; ++i) M = fmaxf(M, stats[(uint64_t)i * rows + r].x);
+  float S = 0.0f;
+  for (uint32_t i = 0; i < tiles; ++i) {
+    const float2 p = stats[(uint64_t)i * rows + r];
+    if (p.x > -INFINITY) S += p.y * expf(p.x - M);
+  }
+  const float log_s = logf(S);
   lse[r] = M + log_s;
   nll[r] = (xt - M) - log_s;
 }
@@ -711,10 +718,12 @@ ce_bwd_pack_kernel(const XT *__restrict__ x, uint32_t rows, uint32_t V, const in
         const uint32_t j = j0 + i0 + u;
         if (j < V) {
           float4 o;
-          o.x = dv[u].x + (expf(xv[u].x - l4.x) - (((uint32_t)t4.x == j) ? 1.0f : 0.0f)) * g;
-          o.y = dv[u].y + (expf(xv[u].y - l4.y) - (((uint32_t)t4.y == j) ? 1.0f : 0.0f)) * g;
-          o.z = dv[u].z + (expf(xv[u].z - l4.z) - (((uint32_t)t4.z == j) ? 1.0f : 0.0f)) * g;
-          o.w = dv[u].w + (expf(xv[u].w - l4.w) - (((uint32_t)t4.w == j) ? 1.0f : 0.0f)) * g;
+          // __expf (ex2.approx, 2 ulp): with expf's ~20 instructions per element the pass was issue-bound (452 us for
+          // 1.65 GB at 8192 x 50257), and the result is scaled by 1/rows and rounded to bf16 right below
+          o.x = dv[u].x + (__expf(xv[u].x - l4.x) - (((uint32_t)t4.x == j) ? 1.0f : 0.0f)) * g;
+          o.y = dv[u].y + (__expf(xv[u].y - l4.y) - (((uint32_t)t4.y == j) ? 1.0f : 0.0f)) * g;
+          o.z = dv[u].z + (__expf(xv[u].z - l4.z) - (((uint32_t)t4.z == j) ? 1.0f : 0.0f)) * g;
+          o.w = dv[u].w + (__expf(xv[u].w - l4.w) - (((uint32_t)t4.w == j) ? 1.0f : 0.0f)) * g;
           const uint64_t off = (uint64_t)j * rows + r;
           if (dlogits) *reinterpret_cast<float4 *>(dlogits + off) = o; // NULL: operand copy + column sums only
           __nv_bfloat162 h[2];
@@ -1066,7 +1075,7 @@ int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t 
   float *nll = nullptr;
   WCU_CHECK(pool_alloc((void **)&nll, sizeof(float) * (size_t)rows, st));
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 8.0 * (double)rows * tiles + 2.0 * (double)rows * K * 2.0);
-  launch_k(ce_fwd_stats_finish, dim3((rows + 127u) / 128u), dim3(128), 0, st, (const float2 *)stats, tiles, rows, V, (const __nv_bfloat16 *)a, a_major, lda,
+  launch_k(ce_fwd_stats_finish, dim3((rows + 31u) / 32u), dim3(256), 0, st, (const float2 *)stats, tiles, rows, V, (const __nv_bfloat16 *)a, a_major, lda,
            (const __nv_bfloat16 *)b, b_major, ldb, K, col_bias, targets, lse, nll);
   int rc = after_launch();
   if (rc == 0) {
