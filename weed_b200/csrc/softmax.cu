@@ -663,7 +663,7 @@ ce_bwd_kernel(const float *__restrict__ x, uint32_t rows, uint32_t V, uint32_t r
     for (int u = 0; u < kCeU; ++u) {
       const uint32_t j = j0 + u * kCeBY;
       if (j < v1) {
-        const float pr = expf(v[u] - l);
+        const float pr = __expf(v[u] - l); // the same ex2-based exp as ce_bwd_pack_kernel: the two backward kernels stay bit-identical
         const float oh = (tgt == j) ? 1.0f : 0.0f;
         dlogits[base + (uint64_t)j * vs] = d[u] + (pr - oh) * g;
       }
