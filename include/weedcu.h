@@ -350,6 +350,12 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
                                   float *const *v, const uint64_t *n, uint16_t *const *shadow, float lr,
                                   float beta1, float beta2, float eps, float bc1, float bc2, float gscale,
                                   void *stream);
+/* weedcu_adam_step_multi_shadow that also performs zero_grad (include/autograd/zero_grad.hpp:21-25) for the parameters
+ * with zero_grad[t] != 0: their gradient is overwritten with zeros right after it is read (+4 B/param on an existing
+ * pass instead of one fill launch per gradient in the next step). g[t] is written in that case. zero_grad may be NULL. */
+int weedcu_adam_step_multi_zero(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v,
+                                const uint64_t *n, uint16_t *const *shadow, const uint8_t *zero_grad, float lr, float beta1, float beta2,
+                                float eps, float bc1, float bc2, float gscale, void *stream);
 
 /* ------------------------------------------------------------------ G1-G4 matmul
  * Weed::matmul (src/ops/matmul.cpp:242-279; dims :95-122): C[M,N] (+)= A[M,K] * B[K,N], every

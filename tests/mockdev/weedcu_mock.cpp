@@ -249,6 +249,14 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
   }
   return 0;
 }
+int weedcu_adam_step_multi_zero(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, uint16_t *const *shadow,
+                                const uint8_t *zero_grad, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float gscale, void *stream) {
+  const int rc = weedcu_adam_step_multi_shadow(count, p, g, m, v, n, shadow, lr, beta1, beta2, eps, bc1, bc2, gscale, stream);
+  if (rc == 0 && zero_grad)
+    for (uint32_t t = 0; t < count; ++t)
+      if (zero_grad[t] && g[t]) memset(const_cast<float *>(g[t]), 0, sizeof(float) * n[t]);
+  return rc;
+}
 int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v, const uint64_t *n, float lr, float beta1, float beta2, float eps,
                            float bc1, float bc2, float gscale, void *stream) {
   return weedcu_adam_step_multi_shadow(count, p, g, m, v, n, nullptr, lr, beta1, beta2, eps, bc1, bc2, gscale, stream);

@@ -325,7 +325,7 @@ struct AdamChunk {
   float *m, *v;
   uint16_t *shadow; // optional bf16 copy of p at the same linear index (the GEMM operand shadow)
   uint32_t n;
-  int vec;
+  int vec; // bit 0: every pointer is 16-byte aligned (128-bit path); bit 1: write zeros back into g after reading it
 };
 constexpr uint64_t kAdamChunk = 32768; // elements per block of the multi-tensor launch
 // sgd_step (reference include/autograd/sgd.hpp:23-37): p -= lr * g.  12 B/param.
@@ -394,7 +394,11 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__restrict__ table, AdamArgs a) {
   pdl_grid_sync();
   const AdamChunk c = table[blockIdx.x];
-  if (c.vec) {
+  // zero_g: the gradient is read here for the last time this step, so zero_grad's fill rides on this pass (the buffer is
+  // then genuinely zero when the next backward accumulates into it: no per-gradient fill launch, no split-K zero fill)
+  const bool zero_g = (c.vec & 2) && c.g;
+  float *gw = const_cast<float *>(c.g);
+  if (c.vec & 1) {
     const uint32_t nq = c.n >> 2;
     for (uint32_t i = threadIdx.x; i < nq; i += 256) {
       float4 pv = reinterpret_cast<float4 *>(c.p)[i];
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__rest
       reinterpret_cast<float4 *>(c.p)[i] = pv;
       reinterpret_cast<float4 *>(c.m)[i] = mv;
       reinterpret_cast<float4 *>(c.v)[i] = vv;
+      if (zero_g) reinterpret_cast<float4 *>(gw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c.shadow) { // the updated weight leaves as fp32 and as the bf16 GEMM operand in the same pass
         __nv_bfloat162 o[2];
         o[0] = __floats2bfloat162_rn(pv.x, pv.y);
@@ -417,11 +422,13 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk *__rest
     }
     for (uint32_t i = (nq << 2) + threadIdx.x; i < c.n; i += 256) {
       adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+      if (zero_g) gw[i] = 0.0f;
       if (c.shadow) reinterpret_cast<__nv_bfloat16 *>(c.shadow)[i] = __float2bfloat16_rn(c.p[i]);
     }
   } else {
     for (uint32_t i = threadIdx.x; i < c.n; i += 256) {
       adam_one(c.p[i], c.g ? c.g[i] : 0.0f, c.m[i], c.v[i], a);
+      if (zero_g) gw[i] = 0.0f;
       if (c.shadow) reinterpret_cast<__nv_bfloat16 *>(c.shadow)[i] = __float2bfloat16_rn(c.p[i]);
     }
   }
@@ -570,6 +577,12 @@ int weedcu_adam_step_multi(uint32_t count, float *const *p, const float *const *
 int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *const *g, float *const *m,
                                   float *const *v, const uint64_t *n, uint16_t *const *shadow, float lr, float beta1,
                                   float beta2, float eps, float bc1, float bc2, float gscale, void *stream) {
+  return weedcu_adam_step_multi_zero(count, p, g, m, v, n, shadow, nullptr, lr, beta1, beta2, eps, bc1, bc2, gscale, stream);
+}
+
+int weedcu_adam_step_multi_zero(uint32_t count, float *const *p, const float *const *g, float *const *m, float *const *v,
+                                const uint64_t *n, uint16_t *const *shadow, const uint8_t *zero_grad, float lr, float beta1, float beta2,
+                                float eps, float bc1, float bc2, float gscale, void *stream) {
   if (!count) return 0;
   if (!p || !g || !m || !v || !n) return WEEDCU_EINVAL;
   cudaStream_t st = resolve_stream(stream);
@@ -586,11 +599,13 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
   static std::mutex table_mutex;
   std::lock_guard<std::mutex> lock(table_mutex);
   std::vector<AdamChunk> table;
-  double total = 0.0, shadowed = 0.0;
+  double total = 0.0, shadowed = 0.0, zeroed = 0.0;
   for (uint32_t t = 0; t < count; ++t) {
     if (!p[t] || !m[t] || !v[t]) return WEEDCU_EINVAL; // g[t] == NULL: an all-zero gradient
+    if (zero_grad && zero_grad[t] && g[t]) zeroed += (double)n[t];
     uint16_t *sh = shadow ? shadow[t] : nullptr;
-    const int vec = (aligned16(p[t]) && (!g[t] || aligned16(g[t])) && aligned16(m[t]) && aligned16(v[t]) && (!sh || aligned16(sh))) ? 1 : 0;
+    const int vec = ((aligned16(p[t]) && (!g[t] || aligned16(g[t])) && aligned16(m[t]) && aligned16(v[t]) && (!sh || aligned16(sh))) ? 1 : 0) |
+                    ((zero_grad && zero_grad[t]) ? 2 : 0);
     for (uint64_t o = 0; o < n[t]; o += kAdamChunk) {
       const uint64_t len = (n[t] - o < kAdamChunk) ? n[t] - o : kAdamChunk;
       table.push_back(AdamChunk{p[t] + o, g[t] ? g[t] + o : nullptr, m[t] + o, v[t] + o, sh ? sh + o : nullptr, (uint32_t)len, vec});
@@ -624,7 +639,7 @@ int weedcu_adam_step_multi_shadow(uint32_t count, float *const *p, const float *
   }
   const CachedTable &use = cache.back();
   AdamArgs a = {lr, beta1, beta2, eps, bc1, bc2, gscale, 1.0f - beta1, 1.0f - beta2};
-  ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total + 2.0 * shadowed);
+  ProfScope prof(WEEDCU_PROF_OPTIMIZER, st, 28.0 * total + 2.0 * shadowed + 4.0 * zeroed);
   launch_k(adam_multi_kernel, dim3((unsigned)use.host.size()), dim3(256), 0, st, use.dev, a);
   return after_launch();
 }

@@ -30,6 +30,8 @@ struct AdamBatch {
   std::vector<const real1 *> g;
   std::vector<uint64_t> n;
   std::vector<uint16_t *> shadow;
+  std::vector<uint8_t> zero_grad;    // 1: the kernel zeroes this gradient after reading it (zero_grad fused into the update)
+  std::vector<StoragePtr> zeroed;    // the gradient storages that will hold zeros once the launch has run
   std::vector<std::pair<StoragePtr, BufferPtr>> refreshed; // (parameter storage, shadow buffer) rewritten by the launch
   void *stream = nullptr;
 };

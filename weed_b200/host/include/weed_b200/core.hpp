@@ -293,6 +293,9 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
   // `version` counts potential writes; the bf16 operand shadows of GpuRealStorage key on it.
   mutable bool zero_pending = false;
   mutable uint64_t version = 0;
+  // the buffer is KNOWN to hold zeros while zero_version == version (the fused Adam kernel zeroes small gradients right
+  // after reading them): FillZeros() is then a no-op, and accumulating kernels add into real zeros — no fill launch
+  uint64_t zero_version = ~(uint64_t)0;
   // Deferred values (fused mode, BackendConfig::defer_grads): a producer that already left everything its
   // consumers read — the bf16 GEMM operand copy and the column sums — may skip writing the fp32 values and
   // register how to compute them instead. The first access that needs the fp32 buffer runs it (a full

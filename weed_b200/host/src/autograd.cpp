@@ -7,6 +7,7 @@
 
 namespace Weed {
 namespace {
+constexpr tcapint kZeroInAdamMax = 4U << 20; // elements; see adam_collect
 // A tensor whose view is exactly its whole storage in storage order (so a flat kernel may walk it)
 bool covers_storage(const Tensor &t) {
   if (t.offset) return false;
@@ -76,6 +77,12 @@ void adam_collect(Adam &opt, const std::vector<ParameterPtr> &params, AdamBatch 
     // a gradient still waiting for its lazy zero-fill was never touched by backward: pass "zeros"
     GpuRealStorage *gs = static_cast<GpuRealStorage *>(g->storage.get());
     b.g.push_back(gs->zero_pending ? nullptr : g->device_ptr_ro());
+    // small gradients (everything but the embedding / LM-head matrices: the ones the next backward accumulates into with
+    // split-K reduce-adds, column sums or LayerNorm partials) are zeroed by this kernel right after it has read them;
+    // the big ones stay lazily zeroed, their first product of the next step overwrites them
+    const bool zero_here = cfg.lazy_zero && !gs->zero_pending && !gs->buffer_shared() && p->storage->size <= kZeroInAdamMax;
+    b.zero_grad.push_back(zero_here ? 1U : 0U);
+    if (zero_here) b.zeroed.push_back(g->storage);
     b.m.push_back(s.m->device_ptr());
     b.v.push_back(s.v->device_ptr());
     b.n.push_back(p->storage->size);
@@ -83,10 +90,15 @@ void adam_collect(Adam &opt, const std::vector<ParameterPtr> &params, AdamBatch 
 }
 void adam_launch(Adam &opt, AdamBatch &b, real1 bias_correction1, real1 bias_correction2, void *stream) {
   if (b.p.empty()) return;
-  throw_on_error(weedcu_adam_step_multi_shadow((uint32_t)b.p.size(), b.p.data(), b.g.data(), b.m.data(), b.v.data(), b.n.data(), b.shadow.data(),
-                                               opt.lr, opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2,
-                                               backend_config().grad_scale, stream ? stream : b.stream),
+  throw_on_error(weedcu_adam_step_multi_zero((uint32_t)b.p.size(), b.p.data(), b.g.data(), b.m.data(), b.v.data(), b.n.data(), b.shadow.data(),
+                                             b.zero_grad.data(), opt.lr, opt.beta1, opt.beta2, opt.eps, bias_correction1, bias_correction2,
+                                             backend_config().grad_scale, stream ? stream : b.stream),
                  "adam_step");
+  for (const StoragePtr &z : b.zeroed) { // contents changed (bf16 copies / column sums of the old values are stale) and are zero
+    GpuRealStorage *gs = static_cast<GpuRealStorage *>(z.get());
+    ++gs->version;
+    gs->zero_version = gs->version;
+  }
   // the shadows written by the kernel describe the parameter as it is now (device_ptr() in adam_collect moved the version)
   for (const auto &r : b.refreshed) {
     GpuRealStorage *ps = static_cast<GpuRealStorage *>(r.first.get());

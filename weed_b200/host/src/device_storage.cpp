@@ -162,6 +162,7 @@ void GpuDevice::CopyBuffer(const BufferPtr &dst, const BufferPtr &src, size_t by
   throw_on_error(weedcu_memcpy_d2d(dst->ptr, src->ptr, bytes, stream), "GpuDevice::CopyBuffer");
 }
 void GpuRealStorage::FillValue(const real1 &v) {
+  if (v == ZERO_R1 && zero_version == version && !zero_pending && !deferred_values) return; // already zero, nothing wrote since
   ++version;
   deferred_values = nullptr;
   if (v == ZERO_R1 && backend_config().fused && backend_config().lazy_zero) { // lazy: see GpuStorage::zero_pending
