@@ -309,6 +309,13 @@ int64_t wh_op(const char *name, const int64_t *ins, int n_in, const float *f, in
     else if (op == "mean") r = Tensor::mean(in(0));
     else if (op == "sum_axis") r = Tensor::sum(in(0), ip(0));
     else if (op == "mean_axis") r = Tensor::mean(in(0), ip(0));
+    else if (op == "max") r = Tensor::max(in(0));
+    else if (op == "min") r = Tensor::min(in(0));
+    else if (op == "max_axis") r = Tensor::max(in(0), ip(0));
+    else if (op == "min_axis") r = Tensor::min(in(0), ip(0));
+    else if (op == "clamp") r = Tensor::clamp(in(0), fp(0), fp(1));
+    else if (op == "sin") r = Tensor::sin(in(0));
+    else if (op == "cos") r = Tensor::cos(in(0));
     else if (op == "softmax") r = Tensor::softmax(in(0), ip(0));
     else if (op == "logsoftmax") r = Tensor::logsoftmax(in(0), ip(0));
     else if (op == "transpose") r = (n_i >= 2) ? Tensor::transpose(in(0), ip(0), ip(1)) : Tensor::transpose(in(0));

@@ -157,6 +157,24 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
  * index_order as above (REDUCE_GRAD_HEAD, reduce.cpp:84-99). */
 int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout,
                             const weedcu_view *doutv, int axis, int index_order, void *stream);
+/* Weed::clamp / clamp_grad (reference src/ops/clamp.cpp:67-73,55-60; OpenCL kernels `clamp_real` / `clamp_grad_real`,
+ * src/common/qengine.cl): out = min(max(a, lo), hi); din += dout where lo < in < hi. Views as weedcu_unary_real. */
+int weedcu_clamp_real(const float *a, const weedcu_view *av, float lo, float hi, float *out, const weedcu_view *ov, void *stream);
+int weedcu_clamp_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                           const weedcu_view *doutv, float lo, float hi, void *stream);
+/* Weed::max / Weed::min over the whole tensor (reference src/ops/real_extremum.cpp:88-106,151-163: the reference copies the
+ * buffer to the host for this): *out = extremum of the view's elements, two-pass device reduction. is_min: 0 max, 1 min. */
+int weedcu_extremum_real(int is_min, const float *a, const weedcu_view *av, float *out, void *stream);
+/* their backward (real_extremum.cpp:50-57; OpenCL `match_grad_real`): din += dout where in == *extremum (device scalar);
+ * dout is the scalar gradient broadcast over din's shape (all strides 0) or any view of the same shape. */
+int weedcu_match_grad_full_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                                const weedcu_view *doutv, const float *extremum, void *stream);
+/* Weed::max / Weed::min along one axis (reference src/ops/reduce.cpp:40-58,239-248,362-386) with the same output layout and
+ * index_order switch as weedcu_reduce_real, and Weed::match_grad (:84-101,263-277,433-449): din += dout[o] where
+ * in == reduced[o], o = the output element the input element was reduced into; `reduced` is read through doutv too. */
+int weedcu_extremum_axis_real(int is_min, const float *a, const weedcu_view *av, int axis, float *out, int index_order, void *stream);
+int weedcu_match_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                           const weedcu_view *doutv, const float *reduced, int axis, int index_order, void *stream);
 /* Weed::sum / mean (src/ops/sum.cpp:74-98): *out = scale * sum_i a[i]. Device-side (the
  * reference copies the buffer to the host, sum.cpp:52-67). Deterministic two-pass tree. */
 int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *stream);

@@ -214,6 +214,104 @@ int wo_reduce_grad_real(float *din, const wo_view *dinv, const float *dout, cons
   return 0;
 }
 
+/* cpu() src/ops/clamp.cpp:67-73: out.write(i, min(max(a[i], l), h)) */
+int wo_clamp_real(const float *a, const wo_view *av, float lo, float hi, float *out, const wo_view *ov) {
+  if (!same_shape(av, ov)) return -1;
+  const uint64_t n = wo_broadcast_size(ov);
+  for (uint64_t i = 0; i < n; ++i) {
+    float x = a[wo_storage_index(av, i)];
+    x = (x < lo) ? lo : x; /* std::max(a, l) */
+    x = (hi < x) ? hi : x; /* std::min(., h) */
+    out[wo_storage_index(ov, i)] = x;
+  }
+  return 0;
+}
+/* CPU_GRAD_KERNEL src/ops/clamp.cpp:55-60: if (l < in[i] && in[i] < h) din.add(i, dout[i]) */
+int wo_clamp_grad_real(float *din, const wo_view *dinv, const float *in, const wo_view *inv, const float *dout, const wo_view *doutv,
+                       float lo, float hi) {
+  if (!same_shape(dinv, inv) || !same_shape(dinv, doutv)) return -1;
+  const uint64_t n = wo_broadcast_size(dinv);
+  for (uint64_t i = 0; i < n; ++i) {
+    const float x = in[wo_storage_index(inv, i)];
+    if (x > lo && x < hi) din[wo_storage_index(dinv, i)] += dout[wo_storage_index(doutv, i)];
+  }
+  return 0;
+}
+/* CPU_MAX / CPU_MIN src/ops/real_extremum.cpp:62-86 (serial par_for: one running extremum seeded with a[0]) */
+int wo_extremum_real(int is_min, const float *a, const wo_view *av, float *out) {
+  const uint64_t n = wo_broadcast_size(av);
+  if (!n) return -1;
+  float m = a[wo_storage_index(av, 0)];
+  for (uint64_t i = 1; i < n; ++i) {
+    const float v = a[wo_storage_index(av, i)];
+    if (is_min ? (v < m) : (v > m)) m = v;
+  }
+  *out = m;
+  return 0;
+}
+/* CPU_GRAD src/ops/real_extremum.cpp:50-57: if (in[i] == m) din.add(i, dout[i]) */
+int wo_match_grad_full_real(float *din, const wo_view *dinv, const float *in, const wo_view *inv, const float *dout, const wo_view *doutv,
+                            const float *extremum) {
+  if (!same_shape(dinv, inv) || !same_shape(dinv, doutv)) return -1;
+  const uint64_t n = wo_broadcast_size(dinv);
+  const float m = *extremum;
+  for (uint64_t i = 0; i < n; ++i)
+    if (in[wo_storage_index(inv, i)] == m) din[wo_storage_index(dinv, i)] += dout[wo_storage_index(doutv, i)];
+  return 0;
+}
+/* REDUCE_HEAD + MAX_LOOP / MIN_LOOP src/ops/reduce.cpp:17-31,40-58 (index_order as wo_reduce_real) */
+int wo_extremum_axis_real(int is_min, const float *a, const wo_view *av, int axis, float *out, int index_order) {
+  if (axis < 0 || axis >= av->rank) return -1;
+  const uint64_t n = wo_broadcast_size(av) / av->shape[axis];
+  for (uint64_t o = 0; o < n; ++o) {
+    uint64_t base = 0, tmp = o;
+    if (index_order) {
+      for (int d = av->rank - 1; d >= 0; --d) {
+        if (d == axis) continue;
+        base += (tmp % av->shape[d]) * av->stride[d];
+        tmp /= av->shape[d];
+      }
+    } else {
+      for (int d = 0; d < av->rank; ++d) {
+        if (d == axis) continue;
+        base += (tmp % av->shape[d]) * av->stride[d];
+        tmp /= av->shape[d];
+      }
+    }
+    float m = a[av->offset + base];
+    for (uint32_t j = 1; j < av->shape[axis]; ++j) {
+      const float v = a[av->offset + base + (uint64_t)j * av->stride[axis]];
+      if (is_min ? (v < m) : (v > m)) m = v;
+    }
+    out[o] = m;
+  }
+  return 0;
+}
+/* REDUCE_GRAD_HEAD + MATCH_GRAD_OUT src/ops/reduce.cpp:84-113: if (in[i] == out[o]) din.add(i, dout[o]) with the index
+ * decompositions of wo_reduce_grad_real; out and dout are read through the same view (value and gradient of one tensor). */
+int wo_match_grad_real(float *din, const wo_view *dinv, const float *in, const wo_view *inv, const float *dout, const wo_view *doutv,
+                       const float *reduced, int axis, int index_order) {
+  if (axis < 0 || axis >= dinv->rank || !same_shape(dinv, doutv) || !same_shape(dinv, inv)) return -1;
+  const uint64_t n = wo_broadcast_size(dinv);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t o = 0, tmp = i;
+    if (index_order) {
+      for (int d = dinv->rank - 1; d >= 0; --d) {
+        if (d == axis) continue;
+        o += (tmp % dinv->shape[d]) * doutv->stride[d];
+        tmp /= dinv->shape[d];
+      }
+    } else {
+      for (int d = 0; d < dinv->rank; ++d) {
+        if (d != axis) o += (tmp % dinv->shape[d]) * doutv->stride[d];
+        tmp /= dinv->shape[d];
+      }
+    }
+    if (in[wo_storage_index(inv, i)] == reduced[doutv->offset + o]) din[wo_storage_index(dinv, i)] += dout[doutv->offset + o];
+  }
+  return 0;
+}
+
 /* CPU_KERNEL src/ops/sum.cpp:27-38 (serial branch of par_for, src/common/parallel_for.cpp:94-106);
  * mean = sum / n (sum.cpp:82-86) is expressed by scale = 1/n applied as a division-equivalent
  * multiply only in the test tolerance; callers wanting the exact quotient pass scale = 1. */

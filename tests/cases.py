@@ -240,6 +240,72 @@ for _shape, _axis in [([30, 17], 1), ([30, 17], 0), ([4, 6, 16], 2), ([1, 12, 16
             return {"din": hd.get()}
 
 
+# ---- round 2: clamp / max / min / match_grad (reference clamp.cpp, real_extremum.cpp, reduce.cpp:40-113)
+def _quantised(rng, n, levels=23):
+    """values on a coarse grid: the extremum is hit by several elements, which is what match_grad is about"""
+    return (rng.integers(-levels, levels + 1, size=n).astype(F32) / F32(4.0)).astype(F32)
+
+
+for _shape in ([1000], [37, 29], [6, 10, 16]):
+    @case(f"clamp_{'x'.join(map(str, _shape))}", tol=0.0)
+    def _c(be, rng, shape=_shape):
+        n = int(np.prod(shape))
+        a = uni(rng, n, -2, 2)
+        ha, ho = be.buf(a), be.buf(np.zeros(n, F32))
+        be.call("clamp_real", ha, cview(shape), F32(-0.75), F32(0.5), ho, cview(shape))
+        din, dout = uni(rng, n), uni(rng, n)
+        hd, hg = be.buf(din), be.buf(dout)
+        be.call("clamp_grad_real", hd, cview(shape), ha, cview(shape), hg, cview(shape), F32(-0.75), F32(0.5))
+        return {"out": ho.get(), "din": hd.get()}
+
+
+@case("clamp_strided_views", tol=0.0)
+def _c(be, rng):
+    s = [20, 12]
+    a, out = uni(rng, 20 * 40 + 7, -2, 2), np.zeros(12 * 25, F32)
+    ha, ho = be.buf(a), be.buf(out)
+    be.call("clamp_real", ha, make_view(s, [1, 40], 7), F32(-1.0), F32(1.0), ho, make_view(s, [12, 1], 0))  # transposed output
+    return {"out": ho.get()}
+
+
+for _ismin in (0, 1):
+    for _shape in ([100003], [300, 70], [5, 7, 11]):
+        @case(f"{'min' if _ismin else 'max'}_full_{'x'.join(map(str, _shape))}", tol=0.0)
+        def _c(be, rng, shape=_shape, ismin=_ismin):
+            n = int(np.prod(shape))
+            a = _quantised(rng, n)
+            ha, ho = be.buf(a), be.buf(np.zeros(1, F32))
+            be.call("extremum_real", I32(ismin), ha, cview(shape), ho)
+            din, g = uni(rng, n), uni(rng, 1)
+            hd, hg = be.buf(din), be.buf(g)
+            be.call("match_grad_full_real", hd, cview(shape), ha, cview(shape), hg, make_view(shape, [0] * len(shape)), ho)
+            return {"out": ho.get(), "din": hd.get()}
+
+    @case(f"{'min' if _ismin else 'max'}_full_strided_view", tol=0.0)
+    def _c(be, rng, ismin=_ismin):
+        a = _quantised(rng, 50 * 64 + 3)
+        ha, ho = be.buf(a), be.buf(np.zeros(1, F32))
+        be.call("extremum_real", I32(ismin), ha, make_view([50, 30], [1, 64], 3), ho)
+        return {"out": ho.get()}
+
+    for _shape, _axis in [([300, 70], 0), ([300, 70], 1), ([6, 10, 96], 2), ([6, 10, 96], 1), ([6, 10, 96], 0), ([1, 40, 64], 2)]:
+        for _order in (0, 1):
+            @case(f"{'min' if _ismin else 'max'}_axis_{'x'.join(map(str, _shape))}_axis{_axis}_order{_order}", tol=0.0)
+            def _c(be, rng, shape=_shape, axis=_axis, order=_order, ismin=_ismin):
+                n = int(np.prod(shape))
+                a = _quantised(rng, n)
+                n_out = n // shape[axis]
+                ha, ho = be.buf(a), be.buf(np.zeros(n_out, F32))
+                be.call("extremum_axis_real", I32(ismin), ha, cview(shape), I32(axis), ho, I32(order))
+                oshape = list(shape)
+                oshape[axis] = 1
+                ost = contiguous_stride(oshape)      # out / dout as Tensor::max builds them, then match_shape'd
+                din, dout = uni(rng, n), uni(rng, n_out)
+                hd, hg = be.buf(din), be.buf(dout)
+                be.call("match_grad_real", hd, cview(shape), ha, cview(shape), hg, make_view(shape, ost), ho, I32(axis), I32(order))
+                return {"out": ho.get(), "din": hd.get()}
+
+
 @case("sum_linear_100003", tol=2e-5)
 def _c(be, rng):
     # positive inputs: the tolerance is relative to |sum|, so keep the sum well conditioned (the

@@ -99,6 +99,23 @@ int weedcu_reduce_real(const float *a, const weedcu_view *av, int axis, float *o
 int weedcu_reduce_grad_real(float *din, const weedcu_view *dinv, const float *dout, const weedcu_view *doutv, int axis, int index_order, void *) {
   return RUN(wo_reduce_grad_real(din, VIEW(dinv), dout, VIEW(doutv), axis, index_order));
 }
+int weedcu_clamp_real(const float *a, const weedcu_view *av, float lo, float hi, float *out, const weedcu_view *ov, void *) {
+  return RUN(wo_clamp_real(a, VIEW(av), lo, hi, out, VIEW(ov)));
+}
+int weedcu_clamp_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, float lo, float hi, void *) {
+  return RUN(wo_clamp_grad_real(din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv), lo, hi));
+}
+int weedcu_extremum_real(int is_min, const float *a, const weedcu_view *av, float *out, void *) { return RUN(wo_extremum_real(is_min, a, VIEW(av), out)); }
+int weedcu_match_grad_full_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, const float *extremum, void *) {
+  return RUN(wo_match_grad_full_real(din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv), extremum));
+}
+int weedcu_extremum_axis_real(int is_min, const float *a, const weedcu_view *av, int axis, float *out, int index_order, void *) {
+  return RUN(wo_extremum_axis_real(is_min, a, VIEW(av), axis, out, index_order));
+}
+int weedcu_match_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout, const weedcu_view *doutv, const float *reduced, int axis,
+                           int index_order, void *) {
+  return RUN(wo_match_grad_real(din, VIEW(dinv), in, VIEW(inv), dout, VIEW(doutv), reduced, axis, index_order));
+}
 int weedcu_sum_real(const float *a, const weedcu_view *av, float scale, float *out, void *) { return RUN(wo_sum_real(a, VIEW(av), scale, out)); }
 int weedcu_softmax_real(int log_mode, const float *a, const weedcu_view *av, int axis, float *out, const weedcu_view *ov, void *) {
   return RUN(wo_softmax_real(log_mode, a, VIEW(av), axis, out, VIEW(ov)));

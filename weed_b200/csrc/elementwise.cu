@@ -177,6 +177,21 @@ template <int OP> struct UnaryF {
   }
 };
 
+// clamp (reference src/ops/clamp.cpp:67-73): min(max(x, lo), hi); its gradient passes dout where lo < x < hi (:55-60)
+struct ClampF {
+  float lo, hi;
+  __device__ float operator()(const float *x) const { return fminf(fmaxf(x[0], lo), hi); }
+};
+struct ClampGradF { // x[0] = din (old), x[1] = in, x[2] = dout
+  float lo, hi;
+  __device__ float operator()(const float *x) const { return (x[1] > lo && x[1] < hi) ? x[0] + x[2] : x[0]; }
+};
+// full max / min backward (reference src/ops/real_extremum.cpp:50-57): dout goes to every element equal to the
+// extremum; x[0] = din (old), x[1] = in, x[2] = dout, x[3] = the extremum (a scalar tensor, all strides 0)
+struct MatchGradF {
+  __device__ float operator()(const float *x) const { return (x[1] == x[3]) ? x[0] + x[2] : x[0]; }
+};
+
 // x[0] = din (old), x[1] = in (forward input or output), x[2] = dout
 template <int OP> struct UnaryGradF {
   __device__ float operator()(const float *x) const {
@@ -536,6 +551,36 @@ int weedcu_unary_grad_real(int op, float *din, const weedcu_view *dinv, const fl
     WCU_GRAD_CASE(WEEDCU_COS)
   }
   return WEEDCU_EINVAL;
+}
+
+int weedcu_clamp_real(const float *a, const weedcu_view *av, float lo, float hi, float *out, const weedcu_view *ov, void *stream) {
+  if (!av || !ov) return WEEDCU_EINVAL;
+  const weedcu_view *views[2] = {av, ov};
+  const float *ins[1] = {a};
+  ClampF f;
+  f.lo = lo;
+  f.hi = hi;
+  return launch_ew<1>(views, ins, out, f, resolve_stream(stream));
+}
+int weedcu_clamp_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                           const weedcu_view *doutv, float lo, float hi, void *stream) {
+  if (!dinv || !inv || !doutv) return WEEDCU_EINVAL;
+  const weedcu_view *views[4] = {dinv, inv, doutv, dinv};
+  const float *ins[3] = {din, in, dout};
+  ClampGradF f;
+  f.lo = lo;
+  f.hi = hi;
+  return launch_ew<3>(views, ins, din, f, resolve_stream(stream));
+}
+int weedcu_match_grad_full_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                                const weedcu_view *doutv, const float *extremum, void *stream) {
+  if (!dinv || !inv || !doutv || !extremum) return WEEDCU_EINVAL;
+  weedcu_view mv = *dinv; // the scalar, broadcast over din's index space
+  mv.offset = 0;
+  for (int d = 0; d < WEEDCU_MAX_RANK; ++d) mv.stride[d] = 0;
+  const weedcu_view *views[5] = {dinv, inv, doutv, &mv, dinv};
+  const float *ins[4] = {din, in, dout, extremum};
+  return launch_ew<4>(views, ins, din, MatchGradF(), resolve_stream(stream));
 }
 
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,

@@ -218,6 +218,128 @@ sum_pass2_kernel(const float *__restrict__ partial, uint32_t n, float scale, flo
   if (threadIdx.x == 0) *out = s * scale;
 }
 
+// ------------------------------------------------------------------------ max / min
+// Full max / min (reference src/ops/real_extremum.cpp:88-106: per-thread running extremum, then the extremum of those)
+// as the same two passes as the full sum; the axis forms (src/ops/reduce.cpp:40-58,239-248) share reduce_generic's
+// index walk, and match_grad (:84-101, MATCH_GRAD_OUT) routes dout to the elements equal to their reduced value.
+template <bool IS_MIN> __device__ __forceinline__ float pick(float a, float b) { return IS_MIN ? fminf(a, b) : fmaxf(a, b); }
+template <bool IS_MIN>
+__global__ void __launch_bounds__(256)
+extremum_pass1_kernel(const float *__restrict__ a, IndexSpace<1> sp, bool linear_vec, float *__restrict__ partial) {
+  pdl_grid_sync();
+  __shared__ float red[32];
+  const float init = IS_MIN ? INFINITY : -INFINITY;
+  float m = init;
+  const uint32_t stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (linear_vec) {
+    const uint32_t nq = sp.n >> 2;
+    const float4 *q = reinterpret_cast<const float4 *>(a);
+    for (uint32_t i = tid; i < nq; i += stride) {
+      const float4 v = q[i];
+      m = pick<IS_MIN>(m, pick<IS_MIN>(pick<IS_MIN>(v.x, v.y), pick<IS_MIN>(v.z, v.w)));
+    }
+    for (uint32_t k = (nq << 2) + tid; k < sp.n; k += stride) m = pick<IS_MIN>(m, a[k]);
+  } else {
+    for (uint32_t i = tid; i < sp.n; i += stride) {
+      uint64_t off = 0;
+      uint32_t rem = i;
+      for (int d = 0; d < sp.rank; ++d) {
+        off += (uint64_t)(rem % sp.shape[d]) * sp.stride[0][d];
+        rem /= sp.shape[d];
+      }
+      m = pick<IS_MIN>(m, a[off]);
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = pick<IS_MIN>(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  if (w == 0) {
+    m = lane < (blockDim.x >> 5) ? red[lane] : init;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = pick<IS_MIN>(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) partial[blockIdx.x] = m;
+  }
+}
+template <bool IS_MIN>
+__global__ void __launch_bounds__(1024) extremum_pass2_kernel(const float *__restrict__ partial, uint32_t n, float *__restrict__ out) {
+  pdl_grid_sync();
+  __shared__ float red[32];
+  const float init = IS_MIN ? INFINITY : -INFINITY;
+  float m = init;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) m = pick<IS_MIN>(m, partial[i]);
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = pick<IS_MIN>(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  if (w == 0) {
+    m = red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = pick<IS_MIN>(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) *out = m;
+  }
+}
+// axis form: a warp covers 32 adjacent outputs (coalesced when the first non-axis dim is the contiguous one)
+template <bool IS_MIN>
+__global__ void __launch_bounds__(256)
+extremum_axis_kernel(const float *__restrict__ a, ReduceView v, uint32_t n_out, float *__restrict__ out, int index_order) {
+  pdl_grid_sync();
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  uint64_t base = 0;
+  uint32_t tmp = o;
+  if (index_order) {
+    for (int d = v.rank - 1; d >= 0; --d) {
+      if (d == v.axis) continue;
+      base += (uint64_t)(tmp % v.shape[d]) * v.stride[d];
+      tmp /= v.shape[d];
+    }
+  } else {
+    for (int d = 0; d < v.rank; ++d) {
+      if (d == v.axis) continue;
+      base += (uint64_t)(tmp % v.shape[d]) * v.stride[d];
+      tmp /= v.shape[d];
+    }
+  }
+  const uint64_t as = v.stride[v.axis];
+  float m = a[base];
+  for (uint32_t j = 1; j < v.shape[v.axis]; ++j) {
+    const float x = a[base + j * as];
+    if (IS_MIN ? (x < m) : (x > m)) m = x; // the reference's strict comparison (MAX_LOOP / MIN_LOOP): NaNs never win
+  }
+  out[o] = m;
+}
+// din[i] += dout[o(i)] where in[i] == red[o(i)]; o(i) drops the axis coordinate. index_order 1 decomposes i over the
+// non-axis dims only, last dim fastest, exactly as REDUCE_GRAD_HEAD does (correct only where the reference is, D2);
+// index_order 0 decomposes i over all dims, first dim fastest (the intended column-major walk).
+__global__ void __launch_bounds__(256)
+match_grad_kernel(float *din, ReduceView dinv, const float *__restrict__ in, ReduceView inv, const float *__restrict__ dout,
+                  const float *__restrict__ red, ReduceView ov, uint32_t n, int index_order) {
+  pdl_grid_sync();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o = 0, off_d = 0, off_i = 0;
+  uint32_t rem = i;
+  for (int d = 0; d < dinv.rank; ++d) {
+    const uint32_t c = rem % dinv.shape[d];
+    rem /= dinv.shape[d];
+    off_d += (uint64_t)c * dinv.stride[d];
+    off_i += (uint64_t)c * inv.stride[d];
+    if (!index_order && d != dinv.axis) o += (uint64_t)c * ov.stride[d];
+  }
+  if (index_order) {
+    uint32_t tmp = i;
+    for (int d = dinv.rank - 1; d >= 0; --d) {
+      if (d == dinv.axis) continue;
+      o += (uint64_t)(tmp % dinv.shape[d]) * ov.stride[d];
+      tmp /= dinv.shape[d];
+    }
+  }
+  if (in[off_i] == red[o]) din[off_d] += dout[o];
+}
+
 // ------------------------------------------------------------------------ argmax over rows
 // logits[rows, V] with row stride rs (normally 1) and vocab stride vs: 32 rows x BY slices per
 // block, lowest index wins ties (matches a serial first-max scan).
@@ -452,6 +574,79 @@ int weedcu_argmax_rows(const float *x, uint64_t offset, uint32_t rows, uint32_t 
   }
   pool_free(ws, st);
   return rc;
+}
+
+int weedcu_extremum_real(int is_min, const float *a, const weedcu_view *av, float *out, void *stream) {
+  if (!a || !av || !out) return WEEDCU_EINVAL;
+  const weedcu_view *views[1] = {av};
+  IndexSpace<1> sp;
+  if (!build_index_space<1>(views, sp)) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  const float *base = a + av->offset;
+  const bool vec = (sp.rank == 1 && sp.stride[0][0] == 1) && aligned16(base);
+  unsigned blocks = grid_for(vec ? (sp.n >> 2) : sp.n, 256, 4);
+  if (blocks > 1024) blocks = 1024;
+  float *partial = nullptr;
+  WCU_CHECK(pool_alloc((void **)&partial, sizeof(float) * blocks, st));
+  ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * sp.n);
+  if (is_min) launch_k(extremum_pass1_kernel<true>, dim3(blocks), dim3(256), 0, st, base, sp, vec, partial);
+  else launch_k(extremum_pass1_kernel<false>, dim3(blocks), dim3(256), 0, st, base, sp, vec, partial);
+  int rc = after_launch();
+  if (rc == 0) {
+    if (is_min) launch_k(extremum_pass2_kernel<true>, dim3(1), dim3(1024), 0, st, (const float *)partial, blocks, out);
+    else launch_k(extremum_pass2_kernel<false>, dim3(1), dim3(1024), 0, st, (const float *)partial, blocks, out);
+    rc = after_launch();
+  }
+  pool_free(partial, st);
+  return rc;
+}
+
+static void fill_reduce_view(ReduceView &v, const weedcu_view *src, int rank, int axis) {
+  v.rank = rank;
+  v.axis = axis;
+  for (int d = 0; d < kMaxRank; ++d) {
+    v.shape[d] = d < rank ? src->shape[d] : 1;
+    v.stride[d] = d < rank ? src->stride[d] : 0;
+  }
+}
+
+int weedcu_extremum_axis_real(int is_min, const float *a, const weedcu_view *av, int axis, float *out, int index_order, void *stream) {
+  if (!a || !av || !out || av->rank <= 0 || av->rank > kMaxRank || axis < 0 || axis >= av->rank) return WEEDCU_EINVAL;
+  uint64_t total = 1;
+  for (int d = 0; d < av->rank; ++d) total *= av->shape[d];
+  const uint32_t L = av->shape[axis];
+  if (!L || !total || total / L > 0xffffffffull) return WEEDCU_EINVAL;
+  const uint32_t n_out = (uint32_t)(total / L);
+  cudaStream_t st = resolve_stream(stream);
+  ReduceView v;
+  fill_reduce_view(v, av, av->rank, axis);
+  ProfScope prof(WEEDCU_PROF_REDUCE, st, 4.0 * total);
+  if (is_min) launch_k(extremum_axis_kernel<true>, dim3((n_out + 255u) / 256u), dim3(256), 0, st, a + av->offset, v, n_out, out, index_order);
+  else launch_k(extremum_axis_kernel<false>, dim3((n_out + 255u) / 256u), dim3(256), 0, st, a + av->offset, v, n_out, out, index_order);
+  return after_launch();
+}
+
+int weedcu_match_grad_real(float *din, const weedcu_view *dinv, const float *in, const weedcu_view *inv, const float *dout,
+                           const weedcu_view *doutv, const float *reduced, int axis, int index_order, void *stream) {
+  if (!din || !dinv || !in || !inv || !dout || !doutv || !reduced || dinv->rank != doutv->rank || dinv->rank != inv->rank || axis < 0 ||
+      axis >= dinv->rank || dinv->rank > kMaxRank)
+    return WEEDCU_EINVAL;
+  uint64_t n = 1;
+  for (int d = 0; d < dinv->rank; ++d) {
+    if (inv->shape[d] != dinv->shape[d]) return WEEDCU_EINVAL;
+    n *= dinv->shape[d];
+  }
+  if (!n || n > 0xffffffffull) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  ReduceView dv, iv, ov;
+  fill_reduce_view(dv, dinv, dinv->rank, axis);
+  fill_reduce_view(iv, inv, dinv->rank, axis);
+  fill_reduce_view(ov, doutv, dinv->rank, axis);
+  ProfScope prof(WEEDCU_PROF_REDUCE, st, 16.0 * n);
+  // dout and the reduced values are read through the same (dout) view: they are the gradient and the value of one tensor
+  launch_k(match_grad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, din + dinv->offset, dv, in + inv->offset, iv, dout + doutv->offset,
+           reduced + doutv->offset, ov, (uint32_t)n, index_order);
+  return after_launch();
 }
 
 } // extern "C"

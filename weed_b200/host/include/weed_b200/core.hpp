@@ -563,6 +563,15 @@ struct Tensor : public BaseTensor, public std::enable_shared_from_this<Tensor> {
   static TensorPtr stddev(TensorPtr a, const tcapint &axis) { return pow(variance(a, axis), real1(0.5)); }
   static TensorPtr sum(TensorPtr a, symint axis);
   static void make_sum_node(TensorPtr a, TensorPtr out, const tcapint &axis);
+  static TensorPtr max(TensorPtr a, symint axis);
+  static TensorPtr min(TensorPtr a, symint axis);
+  static void make_match_node(TensorPtr a, TensorPtr out, const tcapint &axis);
+  static TensorPtr max(TensorPtr a);
+  static void make_max_node(TensorPtr a, TensorPtr out);
+  static TensorPtr min(TensorPtr a);
+  static void make_min_node(TensorPtr a, TensorPtr out);
+  static TensorPtr clamp(TensorPtr a, real1 lo, real1 hi);
+  static void make_clamp_node(TensorPtr a, real1 lo, real1 hi, TensorPtr out);
   static TensorPtr abs(TensorPtr a);
   static void make_abs_node(TensorPtr a, TensorPtr out);
   static TensorPtr sigmoid(TensorPtr a);

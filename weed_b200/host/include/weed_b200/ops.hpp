@@ -42,6 +42,17 @@ void mean(const Tensor &a, Tensor &out);
 void reduce(const tcapint &index, const Tensor &a, Tensor &out);
 void reduce_grad(const tcapint &index, Tensor &din, const Tensor &a, const Tensor &dout);
 
+// reference include/ops/clamp.hpp, real_extremum.hpp, reduce.hpp:27-36
+void clamp(const Tensor &a, const real1 &l, const real1 &h, Tensor &out);
+void clamp_grad(Tensor &din, const Tensor &in, const Tensor &dout, const real1 &l, const real1 &h);
+void max(const Tensor &a, Tensor &out);
+void max_grad(Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out);
+void min(const Tensor &a, Tensor &out);
+void min_grad(Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out);
+void max(const tcapint &index, const Tensor &a, Tensor &out);
+void min(const tcapint &index, const Tensor &a, Tensor &out);
+void match_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out);
+
 void softmax(const tcapint &index, const Tensor &a, Tensor &out);
 void softmax_grad(const tcapint &index, Tensor &din, const Tensor &out, const Tensor &dout);
 void logsoftmax(const tcapint &index, const Tensor &a, Tensor &out);

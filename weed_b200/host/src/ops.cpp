@@ -742,6 +742,76 @@ void reduce_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tens
                  "reduce_grad");
 }
 
+// ---- clamp / max / min (reference src/ops/clamp.cpp:116-170, real_extremum.cpp:165-262, reduce.cpp:362-449)
+void clamp(const Tensor &a, const real1 &l, const real1 &h, Tensor &out) {
+  validate_all_same_device({&a, &out}, "ClampKernel::clamp");
+  if ((a.storage->dtype != DType::REAL) || (out.storage->dtype != DType::REAL))
+    throw std::invalid_argument("In Weed::clamp(a, l, h, out), arguments must all be real-number!");
+  if (a.get_broadcast_size() != out.get_broadcast_size()) throw std::invalid_argument("In Weed::clamp(a, l, h, out), out size does not match input size!");
+  const Dev da = dev_of(a, "clamp"), dout = dev_out(out, "clamp", true);
+  weedcu_view av = a.view(), ov = out.view();
+  conform_views({&ov, &av}, "clamp");
+  throw_on_error(weedcu_clamp_real(da.ptr, &av, l, h, dout.ptr, &ov, dout.stream), "clamp");
+}
+void clamp_grad(Tensor &din, const Tensor &in, const Tensor &dout, const real1 &l, const real1 &h) {
+  validate_all_same_device({&din, &in, &dout}, "ClampKernel::clamp_grad");
+  const tcapint n = din.get_broadcast_size();
+  if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size())) throw std::invalid_argument("In Weed::clamp_grad(din, in, dout, l, h), sizes do not match!");
+  if (in.storage->dtype != DType::REAL) throw std::invalid_argument("In Weed::clamp_grad(din, in, dout, l, h), 'in' dtype must be real-number!");
+  const Dev dd = dev_out(din, "clamp_grad"), di = dev_of(in, "clamp_grad"), dg = dev_of(dout, "clamp_grad");
+  weedcu_view dv = din.view(), iv = in.view(), gv = dout.view();
+  conform_views({&dv, &iv, &gv}, "clamp_grad");
+  throw_on_error(weedcu_clamp_grad_real(dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, l, h, dd.stream), "clamp_grad");
+}
+static void extremum_full(int is_min, const Tensor &a, Tensor &out) {
+  validate_all_same_device({&a, &out}, "RealExtremumKernel::extremum");
+  if ((a.storage->dtype == DType::COMPLEX) || (out.storage->dtype == DType::COMPLEX)) throw std::invalid_argument("Cannot apply extremum reduction on complex tensors!");
+  const Dev da = dev_of(a, "extremum"), dout = dev_out(out, "extremum");
+  const weedcu_view av = a.view();
+  throw_on_error(weedcu_extremum_real(is_min, da.ptr, &av, dout.ptr + out.offset, dout.stream), "extremum");
+}
+static void extremum_full_grad(Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out) {
+  validate_all_same_device({&din, &in, &dout, &out}, "RealExtremumKernel::extremum_grad");
+  if ((in.storage->dtype != DType::REAL) || (out.storage->dtype != DType::REAL))
+    throw std::invalid_argument("In RealExtremumKernel::extremum_grad(din, in, dout), in and out dtype must be real-number!");
+  const tcapint n = din.get_broadcast_size();
+  if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size())) throw std::invalid_argument("In Weed::extremum_grad(din, in, dout), sizes do not match!");
+  const Dev dd = dev_out(din, "extremum_grad"), di = dev_of(in, "extremum_grad"), dg = dev_of(dout, "extremum_grad"), dm = dev_of(out, "extremum_grad");
+  weedcu_view dv = din.view(), iv = in.view(), gv = dout.view();
+  conform_views({&dv, &iv, &gv}, "extremum_grad");
+  throw_on_error(weedcu_match_grad_full_real(dd.ptr, &dv, di.ptr, &iv, dg.ptr, &gv, dm.ptr + out.offset, dd.stream), "extremum_grad");
+}
+void max(const Tensor &a, Tensor &out) { extremum_full(0, a, out); }
+void min(const Tensor &a, Tensor &out) { extremum_full(1, a, out); }
+void max_grad(Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out) { extremum_full_grad(din, in, dout, out); }
+void min_grad(Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out) { extremum_full_grad(din, in, dout, out); }
+static void extremum_axis(int is_min, const tcapint &index, const Tensor &a, Tensor &out, const char *name) {
+  validate_all_same_device({&a, &out}, name);
+  if ((a.storage->dtype != DType::REAL) || (out.storage->dtype != DType::REAL)) throw std::invalid_argument("Tensor dtype mismatch in max / min!");
+  if (index >= a.shape.size()) throw std::invalid_argument("max / min: axis out of range");
+  const Dev da = dev_of(a, name), dout = dev_out(out, name);
+  const weedcu_view av = a.view();
+  // the output is written as a dense buffer starting at out.offset (the tensor Tensor::max(axis) builds, like Tensor::sum)
+  throw_on_error(weedcu_extremum_axis_real(is_min, da.ptr, &av, (int)index, dout.ptr + out.offset, backend_config().ref_index_quirks ? 1 : 0, dout.stream), name);
+}
+void max(const tcapint &index, const Tensor &a, Tensor &out) { extremum_axis(0, index, a, out, "ReduceKernel::max"); }
+void min(const tcapint &index, const Tensor &a, Tensor &out) { extremum_axis(1, index, a, out, "ReduceKernel::min"); }
+void match_grad(const tcapint &index, Tensor &din, const Tensor &in, const Tensor &dout, const Tensor &out) {
+  validate_all_same_device({&din, &dout}, "ReduceKernel::match_grad");
+  const tcapint n = din.get_broadcast_size();
+  if ((n != in.get_broadcast_size()) || (n != dout.get_broadcast_size())) throw std::invalid_argument("In Weed::match_grad(din, in, dout, out), sizes do not match!");
+  const Dev dd = dev_out(din, "match_grad"), di = dev_of(in, "match_grad"), dg = dev_of(dout, "match_grad"), dm = dev_of(out, "match_grad");
+  const weedcu_view dv = din.view(), iv = in.view();
+  weedcu_view gv = dout.view();
+  // the reduced values live at out.offset in the dense layout dout's view describes (the caller match_shape'd dout to din);
+  // both are read through dout's strides, each from its own buffer
+  const uint64_t g_off = gv.offset;
+  gv.offset = 0U;
+  throw_on_error(weedcu_match_grad_real(dd.ptr, &dv, di.ptr, &iv, dg.ptr + g_off, &gv, dm.ptr + out.offset, (int)index, backend_config().ref_index_quirks ? 1 : 0,
+                                        dd.stream),
+                 "match_grad");
+}
+
 static void softmax_fwd(int log_mode, const tcapint &index, const Tensor &a, Tensor &out, const char *name) {
   validate_all_same_device({&a, &out}, name);
   require_real(a, "Tensor dtype mismatch in softmax_forward!");

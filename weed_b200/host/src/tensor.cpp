@@ -568,6 +568,100 @@ void Tensor::make_sum_node(TensorPtr a, TensorPtr out, const tcapint &axis) { //
     a->reduce_grad_broadcast();
   });
 }
+// max / min along an axis (reference tensor.cpp:705-785): the output tensor is laid out exactly like Tensor::sum(a, axis)'s
+namespace {
+TensorPtr axis_extremum(TensorPtr a, symint axis, bool is_min) {
+  axis = wrap_axis(axis, a->shape.size());
+  const size_t p_stride = a->stride[(size_t)axis];
+  if (!p_stride || (a->shape[(size_t)axis] == 1U)) {
+    a->shape[(size_t)axis] = 1U;
+    return a;
+  }
+  a = Tensor::contiguous(a);
+  const bool rg = a->requires_grad;
+  std::vector<tcapint> shp = a->shape, str = a->stride;
+  shp[(size_t)axis] = 1U;
+  str[(size_t)axis] = 0U;
+  size_t j = (size_t)axis + 1;
+  while ((j < str.size()) && !str[j]) ++j;
+  if (j < str.size()) {
+    const size_t o_stride = str[j] / p_stride;
+    for (; j < str.size(); ++j) str[j] /= (tcapint)o_stride;
+  }
+  TensorPtr out = Tensor::allocate_like(shp, str, *a, a->storage->dtype, rg, false);
+  if (is_min) Weed::min((tcapint)axis, *a, *out);
+  else Weed::max((tcapint)axis, *a, *out);
+  if (rg) Tensor::make_match_node(a, out, (tcapint)axis);
+  return out;
+}
+} // namespace
+TensorPtr Tensor::max(TensorPtr a, symint axis) { return axis_extremum(a, axis, false); }
+TensorPtr Tensor::min(TensorPtr a, symint axis) { return axis_extremum(a, axis, true); }
+void Tensor::make_match_node(TensorPtr a, TensorPtr out, const tcapint &axis) { // tensor.cpp:787-814
+  out->make_gradient();
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), axis]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) node_owner_lost();
+    TensorPtr dx = view_copy(a->grad);
+    TensorPtr dy = view_copy(out->grad);
+    if (dy->shape.size() < a->shape.size()) dy->unsqueeze(axis); // re-insert the reduced axis
+    dx->match_shape(a);
+    dx->materialize_broadcast();
+    dy->match_shape(dx);
+    Weed::match_grad(axis, *dx, *a, *dy, *out);
+    a->grad = dx;
+    a->reduce_grad_broadcast();
+  });
+}
+TensorPtr Tensor::max(TensorPtr a) { // tensor.cpp:993-1022
+  const bool rg = a->requires_grad;
+  TensorPtr out = allocate_scalar_like(*a, rg);
+  Weed::max(*a, *out);
+  if (rg) make_max_node(a, out);
+  return out;
+}
+TensorPtr Tensor::min(TensorPtr a) { // tensor.cpp:1024-1053
+  const bool rg = a->requires_grad;
+  TensorPtr out = allocate_scalar_like(*a, rg);
+  Weed::min(*a, *out);
+  if (rg) make_min_node(a, out);
+  return out;
+}
+namespace {
+void make_full_extremum_node(TensorPtr a, TensorPtr out, bool is_min) {
+  out->make_gradient();
+  a->make_gradient(true);
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, wout = std::weak_ptr<Tensor>(out), is_min]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) node_owner_lost();
+    TensorPtr a_grad = full_grad(a);
+    TensorPtr out_grad = view_copy(out->grad);
+    out_grad->match_shape(a_grad);
+    if (is_min) Weed::min_grad(*a_grad, *a, *out_grad, *out);
+    else Weed::max_grad(*a_grad, *a, *out_grad, *out);
+    settle_grad(a, a_grad);
+  });
+}
+} // namespace
+void Tensor::make_max_node(TensorPtr a, TensorPtr out) { make_full_extremum_node(a, out, false); }
+void Tensor::make_min_node(TensorPtr a, TensorPtr out) { make_full_extremum_node(a, out, true); }
+TensorPtr Tensor::clamp(TensorPtr a, real1 lo, real1 hi) { // tensor.cpp:1055-1082
+  const bool rg = a->requires_grad;
+  TensorPtr out = allocate_like(*a, a->storage->dtype, rg, false);
+  Weed::clamp(*a, lo, hi, *out);
+  if (rg) make_clamp_node(a, lo, hi, out);
+  return out;
+}
+void Tensor::make_clamp_node(TensorPtr a, real1 lo, real1 hi, TensorPtr out) {
+  out->make_gradient();
+  out->grad_node = std::make_shared<Node>(std::vector<TensorPtr>{a}, [a, lo, hi, wout = std::weak_ptr<Tensor>(out)]() {
+    TensorPtr out = wout.lock(); // the node is owned by this tensor: a strong capture would be a cycle
+    if (!out) node_owner_lost();
+    TensorPtr a_grad = full_grad(a);
+    Weed::clamp_grad(*a_grad, *a, *(out->grad), lo, hi);
+    settle_grad(a, a_grad);
+  });
+}
 TensorPtr Tensor::mean(TensorPtr a, symint axis) { // tensor.cpp:682-693
   axis = wrap_axis(axis, a->shape.size());
   TensorPtr tmp = sum(a, axis);
