@@ -7,6 +7,7 @@
 // same file builds against both trees is the source-level proof of the drop-in claim — and exposes
 // a small handle-based C-ABI in the style of the reference's own src/shared_api.cpp:79-449
 // (integer handles, int error codes, last-error string).
+#include "common/serializer.hpp" // (modules/max.hpp and friends use Serializer without including it)
 #include "autograd/adam.hpp"
 #include "autograd/bci_with_logits_loss.hpp"
 #include "autograd/cross_entropy_loss.hpp"
@@ -23,11 +24,24 @@
 #include "modules/sequential.hpp"
 #include "modules/sigmoid.hpp"
 #include "modules/tanh.hpp"
+#include "modules/dropout.hpp"
+#include "modules/gru.hpp"
+#include "modules/lstm.hpp"
+#include "modules/max.hpp"
+#include "modules/mean.hpp"
+#include "modules/min.hpp"
+#include "modules/positional_encoding.hpp"
+#include "modules/qwen_decoder_layer.hpp"
+#include "modules/rms_norm.hpp"
+#include "modules/rope.hpp"
+#include "modules/softmax.hpp"
+#include "modules/swiglu.hpp"
 #include "modules/transformer_encoder_layer.hpp"
 #include "tensors/real_tensor.hpp"
 #include "tensors/symbol_tensor.hpp"
 
 #include <chrono>
+#include <fstream>
 #include <cstring>
 #include <iterator>
 #include <map>
@@ -360,7 +374,28 @@ int64_t wh_module(const char *kind, const int64_t *args, int n) {
       e->self_attn->use_kv_cache = false; // public fields; constructor defaults are kv-cache + 4-bit quant
       e->self_attn->kv_quant_bits = 0;
       m = e;
-    } else if (k == "gelu") m = std::make_shared<GeLU>();
+    } else if (k == "rmsnorm") m = std::make_shared<RMSNorm>((tcapint)a(0));
+    else if (k == "swiglu") {
+      SwiGLUPtr sw = std::make_shared<SwiGLU>((tcapint)a(0), (tcapint)a(1));
+      sw->_register_params(); // the constructor leaves param_vector empty (include/modules/swiglu.hpp:35-44)
+      m = sw;
+    } else if (k == "rope") m = std::make_shared<RoPE>((tcapint)a(0), (tcapint)a(1));
+    else if (k == "qwen") {
+      QwenDecoderLayerPtr q = std::make_shared<QwenDecoderLayer>((tcapint)a(0), (tcapint)a(1), (tcapint)a(2), (tcapint)a(3), (tcapint)a(4));
+      q->self_attn->use_kv_cache = false; // constructor defaults: kv cache + 4-bit quantisation (host code with random_device)
+      q->self_attn->kv_quant_bits = 0;
+      q->mlp->_register_params();
+      q->_register_params();
+      m = q;
+    } else if (k == "gru") m = std::make_shared<GRU>((tcapint)a(0), (tcapint)a(1), g_dtag);
+    else if (k == "lstm") m = std::make_shared<LSTM>((tcapint)a(0), (tcapint)a(1), g_dtag);
+    else if (k == "posenc_fixed") m = std::make_shared<PositionalEncoding>((tcapint)a(0), (tcapint)a(1), 8192.0, g_dtag);
+    else if (k == "dropout") m = std::make_shared<Dropout>((real1)a(0) / (real1)1000);
+    else if (k == "softmax") m = std::make_shared<Softmax>((symint)a(0));
+    else if (k == "mean") m = std::make_shared<Mean>((symint)a(0));
+    else if (k == "max") m = std::make_shared<Max>((symint)a(0));
+    else if (k == "min") m = std::make_shared<Min>((symint)a(0));
+    else if (k == "gelu") m = std::make_shared<GeLU>();
     else if (k == "relu") m = std::make_shared<ReLU>();
     else if (k == "tanh") m = std::make_shared<Tanh>();
     else if (k == "sigmoid") m = std::make_shared<Sigmoid>();
@@ -369,6 +404,26 @@ int64_t wh_module(const char *kind, const int64_t *args, int n) {
       for (int i = 0; i < n; ++i) layers.push_back(M(args[i]));
       m = std::make_shared<Sequential>(layers);
     } else throw std::invalid_argument("wh_module: unknown kind '" + k + "'");
+    g_modules[g_next] = m;
+    return g_next++;
+  })
+}
+// checkpoint round trip through Module::save / Module::load (src/modules/module.cpp:53-375)
+int wh_module_save(int64_t mh, const char *path) {
+  WH_TRY({
+    std::ofstream o(path, std::ios::binary);
+    if (!o) throw std::invalid_argument("wh_module_save: cannot open the file");
+    M(mh)->save(o);
+    o.close();
+    return 0;
+  })
+}
+int64_t wh_module_load(const char *path) {
+  WH_TRY({
+    std::ifstream i(path, std::ios::binary);
+    if (!i) throw std::invalid_argument("wh_module_load: cannot open the file");
+    ModulePtr m = Module::load(i);
+    i.close();
     g_modules[g_next] = m;
     return g_next++;
   })

@@ -863,3 +863,306 @@ def test_gemm_epilogue_fusions_match_unfused_passes(P):
         assert cases.rel_err(b, a) <= 5e-3, (i, cases.rel_err(b, a))
         checked += 1
     assert checked >= 18
+
+
+# ------------------------------------------------------------------------------------ round 2: §8(f)-3 checkpoints + C API, §8(f)-4 modules
+def _walk_checkpoint(buf):
+    """Independent reader of the reference's checkpoint layout (src/modules/module.cpp:53-375, src/tensors/parameter.cpp:16-56,
+    src/storage/storage.cpp:25-119). Returns the byte ranges whose content the reference leaves undefined: the high word of
+    every storage's 8-byte device id (include/common/serializer.hpp:51-56 writes 8 bytes starting at a 4-byte symint)."""
+    import struct
+    pos, undefined = [0], []
+    u32 = lambda: (struct.unpack_from("<I", buf, pos[0])[0], pos.__setitem__(0, pos[0] + 4))[0]
+    skip = lambda n: pos.__setitem__(0, pos[0] + n)
+
+    def storage():
+        stype = u32()
+        undefined.append((pos[0] + 4, pos[0] + 8))
+        skip(8)
+        size = u32()
+        assert stype in (1, 2, 5, 6), stype
+        skip(4 * size)
+
+    def parameter():
+        skip(4)          # device id
+        skip(4)          # offset
+        rank = u32()
+        skip(8 * rank)   # (shape, stride) pairs
+        storage()
+
+    def boolean():
+        b = buf[pos[0]]
+        skip(1)
+        return bool(b)
+
+    def module():
+        t = u32()
+        if t == 1:       # Sequential
+            for _ in range(u32()):
+                module()
+        elif t == 2:     # Linear
+            skip(8)
+            parameter()
+            if boolean():
+                parameter()
+        elif t in (3, 4, 5, 19, 11, 12):   # ReLU, Sigmoid, Tanh, GeLU, MigrateCpu, MigrateGpu
+            pass
+        elif t == 6:     # Dropout
+            skip(5)
+        elif t == 7:     # LayerNorm
+            skip(8)
+            parameter()
+            parameter()
+        elif t == 8:     # Embedding
+            skip(8)
+            parameter()
+        elif t in (9, 10):  # GRU, LSTM
+            skip(8)
+            module()
+            module()
+        elif t in (13, 14, 20, 21, 22, 24, 25, 27, 28):  # axis modules
+            skip(4)
+        elif t == 17:    # MultiHeadAttention
+            skip(4 + 16 + 1 + 4)
+            for _ in range(4):
+                module()
+            if boolean():
+                module()
+        elif t == 18:    # TransformerEncoderLayer
+            skip(12)
+            for _ in range(6):
+                module()
+        elif t == 23:    # Reshape
+            skip(4 * u32())
+        elif t == 26:    # PositionalEncoding
+            skip(12)
+        elif t == 29:    # LearnedPositionalEncoding
+            skip(8)
+            parameter()
+        elif t == 30:    # RMSNorm
+            skip(8)
+            parameter()
+        elif t == 31:    # RoPE
+            skip(12)
+        elif t == 32:    # SwiGLU
+            skip(8)
+            for _ in range(3):
+                module()
+        elif t == 33:    # QwenDecoderLayer
+            skip(12)
+            for _ in range(4):
+                module()
+        else:
+            raise AssertionError(f"unknown module type {t} at byte {pos[0] - 4}")
+
+    module()
+    assert pos[0] == len(buf), (pos[0], len(buf))
+    return undefined
+
+
+def _checkpoint_model(H, seed):
+    T, d = 8, 16
+    mods = [H.module("posenc", T, d), H.module("encoder", d, 2, 32), H.module("layernorm", d), H.module("linear", d, 24, 1), H.module("softmax", -1)]
+    model = H.module("sequential", *mods)
+    H.init_params(model, seed)
+    return model, T, d
+
+
+def test_checkpoint_round_trip_with_reference(P, R, tmp_path):
+    """a model saved by the reference build loads in the product (same outputs), the product's own save of
+    it is byte-identical to the reference's file except for the bytes the reference leaves undefined, and the reference
+    loads the product's file back."""
+    set_mode(P, 1)
+    ref_path, prod_path, ref2_path = (str(tmp_path / n) for n in ("ref.qml", "prod.qml", "ref2.qml"))
+    model_r, T, d = _checkpoint_model(R, 71)
+    R.module_save(model_r, ref_path)   # before the first forward
+    x = np.random.default_rng(72).uniform(-1, 1, size=T * d).astype(np.float32)
+    y_ref = R.read(R.forward(model_r, R.tensor(x, [1, T, d])))
+
+    loaded = P.module_load(ref_path)
+    assert P.param_count(loaded) == R.param_count(model_r)   # a loaded model can resume training
+    # (saved before its first forward, like the reference's file: `y + bias` mutates a bias Parameter to rank 3 in both builds,
+    #  tensor.cpp:306-332, and Parameter::save writes the mutated rank)
+    P.module_save(loaded, prod_path)
+    y = P.read(P.forward(loaded, P.tensor(x, [1, T, d])))
+    assert cases.rel_err(y, y_ref) <= 2e-5
+    a, b = open(ref_path, "rb").read(), open(prod_path, "rb").read()
+    assert len(a) == len(b)
+    undefined = _walk_checkpoint(a)
+    assert _walk_checkpoint(b) == undefined
+    ma, mb = bytearray(a), bytearray(b)
+    for lo, hi in undefined:
+        ma[lo:hi] = bytes(hi - lo)
+        mb[lo:hi] = bytes(hi - lo)
+    assert ma == mb, "the product's checkpoint differs from the reference's outside the undefined device-id high words"
+
+    back = R.module_load(prod_path)
+    R.module_save(back, ref2_path)
+    y_back = R.read(R.forward(back, R.tensor(x, [1, T, d])))
+    assert np.array_equal(y_back, y_ref)
+    c = bytearray(open(ref2_path, "rb").read())
+    for lo, hi in undefined:
+        c[lo:hi] = bytes(hi - lo)
+    assert c == ma
+    P.reset()
+    R.reset()
+
+
+def test_checkpoint_of_every_module_family_round_trips(P, tmp_path):
+    """Module::save / Module::load for the §8(f)-4 families: the reloaded model computes the same outputs, and saving it
+    again gives the same bytes."""
+    set_mode(P, 1)
+    rng = np.random.default_rng(73)
+    builds = {
+        "qwen": (lambda: P.module("qwen", 16, 2, 2, 32, 32), [1, 6, 16]),
+        "swiglu_rms": (lambda: P.module("sequential", P.module("rmsnorm", 16), P.module("swiglu", 16, 32)), [1, 6, 16]),
+        "lstm": (lambda: P.module("lstm", 5, 7), [3, 5]),
+        "misc": (lambda: P.module("sequential", P.module("posenc_fixed", 12, 8), P.module("dropout", 0), P.module("mean", 0), P.module("tanh")), [2, 6, 8]),
+    }
+    for name, (build, shape) in builds.items():
+        m = build()
+        P.init_params(m, 80)
+        x = rng.uniform(-1, 1, size=int(np.prod(shape))).astype(np.float32)
+        y0 = P.read(P.forward(m, P.tensor(x, shape)))
+        p1, p2 = str(tmp_path / f"{name}_1.qml"), str(tmp_path / f"{name}_2.qml")
+        P.module_save(m, p1)
+        m2 = P.module_load(p1)
+        y1 = P.read(P.forward(m2, P.tensor(x, shape)))
+        assert np.array_equal(y0, y1), name
+        P.module_save(m2, p2)
+        assert open(p1, "rb").read() == open(p2, "rb").read(), name
+        _walk_checkpoint(open(p1, "rb").read())
+        P.reset()
+
+
+def test_shared_c_api_load_forward_train_step(P, tmp_path):
+    """The reference's C API (include/shared_api.hpp:34-60) exported by the product's host library: load_module, forward /
+    forward_int, get_result*, train_step, save_module, free_module, get_error codes."""
+    import ctypes as C
+    set_mode(P, 1)
+    host_lib = os.path.join(os.path.dirname(P.path), "libweed_b200_mock.so" if "mock" in os.path.basename(P.path) else "libweed_b200.so")
+    api = C.CDLL(host_lib)
+    U = C.c_ulonglong
+    for f in ("load_module", "get_result_index_count", "get_result_size", "get_result_offset", "get_result_type"):
+        getattr(api, f).restype = U
+    # (a) a real-valued MLP: forward == the harness' forward of the same checkpoint
+    mlp = P.module("sequential", P.module("linear", 6, 9, 1), P.module("tanh"), P.module("linear", 9, 4, 1))
+    P.init_params(mlp, 90)
+    path = str(tmp_path / "mlp.qml")
+    P.module_save(mlp, path)
+    x = np.random.default_rng(91).uniform(-1, 1, size=5 * 6).astype(np.float32)
+    want = P.read_storage(P.forward(mlp, P.tensor(x, [5, 6])))
+    mid = api.load_module(path.encode())
+    assert api.get_error(U(mid)) == 0
+    shape = (U * 2)(5, 6)
+    xd = (C.c_double * 30)(*x.astype(np.float64))
+    api.forward(U(mid), U(1), U(2), shape, xd)
+    assert api.get_error(U(mid)) == 0
+    assert api.get_result_index_count(U(mid)) == 2 and api.get_result_size(U(mid)) == 20 and api.get_result_type(U(mid)) == 1
+    dims, strides = (U * 2)(), (U * 2)()
+    api.get_result_dims(U(mid), dims, strides)
+    assert list(dims) == [5, 4] and list(strides) == [1, 5]
+    out = (C.c_double * 20)()
+    api.get_result(U(mid), out)
+    assert np.array_equal(np.array(out, np.float32), want)
+    # (b) a token model: train_step moves the parameters, save_module writes a loadable file, forward_int runs it
+    tok = P.module("sequential", P.module("embedding", 11, 8), P.module("linear", 8, 11, 1))
+    P.init_params(tok, 92)
+    tpath, tpath2 = str(tmp_path / "tok.qml"), str(tmp_path / "tok2.qml")
+    P.module_save(tok, tpath)
+    tid = api.load_module(tpath.encode())
+    ids = (C.c_longlong * 6)(1, 4, 2, 7, 7, 3)
+    tgt = (C.c_longlong * 6)(4, 2, 7, 7, 3, 0)
+    tshape = (U * 1)(6)
+    api.forward_int(U(tid), U(3), U(1), tshape, ids)
+    assert api.get_error(U(tid)) == 0 and api.get_result_size(U(tid)) == 66
+    before = (C.c_double * 66)()
+    api.get_result(U(tid), before)
+    for _ in range(3):
+        api.train_step(U(tid), U(1), tshape, ids, U(6), tgt, C.c_double(0.5))
+        assert api.get_error(U(tid)) == 0
+    api.forward_int(U(tid), U(3), U(1), tshape, ids)
+    after = (C.c_double * 66)()
+    api.get_result(U(tid), after)
+    lg0, lg1 = np.array(before).reshape(11, 6), np.array(after).reshape(11, 6)     # [6, 11] column-major
+    nll = lambda lg: float(np.mean([np.log(np.exp(lg[:, t]).sum()) - lg[tgt[t], t] for t in range(6)]))
+    assert nll(lg1) < nll(lg0) - 0.05, (nll(lg0), nll(lg1))
+    api.save_module(U(tid), tpath2.encode())
+    assert api.get_error(U(tid)) == 0
+    tid2 = api.load_module(tpath2.encode())      # (its bias is saved at the rank `y + bias` mutated it to: 8 bytes longer)
+    assert api.get_error(U(tid2)) == 0 and tid2 != tid
+    api.forward_int(U(tid2), U(3), U(1), tshape, ids)
+    again = (C.c_double * 66)()
+    api.get_result(U(tid2), again)
+    assert np.array_equal(np.array(again), np.array(after))
+    api.free_module(U(tid2))
+    # (c) error codes: unknown id -> 2; a failing forward latches 1 on the module
+    assert api.get_error(U(57)) == 2
+    bad = (U * 2)(5, 7)
+    api.forward(U(mid), U(1), U(2), bad, (C.c_double * 35)())
+    assert api.get_error(U(mid)) == 1
+    api.free_module(U(mid))
+    api.free_module(U(tid))
+    assert api.get_error(U(mid)) == 2
+    P.reset()
+
+
+def _module_fwd_bwd(H, kind, args, shape, x, w, seed, steps=1):
+    m = H.module(kind, *args)
+    H.init_params(m, seed)
+    xt = H.tensor(x, shape, True)
+    ys = []
+    y = None
+    for _ in range(steps):
+        y = H.forward(m, xt)
+        ys.append(H.read(y))
+    H.backward(H.op("sum", [H.op("mul", [y, H.tensor(w, H.info(y)["shape"])])]))
+    out = {"y": np.concatenate(ys), "dx": H.read(H.grad(xt))}
+    for i in range(H.param_count(m)):
+        g = H.grad(H.param(m, i))
+        out[f"g{i}"] = H.read_storage(g) if g else np.zeros(1, np.float32)
+    H.reset()
+    return out
+
+
+@pytest.mark.parametrize("kind,args,shape,steps", [
+    ("rmsnorm", (16,), [1, 7, 16], 1), ("swiglu", (16, 40), [1, 7, 16], 1), ("rope", (8, 32), [2, 3, 5, 8], 1),
+    ("qwen", (16, 2, 2, 32, 32), [1, 6, 16], 1), ("lstm", (5, 7), [3, 5], 2),
+    ("posenc_fixed", (12, 8), [2, 6, 8], 1), ("max", (1,), [4, 9], 1), ("min", (-1,), [1, 5, 6], 1),
+], ids=["rmsnorm", "swiglu", "rope", "qwen_layer", "lstm_two_steps", "positional_encoding", "max_module", "min_module"])
+def test_f4_module_families_match_reference(P, R, kind, args, shape, steps):
+    """RMSNorm, SwiGLU, RoPE, QwenDecoderLayer (RoPE attention), LSTM (two recurrent steps), the fixed
+    PositionalEncoding and the Max / Min modules: forward, input gradient and every parameter gradient against the compiled
+    reference CPU build (shapes where its reductions are self-consistent, D1 / D2). Not covered because the reference
+    itself throws there [measured]: grouped KV heads (W_k is d_model wide but reshaped to num_kv_heads * head_dim,
+    multihead_attention.cpp:155-157) and GRU::forward (adds a [B, H] chunk to a [B, 3H] projection, gru.cpp:31)."""
+    rng = np.random.default_rng(sum(map(ord, kind)) + len(shape))
+    n = int(np.prod(shape))
+    x = rng.uniform(-1, 1, size=n).astype(np.float32)
+    w = rng.uniform(-1, 1, size=4096).astype(np.float32)
+    # the weight tensor of the scalar loss needs the output's element count: run the reference first to learn it
+    probe = R.module(kind, *args)
+    R.init_params(probe, 60)
+    n_out = int(np.prod(R.info(R.forward(probe, R.tensor(x, shape)))["shape"]))
+    R.reset()
+    a = _module_fwd_bwd(R, kind, args, shape, x, w[:n_out], 60, steps)
+    for fused in (1, 0):
+        set_mode(P, fused)
+        b = _module_fwd_bwd(P, kind, args, shape, x, w[:n_out], 60, steps)
+        assert a.keys() == b.keys()
+        for k in a:
+            same_or_both_zero(a[k], b[k], 5e-5, f"{kind} fused={fused}: {k}")
+    set_mode(P, 1)
+
+
+def test_reference_catch_suite_passes_on_the_cuda_device():
+    """The reference's OWN unit tests (test/tests.cpp, its 42 real-dtype dense TEST_CASEs; test_main.cpp already expects a
+    CUDAEngine under WEED_ENABLE_CUDA, :31-37) compiled against this repo's host library and run with --device-gpu.
+    Built by oracle/Makefile (_ref/ref_unittest_b200) from the sources where they lie; skipped on a box without it."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_unittest_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_unittest_b200 not present on this box")
+    res = subprocess.run([exe, "--device-gpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert res.stdout.count("All tests passed") == 2, res.stdout[-3000:]   # TEST_DTAG = GPU, then DEFAULT_DEVICE

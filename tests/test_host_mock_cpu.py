@@ -48,6 +48,10 @@ test_token_model_bf16_arbiter = G.test_token_model_fused_bf16_matches_fp64_bf16_
 test_encoder_fp64_arbiter = G.test_encoder_layer_fused_matches_fp64_arbiter_B4
 test_c4_scaled_B1 = G.test_config_c4_scaled_dims_B1_matches_reference
 test_gemm_epilogue_fusions = G.test_gemm_epilogue_fusions_match_unfused_passes
+test_checkpoint_round_trip = G.test_checkpoint_round_trip_with_reference
+test_checkpoint_families = G.test_checkpoint_of_every_module_family_round_trips
+test_shared_c_api = G.test_shared_c_api_load_forward_train_step
+test_f4_modules = G.test_f4_module_families_match_reference
 
 
 def test_training_steps_do_not_leak_device_buffers(P):
@@ -81,3 +85,15 @@ def test_training_steps_do_not_leak_device_buffers(P):
         assert outstanding() == base, f"fused={fused}: {outstanding() - base} device buffers leaked over 5 steps"
         P.reset()
     G.set_mode(P, 1)
+
+
+def test_reference_catch_suite_passes_on_the_mock_device():
+    """The reference's own Catch suite (real-dtype TEST_CASEs, filtered at build time by tools/ref_tests/filter_tests.py)
+    against the product's host library on the oracle-backed mock device."""
+    if not os.path.exists("/root/reference/test/tests.cpp"):
+        pytest.skip("reference sources not present")
+    subprocess.check_call(["make", "-C", MOCK_DIR, "ref_unittest_mock"], stdout=subprocess.DEVNULL)
+    res = subprocess.run([os.path.join(MOCK_DIR, "ref_unittest_mock"), "--device-gpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert res.stdout.count("All tests passed") == 2, res.stdout[-3000:]

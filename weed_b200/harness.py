@@ -151,6 +151,13 @@ class Harness:
         a = (C.c_int64 * max(len(args), 1))(*[int(x) for x in args])
         return self._ck(self.lib.wh_module(kind.encode(), a, C.c_int(len(args))))
 
+    def module_save(self, m, path):
+        self._ck(self.lib.wh_module_save(C.c_int64(m), path.encode()))
+
+    def module_load(self, path):
+        self.lib.wh_module_load.restype = C.c_int64
+        return self._ck(self.lib.wh_module_load(path.encode()))
+
     def module_set(self, m, field, value):
         self._ck(self.lib.wh_module_set(C.c_int64(m), field.encode(), C.c_int64(int(value))))
 

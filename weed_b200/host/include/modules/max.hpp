@@ -1,0 +1,3 @@
+// Source-compatibility forwarder: client code written against vm6502q/weed includes "modules/max.hpp".
+#pragma once
+#include "weed_b200/modules.hpp"

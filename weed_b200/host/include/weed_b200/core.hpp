@@ -49,6 +49,9 @@ typedef std::complex<real1> complex;
 #define HALF_R1 0.5f
 #define ZERO_R1_F 0.0f
 #define ONE_R1_F 1.0f
+const complex ONE_CMPLX = complex(ONE_R1, ZERO_R1); // reference include/common/weed_types.hpp:206-208
+const complex ZERO_CMPLX = complex(ZERO_R1, ZERO_R1);
+const complex I_CMPLX = complex(ZERO_R1, ONE_R1);
 constexpr real1 PI_R1 = (real1)3.14159265358979323846;
 constexpr real1 E_R1 = (real1)2.71828182845904523536;
 constexpr real1 ADAM_BETA1_DEFAULT = (real1)0.9;
@@ -105,6 +108,10 @@ struct BackendConfig {
   // a Linear with at least this many output features whose output takes part in autograd is treated as an LM head: bf16-only
   // logits + log-sum-exp partials from the GEMM epilogue, fp32 logits only if something reads them
   tcapint lm_head_min_cols = 4096U;
+  // Module::save writes device storages as REAL_CPU_DENSE / device id -1 — byte-compatible with what the reference's CPU
+  // build writes for the same weights, and loadable by it. Off: REAL_GPU_DENSE + the device id, as the reference's GPU
+  // build does (src/storage/gpu_real_storage.cpp:35-50). Loading accepts both and always places the data on the device.
+  bool save_portable = true;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)
@@ -201,7 +208,32 @@ struct Storage : public std::enable_shared_from_this<Storage> {
   virtual bool is_gpu() = 0;
   virtual StoragePtr cpu() = 0;
   virtual StoragePtr gpu(const int64_t &did = -1) = 0;
+  // Checkpoint format of the reference (src/storage/storage.cpp:25-119): storage type, device id (8 bytes), element count,
+  // then the elements. GPU storages are read back to the host first (src/storage/gpu_real_storage.cpp:35-50).
   virtual void save(std::ostream &) const;
+  static StoragePtr load(std::istream &);
+  static void write_storage_type(std::ostream &out, const StorageType &x);
+  static void read_storage_type(std::istream &in, StorageType &x);
+};
+
+// reference include/common/serializer.hpp:25-99: raw little-endian fields, no framing
+struct Serializer {
+  static void write_bool(std::ostream &out, const bool &x);
+  static void read_bool(std::istream &in, bool &x);
+  static void write_tcapint(std::ostream &out, const tcapint &x);
+  static void read_tcapint(std::istream &in, tcapint &x);
+  static void write_symint(std::ostream &out, const symint &x);
+  static void read_symint(std::istream &in, symint &x);
+  // the reference writes sizeof(int64_t) bytes starting at a 4-byte symint (serializer.hpp:51-56): the low word is the
+  // value, the high word whatever followed it on the stack. Here: the sign-extended value; readers use the low word.
+  static void write_int64(std::ostream &out, const symint &x);
+  static void read_int64(std::istream &in, symint &x);
+  static void write_size_t(std::ostream &out, const size_t &x);
+  static void read_size_t(std::istream &in, size_t &x);
+  static void write_real(std::ostream &out, const real1 &x);
+  static void read_real(std::istream &in, real1 &x);
+  static void write_real1_f(std::ostream &out, const real1_f &x);
+  static void read_real1_f(std::istream &in, real1_f &x);
 };
 
 template <typename T> struct TypedStorage : Storage {
@@ -234,11 +266,13 @@ struct CpuRealStorage : CpuStorage<real1> {
   CpuRealStorage(tcapint n) : CpuStorage<real1>(REAL_CPU_DENSE, n) {}
   CpuRealStorage(const std::vector<real1> &v) : CpuStorage<real1>(REAL_CPU_DENSE, v) {}
   StoragePtr gpu(const int64_t &did = -1) override;
+  void save(std::ostream &) const override;
 };
 struct CpuIntStorage : CpuStorage<symint> {
   CpuIntStorage(tcapint n) : CpuStorage<symint>(INT_CPU_DENSE, n) {}
   CpuIntStorage(const std::vector<symint> &v) : CpuStorage<symint>(INT_CPU_DENSE, v) {}
   StoragePtr gpu(const int64_t &did = -1) override;
+  void save(std::ostream &) const override;
 };
 typedef std::shared_ptr<CpuRealStorage> CpuRealStoragePtr;
 typedef std::shared_ptr<CpuIntStorage> CpuIntStoragePtr;
@@ -349,6 +383,7 @@ struct GpuRealStorage : GpuStorage<real1> {
     return dev->GetReal(buffer, idx);
   }
   StoragePtr cpu() override;
+  void save(std::ostream &) const override;
   // bf16 copies of matrix views of this storage, packed for the tensor-core GEMM (ops.cpp)
   struct Bf16Shadow {
     BufferPtr buf;
@@ -396,6 +431,7 @@ struct GpuIntStorage : GpuStorage<symint> {
     return dev->GetInt(buffer, idx);
   }
   StoragePtr cpu() override;
+  void save(std::ostream &) const override;
 };
 typedef std::shared_ptr<GpuRealStorage> GpuRealStoragePtr;
 typedef std::shared_ptr<GpuIntStorage> GpuIntStoragePtr;

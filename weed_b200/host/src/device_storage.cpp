@@ -153,7 +153,6 @@ StoragePtr Storage::Upcast(const DType &dt) {
   if (dt == DType::COMPLEX) throw std::invalid_argument("Complex storage is outside the CUDA backend's scope (SURVEY §8)");
   return get_ptr();
 }
-void Storage::save(std::ostream &) const { throw std::domain_error("Storage::save: serialisation is outside this backend's scope"); }
 
 StoragePtr CpuRealStorage::gpu(const int64_t &did) { return std::make_shared<GpuRealStorage>(data, did); }
 StoragePtr CpuIntStorage::gpu(const int64_t &did) { return std::make_shared<GpuIntStorage>(data, did); }

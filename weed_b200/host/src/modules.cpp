@@ -260,13 +260,15 @@ MultiHeadAttention::MultiHeadAttention(tcapint d_model_, tcapint num_heads_, tca
       W_o(std::make_shared<Linear>(d_model_, d_model_, true, true, DType::REAL, dtag, did)), rope(r), use_kv_cache(_use_kv_cache),
       kv_quant_bits(kv_quant_bits_) {
   if (d_model % num_heads) throw std::invalid_argument("d_model must be divisible by num_heads");
-  if (rope) throw std::invalid_argument("RoPE is outside the CUDA backend's scope (SURVEY §8 f-4)");
+  _register_params();
+  if (mask_val == ZERO_R1) mask_val = -1.701411835e38f; // -2^127, multihead_attention.hpp:106-114
+}
+void MultiHeadAttention::_register_params() {
   param_vector = W_q->parameters();
   auto add = [&](const std::vector<ParameterPtr> &q) { param_vector.insert(param_vector.end(), q.begin(), q.end()); };
   add(W_k->parameters());
   add(W_v->parameters());
   add(W_o->parameters());
-  if (mask_val == ZERO_R1) mask_val = -1.701411835e38f; // -2^127, multihead_attention.hpp:106-114
 }
 void MultiHeadAttention::train() {
   for (auto &l : {W_q, W_k, W_v, W_o}) l->train();
@@ -295,7 +297,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
   if (W_q->bias && W_k->bias && W_v->bias) {
     // when the fused tensor-core attention core follows, it is the projections' only reader and takes their bf16 copies
     const BackendConfig &c0 = backend_config();
-    const bool core_reads_bf16 = c0.fused && c0.matmul_precision == WEEDCU_GEMM_BF16 && !use_kv_cache && num_kv_heads == num_heads && head_dim == 64 &&
+    const bool core_reads_bf16 = c0.fused && c0.matmul_precision == WEEDCU_GEMM_BF16 && !use_kv_cache && !rope && num_kv_heads == num_heads && head_dim == 64 &&
                                  (x->shape[0] % 8U) == 0U && x->shape.size() == 3U && (x->shape[1] % 8U) == 0U && x->shape[1] >= 64U;
     const std::vector<TensorPtr> qkv =
         Tensor::linear_grouped(x, {W_q->weight, W_k->weight, W_v->weight}, {W_q->bias, W_k->bias, W_v->bias}, core_reads_bf16);
@@ -314,7 +316,8 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
     throw std::domain_error("4-bit TurboQuant KV cache (multihead_attention.cpp:205-277) is host-loop code outside this backend's "
                             "scope; construct with kv_quant_bits = 0 or set use_kv_cache = false");
   const BackendConfig &cfg = backend_config();
-  const bool fuse = cfg.fused && !use_kv_cache && (num_kv_heads == num_heads) && dense_contiguous(*Q) && dense_contiguous(*K) &&
+  // (RoPE rotates Q and K between the projections and the scores: those layers take the reference's composition below)
+  const bool fuse = cfg.fused && !use_kv_cache && !rope && (num_kv_heads == num_heads) && dense_contiguous(*Q) && dense_contiguous(*K) &&
                     dense_contiguous(*V);
   TensorPtr out;
   if (fuse) {
@@ -364,7 +367,7 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
     return fuse_residual ? W_o->forward_add(out, fuse_residual) : W_o->forward(out);
   }
 
-  if (cfg.fused && use_kv_cache && kv_quant_bits == 0 && num_kv_heads == num_heads && head_dim <= 64 && dense_contiguous(*Q) &&
+  if (cfg.fused && use_kv_cache && !rope && kv_quant_bits == 0 && num_kv_heads == num_heads && head_dim <= 64 && dense_contiguous(*Q) &&
       dense_contiguous(*K) && dense_contiguous(*V) && x->storage->device == DeviceTag::GPU) {
     // Float KV cache (multihead_attention.cpp:169-199, 278-287) with the attention over it as ONE
     // entry: append K, V to their slots, scores against the cache in place, softmax, P V, output
@@ -397,11 +400,15 @@ TensorPtr MultiHeadAttention::forward(const TensorPtr x) { // multihead_attentio
   Q = Tensor::transpose(Q, 1, 2);
   K = Tensor::transpose(K, 1, 2);
   V = Tensor::transpose(V, 1, 2);
+  if (rope) { // optional rotary embedding (Qwen), multihead_attention.cpp:163-167
+    Q = rope->forward(Q);
+    K = rope->forward(K);
+  }
 
   if (use_kv_cache) { // float cache, multihead_attention.cpp:169-199,278-287
     const tcapint T_new = (tcapint)T;
     if (!k_cache) {
-      if (!max_seq_len) max_seq_len = 2048U;
+      if (!max_seq_len) max_seq_len = rope ? rope->max_seq_len : 2048U;
       cache_len = 0U;
       const std::vector<tcapint> cs{(tcapint)B, (tcapint)num_kv_heads, max_seq_len, (tcapint)head_dim};
       k_cache = Tensor::zeros(cs, false, false, DType::REAL, x->storage->device, x->storage->get_device_id());
@@ -460,10 +467,13 @@ TransformerEncoderLayer::TransformerEncoderLayer(const tcapint &d_model_, const 
   case SIGMOID_FN: activation = std::make_shared<Sigmoid>(); break;
   case TANH_FN: activation = std::make_shared<Tanh>(); break;
   case RELU_FN: activation = std::make_shared<ReLU>(); break;
-  case SWIGLU_FN: throw std::invalid_argument("SwiGLU is outside the CUDA backend's scope (SURVEY §8 f-4)");
+  case SWIGLU_FN: activation = std::make_shared<SwiGLU>(); break; // (as the reference: a default-constructed SwiGLU without projections)
   case GELU_FN:
   default: activation = std::make_shared<GeLU>();
   }
+  _register_params();
+}
+void TransformerEncoderLayer::_register_params() {
   param_vector = self_attn->parameters();
   auto add = [&](const std::vector<ParameterPtr> &q) { param_vector.insert(param_vector.end(), q.begin(), q.end()); };
   add(ff1->parameters());
