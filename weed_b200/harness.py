@@ -197,6 +197,11 @@ class Harness:
     def adam(self, module, lr, b1=0.9, b2=0.999, eps=1e-8):
         return self._ck(self.lib.wh_adam(C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_int64(module)))
 
+    def adam_moment(self, opt, module, i, which=0):
+        """Adam's first (which=0) / second (which=1) moment of parameter i as a tensor handle."""
+        self.lib.wh_adam_moment.restype = C.c_int64
+        return self._ck(self.lib.wh_adam_moment(C.c_int64(opt), C.c_int64(module), C.c_int(i), C.c_int(which)))
+
     def adam_step(self, opt, module):
         self._ck(self.lib.wh_adam_step(C.c_int64(opt), C.c_int64(module)))
 
