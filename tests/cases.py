@@ -704,6 +704,22 @@ for _M, _K, _N, _al, _bl, _batch, _acc in [
         return _matmul(be, rng, M, K, N, al, bl, batch, acc, 0)
 
 
+# Few outputs, long reduction: the weight-gradient products of the small-feature configs (C2's
+# 13x65536x26, C4's 512x32768x1), which the product runs split-K (gemm_f32.cu). The oracle sums K
+# terms in order in fp32, the kernel in per-slice partials, so the bound scales with sqrt(K)*eps.
+for _M, _K, _N, _al, _bl, _acc in [
+        (13, 65536, 26, "row", "col", 0),       # dW = X^T dY: both operands K-contiguous
+        (13, 65536, 26, "row", "col", 1),
+        (26, 32768, 1, "row", "col", 1),
+        (512, 4096, 1, "col", "col", 0),        # A K-strided
+        (70, 2048, 150, "col", "row", 0),       # B K-strided, ragged tiles
+        (64, 2051, 64, "row", "row", 0),        # ragged K
+]:
+    @case(f"matmul_f32_splitk_{_M}x{_K}x{_N}_{_al}_{_bl}_acc{_acc}", tol=1e-4)
+    def _c(be, rng, M=_M, K=_K, N=_N, al=_al, bl=_bl, acc=_acc):
+        return _matmul(be, rng, M, K, N, al, bl, 1, acc, 0)
+
+
 # --------------------------------------------------------------------------------------- decode
 def _decode(be, rng, B, H, hd, S, steps, causal=1):
     """KV-cache attention over a sequence of calls (cache append + attention): `steps` = T_new of

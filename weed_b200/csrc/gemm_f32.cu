@@ -149,6 +149,73 @@ gemm_f32_thin_kernel(GemmArgs g) {
   *d = g.accumulate ? (*d + s) : s;
 }
 
+// Few outputs, long reduction (the weight gradients of a small layer over a big batch: dW = X^T dY with X [65536, 13] in the
+// heart_attack MLP, or the [512, 1] head of the binary-addition transformer over 32768 tokens): the 128 x 128 tile kernel
+// puts the whole reduction on one block (1.6 ms for 13 x 26 x 65536), one-thread-per-output likewise. Here the reduction
+// is split over blockIdx.z: a block stages 64 x 64-deep slabs of both operands in shared memory (whichever index is
+// contiguous in memory is the one adjacent threads walk), every thread carries a 4 x 4 register tile over its slice, and
+// the per-slice partial tiles are summed in slice order by a second kernel (deterministic: no atomics).
+constexpr int SK_T = 64, SK_K = 64;
+__global__ void __launch_bounds__(256)
+gemm_f32_splitk_kernel(GemmArgs g, uint32_t k_per_slice, float *__restrict__ partial) {
+  pdl_grid_sync();
+  __shared__ float As[SK_K][SK_T + 1]; // As[k][m]
+  __shared__ float Bs[SK_K][SK_T + 1]; // Bs[k][n]
+  const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // tx -> rows m (4 each), ty -> cols n (4 each)
+  const uint32_t m0 = blockIdx.x * SK_T, n0 = blockIdx.y * SK_T;
+  const uint32_t k_begin = blockIdx.z * k_per_slice, k_end = min(g.K, k_begin + k_per_slice);
+  const bool a_kfast = g.as1 <= g.as0, b_kfast = g.bs0 <= g.bs1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (uint32_t k0 = k_begin; k0 < k_end; k0 += SK_K) {
+    for (uint32_t i = tid; i < SK_T * SK_K; i += 256) {
+      const uint32_t am_ = a_kfast ? i / SK_K : i % SK_T, ak = a_kfast ? i % SK_K : i / SK_T;
+      const uint32_t gm = m0 + am_, gk = k0 + ak;
+      As[ak][am_] = (gm < g.M && gk < k_end) ? g.a[(uint64_t)gm * g.as0 + (uint64_t)gk * g.as1] : 0.0f;
+      const uint32_t bn = b_kfast ? i / SK_K : i % SK_T, bk = b_kfast ? i % SK_K : i / SK_T;
+      const uint32_t gn = n0 + bn, gkb = k0 + bk;
+      Bs[bk][bn] = (gn < g.N && gkb < k_end) ? g.b[(uint64_t)gkb * g.bs0 + (uint64_t)gn * g.bs1] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < SK_K; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = As[kk][tx * 4 + i];
+        bv[i] = Bs[kk][ty * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float *dst = partial + (uint64_t)blockIdx.z * g.M * g.N;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t m = m0 + tx * 4 + i, n = n0 + ty * 4 + j;
+      if (m < g.M && n < g.N) dst[(uint64_t)n * g.M + m] = acc[i][j];
+    }
+}
+__global__ void __launch_bounds__(256)
+gemm_f32_splitk_reduce_kernel(GemmArgs g, uint32_t slices, const float *__restrict__ partial) {
+  pdl_grid_sync();
+  const uint64_t total = (uint64_t)g.M * g.N, idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float s = 0.0f;
+  for (uint32_t z = 0; z < slices; ++z) s += partial[(uint64_t)z * total + idx];
+  const uint32_t m = (uint32_t)(idx % g.M), n = (uint32_t)(idx / g.M);
+  float *d = g.c + (uint64_t)m * g.cs0 + (uint64_t)n * g.cs1;
+  *d = g.accumulate ? (*d + s) : s;
+}
+
 int launch_gemm_f32(const float *a, const weedcu_mat *am, const float *b, const weedcu_mat *bm,
                     float *c, const weedcu_mat *cm, uint32_t M, uint32_t K, uint32_t N,
                     uint32_t batch, int accumulate, cudaStream_t st) {
@@ -166,6 +233,29 @@ int launch_gemm_f32(const float *a, const weedcu_mat *am, const float *b, const 
   g.accumulate = accumulate;
   if (batch > 65535) return WEEDCU_EINVAL;
   ProfScope prof(WEEDCU_PROF_GEMM_F32, st, 2.0 * (double)M * N * K * batch);
+  {
+    const uint32_t tiles = ((M + SK_T - 1) / SK_T) * ((N + SK_T - 1) / SK_T);
+    if (batch == 1 && K >= 2048u && tiles <= 64u && (uint64_t)M * N <= (1ull << 18)) {
+      uint32_t slices = (2u * (uint32_t)kNumSMs + tiles - 1) / tiles;
+      const uint32_t max_slices = (K + 4 * SK_K - 1) / (4 * SK_K); // at least 4 slabs per slice
+      if (slices > max_slices) slices = max_slices;
+      if (slices >= 2u) {
+        uint32_t kps = (K + slices - 1) / slices;
+        kps = (kps + SK_K - 1) / SK_K * SK_K;
+        slices = (K + kps - 1) / kps;
+        float *partial = nullptr;
+        WCU_CHECK(pool_alloc((void **)&partial, sizeof(float) * (size_t)slices * M * N, st));
+        launch_k(gemm_f32_splitk_kernel, dim3((M + SK_T - 1) / SK_T, (N + SK_T - 1) / SK_T, slices), dim3(256), 0, st, g, kps, partial);
+        int rc = after_launch();
+        if (rc == 0) {
+          launch_k(gemm_f32_splitk_reduce_kernel, dim3((unsigned)(((uint64_t)M * N + 255) / 256)), dim3(256), 0, st, g, slices, (const float *)partial);
+          rc = after_launch();
+        }
+        pool_free(partial, st);
+        return rc;
+      }
+    }
+  }
   if ((uint64_t)M * N * (uint64_t)K <= (1ull << 22) || N <= 4 || M <= 4) {
     if ((uint64_t)M * N <= (1ull << 24) && (N <= 4 || M <= 4 || (uint64_t)M * N * K <= (1ull << 18))) {
       const uint64_t total = (uint64_t)M * N;
