@@ -239,11 +239,11 @@ def check_dp(P, args, cfg, rank, world, dist, torch):
     """N ranks on a global batch of GB sequences (GB / N per rank, bucketed gradient all-reduce overlapped with backward,
     1/N folded into the fused Adam) against ONE rank on the same GB sequences, in both GEMM precisions:
       * per-step loss: <= 1e-3 relative with bf16 tensor-core GEMMs, <= 1e-5 with the fp32 path;
-      * Adam's first and second moment of EVERY parameter after the steps (linear / quadratic in the exchanged gradients):
-        rel-to-max <= 1e-4 at fp32, <= 2e-2 (the bf16 bound) at bf16.
+      * Adam's first and second moment of every parameter after the steps (linear / quadratic in the exchanged gradients):
+        rel-to-max <= 1e-4 at fp32, <= 2e-2 (the bf16 bound) at bf16; parameters with an exactly-zero gradient are listed.
     Parameter checksums are reported, not gated: Adam's step is lr * m / (sqrt(v) + eps) ~ lr * sign(g) wherever a gradient
     is rounding noise around zero (zero-initialised biases), so two correct runs differ by 2 * lr in those elements."""
-    steps = 3
+    steps = int(os.environ.get("CHECK_DP_STEPS", "3"))
     GB = args.batch * world if args.batch else 16
     assert GB % world == 0
     Bl = GB // world
@@ -278,7 +278,15 @@ def check_dp(P, args, cfg, rank, world, dist, torch):
 
     result = {"check_dp": True, "n_gpus": world, "global_batch": GB, "batch_per_gpu": Bl, "steps": steps, "layers": cfg["L"], "vocab": cfg["V"],
               "seq_len": T, "adam_chained_per_bucket": os.environ.get("WH_DP_CHAIN_ADAM", "0") != "0", "ok": True}
-    for precision, name, loss_bound, moment_bound in ((GEMM_FP32, "fp32", 1e-5, 1e-4), (GEMM_BF16, "bf16", 1e-3, 2e-2)):
+    # The gated legs run LayerNorm's backward with the analytic gradient. The reference's autograd chain (the default, kept
+    # for parity) leaves a term in dx that does not scale with the upstream gradient (core.hpp: layernorm_exact_grad), so
+    # with it a gradient of the mean loss over GB sequences and the mean of N gradients over GB / N sequences differ by
+    # (1 - 1/N) of that term per LayerNorm -- measured ~0.3 % of the gradient per layer at this shape -- whoever exchanges
+    # them. The third leg reports that figure, ungated.
+    legs = ((GEMM_FP32, "fp32", 1e-5, 1e-4, 1, True), (GEMM_BF16, "bf16", 1e-3, 2e-2, 1, True),
+            (GEMM_BF16, "bf16_reference_layernorm_chain", 1e-3, 2e-2, 0, False))
+    for precision, name, loss_bound, moment_bound, exact_ln, gated in legs:
+        P.config("layernorm_exact_grad", exact_ln)
         dp_losses, dp_mom, dp_sums = run(lcfg, rank, precision)
         t = torch.tensor(dp_losses, dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
@@ -288,19 +296,36 @@ def check_dp(P, args, cfg, rank, world, dist, torch):
             one_losses, one_mom, one_sums = run(gcfg, None, precision)
             P.lib.wh_dp_set_active(C.c_int(1))
             loss_rel = float(max(abs(a - b) / abs(b) for a, b in zip(dp_losses, one_losses)))
+            # Parameters whose gradient is exactly zero -- the Q/K/V projections and the LayerNorm in front of them: the
+            # reference propagates nothing through its batched matmul (SURVEY defect D9), reproduced here -- or rounding
+            # noise only (max|m| below 1e-4 of the median over all parameters) are listed, not compared.
+            scale = np.array([float(np.max(np.abs(m0))) for m0, _ in one_mom])
+            floor = 1e-4 * float(np.median(scale[scale > 0]))
             worst_m = worst_v = 0.0
-            for (m1, v1), (m0, v0) in zip(dp_mom, one_mom):
-                if np.any(m0):
-                    worst_m = max(worst_m, float(np.max(np.abs(m1 - m0)) / np.max(np.abs(m0))))
-                if np.any(v0):
-                    worst_v = max(worst_v, float(np.max(np.abs(v1 - v0)) / np.max(np.abs(v0))))
+            noise, rows = [], []
+            for i, ((m1, v1), (m0, v0)) in enumerate(zip(dp_mom, one_mom)):
+                if scale[i] <= floor:
+                    noise.append({"param": i, "size": int(m0.size), "max_abs_m": scale[i]})
+                    continue
+                dm = float(np.max(np.abs(m1 - m0)) / np.max(np.abs(m0)))
+                dv = float(np.max(np.abs(v1 - v0)) / np.max(np.abs(v0)))
+                rows.append((max(dm, dv), i, int(m0.size), scale[i], dm, dv))
+                worst_m, worst_v = max(worst_m, dm), max(worst_v, dv)
+            if os.environ.get("CHECK_DP_VERBOSE"):
+                print(name, [(r[1], round(r[4], 6)) for r in sorted(rows, key=lambda r: r[1])], file=sys.stderr)
+            rows.sort(reverse=True)
             chk = float(np.max(np.abs(dp_sums - one_sums) / np.maximum(one_sums[:, 1:2], 1e-30)))
             ok = bool(loss_rel <= loss_bound and worst_m <= moment_bound and worst_v <= moment_bound)
             result[name] = {"loss_dp": dp_losses, "loss_single": one_losses, "loss_rel_diff": loss_rel, "loss_bound": loss_bound,
                             "adam_m_rel_to_max_diff": worst_m, "adam_v_rel_to_max_diff": worst_v, "moment_bound": moment_bound,
-                            "param_checksum_rel_diff_not_gated": chk, "ok": ok}
-            result["ok"] = result["ok"] and ok
+                            "params_gated": len(rows), "params_zero_gradient_noise_only": noise, "median_max_abs_m": float(np.median(scale)),
+                            "worst_params": [{"param": r[1], "size": r[2], "max_abs_m": r[3], "m_diff": r[4], "v_diff": r[5]} for r in rows[:4]],
+                            "param_checksum_rel_diff_not_gated": chk, "layernorm_backward": "analytic" if exact_ln else "reference chain",
+                            "gated": gated, "ok": ok}
+            if gated:
+                result["ok"] = result["ok"] and ok
         dist.barrier()
+    P.config("layernorm_exact_grad", 0)
     return result if rank == 0 else None
 
 

@@ -50,6 +50,23 @@ class Timer:
         return ms.value / iters
 
 
+class LossEnds:
+    """Drops each step's handles (and with them its autograd graph and activations) as the step ends, reading the loss on
+    the first and the last of `total` calls only, so that the steps in between run without a host sync."""
+
+    def __init__(self, P, total):
+        self.P, self.total, self.calls, self.first, self.last = P, total, 0, None, None
+
+    def step_done(self, loss, *others):
+        self.calls += 1
+        if self.calls == 1:
+            self.first = float(np.sum(self.P.read(loss)))
+        if self.calls == self.total:
+            self.last = float(np.sum(self.P.read(loss)))
+        for h in (loss,) + others:
+            self.P.free(h)
+
+
 # ----------------------------------------------------------------------------------- C2
 def run_c2(P, timer, peaks):
     """examples/heart_attack.cpp scaled to 65536 x 13: Linear(13,26)-Tanh-Linear(26,1), bci_with_logits_loss,
@@ -64,7 +81,7 @@ def run_c2(P, timer, peaks):
     P.init_params(m, 2000)
     opt = P.adam(m, 1e-3)
     xt, yt = P.tensor(np.ascontiguousarray(x.T).ravel(), [rows, 13]), P.tensor(y, [rows, 1])
-    losses = []
+    seen = LossEnds(P, 3 + 20)
 
     def step(_i):
         pred = P.forward(m, xt)
@@ -72,10 +89,10 @@ def run_c2(P, timer, peaks):
         P.backward(loss)
         P.adam_step(opt, m)
         P.zero_grad(m)
-        losses.append(loss)
+        seen.step_done(loss, pred)
 
     ms = timer.time(step, 20, 3)
-    first, last = float(np.sum(P.read(losses[0]))), float(np.sum(P.read(losses[-1])))
+    first, last = seen.first, seen.last
     P.release_since(mark)
     # algorithmic bytes of one step: x read twice (forward, dW1), hidden [rows, 26] ~10 passes, output column ~12 passes
     alg_bytes = 4.0 * rows * (2 * 13 + 10 * 26 + 12)
@@ -213,7 +230,7 @@ def run_c4(P, timer, peaks):
     opt = P.adam(model, 1e-4)
     tok = P.symbol(np.ascontiguousarray(tokens.T).ravel(), [B, T])
     tgt = P.tensor(np.ascontiguousarray(target.T).ravel(), [B, tlen])
-    losses = []
+    seen = LossEnds(P, 3 + 10)
 
     def step(_i):
         logits = P.forward_symbol(model, tok)
@@ -224,10 +241,10 @@ def run_c4(P, timer, peaks):
         P.adam_step(opt, model)
         P.zero_grad(model)
         P.module_set(model, "reset_cache", 1)
-        losses.append(loss)
+        seen.step_done(loss, pred, logits)
 
     ms = timer.time(step, 10, 3)
-    first, last = float(np.sum(P.read(losses[0]))) / (B * tlen), float(np.sum(P.read(losses[-1]))) / (B * tlen)
+    first, last = seen.first / (B * tlen), seen.last / (B * tlen)
     P.release_since(mark)
     toks = B * T
     flop = 2.0 * toks * d * d * 4 + 2.0 * toks * d * dff * 2 + 4.0 * B * Hh * T * T * (d // Hh)   # forward

@@ -543,6 +543,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (warp == 2) tmem_alloc_pair(smem_u32((const void *)tmem_slot), TMEM_COLS);
   tcgen05_fence_before();
+  __syncthreads();    // implied by the cluster barrier below; stated for compute-sanitizer, which does not model barrier.cluster
   cluster_sync_all(); // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;

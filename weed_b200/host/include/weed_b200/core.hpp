@@ -112,6 +112,11 @@ struct BackendConfig {
   // build writes for the same weights, and loadable by it. Off: REAL_GPU_DENSE + the device id, as the reference's GPU
   // build does (src/storage/gpu_real_storage.cpp:35-50). Loading accepts both and always places the data on the device.
   bool save_portable = true;
+  // LayerNorm backward: false = what the reference's autograd chain computes (its div node drops dout on the denominator
+  // branch, tensor.cpp:1506-1521, leaving a term that does not scale with the upstream gradient); true = the analytic
+  // gradient. bench.py --check-dp uses `true` to test the gradient exchange: with the reference chain a sharded batch and
+  // a whole batch differ by that unscaled term, whatever exchanges the gradients.
+  bool layernorm_exact_grad = false;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)

@@ -204,7 +204,7 @@ tcapint BaseTensor::get_broadcast_size() const {
 bool BaseTensor::is_scalar() const {
   if (shape.empty()) return false;
   for (size_t i = 0U; i < shape.size(); ++i)
-    if ((shape[i] - 1U) * stride[i]) return false;
+    if (shape[i] != 1U && stride[i] != 0U) return false;
   return true;
 }
 tcapint BaseTensor::get_storage_index(const tcapint &idx) const {

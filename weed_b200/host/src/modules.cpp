@@ -177,7 +177,7 @@ TensorPtr LayerNorm::forward(const TensorPtr x) {
                                                g->device_ptr_ro() + g->offset, mean->device_ptr_ro(), rstd->device_ptr_ro(),
                                                dx_src ? dx_src + dx->offset : nullptr, dx_ptr + dx->offset,
                                                dg ? dg->device_ptr() + dg->offset : nullptr, db ? db->device_ptr() + db->offset : nullptr,
-                                               0 /* reference chain */, x->stream()),
+                                               backend_config().layernorm_exact_grad ? 1 : 0 /* reference chain */, x->stream()),
                      "LayerNorm backward");
       if (x->requires_grad) x->grad = dx;
       if (dg) g->grad = dg;
