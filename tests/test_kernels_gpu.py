@@ -431,7 +431,7 @@ def test_gemm_bf16_grouped_bf16out(gpu, M, N, K, groups, mode):
         gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
 
 
-@pytest.mark.parametrize("rows,V,K", [(1024, 5003, 64), (256, 1000, 136), (8192, 2048, 768)])
+@pytest.mark.parametrize("rows,V,K", [(1024, 5003, 64), (256, 1000, 136), (8192, 2048, 768), (264, 1000, 100), (2048, 70, 64)])
 def test_cross_entropy_on_bf16_logits(gpu, rows, V, K):
     """weedcu_cross_entropy_fwd_bf16in / _bwd_pack_bf16in: the loss path when the LM head's epilogue wrote only the bf16 copy
     of the logits. lse from the bf16 logits, the target logit recomputed exactly from the product's bf16 operands

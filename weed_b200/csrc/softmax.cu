@@ -594,28 +594,58 @@ ce_fwd_partial_bf16(const __nv_bfloat16 *__restrict__ x, uint32_t rows, uint32_t
 // ce_fwd_partial_bf16): merge the (max, sum exp) pairs, and recompute the ONE logit the loss needs per row — the target
 // column — as the same bf16 x bf16 -> fp32 dot product (+ bias) the tensor cores formed, from the GEMM's own operands.
 // Block = 32 adjacent rows x 8 k-slices (a warp reads 32 adjacent rows of one k: coalesced for the MN-major activations).
+// The 32 target columns of a K-major weight operand are scattered 2*K-byte runs: read per thread they are 32 different
+// sectors per load instruction (251 us at 8192 x 768), so each warp first copies 4 of them into shared memory with 16-byte
+// loads (row pitch K + 2 halves: the 32 rows of a k land in 32 different banks).
 __global__ void __launch_bounds__(256)
 ce_fwd_stats_finish(const float2 *__restrict__ stats, uint32_t tiles, uint32_t rows, uint32_t V, const __nv_bfloat16 *__restrict__ a, int a_major,
                     uint64_t lda, const __nv_bfloat16 *__restrict__ b, int b_major, uint64_t ldb, uint32_t K, const float *__restrict__ bias,
-                    const int32_t *__restrict__ targets, float *__restrict__ lse, float *__restrict__ nll) {
+                    const int32_t *__restrict__ targets, float *__restrict__ lse, float *__restrict__ nll, int stage_b) {
   pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t ce_finish_smem[];
+  __nv_bfloat16 *bsm = reinterpret_cast<__nv_bfloat16 *>(ce_finish_smem);
   __shared__ float red[8][33];
   const uint32_t rx = threadIdx.x & 31u, kx = threadIdx.x >> 5;
   const uint32_t r = blockIdx.x * 32u + rx;
   const bool live = r < rows;
   const uint32_t t = live ? (uint32_t)targets[r] : 0u;
+  const uint32_t pitch = K + 2u;
+  if (stage_b) { // K-major b, K % 8 == 0, 16-byte aligned rows: warp kx copies the target rows of block rows 4 kx .. 4 kx + 3
+    for (uint32_t i = 0; i < 4u; ++i) {
+      const uint32_t lr = 4u * kx + i, gr = blockIdx.x * 32u + lr;
+      const uint32_t tt = (gr < rows) ? (uint32_t)targets[gr] : V;
+      if (tt >= V) continue; // warp-uniform
+      const uint4 *src = reinterpret_cast<const uint4 *>(b + (uint64_t)tt * ldb);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(bsm + lr * pitch); // pitch is even: 4-byte aligned
+      for (uint32_t c = rx; c < K / 8u; c += 32u) {
+        const uint4 v = __ldg(src + c);
+        dst[4u * c] = v.x, dst[4u * c + 1u] = v.y, dst[4u * c + 2u] = v.z, dst[4u * c + 3u] = v.w;
+      }
+    }
+    __syncthreads();
+  }
   float acc = 0.0f;
   if (live && t < V) {
     const __nv_bfloat16 *ap = a_major ? a + r : a + (uint64_t)r * lda;
-    const __nv_bfloat16 *bp = b_major ? b + t : b + (uint64_t)t * ldb;
-    const uint64_t as = a_major ? lda : 1u, bs = b_major ? ldb : 1u;
+    const uint64_t as = a_major ? lda : 1u;
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t k = kx;
-    for (; k + 24u < K; k += 32u) { // 4 independent products in flight
+    if (stage_b) {
+      const __nv_bfloat16 *bp = bsm + rx * pitch;
+      for (; k + 24u < K; k += 32u) { // 4 independent products in flight
 #pragma unroll
-      for (uint32_t u = 0; u < 4; ++u) a4[u] += __bfloat162float(ap[(uint64_t)(k + 8u * u) * as]) * __bfloat162float(bp[(uint64_t)(k + 8u * u) * bs]);
+        for (uint32_t u = 0; u < 4; ++u) a4[u] += __bfloat162float(ap[(uint64_t)(k + 8u * u) * as]) * __bfloat162float(bp[k + 8u * u]);
+      }
+      for (; k < K; k += 8u) a4[0] += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[k]);
+    } else {
+      const __nv_bfloat16 *bp = b_major ? b + t : b + (uint64_t)t * ldb;
+      const uint64_t bs = b_major ? ldb : 1u;
+      for (; k + 24u < K; k += 32u) {
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) a4[u] += __bfloat162float(ap[(uint64_t)(k + 8u * u) * as]) * __bfloat162float(bp[(uint64_t)(k + 8u * u) * bs]);
+      }
+      for (; k < K; k += 8u) a4[0] += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[(uint64_t)k * bs]);
     }
-    for (; k < K; k += 8u) a4[0] += __bfloat162float(ap[(uint64_t)k * as]) * __bfloat162float(bp[(uint64_t)k * bs]);
     acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
   red[kx][rx] = acc;
@@ -748,6 +778,87 @@ ce_bwd_pack_kernel(const XT *__restrict__ x, uint32_t rows, uint32_t V, const in
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
     part[(uint64_t)blockIdx.x * V + j0 + threadIdx.x] = t;
   }
+}
+// ce_bwd_pack_kernel<bf16> for the LM-head case (no fp32 dlogits, nothing to accumulate into): 2 B read + 2 B written per
+// element, so the pass is bound by how few instructions an element costs. A thread owns 8 adjacent rows (one 16-byte
+// load / store per column), a block 1024 rows x kCeP16Cols columns in batches of 8 columns (8 loads in flight per
+// thread). Per element: unpack, one FFMA into the ex2 argument (-lse * log2(e) is per row), ex2.approx, scale, pack, column
+// sum. The one-hot term is not in the loop: a row whose target falls into the block's columns patches that one element
+// afterwards (and the block's column sum through shared memory), bit-identical to computing (p - 1) * g in place.
+constexpr int kCeP16Cols = 32;
+__device__ __forceinline__ float exp2f_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__global__ void __launch_bounds__(128)
+ce_bwd_pack16_kernel(const __nv_bfloat16 *__restrict__ x, uint32_t rows, uint32_t V, const int32_t *__restrict__ targets,
+                     const float *__restrict__ lse, const float *__restrict__ dloss, __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  pdl_grid_sync();
+  __shared__ float red[4][kCeP16Cols];
+  __shared__ float fix[kCeP16Cols];
+  const uint32_t r = (blockIdx.x * 128u + threadIdx.x) * 8u;
+  const bool live = r < rows;
+  const uint32_t j0 = blockIdx.y * kCeP16Cols;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const float g = dloss[0] / (float)rows;
+  constexpr float kLog2e = 1.4426950408889634f;
+  if (threadIdx.x < kCeP16Cols) fix[threadIdx.x] = 0.0f;
+  float nl[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) nl[k] = 0.0f;
+  if (live) {
+    const float4 la = *reinterpret_cast<const float4 *>(lse + r), lb = *reinterpret_cast<const float4 *>(lse + r + 4);
+    nl[0] = -la.x * kLog2e, nl[1] = -la.y * kLog2e, nl[2] = -la.z * kLog2e, nl[3] = -la.w * kLog2e;
+    nl[4] = -lb.x * kLog2e, nl[5] = -lb.y * kLog2e, nl[6] = -lb.z * kLog2e, nl[7] = -lb.w * kLog2e;
+  }
+  __syncthreads(); // fix[] zeroed
+#pragma unroll 1
+  for (uint32_t c0 = 0; c0 < (uint32_t)kCeP16Cols; c0 += 8u) {
+    uint4 xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t j = j0 + c0 + u;
+      xv[u] = (live && j < V) ? __ldg(reinterpret_cast<const uint4 *>(x + (uint64_t)j * rows + r)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t j = j0 + c0 + u;
+      const uint32_t wd[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      uint32_t out[4];
+      float cs = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float e0 = __uint_as_float(wd[q] << 16), e1 = __uint_as_float(wd[q] & 0xffff0000u);
+        const float o0 = exp2f_approx(fmaf(e0, kLog2e, nl[2 * q])) * g, o1 = exp2f_approx(fmaf(e1, kLog2e, nl[2 * q + 1])) * g;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+        out[q] = *reinterpret_cast<const uint32_t *>(&h);
+        cs += o0 + o1;
+      }
+      if (live && j < V) *reinterpret_cast<uint4 *>(shadow + (uint64_t)j * rows + r) = make_uint4(out[0], out[1], out[2], out[3]);
+      else cs = 0.0f;
+      cs = warp_sum(cs);
+      if (lane == 0) red[w][c0 + u] = cs;
+    }
+  }
+  if (live) { // the one-hot term of the rows whose target is one of this block's columns
+    const int4 ta = *reinterpret_cast<const int4 *>(targets + r), tb = *reinterpret_cast<const int4 *>(targets + r + 4);
+    const uint32_t tg[8] = {(uint32_t)ta.x, (uint32_t)ta.y, (uint32_t)ta.z, (uint32_t)ta.w, (uint32_t)tb.x, (uint32_t)tb.y, (uint32_t)tb.z, (uint32_t)tb.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t tj = tg[k] - j0;
+      if (tj < (uint32_t)kCeP16Cols && tg[k] < V) {
+        const uint64_t off = (uint64_t)tg[k] * rows + r + k;
+        const float e = __bfloat162float(x[off]);
+        const float p = exp2f_approx(fmaf(e, kLog2e, nl[k]));
+        shadow[off] = __float2bfloat16_rn((p - 1.0f) * g);
+        atomicAdd(&fix[tj], -g); // every addend is the same value: the sum does not depend on the order
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kCeP16Cols && j0 + threadIdx.x < V)
+    part[(uint64_t)blockIdx.x * V + j0 + threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])) + fix[threadIdx.x];
 }
 // colsum[j] (+)= sum_c part[c][j] in a fixed order
 __global__ void __launch_bounds__(256)
@@ -1075,8 +1186,18 @@ int weedcu_cross_entropy_fwd_stats(const float *stats, uint32_t tiles, uint32_t 
   float *nll = nullptr;
   WCU_CHECK(pool_alloc((void **)&nll, sizeof(float) * (size_t)rows, st));
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, 8.0 * (double)rows * tiles + 2.0 * (double)rows * K * 2.0);
-  launch_k(ce_fwd_stats_finish, dim3((rows + 31u) / 32u), dim3(256), 0, st, (const float2 *)stats, tiles, rows, V, (const __nv_bfloat16 *)a, a_major, lda,
-           (const __nv_bfloat16 *)b, b_major, ldb, K, col_bias, targets, lse, nll);
+  // K-major weights: stage the 32 target columns of a block in shared memory (dynamic: 32 x (K + 2) halves)
+  const size_t stage_bytes = 32u * ((size_t)K + 2u) * 2u;
+  const int stage_b = !b_major && (K % 8u) == 0 && (ldb % 8u) == 0 && aligned16(b) && stage_bytes <= 200u * 1024u;
+  if (stage_b && stage_bytes > 48u * 1024u) {
+    static size_t granted = 0; // per process: the attribute only ever grows
+    if (stage_bytes > granted) {
+      WCU_CHECK(cudaFuncSetAttribute(ce_fwd_stats_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+      granted = stage_bytes;
+    }
+  }
+  launch_k(ce_fwd_stats_finish, dim3((rows + 31u) / 32u), dim3(256), stage_b ? stage_bytes : 0, st, (const float2 *)stats, tiles, rows, V,
+           (const __nv_bfloat16 *)a, a_major, lda, (const __nv_bfloat16 *)b, b_major, ldb, K, col_bias, targets, lse, nll, stage_b);
   int rc = after_launch();
   if (rc == 0) {
     weedcu_view v;
@@ -1103,8 +1224,12 @@ int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t r
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * V, st));
   ProfScope prof(WEEDCU_PROF_CROSS_ENTROPY, st, (accumulate ? 12.0 : (d ? 8.0 : 4.0)) * (double)rows * V);
-  launch_k(ce_bwd_pack_kernel<__nv_bfloat16>, dim3(nchunks, cgroups), dim3(256), 0, st, (const __nv_bfloat16 *)logits_bf16, rows, V, targets, lse, dloss, d,
-           accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
+  if (!d && aligned16(logits_bf16) && (V + kCeP16Cols - 1) / kCeP16Cols <= 65535u)
+    launch_k(ce_bwd_pack16_kernel, dim3(nchunks, (V + kCeP16Cols - 1) / kCeP16Cols), dim3(128), 0, st, (const __nv_bfloat16 *)logits_bf16, rows, V, targets, lse,
+             dloss, (__nv_bfloat16 *)dlogits_bf16, part);
+  else
+    launch_k(ce_bwd_pack_kernel<__nv_bfloat16>, dim3(nchunks, cgroups), dim3(256), 0, st, (const __nv_bfloat16 *)logits_bf16, rows, V, targets, lse, dloss, d,
+             accumulate, (__nv_bfloat16 *)dlogits_bf16, part);
   int rc = after_launch();
   if (rc == 0) {
     launch_k(ce_colsum_finish_kernel, dim3((V + 255u) / 256u), dim3(256), 0, st, part, nchunks, V, colsum);
