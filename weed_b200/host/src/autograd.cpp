@@ -57,6 +57,14 @@ void adam_collect(Adam &opt, const std::vector<ParameterPtr> &params, AdamBatch 
       slow.push_back(p);
       continue;
     }
+    {
+      // never touched by any backward so far: the gradient and both moments are still pending lazy zero fills, and with
+      // g = m = v = 0 the update (adam.hpp:84-104) leaves m, v and the parameter exactly as they are — nothing to launch
+      // (the Q/K/V projections and the LayerNorm in front of them, which the reference's attention sends no gradient to)
+      const GpuRealStorage *g0 = static_cast<const GpuRealStorage *>(g->storage.get());
+      const GpuRealStorage *m0 = static_cast<const GpuRealStorage *>(s.m->storage.get()), *v0 = static_cast<const GpuRealStorage *>(s.v->storage.get());
+      if (cfg.lazy_zero && g0->zero_pending && m0->zero_pending && v0->zero_pending) continue;
+    }
     if (b.stream && b.stream != p->stream()) throw std::domain_error("adam_step: parameters live on different devices");
     b.stream = p->stream();
     b.p.push_back(p->device_ptr());
