@@ -141,6 +141,11 @@ int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n,
  * din may be NULL when accumulate == 0 (bf16 copy and column sums only; weedcu_unary_grad_real gives the fp32 values). */
 int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols,
                           int accumulate, uint16_t *din_bf16, float *colsum, void *stream);
+/* weedcu_gelu_grad_pack with dout given as its bf16 copy ([rows, cols], rows contiguous): the case where the product that
+ * formed dout (the dA of the Linear behind the activation, matmul backward tensor.cpp:1105-1136) wrote only that copy
+ * because this node is its only reader. Same outputs. */
+int weedcu_gelu_grad_pack_bf16dy(float *din, const float *in, const uint16_t *dout_bf16, uint32_t rows, uint32_t cols,
+                                 int accumulate, uint16_t *din_bf16, float *colsum, void *stream);
 
 /* ------------------------------------------------------------------ R1-R2 reductions
  * Weed::reduce (src/ops/reduce.cpp:17-38,60-66): out[o] = sum_j a[base(o) + j*stride[axis]];

@@ -396,6 +396,12 @@ int weedcu_cross_entropy_fwd_bf16in(const uint16_t *logits_bf16, uint32_t rows, 
   }
   return weedcu_cross_entropy_fwd_stats(stats.data(), 1, rows, V, a, a_major, lda, b, b_major, ldb, K, col_bias, targets, lse, loss, stream);
 }
+int weedcu_gelu_grad_pack_bf16dy(float *din, const float *in, const uint16_t *dout_bf16, uint32_t rows, uint32_t cols, int accumulate, uint16_t *din_bf16,
+                                 float *colsum, void *stream) {
+  std::vector<float> wide((size_t)rows * cols);
+  for (size_t i = 0; i < wide.size(); ++i) wide[i] = bf16_widen(dout_bf16[i]);
+  return weedcu_gelu_grad_pack(din, in, wide.data(), rows, cols, accumulate, din_bf16, colsum, stream);
+}
 int weedcu_cross_entropy_bwd_pack_bf16in(const uint16_t *logits_bf16, uint32_t rows, uint32_t V, const int32_t *targets, const float *lse, const float *dloss,
                                          float *dlogits, uint64_t d_offset, int accumulate, uint16_t *dlogits_bf16, float *colsum, void *stream) {
   if (!logits_bf16) return WEEDCU_EINVAL;

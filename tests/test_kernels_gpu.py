@@ -470,3 +470,39 @@ def test_cross_entropy_on_bf16_logits(gpu, rows, V, K):
         assert cases.rel_err(d.reshape(V, rows).T, want) <= 2e-5
         assert np.array_equal(hsh.get(), _bf16_bits(d))
         assert cases.rel_err(hcs.get(), d.reshape(V, rows).sum(1)) <= 2e-5
+
+
+@pytest.mark.parametrize("rows,cols,acc", [(1032, 50, 0), (2048, 24, 1), (8192, 96, 0)])
+def test_gelu_grad_pack_on_bf16_dout(gpu, oracle, rows, cols, acc):
+    """weedcu_gelu_grad_pack_bf16dy: dout arrives as the bf16 copy the product behind it wrote. Bit-identical to
+    weedcu_gelu_grad_pack on the widened values, and equal to the oracle's gelu_grad_pack on them within 2e-5."""
+    import ctypes as C
+    U32, I32 = C.c_uint32, C.c_int
+    rng = np.random.default_rng(rows * 7 + cols)
+    n = rows * cols
+    d0, x = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-4, 4, n).astype(np.float32)
+    g_bits = _bf16_bits(rng.uniform(-1, 1, n).astype(np.float32))
+    g_wide = _bf16_widen(g_bits).astype(np.float32)
+    out = {}
+    for be, name in ((gpu, "bf16dy"), (gpu, "wide"), (oracle, "oracle")):
+        hd, hx = be.buf(d0.copy()), be.buf(x)
+        hs, hc = be.buf(np.zeros(n, np.uint16)), be.buf(np.full(cols, 3.0, np.float32))
+        if name == "bf16dy":
+            be.call("gelu_grad_pack_bf16dy", hd, hx, be.buf(g_bits), U32(rows), U32(cols), I32(acc), hs, hc)
+        else:
+            be.call("gelu_grad_pack", hd, hx, be.buf(g_wide), U32(rows), U32(cols), I32(acc), hs, hc)
+        be.sync()
+        out[name] = (hd.get(), hs.get(), hc.get())
+    for k in range(3):
+        assert np.array_equal(out["bf16dy"][k], out["wide"][k])
+    assert cases.rel_err(out["bf16dy"][0], out["oracle"][0]) <= 2e-5
+    assert cases.rel_err(out["bf16dy"][2], out["oracle"][2]) <= 2e-5
+    if not acc:
+        # no fp32 output asked for (the production call): the tanh.approx path; the bf16 copy may differ from the exact one by
+        # one bf16 ulp (2^-7 of the value), the column sums by the approximation's 2^-11
+        hs, hc = gpu.buf(np.zeros(n, np.uint16)), gpu.buf(np.zeros(cols, np.float32))
+        gpu.call("gelu_grad_pack_bf16dy", None, gpu.buf(x), gpu.buf(g_bits), U32(rows), U32(cols), I32(0), hs, hc)
+        gpu.sync()
+        exact = _bf16_widen(out["oracle"][1]).astype(np.float64)
+        assert np.max(np.abs(_bf16_widen(hs.get()).astype(np.float64) - exact)) <= 2.0 ** -7 * np.max(np.abs(exact)) + 1e-30
+        assert cases.rel_err(hc.get(), out["oracle"][2]) <= 2e-3

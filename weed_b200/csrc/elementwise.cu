@@ -158,6 +158,15 @@ __device__ __forceinline__ float gelu_dfdx(float x) {
   const float dinner = k2 * (1.0f + 3.0f * k1 * (x * x));
   return 0.5f * (1.0f + t) + (0.5f * x) * ((1.0f - t * t) * dinner);
 }
+// gelu_dfdx for a result that is rounded to bf16 right after: MUFU tanh (2^-11 relative) instead of the ~30-instruction
+// tanhf (gelu_grad_pack with no fp32 output was bound by instruction issue, not by its 6-8 B/elem: 52 us at 8192 x 3072)
+__device__ __forceinline__ float gelu_dfdx_for_bf16(float x) {
+  const float k1 = 0.044715f, k2 = 0.7978845608028654f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k2 * (x + k1 * ((x * x) * x))));
+  const float dinner = k2 * (1.0f + 3.0f * k1 * (x * x));
+  return 0.5f * (1.0f + t) + (0.5f * x) * ((1.0f - t * t) * dinner);
+}
 
 template <int OP> struct UnaryF {
   float param;
@@ -263,8 +272,16 @@ gelu_fwd_bf16_kernel(const float *__restrict__ x, float *__restrict__ y, __nv_bf
 // (that Linear's bias gradient). Same block shape as the LayerNorm / cross-entropy apply passes:
 // 256 threads x 4 adjacent rows x 8 columns, column partials per row chunk.
 constexpr int kGgCols = 8;
+// four adjacent rows of one column of dout: fp32, or the bf16 copy the product that formed it wrote instead (the ff2
+// Linear's dA when this node is its only reader: 2 B/elem less written by the GEMM and read here)
+__device__ __forceinline__ float4 gg_load4(const float *x, uint64_t off) { return *reinterpret_cast<const float4 *>(x + off); }
+__device__ __forceinline__ float4 gg_load4(const __nv_bfloat16 *x, uint64_t off) {
+  const uint2 u = *reinterpret_cast<const uint2 *>(x + off);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename DT, bool FAST>
 __global__ void __launch_bounds__(256)
-gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__restrict__ dout, uint32_t rows, uint32_t cols,
+gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const DT *__restrict__ dout, uint32_t rows, uint32_t cols,
                       int accumulate, __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
   pdl_grid_sync();
   __shared__ float red[8][kGgCols];
@@ -285,7 +302,7 @@ gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__r
         if (j < cols) {
           const uint64_t off = (uint64_t)j * rows + r;
           xv[u] = *reinterpret_cast<const float4 *>(in + off);
-          gv[u] = *reinterpret_cast<const float4 *>(dout + off);
+          gv[u] = gg_load4(dout, off);
           dv[u] = accumulate ? *reinterpret_cast<const float4 *>(din + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -294,10 +311,17 @@ gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__r
         const uint32_t j = j0 + i0 + u;
         if (j < cols) {
           float4 o;
-          o.x = dv[u].x + gv[u].x * gelu_dfdx(xv[u].x);
-          o.y = dv[u].y + gv[u].y * gelu_dfdx(xv[u].y);
-          o.z = dv[u].z + gv[u].z * gelu_dfdx(xv[u].z);
-          o.w = dv[u].w + gv[u].w * gelu_dfdx(xv[u].w);
+          if (FAST) { // only the bf16 copy and the column sums leave the kernel
+            o.x = dv[u].x + gv[u].x * gelu_dfdx_for_bf16(xv[u].x);
+            o.y = dv[u].y + gv[u].y * gelu_dfdx_for_bf16(xv[u].y);
+            o.z = dv[u].z + gv[u].z * gelu_dfdx_for_bf16(xv[u].z);
+            o.w = dv[u].w + gv[u].w * gelu_dfdx_for_bf16(xv[u].w);
+          } else {
+            o.x = dv[u].x + gv[u].x * gelu_dfdx(xv[u].x);
+            o.y = dv[u].y + gv[u].y * gelu_dfdx(xv[u].y);
+            o.z = dv[u].z + gv[u].z * gelu_dfdx(xv[u].z);
+            o.w = dv[u].w + gv[u].w * gelu_dfdx(xv[u].w);
+          }
           const uint64_t off = (uint64_t)j * rows + r;
           if (din) *reinterpret_cast<float4 *>(din + off) = o; // NULL: operand copy + column sums only
           __nv_bfloat162 h[2];
@@ -322,6 +346,60 @@ gelu_grad_pack_kernel(float *din, const float *__restrict__ in, const float *__r
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
     part[(uint64_t)blockIdx.x * cols + j0 + threadIdx.x] = t;
   }
+}
+// gelu_grad_pack for the production case (bf16 dout, no fp32 output, nothing to accumulate into): a thread owns 8 adjacent
+// rows — one 16-byte load of dout, two of the pre-activation and one 16-byte store per column — a block 1024 rows x 16
+// columns in two batches of 8 columns. 8 B/elem.
+constexpr int kGg16Cols = 16;
+__global__ void __launch_bounds__(128)
+gelu_grad_pack16_kernel(const float *__restrict__ in, const __nv_bfloat16 *__restrict__ dout, uint32_t rows, uint32_t cols,
+                        __nv_bfloat16 *__restrict__ shadow, float *__restrict__ part) {
+  pdl_grid_sync();
+  __shared__ float red[4][kGg16Cols];
+  const uint32_t r = (blockIdx.x * 128u + threadIdx.x) * 8u;
+  const bool live = r < rows;
+  const uint32_t j0 = blockIdx.y * kGg16Cols;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#pragma unroll 1
+  for (uint32_t c0 = 0; c0 < (uint32_t)kGg16Cols; c0 += 8u) {
+    float4 xa[8], xb[8];
+    uint4 gv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t j = j0 + c0 + u;
+      if (live && j < cols) {
+        const uint64_t off = (uint64_t)j * rows + r;
+        xa[u] = __ldg(reinterpret_cast<const float4 *>(in + off));
+        xb[u] = __ldg(reinterpret_cast<const float4 *>(in + off + 4));
+        gv[u] = __ldg(reinterpret_cast<const uint4 *>(dout + off));
+      } else {
+        xa[u] = xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gv[u] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t j = j0 + c0 + u;
+      const float xs[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+      const uint32_t gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      uint32_t out[4];
+      float cs = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float o0 = __uint_as_float(gw[q] << 16) * gelu_dfdx_for_bf16(xs[2 * q]);
+        const float o1 = __uint_as_float(gw[q] & 0xffff0000u) * gelu_dfdx_for_bf16(xs[2 * q + 1]);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+        out[q] = *reinterpret_cast<const uint32_t *>(&h);
+        cs += o0 + o1;
+      }
+      if (live && j < cols) *reinterpret_cast<uint4 *>(shadow + (uint64_t)j * rows + r) = make_uint4(out[0], out[1], out[2], out[3]);
+      cs = warp_sum(cs);
+      if (lane == 0) red[w][c0 + u] = cs;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kGg16Cols && j0 + threadIdx.x < cols)
+    part[(uint64_t)blockIdx.x * cols + j0 + threadIdx.x] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t cols, float *__restrict__ colsum) {
@@ -583,8 +661,10 @@ int weedcu_match_grad_full_real(float *din, const weedcu_view *dinv, const float
   return launch_ew<4>(views, ins, din, MatchGradF(), resolve_stream(stream));
 }
 
-int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,
-                          uint16_t *din_bf16, float *colsum, void *stream) {
+extern "C++" {
+template <typename DT>
+static int gelu_grad_pack_impl(float *din, const float *in, const DT *dout, uint32_t rows, uint32_t cols, int accumulate, uint16_t *din_bf16,
+                               float *colsum, void *stream) {
   if (!in || !dout || !din_bf16 || !colsum || !rows || !cols) return WEEDCU_EINVAL;
   if (!din && accumulate) return WEEDCU_EINVAL; // nothing to accumulate into
   if ((rows % 8u) || (din && !aligned16(din)) || !aligned16(in) || !aligned16(dout) || !aligned16(din_bf16)) return WEEDCU_ENOSUP;
@@ -593,8 +673,12 @@ int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32
   cudaStream_t st = resolve_stream(stream);
   float *part = nullptr;
   WCU_CHECK(pool_alloc((void **)&part, sizeof(float) * (size_t)nchunks * cols, st));
-  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, (accumulate ? 18.0 : (din ? 14.0 : 10.0)) * (double)rows * cols);
-  launch_k(gelu_grad_pack_kernel, dim3(nchunks, cgroups), dim3(256), 0, st, din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
+  ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, ((accumulate ? 14.0 : (din ? 10.0 : 6.0)) + sizeof(DT)) * (double)rows * cols);
+  if (!din && sizeof(DT) == 2 && (cols + kGg16Cols - 1) / kGg16Cols <= 65535u)
+    launch_k(gelu_grad_pack16_kernel, dim3(nchunks, (cols + kGg16Cols - 1) / kGg16Cols), dim3(128), 0, st, in, (const __nv_bfloat16 *)dout, rows, cols,
+             (__nv_bfloat16 *)din_bf16, part);
+  else // (fp32 dout keeps the accurate tanh with or without an fp32 output: switching the operand cache on changes no value)
+    launch_k(gelu_grad_pack_kernel<DT, false>, dim3(nchunks, cgroups), dim3(256), 0, st, din, in, dout, rows, cols, accumulate, (__nv_bfloat16 *)din_bf16, part);
   int rc = after_launch();
   if (rc == 0) {
     launch_k(colsum_finish_kernel, dim3((cols + 255u) / 256u), dim3(256), 0, st, part, nchunks, cols, colsum);
@@ -602,6 +686,15 @@ int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32
   }
   pool_free(part, st);
   return rc;
+}
+} // extern "C++"
+int weedcu_gelu_grad_pack(float *din, const float *in, const float *dout, uint32_t rows, uint32_t cols, int accumulate,
+                          uint16_t *din_bf16, float *colsum, void *stream) {
+  return gelu_grad_pack_impl<float>(din, in, dout, rows, cols, accumulate, din_bf16, colsum, stream);
+}
+int weedcu_gelu_grad_pack_bf16dy(float *din, const float *in, const uint16_t *dout_bf16, uint32_t rows, uint32_t cols, int accumulate,
+                                 uint16_t *din_bf16, float *colsum, void *stream) {
+  return gelu_grad_pack_impl<__nv_bfloat16>(din, in, (const __nv_bfloat16 *)dout_bf16, rows, cols, accumulate, din_bf16, colsum, stream);
 }
 
 int weedcu_gelu_fwd_bf16(const float *x, float *y, uint16_t *y_bf16, uint64_t n, void *stream) {

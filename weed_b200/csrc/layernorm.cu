@@ -260,9 +260,15 @@ layernorm_stats_merge_kernel(const float2 *__restrict__ stats, uint32_t rows, ui
   const uint32_t r = blockIdx.x * 128u + threadIdx.x;
   if (r >= rows) return;
   float mu = 0.0f, m2 = 0.0f, n = 0.0f;
-  for (uint32_t t = 0; t < tiles && t * tile_cols < F; ++t) { // (trailing partials beyond F are empty)
+  // all partials in flight at once (<= 16 by the producer's contract): one memory round trip, not one per partial
+  float2 pt[16];
+#pragma unroll
+  for (uint32_t t = 0; t < 16u; ++t) pt[t] = (t < tiles && t * tile_cols < F) ? stats[(uint64_t)t * rows + r] : make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (uint32_t t = 0; t < 16u; ++t) {
+    if (!(t < tiles && t * tile_cols < F)) break; // (trailing partials beyond F are empty)
     const float cnt = (float)(min(F, (t + 1u) * tile_cols) - t * tile_cols), tot = n + cnt;
-    const float2 p = stats[(uint64_t)t * rows + r];
+    const float2 p = pt[t];
     const float delta = p.x - mu;
     mu += delta * (cnt / tot);
     m2 += p.y + delta * delta * (n * cnt / tot);
@@ -585,6 +591,7 @@ int weedcu_layernorm_fwd_stats(const float *x, uint32_t rows, uint32_t F, const 
                                void *stream) {
   if (!x || !stats || !gamma || !beta || !y || !rows || !F || !tiles || !tile_cols) return WEEDCU_EINVAL;
   if ((uint64_t)tiles * tile_cols < F) return WEEDCU_EINVAL; // the tiles must cover [0, F)
+  if (tiles > 16u && (uint64_t)16u * tile_cols < F) return WEEDCU_ENOSUP; // the merge kernel holds <= 16 live partials per row
   const unsigned fgroups = (F + kLnFB - 1) / kLnFB;
   if ((rows % 4u) || !aligned16(x) || !aligned16(y) || !aligned16(stats) || (y_bf16 && !aligned16(y_bf16)) || (mean && !aligned16(mean)) ||
       (rstd && !aligned16(rstd)) || fgroups > 65535u)

@@ -330,6 +330,9 @@ template <typename T> struct GpuStorage : TypedStorage<T> {
   // by the first access that does not overwrite the whole buffer, and skipped entirely when the
   // first consumer overwrites it (matmul / copy instead of accumulate) or nothing ever touches it.
   // `version` counts potential writes; the bf16 operand shadows of GpuRealStorage key on it.
+  // the only reader of these values takes their bf16 copy (the gradient of a fused Linear + GELU output: gelu_grad): a
+  // tensor-core product that overwrites the whole storage may then write that copy alone and defer the fp32 values
+  bool accept_bf16_values = false;
   mutable bool zero_pending = false;
   mutable uint64_t version = 0;
   // the buffer is KNOWN to hold zeros while zero_version == version (the fused Adam kernel zeroes small gradients right

@@ -305,6 +305,24 @@ bool bf16_operand(const Tensor &t, tcapint s_mn, tcapint s_k, tcapint n_mn, tcap
 
 // `bias` (optional): a dense [N] vector added to every row in the GEMM epilogue; when given and the
 // tensor-core path does not apply, nothing is computed and false is returned.
+// `cs` received only the bf16 copy of the product a b: produce the fp32 values on demand with the plain product of the same
+// operand copies, as long as neither operand has changed since
+void defer_product_output(GpuRealStorage *cs, const Bf16Operand &pa, const Bf16Operand &pb, tcapint M, tcapint N, tcapint K, const Tensor &a,
+                          const Tensor &b) {
+  const StoragePtr a_s = a.storage, b_s = b.storage;
+  const uint64_t a_v = static_cast<GpuRealStorage *>(a_s.get())->version, b_v = static_cast<GpuRealStorage *>(b_s.get())->version;
+  const BufferPtr abuf = pa.buf, bbuf = pb.buf;
+  const int a_major = pa.major, b_major = pb.major;
+  const uint64_t lda = pa.ld, ldb = pb.ld;
+  cs->deferred_values = [cs, a_s, b_s, a_v, b_v, abuf, bbuf, a_major, b_major, lda, ldb, M, N, K]() {
+    if (static_cast<GpuRealStorage *>(a_s.get())->version != a_v || static_cast<GpuRealStorage *>(b_s.get())->version != b_v)
+      throw std::runtime_error("matmul: an operand was modified before the deferred fp32 product was read");
+    cs->dev->Bind();
+    throw_on_error(weedcu_gemm_bf16((const uint16_t *)abuf->ptr, a_major, lda, (const uint16_t *)bbuf->ptr, b_major, ldb, (real1 *)cs->buffer->ptr, M, M, N, K,
+                                    0, nullptr, cs->dev->stream),
+                   "matmul (deferred fp32 product)");
+  };
+}
 bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, const Tensor *bias = nullptr, const Tensor *residual = nullptr) {
   validate_all_same_device({&a, &b, &out}, "MatMulKernel::matmul");
   if ((a.shape.size() != 2U) || (b.shape.size() != 2U) || (out.shape.size() != 2U))
@@ -349,6 +367,26 @@ bool matmul_impl(const Tensor &a, const Tensor &b, Tensor &out, int accumulate, 
           cs->row_stats_cols = N;
           cs->row_stats_version = cs->version;
         }
+      } else if (!accumulate && !bias && !residual && cs->accept_bf16_values && cfg.defer_grads && cfg.epilogue_stats && !out.offset &&
+                 covers_storage(out) && out.stride[1U] == M && (M % 8U) == 0U && N >= 32U) {
+        // the whole storage is overwritten and its one reader takes bf16 (core.hpp: accept_bf16_values): write only the
+        // bf16 copy; the fp32 values are formed on demand by the plain product of the same operand copies
+        const OutputShadow os = begin_output_shadow(out, N);
+        rc = WEEDCU_ENOSUP;
+        if (os.ptr) {
+          cs->dev->Bind();
+          cs->device_ptr_overwrite();
+          weedcu_gemm_epilogue epi;
+          memset(&epi, 0, sizeof(epi));
+          rc = weedcu_gemm_bf16_ex(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, nullptr, 0U, os.ptr, M, M, N, K, &epi, dc.stream);
+          if (rc == 0) {
+            end_output_shadow(os);
+            defer_product_output(cs, pa, pb, M, N, K, a, b);
+          }
+        }
+        if (rc == WEEDCU_ENOSUP)
+          rc = weedcu_gemm_bf16(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K, accumulate, bias_ptr,
+                                dc.stream);
       } else if (residual) // [M, N] with the layout of `out`, added after the bias in the epilogue
         rc = weedcu_gemm_bf16_residual(pa.ptr, pa.major, pa.ld, pb.ptr, pb.major, pb.ld, dc.ptr + out.offset, out.stride[1U], M, N, K, bias_ptr,
                                        dev_of(*residual, "matmul").ptr + residual->offset, out.stride[1U], dc.stream);
@@ -670,11 +708,20 @@ void gelu_grad(Tensor &din, const Tensor &in, const Tensor &dout) {
         ds->colsum = ds->dev->MakeBuffer(sizeof(real1) * (size_t)cols);
         ds->colsum_n = cols;
       }
-      const Dev di = dev_of(in, "gelu_grad"), dg = dev_of(dout, "gelu_grad");
+      // dout whose fp32 values are still deferred behind a current bf16 copy (matmul_impl: accept_bf16_values): read that
+      GpuRealStorage *gs = gpu_storage(dout, "gelu_grad");
+      const uint16_t *dout_bf16 = nullptr;
+      if (gs->deferred_values)
+        for (const GpuRealStorage::Bf16Shadow &sh : gs->shadows)
+          if (sh.offset == 0U && sh.n_fast == rows && sh.n_slow == cols && sh.s_fast == 1U && sh.s_slow == rows && sh.version == gs->version)
+            dout_bf16 = (const uint16_t *)sh.buf->ptr;
+      const Dev di = dev_of(in, "gelu_grad");
       const bool defer = !accumulate && cfg.defer_grads;
       real1 *out = accumulate ? ds->device_ptr() : ds->device_ptr_overwrite();
-      const int rc = weedcu_gelu_grad_pack(defer ? nullptr : out, di.ptr, dg.ptr, rows, cols, accumulate, (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr,
-                                           ds->dev->stream);
+      const int rc = dout_bf16 ? weedcu_gelu_grad_pack_bf16dy(defer ? nullptr : out, di.ptr, dout_bf16, rows, cols, accumulate, (uint16_t *)hit->buf->ptr,
+                                                              (real1 *)ds->colsum->ptr, ds->dev->stream)
+                               : weedcu_gelu_grad_pack(defer ? nullptr : out, di.ptr, dev_of(dout, "gelu_grad").ptr, rows, cols, accumulate,
+                                                       (uint16_t *)hit->buf->ptr, (real1 *)ds->colsum->ptr, ds->dev->stream);
       if (rc == 0) {
         hit->version = ds->version;
         ds->colsum_version = ds->version;

@@ -1131,7 +1131,11 @@ TensorPtr Tensor::linear_gelu(TensorPtr a, TensorPtr w, TensorPtr bias) {
   if (!Weed::matmul_bias_gelu(*a2, *w, *bias, *h, *y)) return nullptr;
   h = finish_linear(a, w, bias, h, rg);
   if (h->shape.size() != 2U) y->BaseTensor::reshape(std::vector<symint>(h->shape.begin(), h->shape.end()));
-  if (rg) make_gelu_node(h, y);
+  if (rg) {
+    make_gelu_node(h, y);
+    // y's gradient is read by gelu_grad alone, which takes a bf16 copy: the ff2 Linear's dA product may write just that
+    if (y->grad && y->grad->storage->device == DeviceTag::GPU) static_cast<GpuRealStorage *>(y->grad->storage.get())->accept_bf16_values = true;
+  }
   return y;
 }
 
