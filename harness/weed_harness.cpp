@@ -665,11 +665,36 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     Tensor::backward(loss);
     const auto t3 = now();
 #ifdef WEED_B200
-    if (dp && overlap) g_buckets->finish(params);
+    // WH_DP_SPLIT_ADAM=1: the parameters outside the last bucket are updated while that bucket (the embedding's gradient,
+    // 154 MB at the GPT-2 shape) is still being exchanged. Off by default: measured on 8 x B200 it changes nothing
+    // (10.56 against 10.54 ms/step) — the update and the exchange compete for the same HBM
+    static const bool split = getenv("WH_DP_SPLIT_ADAM") && atoi(getenv("WH_DP_SPLIT_ADAM")) != 0;
+    bool updated = false;
+    if (dp && overlap && !chained && split) {
+      g_buckets->finish_async(params);
+      std::unordered_set<Tensor *> in_tail(g_buckets->tail.begin(), g_buckets->tail.end());
+      std::vector<ParameterPtr> head, tail;
+      for (const ParameterPtr &p : params) (in_tail.count(p.get()) ? tail : head).push_back(p);
+      Adam &o = *g_adams.at(opt);
+      real1 bc1, bc2;
+      adam_begin_step(o, bc1, bc2);
+      std::vector<ParameterPtr> slow;
+      AdamBatch hb, tb;
+      adam_collect(o, head, hb, slow);
+      adam_collect(o, tail, tb, slow);
+      g_buckets->wait_head();
+      adam_launch(o, hb, bc1, bc2, nullptr);
+      g_buckets->wait_all();
+      adam_launch(o, tb, bc1, bc2, nullptr);
+      for (const ParameterPtr &p : slow) adam_slow(o, p, bc1, bc2);
+      updated = true;
+    } else if (dp && overlap) g_buckets->finish(params);
     else if (dp) allreduce_gradients(params, g_comm);
+#else
+    const bool updated = false;
 #endif
     const auto t4 = now();
-    if (!chained) adam_step(*g_adams.at(opt), params);
+    if (!chained && !updated) adam_step(*g_adams.at(opt), params);
     const auto t5 = now();
     zero_grad(params);
     m->reset_cache();

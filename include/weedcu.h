@@ -525,6 +525,9 @@ int weedcu_nccl_destroy(void *comm);
 int weedcu_nccl_group_start(void);
 int weedcu_nccl_group_end(void);
 int weedcu_nccl_allreduce_sum(void *comm, float *buf, uint64_t n, void *stream);
+/* dst[t][0 .. n[t]) = src[t][0 .. n[t]) for `count` dense fp32 runs in one or a few launches (host arrays of device
+ * pointers). Used to gather the small gradients of a bucket into one all-reduce message and to scatter the sum back. */
+int weedcu_multi_copy(uint32_t count, const float *const *src, float *const *dst, const uint64_t *n, void *stream);
 int weedcu_nccl_broadcast(void *comm, float *buf, uint64_t n, int root, void *stream);
 
 #ifdef __cplusplus

@@ -492,6 +492,11 @@ int weedcu_nccl_group_end(void) { return 0; }
 typedef int (*mock_allreduce_hook)(float *buf, uint64_t n);
 static mock_allreduce_hook g_allreduce_hook = nullptr, g_bcast_hook = nullptr;
 void weedcu_mock_set_collective_hooks(mock_allreduce_hook allreduce, mock_allreduce_hook bcast) { g_allreduce_hook = allreduce; g_bcast_hook = bcast; }
+int weedcu_multi_copy(uint32_t count, const float *const *src, float *const *dst, const uint64_t *n, void *) {
+  ++g_launches;
+  for (uint32_t t = 0; t < count; ++t) memmove(dst[t], src[t], sizeof(float) * (size_t)n[t]);
+  return 0;
+}
 int weedcu_nccl_allreduce_sum(void *, float *buf, uint64_t n, void *) { ++g_launches; return g_allreduce_hook ? g_allreduce_hook(buf, n) : 0; }
 int weedcu_nccl_broadcast(void *, float *buf, uint64_t n, int, void *) { ++g_launches; return g_bcast_hook ? g_bcast_hook(buf, n) : 0; }
 }

@@ -44,9 +44,10 @@ def _single_process_reference(world):
     return np.array(losses), params
 
 
-@pytest.mark.parametrize("overlap,bucket_bytes,chain", [(1, 0, 1), (1, 2048, 1), (1, 2048, 0), (0, 0, 0)],
-                         ids=["overlap_default_bucket_adam_chained", "overlap_2KB_buckets_adam_chained", "overlap_2KB_buckets", "after_backward"])
-def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap, bucket_bytes, chain):
+@pytest.mark.parametrize("overlap,bucket_bytes,chain,split", [(1, 0, 1, 0), (1, 2048, 1, 0), (1, 2048, 0, 0), (1, 2048, 0, 1), (0, 0, 0, 0)],
+                         ids=["overlap_default_bucket_adam_chained", "overlap_2KB_buckets_adam_chained", "overlap_2KB_buckets",
+                              "overlap_2KB_buckets_adam_split_around_last_bucket", "after_backward"])
+def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap, bucket_bytes, chain, split):
     """overlap=1: GradientBuckets hands gradients to the all-reduce as Tensor::backward reports them
     final (tiny buckets force several flushes in the middle of the walk); overlap=0: one grouped
     all-reduce after backward. chain=1: the fused Adam update of each bucket's parameters is issued right behind that
@@ -57,7 +58,7 @@ def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap, bucket
     procs, outs = [], []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   GLOO_SOCKET_IFNAME="lo", WH_DP_OVERLAP=str(overlap), WH_DP_CHAIN_ADAM=str(chain))
+                   GLOO_SOCKET_IFNAME="lo", WH_DP_OVERLAP=str(overlap), WH_DP_CHAIN_ADAM=str(chain), WH_DP_SPLIT_ADAM=str(split))
         if bucket_bytes:
             env["WH_DP_BUCKET_BYTES"] = str(bucket_bytes)
         out = str(tmp_path / f"rank{r}.json")

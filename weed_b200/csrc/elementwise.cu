@@ -401,6 +401,23 @@ gelu_grad_pack16_kernel(const float *__restrict__ in, const __nv_bfloat16 *__res
   if (threadIdx.x < kGg16Cols && j0 + threadIdx.x < cols)
     part[(uint64_t)blockIdx.x * cols + j0 + threadIdx.x] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
+// up to 64 (source, destination, length) triples per launch: the small gradients of a data-parallel bucket are gathered into
+// one staging buffer, all-reduced as one message and scattered back (autograd.cpp: GradientBuckets::flush)
+struct MultiCopyArgs {
+  const float *src[64];
+  float *dst[64];
+  uint64_t n[64];
+  uint32_t count;
+};
+__global__ void __launch_bounds__(256)
+multi_copy_kernel(const __grid_constant__ MultiCopyArgs a) {
+  pdl_grid_sync();
+  const uint32_t t = blockIdx.x;
+  const float *__restrict__ s = a.src[t];
+  float *__restrict__ d = a.dst[t];
+  const uint64_t n = a.n[t];
+  for (uint64_t i = (uint64_t)blockIdx.y * 256u + threadIdx.x; i < n; i += (uint64_t)gridDim.y * 256u) d[i] = s[i];
+}
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float *__restrict__ part, uint32_t nchunks, uint32_t cols, float *__restrict__ colsum) {
   pdl_grid_sync();
@@ -533,6 +550,32 @@ using namespace weedcu;
 
 extern "C" {
 
+// dst[t][0 .. n[t]) = src[t][0 .. n[t]) for up to 64 tensors per launch (pointers travel as kernel parameters)
+int weedcu_multi_copy(uint32_t count, const float *const *src, float *const *dst, const uint64_t *n, void *stream) {
+  if (!count) return 0;
+  if (!src || !dst || !n) return WEEDCU_EINVAL;
+  cudaStream_t st = resolve_stream(stream);
+  for (uint32_t t0 = 0; t0 < count; t0 += 64u) {
+    MultiCopyArgs a;
+    a.count = min(64u, count - t0);
+    uint64_t longest = 0;
+    for (uint32_t t = 0; t < a.count; ++t) {
+      if (!src[t0 + t] || !dst[t0 + t]) return WEEDCU_EINVAL;
+      a.src[t] = src[t0 + t];
+      a.dst[t] = dst[t0 + t];
+      a.n[t] = n[t0 + t];
+      longest = longest > a.n[t] ? longest : a.n[t];
+    }
+    if (!longest) continue;
+    const uint64_t per_block = 256u * 16u;
+    const unsigned by = (unsigned)((longest + per_block - 1) / per_block < 1024u ? (longest + per_block - 1) / per_block : 1024u);
+    ProfScope prof(WEEDCU_PROF_ELEMENTWISE, st, 0.0);
+    launch_k(multi_copy_kernel, dim3(a.count, by), dim3(256), 0, st, a);
+    const int rc = after_launch();
+    if (rc) return rc;
+  }
+  return 0;
+}
 int weedcu_fill_real(float *p, uint64_t n, float value, void *stream) {
   if (!p) return WEEDCU_EINVAL;
   if (!n) return 0;

@@ -818,6 +818,16 @@ static bool make_c16_map(CUtensorMap *map, uint16_t *c, uint64_t M, uint64_t N, 
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// SMs the persistent product kernels may occupy (WEEDCU_GEMM_SMS, default all): a data-parallel run can leave a few SMs to
+// the collective's kernels, whose CTAs do not fit next to a 224 KB product CTA
+static unsigned gemm_sm_limit() {
+  static const unsigned lim = [] {
+    const char *e = getenv("WEEDCU_GEMM_SMS");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 2 && v <= kNumSMs) ? (unsigned)(v & ~1) : (unsigned)kNumSMs;
+  }();
+  return lim;
+}
 template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS>
 static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
                       int b_major, cudaStream_t st) {
@@ -826,7 +836,7 @@ static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const Tens
   const uint32_t smem = L::TOTAL + 1024; // slack for the 1024-B round-up
   const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const uint32_t num_units = num_tiles * p.splits;
-  const unsigned grid = num_units < (uint32_t)kNumSMs ? num_units : (unsigned)kNumSMs;
+  const unsigned grid = num_units < gemm_sm_limit() ? num_units : gemm_sm_limit();
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
     auto k = gemm_bf16_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                           \
@@ -848,7 +858,7 @@ static int launch_pair_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const
   static_assert(L::TOTAL + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
   const uint32_t smem = L::TOTAL + 1024;
   const uint32_t num_units = p.tiles_m * p.tiles_n * p.batch * p.splits;
-  const unsigned pairs = num_units < (uint32_t)(kNumSMs / 2) ? num_units : (unsigned)(kNumSMs / 2);
+  const unsigned pairs = num_units < gemm_sm_limit() / 2 ? num_units : gemm_sm_limit() / 2;
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
     auto k = gemm_bf16_pair_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                      \

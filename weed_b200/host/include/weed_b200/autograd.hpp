@@ -77,6 +77,18 @@ struct GradientBuckets {
   real1 bc1 = ONE_R1, bc2 = ONE_R1;
   std::unordered_map<Tensor *, ParameterPtr> owners;
   std::vector<ParameterPtr> slow;
+  // gradients below small_elems travel together: gathered into `staging`, all-reduced as ONE message, scattered back (a
+  // GPT-2-small step has ~60 bias / LayerNorm gradients of 768 .. 3072 floats: as separate collectives their per-message
+  // latency, not their bytes, was most of the exchange at 8 GPUs)
+  size_t small_elems = 65536U;
+  BufferPtr staging;
+  size_t staging_elems = 0U;
+  // split update (finish_async): `tail` = the parameters of the last bucket; everything before it is complete at ev_head
+  void *ev_head = nullptr;
+  std::vector<Tensor *> tail;
+  void *tail_compute = nullptr;
+  Adam *chained_opt = nullptr;
+  std::vector<ParameterPtr> chained_done;
   explicit GradientBuckets(void *c, size_t bytes = 32U << 20);
   ~GradientBuckets();
   void begin();
@@ -84,6 +96,12 @@ struct GradientBuckets {
   void add(Tensor *leaf);
   void flush();
   void finish(const std::vector<ParameterPtr> &params);
+  // finish() without the final wait: the last bucket's all-reduce is in flight when this returns. wait_head() makes the
+  // compute stream wait for every bucket before the last one, wait_all() for the last one too — a caller updates the
+  // parameters outside `tail` between the two, behind which the last exchange hides.
+  void finish_async(const std::vector<ParameterPtr> &params);
+  void wait_head();
+  void wait_all();
 };
 void broadcast_parameters(const std::vector<ParameterPtr> &params, void *comm, int root);
 } // namespace Weed

@@ -235,11 +235,13 @@ GradientBuckets::GradientBuckets(void *c, size_t bytes) : comm(c), bucket_bytes(
   throw_on_error(weedcu_stream_create_priority(&comm_stream, 1), "GradientBuckets");
   throw_on_error(weedcu_event_create(&ev_ready), "GradientBuckets");
   throw_on_error(weedcu_event_create(&ev_done), "GradientBuckets");
+  throw_on_error(weedcu_event_create(&ev_head), "GradientBuckets");
 }
 GradientBuckets::~GradientBuckets() {
   backend_config().on_leaf_grad_final = nullptr;
   if (ev_ready) weedcu_event_destroy(ev_ready);
   if (ev_done) weedcu_event_destroy(ev_done);
+  if (ev_head) weedcu_event_destroy(ev_head);
   if (comm_stream) weedcu_stream_destroy(comm_stream);
 }
 void GradientBuckets::begin() {
@@ -284,9 +286,38 @@ void GradientBuckets::flush() {
   }
   throw_on_error(weedcu_event_record(ev_ready, compute), "GradientBuckets::flush");
   throw_on_error(weedcu_stream_wait_event(comm_stream, ev_ready), "GradientBuckets::flush");
+  // small gradients ride in one message
+  std::vector<const real1 *> s_src;
+  std::vector<real1 *> s_dst;
+  std::vector<uint64_t> s_n;
+  size_t s_total = 0U;
+  if (small_elems)
+    for (const auto &b : bufs)
+      if (b.second < small_elems) s_total += (b.second + 3U) & ~(size_t)3U;
+  if (s_total && s_total > staging_elems) {
+    staging = static_cast<GpuRealStorage *>(pending.front()->grad->storage.get())->dev->MakeBuffer(sizeof(real1) * s_total);
+    staging_elems = s_total;
+  }
+  const bool coalesce = s_total != 0U;
+  if (coalesce) {
+    size_t at = 0U;
+    for (const auto &b : bufs)
+      if (b.second < small_elems) {
+        s_src.push_back(b.first);
+        s_dst.push_back((real1 *)staging->ptr + at);
+        s_n.push_back(b.second);
+        at += (b.second + 3U) & ~(size_t)3U;
+      }
+    throw_on_error(weedcu_multi_copy((uint32_t)s_n.size(), s_src.data(), s_dst.data(), s_n.data(), comm_stream), "GradientBuckets::flush (gather)");
+  }
   throw_on_error(weedcu_nccl_group_start(), "GradientBuckets::flush");
-  for (const auto &b : bufs) throw_on_error(weedcu_nccl_allreduce_sum(comm, b.first, b.second, comm_stream), "GradientBuckets::flush");
+  for (const auto &b : bufs)
+    if (!coalesce || b.second >= small_elems) throw_on_error(weedcu_nccl_allreduce_sum(comm, b.first, b.second, comm_stream), "GradientBuckets::flush");
+  if (coalesce) throw_on_error(weedcu_nccl_allreduce_sum(comm, (real1 *)staging->ptr, s_total, comm_stream), "GradientBuckets::flush");
   throw_on_error(weedcu_nccl_group_end(), "GradientBuckets::flush");
+  if (coalesce) // back to where the optimiser reads them (the padding between runs is summed too and ignored)
+    throw_on_error(weedcu_multi_copy((uint32_t)s_n.size(), (const real1 *const *)s_dst.data(), const_cast<real1 *const *>((real1 **)s_src.data()), s_n.data(), comm_stream),
+                   "GradientBuckets::flush (scatter)");
   // bucket reduced -> its parameters are updated right behind it on the communication stream, while the compute
   // stream carries on with the rest of backward (SURVEY 8e "fusion opportunity"): a parameter is only read by the
   // nodes that list it as a parent, and all of those were issued before ev_ready
@@ -296,6 +327,20 @@ void GradientBuckets::flush() {
   pending_bytes = 0U;
 }
 void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
+  finish_async(params);
+  wait_all();
+}
+void GradientBuckets::wait_head() {
+  if (tail_compute) throw_on_error(weedcu_stream_wait_event(tail_compute, ev_head), "GradientBuckets::wait_head");
+}
+void GradientBuckets::wait_all() {
+  if (tail_compute) throw_on_error(weedcu_stream_wait_event(tail_compute, ev_done), "GradientBuckets::wait_all");
+  if (chained_done.size()) {
+    for (const ParameterPtr &p : chained_done) adam_slow(*chained_opt, p, bc1, bc2); // parameters the fused kernel cannot take: reference composition
+    chained_done.clear();
+  }
+}
+void GradientBuckets::finish_async(const std::vector<ParameterPtr> &params) {
   backend_config().on_leaf_grad_final = nullptr;
   void *compute = nullptr;
   std::vector<ParameterPtr> untouched;
@@ -314,6 +359,9 @@ void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
     pending.push_back(p.get());
     pending_bytes += (size_t)g.storage->size * sizeof(real1);
   }
+  // everything enqueued so far is complete at ev_head; what is still pending is the tail
+  tail.assign(pending.begin(), pending.end());
+  throw_on_error(weedcu_event_record(ev_head, comm_stream), "GradientBuckets::finish");
   flush();
   if (chained && !untouched.empty()) {
     // zero gradients still decay the moments (adam.hpp:84-104): one more launch behind the last bucket
@@ -325,12 +373,11 @@ void GradientBuckets::finish(const std::vector<ParameterPtr> &params) {
     }
     adam_launch(*chained, batch, bc1, bc2, comm_stream);
   }
-  if (compute) {
-    throw_on_error(weedcu_event_record(ev_done, comm_stream), "GradientBuckets::finish");
-    throw_on_error(weedcu_stream_wait_event(compute, ev_done), "GradientBuckets::finish");
-  }
+  tail_compute = compute;
+  if (compute) throw_on_error(weedcu_event_record(ev_done, comm_stream), "GradientBuckets::finish");
   if (chained) {
-    for (const ParameterPtr &p : slow) adam_slow(*chained, p, bc1, bc2); // parameters the fused kernel cannot take: reference composition
+    chained_opt = chained;
+    chained_done = slow; // updated by wait_all(), once the compute stream has been told to wait for the exchange
     chained = nullptr;
     owners.clear();
     slow.clear();
