@@ -362,6 +362,9 @@ def main_ours(args):
     P.config("fused", 1)
     P.config("ref_index_quirks", 0)
     P.config("matmul_precision", precision)
+    for kv in filter(None, os.environ.get("WH_CONFIG", "").split(",")):  # backend switches for A/B runs: WH_CONFIG="bf16_act_grad=0,..."
+        k, v = kv.split("=")
+        P.config(k.strip(), float(v))
     if world > 1:
         import torch as _t
         nccl_path = os.path.join(os.path.dirname(_t.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2")

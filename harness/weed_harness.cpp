@@ -140,6 +140,7 @@ int wh_config(const char *name, double value) {
     else if (n == "matmul_precision") c.matmul_precision = (int)value;
     else if (n == "grad_scale") c.grad_scale = (real1)value;
     else if (n == "layernorm_exact_grad") c.layernorm_exact_grad = value != 0;
+    else if (n == "bf16_act_grad") c.bf16_act_grad = value != 0;
     else if (n == "operand_cache") c.operand_cache = value != 0;
     else if (n == "lazy_zero") c.lazy_zero = value != 0;
     else if (n == "defer_grads") c.defer_grads = value != 0;

@@ -117,6 +117,8 @@ struct BackendConfig {
   // gradient. bench.py --check-dp uses `true` to test the gradient exchange: with the reference chain a sharded batch and
   // a whole batch differ by that unscaled term, whatever exchanges the gradients.
   bool layernorm_exact_grad = false;
+  // the ff2 Linear's dA is written as its bf16 copy alone when GELU backward is its only reader (tensor.cpp: linear_gelu)
+  bool bf16_act_grad = true;
   // Tensor::backward calls this for every leaf tensor (no grad_node, requires_grad: the Parameters)
   // right after the LAST node that lists it as a parent has run, i.e. when its gradient is final;
   // data-parallel training hangs the bucketed all-reduce on it (autograd.hpp: GradientBuckets)

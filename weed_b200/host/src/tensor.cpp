@@ -1134,7 +1134,7 @@ TensorPtr Tensor::linear_gelu(TensorPtr a, TensorPtr w, TensorPtr bias) {
   if (rg) {
     make_gelu_node(h, y);
     // y's gradient is read by gelu_grad alone, which takes a bf16 copy: the ff2 Linear's dA product may write just that
-    if (y->grad && y->grad->storage->device == DeviceTag::GPU) static_cast<GpuRealStorage *>(y->grad->storage.get())->accept_bf16_values = true;
+    if (backend_config().bf16_act_grad && y->grad && y->grad->storage->device == DeviceTag::GPU) static_cast<GpuRealStorage *>(y->grad->storage.get())->accept_bf16_values = true;
   }
   return y;
 }
