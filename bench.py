@@ -230,8 +230,10 @@ def parity_legs(P, cfg, steps=5):
 
 
 # stated bf16 bound on the loss of the benchmarked configuration after 5 seeded steps (north_star: "a stated looser bound
-# for bf16"); measured on B200 in round 2: see profiles/README.md
-BF16_LOSS_BOUND = 2e-3
+# for bf16"). Measured on B200 in round 2: 3.0e-4 with bf16 logits feeding the loss, 9e-6 with fp32 logits
+# (profiles/r02_parity_ab.txt); the fp32 trajectory itself moves by ~1e-5 between builds at step 4-5 (Adam amplifies
+# rounding-level differences ~3x per step at this shape), so the bound keeps a factor 3 over the measured figure.
+BF16_LOSS_BOUND = 1e-3
 
 
 # ----------------------------------------------------------------------------------- data-parallel equality

@@ -409,7 +409,8 @@ def test_greedy_decode_batched_fused_equals_unfused(P):
 
 def test_gpt_shape_train_step_bf16_vs_fp32(P):
     """Token model with the fused cross-entropy: bf16 tensor-core GEMMs vs the fp32 path on the same
-    weights — loss after 3 steps within the stated bf16 bound (2e-2 relative)."""
+    weights — loss after 3 steps within the stated bf16 bound for this toy shape (1e-4 relative, measured 5e-6; the full shape is bounded
+    in bench.py's parity leg)."""
     B, T, V, d, L = 2, 64, 512, 64, 2
 
     def run(precision):
@@ -431,7 +432,8 @@ def test_gpt_shape_train_step_bf16_vs_fp32(P):
     f32, bf16 = run(0), run(1)
     set_mode(P, 1)
     assert np.all(np.isfinite(f32)) and abs(f32[0] - np.log(V)) < 1.0
-    assert np.max(np.abs(f32 - bf16) / np.abs(f32)) <= 2e-2, (f32, bf16)
+    print("bf16 vs fp32 toy loss rel diff:", np.max(np.abs(f32 - bf16) / np.abs(f32)))
+    assert np.max(np.abs(f32 - bf16) / np.abs(f32)) <= 1e-4, (f32, bf16)
 
 
 def test_operand_cache_and_lazy_zero_change_nothing(P):

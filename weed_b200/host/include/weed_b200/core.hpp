@@ -697,6 +697,8 @@ struct Node {
     for (auto &t : parents) {
       t->make_gradient();
       ++t->consumers;
+      // a view of a graph tensor shares that tensor's gradient: a contribution through the view is one for the owner too
+      if (t->view_owner) ++t->view_owner->consumers;
     }
   }
 };

@@ -862,6 +862,7 @@ TensorPtr Tensor::add(TensorPtr a, TensorPtr b) { // tensor.cpp:1084-1103
 static bool adopt_incoming_gradient(const TensorPtr &parent, const TensorPtr &out_grad) {
   if (!backend_config().fused || !backend_config().lazy_zero) return false;
   if (!parent->grad_node || parent->consumers != 1U || !parent->grad || parent.get() == out_grad.get()) return false;
+  if (parent->view_owner) return false; // a view shares its owner's gradient tensor: replacing the view's pointer alone would orphan it
   const TensorPtr &g = parent->grad;
   if (g->storage->device != DeviceTag::GPU || out_grad->storage->device != DeviceTag::GPU || g->storage->dtype != DType::REAL) return false;
   if (g->shape != out_grad->shape || g->stride != out_grad->stride || g->shape != parent->shape) return false;
