@@ -167,12 +167,17 @@ softmax_rows_partial_kernel(const float *__restrict__ a, uint32_t inner, uint32_
 #pragma unroll
       for (int u = 1; u < kSmU; ++u) m8 = fmaxf(m8, v[u]);
       if (m8 > mx) { // rescale the running sum once per batch
-        s *= expf(mx - m8);
+        s *= __expf(mx - m8);
         mx = m8;
       }
-      if (mx > -INFINITY) {
+      if (mx > -INFINITY) { // (__expf = ex2.approx of the scaled argument, 2 ulp: the pass was issue-bound with expf's ~15 instructions)
+        float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-        for (int u = 0; u < kSmU; ++u) s += expf(v[u] - mx);
+        for (int u = 0; u < kSmU; u += 2) {
+          s0 += __expf(v[u] - mx);
+          s1 += __expf(v[u + 1] - mx);
+        }
+        s += s0 + s1;
       }
     }
   red_m[ty][tx] = mx;
@@ -209,7 +214,7 @@ softmax_rows_finish_kernel(const float *__restrict__ part_m, const float *__rest
     if (my > -INFINITY) S += part_s[(uint64_t)k * n_rows + row] * expf(my - M);
   }
   row_m[row] = M;
-  row_s[row] = LOG ? logf(S) : S;
+  row_s[row] = LOG ? logf(S) : 1.0f / S; // softmax_apply multiplies
 }
 // out = exp(x - M) / S   or   (x - M) - log S ; VEC adjacent rows x kSmCols columns per thread
 template <bool LOG, int VEC>
@@ -245,7 +250,7 @@ softmax_apply_kernel(const float *__restrict__ a, float *__restrict__ out, uint3
     if (j < j_end) {
       float o[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o[k] = LOG ? ((xv[i][k] - M[k]) - S[k]) : (expf(xv[i][k] - M[k]) / S[k]);
+      for (int k = 0; k < VEC; ++k) o[k] = LOG ? ((xv[i][k] - M[k]) - S[k]) : (__expf(xv[i][k] - M[k]) * S[k]);
       float *dst = out + slab + (uint64_t)j * inner + r;
       if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(o);
       else *dst = o[0];
