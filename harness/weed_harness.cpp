@@ -637,11 +637,40 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     };
     const auto t0 = now();
     ModulePtr m = M(model);
+#ifdef WEED_B200
+    // WH_DP_EVENTS=1: device timeline of the step's phases on the compute stream (diagnostic; printed two steps late so that
+    // reading the events never blocks the step being issued)
+    static const bool ev_on = getenv("WH_DP_EVENTS") && atoi(getenv("WH_DP_EVENTS")) != 0;
+    static void *evs[3][5] = {{nullptr}};
+    static uint64_t ev_step = 0;
+    void *cstream = nullptr;
+    if (ev_on) {
+      cstream = m->parameters().front()->stream();
+      if (!evs[0][0])
+        for (auto &row : evs)
+          for (void *&e : row) throw_on_error(weedcu_event_create(&e), "events");
+      if (ev_step >= 2) {
+        void **old = evs[(ev_step - 2) % 3];
+        float a = 0, b = 0, c = 0, d = 0;
+        weedcu_event_sync(old[4]);
+        weedcu_event_elapsed_ms(old[0], old[1], &a);
+        weedcu_event_elapsed_ms(old[1], old[2], &b);
+        weedcu_event_elapsed_ms(old[2], old[3], &c);
+        weedcu_event_elapsed_ms(old[3], old[4], &d);
+        static const int ev_rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+        if (ev_rank == 0) fprintf(stderr, "[wh events] forward+loss %.3f ms, backward %.3f, exchange tail %.3f, adam+zero %.3f\n", a, b, c, d);
+      }
+      throw_on_error(weedcu_event_record(evs[ev_step % 3][0], cstream), "events");
+    }
+#endif
     TensorPtr logits = m->forward(g_symbols.at(tokens));
     const auto t1 = now();
     TensorPtr loss = cross_entropy_loss(logits, g_symbols.at(targets));
     const auto t2 = now();
     const std::vector<ParameterPtr> params = m->parameters();
+#ifdef WEED_B200
+    if (ev_on) throw_on_error(weedcu_event_record(evs[ev_step % 3][1], cstream), "events");
+#endif
     bool chained = false;
 #ifdef WEED_B200
     // data parallel: bucketed gradient all-reduce on a communication stream, overlapped with the
@@ -666,10 +695,11 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     Tensor::backward(loss);
     const auto t3 = now();
 #ifdef WEED_B200
-    // WH_DP_SPLIT_ADAM=1: the parameters outside the last bucket are updated while that bucket (the embedding's gradient,
-    // 154 MB at the GPT-2 shape) is still being exchanged. Off by default: measured on 8 x B200 it changes nothing
-    // (10.56 against 10.54 ms/step) — the update and the exchange compete for the same HBM
-    static const bool split = getenv("WH_DP_SPLIT_ADAM") && atoi(getenv("WH_DP_SPLIT_ADAM")) != 0;
+    if (ev_on) throw_on_error(weedcu_event_record(evs[ev_step % 3][2], cstream), "events");
+    // The parameters outside the last flushed bucket (the embedding's gradient, 154 MB at the GPT-2 shape) are updated while
+    // that bucket is still being exchanged: 10.60 -> 10.38 ms/step on 8 x B200, 9.86 -> 9.77 on 2 (WH_DP_SPLIT_ADAM=0: one
+    // update after the whole exchange)
+    static const bool split = !(getenv("WH_DP_SPLIT_ADAM") && atoi(getenv("WH_DP_SPLIT_ADAM")) == 0);
     bool updated = false;
     if (dp && overlap && !chained && split) {
       g_buckets->finish_async(params);
@@ -684,9 +714,27 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
       adam_collect(o, head, hb, slow);
       adam_collect(o, tail, tb, slow);
       g_buckets->wait_head();
+      static void *sev[4] = {nullptr, nullptr, nullptr, nullptr};
+      static uint64_t scount = 0;
+      if (ev_on) {
+        if (!sev[0])
+          for (void *&e : sev) throw_on_error(weedcu_event_create(&e), "events");
+        else if (scount % 4 == 3) { // previous step's: head update, and the last bucket's exchange as the communication stream saw it
+          float a = 0, b = 0, c = 0;
+          weedcu_event_sync(sev[2]);
+          weedcu_event_elapsed_ms(sev[0], sev[1], &a);
+          weedcu_event_elapsed_ms(g_buckets->ev_head, g_buckets->ev_done, &b);
+          weedcu_event_elapsed_ms(sev[0], sev[2], &c);
+          fprintf(stderr, "[wh split] adam(head) %.3f ms, last bucket on the comm stream %.3f ms, adam(head) start -> adam(tail) end %.3f ms\n", a, b, c);
+        }
+        ++scount;
+        throw_on_error(weedcu_event_record(sev[0], cstream), "events");
+      }
       adam_launch(o, hb, bc1, bc2, nullptr);
+      if (ev_on) throw_on_error(weedcu_event_record(sev[1], cstream), "events");
       g_buckets->wait_all();
       adam_launch(o, tb, bc1, bc2, nullptr);
+      if (ev_on) throw_on_error(weedcu_event_record(sev[2], cstream), "events");
       for (const ParameterPtr &p : slow) adam_slow(o, p, bc1, bc2);
       updated = true;
     } else if (dp && overlap) g_buckets->finish(params);
@@ -695,10 +743,19 @@ int64_t wh_train_step_tokens(int64_t model, int64_t opt, int64_t tokens, int64_t
     const bool updated = false;
 #endif
     const auto t4 = now();
+#ifdef WEED_B200
+    if (ev_on) throw_on_error(weedcu_event_record(evs[ev_step % 3][3], cstream), "events");
+#endif
     if (!chained && !updated) adam_step(*g_adams.at(opt), params);
     const auto t5 = now();
     zero_grad(params);
     m->reset_cache();
+#ifdef WEED_B200
+    if (ev_on) {
+      throw_on_error(weedcu_event_record(evs[ev_step % 3][4], cstream), "events");
+      ++ev_step;
+    }
+#endif
     const auto t6 = now();
     if (timing)
       fprintf(stderr, "[wh] forward %.0f us, loss %.0f, backward %.0f, allreduce %.0f, adam %.0f, zero_grad %.0f\n", us(t0, t1), us(t1, t2),

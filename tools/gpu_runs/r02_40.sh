@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+for cfg in "WH_DP_SPLIT_ADAM=1" "WH_DP_SPLIT_ADAM=0"; do
+echo "N=2 $cfg"
+env $cfg WH_DP_EVENTS=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29801 bench.py --gpus 2 --steps 12 --warmup 3 --no-cpu-baseline --no-parity --no-configs --no-clocks 2> gpurun_out/r02_40.err > gpurun_out/r02_40.json
+grep "wh split\|wh events" gpurun_out/r02_40.err | tail -3
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02_40.json').read().strip().splitlines()[-1]); print(round(d['ms_per_step'],3), round(d['value'],1))
+PY
+done

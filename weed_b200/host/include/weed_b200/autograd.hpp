@@ -83,7 +83,7 @@ struct GradientBuckets {
   size_t small_elems = 65536U;
   BufferPtr staging;
   size_t staging_elems = 0U;
-  // split update (finish_async): `tail` = the parameters of the last bucket; everything before it is complete at ev_head
+  // split update (finish_async): `tail` = the parameters of the last bucket that was flushed; everything before it is complete at ev_head
   void *ev_head = nullptr;
   std::vector<Tensor *> tail;
   void *tail_compute = nullptr;

@@ -248,6 +248,7 @@ void GradientBuckets::begin() {
   pending.clear();
   pending_bytes = 0U;
   reduced.clear();
+  tail.clear();
   backend_config().on_leaf_grad_final = [this](Tensor *leaf) { add(leaf); };
 }
 void GradientBuckets::begin(Adam &opt, const std::vector<ParameterPtr> &params) {
@@ -284,6 +285,10 @@ void GradientBuckets::flush() {
     for (Tensor *leaf : pending) ps.push_back(owners.at(leaf));
     adam_collect(*chained, ps, batch, slow);
   }
+  // (everything enqueued on the communication stream so far is complete at ev_head; this bucket becomes the tail of a split
+  // update unless another one follows)
+  tail.assign(pending.begin(), pending.end());
+  throw_on_error(weedcu_event_record(ev_head, comm_stream), "GradientBuckets::flush");
   throw_on_error(weedcu_event_record(ev_ready, compute), "GradientBuckets::flush");
   throw_on_error(weedcu_stream_wait_event(comm_stream, ev_ready), "GradientBuckets::flush");
   // small gradients ride in one message
@@ -359,10 +364,7 @@ void GradientBuckets::finish_async(const std::vector<ParameterPtr> &params) {
     pending.push_back(p.get());
     pending_bytes += (size_t)g.storage->size * sizeof(real1);
   }
-  // everything enqueued so far is complete at ev_head; what is still pending is the tail
-  tail.assign(pending.begin(), pending.end());
-  throw_on_error(weedcu_event_record(ev_head, comm_stream), "GradientBuckets::finish");
-  flush();
+  flush(); // (the last bucket flushed — here or, when nothing is pending, during backward — is the tail: see flush())
   if (chained && !untouched.empty()) {
     // zero gradients still decay the moments (adam.hpp:84-104): one more launch behind the last bucket
     AdamBatch batch;
