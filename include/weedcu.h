@@ -484,6 +484,11 @@ int weedcu_gemm_bf16_grouped_bf16out(const uint16_t *a, int a_major, uint64_t ld
  * pair * 1000000 + BLOCK_N * 1000 + splits = one forced configuration (tuning sweeps). Results of the
  * families differ only by fp32 summation order across split-K slices. */
 int weedcu_gemm_set_mode(int mode);
+/* Dynamic tile scheduling in the CTA-pair GEMM kernel (env WEEDCU_GEMM_DYNAMIC): work units are drawn from a per-launch
+ * counter instead of being strided over the clusters, so that a cluster whose SMs are busy with another stream's kernel
+ * (the data-parallel all-reduce) does not hold a fixed share of the tiles. Same results: a unit is computed the same way by
+ * whichever cluster takes it. */
+int weedcu_gemm_set_dynamic(int on);
 /* strided fp32 -> packed bf16 (round-to-nearest-even); dst is a dense [rows, cols] matrix whose
  * contiguous index is chosen by dst_major (0: cols contiguous, 1: rows contiguous). */
 int weedcu_pack_bf16(const float *src, uint64_t offset, uint32_t s0, uint32_t s1, uint32_t rows,

@@ -76,6 +76,7 @@ int weedcu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *) { memmov
 int weedcu_launch_count(uint64_t *count) { if (!count) return WEEDCU_EINVAL; *count = g_launches; return 0; }
 int weedcu_host_stats(double *a, uint64_t *b, double *c, uint64_t *d) { if (a) *a = 0; if (b) *b = g_mallocs; if (c) *c = 0; if (d) *d = g_frees; return 0; }
 int weedcu_prof_enable(int) { return 0; }
+int weedcu_gemm_set_dynamic(int) { return 0; }
 int weedcu_gemm_set_mode(int) { return 0; }
 int weedcu_set_pdl(int) { return 0; }
 int weedcu_prof_read(int, double *t, uint64_t *n, double *w) { if (t) *t = 0; if (n) *n = 0; if (w) *w = 0; return 0; }

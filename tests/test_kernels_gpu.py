@@ -212,6 +212,39 @@ def test_gemm_bf16_cta_pair_matches_model(gpu, M, N, K, am, bm, mode, acc, bias)
     assert cases.rel_err(got, want.astype(np.float32)) <= 1e-4
 
 
+@pytest.mark.parametrize("M,N,K,am,bm,mode,splits_hint", [(8192, 768, 768, 1, 0, 1192001, 1), (4096, 1024, 512, 1, 1, 1256001, 1), (2048, 520, 4096, 0, 0, 1128002, 2),
+                                                          (1100, 1000, 320, 1, 0, 1128001, 1)])
+def test_gemm_bf16_cta_pair_dynamic_tile_scheduler(gpu, M, N, K, am, bm, mode, splits_hint):
+    """weedcu_gemm_set_dynamic(1): the clusters of the CTA-pair kernel draw their work units from a per-launch counter through
+    the shared-memory unit ring instead of striding over them. Bit-identical to the static schedule (a unit is computed the
+    same way by whichever cluster takes it), also over many consecutive launches (counter slots are re-armed by the launch
+    that used them) and with more units than clusters (several rounds through the 8-entry ring)."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K)
+    U32, U64, I32 = C.c_uint32, C.c_uint64, C.c_int
+    a_dev, lda, A = _operand(rng, M, K, am)
+    b_dev, ldb, B = _operand(rng, N, K, bm)
+    pa, pb = gpu.buf(a_dev), gpu.buf(b_dev)
+    out = {}
+    assert gpu.lib.weedcu_gemm_set_mode(C.c_int(mode)) == 0
+    try:
+        for dyn in (0, 1):
+            assert gpu.lib.weedcu_gemm_set_dynamic(C.c_int(dyn)) == 0
+            hc = gpu.buf(np.zeros(M * N, np.float32))
+            for _ in range(300 if dyn else 1):  # more launches than counter slots
+                gpu.call("gemm_bf16", pa, I32(am), U64(lda), pb, I32(bm), U64(ldb), hc, U64(M), U32(M), U32(N), U32(K), I32(0), C.c_void_p(0))
+            gpu.sync()
+            out[dyn] = hc.get()
+    finally:
+        gpu.lib.weedcu_gemm_set_dynamic(C.c_int(0))
+        gpu.lib.weedcu_gemm_set_mode(C.c_int(0))
+    if splits_hint == 1:
+        assert np.array_equal(out[0], out[1])
+    else:  # split-K slices meet by reduce-add: the order of the adds is not fixed in either schedule
+        assert cases.rel_err(out[1], out[0]) <= 1e-6
+    assert cases.rel_err(out[1].reshape(N, M).T, (A @ B.T).astype(np.float32)) <= 1e-4
+
+
 @pytest.mark.parametrize("mode", [256001, 192001, 1256001, 1128001])
 @pytest.mark.parametrize("M,N,K,groups", [(8192, 768, 768, 3), (300, 200, 96, 2), (1024, 130, 256, 3), (256, 64, 64, 1)])
 def test_gemm_bf16_grouped_equals_separate_launches(gpu, M, N, K, groups, mode):

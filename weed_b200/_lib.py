@@ -92,7 +92,7 @@ weedcu_inplace_real weedcu_copy_real weedcu_unary_real weedcu_unary_grad_real we
 weedcu_reduce_grad_real weedcu_sum_real weedcu_clamp_real weedcu_clamp_grad_real weedcu_extremum_real weedcu_match_grad_full_real weedcu_extremum_axis_real weedcu_match_grad_real weedcu_softmax_real weedcu_softmax_grad_real
 weedcu_attn_softmax_real weedcu_attention_fwd weedcu_attention_fwd_bf16out weedcu_attention_fwd_bf16in weedcu_attention_decode weedcu_matmul_skinny weedcu_matmul_skinny_grouped weedcu_matmul_skinny_residual weedcu_cross_entropy_fwd weedcu_cross_entropy_bwd weedcu_cross_entropy_bwd_pack weedcu_cross_entropy_fwd_stats weedcu_cross_entropy_fwd_bf16in weedcu_cross_entropy_bwd_pack_bf16in weedcu_layernorm_fwd weedcu_layernorm_fwd_bf16 weedcu_layernorm_fwd_stats weedcu_gelu_fwd_bf16 weedcu_gelu_grad_pack weedcu_gelu_grad_pack_bf16dy weedcu_multi_copy
 weedcu_layernorm_bwd weedcu_layernorm_bwd_from weedcu_embedding_gather weedcu_embedding_scatter_add weedcu_triu_fill_real
-weedcu_argmax_rows weedcu_sgd_step weedcu_adam_step weedcu_adam_step_multi weedcu_adam_step_multi_shadow weedcu_adam_step_multi_zero weedcu_matmul_real weedcu_gemm_bf16 weedcu_gemm_bf16_grouped weedcu_gemm_bf16_residual weedcu_gemm_bf16_ex weedcu_gemm_bf16_grouped_bf16out weedcu_gemm_set_mode
+weedcu_argmax_rows weedcu_sgd_step weedcu_adam_step weedcu_adam_step_multi weedcu_adam_step_multi_shadow weedcu_adam_step_multi_zero weedcu_matmul_real weedcu_gemm_bf16 weedcu_gemm_bf16_grouped weedcu_gemm_bf16_residual weedcu_gemm_bf16_ex weedcu_gemm_bf16_grouped_bf16out weedcu_gemm_set_mode weedcu_gemm_set_dynamic
 weedcu_pack_bf16 weedcu_pack_bf16_colsum weedcu_gemm_workspace_bytes weedcu_prof_enable weedcu_prof_read weedcu_nccl_load weedcu_nccl_unique_id
 weedcu_nccl_init weedcu_nccl_destroy weedcu_nccl_group_start weedcu_nccl_group_end weedcu_nccl_allreduce_sum
 weedcu_nccl_broadcast

@@ -58,6 +58,10 @@ struct Params {
   __nv_bfloat16 *c16;
   uint64_t ldc16;
   float2 *row_stats; // [tiles_n][M]
+  // dynamic tile scheduling (CTA-pair kernel): {next unit, clusters done} of this launch; NULL = unit u goes to cluster
+  // u % clusters. With it, a cluster that becomes resident late (its SMs lent to a collective's kernel) finds the queue
+  // drained instead of holding a static share of the tiles that everyone else then waits for.
+  uint32_t *sched;
 };
 
 // per-thread running row statistics across the 32-column chunks of one tile
@@ -486,8 +490,9 @@ template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS> struct PairSmemL
   static constexpr uint32_t B_BYTES = HALF_N * BLOCK_K * 2;
   static constexpr uint32_t EPI_OFF = STAGES * (A_BYTES + B_BYTES);
   static constexpr uint32_t BAR_OFF = EPI_OFF + EPI_BUFS * EPI_BUF_BYTES;
-  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 2 * EPI_BUFS; // full/empty, tmem full/empty, staging full/empty
-  static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+  static constexpr uint32_t SCHED_SLOTS = 8; // unit ring: the producer runs < 5 units ahead of the slowest role (stages, 2 accumulators, 1 prefetch)
+  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 2 * EPI_BUFS + SCHED_SLOTS; // full/empty, tmem full/empty, staging full/empty, unit published
+  static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + SCHED_SLOTS * 4;
 };
 
 template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS, int A_MN, int B_MN>
@@ -513,7 +518,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   auto tempty_bar = [&](uint32_t a) { return bars + 8 * (2 * STAGES + 2 + a); };
   auto efull_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + b); };            // staging buffer b holds a finished chunk
   auto eempty_bar = [&](uint32_t b) { return bars + 8 * (2 * STAGES + 4 + EPI_BUFS + b); }; // its TMA store has finished reading it
+  auto sfull_bar = [&](uint32_t s) { return bars + 8 * (2 * STAGES + 4 + 2 * EPI_BUFS + s); };           // unit ring entry s is published
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + L::NUM_BARS * 8);
+  const uint32_t sched_ring = base + L::BAR_OFF + L::NUM_BARS * 8 + 16;
+  volatile uint32_t *sched_gen = reinterpret_cast<volatile uint32_t *>(gen_base + L::BAR_OFF + L::NUM_BARS * 8 + 16);
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank(), cid = cluster_id_x(), ncl = num_clusters_x();
@@ -521,6 +529,28 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t tiles_per_batch = p.tiles_m * p.tiles_n;
   const uint32_t num_tiles = tiles_per_batch * p.batch;
   const uint32_t num_units = num_tiles * p.splits;
+  // Work units: static (unit it of this cluster = cid + it * clusters) or, with p.sched, drawn from a global counter by the
+  // leader's producer lane and handed to every role of both CTAs through a ring in shared memory (entry it & 7, one
+  // mbarrier per entry; the slowest role is < 5 entries behind the producer, so no "entry consumed" barrier is needed).
+  constexpr uint32_t NO_UNIT = 0xffffffffu;
+  const bool dyn = p.sched != nullptr;
+  uint32_t first_unit = 0;
+  if (dyn && rank == 0 && warp == 0 && lane == 0) first_unit = atomicAdd(p.sched, 1u); // this launch's own counter: no dependency on the previous kernel
+  auto unit_at = [&](uint32_t it) -> uint32_t {
+    if (!dyn) {
+      const uint32_t u = cid + it * ncl;
+      return u < num_units ? u : NO_UNIT;
+    }
+    mbar_wait_cluster(sfull_bar(it & 7u), (it >> 3) & 1u);
+    return sched_gen[it & 7u];
+  };
+  auto publish_unit = [&](uint32_t it, uint32_t u) { // leader's producer lane 0
+    const uint32_t val = u < num_units ? u : NO_UNIT, slot = it & 7u;
+    sched_gen[slot] = val;
+    st_shared_cluster_u32(mapa_shared(sched_ring + 4u * slot, 1), val);
+    mbar_arrive_cluster(mapa_shared(sfull_bar(slot), 0));
+    mbar_arrive_cluster(mapa_shared(sfull_bar(slot), 1));
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -539,6 +569,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(efull_bar(b), 4);
       mbar_init(eempty_bar(b), 1);
     }
+    for (uint32_t s = 0; s < L::SCHED_SLOTS; ++s) mbar_init(sfull_bar(s), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(smem_u32((const void *)tmem_slot), TMEM_COLS);
@@ -551,8 +582,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ==========================
-    uint32_t stage = 0, phase = 0;
-    for (uint32_t unit = cid; unit < num_units; unit += ncl) {
+    uint32_t stage = 0, phase = 0, next_unit = 0;
+    const bool scheduler = dyn && rank == 0;
+    if (scheduler && lane == 0) publish_unit(0, first_unit);
+    for (uint32_t it = 0;; ++it) {
+      __syncwarp();
+      const uint32_t unit = unit_at(it);
+      if (unit == NO_UNIT) break;
+      if (scheduler && lane == 0) next_unit = atomicAdd(p.sched, 1u); // in flight behind this tile's first loads
+      bool publish_pending = scheduler;
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
       const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
@@ -583,7 +621,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         __syncwarp();
+        if (publish_pending) { // the next unit reaches the peer while this tile's loads are in flight
+          if (lane == 0) publish_unit(it + 1u, next_unit);
+          publish_pending = false;
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (publish_pending && lane == 0) publish_unit(it + 1u, next_unit); // (a unit without k-blocks)
+    }
+    if (scheduler && lane == 0) { // the last cluster to run out of work re-arms this launch's counter slot
+      if (atomicAdd(p.sched + 1, 1u) == ncl - 1u) {
+        p.sched[0] = 0u;
+        p.sched[1] = 0u;
       }
     }
   } else if (warp == 1) {
@@ -593,8 +642,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint64_t adesc0 = A_MN ? make_smem_desc(sA, BLOCK_K * 128, 1024) : make_smem_desc(sA, 16, 1024);
       const uint64_t bdesc0 = B_MN ? make_smem_desc(sB, BLOCK_K * 128, 1024) : make_smem_desc(sB, 16, 1024);
       constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t unit = unit_at(it);
+        if (unit == NO_UNIT) break;
         const uint32_t ks = unit / num_tiles;
         const uint32_t kb0 = ks * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const uint32_t acc = it % NUM_ACC, acc_phase = (it / NUM_ACC) & 1;
@@ -623,7 +674,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       const uint32_t sEpi = base + L::EPI_OFF;
       uint32_t epi_chunk = 0;
-      for (uint32_t unit = cid; unit < num_units; unit += ncl) {
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t unit = unit_at(it);
+        if (unit == NO_UNIT) break;
         const uint32_t tile = unit % num_tiles;
         const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
         const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
@@ -653,8 +706,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t eg = (warp - EPI_WARP0) >> 2; // column half of the tile this warp drains
     constexpr uint32_t CHUNKS = BLOCK_N / EPI_COLS;
     const uint32_t sEpi = base + L::EPI_OFF;
-    uint32_t it = 0;
-    for (uint32_t unit = cid; unit < num_units; unit += ncl, ++it) {
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t unit = unit_at(it);
+      if (unit == NO_UNIT) break;
       const uint32_t tile = unit % num_tiles, ks = unit / num_tiles;
       const uint32_t z = tile / tiles_per_batch, t = tile % tiles_per_batch;
       const uint32_t tn = t / p.tiles_m, grp = tn / p.tiles_n_group;
@@ -851,6 +905,26 @@ static int launch_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const Tens
   return after_launch();
 }
 
+// Counter slots of the dynamic tile scheduler: {next unit, clusters done} per launch, 256 slots per device used in turn (a
+// slot is re-armed by the last cluster of the launch that used it, long before its turn comes again). WEEDCU_GEMM_DYNAMIC /
+// weedcu_gemm_set_dynamic: 0 = static striding, 1 = dynamic.
+static int g_gemm_dynamic = [] {
+  const char *e = getenv("WEEDCU_GEMM_DYNAMIC");
+  return e ? atoi(e) : 0;
+}();
+static uint32_t *next_sched_slot() {
+  constexpr int kSlots = 256, kMaxDev = 16;
+  static uint32_t *slots[kMaxDev] = {nullptr};
+  static unsigned turn[kMaxDev] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!slots[dev]) {
+    if (cudaMalloc((void **)&slots[dev], sizeof(uint32_t) * 2 * kSlots) != cudaSuccess) return nullptr;
+    if (cudaMemset(slots[dev], 0, sizeof(uint32_t) * 2 * kSlots) != cudaSuccess) return nullptr; // (synchronising: once per device)
+  }
+  return slots[dev] + 2 * (turn[dev]++ % kSlots);
+}
+
 template <uint32_t BLOCK_N, uint32_t STAGES, uint32_t EPI_BUFS>
 static int launch_pair_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const TensorMaps &tmCs, const Params &p, int a_major,
                            int b_major, cudaStream_t st) {
@@ -859,11 +933,13 @@ static int launch_pair_cfg(const CUtensorMap &tmA, const TensorMaps &tmBs, const
   const uint32_t smem = L::TOTAL + 1024;
   const uint32_t num_units = p.tiles_m * p.tiles_n * p.batch * p.splits;
   const unsigned pairs = num_units < gemm_sm_limit() / 2 ? num_units : gemm_sm_limit() / 2;
+  Params pd = p;
+  pd.sched = (g_gemm_dynamic && num_units > pairs) ? next_sched_slot() : nullptr; // (one unit per cluster: nothing to balance)
 #define WCU_TC_LAUNCH(AM, BM_)                                                                     \
   {                                                                                                \
     auto k = gemm_bf16_pair_kernel<BLOCK_N, STAGES, EPI_BUFS, AM, BM_>;                                      \
     ensure_dynamic_smem((const void *)k, (int)smem);                                               \
-    launch_k(k, dim3(2 * pairs), dim3(NUM_THREADS), smem, st, tmA, tmBs, tmCs, p);                                   \
+    launch_k(k, dim3(2 * pairs), dim3(NUM_THREADS), smem, st, tmA, tmBs, tmCs, pd);                                  \
   }
   if constexpr ((BLOCK_N / 2) % 64 == 0) {
     if (a_major && b_major) WCU_TC_LAUNCH(1, 1)
@@ -1016,6 +1092,7 @@ int launch_gemm_bf16_grouped(const uint16_t *a, int a_major, uint64_t lda, uint6
   p.c16 = ext ? (__nv_bfloat16 *)ext->c16[0] : nullptr;
   p.ldc16 = ext ? ext->ldc16 : 0;
   p.row_stats = ext ? (float2 *)ext->row_stats : nullptr;
+  p.sched = nullptr;
   p.c_bs = c_bs;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.tiles_m = tiles_m;
@@ -1274,6 +1351,10 @@ int weedcu_gemm_bf16_grouped_bf16out(const uint16_t *a, int a_major, uint64_t ld
                                       nullptr, 0, &ext);
 }
 
+int weedcu_gemm_set_dynamic(int on) {
+  weedcu::tc::g_gemm_dynamic = on ? 1 : 0;
+  return 0;
+}
 int weedcu_gemm_set_mode(int mode) {
   tc::set_gemm_mode(mode);
   return 0;
